@@ -1,0 +1,264 @@
+"""ctypes bindings of include/grlgpu.h (device parse phase) and include/grlbwt.h (host side).
+
+There is no fallback: if the shared libraries are missing, or no CUDA device is usable, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+LIB_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
+FLAG_SMALL_TABLE, FLAG_FORCE_SLOW_SCAN, FLAG_KEEP_DICT = 1, 2, 4
+CELL = {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}
+
+
+class GrlGpuError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"grlgpu status {status}: {msg}")
+        self.status = status
+
+
+class Stats(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in ("n_syms", "n_strings", "longest_string", "min_sym", "max_sym", "max_sym_freq", "sep_sym")]
+
+
+class Round(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in ("round", "n_in", "n_strings", "parse_len", "n_phrases", "dict_syms", "max_freq", "alphabet",
+                                          "tot_phrases", "n_pre_runs", "algorithmic_bytes")] + \
+               [(k, C.c_uint32) for k in ("cell_bytes_in", "cell_bytes_out", "sym_bytes", "done")] + \
+               [(k, C.c_float) for k in ("device_ms", "text_pass_ms", "dict_ms", "rewrite_ms")]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class BwtResult(C.Structure):
+    _fields_ = [("n_runs", C.c_uint64), ("sb", C.c_uint64), ("fb", C.c_uint64), ("syms", C.POINTER(C.c_uint64)),
+                ("lens", C.POINTER(C.c_uint64)), ("n_rounds", C.c_uint64), ("h2d_ms", C.c_double), ("par_phase_ms", C.c_double),
+                ("ind_phase_ms", C.c_double), ("device_ms", C.c_double), ("algorithmic_bytes", C.c_uint64)]
+
+
+_gpu = None
+_host = None
+
+
+def lib_gpu():
+    global _gpu
+    if _gpu is None:
+        path = os.path.join(LIB_DIR, "libgrlgpu.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: build it with `make -C grlbwt_b200` (or __graft_entry__.build()); there is no fallback path")
+        L = C.CDLL(path)
+        vp, u64 = C.c_void_p, C.c_uint64
+        L.grlgpu_create.argtypes = [C.POINTER(vp), C.c_int, u64]
+        L.grlgpu_destroy.argtypes = [vp]
+        L.grlgpu_set_text.argtypes = [vp, vp, u64, C.c_int]
+        L.grlgpu_set_text_device.argtypes = [vp, vp, u64, C.c_int]
+        L.grlgpu_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.grlgpu_round.argtypes = [vp, C.POINTER(Round)]
+        L.grlgpu_fetch_level.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.grlgpu_fetch_parse.argtypes = [vp, vp]
+        L.grlgpu_fetch_str_ptrs.argtypes = [vp, vp]
+        L.grlgpu_fetch_dictionary.argtypes = [vp, vp, vp, vp, vp]
+        L.grlgpu_strerror.restype = C.c_char_p
+        L.grlgpu_strerror.argtypes = [C.c_int]
+        L.grlgpu_last_error.restype = C.c_char_p
+        L.grlgpu_last_error.argtypes = [vp]
+        L.grlgpu_selftest_scan.argtypes = [vp, u64, vp, vp]
+        L.grlgpu_selftest_sort.argtypes = [vp, vp, u64, C.c_int]
+        L.grlgpu_selftest_compact.argtypes = [vp, vp, u64, vp, vp]
+        _gpu = L
+    return _gpu
+
+
+def lib_host():
+    global _host
+    if _host is None:
+        lib_gpu()
+        path = os.path.join(LIB_DIR, "libgrlbwt.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: build it with `make -C grlbwt_b200`")
+        L = C.CDLL(path)
+        L.grlbwt_build.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(BwtResult)]
+        L.grlbwt_free_result.argtypes = [C.POINTER(BwtResult)]
+        L.grlbwt_build_file.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.grlbwt_last_error.restype = C.c_char_p
+        _host = L
+    return _host
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class GrlGpu:
+    """One device context = the GPU parse strategy (mirrors the duck-typed strategy concept used by
+    par_round, exact_par_phase.cpp:374-497: get_phrases / map / parse_text, fused into round())."""
+
+    def __init__(self, device: int = 0, flags: int = 0):
+        self._L = lib_gpu()
+        self._h = C.c_void_p()
+        self._check(self._L.grlgpu_create(C.byref(self._h), device, flags), ctx=False)
+        self.last = None
+        self._keep = None
+
+    def _check(self, rc, ctx=True):
+        if rc != 0:
+            msg = self._L.grlgpu_strerror(rc).decode()
+            if ctx and self._h:
+                msg += " | " + self._L.grlgpu_last_error(self._h).decode()
+            raise GrlGpuError(rc, msg)
+
+    def set_text(self, text: np.ndarray):
+        text = np.ascontiguousarray(text)
+        if text.dtype not in (np.uint8, np.uint16, np.uint32, np.uint64):
+            raise GrlGpuError(-1, "symbol width must be 1, 2, 4 or 8 bytes")
+        self._keep = text
+        self._check(self._L.grlgpu_set_text(self._h, _ptr(text) if text.size else None, text.size, text.dtype.itemsize))
+
+    def set_text_device(self, dev_ptr: int, n_syms: int, sym_bytes: int):
+        self._check(self._L.grlgpu_set_text_device(self._h, C.c_void_p(dev_ptr), n_syms, sym_bytes))
+
+    def stats(self) -> Stats:
+        s = Stats()
+        self._check(self._L.grlgpu_stats(self._h, C.byref(s)))
+        return s
+
+    def round(self) -> Round:
+        r = Round()
+        self._check(self._L.grlgpu_round(self._h, C.byref(r)))
+        self.last = r
+        return r
+
+    def fetch_level(self):
+        """-> dict(rule_l, rule_r, has_hocc, pre_sym, pre_len) as numpy arrays (u64 / u8)"""
+        r = self.last
+        st = np.uint32 if r.sym_bytes == 4 else np.uint64
+        rl, rr = np.zeros(r.tot_phrases, st), np.zeros(r.tot_phrases, st)
+        hh = np.zeros(r.tot_phrases, np.uint8)
+        ps, pl = np.zeros(r.n_pre_runs, st), np.zeros(r.n_pre_runs, np.uint64)
+        self._check(self._L.grlgpu_fetch_level(self._h, _ptr(rl), _ptr(rr), _ptr(hh), _ptr(ps), _ptr(pl)))
+        return {"rule_l": rl.astype(np.uint64), "rule_r": rr.astype(np.uint64), "has_hocc": hh, "pre_sym": ps.astype(np.uint64), "pre_len": pl}
+
+    def fetch_parse(self) -> np.ndarray:
+        r = self.last
+        out = np.zeros(r.parse_len, CELL[r.cell_bytes_out])
+        self._check(self._L.grlgpu_fetch_parse(self._h, _ptr(out)))
+        return out
+
+    def fetch_str_ptrs(self) -> np.ndarray:
+        out = np.zeros(self.last.n_strings + 1, np.uint64)
+        self._check(self._L.grlgpu_fetch_str_ptrs(self._h, _ptr(out)))
+        return out
+
+    def fetch_dictionary(self):
+        r = self.last
+        syms, lens = np.zeros(r.dict_syms, np.uint64), np.zeros(r.n_phrases, np.uint64)
+        freqs, metas = np.zeros(r.n_phrases, np.uint64), np.zeros(r.n_phrases, np.uint64)
+        self._check(self._L.grlgpu_fetch_dictionary(self._h, _ptr(syms), _ptr(lens), _ptr(freqs), _ptr(metas)))
+        return syms, lens, freqs, metas
+
+    def close(self):
+        if self._h:
+            self._L.grlgpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def build_bwt(text: np.ndarray, device: int = 0, n_threads: int = 1, verbose: bool = False):
+    """Whole construction (device parse phase + host induction) -> (syms u64, lens u64, sb, fb, info dict)."""
+    L = lib_host()
+    text = np.ascontiguousarray(text)
+    res = BwtResult()
+    rc = L.grlbwt_build(_ptr(text), text.size, text.dtype.itemsize, device, n_threads, int(verbose), C.byref(res))
+    if rc != 0:
+        raise GrlGpuError(rc, L.grlbwt_last_error().decode())
+    try:
+        syms = np.ctypeslib.as_array(res.syms, shape=(res.n_runs,)).copy()
+        lens = np.ctypeslib.as_array(res.lens, shape=(res.n_runs,)).copy()
+        info = {k: getattr(res, k) for k in ("n_rounds", "h2d_ms", "par_phase_ms", "ind_phase_ms", "device_ms", "algorithmic_bytes")}
+        return syms, lens, int(res.sb), int(res.fb), info
+    finally:
+        L.grlbwt_free_result(C.byref(res))
+
+
+def build_bwt_file(inp: str, out: str, sym_bytes: int = 1, device: int = 0, n_threads: int = 1, verbose: bool = False):
+    L = lib_host()
+    rc = L.grlbwt_build_file(inp.encode(), out.encode(), sym_bytes, device, n_threads, int(verbose))
+    if rc != 0:
+        raise GrlGpuError(rc, L.grlbwt_last_error().decode())
+
+
+def selftest_induce(levels, final_parse: np.ndarray):
+    """levels: list of dicts with alphabet, tot, rule_l, rule_r (u64), has_hocc (u8), pre_sym, pre_len (u64). CPU only."""
+    L = lib_host()
+    n = len(levels)
+    u64p, u8p = C.POINTER(C.c_uint64), C.POINTER(C.c_uint8)
+    keep = []
+
+    def arr(key, dt, ptype):
+        out = (ptype * n)()
+        for i, lv in enumerate(levels):
+            a = np.ascontiguousarray(lv[key], dt)
+            if a.size == 0:
+                a = np.zeros(1, dt)
+            keep.append(a)
+            out[i] = a.ctypes.data_as(ptype)
+        return out
+
+    alph = np.array([lv["alphabet"] for lv in levels], np.uint64)
+    tot = np.array([lv["tot"] for lv in levels], np.uint64)
+    npre = np.array([len(lv["pre_sym"]) for lv in levels], np.uint64)
+    fp = np.ascontiguousarray(final_parse, np.uint64)
+    res = BwtResult()
+    L.grlbwt_selftest_induce.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(u64p), C.POINTER(u64p), C.POINTER(u8p), C.c_void_p,
+                                         C.POINTER(u64p), C.POINTER(u64p), C.c_void_p, C.c_uint64, C.POINTER(BwtResult)]
+    rc = L.grlbwt_selftest_induce(n, _ptr(alph), _ptr(tot), arr("rule_l", np.uint64, u64p), arr("rule_r", np.uint64, u64p),
+                                  arr("has_hocc", np.uint8, u8p), _ptr(npre), arr("pre_sym", np.uint64, u64p), arr("pre_len", np.uint64, u64p),
+                                  _ptr(fp), fp.size, C.byref(res))
+    if rc != 0:
+        raise RuntimeError(L.grlbwt_last_error().decode())
+    try:
+        return (np.ctypeslib.as_array(res.syms, shape=(res.n_runs,)).copy(), np.ctypeslib.as_array(res.lens, shape=(res.n_runs,)).copy())
+    finally:
+        L.grlbwt_free_result(C.byref(res))
+
+
+def selftest_scan(a: np.ndarray):
+    a = np.ascontiguousarray(a, np.uint32)
+    out, tot = np.zeros(a.size, np.uint64), np.zeros(1, np.uint64)
+    rc = lib_gpu().grlgpu_selftest_scan(_ptr(a), a.size, _ptr(out), _ptr(tot))
+    if rc != 0:
+        raise GrlGpuError(rc, lib_gpu().grlgpu_strerror(rc).decode())
+    return out, int(tot[0])
+
+
+def selftest_sort(keys: np.ndarray, vals: np.ndarray, n_bits: int):
+    k, v = np.ascontiguousarray(keys, np.uint64).copy(), np.ascontiguousarray(vals, np.uint32).copy()
+    rc = lib_gpu().grlgpu_selftest_sort(_ptr(k), _ptr(v), k.size, n_bits)
+    if rc != 0:
+        raise GrlGpuError(rc, lib_gpu().grlgpu_strerror(rc).decode())
+    return k, v
+
+
+def selftest_compact(bits: np.ndarray, prev_bits, n_bits: int):
+    b = np.ascontiguousarray(bits, np.uint32)
+    pb = None if prev_bits is None else np.ascontiguousarray(prev_bits, np.uint32)
+    out, cnt = np.zeros(max(1, n_bits), np.uint64), np.zeros(1, np.uint64)
+    rc = lib_gpu().grlgpu_selftest_compact(_ptr(b), _ptr(pb), n_bits, _ptr(out), _ptr(cnt))
+    if rc != 0:
+        raise GrlGpuError(rc, lib_gpu().grlgpu_strerror(rc).decode())
+    return out[: int(cnt[0])]

@@ -1,0 +1,245 @@
+// Dictionary-side kernels of one parse round: compaction of the phrase table into a contiguous
+// dictionary (exact_par_phase.hpp:106-183), ordering of ALL dictionary suffixes under the
+// "proper prefix is greater" order with equal-suffix grouping (what suffix_induction,
+// exact_LMS_induction.h:94-158, produces), ranks among unsolved blocks + preliminary BWT
+// (produce_pre_bwt, exact_par_phase.cpp:136-242), grammar rules (produce_grammar, :14-95) and
+// metasymbol assignment (:427-450).
+//
+// Dictionary layout in HBM (structure of arrays over the nE = sum of phrase lengths entries):
+//   D[e]       symbol value          phr_of[e]  index of the phrase the entry belongs to
+//   rem[e]     symbols after e inside its phrase (0 for the last symbol)
+// The suffix order is computed by prefix doubling on packed keys: a first key packs the first K
+// symbols (code 0 = past the terminator, 1..A = symbol+1, A+1 = terminator, so a proper prefix
+// compares greater), then (rank[e], rank[e+h]) pairs are re-sorted until the grouping is stable.
+#pragma once
+#include "util.cuh"
+#include "parse_kernels.cuh"
+
+namespace grl {
+
+struct IsSuffix {  // phrase_desc bit-vector of the round (exact_par_phase.cpp:311-312, :443)
+    const u8* arr;
+    u64 sep;
+    bool first;
+    __device__ __forceinline__ bool operator()(u64 sym) const { return first ? sym == sep : arr[sym] != 0; }
+};
+
+// per distinct phrase: first-occurrence position, true length, frequency
+template <class PosT>
+__global__ void __launch_bounds__(256) dict_meta_kernel(const ulonglong2* __restrict__ table, const u32* __restrict__ occ_slots, u64 d,
+                                                        const PosT* __restrict__ ps, u64 p, u64* __restrict__ ph_pos, u32* __restrict__ ph_len,
+                                                        u64* __restrict__ ph_freq) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d) return;
+    const ulonglong2 ent = table[occ_slots[i]];
+    const u64 pos = ent.x >> 24;
+    u64 len = ent.x & HT_LEN_SAT;
+    if (len == HT_LEN_SAT) len = phrase_len_at<PosT>(ps, p, pos);
+    ph_pos[i] = pos;
+    ph_len[i] = (u32)len;
+    ph_freq[i] = ent.y;
+}
+
+template <class CellT, bool FIRST, class SymT>
+__global__ void __launch_bounds__(256) dict_gather_kernel(const CellT* __restrict__ text, const u64* __restrict__ ph_pos, const u32* __restrict__ ph_len,
+                                                          const u32* __restrict__ ph_off, u64 d, SymT* __restrict__ D, u32* __restrict__ phr_of,
+                                                          u32* __restrict__ rem) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d) return;
+    const u64 pos = ph_pos[i];
+    const u32 len = ph_len[i], off = ph_off[i];
+    for (u32 k = 0; k < len; k++) {
+        D[off + k] = (SymT)cell_value<CellT, FIRST>(text[pos + k]);
+        phr_of[off + k] = (u32)i;
+        rem[off + k] = len - 1 - k;
+    }
+}
+
+// first sort key: K symbol codes of `bits` bits each, most significant first
+template <class SymT>
+__global__ void __launch_bounds__(256) sfx_first_key_kernel(const SymT* __restrict__ D, const u32* __restrict__ rem, u64 nE, u64 term_code, int bits, int K,
+                                                            u64* __restrict__ keys, u32* __restrict__ vals) {
+    const u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nE) return;
+    const u32 r = rem[e];
+    u64 key = 0;
+    for (int t = 0; t < K; t++) {
+        u64 code = 0;
+        if ((u32)t <= r) code = (u64)D[e + t] + 1;
+        else if ((u32)t == r + 1) code = term_code;
+        key = (bits == 64) ? code : ((key << bits) | code);
+    }
+    keys[e] = key;
+    vals[e] = (u32)e;
+}
+
+// after a sort: 1 where the key differs from its predecessor
+static __global__ void __launch_bounds__(256) key_head_flags_kernel(const u64* __restrict__ keys, u64 n, u32* __restrict__ flags) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+
+// rank[order[i]] = 1-based dense rank of the key at sorted index i
+static __global__ void __launch_bounds__(256) scatter_rank_kernel(const u32* __restrict__ flags, const u32* __restrict__ excl, const u32* __restrict__ order, u64 n,
+                                                                  u32* __restrict__ rank) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    rank[order[i]] = excl[i] + flags[i];
+}
+
+// doubling key: (rank[e] << bits) | rank of the suffix h symbols further (0 past the terminator, term at it)
+static __global__ void __launch_bounds__(256) sfx_double_key_kernel(const u32* __restrict__ rank, const u32* __restrict__ rem, const u32* __restrict__ order, u64 nE,
+                                                                    u32 h, u32 term_rank, int bits, u64* __restrict__ keys) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nE) return;
+    const u32 e = order[i];
+    const u32 r = rem[e];
+    u64 second = 0;
+    if (h <= r) second = rank[e + h];
+    else if (h == r + 1) second = term_rank;
+    keys[i] = ((u64)rank[e] << bits) | second;
+}
+
+// ---- segmented warp reductions over runs of equal keys that are contiguous across lanes ----
+template <class T, class Op>
+__device__ __forceinline__ T seg_reduce(T v, u32 seg_last, Op op) {
+    const u32 l = lane_id();
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        T x = __shfl_down_sync(0xffffffffu, v, o);
+        if (l + o <= seg_last) v = op(v, x);
+    }
+    return v;
+}
+struct OpSum { template <class T> __device__ __forceinline__ T operator()(T a, T b) const { return a + b; } };
+struct OpMin { template <class T> __device__ __forceinline__ T operator()(T a, T b) const { return a < b ? a : b; } };
+struct OpMax { template <class T> __device__ __forceinline__ T operator()(T a, T b) const { return a > b ? a : b; } };
+
+// G1: per-group aggregates over the sorted entries (produce_pre_bwt exact_par_phase.cpp:159-187).
+// gcnt = entries | full<<31 ; gmin/gmax over (left symbol + 1) of the non-full entries (0 = none).
+template <class SymT>
+__global__ void __launch_bounds__(256) group_reduce_kernel(const u32* __restrict__ order, const u32* __restrict__ rank, const SymT* __restrict__ D,
+                                                           const u32* __restrict__ rem, const u32* __restrict__ phr_of, const u32* __restrict__ ph_off,
+                                                           const u64* __restrict__ ph_freq, u64 nE, IsSuffix is_suffix, u32* gcnt, u64* gacc, u64* gmin,
+                                                           u64* gmax, u32* __restrict__ grep) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 g = 0xffffffffu, cnt = 0;
+    u64 acc = 0, mn = ~0ULL, mx = 0;
+    if (i < nE) {
+        const u32 e = order[i];
+        g = rank[e] - 1;
+        const bool valid = rem[e] > 0 || is_suffix((u64)D[e]);  // exact_par_phase.cpp:163
+        if (valid) {
+            const u32 ph = phr_of[e];
+            const bool full = e == ph_off[ph];
+            cnt = 1u | (full ? 0x80000000u : 0u);
+            acc = ph_freq[ph];
+            if (!full) { mn = mx = (u64)D[e - 1] + 1; }
+        }
+        if (i == 0 || rank[order[i - 1]] != rank[e]) grep[g] = e;
+    }
+    const u32 m = __match_any_sync(0xffffffffu, g);
+    const u32 first = __ffs(m) - 1, last = 31 - __clz(m);
+    cnt = seg_reduce(cnt, last, OpSum());
+    acc = seg_reduce(acc, last, OpSum());
+    mn = seg_reduce(mn, last, OpMin());
+    mx = seg_reduce(mx, last, OpMax());
+    if (lane_id() == first && g != 0xffffffffu && (cnt & 0x7fffffffu)) {
+        atomicAdd(&gcnt[g], cnt);
+        atomicAdd(&gacc[g], acc);
+        if (mx) { atomicMin(&gmin[g], mn); atomicMax(&gmax[g], mx); }
+    }
+}
+
+// G2: ranked / valid flags and the preliminary-BWT symbol of each group (exact_par_phase.cpp:187-216)
+static __global__ void __launch_bounds__(256) group_finalize_kernel(const u32* __restrict__ gcnt, const u64* __restrict__ gmin, const u64* __restrict__ gmax, u64 G,
+                                                                    u64 bwt_dummy, u64 hocc_dummy, u32* __restrict__ rflag, u32* __restrict__ vflag,
+                                                                    u64* __restrict__ psym) {
+    const u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    const u32 c = gcnt[g], cnt = c & 0x7fffffffu;
+    const bool full = c >> 31, valid = cnt > 0;
+    const bool ranked = valid && (full || gmin[g] != gmax[g]);
+    rflag[g] = ranked;
+    vflag[g] = valid;
+    psym[g] = ranked ? (cnt > 1 ? hocc_dummy : bwt_dummy) : (valid ? gmin[g] - 1 : 0);
+}
+
+static __global__ void __launch_bounds__(256) prebwt_compact_kernel(const u32* __restrict__ vflag, const u32* __restrict__ vidx, const u64* __restrict__ psym,
+                                                                    const u64* __restrict__ gacc, u64 G, u64* __restrict__ csym, u64* __restrict__ clen) {
+    const u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G || !vflag[g]) return;
+    csym[vidx[g]] = psym[g];
+    clen[vidx[g]] = gacc[g];
+}
+
+// maximal runs of the compacted (symbol, length) sequence: run id = inclusive count of heads - 1
+template <class SymT>
+__global__ void __launch_bounds__(256) prebwt_runs_kernel(const u64* __restrict__ csym, const u64* __restrict__ clen, const u32* __restrict__ hflag,
+                                                          const u32* __restrict__ hexcl, u64 nV, SymT* __restrict__ run_sym, u64* run_len) {
+    const u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 rid = 0xffffffffu;
+    u64 len = 0;
+    if (v < nV) {
+        rid = hexcl[v] + hflag[v] - 1;
+        len = clen[v];
+        if (hflag[v]) run_sym[rid] = (SymT)csym[v];
+    }
+    const u32 m = __match_any_sync(0xffffffffu, rid);
+    const u32 first = __ffs(m) - 1, last = 31 - __clz(m);
+    len = seg_reduce(len, last, OpSum());
+    if (lane_id() == first && rid != 0xffffffffu) atomicAdd(&run_len[rid], len);
+}
+
+// G4: per entry: metasymbol of full phrases (exact_par_phase.cpp:174-176, :437-444), is_suffix of the
+// next round (:443), rank marks of entries in hocc groups (phr_marks + new_phrases_ht, :190-207)
+template <class SymT>
+__global__ void __launch_bounds__(256) entry_finalize_kernel(const u32* __restrict__ rank, const SymT* __restrict__ D, const u32* __restrict__ rem,
+                                                             const u32* __restrict__ phr_of, const u32* __restrict__ ph_off, const u64* __restrict__ ph_freq,
+                                                             const u32* __restrict__ occ_slots, u64 nE, IsSuffix is_suffix, const u32* __restrict__ gcnt,
+                                                             const u32* __restrict__ rflag, const u32* __restrict__ rrank, ulonglong2* table,
+                                                             u8* __restrict__ is_suffix_next, u32* __restrict__ erank) {
+    const u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nE) return;
+    const u32 g = rank[e] - 1;
+    if (!rflag[g]) return;  // invalid and unranked groups carry no rank
+    const u32 r = rrank[g];
+    const u32 ph = phr_of[e];
+    if (e == ph_off[ph]) {
+        table[occ_slots[ph]].y = ((u64)r << 1) | (ph_freq[ph] > 1 ? 1ULL : 0ULL);
+        is_suffix_next[r] = is_suffix((u64)D[e + rem[e]]) ? 1 : 0;
+    }
+    if ((gcnt[g] & 0x7fffffffu) > 1) erank[e] = r;
+}
+
+// G5: grammar rule of every ranked group from its representative entry (produce_grammar exact_par_phase.cpp:33-87)
+template <class SymT>
+__global__ void __launch_bounds__(256) rules_kernel(const u32* __restrict__ gcnt, const u32* __restrict__ rflag, const u32* __restrict__ rrank,
+                                                    const u32* __restrict__ grep, u64 G, const SymT* __restrict__ D, const u32* __restrict__ rem,
+                                                    const u32* __restrict__ erank, IsSuffix is_suffix, u64 alph3, u64 metasym_dummy,
+                                                    SymT* __restrict__ rule_l, SymT* __restrict__ rule_r, u8* __restrict__ has_hocc) {
+    const u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G || !rflag[g]) return;
+    const u32 u = rrank[g];
+    has_hocc[u] = (gcnt[g] & 0x7fffffffu) > 1;
+    u32 pos = grep[g];
+    if (rem[pos] == 0) {  // :38-41 one-symbol suffix
+        rule_l[u] = (SymT)metasym_dummy;
+        rule_r[u] = D[pos];
+        return;
+    }
+    pos++;
+    while (erank[pos] == 0xffffffffu && rem[pos] != 0) pos++;  // :43-44
+    const SymT l_sym = D[pos - 1];
+    if (erank[pos] != 0xffffffffu) {  // :49-80
+        rule_l[u] = l_sym;
+        rule_r[u] = (SymT)(alph3 + erank[pos]);
+    } else {  // :81-85
+        const SymT r_sym = D[pos];
+        rule_l[u] = (SymT)metasym_dummy;
+        rule_r[u] = is_suffix((u64)r_sym) ? r_sym : l_sym;
+    }
+}
+
+}  // namespace grl

@@ -1,0 +1,763 @@
+// C ABI (include/grlgpu.h) and host-side sequencing of one parse round on one B200.
+// Replaces the strategy + par_round pair of the reference (lib/exact_algo/exact_par_phase.cpp:265-497).
+#include "../../include/grlgpu.h"
+#include "util.cuh"
+#include "primitives.cuh"
+#include "parse_kernels.cuh"
+#include "dict_kernels.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+using namespace grl;
+
+
+struct grlgpu_ctx {
+    int device = 0;
+    u64 flags = 0;
+    cudaStream_t st = nullptr;
+    std::string last_error;
+
+    // current text
+    const void* text = nullptr;  // device
+    DevBuf<u8> text_own;         // owns `text` unless borrowed
+    u64 n = 0;
+    int w = 0;
+    bool first = true;
+    DevBuf<u32> end_bits;   // string-end bitmap of the current text (rounds >= 2)
+    DevBuf<u8> is_suffix;   // per symbol of the current alphabet (rounds >= 2)
+    u64 alphabet = 0;       // A
+    u64 n_strings = 0;
+    u64 sep = 0;
+    int round = 0;
+    bool done = false;
+    bool have_stats = false;
+    grlgpu_stats_t stats{};
+
+    // artefacts of the last round (device)
+    int lvl_sym_bytes = 4;
+    u64 lvl_tot = 0, lvl_npre = 0;
+    DevBuf<u8> rule_l, rule_r, has_hocc, pre_sym;
+    DevBuf<u64> pre_len;
+
+    // optional: dictionary of the last round kept for tests (GRLGPU_FLAG_KEEP_DICT)
+    u64 kd_d = 0, kd_nE = 0;
+    DevBuf<u8> kd_D;
+    DevBuf<u32> kd_off, kd_len, kd_order, kd_phr_of;
+    DevBuf<u64> kd_freq, kd_meta;
+};
+
+namespace {
+
+struct Timer {
+    cudaEvent_t a{}, b{};
+    cudaStream_t st;
+    explicit Timer(cudaStream_t s) : st(s) {
+        GRL_CUDA(cudaEventCreate(&a));
+        GRL_CUDA(cudaEventCreate(&b));
+    }
+    ~Timer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+    void start() { GRL_CUDA(cudaEventRecord(a, st)); }
+    void stop() { GRL_CUDA(cudaEventRecord(b, st)); }
+    float ms() {
+        GRL_CUDA(cudaEventSynchronize(b));
+        float t = 0;
+        GRL_CUDA(cudaEventElapsedTime(&t, a, b));
+        return t;
+    }
+};
+
+template <class T>
+T d2h_scalar(const T* dptr, cudaStream_t st) {
+    T h;
+    GRL_CUDA(cudaMemcpyAsync(&h, dptr, sizeof(T), cudaMemcpyDeviceToHost, st));
+    GRL_CUDA(cudaStreamSynchronize(st));
+    return h;
+}
+
+inline unsigned grid_for(u64 n, int threads) { return (unsigned)std::max<u64>(1, div_up(n, (u64)threads)); }
+
+static __global__ void table_init_kernel(ulonglong2* table, u64 cap) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cap) table[i] = make_ulonglong2(HT_EMPTY, 0ULL);
+}
+template <class PosT>
+__global__ void set_sentinel_kernel(PosT* ps, u64 p, u64 n) {
+    ps[p] = (PosT)n | PosFlag<PosT>::FLAG;
+}
+template <class PosT>
+__global__ void strip_flag_kernel(const PosT* __restrict__ in, u64 cnt, u64* __restrict__ out) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cnt) out[i] = (u64)(in[i] & ~PosFlag<PosT>::FLAG);
+}
+static __global__ void next_start_bits_kernel(const u32* __restrict__ end_bits, u64 n, u32* __restrict__ start_bits) {
+    // start_bits[q] = (q == 0) || end_bits[q-1]   (string starts of the current text)
+    const u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 n_words = (n + 31) / 32;
+    if (w >= n_words) return;
+    u32 cur = end_bits[w];
+    u32 prev = w ? end_bits[w - 1] : 0x80000000u;
+    u32 s = (cur << 1) | (prev >> 31);
+    if (w == n_words - 1 && (n & 31)) s &= (1u << (n & 31)) - 1u;
+    start_bits[w] = s;
+}
+template <class CellT>
+__global__ void first_round_end_bits_kernel(const CellT* __restrict__ text, u64 n, CellT sep, u32* __restrict__ end_bits) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool e = i < n && text[i] == sep;
+    const u32 b = __ballot_sync(0xffffffffu, e);
+    if (lane_id() == 0 && (i >> 5) < ((n + 31) >> 5)) end_bits[i >> 5] = b;
+}
+static __global__ void adjacent_max_diff_kernel(const u64* __restrict__ ptrs, u64 n_str, u64* out) {
+    u64 m = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_str; i += (u64)gridDim.x * blockDim.x) {
+        const u64 dlt = ptrs[i + 1] - ptrs[i];
+        m = dlt > m ? dlt : m;
+    }
+    m = warp_max(m);
+    if (lane_id() == 0 && m) atomicMax(out, m);
+}
+static __global__ void u32_to_u64_kernel(const u32* __restrict__ in, u64 n, u64* __restrict__ out) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+
+// state shared by the stages of one round
+struct Round {
+    grlgpu_ctx* c;
+    cudaStream_t st;
+    u64 n, p = 0, d = 0, nE = 0, cap = 0, G = 0, tot = 0, n_pre = 0, max_freq = 0, max_len = 0;
+    DevBuf<u32> start_bits, end_bits_first;
+    const u32* end_bits = nullptr;  // of the input text
+    DevBuf<u8> ps_raw;              // PosT[p+1]
+    DevBuf<ulonglong2> table;
+    DevBuf<u32> slot_of_phrase, occ_slots;
+    DevBuf<u64> ph_pos, ph_freq;
+    DevBuf<u32> ph_len, ph_off;
+    DevBuf<u8> D_raw;
+    DevBuf<u32> phr_of, rem, rank, order;
+    explicit Round(grlgpu_ctx* ctx) : c(ctx), st(ctx->st), n(ctx->n) {}
+};
+
+// ---------------- text stage: boundary flags -> phrase starts -> dedup table -> distinct list ----------------
+template <class CellT, bool FIRST>
+void stage_flags(Round& R) {
+    grlgpu_ctx* c = R.c;
+    const CellT* text = (const CellT*)c->text;
+    const u64 n_words = div_up(R.n, 32);
+    const u64 n_blocks = div_up(n_words, LMS_THREADS);
+    R.start_bits.alloc(n_words, R.st);
+    u32* end_out = nullptr;
+    if (FIRST) {
+        R.end_bits_first.alloc(n_words, R.st);
+        end_out = R.end_bits_first.p;
+        R.end_bits = R.end_bits_first.p;
+    } else R.end_bits = c->end_bits.p;
+    const u32* end_in = FIRST ? nullptr : c->end_bits.p;
+    DevBuf<u32> need_slow(1, R.st);
+    need_slow.zero();
+    const CellT sep = (CellT)c->sep;
+    bool slow = (c->flags & GRLGPU_FLAG_FORCE_SLOW_SCAN) != 0;
+    if (!slow) {
+        lms_flags_kernel<CellT, FIRST, 0><<<(unsigned)n_blocks, LMS_THREADS, 0, R.st>>>(text, R.n, sep, end_in, end_out, R.start_bits.p, nullptr, nullptr,
+                                                                                        need_slow.p);
+        GRL_KERNEL_CHECK();
+        slow = d2h_scalar(need_slow.p, R.st) != 0;
+    }
+    if (slow) {  // a run of equal cells crosses a CTA boundary by more than the look-ahead
+        DevBuf<u8> state(n_blocks, R.st), incoming(n_blocks, R.st);
+        lms_flags_kernel<CellT, FIRST, 1><<<(unsigned)n_blocks, LMS_THREADS, 0, R.st>>>(text, R.n, sep, end_in, end_out, R.start_bits.p, state.p, nullptr,
+                                                                                        need_slow.p);
+        GRL_KERNEL_CHECK();
+        lms_resolve_kernel<<<1, 32, 0, R.st>>>(state.p, incoming.p, n_blocks);
+        GRL_KERNEL_CHECK();
+        lms_flags_kernel<CellT, FIRST, 2><<<(unsigned)n_blocks, LMS_THREADS, 0, R.st>>>(text, R.n, sep, end_in, end_out, R.start_bits.p, nullptr, incoming.p,
+                                                                                        need_slow.p);
+        GRL_KERNEL_CHECK();
+        GRL_CUDA(cudaStreamSynchronize(R.st));
+    }
+}
+
+template <class CellT, class PosT>
+void stage_dedup(Round& R) {
+    grlgpu_ctx* c = R.c;
+    const CellT* text = (const CellT*)c->text;
+    BitmapCompactor bc;
+    R.p = bc.count(R.start_bits.p, R.n, R.st);
+    R.ps_raw.alloc((R.p + 1) * sizeof(PosT), R.st);
+    PosT* ps = (PosT*)R.ps_raw.p;
+    bc.write<PosT>(R.end_bits, ps);
+    set_sentinel_kernel<PosT><<<1, 1, 0, R.st>>>(ps, R.p, R.n);
+    GRL_KERNEL_CHECK();
+    R.start_bits.release();
+
+    R.slot_of_phrase.alloc(R.p, R.st);
+    DevBuf<u32> overflow(1, R.st);
+    // capacity: power of two >= 2p when that is affordable, else grow on demand
+    u64 cap = 1024;
+    const u64 want = 2 * R.p;
+    const u64 start_cap = (c->flags & GRLGPU_FLAG_SMALL_TABLE) ? 1024 : (1ull << 28);
+    while (cap < want && cap < start_cap) cap <<= 1;
+    for (;;) {
+        if (cap > (1ull << 31)) throw Error(GRLGPU_ERR_LIMIT, "phrase table would exceed 2^31 slots");
+        R.table.alloc(cap, R.st);
+        table_init_kernel<<<grid_for(cap, 256), 256, 0, R.st>>>(R.table.p, cap);
+        GRL_KERNEL_CHECK();
+        overflow.zero();
+        phrase_insert_kernel<CellT, PosT><<<grid_for(R.p, 256), 256, 0, R.st>>>(text, ps, R.p, R.table.p, cap - 1, R.slot_of_phrase.p, overflow.p);
+        GRL_KERNEL_CHECK();
+        bool ovf = d2h_scalar(overflow.p, R.st) != 0;
+        u64 d = 0;
+        if (!ovf) {
+            DevBuf<u32> occ_bits(cap / 32, R.st);
+            table_occupancy_kernel<<<(unsigned)(cap / 256), 256, 0, R.st>>>(R.table.p, cap, occ_bits.p);
+            GRL_KERNEL_CHECK();
+            BitmapCompactor oc;
+            d = oc.count(occ_bits.p, cap, R.st);
+            if (d * 10 <= cap * 7 || cap >= want) {  // load factor <= 0.7 (or the table can no longer be too small)
+                R.occ_slots.alloc(d, R.st);
+                oc.write<u32>(nullptr, R.occ_slots.p);
+                R.d = d;
+                R.cap = cap;
+                break;
+            }
+        }
+        cap <<= 2;  // too full: regrow and redo the pass
+    }
+    R.ph_pos.alloc(R.d, R.st);
+    R.ph_len.alloc(R.d, R.st);
+    R.ph_freq.alloc(R.d, R.st);
+    dict_meta_kernel<PosT><<<grid_for(R.d, 256), 256, 0, R.st>>>(R.table.p, R.occ_slots.p, R.d, ps, R.p, R.ph_pos.p, R.ph_len.p, R.ph_freq.p);
+    GRL_KERNEL_CHECK();
+    R.ph_off.alloc(R.d + 1, R.st);
+    DevBuf<u64> tot64(1, R.st);
+    {   // offsets as u64 first to detect overflow of the 32-bit entry index space
+        DevBuf<u64> off64(R.d, R.st);
+        exclusive_scan<u32, u64>(R.ph_len.p, off64.p, R.d, tot64.p, R.st);
+        R.nE = d2h_scalar(tot64.p, R.st);
+        if (R.nE >= 0xfffffff0ull) throw Error(GRLGPU_ERR_LIMIT, "dictionary of this round exceeds 2^32 symbols");
+    }
+    exclusive_scan<u32, u32>(R.ph_len.p, R.ph_off.p, R.d, R.ph_off.p + R.d, R.st);
+    DevBuf<u64> mx(2, R.st);
+    mx.zero();
+    reduce_max_u64_kernel<<<296, 256, 0, R.st>>>(R.ph_freq.p, R.d, mx.p);
+    GRL_KERNEL_CHECK();
+    {
+        DevBuf<u64> len64(R.d, R.st);
+        u32_to_u64_kernel<<<grid_for(R.d, 256), 256, 0, R.st>>>(R.ph_len.p, R.d, len64.p);
+        reduce_max_u64_kernel<<<296, 256, 0, R.st>>>(len64.p, R.d, mx.p + 1);
+        GRL_KERNEL_CHECK();
+    }
+    u64 hmx[2];
+    GRL_CUDA(cudaMemcpyAsync(hmx, mx.p, 16, cudaMemcpyDeviceToHost, R.st));
+    GRL_CUDA(cudaStreamSynchronize(R.st));
+    R.max_freq = hmx[0];
+    R.max_len = hmx[1];
+    R.ps_raw.release();
+}
+
+template <class CellT, bool FIRST, class SymT>
+void stage_gather(Round& R) {
+    R.D_raw.alloc((R.nE + 1) * sizeof(SymT), R.st);
+    R.phr_of.alloc(R.nE, R.st);
+    R.rem.alloc(R.nE, R.st);
+    dict_gather_kernel<CellT, FIRST, SymT><<<grid_for(R.d, 256), 256, 0, R.st>>>((const CellT*)R.c->text, R.ph_pos.p, R.ph_len.p, R.ph_off.p, R.d,
+                                                                                (SymT*)R.D_raw.p, R.phr_of.p, R.rem.p);
+    GRL_KERNEL_CHECK();
+}
+
+// ---------------- dictionary stage: suffix order, groups, ranks, pre-BWT, rules, metasymbols ----------------
+template <class SymT>
+void stage_dict(Round& R) {
+    grlgpu_ctx* c = R.c;
+    cudaStream_t st = R.st;
+    const u64 nE = R.nE, A = c->alphabet;
+    const SymT* D = (const SymT*)R.D_raw.p;
+    IsSuffix isuf{c->is_suffix.p, c->sep, c->first};
+
+    // -- suffix order by prefix doubling --
+    DevBuf<u64> keys(nE, st), keys_alt(nE, st);
+    DevBuf<u32> vals(nE, st), vals_alt(nE, st), flags(nE, st), excl(nE, st), gcount(1, st);
+    R.rank.alloc(nE, st);
+    u64 *kp = keys.p, *ka = keys_alt.p;
+    u32 *vp = vals.p, *va = vals_alt.p;
+    const int sym_bits = bit_width64(A + 1);
+    const int K = std::max(1, 64 / sym_bits);
+    sfx_first_key_kernel<SymT><<<grid_for(nE, 256), 256, 0, st>>>(D, R.rem.p, nE, A + 1, sym_bits, K, kp, vp);
+    GRL_KERNEL_CHECK();
+    radix_sort_pairs(&kp, &vp, &ka, &va, nE, std::min(64, sym_bits * K), st);
+    u64 G = 0;
+    u64 h = (u64)K;
+    for (;;) {
+        key_head_flags_kernel<<<grid_for(nE, 256), 256, 0, st>>>(kp, nE, flags.p);
+        GRL_KERNEL_CHECK();
+        exclusive_scan<u32, u32>(flags.p, excl.p, nE, gcount.p, st);
+        scatter_rank_kernel<<<grid_for(nE, 256), 256, 0, st>>>(flags.p, excl.p, vp, nE, R.rank.p);
+        GRL_KERNEL_CHECK();
+        const u64 Gn = d2h_scalar(gcount.p, st);
+        const bool stable = (Gn == G);
+        G = Gn;
+        // a key of h codes covers any suffix (<= max_len symbols + terminator) once h > max_len
+        if (stable || G == nE || h > R.max_len) break;
+        const int rb = bit_width64(G + 1);
+        sfx_double_key_kernel<<<grid_for(nE, 256), 256, 0, st>>>(R.rank.p, R.rem.p, vp, nE, (u32)std::min<u64>(h, 0xffffffffull), (u32)(G + 1), rb, kp);
+        GRL_KERNEL_CHECK();
+        radix_sort_pairs(&kp, &vp, &ka, &va, nE, 2 * rb, st);
+        h *= 2;
+    }
+    R.G = G;
+    const u32* order = vp;
+
+    // -- group aggregates --
+    DevBuf<u32> gcnt(G, st), grep(G, st), rflag(G, st), vflag(G, st), rrank(G, st), vidx(G, st);
+    DevBuf<u64> gacc(G, st), gmin(G, st), gmax(G, st), psym(G, st);
+    gcnt.zero(); gacc.zero(); gmax.zero(); gmin.fill_ff();
+    group_reduce_kernel<SymT><<<grid_for(nE, 256), 256, 0, st>>>(order, R.rank.p, D, R.rem.p, R.phr_of.p, R.ph_off.p, R.ph_freq.p, nE, isuf, gcnt.p, gacc.p,
+                                                                 gmin.p, gmax.p, grep.p);
+    GRL_KERNEL_CHECK();
+    const u64 bwt_dummy = A + 1, hocc_dummy = A + 2;  // exact_par_phase.hpp:113-115
+    group_finalize_kernel<<<grid_for(G, 256), 256, 0, st>>>(gcnt.p, gmin.p, gmax.p, G, bwt_dummy, hocc_dummy, rflag.p, vflag.p, psym.p);
+    GRL_KERNEL_CHECK();
+    DevBuf<u32> cnt2(2, st);
+    exclusive_scan<u32, u32>(rflag.p, rrank.p, G, cnt2.p, st);
+    exclusive_scan<u32, u32>(vflag.p, vidx.p, G, cnt2.p + 1, st);
+    u32 hc[2];
+    GRL_CUDA(cudaMemcpyAsync(hc, cnt2.p, 8, cudaMemcpyDeviceToHost, st));
+    GRL_CUDA(cudaStreamSynchronize(st));
+    const u64 tot = hc[0], nV = hc[1];
+    R.tot = tot;
+
+    // -- preliminary BWT: maximal runs over the valid groups --
+    c->lvl_sym_bytes = sizeof(SymT);
+    {
+        DevBuf<u64> csym(nV, st), clen(nV, st);
+        prebwt_compact_kernel<<<grid_for(G, 256), 256, 0, st>>>(vflag.p, vidx.p, psym.p, gacc.p, G, csym.p, clen.p);
+        GRL_KERNEL_CHECK();
+        DevBuf<u32> hflag(nV, st), hexcl(nV, st), nrun(1, st);
+        key_head_flags_kernel<<<grid_for(nV, 256), 256, 0, st>>>(csym.p, nV, hflag.p);
+        GRL_KERNEL_CHECK();
+        exclusive_scan<u32, u32>(hflag.p, hexcl.p, nV, nrun.p, st);
+        R.n_pre = d2h_scalar(nrun.p, st);
+        c->pre_sym.alloc(R.n_pre * sizeof(SymT), st);
+        c->pre_len.alloc(R.n_pre, st);
+        c->pre_len.zero();
+        prebwt_runs_kernel<SymT><<<grid_for(nV, 256), 256, 0, st>>>(csym.p, clen.p, hflag.p, hexcl.p, nV, (SymT*)c->pre_sym.p, c->pre_len.p);
+        GRL_KERNEL_CHECK();
+    }
+
+    // -- metasymbols, next is_suffix, hocc marks, rules --
+    DevBuf<u8> is_suffix_next(tot, st);
+    is_suffix_next.zero();
+    DevBuf<u32> erank(nE, st);
+    erank.fill_ff();
+    entry_finalize_kernel<SymT><<<grid_for(nE, 256), 256, 0, st>>>(R.rank.p, D, R.rem.p, R.phr_of.p, R.ph_off.p, R.ph_freq.p, R.occ_slots.p, nE, isuf, gcnt.p,
+                                                                   rflag.p, rrank.p, R.table.p, is_suffix_next.p, erank.p);
+    GRL_KERNEL_CHECK();
+    c->rule_l.alloc(tot * sizeof(SymT), st);
+    c->rule_r.alloc(tot * sizeof(SymT), st);
+    c->has_hocc.alloc(tot, st);
+    const u64 alph3 = A + 3, metasym_dummy = alph3 + tot + 1;  // exact_par_phase.cpp:19-20
+    rules_kernel<SymT><<<grid_for(G, 256), 256, 0, st>>>(gcnt.p, rflag.p, rrank.p, grep.p, G, D, R.rem.p, erank.p, isuf, alph3, metasym_dummy,
+                                                         (SymT*)c->rule_l.p, (SymT*)c->rule_r.p, c->has_hocc.p);
+    GRL_KERNEL_CHECK();
+    c->lvl_tot = tot;
+    c->lvl_npre = R.n_pre;
+
+    if (c->flags & GRLGPU_FLAG_KEEP_DICT) {
+        c->kd_d = R.d; c->kd_nE = nE;
+        c->kd_order.alloc(nE, st);
+        GRL_CUDA(cudaMemcpyAsync(c->kd_order.p, order, nE * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    GRL_CUDA(cudaStreamSynchronize(st));  // temporaries above are released in stream order
+    c->is_suffix = std::move(is_suffix_next);
+}
+
+template <class OutT>
+void stage_rewrite(Round& R, DevBuf<u8>& new_text, DevBuf<u32>& new_end_bits) {
+    new_text.alloc(std::max<u64>(R.p * sizeof(OutT), 16), R.st);
+    new_end_bits.alloc(div_up(R.p, 32), R.st);
+    rewrite_kernel<OutT><<<grid_for(R.p, 256), 256, 0, R.st>>>(R.slot_of_phrase.p, R.p, R.table.p, (OutT*)new_text.p, new_end_bits.p);
+    GRL_KERNEL_CHECK();
+}
+
+template <class CellT, bool FIRST>
+void run_round_t(grlgpu_ctx* c, grlgpu_round_t* out) {
+    Round R(c);
+    Timer t_all(c->st), t_text(c->st), t_dict(c->st), t_rw(c->st);
+    t_all.start();
+    t_text.start();
+    stage_flags<CellT, FIRST>(R);
+    if (R.n < (1ull << 31)) stage_dedup<CellT, u32>(R); else stage_dedup<CellT, u64>(R);
+    t_text.stop();
+    t_dict.start();
+    const u64 A = c->alphabet;
+    // rule values go up to A + 3 + tot + 1 with tot <= nE
+    const bool wide = (A + R.nE + 8) >= (1ull << 32);
+    if (wide) { stage_gather<CellT, FIRST, u64>(R); stage_dict<u64>(R); }
+    else { stage_gather<CellT, FIRST, u32>(R); stage_dict<u32>(R); }
+    t_dict.stop();
+    if (c->flags & GRLGPU_FLAG_KEEP_DICT) {
+        c->kd_D = std::move(R.D_raw);
+        c->kd_off = std::move(R.ph_off);
+        c->kd_len = std::move(R.ph_len);
+        c->kd_freq = std::move(R.ph_freq);
+        c->kd_phr_of = std::move(R.phr_of);
+        c->kd_meta.alloc(R.d, c->st);
+    }
+    t_rw.start();
+    const int bps = bit_width64(R.tot) + 1;  // exact_par_phase.cpp:456-465
+    const int w_out = bps <= 8 ? 1 : bps <= 16 ? 2 : bps <= 32 ? 4 : 8;
+    DevBuf<u8> new_text;
+    DevBuf<u32> new_end;
+    if (w_out == 1) stage_rewrite<u8>(R, new_text, new_end);
+    else if (w_out == 2) stage_rewrite<u16>(R, new_text, new_end);
+    else if (w_out == 4) stage_rewrite<u32>(R, new_text, new_end);
+    else stage_rewrite<u64>(R, new_text, new_end);
+    t_rw.stop();
+    t_all.stop();
+
+    memset(out, 0, sizeof(*out));
+    out->round = (u64)c->round + 1;
+    out->n_in = R.n;
+    out->n_strings = c->n_strings;
+    out->parse_len = R.p;
+    out->n_phrases = R.d;
+    out->dict_syms = R.nE;
+    out->max_freq = R.max_freq;
+    out->alphabet = A;
+    out->tot_phrases = R.tot;
+    out->n_pre_runs = R.n_pre;
+    out->cell_bytes_in = (u32)c->w;
+    out->cell_bytes_out = (u32)w_out;
+    out->sym_bytes = (u32)c->lvl_sym_bytes;
+    out->done = R.p == c->n_strings;
+    out->algorithmic_bytes = R.n * (u64)c->w + R.p * (u64)w_out + R.nE * (u64)c->w + 8 * R.d;
+    out->device_ms = t_all.ms();
+    out->text_pass_ms = t_text.ms();
+    out->dict_ms = t_dict.ms();
+    out->rewrite_ms = t_rw.ms();
+
+    if ((c->flags & GRLGPU_FLAG_KEEP_DICT)) {  // metasymbol per distinct phrase, for tests
+        std::vector<u32> slots(R.d);
+        GRL_CUDA(cudaMemcpy(slots.data(), R.occ_slots.p, R.d * 4, cudaMemcpyDeviceToHost));
+        std::vector<ulonglong2> tab(R.cap);
+        GRL_CUDA(cudaMemcpy(tab.data(), R.table.p, R.cap * sizeof(ulonglong2), cudaMemcpyDeviceToHost));
+        std::vector<u64> metas(R.d);
+        for (u64 i = 0; i < R.d; i++) metas[i] = tab[slots[i]].y;
+        GRL_CUDA(cudaMemcpy(c->kd_meta.p, metas.data(), R.d * 8, cudaMemcpyHostToDevice));
+    }
+
+    // the parse becomes the text of the next round
+    GRL_CUDA(cudaStreamSynchronize(c->st));
+    c->text_own = std::move(new_text);
+    c->text = c->text_own.p;
+    c->end_bits = std::move(new_end);
+    c->n = R.p;
+    c->w = w_out;
+    c->first = false;
+    c->alphabet = R.tot;
+    c->round++;
+    c->done = out->done != 0;
+}
+
+void run_round(grlgpu_ctx* c, grlgpu_round_t* out) {
+    if (c->first) {
+        switch (c->w) {
+            case 1: run_round_t<u8, true>(c, out); break;
+            case 2: run_round_t<u16, true>(c, out); break;
+            case 4: run_round_t<u32, true>(c, out); break;
+            default: run_round_t<u64, true>(c, out); break;
+        }
+    } else {
+        switch (c->w) {
+            case 1: run_round_t<u8, false>(c, out); break;
+            case 2: run_round_t<u16, false>(c, out); break;
+            case 4: run_round_t<u32, false>(c, out); break;
+            default: run_round_t<u64, false>(c, out); break;
+        }
+    }
+}
+
+template <class CellT>
+void compute_stats(grlgpu_ctx* c) {
+    const CellT* text = (const CellT*)c->text;
+    CellT sep_c;
+    GRL_CUDA(cudaMemcpyAsync(&sep_c, text + (c->n - 1), sizeof(CellT), cudaMemcpyDeviceToHost, c->st));
+    GRL_CUDA(cudaStreamSynchronize(c->st));
+    DevBuf<StatsAcc> acc(1, c->st);
+    StatsAcc h;
+    memset(&h, 0, sizeof(h));
+    h.min_sym = ~0ULL;
+    GRL_CUDA(cudaMemcpyAsync(acc.p, &h, sizeof(h), cudaMemcpyHostToDevice, c->st));
+    stats_kernel<CellT><<<148 * 8, 256, 0, c->st>>>(text, c->n, sep_c, acc.p);
+    GRL_KERNEL_CHECK();
+    GRL_CUDA(cudaMemcpyAsync(&h, acc.p, sizeof(h), cudaMemcpyDeviceToHost, c->st));
+    GRL_CUDA(cudaStreamSynchronize(c->st));
+    grlgpu_stats_t& s = c->stats;
+    s.n_syms = c->n;
+    s.sep_sym = (u64)sep_c;
+    s.n_strings = h.n_sep;
+    s.max_sym_freq = c->n;  // utils.cpp:117
+    if (sizeof(CellT) == 1) {  // utils.cpp:161-175
+        int lo = 0, hi = 255;
+        while (h.hist[lo] == 0) lo++;
+        while (h.hist[hi] == 0) hi--;
+        s.min_sym = lo; s.max_sym = hi;
+        u64 m = 0;
+        for (int i = 0; i < 256; i++) m = std::max<u64>(m, h.hist[i]);
+        s.max_sym_freq = m;
+    } else { s.min_sym = h.min_sym; s.max_sym = h.max_sym; }
+    if (s.sep_sym != s.min_sym) throw Error(GRLGPU_ERR_ILL_FORMED, "the collection is ill formed: the last symbol is not the smallest symbol");
+    // longest string: positions of the separators -> adjacent differences
+    {
+        const u64 n_words = div_up(c->n, 32);
+        DevBuf<u32> eb(n_words, c->st), sb(n_words, c->st);
+        first_round_end_bits_kernel<CellT><<<grid_for(c->n, 256), 256, 0, c->st>>>(text, c->n, sep_c, eb.p);
+        next_start_bits_kernel<<<grid_for(n_words, 256), 256, 0, c->st>>>(eb.p, c->n, sb.p);
+        GRL_KERNEL_CHECK();
+        BitmapCompactor bc;
+        const u64 ns = bc.count(sb.p, c->n, c->st);
+        DevBuf<u64> ptrs(ns + 1, c->st), mx(1, c->st);
+        bc.write<u64>(nullptr, ptrs.p);
+        GRL_CUDA(cudaMemcpyAsync(ptrs.p + ns, &c->n, 8, cudaMemcpyHostToDevice, c->st));
+        mx.zero();
+        adjacent_max_diff_kernel<<<296, 256, 0, c->st>>>(ptrs.p, ns, mx.p);
+        GRL_KERNEL_CHECK();
+        s.longest_string = d2h_scalar(mx.p, c->st);
+    }
+    c->sep = s.sep_sym;
+    c->n_strings = s.n_strings;
+    c->alphabet = s.max_sym + 1;  // exact_par_phase.cpp:316
+    c->have_stats = true;
+}
+
+template <class F>
+int guarded(grlgpu_ctx* c, F&& f) {
+    try {
+        if (c) GRL_CUDA(cudaSetDevice(c->device));
+        f();
+        return GRLGPU_OK;
+    } catch (const Error& e) {
+        if (c) c->last_error = e.what();
+        cudaGetLastError();
+        if (e.code == GRLGPU_ERR_CUDA && std::string(e.what()).find("out of memory") != std::string::npos) return GRLGPU_ERR_NOMEM;
+        return e.code;
+    } catch (const std::exception& e) {
+        if (c) c->last_error = e.what();
+        return GRLGPU_ERR_CUDA;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int grlgpu_create(grlgpu_ctx** ctx, int device, uint64_t flags) {
+    if (!ctx) return GRLGPU_ERR_ARG;
+    *ctx = nullptr;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0 || device < 0 || device >= n_dev) return GRLGPU_ERR_CUDA;
+    std::unique_ptr<grlgpu_ctx> c(new grlgpu_ctx());
+    c->device = device;
+    c->flags = flags;
+    int rc = guarded(c.get(), [&] {
+        GRL_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+        cudaMemPool_t pool;
+        GRL_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        u64 thr = ~0ULL;  // keep freed blocks in the pool: rounds reuse them
+        GRL_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    });
+    if (rc != GRLGPU_OK) return rc;
+    *ctx = c.release();
+    return GRLGPU_OK;
+}
+
+int grlgpu_destroy(grlgpu_ctx* ctx) {
+    if (!ctx) return GRLGPU_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->st);
+    cudaStream_t st = ctx->st;
+    delete ctx;
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    return GRLGPU_OK;
+}
+
+static int set_text_common(grlgpu_ctx* ctx, const void* text, uint64_t n_syms, int sym_bytes, bool on_device) {
+    if (!ctx || !text || n_syms == 0 || !(sym_bytes == 1 || sym_bytes == 2 || sym_bytes == 4 || sym_bytes == 8)) return GRLGPU_ERR_ARG;
+    if (on_device && ((uintptr_t)text & 15)) return GRLGPU_ERR_ARG;
+    return guarded(ctx, [&] {
+        ctx->n = n_syms; ctx->w = sym_bytes; ctx->first = true; ctx->round = 0; ctx->done = false; ctx->have_stats = false;
+        if (on_device) { ctx->text_own.release(); ctx->text = text; }
+        else {
+            ctx->text_own.alloc(n_syms * (u64)sym_bytes + 16, ctx->st);
+            GRL_CUDA(cudaMemcpyAsync(ctx->text_own.p, text, n_syms * (u64)sym_bytes, cudaMemcpyHostToDevice, ctx->st));
+            GRL_CUDA(cudaStreamSynchronize(ctx->st));
+            ctx->text = ctx->text_own.p;
+        }
+    });
+}
+int grlgpu_set_text(grlgpu_ctx* ctx, const void* text, uint64_t n_syms, int sym_bytes) { return set_text_common(ctx, text, n_syms, sym_bytes, false); }
+int grlgpu_set_text_device(grlgpu_ctx* ctx, const void* dev_text, uint64_t n_syms, int sym_bytes) { return set_text_common(ctx, dev_text, n_syms, sym_bytes, true); }
+
+int grlgpu_stats(grlgpu_ctx* ctx, grlgpu_stats_t* out) {
+    if (!ctx || !out) return GRLGPU_ERR_ARG;
+    if (!ctx->text || !ctx->first) return GRLGPU_ERR_STATE;
+    int rc = guarded(ctx, [&] {
+        if (!ctx->have_stats) {
+            switch (ctx->w) {
+                case 1: compute_stats<u8>(ctx); break;
+                case 2: compute_stats<u16>(ctx); break;
+                case 4: compute_stats<u32>(ctx); break;
+                default: compute_stats<u64>(ctx); break;
+            }
+        }
+    });
+    if (rc == GRLGPU_OK) *out = ctx->stats;
+    return rc;
+}
+
+int grlgpu_round(grlgpu_ctx* ctx, grlgpu_round_t* out) {
+    if (!ctx || !out) return GRLGPU_ERR_ARG;
+    if (!ctx->text || ctx->done) return GRLGPU_ERR_STATE;
+    if (!ctx->have_stats) {
+        grlgpu_stats_t s;
+        int rc = grlgpu_stats(ctx, &s);
+        if (rc != GRLGPU_OK) return rc;
+    }
+    return guarded(ctx, [&] { run_round(ctx, out); });
+}
+
+int grlgpu_fetch_level(grlgpu_ctx* ctx, void* rule_l, void* rule_r, uint8_t* has_hocc, void* pre_sym, uint64_t* pre_len) {
+    if (!ctx) return GRLGPU_ERR_ARG;
+    if (ctx->round == 0) return GRLGPU_ERR_STATE;
+    return guarded(ctx, [&] {
+        const u64 sb = (u64)ctx->lvl_sym_bytes;
+        if (rule_l) GRL_CUDA(cudaMemcpyAsync(rule_l, ctx->rule_l.p, ctx->lvl_tot * sb, cudaMemcpyDeviceToHost, ctx->st));
+        if (rule_r) GRL_CUDA(cudaMemcpyAsync(rule_r, ctx->rule_r.p, ctx->lvl_tot * sb, cudaMemcpyDeviceToHost, ctx->st));
+        if (has_hocc) GRL_CUDA(cudaMemcpyAsync(has_hocc, ctx->has_hocc.p, ctx->lvl_tot, cudaMemcpyDeviceToHost, ctx->st));
+        if (pre_sym) GRL_CUDA(cudaMemcpyAsync(pre_sym, ctx->pre_sym.p, ctx->lvl_npre * sb, cudaMemcpyDeviceToHost, ctx->st));
+        if (pre_len) GRL_CUDA(cudaMemcpyAsync(pre_len, ctx->pre_len.p, ctx->lvl_npre * 8, cudaMemcpyDeviceToHost, ctx->st));
+        GRL_CUDA(cudaStreamSynchronize(ctx->st));
+    });
+}
+
+int grlgpu_fetch_parse(grlgpu_ctx* ctx, void* dst) {
+    if (!ctx || !dst) return GRLGPU_ERR_ARG;
+    if (ctx->round == 0) return GRLGPU_ERR_STATE;
+    return guarded(ctx, [&] {
+        GRL_CUDA(cudaMemcpyAsync(dst, ctx->text, ctx->n * (u64)ctx->w, cudaMemcpyDeviceToHost, ctx->st));
+        GRL_CUDA(cudaStreamSynchronize(ctx->st));
+    });
+}
+
+int grlgpu_fetch_str_ptrs(grlgpu_ctx* ctx, uint64_t* dst) {
+    if (!ctx || !dst) return GRLGPU_ERR_ARG;
+    if (ctx->round == 0) return GRLGPU_ERR_STATE;
+    return guarded(ctx, [&] {
+        const u64 n_words = div_up(ctx->n, 32);
+        DevBuf<u32> sb(n_words, ctx->st);
+        next_start_bits_kernel<<<grid_for(n_words, 256), 256, 0, ctx->st>>>(ctx->end_bits.p, ctx->n, sb.p);
+        GRL_KERNEL_CHECK();
+        BitmapCompactor bc;
+        const u64 ns = bc.count(sb.p, ctx->n, ctx->st);
+        if (ns != ctx->n_strings) throw Error(GRLGPU_ERR_STATE, "string count changed between rounds");
+        DevBuf<u64> ptrs(ns + 1, ctx->st);
+        bc.write<u64>(nullptr, ptrs.p);
+        GRL_CUDA(cudaMemcpyAsync(dst, ptrs.p, ns * 8, cudaMemcpyDeviceToHost, ctx->st));
+        GRL_CUDA(cudaStreamSynchronize(ctx->st));
+        dst[ns] = ctx->n;
+    });
+}
+
+int grlgpu_fetch_dictionary(grlgpu_ctx* ctx, uint64_t* syms, uint64_t* lens, uint64_t* freqs, uint64_t* metas) {
+    if (!ctx) return GRLGPU_ERR_ARG;
+    if (ctx->round == 0 || !(ctx->flags & GRLGPU_FLAG_KEEP_DICT) || !ctx->kd_order.p) return GRLGPU_ERR_STATE;
+    return guarded(ctx, [&] {
+        const u64 d = ctx->kd_d, nE = ctx->kd_nE;
+        std::vector<u32> order(nE), phr_of(nE), off(d + 1), len(d);
+        std::vector<u64> freq(d), meta(d);
+        std::vector<u8> Draw(nE * (u64)ctx->lvl_sym_bytes);
+        GRL_CUDA(cudaMemcpy(order.data(), ctx->kd_order.p, nE * 4, cudaMemcpyDeviceToHost));
+        GRL_CUDA(cudaMemcpy(phr_of.data(), ctx->kd_phr_of.p, nE * 4, cudaMemcpyDeviceToHost));
+        GRL_CUDA(cudaMemcpy(off.data(), ctx->kd_off.p, (d + 1) * 4, cudaMemcpyDeviceToHost));
+        GRL_CUDA(cudaMemcpy(len.data(), ctx->kd_len.p, d * 4, cudaMemcpyDeviceToHost));
+        GRL_CUDA(cudaMemcpy(freq.data(), ctx->kd_freq.p, d * 8, cudaMemcpyDeviceToHost));
+        GRL_CUDA(cudaMemcpy(meta.data(), ctx->kd_meta.p, d * 8, cudaMemcpyDeviceToHost));
+        GRL_CUDA(cudaMemcpy(Draw.data(), ctx->kd_D.p, Draw.size(), cudaMemcpyDeviceToHost));
+        u64 k = 0, so = 0;
+        for (u64 i = 0; i < nE; i++) {  // full-phrase entries in suffix order = phrases in A.2 order
+            const u32 e = order[i], ph = phr_of[e];
+            if (e != off[ph]) continue;
+            if (lens) lens[k] = len[ph];
+            if (freqs) freqs[k] = freq[ph];
+            if (metas) metas[k] = meta[ph];
+            if (syms)
+                for (u32 t = 0; t < len[ph]; t++)
+                    syms[so + t] = ctx->lvl_sym_bytes == 4 ? ((const u32*)Draw.data())[e + t] : ((const u64*)Draw.data())[e + t];
+            so += len[ph];
+            k++;
+        }
+    });
+}
+
+const char* grlgpu_strerror(int status) {
+    switch (status) {
+        case GRLGPU_OK: return "ok";
+        case GRLGPU_ERR_ARG: return "invalid argument";
+        case GRLGPU_ERR_ILL_FORMED: return "the collection is ill formed";
+        case GRLGPU_ERR_CUDA: return "CUDA error or no usable device";
+        case GRLGPU_ERR_NOMEM: return "out of device memory";
+        case GRLGPU_ERR_STATE: return "call out of order";
+        case GRLGPU_ERR_LIMIT: return "size limit of the device path exceeded";
+    }
+    return "unknown status";
+}
+const char* grlgpu_last_error(const grlgpu_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+// ---- self-test hooks ----
+int grlgpu_selftest_scan(const uint32_t* in, uint64_t n, uint64_t* out_exclusive, uint64_t* total) {
+    return guarded(nullptr, [&] {
+        cudaStream_t st = nullptr;
+        DevBuf<u32> din(n, st);
+        DevBuf<u64> dout(n, st), tot(1, st);
+        GRL_CUDA(cudaMemcpy(din.p, in, n * 4, cudaMemcpyHostToDevice));
+        exclusive_scan<u32, u64>(din.p, dout.p, n, tot.p, st);
+        GRL_CUDA(cudaMemcpy(out_exclusive, dout.p, n * 8, cudaMemcpyDeviceToHost));
+        GRL_CUDA(cudaMemcpy(total, tot.p, 8, cudaMemcpyDeviceToHost));
+    });
+}
+int grlgpu_selftest_sort(uint64_t* keys, uint32_t* vals, uint64_t n, int n_bits) {
+    return guarded(nullptr, [&] {
+        cudaStream_t st = nullptr;
+        DevBuf<u64> k(n, st), ka(n, st);
+        DevBuf<u32> v(n, st), va(n, st);
+        GRL_CUDA(cudaMemcpy(k.p, keys, n * 8, cudaMemcpyHostToDevice));
+        GRL_CUDA(cudaMemcpy(v.p, vals, n * 4, cudaMemcpyHostToDevice));
+        u64 *kp = k.p, *kap = ka.p;
+        u32 *vp = v.p, *vap = va.p;
+        radix_sort_pairs(&kp, &vp, &kap, &vap, n, n_bits, st);
+        GRL_CUDA(cudaStreamSynchronize(st));
+        GRL_CUDA(cudaMemcpy(keys, kp, n * 8, cudaMemcpyDeviceToHost));
+        GRL_CUDA(cudaMemcpy(vals, vp, n * 4, cudaMemcpyDeviceToHost));
+    });
+}
+int grlgpu_selftest_compact(const uint32_t* bits, const uint32_t* prev_bits, uint64_t n_bits, uint64_t* out, uint64_t* count) {
+    return guarded(nullptr, [&] {
+        cudaStream_t st = nullptr;
+        const u64 n_words = div_up(n_bits, 32);
+        DevBuf<u32> b(n_words, st), pb(n_words, st);
+        GRL_CUDA(cudaMemcpy(b.p, bits, n_words * 4, cudaMemcpyHostToDevice));
+        if (prev_bits) GRL_CUDA(cudaMemcpy(pb.p, prev_bits, n_words * 4, cudaMemcpyHostToDevice));
+        BitmapCompactor bc;
+        const u64 cnt = bc.count(b.p, n_bits, st);
+        DevBuf<u64> o(cnt, st);
+        bc.write<u64>(prev_bits ? pb.p : nullptr, o.p);
+        GRL_CUDA(cudaMemcpy(out, o.p, cnt * 8, cudaMemcpyDeviceToHost));
+        *count = cnt;
+    });
+}
+
+}  // extern "C"

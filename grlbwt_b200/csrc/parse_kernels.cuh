@@ -1,0 +1,319 @@
+// Text-side kernels of one parse round (reference: include/parsing_strategies.h:82-145 scan,
+// include/exact_algo/exact_par_phase.hpp:14-84 hash / rewrite functors, external/cdt/lib/utils.cpp:100-189 stats).
+//
+// Text layout in HBM: n cells of CellT (1/2/4/8 bytes, little endian). Round 1: raw symbols
+// (rep bit implicitly 1). Later rounds: cell = (rank << 1) | rep. String ends are a bitmap
+// (bit i set <=> cell i is the last cell of its string); in round 1 it is derived from cell == sep.
+#pragma once
+#include "util.cuh"
+
+namespace grl {
+
+// ------------------------------------------------------------------------------------------------
+// K0  collection statistics (utils.cpp:100-189): min / max symbol, number of separators, byte histogram
+// ------------------------------------------------------------------------------------------------
+struct StatsAcc {
+    u64 min_sym, max_sym, n_sep;
+    u64 hist[256];
+};
+
+template <class CellT>
+__global__ void __launch_bounds__(256) stats_kernel(const CellT* __restrict__ text, u64 n, CellT sep, StatsAcc* acc) {
+    constexpr int VEC = 16 / sizeof(CellT);
+    __shared__ u32 sh[256];
+    if (sizeof(CellT) == 1) sh[threadIdx.x] = 0;
+    __syncthreads();
+    u64 mn = ~0ULL, mx = 0, ns = 0;
+    const u64 n_vec = n / VEC;
+    const uint4* tv = reinterpret_cast<const uint4*>(text);
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (u64)gridDim.x * blockDim.x) {
+        uint4 q = tv[i];
+        const CellT* c = reinterpret_cast<const CellT*>(&q);
+#pragma unroll
+        for (int k = 0; k < VEC; k++) {
+            const u64 s = c[k];
+            if (sizeof(CellT) == 1) atomicAdd(&sh[s & 255], 1u);
+            else { mn = s < mn ? s : mn; mx = s > mx ? s : mx; }
+            ns += (c[k] == sep);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n - n_vec * VEC)) {  // tail cells
+        const u64 s = text[n_vec * VEC + threadIdx.x];
+        if (sizeof(CellT) == 1) atomicAdd(&sh[s & 255], 1u);
+        else { mn = s < mn ? s : mn; mx = s > mx ? s : mx; }
+        ns += (s == (u64)sep);
+    }
+    ns = warp_sum(ns);
+    if (lane_id() == 0 && ns) atomicAdd(&acc->n_sep, ns);
+    if (sizeof(CellT) == 1) {
+        __syncthreads();
+        if (sh[threadIdx.x]) atomicAdd(&acc->hist[threadIdx.x], (u64)sh[threadIdx.x]);
+    } else {
+        mn = warp_min(mn);
+        mx = warp_max(mx);
+        if (lane_id() == 0) { atomicMin(&acc->min_sym, mn); atomicMax(&acc->max_sym, mx); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1  LMS phrase-start flags (parsing_strategies.h:112-138; data-parallel form of SURVEY.md App. H).
+// One thread = 32 consecutive cells = one word of the output bitmaps. type[i] (S=1 / L=0) is
+// resolved inside the thread where possible, else by the first determined cell to the right:
+// ballot inside the warp, shared memory across warps, bounded look-ahead past the CTA; a run of
+// equal cells longer than the look-ahead raises *need_slow and the host re-runs with per-CTA
+// incoming types computed by the summary/resolve kernels (MODE 1 / lms_resolve_kernel / MODE 2).
+// ------------------------------------------------------------------------------------------------
+constexpr int LMS_THREADS = 256;
+constexpr int LMS_CELLS = 32;
+constexpr int LMS_LOOKAHEAD = 128;
+enum { ST_L = 0, ST_S = 1, ST_PASS = 2 };
+
+template <class CellT, bool FIRST>
+__device__ __forceinline__ u64 cell_value(CellT c) { return FIRST ? (u64)c : ((u64)c >> 1); }
+
+template <class CellT, bool FIRST>
+__device__ __forceinline__ bool cell_is_end(const CellT* __restrict__ text, const u32* __restrict__ end_bits, CellT sep, u64 i) {
+    if (FIRST) return text[i] == sep;
+    return (end_bits[i >> 5] >> (i & 31)) & 1u;
+}
+
+// MODE 0: flags with bounded look-ahead; MODE 1: only the per-CTA summary state; MODE 2: flags with given incoming types
+template <class CellT, bool FIRST, int MODE>
+__global__ void __launch_bounds__(LMS_THREADS) lms_flags_kernel(const CellT* __restrict__ text, u64 n, CellT sep, const u32* __restrict__ end_bits_in,
+                                                                u32* __restrict__ end_bits_out, u32* __restrict__ start_bits,
+                                                                u8* __restrict__ block_state, const u8* __restrict__ block_incoming, u32* need_slow) {
+    __shared__ u32 s_warp[LMS_THREADS / 32];
+    __shared__ u32 s_xblk;
+    const u64 word = (u64)blockIdx.x * LMS_THREADS + threadIdx.x;
+    const u64 base = word * LMS_CELLS;
+    const u32 lane = lane_id(), warp = threadIdx.x >> 5;
+
+    // ---- CTA incoming type: type of the first cell after this CTA's range ----
+    if (threadIdx.x == LMS_THREADS - 1) {
+        u32 x = ST_L;
+        if (MODE == 2) x = block_incoming[blockIdx.x];
+        else if (MODE == 0) {
+            u64 q = ((u64)blockIdx.x + 1) * LMS_THREADS * LMS_CELLS;
+            if (q < n) {
+                x = ST_PASS;
+                for (int k = 0; k < LMS_LOOKAHEAD; k++, q++) {
+                    if (cell_is_end<CellT, FIRST>(text, end_bits_in, sep, q)) { x = ST_L; break; }
+                    const u64 a = cell_value<CellT, FIRST>(text[q]), b = cell_value<CellT, FIRST>(text[q + 1]);
+                    if (a != b) { x = a < b ? ST_S : ST_L; break; }
+                }
+                if (x == ST_PASS) { atomicExch(need_slow, 1u); x = ST_L; }
+            }
+        }
+        s_xblk = x;
+    }
+
+    // ---- load 32 cells; per-cell determined/value masks ----
+    u32 valid = 0, endm = 0, repm = 0, detm = 0, valm = 0, gtprev = 0;
+    u32 left_end = 1, left_rep = 1;  // position 0 starts a string
+    if (base < n) {
+        const u64 cnt = n - base;
+        valid = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+        __align__(16) CellT c[LMS_CELLS];
+        if (cnt >= 32) {
+            constexpr int NV = LMS_CELLS * sizeof(CellT) / 16;
+            const uint4* src = reinterpret_cast<const uint4*>(text + base);
+            uint4* dst = reinterpret_cast<uint4*>(c);
+#pragma unroll
+            for (int k = 0; k < NV; k++) dst[k] = src[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < LMS_CELLS; k++) c[k] = (u64)k < cnt ? text[base + k] : sep;
+        }
+        if (FIRST) {
+#pragma unroll
+            for (int k = 0; k < LMS_CELLS; k++) endm |= (u32)(c[k] == sep) << k;
+            repm = 0xffffffffu;
+        } else {
+            endm = end_bits_in[word];
+#pragma unroll
+            for (int k = 0; k < LMS_CELLS; k++) repm |= (u32)(c[k] & 1) << k;
+        }
+        endm = (endm & valid) | ~valid;  // cells past the end behave as string ends
+        u64 vnext = 0;
+        if (cnt > 32) vnext = cell_value<CellT, FIRST>(text[base + 32]);
+        u64 vleft = 0;
+        if (base > 0) {
+            const CellT cl = text[base - 1];
+            vleft = cell_value<CellT, FIRST>(cl);
+            left_rep = FIRST ? 1u : (u32)(cl & 1);
+            left_end = FIRST ? (u32)(cl == sep) : (end_bits_in[word - 1] >> 31);
+        }
+#pragma unroll
+        for (int k = 0; k < LMS_CELLS; k++) {
+            const u64 v = cell_value<CellT, FIRST>(c[k]);
+            const u64 nv = k == LMS_CELLS - 1 ? vnext : cell_value<CellT, FIRST>(c[k == LMS_CELLS - 1 ? k : k + 1]);
+            const u64 pv = k == 0 ? vleft : cell_value<CellT, FIRST>(c[k == 0 ? 0 : k - 1]);
+            const bool e = (endm >> k) & 1u;
+            detm |= (u32)(e || v != nv) << k;
+            valm |= (u32)(!e && v < nv) << k;
+            gtprev |= (u32)(pv > v) << k;
+        }
+    } else {
+        detm = 0xffffffffu;  // out of range: determined, L
+        endm = 0xffffffffu;
+    }
+
+    // ---- thread summary and incoming type ----
+    const u32 my_state = detm ? ((valm >> (__ffs(detm) - 1)) & 1u) : (u32)ST_PASS;
+    const u32 nonpass = __ballot_sync(0xffffffffu, my_state != ST_PASS);
+    const u32 sbits = __ballot_sync(0xffffffffu, my_state == ST_S);
+    if (lane == 0) s_warp[warp] = nonpass ? ((sbits >> (__ffs(nonpass) - 1)) & 1u) : (u32)ST_PASS;
+    __syncthreads();
+    if (MODE == 1) {
+        if (threadIdx.x == 0) {
+            u32 st = ST_PASS;
+            for (int w = 0; w < LMS_THREADS / 32; w++)
+                if (s_warp[w] != ST_PASS) { st = s_warp[w]; break; }
+            block_state[blockIdx.x] = (u8)st;
+        }
+        return;
+    }
+    u32 x;
+    {
+        const u32 m = lane == 31 ? 0u : (nonpass & ~((2u << lane) - 1u));
+        if (m) x = (sbits >> (__ffs(m) - 1)) & 1u;
+        else {
+            x = ST_PASS;
+            for (int w = warp + 1; w < LMS_THREADS / 32; w++)
+                if (s_warp[w] != ST_PASS) { x = s_warp[w]; break; }
+            if (x == ST_PASS) x = s_xblk;
+        }
+    }
+    if (base >= n) return;
+
+    // ---- types of own cells: type(k) = det(k) ? val(k) : type(k+1), type(32) = x ----
+    u32 typem = 0, t = x;
+#pragma unroll
+    for (int k = LMS_CELLS - 1; k >= 0; k--) {
+        t = ((detm >> k) & 1u) ? ((valm >> k) & 1u) : t;
+        typem |= t << k;
+    }
+    const u32 real_end = endm & valid;
+    const u32 prev_end = (real_end << 1) | left_end;   // is_start(k): k begins a string
+    const u32 prev_rep = (repm << 1) | left_rep;
+    const u32 brk = gtprev & typem & repm & prev_rep & ~prev_end;  // parsing_strategies.h:121-123
+    start_bits[word] = (prev_end | brk) & valid;
+    if (FIRST) end_bits_out[word] = real_end;
+}
+
+// serial reverse pass over the per-CTA summary states (slow path only; one thread)
+static __global__ void lms_resolve_kernel(const u8* __restrict__ block_state, u8* __restrict__ block_incoming, u64 n_blocks) {
+    if (blockIdx.x || threadIdx.x) return;
+    u8 inc = ST_L;
+    for (u64 b = n_blocks; b-- > 0;) {
+        block_incoming[b] = inc;
+        if (block_state[b] != ST_PASS) inc = block_state[b];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3  phrase deduplication + counting (ext_hash_functor exact_par_phase.hpp:33-39; replaces the
+// XXH3-keyed Robin-Hood table hash_table.hpp:451-539). Open addressing, linear probing, 16-byte
+// entries {key = first-occurrence position << 24 | min(len, LEN_SAT), count}; a key is claimed
+// with one 64-bit CAS and is immediately complete because it points into the immutable text.
+// ------------------------------------------------------------------------------------------------
+constexpr u64 HT_EMPTY = ~0ULL;
+constexpr u64 HT_LEN_SAT = 0xFFFFFFULL;
+constexpr int HT_MAX_PROBES = 4096;
+
+template <class PosT>
+struct PosFlag {
+    static constexpr PosT FLAG = PosT(1) << (sizeof(PosT) * 8 - 1);
+};
+
+// phrase j covers [s, e] (closed); fin = it is the last phrase of its string (parsing_strategies.h:126,141)
+template <class PosT>
+__device__ __forceinline__ void phrase_span(const PosT* __restrict__ ps, u64 j, u64& s, u64& e, bool& fin) {
+    constexpr PosT FLAG = PosFlag<PosT>::FLAG;
+    const PosT a = ps[j], b = ps[j + 1];
+    s = (u64)(a & ~FLAG);
+    fin = (b & FLAG) != 0;
+    e = fin ? (u64)(b & ~FLAG) - 1 : (u64)(b & ~FLAG);
+}
+
+template <class PosT>
+__device__ u64 phrase_len_at(const PosT* __restrict__ ps, u64 p, u64 pos) {  // true length of the phrase starting at pos
+    constexpr PosT FLAG = PosFlag<PosT>::FLAG;
+    u64 lo = 0, hi = p;
+    while (lo < hi) {
+        const u64 mid = (lo + hi) >> 1;
+        if ((u64)(ps[mid] & ~FLAG) < pos) lo = mid + 1; else hi = mid;
+    }
+    u64 s, e; bool f;
+    phrase_span<PosT>(ps, lo, s, e, f);
+    return e - s + 1;
+}
+
+template <class CellT>
+__device__ __forceinline__ u64 phrase_hash(const CellT* __restrict__ text, u64 s, u64 len) {
+    u64 h = 0xcbf29ce484222325ULL ^ len;
+    for (u64 i = 0; i < len; i++) h = (h ^ (u64)text[s + i]) * 0x100000001b3ULL;
+    return mix64(h);
+}
+
+template <class CellT, class PosT>
+__global__ void __launch_bounds__(256) phrase_insert_kernel(const CellT* __restrict__ text, const PosT* __restrict__ ps, u64 p, ulonglong2* table,
+                                                            u64 cap_mask, u32* __restrict__ slot_of_phrase, u32* overflow) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p) return;
+    u64 s, e; bool fin;
+    phrase_span<PosT>(ps, j, s, e, fin);
+    const u64 len = e - s + 1;
+    const u64 lenf = len < HT_LEN_SAT ? len : HT_LEN_SAT;
+    const u64 mykey = (s << 24) | lenf;
+    u64 slot = phrase_hash<CellT>(text, s, len) & cap_mask;
+    for (int probes = 0; probes < HT_MAX_PROBES; probes++) {
+        u64 k = *reinterpret_cast<volatile u64*>(&table[slot].x);
+        if (k == HT_EMPTY) {
+            const u64 old = atomicCAS(&table[slot].x, HT_EMPTY, mykey);
+            k = old == HT_EMPTY ? mykey : old;
+        }
+        bool match = k == mykey;
+        if (!match && (k & HT_LEN_SAT) == lenf) {
+            const u64 kpos = k >> 24;
+            match = true;
+            for (u64 i = 0; i < len; i++)
+                if (text[kpos + i] != text[s + i]) { match = false; break; }
+            if (match && lenf == HT_LEN_SAT) match = phrase_len_at<PosT>(ps, p, kpos) == len;
+        }
+        if (match) {
+            atomicAdd(&table[slot].y, 1ULL);
+            slot_of_phrase[j] = (u32)slot | (fin ? 0x80000000u : 0u);
+            return;
+        }
+        slot = (slot + 1) & cap_mask;
+    }
+    atomicExch(overflow, 1u);
+}
+
+static __global__ void __launch_bounds__(256) table_occupancy_kernel(const ulonglong2* __restrict__ table, u64 cap, u32* __restrict__ occ_bits) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;  // cap is a multiple of 256
+    const u32 b = __ballot_sync(0xffffffffu, table[i].x != HT_EMPTY);
+    if (lane_id() == 0) occ_bits[i >> 5] = b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7  rewrite (ext_parse_functor exact_par_phase.hpp:53-59, parse_text parsing_strategies.h:644-676):
+// out[j] = metasymbol of phrase occurrence j (stored in the entry's count field by then), forward
+// order; the string-end bitmap of the new text comes from the per-occurrence "final" flag.
+// ------------------------------------------------------------------------------------------------
+template <class OutT>
+__global__ void __launch_bounds__(256) rewrite_kernel(const u32* __restrict__ slot_of_phrase, u64 p, const ulonglong2* __restrict__ table,
+                                                      OutT* __restrict__ out, u32* __restrict__ end_bits_out) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 fin = 0;
+    if (j < p) {
+        const u32 sv = slot_of_phrase[j];
+        fin = sv >> 31;
+        out[j] = (OutT)table[sv & 0x7fffffffu].y;
+    }
+    const u32 b = __ballot_sync(0xffffffffu, fin);
+    if (lane_id() == 0 && (j >> 5) < ((p + 31) >> 5)) end_bits_out[j >> 5] = b;
+}
+
+}  // namespace grl

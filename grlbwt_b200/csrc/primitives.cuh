@@ -1,0 +1,323 @@
+// Device-wide building blocks written for this path: exclusive scan, bitmap -> position compaction,
+// LSD radix sort of (u64 key, u32 value) pairs, max-reduction. All are plain multi-kernel
+// formulations (no inter-CTA spin waits), HBM-bound, grid sized from the data.
+#pragma once
+#include "util.cuh"
+
+namespace grl {
+
+// ------------------------------------------------------------------------------------------------
+// Exclusive scan: out[i] = sum_{j<i} in[j]  (TOut accumulates). Works in place (in == out).
+// ------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+template <class TIn, class TOut>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums_kernel(const TIn* __restrict__ in, TOut* __restrict__ partial, u64 n) {
+    __shared__ TOut sm[33];
+    const u64 base = (u64)blockIdx.x * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
+    TOut s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++)
+        if (base + i < n) s += (TOut)in[base + i];
+    TOut tot;
+    block_exclusive_sum<TOut>(s, sm, tot);
+    if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+
+// single block scans a short array (n <= any size, loops tile by tile), writes the grand total
+template <class TIn, class TOut>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_single_block_kernel(const TIn* in, TOut* out, u64 n, TOut* total) {
+    __shared__ TOut sm[33];
+    TOut carry = 0;
+    for (u64 t0 = 0; t0 < n; t0 += SCAN_TILE) {
+        const u64 base = t0 + (u64)threadIdx.x * SCAN_ITEMS;
+        TOut v[SCAN_ITEMS];
+        TOut s = 0;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++) {
+            v[i] = (base + i < n) ? (TOut)in[base + i] : TOut(0);
+            s += v[i];
+        }
+        TOut tot;
+        TOut ex = block_exclusive_sum<TOut>(s, sm, tot) + carry;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++) {
+            if (base + i < n) out[base + i] = ex;
+            ex += v[i];
+        }
+        carry += tot;
+    }
+    if (threadIdx.x == 0 && total) *total = carry;
+}
+
+template <class TIn, class TOut>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const TIn* in, TOut* out, const TOut* __restrict__ tile_prefix, u64 n) {
+    __shared__ TOut sm[33];
+    const u64 base = (u64)blockIdx.x * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
+    TOut v[SCAN_ITEMS];
+    TOut s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        v[i] = (base + i < n) ? (TOut)in[base + i] : TOut(0);
+        s += v[i];
+    }
+    TOut tot;
+    TOut ex = block_exclusive_sum<TOut>(s, sm, tot) + tile_prefix[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        if (base + i < n) out[base + i] = ex;
+        ex += v[i];
+    }
+}
+
+// total_dev (optional, device pointer) receives the sum of all inputs.
+template <class TIn, class TOut>
+void exclusive_scan(const TIn* in, TOut* out, u64 n, TOut* total_dev, cudaStream_t st) {
+    if (n <= (u64)SCAN_TILE * 4) {
+        scan_single_block_kernel<TIn, TOut><<<1, SCAN_THREADS, 0, st>>>(in, out, n, total_dev);
+        GRL_KERNEL_CHECK();
+        return;
+    }
+    const u64 tiles = div_up(n, SCAN_TILE);
+    DevBuf<TOut> partial(tiles, st);
+    scan_tile_sums_kernel<TIn, TOut><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, partial.p, n);
+    GRL_KERNEL_CHECK();
+    exclusive_scan<TOut, TOut>(partial.p, partial.p, tiles, total_dev, st);
+    scan_apply_kernel<TIn, TOut><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, out, partial.p, n);
+    GRL_KERNEL_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bitmap compaction: positions of the set bits of `bits` (n_bits bits, u32 words, LSB first), in
+// increasing order. If `prev_bits` is given, the output carries a flag in its top bit:
+// flag(q) = (q == 0) || prev_bits[q-1]   (used as "q starts a string" when prev_bits marks string ends).
+// ------------------------------------------------------------------------------------------------
+constexpr int BC_THREADS = 256;
+constexpr int BC_WORDS = 8;                      // words per thread
+constexpr int BC_TILE_WORDS = BC_THREADS * BC_WORDS;
+
+__device__ __forceinline__ u32 bc_load_word(const u32* __restrict__ bits, u64 w, u64 n_words, u64 n_bits) {
+    if (w >= n_words) return 0;
+    u32 x = bits[w];
+    if (w == n_words - 1 && (n_bits & 31)) x &= (1u << (n_bits & 31)) - 1u;
+    return x;
+}
+
+static __global__ void __launch_bounds__(BC_THREADS) bitmap_count_kernel(const u32* __restrict__ bits, u64 n_bits, u32* __restrict__ tile_count) {
+    __shared__ u32 sm[33];
+    const u64 n_words = (n_bits + 31) / 32;
+    const u64 w0 = (u64)blockIdx.x * BC_TILE_WORDS + (u64)threadIdx.x * BC_WORDS;
+    u32 c = 0;
+#pragma unroll
+    for (int i = 0; i < BC_WORDS; i++) c += __popc(bc_load_word(bits, w0 + i, n_words, n_bits));
+    u32 tot;
+    block_exclusive_sum<u32>(c, sm, tot);
+    if (threadIdx.x == 0) tile_count[blockIdx.x] = tot;
+}
+
+template <class PosT>
+__global__ void __launch_bounds__(BC_THREADS) bitmap_write_kernel(const u32* __restrict__ bits, const u32* __restrict__ prev_bits, u64 n_bits,
+                                                                  const u64* __restrict__ tile_off, PosT* __restrict__ out) {
+    __shared__ u32 sm[33];
+    constexpr PosT FLAG = PosT(1) << (sizeof(PosT) * 8 - 1);
+    const u64 n_words = (n_bits + 31) / 32;
+    const u64 w0 = (u64)blockIdx.x * BC_TILE_WORDS + (u64)threadIdx.x * BC_WORDS;
+    u32 wd[BC_WORDS];
+    u32 c = 0;
+#pragma unroll
+    for (int i = 0; i < BC_WORDS; i++) {
+        wd[i] = bc_load_word(bits, w0 + i, n_words, n_bits);
+        c += __popc(wd[i]);
+    }
+    u32 tot;
+    u32 ex = block_exclusive_sum<u32>(c, sm, tot);
+    u64 o = tile_off[blockIdx.x] + ex;
+#pragma unroll
+    for (int i = 0; i < BC_WORDS; i++) {
+        u32 x = wd[i];
+        if (!x) continue;
+        const u64 w = w0 + i;
+        u32 fl = 0;
+        if (prev_bits) {
+            u32 pw = bc_load_word(prev_bits, w, n_words, n_bits);
+            u32 pp = w ? bc_load_word(prev_bits, w - 1, n_words, n_bits) : 0x80000000u;  // position 0 starts a string
+            fl = (pw << 1) | (pp >> 31);
+        }
+        while (x) {
+            const int b = __ffs(x) - 1;
+            x &= x - 1;
+            PosT q = (PosT)(w * 32 + b);
+            if ((fl >> b) & 1u) q |= FLAG;
+            out[o++] = q;
+        }
+    }
+}
+
+// Returns the number of set bits (host value; synchronises the stream). out must hold count entries:
+// call with out == nullptr first to size it, or give an upper bound. Here: two-phase API.
+struct BitmapCompactor {
+    DevBuf<u32> tile_count;
+    DevBuf<u64> tile_off;
+    DevBuf<u64> total;
+    u64 n_bits = 0, tiles = 0;
+    const u32* bits = nullptr;
+    cudaStream_t st = nullptr;
+    // phase 1: count
+    u64 count(const u32* bits_, u64 n_bits_, cudaStream_t s) {
+        bits = bits_; n_bits = n_bits_; st = s;
+        const u64 n_words = (n_bits + 31) / 32;
+        tiles = div_up(n_words ? n_words : 1, BC_TILE_WORDS);
+        tile_count.alloc(tiles, st);
+        tile_off.alloc(tiles, st);
+        total.alloc(1, st);
+        bitmap_count_kernel<<<(unsigned)tiles, BC_THREADS, 0, st>>>(bits, n_bits, tile_count.p);
+        GRL_KERNEL_CHECK();
+        exclusive_scan<u32, u64>(tile_count.p, tile_off.p, tiles, total.p, st);
+        u64 h = 0;
+        GRL_CUDA(cudaMemcpyAsync(&h, total.p, sizeof(u64), cudaMemcpyDeviceToHost, st));
+        GRL_CUDA(cudaStreamSynchronize(st));
+        return h;
+    }
+    // phase 2: write positions
+    template <class PosT>
+    void write(const u32* prev_bits, PosT* out) {
+        bitmap_write_kernel<PosT><<<(unsigned)tiles, BC_THREADS, 0, st>>>(bits, prev_bits, n_bits, tile_off.p, out);
+        GRL_KERNEL_CHECK();
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// LSD radix sort of (u64 key, u32 value) pairs on key bits [0, n_bits), 8 bits per pass, stable.
+// Per pass: per-tile digit histogram -> exclusive scan of the digit-major table -> ranked scatter
+// through shared memory (writes of one digit from one tile are contiguous).
+// ------------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_WARP_ITEMS = RS_TILE / RS_WARPS;  // 512
+constexpr size_t RS_SMEM = (size_t)RS_TILE * (sizeof(u64) + sizeof(u32)) + (size_t)RS_WARPS * 257 * sizeof(u32) + 2 * 256 * sizeof(u32) + 34 * sizeof(u32);
+
+static __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const u64* __restrict__ keys, u64 n, int shift, u32* __restrict__ hist, u64 tiles) {
+    __shared__ u32 cnt[256];
+    cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const u64 base = (u64)blockIdx.x * RS_TILE;
+#pragma unroll 4
+    for (int i = 0; i < RS_ITEMS; i++) {
+        const u64 idx = base + (u64)i * RS_THREADS + threadIdx.x;
+        if (idx < n) atomicAdd(&cnt[(u32)(keys[idx] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(u64)threadIdx.x * tiles + blockIdx.x] = cnt[threadIdx.x];
+}
+
+static __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in,
+                                                                          u64* __restrict__ keys_out, u32* __restrict__ vals_out, u64 n, int shift,
+                                                                          const u64* __restrict__ goff, u64 tiles) {
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    u64* s_keys = (u64*)rs_smem;
+    u32* s_vals = (u32*)(s_keys + RS_TILE);
+    u32* s_cnt = s_vals + RS_TILE;            // [RS_WARPS][257]
+    u32* s_dstart = s_cnt + RS_WARPS * 257;   // [256] tile-local start of each digit
+    u32* s_scan = s_dstart + 256;             // 33 scratch  (then s_goff_lo.. below)
+    __shared__ u64 s_goff[256];
+
+    const u32 lane = lane_id(), warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < RS_WARPS * 257; i += RS_THREADS) s_cnt[i] = 0;
+    __syncthreads();
+
+    const u64 tile_base = (u64)blockIdx.x * RS_TILE;
+    u64 key[RS_ITEMS];
+    u32 val[RS_ITEMS];
+    u32 rnk[RS_ITEMS];
+    u32* wc = s_cnt + warp * 257;
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        const u64 idx = tile_base + (u64)warp * RS_WARP_ITEMS + (u64)r * 32 + lane;
+        const bool ok = idx < n;
+        key[r] = ok ? keys_in[idx] : ~0ULL;
+        val[r] = ok ? vals_in[idx] : 0u;
+        const u32 d = ok ? ((u32)(key[r] >> shift) & 255u) : 256u;
+        const u32 m = __match_any_sync(0xffffffffu, d);
+        const u32 b = wc[d];
+        __syncwarp();
+        if (lane == (u32)(__ffs(m) - 1)) wc[d] = b + __popc(m);
+        __syncwarp();
+        rnk[r] = b + __popc(m & lanemask_lt());
+    }
+    __syncthreads();
+    // per digit: exclusive prefix over warps, tile count
+    {
+        const u32 d = threadIdx.x;
+        u32 run = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) {
+            u32 t = s_cnt[w * 257 + d];
+            s_cnt[w * 257 + d] = run;
+            run += t;
+        }
+        u32 tot;
+        u32 ex = block_exclusive_sum<u32>(run, s_scan, tot);
+        s_dstart[d] = ex;
+        s_goff[d] = goff[(u64)d * tiles + blockIdx.x];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        const u64 idx = tile_base + (u64)warp * RS_WARP_ITEMS + (u64)r * 32 + lane;
+        if (idx < n) {
+            const u32 d = (u32)(key[r] >> shift) & 255u;
+            const u32 pos = s_dstart[d] + wc[d] + rnk[r];
+            s_keys[pos] = key[r];
+            s_vals[pos] = val[r];
+        }
+    }
+    __syncthreads();
+    const u64 rem = n - tile_base;
+    const u32 valid = rem < (u64)RS_TILE ? (u32)rem : (u32)RS_TILE;
+    for (u32 i = threadIdx.x; i < valid; i += RS_THREADS) {
+        const u64 k = s_keys[i];
+        const u32 d = (u32)(k >> shift) & 255u;
+        const u64 g = s_goff[d] + (i - s_dstart[d]);
+        keys_out[g] = k;
+        vals_out[g] = s_vals[i];
+    }
+}
+
+// Sorts in place logically: on return *keys / *vals point at the buffers holding the sorted data
+// (either the inputs or the alternates).
+inline void radix_sort_pairs(u64** keys, u32** vals, u64** keys_alt, u32** vals_alt, u64 n, int n_bits, cudaStream_t st) {
+    if (n <= 1 || n_bits <= 0) return;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GRL_CUDA(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM));
+        attr_set = true;
+    }
+    const u64 tiles = div_up(n, RS_TILE);
+    DevBuf<u32> hist(256 * tiles, st);
+    DevBuf<u64> goff(256 * tiles, st);
+    for (int shift = 0; shift < n_bits; shift += 8) {
+        radix_hist_kernel<<<(unsigned)tiles, RS_THREADS, 0, st>>>(*keys, n, shift, hist.p, tiles);
+        GRL_KERNEL_CHECK();
+        exclusive_scan<u32, u64>(hist.p, goff.p, 256 * tiles, nullptr, st);
+        radix_scatter_kernel<<<(unsigned)tiles, RS_THREADS, RS_SMEM, st>>>(*keys, *vals, *keys_alt, *vals_alt, n, shift, goff.p, tiles);
+        GRL_KERNEL_CHECK();
+        u64* tk = *keys; *keys = *keys_alt; *keys_alt = tk;
+        u32* tv = *vals; *vals = *vals_alt; *vals_alt = tv;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// max-reduction of a u64 array into *out (device, must be zeroed by the caller)
+// ------------------------------------------------------------------------------------------------
+static __global__ void reduce_max_u64_kernel(const u64* __restrict__ in, u64 n, u64* out) {
+    u64 m = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) m = in[i] > m ? in[i] : m;
+    m = warp_max(m);
+    if (lane_id() == 0 && m) atomicMax(out, m);
+}
+
+}  // namespace grl

@@ -1,0 +1,100 @@
+// C entry points of the host side (include/grlbwt.h): whole BCR BWT construction for callers that
+// cannot include the C++ templates of grl_bwt.hpp (tests, bench.py through ctypes).
+#include "../../include/grlbwt.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "grl_bwt.hpp"
+
+static thread_local std::string g_last_error;
+
+extern "C" {
+
+int grlbwt_build(const void* text, uint64_t n_syms, int sym_bytes, int device, int n_threads, int verbose, grlbwt_result_t* out) {
+    if (!text || !out || n_syms == 0) return GRLGPU_ERR_ARG;
+    memset(out, 0, sizeof(*out));
+    try {
+        grlbwt::BwtResult r = grlbwt::build_bwt(text, n_syms, sym_bytes, device, (size_t)(n_threads > 0 ? n_threads : 1), verbose != 0);
+        out->n_runs = r.runs.size();
+        out->sb = r.sb;
+        out->fb = r.fb;
+        out->syms = (uint64_t*)malloc((r.runs.size() ? r.runs.size() : 1) * sizeof(uint64_t));
+        out->lens = (uint64_t*)malloc((r.runs.size() ? r.runs.size() : 1) * sizeof(uint64_t));
+        if (!out->syms || !out->lens) { free(out->syms); free(out->lens); g_last_error = "out of host memory"; return -100; }
+        memcpy(out->syms, r.runs.sym.data(), r.runs.size() * sizeof(uint64_t));
+        memcpy(out->lens, r.runs.len.data(), r.runs.size() * sizeof(uint64_t));
+        out->n_rounds = r.parse.rounds.size();
+        out->h2d_ms = r.parse.h2d_ms;
+        out->par_phase_ms = r.parse.par_ms;
+        out->ind_phase_ms = r.ind_ms;
+        for (const auto& rd : r.parse.rounds) { out->device_ms += rd.device_ms; out->algorithmic_bytes += rd.algorithmic_bytes; }
+        return GRLGPU_OK;
+    } catch (const grlbwt::GpuError& e) {
+        g_last_error = e.what();
+        return e.status;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return -100;
+    }
+}
+
+void grlbwt_free_result(grlbwt_result_t* r) {
+    if (!r) return;
+    free(r->syms);
+    free(r->lens);
+    r->syms = r->lens = nullptr;
+    r->n_runs = 0;
+}
+
+int grlbwt_build_file(const char* input_file, const char* output_file, int sym_bytes, int device, int n_threads, int verbose) {
+    if (!input_file || !output_file) return GRLGPU_ERR_ARG;
+    try {
+        std::vector<unsigned char> buf = grlbwt::read_whole_file(input_file);
+        if (buf.empty() || buf.size() % (size_t)sym_bytes) return GRLGPU_ERR_ILL_FORMED;
+        grlbwt::BwtResult r = grlbwt::build_bwt(buf.data(), buf.size() / (size_t)sym_bytes, sym_bytes, device, (size_t)(n_threads > 0 ? n_threads : 1), verbose != 0);
+        grlbwt::write_rl_bwt(output_file, r.runs.sym.data(), r.runs.len.data(), r.runs.size(), r.sb, r.fb);
+        return GRLGPU_OK;
+    } catch (const grlbwt::GpuError& e) {
+        g_last_error = e.what();
+        return e.status;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return -100;
+    }
+}
+
+const char* grlbwt_last_error(void) { return g_last_error.c_str(); }
+
+// host induction alone, from caller-provided level artefacts (CPU-only self test of ind_phase.hpp)
+int grlbwt_selftest_induce(int n_levels, const uint64_t* alphabet, const uint64_t* tot, const uint64_t* const* rule_l, const uint64_t* const* rule_r,
+                           const uint8_t* const* has_hocc, const uint64_t* n_pre, const uint64_t* const* pre_sym, const uint64_t* const* pre_len,
+                           const uint64_t* final_parse, uint64_t n_strings, grlbwt_result_t* out) {
+    try {
+        std::vector<grlbwt::Level> levels((size_t)n_levels);
+        for (int i = 0; i < n_levels; i++) {
+            grlbwt::Level& L = levels[(size_t)i];
+            L.alphabet = alphabet[i];
+            L.tot_phrases = tot[i];
+            L.rule_l.assign(rule_l[i], rule_l[i] + tot[i]);
+            L.rule_r.assign(rule_r[i], rule_r[i] + tot[i]);
+            L.has_hocc.assign(has_hocc[i], has_hocc[i] + tot[i]);
+            L.pre_sym.assign(pre_sym[i], pre_sym[i] + n_pre[i]);
+            L.pre_len.assign(pre_len[i], pre_len[i] + n_pre[i]);
+        }
+        grlbwt::RunList r = grlbwt::ind_phase<uint64_t>(levels, final_parse, n_strings);
+        memset(out, 0, sizeof(*out));
+        out->n_runs = r.size();
+        out->syms = (uint64_t*)malloc((r.size() ? r.size() : 1) * sizeof(uint64_t));
+        out->lens = (uint64_t*)malloc((r.size() ? r.size() : 1) * sizeof(uint64_t));
+        memcpy(out->syms, r.sym.data(), r.size() * sizeof(uint64_t));
+        memcpy(out->lens, r.len.data(), r.size() * sizeof(uint64_t));
+        return 0;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return -100;
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,68 @@
+// .rl_bwt run-length BWT format (bit-exact contract, reference include/bwt_io.h:184,377-382,448-490,541-550):
+// bytes 0-7 sb (u64 LE), bytes 8-15 fb (u64 LE), then r records of sb symbol bytes + fb length bytes, LE.
+// Fresh sequential writer/reader; the reference's in-place block cache is not needed here.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace grlbwt {
+
+inline int sym_width(uint64_t v) { return v == 0 ? 0 : 64 - __builtin_clzll(v); }  // cdt_common.cpp:6-9
+inline uint64_t int_ceil(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+struct RunList {
+    std::vector<uint64_t> sym, len;
+    size_t size() const { return sym.size(); }
+    // appends, merging with the previous run when the symbol repeats (bwt_io.h:448-498 call sites)
+    inline void push(uint64_t s, uint64_t l) {
+        if (l == 0) return;
+        if (!sym.empty() && sym.back() == s) { len.back() += l; return; }
+        sym.push_back(s);
+        len.push_back(l);
+    }
+};
+
+inline void write_rl_bwt(const std::string& path, const uint64_t* sym, const uint64_t* len, uint64_t n_runs, uint64_t sb, uint64_t fb) {
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) throw std::runtime_error("cannot open " + path + " for writing");
+    const size_t rec = sb + fb;
+    std::vector<unsigned char> buf;
+    buf.reserve((size_t)1 << 24);
+    uint64_t hdr[2] = {sb, fb};
+    bool ok = fwrite(hdr, 8, 2, f) == 2;
+    for (uint64_t i = 0; i < n_runs && ok; i++) {
+        unsigned char tmp[16];
+        memcpy(tmp, &sym[i], sb);       // little endian hosts only
+        memcpy(tmp + sb, &len[i], fb);
+        buf.insert(buf.end(), tmp, tmp + rec);
+        if (buf.size() + rec > buf.capacity()) { ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size(); buf.clear(); }
+    }
+    if (ok && !buf.empty()) ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) throw std::runtime_error("short write on " + path);
+}
+
+inline void read_rl_bwt(const std::string& path, RunList& out, uint64_t& sb, uint64_t& fb) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) throw std::runtime_error("cannot open " + path);
+    uint64_t hdr[2];
+    if (fread(hdr, 8, 2, f) != 2) { fclose(f); throw std::runtime_error("truncated header in " + path); }
+    sb = hdr[0]; fb = hdr[1];
+    if (sb == 0 || sb > 8 || fb == 0 || fb > 8) { fclose(f); throw std::runtime_error("bad header in " + path); }
+    unsigned char rec[16];
+    out.sym.clear(); out.len.clear();
+    while (fread(rec, 1, sb + fb, f) == sb + fb) {
+        uint64_t s = 0, l = 0;
+        memcpy(&s, rec, sb);
+        memcpy(&l, rec + sb, fb);
+        out.sym.push_back(s);
+        out.len.push_back(l);
+    }
+    fclose(f);
+}
+
+}  // namespace grlbwt

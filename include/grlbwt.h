@@ -1,0 +1,46 @@
+/*
+ * grlbwt.h -- C entry points of the host side (libgrlbwt.so): the whole BCR BWT construction
+ * (device parse phase through include/grlgpu.h + host induction phase + .rl_bwt writer).
+ * Mirrors grl_bwt_algo<sym_type,false>() of the reference (include/grl_bwt.hpp:23-79) for
+ * callers that cannot include C++ templates (tests, Python via ctypes).
+ */
+#ifndef GRLBWT_H
+#define GRLBWT_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+    uint64_t n_runs;
+    uint64_t sb, fb;          /* header of the .rl_bwt (bwt_io.h:377-382) */
+    uint64_t* syms;           /* n_runs, malloc'ed; release with grlbwt_free_result */
+    uint64_t* lens;
+    uint64_t n_rounds;
+    double h2d_ms;            /* host -> device copy of the text */
+    double par_phase_ms;      /* device parse rounds + fetch of the level artefacts */
+    double ind_phase_ms;      /* host induction */
+    double device_ms;         /* sum of CUDA-event round times */
+    uint64_t algorithmic_bytes; /* sum of B_r over the rounds */
+} grlbwt_result_t;
+
+/* BWT of a collection held in host memory; status codes of grlgpu.h (or -100 for host-side errors) */
+int grlbwt_build(const void* text, uint64_t n_syms, int sym_bytes, int device, int n_threads, int verbose, grlbwt_result_t* out);
+void grlbwt_free_result(grlbwt_result_t* r);
+
+/* same as the CLI: TEXT file -> .rl_bwt file (main.cpp:98-154 + grl_bwt.hpp:23-79) */
+int grlbwt_build_file(const char* input_file, const char* output_file, int sym_bytes, int device, int n_threads, int verbose);
+
+const char* grlbwt_last_error(void);
+
+/* self test of the host induction phase alone (no device): levels given as parallel arrays,
+ * level 0 = round 1; fills out->syms / out->lens / out->n_runs */
+int grlbwt_selftest_induce(int n_levels, const uint64_t* alphabet, const uint64_t* tot, const uint64_t* const* rule_l, const uint64_t* const* rule_r,
+                           const uint8_t* const* has_hocc, const uint64_t* n_pre, const uint64_t* const* pre_sym, const uint64_t* const* pre_len,
+                           const uint64_t* final_parse, uint64_t n_strings, grlbwt_result_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

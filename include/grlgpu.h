@@ -1,0 +1,120 @@
+/*
+ * grlgpu.h -- C ABI of the B200 (sm_100a) parse phase of grlBWT.
+ *
+ * The reference (ddiazdom/grlBWT) has no FFI: the path sits behind C++ templates. This header is the
+ * boundary a maintainer binds instead of those templates; every entry point cites the reference
+ * interface it replaces (paths relative to the reference tree). Conventions: plain pointers and
+ * sizes, caller-owned buffers, int status (0 = ok, < 0 = grlgpu_status), no exceptions and no
+ * exit() across the boundary, one context driven by one host thread, one context per GPU.
+ * There is no CPU fallback: every call fails with GRLGPU_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef GRLGPU_H
+#define GRLGPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct grlgpu_ctx grlgpu_ctx;
+
+enum grlgpu_status {
+    GRLGPU_OK = 0,
+    GRLGPU_ERR_ARG = -1,        /* bad argument (null pointer, symbol width not in {1,2,4,8}, empty text) */
+    GRLGPU_ERR_ILL_FORMED = -2, /* "Error: the file is ill formed" (external/cdt/lib/utils.cpp:177-180) */
+    GRLGPU_ERR_CUDA = -3,       /* CUDA runtime error / no device */
+    GRLGPU_ERR_NOMEM = -4,      /* device memory exhausted */
+    GRLGPU_ERR_STATE = -5,      /* call out of order (no text, phase already finished, ...) */
+    GRLGPU_ERR_LIMIT = -6       /* dictionary of one round exceeds 2^32 symbols or the table 2^31 slots */
+};
+
+/* flags of grlgpu_create */
+#define GRLGPU_FLAG_SMALL_TABLE 1ull /* tests: start the phrase table tiny so the regrow path runs */
+#define GRLGPU_FLAG_FORCE_SLOW_SCAN 2ull /* tests: always take the long-run (summary/resolve) LMS path */
+#define GRLGPU_FLAG_KEEP_DICT 4ull /* tests: keep the last round's dictionary for grlgpu_fetch_dictionary */
+
+/* = str_collection (external/cdt/include/utils.h:20-28) as filled by collection_stats (utils.cpp:100-189) */
+typedef struct {
+    uint64_t n_syms;
+    uint64_t n_strings;
+    uint64_t longest_string;
+    uint64_t min_sym;
+    uint64_t max_sym;
+    uint64_t max_sym_freq; /* byte alphabet: highest histogram count; wider alphabets: n_syms (utils.cpp:117) */
+    uint64_t sep_sym;
+} grlgpu_stats_t;
+
+/* what one parse round reports (the "Stats:" block of par_round, lib/exact_algo/exact_par_phase.cpp:484-488,
+ * plus the sizes the caller needs to fetch the level's artefacts) */
+typedef struct {
+    uint64_t round;          /* 1-based */
+    uint64_t n_in;           /* cells of the round's input text */
+    uint64_t n_strings;
+    uint64_t parse_len;      /* p: phrase occurrences = cells of the output parse ("Parse size") */
+    uint64_t n_phrases;      /* d: distinct phrases ("Parsing phrases") */
+    uint64_t dict_syms;      /* sum of phrase lengths ("Number of symbols in the phrases") */
+    uint64_t max_freq;       /* highest phrase frequency */
+    uint64_t alphabet;       /* A: alphabet size of the input text (= tot_phrases of the previous round) */
+    uint64_t tot_phrases;    /* ranks handed out = "Number of unsolved BWT blocks" */
+    uint64_t n_pre_runs;     /* runs of the preliminary BWT of this level */
+    uint64_t algorithmic_bytes; /* B_r = n*w + p*w' + dict_syms*w + 8*d */
+    uint32_t cell_bytes_in;  /* w  */
+    uint32_t cell_bytes_out; /* w' by sym_width(tot_phrases)+1 (exact_par_phase.cpp:456-465) */
+    uint32_t sym_bytes;      /* element width (4 or 8) of rule_l / rule_r / pre_sym in grlgpu_fetch_level */
+    uint32_t done;           /* 1 when parse_len == n_strings (exact_par_phase.cpp:496) */
+    float device_ms;         /* CUDA-event time of the whole round on the context's stream */
+    float text_pass_ms;      /* of which: boundary scan + compaction + dedup (text read) */
+    float dict_ms;           /* of which: dictionary gather + suffix ordering + ranks + rules */
+    float rewrite_ms;        /* of which: rewrite */
+} grlgpu_round_t;
+
+/* context on one device. replaces: construction of the parse strategy (exact_par_phase.cpp:265-283) */
+int grlgpu_create(grlgpu_ctx** ctx, int device, uint64_t flags);
+int grlgpu_destroy(grlgpu_ctx* ctx);
+
+/* round-1 input, caller-owned HOST memory, copied to the device. replaces: i_file_stream over the
+ * input file (external/cdt/include/file_streams.hpp:93-105) */
+int grlgpu_set_text(grlgpu_ctx* ctx, const void* text, uint64_t n_syms, int sym_bytes);
+/* same, text already resident in DEVICE memory (16-byte aligned); borrowed, not copied, never written */
+int grlgpu_set_text_device(grlgpu_ctx* ctx, const void* dev_text, uint64_t n_syms, int sym_bytes);
+
+/* replaces: collection_stats<sym_type>() (utils.cpp:100-189); validates sep == min && last == sep */
+int grlgpu_stats(grlgpu_ctx* ctx, grlgpu_stats_t* out);
+
+/* one parse round on the device. replaces: par_round<strategy>() (exact_par_phase.cpp:374-497):
+ * get_phrases (parsing_strategies.h:244-275 / :618-642), dictionary + process_dictionary
+ * (exact_par_phase.hpp:106-183, exact_par_phase.cpp:97-263), metasymbol assignment (:427-450),
+ * parse_text (parsing_strategies.h:388-497 / :644-676). The new parse stays on the device. */
+int grlgpu_round(grlgpu_ctx* ctx, grlgpu_round_t* out);
+
+/* artefacts of the last round for the induction phase, copied to caller-owned host buffers.
+ * replaces: files dict_lev_k (exact_par_phase.hpp:189-203) and pre_bwt_lev_k (exact_par_phase.cpp:150-155).
+ *   rule_l, rule_r : tot_phrases elements of sym_bytes each (dict[2u], dict[2u+1] of produce_grammar,
+ *                    numeric conventions of exact_par_phase.cpp:19-20: alphabet A+3, dummy A+3+tot+1)
+ *   has_hocc       : tot_phrases bytes (phrases_has_hocc)
+ *   pre_sym/len    : n_pre_runs runs, maximal; dummies A+1 (from BWT i+1) and A+2 (from hocc buffer)
+ * any pointer may be NULL to skip that array. */
+int grlgpu_fetch_level(grlgpu_ctx* ctx, void* rule_l, void* rule_r, uint8_t* has_hocc, void* pre_sym, uint64_t* pre_len);
+
+/* current parse (output of the last round): parse_len cells of cell_bytes_out bytes, cells = rank<<1|rep.
+ * replaces: file tmp_input (exact_par_phase.cpp:307-308); after the last round this is the final parse
+ * consumed by parse2bwt (exact_ind_phase.cpp:603-672) */
+int grlgpu_fetch_parse(grlgpu_ctx* ctx, void* dst);
+/* start offset of every string in the current parse, n_strings+1 entries (parsing_info::str_ptrs) */
+int grlgpu_fetch_str_ptrs(grlgpu_ctx* ctx, uint64_t* dst);
+/* dictionary of the last round in insertion-independent form, for tests: phrases listed in the A.2
+ * order; syms: dict_syms u64 values, lens/freqs/metas: n_phrases entries (NULL to skip) */
+int grlgpu_fetch_dictionary(grlgpu_ctx* ctx, uint64_t* syms, uint64_t* lens, uint64_t* freqs, uint64_t* metas);
+
+const char* grlgpu_strerror(int status);
+const char* grlgpu_last_error(const grlgpu_ctx* ctx);
+
+/* self-test hooks for the device primitives the path is built from (host buffers in / out) */
+int grlgpu_selftest_scan(const uint32_t* in, uint64_t n, uint64_t* out_exclusive, uint64_t* total);
+int grlgpu_selftest_sort(uint64_t* keys, uint32_t* vals, uint64_t n, int n_bits);
+int grlgpu_selftest_compact(const uint32_t* bits, const uint32_t* prev_bits, uint64_t n_bits, uint64_t* out, uint64_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRLGPU_H */
