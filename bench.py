@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- parse-phase throughput of the B200 path (BASELINE.json metric: input MB/s to BCR BWT;
+parse-round HBM GB/s vs peak) on the C2 workload: synthetic DNA reads, 150 bp, '\\n'-separated.
+
+A "step" = one pass of the hot path over the collection: collection statistics + every parse round
+(boundary scan, dedup, dictionary ranking, pre-BWT/grammar, rewrite) until each string is one
+metasymbol, i.e. what exact_algo::par_phase does in the reference.
+  value : text already resident in HBM (grlgpu_set_text_device), nothing copied.
+  e2e   : through the C ABI with HOST buffers: pinned text -> device every step, every level's
+          artefacts (rules, hocc marks, preliminary BWT) and the final parse copied back to host.
+  --impl reference : the UNMODIFIED reference parse phase (oracle/_ref/ref_harness = its par_phase,
+          built from /root/reference by oracle/Makefile) on the host cores, on a bounded sample.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "input MB/s to BCR BWT (parse phase: all rounds on device)"
+READ_LEN = 150
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=50_000_000, help="reads per GPU (C2: 50M x 150 bp = 7.55 GB)")
+    ap.add_argument("--sample-reads", type=int, default=100_000, help="reads of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------- reference / CPU baseline
+def cpu_parse_phase(sample_reads, threads, repeats=1):
+    """time the reference's own parse phase on `sample_reads` C2-shaped reads; -> (MB/s, kind, sample description)"""
+    import numpy as np
+    import gen
+    arr = gen.dna_reads(sample_reads, READ_LEN, seed=42)
+    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    desc = f"{sample_reads} reads x {READ_LEN} bp ({arr.nbytes / 1e6:.1f} MB) of the same generator"
+    secs = []
+    if os.path.exists(harness):
+        with tempfile.TemporaryDirectory(dir="/tmp") as td:
+            inp = os.path.join(td, "sample.txt")
+            arr.tofile(inp)
+            for _ in range(repeats):
+                r = subprocess.run([harness, "parse", inp, "1", str(threads), td], capture_output=True, text=True, cwd=td)
+                t = [ln for ln in r.stdout.splitlines() if ln.startswith("PAR_PHASE_SECONDS")]
+                if r.returncode != 0 or not t:
+                    raise RuntimeError("reference harness failed: " + (r.stdout + r.stderr)[-400:])
+                secs.append(float(t[0].split()[1]))
+        return [arr.nbytes / 1e6 / s for s in secs], "reference", desc + f"; reference par_phase, -t {threads}", threads
+    from oracle import oracle as O  # port (single thread)
+    for _ in range(repeats):
+        t0 = time.time()
+        o = O.Oracle(arr)
+        o.par_phase()
+        secs.append(time.time() - t0)
+        o.close()
+    return [arr.nbytes / 1e6 / s for s in secs], "port", desc + "; oracle/oracle.c restatement, 1 thread", 1
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    total = args.warmup + args.steps
+    rates, kind, desc, cores = cpu_parse_phase(args.sample_reads, threads, repeats=total)
+    timed = rates[args.warmup:]
+    sample_mb = args.sample_reads * (READ_LEN + 1) / 1e6
+    ms = [sample_mb / r * 1e3 for r in timed]
+    val = sample_mb * len(timed) / (sum(ms) / 1e3)
+    line = {"impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": "MB/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(sum(ms) / len(ms), 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic", "config": {"workload": f"C2-shaped sample: {desc}", "timing": "host wall clock inside the harness"},
+            "cpu_baseline": {"value": round(val, 3), "unit": "MB/s", "cores": cores, "kind": kind, "sample": desc},
+            "e2e": {"value": round(val, 3), "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([x.strip() for x in ln.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------- our arm
+def make_reads_on_device(torch, n_reads, seed, device):
+    """C2 generator on the device (uniform ACGT + '\\n'); same shape as tests/gen.dna_reads, torch RNG"""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=device)
+    out = torch.empty((n_reads, READ_LEN + 1), dtype=torch.uint8, device=device)
+    chunk = 2_000_000
+    for i in range(0, n_reads, chunk):
+        j = min(n_reads, i + chunk)
+        idx = torch.randint(0, 4, (j - i, READ_LEN), generator=g, device=device, dtype=torch.int64)
+        out[i:j, :READ_LEN] = lut[idx]
+        del idx
+    out[:, READ_LEN] = 10
+    return out.reshape(-1)
+
+
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import grlbwt_b200 as G
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the parse phase has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json (measured copy)") if "hbm_gbs" in peaks else (6650.0, "fallback 6.65 TB/s")
+
+    text = make_reads_on_device(torch, args.reads, 42 + rank, dev)
+    n = text.numel()
+    torch.cuda.synchronize()
+    stream = torch.cuda.Stream(device=dev)   # the library issues every kernel on this stream, so torch events bracket it
+    torch.cuda.set_stream(stream)
+    ctx = G.GrlGpu(local_rank, 0, stream=stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(collect=None):
+        ctx.set_text_device(text.data_ptr(), n, 1)
+        ctx.stats()
+        while True:
+            r = ctx.round()
+            if collect is not None:
+                collect.append(r.as_dict())
+            if r.done:
+                return
+
+    # ---- value: text resident in HBM ----
+    for _ in range(args.warmup):
+        step_resident()
+    rounds_info = []
+    step_resident(rounds_info)           # untimed: per-round figures with per-kernel CUDA-event timing enabled
+    ctx.profile_reset(); ctx.profile_enable(True)
+    step_resident()
+    prof = ctx.profile()
+    ctx.profile_enable(False); ctx.profile_reset()
+
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+    e1.record(stream)
+    barrier()
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    value = world * n * args.steps / 1e6 / (ms_total / 1e3)
+
+    # ---- e2e: host buffers through the C ABI ----
+    e2e = None
+    if not args.no_e2e:
+        host_text = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        host_text.copy_(text)
+        torch.cuda.synchronize()
+        host_np = host_text.numpy()
+        d2h_bytes = [0]
+
+        def step_e2e():
+            ctx.set_text(host_np)
+            ctx.stats()
+            b = 0
+            while True:
+                r = ctx.round()
+                L = ctx.fetch_level()
+                b += r.tot_phrases * (2 * r.sym_bytes + 1) + r.n_pre_runs * (r.sym_bytes + 8)
+                if r.done:
+                    fp = ctx.fetch_parse()
+                    b += fp.nbytes
+                    d2h_bytes[0] = b
+                    return
+                del L
+
+        for _ in range(max(1, min(args.warmup, 1))):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_e2e()
+        e1.record(stream)
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        if world > 1:
+            t = torch.tensor([wall_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            wall_ms = float(t.item())
+        e2e = {"value": round(world * n * args.steps / 1e6 / (wall_ms / 1e3), 3), "unit": "MB/s", "h2d_bytes_per_step": int(n),
+               "d2h_bytes_per_step": int(d2h_bytes[0]), "ms_per_step": round(wall_ms / args.steps, 3),
+               "timing": "host wall clock between stream synchronisations (fetches are host-blocking)"}
+    ctx.close()
+
+    # ---- roofline of the dominant kernel (CUDA events on the launch stream, live, one profiled step) ----
+    roof = None
+    if prof:
+        name, (nl, ms, by) = max(prof.items(), key=lambda kv: kv[1][1])
+        achieved = by / 1e9 / (ms / 1e3) if ms > 0 else 0.0
+        roof = {"bound": "hbm", "kernel": name, "launches_per_step": nl, "avg_launch_ms": round(ms / max(nl, 1), 4), "achieved": round(achieved, 1),
+                "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+                "share_of_step": round(ms / sum(v[1] for v in prof.values()), 4),
+                "bytes_model": "expected DRAM bytes of the kernel's launches (SURVEY.md 8d traffic table; DESIGN.md kernels section)"}
+    alg_bytes = sum(r["algorithmic_bytes"] for r in rounds_info)
+    round_ms = sum(r["device_ms"] for r in rounds_info)
+    parse_rounds = {"algorithmic_GB": round(alg_bytes / 1e9, 3), "device_ms": round(round_ms, 3),
+                    "achieved_GBps": round(alg_bytes / 1e6 / round_ms, 1) if round_ms else None,
+                    "frac_of_measured_peak": round(alg_bytes / 1e6 / round_ms / hbm_peak, 4) if round_ms else None,
+                    "frac_of_nominal_8TBps": round(alg_bytes / 1e6 / round_ms / 8000.0, 4) if round_ms else None,
+                    "per_round": [{k: (round(v, 3) if isinstance(v, float) else v) for k, v in r.items()
+                                   if k in ("round", "n_in", "parse_len", "n_phrases", "dict_syms", "tot_phrases", "device_ms", "text_pass_ms", "dict_ms",
+                                            "rewrite_ms", "algorithmic_bytes")} for r in rounds_info]}
+    kernels = {k: {"launches": v[0], "ms": round(v[1], 3), "model_GBps": round(v[2] / 1e6 / v[1], 1) if v[1] > 0 else None}
+               for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:10]}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            rates, kind, desc, cores = cpu_parse_phase(args.sample_reads, os.cpu_count() or 1, repeats=1)
+            cpu = {"value": round(rates[0], 3), "unit": "MB/s", "cores": cores, "kind": kind, "sample": desc}
+        except Exception as e:  # the baseline is reporting only
+            cpu = {"value": None, "unit": "MB/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": round(value, 3), "unit": "MB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+                "data": "synthetic",
+                "config": {"workload": f"C2: {args.reads} reads x {READ_LEN} bp uniform ACGT + newline per GPU ({n / 1e9:.3f} GB), BASELINE.json configs[1]",
+                           "reads_per_gpu": args.reads, "cache": "inputs (>= 302 MB per round-1 pass at the default size 7.55 GB) exceed the 126 MB L2",
+                           "parallelism": "1 GPU" if world == 1 else f"{world} ranks, one independent collection per rank (no cross-rank dictionary exchange yet)"},
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parse_rounds": parse_rounds,
+                "kernels": kernels}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

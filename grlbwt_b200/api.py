@@ -66,6 +66,12 @@ def lib_gpu():
         L.grlgpu_strerror.argtypes = [C.c_int]
         L.grlgpu_last_error.restype = C.c_char_p
         L.grlgpu_last_error.argtypes = [vp]
+        L.grlgpu_create_on_stream.argtypes = [C.POINTER(vp), C.c_int, u64, vp]
+        L.grlgpu_profile_enable.argtypes = [vp, C.c_int]
+        L.grlgpu_profile_reset.argtypes = [vp]
+        L.grlgpu_launch_count.argtypes = [vp]
+        L.grlgpu_launch_count.restype = u64
+        L.grlgpu_profile_entry.argtypes = [vp, C.c_int, C.c_char_p, C.c_int, C.POINTER(u64), C.POINTER(C.c_double), C.POINTER(u64)]
         L.grlgpu_selftest_scan.argtypes = [vp, u64, vp, vp]
         L.grlgpu_selftest_sort.argtypes = [vp, vp, u64, C.c_int]
         L.grlgpu_selftest_compact.argtypes = [vp, vp, u64, vp, vp]
@@ -97,10 +103,10 @@ class GrlGpu:
     """One device context = the GPU parse strategy (mirrors the duck-typed strategy concept used by
     par_round, exact_par_phase.cpp:374-497: get_phrases / map / parse_text, fused into round())."""
 
-    def __init__(self, device: int = 0, flags: int = 0):
+    def __init__(self, device: int = 0, flags: int = 0, stream: int = 0):
         self._L = lib_gpu()
         self._h = C.c_void_p()
-        self._check(self._L.grlgpu_create(C.byref(self._h), device, flags), ctx=False)
+        self._check(self._L.grlgpu_create_on_stream(C.byref(self._h), device, flags, C.c_void_p(stream) if stream else None), ctx=False)
         self.last = None
         self._keep = None
 
@@ -159,6 +165,25 @@ class GrlGpu:
         freqs, metas = np.zeros(r.n_phrases, np.uint64), np.zeros(r.n_phrases, np.uint64)
         self._check(self._L.grlgpu_fetch_dictionary(self._h, _ptr(syms), _ptr(lens), _ptr(freqs), _ptr(metas)))
         return syms, lens, freqs, metas
+
+    def profile_enable(self, on: bool = True):
+        self._check(self._L.grlgpu_profile_enable(self._h, int(on)))
+
+    def profile_reset(self):
+        self._check(self._L.grlgpu_profile_reset(self._h))
+
+    def launch_count(self) -> int:
+        return int(self._L.grlgpu_launch_count(self._h))
+
+    def profile(self):
+        """-> {kernel name: (launches, total_ms, model_bytes)} measured with CUDA events on the launch stream"""
+        out, i = {}, 0
+        name = C.create_string_buffer(128)
+        n, ms, by = C.c_uint64(), C.c_double(), C.c_uint64()
+        while self._L.grlgpu_profile_entry(self._h, i, name, 128, C.byref(n), C.byref(ms), C.byref(by)) == 0:
+            out[name.value.decode()] = (int(n.value), float(ms.value), int(by.value))
+            i += 1
+        return out
 
     def close(self):
         if self._h:

@@ -18,7 +18,10 @@ struct grlgpu_ctx {
     int device = 0;
     u64 flags = 0;
     cudaStream_t st = nullptr;
+    bool own_stream = true;
     std::string last_error;
+    DevicePool pool;  // declared before every DevBuf member: destroyed after them
+    Profiler prof;
 
     // current text
     const void* text = nullptr;  // device
@@ -161,21 +164,14 @@ void stage_flags(Round& R) {
     const CellT sep = (CellT)c->sep;
     bool slow = (c->flags & GRLGPU_FLAG_FORCE_SLOW_SCAN) != 0;
     if (!slow) {
-        lms_flags_kernel<CellT, FIRST, 0><<<(unsigned)n_blocks, LMS_THREADS, 0, R.st>>>(text, R.n, sep, end_in, end_out, R.start_bits.p, nullptr, nullptr,
-                                                                                        need_slow.p);
-        GRL_KERNEL_CHECK();
+        GRL_LAUNCH("lms_flags", R.n * sizeof(CellT) + R.n / 4, (lms_flags_kernel<CellT, FIRST, 0>), (unsigned)n_blocks, LMS_THREADS, 0, R.st, text, R.n, sep, end_in, end_out, R.start_bits.p, nullptr, nullptr, need_slow.p);
         slow = d2h_scalar(need_slow.p, R.st) != 0;
     }
     if (slow) {  // a run of equal cells crosses a CTA boundary by more than the look-ahead
         DevBuf<u8> state(n_blocks, R.st), incoming(n_blocks, R.st);
-        lms_flags_kernel<CellT, FIRST, 1><<<(unsigned)n_blocks, LMS_THREADS, 0, R.st>>>(text, R.n, sep, end_in, end_out, R.start_bits.p, state.p, nullptr,
-                                                                                        need_slow.p);
-        GRL_KERNEL_CHECK();
-        lms_resolve_kernel<<<1, 32, 0, R.st>>>(state.p, incoming.p, n_blocks);
-        GRL_KERNEL_CHECK();
-        lms_flags_kernel<CellT, FIRST, 2><<<(unsigned)n_blocks, LMS_THREADS, 0, R.st>>>(text, R.n, sep, end_in, end_out, R.start_bits.p, nullptr, incoming.p,
-                                                                                        need_slow.p);
-        GRL_KERNEL_CHECK();
+        GRL_LAUNCH("lms_flags", R.n * sizeof(CellT) + R.n / 4, (lms_flags_kernel<CellT, FIRST, 1>), (unsigned)n_blocks, LMS_THREADS, 0, R.st, text, R.n, sep, end_in, end_out, R.start_bits.p, state.p, nullptr, need_slow.p);
+        GRL_LAUNCH("lms_resolve", 0, lms_resolve_kernel, 1, 32, 0, R.st, state.p, incoming.p, n_blocks);
+        GRL_LAUNCH("lms_flags", R.n * sizeof(CellT) + R.n / 4, (lms_flags_kernel<CellT, FIRST, 2>), (unsigned)n_blocks, LMS_THREADS, 0, R.st, text, R.n, sep, end_in, end_out, R.start_bits.p, nullptr, incoming.p, need_slow.p);
         GRL_CUDA(cudaStreamSynchronize(R.st));
     }
 }
@@ -189,8 +185,7 @@ void stage_dedup(Round& R) {
     R.ps_raw.alloc((R.p + 1) * sizeof(PosT), R.st);
     PosT* ps = (PosT*)R.ps_raw.p;
     bc.write<PosT>(R.end_bits, ps);
-    set_sentinel_kernel<PosT><<<1, 1, 0, R.st>>>(ps, R.p, R.n);
-    GRL_KERNEL_CHECK();
+    GRL_LAUNCH("set_sentinel", 0, (set_sentinel_kernel<PosT>), 1, 1, 0, R.st, ps, R.p, R.n);
     R.start_bits.release();
 
     R.slot_of_phrase.alloc(R.p, R.st);
@@ -203,17 +198,14 @@ void stage_dedup(Round& R) {
     for (;;) {
         if (cap > (1ull << 31)) throw Error(GRLGPU_ERR_LIMIT, "phrase table would exceed 2^31 slots");
         R.table.alloc(cap, R.st);
-        table_init_kernel<<<grid_for(cap, 256), 256, 0, R.st>>>(R.table.p, cap);
-        GRL_KERNEL_CHECK();
+        GRL_LAUNCH("table_init", cap * 16, table_init_kernel, grid_for(cap, 256), 256, 0, R.st, R.table.p, cap);
         overflow.zero();
-        phrase_insert_kernel<CellT, PosT><<<grid_for(R.p, 256), 256, 0, R.st>>>(text, ps, R.p, R.table.p, cap - 1, R.slot_of_phrase.p, overflow.p);
-        GRL_KERNEL_CHECK();
+        GRL_LAUNCH("phrase_insert", (R.n + R.p) * sizeof(CellT) + R.p * (2 * sizeof(PosT) + 4 + 32), (phrase_insert_kernel<CellT, PosT>), grid_for(R.p, 256), 256, 0, R.st, text, ps, R.p, R.table.p, cap - 1, R.slot_of_phrase.p, overflow.p);
         bool ovf = d2h_scalar(overflow.p, R.st) != 0;
         u64 d = 0;
         if (!ovf) {
             DevBuf<u32> occ_bits(cap / 32, R.st);
-            table_occupancy_kernel<<<(unsigned)(cap / 256), 256, 0, R.st>>>(R.table.p, cap, occ_bits.p);
-            GRL_KERNEL_CHECK();
+            GRL_LAUNCH("table_occupancy", cap * 16, table_occupancy_kernel, (unsigned)(cap / 256), 256, 0, R.st, R.table.p, cap, occ_bits.p);
             BitmapCompactor oc;
             d = oc.count(occ_bits.p, cap, R.st);
             if (d * 10 <= cap * 7 || cap >= want) {  // load factor <= 0.7 (or the table can no longer be too small)
@@ -229,8 +221,7 @@ void stage_dedup(Round& R) {
     R.ph_pos.alloc(R.d, R.st);
     R.ph_len.alloc(R.d, R.st);
     R.ph_freq.alloc(R.d, R.st);
-    dict_meta_kernel<PosT><<<grid_for(R.d, 256), 256, 0, R.st>>>(R.table.p, R.occ_slots.p, R.d, ps, R.p, R.ph_pos.p, R.ph_len.p, R.ph_freq.p);
-    GRL_KERNEL_CHECK();
+    GRL_LAUNCH("dict_meta", 0, (dict_meta_kernel<PosT>), grid_for(R.d, 256), 256, 0, R.st, R.table.p, R.occ_slots.p, R.d, ps, R.p, R.ph_pos.p, R.ph_len.p, R.ph_freq.p);
     R.ph_off.alloc(R.d + 1, R.st);
     DevBuf<u64> tot64(1, R.st);
     {   // offsets as u64 first to detect overflow of the 32-bit entry index space
@@ -242,13 +233,11 @@ void stage_dedup(Round& R) {
     exclusive_scan<u32, u32>(R.ph_len.p, R.ph_off.p, R.d, R.ph_off.p + R.d, R.st);
     DevBuf<u64> mx(2, R.st);
     mx.zero();
-    reduce_max_u64_kernel<<<296, 256, 0, R.st>>>(R.ph_freq.p, R.d, mx.p);
-    GRL_KERNEL_CHECK();
+    GRL_LAUNCH("reduce_max_u64", 0, reduce_max_u64_kernel, 296, 256, 0, R.st, R.ph_freq.p, R.d, mx.p);
     {
         DevBuf<u64> len64(R.d, R.st);
-        u32_to_u64_kernel<<<grid_for(R.d, 256), 256, 0, R.st>>>(R.ph_len.p, R.d, len64.p);
-        reduce_max_u64_kernel<<<296, 256, 0, R.st>>>(len64.p, R.d, mx.p + 1);
-        GRL_KERNEL_CHECK();
+        GRL_LAUNCH("u32_to_u64", 0, u32_to_u64_kernel, grid_for(R.d, 256), 256, 0, R.st, R.ph_len.p, R.d, len64.p);
+        GRL_LAUNCH("reduce_max_u64", 0, reduce_max_u64_kernel, 296, 256, 0, R.st, len64.p, R.d, mx.p + 1);
     }
     u64 hmx[2];
     GRL_CUDA(cudaMemcpyAsync(hmx, mx.p, 16, cudaMemcpyDeviceToHost, R.st));
@@ -263,9 +252,7 @@ void stage_gather(Round& R) {
     R.D_raw.alloc((R.nE + 1) * sizeof(SymT), R.st);
     R.phr_of.alloc(R.nE, R.st);
     R.rem.alloc(R.nE, R.st);
-    dict_gather_kernel<CellT, FIRST, SymT><<<grid_for(R.d, 256), 256, 0, R.st>>>((const CellT*)R.c->text, R.ph_pos.p, R.ph_len.p, R.ph_off.p, R.d,
-                                                                                (SymT*)R.D_raw.p, R.phr_of.p, R.rem.p);
-    GRL_KERNEL_CHECK();
+    GRL_LAUNCH("dict_gather", R.nE * (sizeof(CellT) + sizeof(SymT) + 8) + R.d * 16, (dict_gather_kernel<CellT, FIRST, SymT>), grid_for(R.d, 256), 256, 0, R.st, (const CellT*)R.c->text, R.ph_pos.p, R.ph_len.p, R.ph_off.p, R.d, (SymT*)R.D_raw.p, R.phr_of.p, R.rem.p);
 }
 
 // ---------------- dictionary stage: suffix order, groups, ranks, pre-BWT, rules, metasymbols ----------------
@@ -285,25 +272,21 @@ void stage_dict(Round& R) {
     u32 *vp = vals.p, *va = vals_alt.p;
     const int sym_bits = bit_width64(A + 1);
     const int K = std::max(1, 64 / sym_bits);
-    sfx_first_key_kernel<SymT><<<grid_for(nE, 256), 256, 0, st>>>(D, R.rem.p, nE, A + 1, sym_bits, K, kp, vp);
-    GRL_KERNEL_CHECK();
+    GRL_LAUNCH("sfx_first_key", nE * (sizeof(SymT) + 4 + 12), (sfx_first_key_kernel<SymT>), grid_for(nE, 256), 256, 0, st, D, R.rem.p, nE, A + 1, sym_bits, K, kp, vp);
     radix_sort_pairs(&kp, &vp, &ka, &va, nE, std::min(64, sym_bits * K), st);
     u64 G = 0;
     u64 h = (u64)K;
     for (;;) {
-        key_head_flags_kernel<<<grid_for(nE, 256), 256, 0, st>>>(kp, nE, flags.p);
-        GRL_KERNEL_CHECK();
+        GRL_LAUNCH("key_head_flags", 0, key_head_flags_kernel, grid_for(nE, 256), 256, 0, st, kp, nE, flags.p);
         exclusive_scan<u32, u32>(flags.p, excl.p, nE, gcount.p, st);
-        scatter_rank_kernel<<<grid_for(nE, 256), 256, 0, st>>>(flags.p, excl.p, vp, nE, R.rank.p);
-        GRL_KERNEL_CHECK();
+        GRL_LAUNCH("scatter_rank", nE * 16, scatter_rank_kernel, grid_for(nE, 256), 256, 0, st, flags.p, excl.p, vp, nE, R.rank.p);
         const u64 Gn = d2h_scalar(gcount.p, st);
         const bool stable = (Gn == G);
         G = Gn;
         // a key of h codes covers any suffix (<= max_len symbols + terminator) once h > max_len
         if (stable || G == nE || h > R.max_len) break;
         const int rb = bit_width64(G + 1);
-        sfx_double_key_kernel<<<grid_for(nE, 256), 256, 0, st>>>(R.rank.p, R.rem.p, vp, nE, (u32)std::min<u64>(h, 0xffffffffull), (u32)(G + 1), rb, kp);
-        GRL_KERNEL_CHECK();
+        GRL_LAUNCH("sfx_double_key", nE * (4 + 4 + 4 + 4 + 8), sfx_double_key_kernel, grid_for(nE, 256), 256, 0, st, R.rank.p, R.rem.p, vp, nE, (u32)std::min<u64>(h, 0xffffffffull), (u32)(G + 1), rb, kp);
         radix_sort_pairs(&kp, &vp, &ka, &va, nE, 2 * rb, st);
         h *= 2;
     }
@@ -314,12 +297,9 @@ void stage_dict(Round& R) {
     DevBuf<u32> gcnt(G, st), grep(G, st), rflag(G, st), vflag(G, st), rrank(G, st), vidx(G, st);
     DevBuf<u64> gacc(G, st), gmin(G, st), gmax(G, st), psym(G, st);
     gcnt.zero(); gacc.zero(); gmax.zero(); gmin.fill_ff();
-    group_reduce_kernel<SymT><<<grid_for(nE, 256), 256, 0, st>>>(order, R.rank.p, D, R.rem.p, R.phr_of.p, R.ph_off.p, R.ph_freq.p, nE, isuf, gcnt.p, gacc.p,
-                                                                 gmin.p, gmax.p, grep.p);
-    GRL_KERNEL_CHECK();
+    GRL_LAUNCH("group_reduce", nE * 40, (group_reduce_kernel<SymT>), grid_for(nE, 256), 256, 0, st, order, R.rank.p, D, R.rem.p, R.phr_of.p, R.ph_off.p, R.ph_freq.p, nE, isuf, gcnt.p, gacc.p, gmin.p, gmax.p, grep.p);
     const u64 bwt_dummy = A + 1, hocc_dummy = A + 2;  // exact_par_phase.hpp:113-115
-    group_finalize_kernel<<<grid_for(G, 256), 256, 0, st>>>(gcnt.p, gmin.p, gmax.p, G, bwt_dummy, hocc_dummy, rflag.p, vflag.p, psym.p);
-    GRL_KERNEL_CHECK();
+    GRL_LAUNCH("group_finalize", 0, group_finalize_kernel, grid_for(G, 256), 256, 0, st, gcnt.p, gmin.p, gmax.p, G, bwt_dummy, hocc_dummy, rflag.p, vflag.p, psym.p);
     DevBuf<u32> cnt2(2, st);
     exclusive_scan<u32, u32>(rflag.p, rrank.p, G, cnt2.p, st);
     exclusive_scan<u32, u32>(vflag.p, vidx.p, G, cnt2.p + 1, st);
@@ -333,18 +313,15 @@ void stage_dict(Round& R) {
     c->lvl_sym_bytes = sizeof(SymT);
     {
         DevBuf<u64> csym(nV, st), clen(nV, st);
-        prebwt_compact_kernel<<<grid_for(G, 256), 256, 0, st>>>(vflag.p, vidx.p, psym.p, gacc.p, G, csym.p, clen.p);
-        GRL_KERNEL_CHECK();
+        GRL_LAUNCH("prebwt_compact", 0, prebwt_compact_kernel, grid_for(G, 256), 256, 0, st, vflag.p, vidx.p, psym.p, gacc.p, G, csym.p, clen.p);
         DevBuf<u32> hflag(nV, st), hexcl(nV, st), nrun(1, st);
-        key_head_flags_kernel<<<grid_for(nV, 256), 256, 0, st>>>(csym.p, nV, hflag.p);
-        GRL_KERNEL_CHECK();
+        GRL_LAUNCH("key_head_flags", 0, key_head_flags_kernel, grid_for(nV, 256), 256, 0, st, csym.p, nV, hflag.p);
         exclusive_scan<u32, u32>(hflag.p, hexcl.p, nV, nrun.p, st);
         R.n_pre = d2h_scalar(nrun.p, st);
         c->pre_sym.alloc(R.n_pre * sizeof(SymT), st);
         c->pre_len.alloc(R.n_pre, st);
         c->pre_len.zero();
-        prebwt_runs_kernel<SymT><<<grid_for(nV, 256), 256, 0, st>>>(csym.p, clen.p, hflag.p, hexcl.p, nV, (SymT*)c->pre_sym.p, c->pre_len.p);
-        GRL_KERNEL_CHECK();
+        GRL_LAUNCH("prebwt_runs", 0, (prebwt_runs_kernel<SymT>), grid_for(nV, 256), 256, 0, st, csym.p, clen.p, hflag.p, hexcl.p, nV, (SymT*)c->pre_sym.p, c->pre_len.p);
     }
 
     // -- metasymbols, next is_suffix, hocc marks, rules --
@@ -352,16 +329,12 @@ void stage_dict(Round& R) {
     is_suffix_next.zero();
     DevBuf<u32> erank(nE, st);
     erank.fill_ff();
-    entry_finalize_kernel<SymT><<<grid_for(nE, 256), 256, 0, st>>>(R.rank.p, D, R.rem.p, R.phr_of.p, R.ph_off.p, R.ph_freq.p, R.occ_slots.p, nE, isuf, gcnt.p,
-                                                                   rflag.p, rrank.p, R.table.p, is_suffix_next.p, erank.p);
-    GRL_KERNEL_CHECK();
+    GRL_LAUNCH("entry_finalize", nE * 32, (entry_finalize_kernel<SymT>), grid_for(nE, 256), 256, 0, st, R.rank.p, D, R.rem.p, R.phr_of.p, R.ph_off.p, R.ph_freq.p, R.occ_slots.p, nE, isuf, gcnt.p, rflag.p, rrank.p, R.table.p, is_suffix_next.p, erank.p);
     c->rule_l.alloc(tot * sizeof(SymT), st);
     c->rule_r.alloc(tot * sizeof(SymT), st);
     c->has_hocc.alloc(tot, st);
     const u64 alph3 = A + 3, metasym_dummy = alph3 + tot + 1;  // exact_par_phase.cpp:19-20
-    rules_kernel<SymT><<<grid_for(G, 256), 256, 0, st>>>(gcnt.p, rflag.p, rrank.p, grep.p, G, D, R.rem.p, erank.p, isuf, alph3, metasym_dummy,
-                                                         (SymT*)c->rule_l.p, (SymT*)c->rule_r.p, c->has_hocc.p);
-    GRL_KERNEL_CHECK();
+    GRL_LAUNCH("rules", 0, (rules_kernel<SymT>), grid_for(G, 256), 256, 0, st, gcnt.p, rflag.p, rrank.p, grep.p, G, D, R.rem.p, erank.p, isuf, alph3, metasym_dummy, (SymT*)c->rule_l.p, (SymT*)c->rule_r.p, c->has_hocc.p);
     c->lvl_tot = tot;
     c->lvl_npre = R.n_pre;
 
@@ -378,8 +351,7 @@ template <class OutT>
 void stage_rewrite(Round& R, DevBuf<u8>& new_text, DevBuf<u32>& new_end_bits) {
     new_text.alloc(std::max<u64>(R.p * sizeof(OutT), 16), R.st);
     new_end_bits.alloc(div_up(R.p, 32), R.st);
-    rewrite_kernel<OutT><<<grid_for(R.p, 256), 256, 0, R.st>>>(R.slot_of_phrase.p, R.p, R.table.p, (OutT*)new_text.p, new_end_bits.p);
-    GRL_KERNEL_CHECK();
+    GRL_LAUNCH("rewrite", R.p * (4 + 16 + sizeof(OutT)), (rewrite_kernel<OutT>), grid_for(R.p, 256), 256, 0, R.st, R.slot_of_phrase.p, R.p, R.table.p, (OutT*)new_text.p, new_end_bits.p);
 }
 
 template <class CellT, bool FIRST>
@@ -451,6 +423,7 @@ void run_round_t(grlgpu_ctx* c, grlgpu_round_t* out) {
 
     // the parse becomes the text of the next round
     GRL_CUDA(cudaStreamSynchronize(c->st));
+    c->prof.resolve();
     c->text_own = std::move(new_text);
     c->text = c->text_own.p;
     c->end_bits = std::move(new_end);
@@ -491,8 +464,7 @@ void compute_stats(grlgpu_ctx* c) {
     memset(&h, 0, sizeof(h));
     h.min_sym = ~0ULL;
     GRL_CUDA(cudaMemcpyAsync(acc.p, &h, sizeof(h), cudaMemcpyHostToDevice, c->st));
-    stats_kernel<CellT><<<148 * 8, 256, 0, c->st>>>(text, c->n, sep_c, acc.p);
-    GRL_KERNEL_CHECK();
+    GRL_LAUNCH("stats", 0, (stats_kernel<CellT>), 148 * 8, 256, 0, c->st, text, c->n, sep_c, acc.p);
     GRL_CUDA(cudaMemcpyAsync(&h, acc.p, sizeof(h), cudaMemcpyDeviceToHost, c->st));
     GRL_CUDA(cudaStreamSynchronize(c->st));
     grlgpu_stats_t& s = c->stats;
@@ -514,17 +486,15 @@ void compute_stats(grlgpu_ctx* c) {
     {
         const u64 n_words = div_up(c->n, 32);
         DevBuf<u32> eb(n_words, c->st), sb(n_words, c->st);
-        first_round_end_bits_kernel<CellT><<<grid_for(c->n, 256), 256, 0, c->st>>>(text, c->n, sep_c, eb.p);
-        next_start_bits_kernel<<<grid_for(n_words, 256), 256, 0, c->st>>>(eb.p, c->n, sb.p);
-        GRL_KERNEL_CHECK();
+        GRL_LAUNCH("first_round_end_bits", 0, (first_round_end_bits_kernel<CellT>), grid_for(c->n, 256), 256, 0, c->st, text, c->n, sep_c, eb.p);
+        GRL_LAUNCH("next_start_bits", 0, next_start_bits_kernel, grid_for(n_words, 256), 256, 0, c->st, eb.p, c->n, sb.p);
         BitmapCompactor bc;
         const u64 ns = bc.count(sb.p, c->n, c->st);
         DevBuf<u64> ptrs(ns + 1, c->st), mx(1, c->st);
         bc.write<u64>(nullptr, ptrs.p);
         GRL_CUDA(cudaMemcpyAsync(ptrs.p + ns, &c->n, 8, cudaMemcpyHostToDevice, c->st));
         mx.zero();
-        adjacent_max_diff_kernel<<<296, 256, 0, c->st>>>(ptrs.p, ns, mx.p);
-        GRL_KERNEL_CHECK();
+        GRL_LAUNCH("adjacent_max_diff", 0, adjacent_max_diff_kernel, 296, 256, 0, c->st, ptrs.p, ns, mx.p);
         s.longest_string = d2h_scalar(mx.p, c->st);
     }
     c->sep = s.sep_sym;
@@ -535,6 +505,10 @@ void compute_stats(grlgpu_ctx* c) {
 
 template <class F>
 int guarded(grlgpu_ctx* c, F&& f) {
+    struct CtxGuard {  // per-call binding of the context's launch accounting and memory pool
+        explicit CtxGuard(grlgpu_ctx* x) { g_prof = x ? &x->prof : nullptr; g_pool = x ? &x->pool : nullptr; }
+        ~CtxGuard() { g_prof = nullptr; g_pool = nullptr; }
+    } cg(c);
     try {
         if (c) GRL_CUDA(cudaSetDevice(c->device));
         f();
@@ -554,7 +528,10 @@ int guarded(grlgpu_ctx* c, F&& f) {
 
 extern "C" {
 
-int grlgpu_create(grlgpu_ctx** ctx, int device, uint64_t flags) {
+int grlgpu_create_on_stream(grlgpu_ctx** ctx, int device, uint64_t flags, void* cuda_stream);
+int grlgpu_create(grlgpu_ctx** ctx, int device, uint64_t flags) { return grlgpu_create_on_stream(ctx, device, flags, nullptr); }
+
+int grlgpu_create_on_stream(grlgpu_ctx** ctx, int device, uint64_t flags, void* cuda_stream) {
     if (!ctx) return GRLGPU_ERR_ARG;
     *ctx = nullptr;
     int n_dev = 0;
@@ -563,11 +540,8 @@ int grlgpu_create(grlgpu_ctx** ctx, int device, uint64_t flags) {
     c->device = device;
     c->flags = flags;
     int rc = guarded(c.get(), [&] {
-        GRL_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
-        cudaMemPool_t pool;
-        GRL_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-        u64 thr = ~0ULL;  // keep freed blocks in the pool: rounds reuse them
-        GRL_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        if (cuda_stream) { c->st = (cudaStream_t)cuda_stream; c->own_stream = false; }
+        else GRL_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     });
     if (rc != GRLGPU_OK) return rc;
     *ctx = c.release();
@@ -579,9 +553,10 @@ int grlgpu_destroy(grlgpu_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->st);
     cudaStream_t st = ctx->st;
-    delete ctx;
-    cudaStreamSynchronize(st);
-    cudaStreamDestroy(st);
+    const bool own = ctx->own_stream;
+    ctx->prof.resolve();
+    delete ctx;  // the stream was synchronised above: the pool's slabs are idle
+    if (own) cudaStreamDestroy(st);
     return GRLGPU_OK;
 }
 
@@ -659,8 +634,7 @@ int grlgpu_fetch_str_ptrs(grlgpu_ctx* ctx, uint64_t* dst) {
     return guarded(ctx, [&] {
         const u64 n_words = div_up(ctx->n, 32);
         DevBuf<u32> sb(n_words, ctx->st);
-        next_start_bits_kernel<<<grid_for(n_words, 256), 256, 0, ctx->st>>>(ctx->end_bits.p, ctx->n, sb.p);
-        GRL_KERNEL_CHECK();
+        GRL_LAUNCH("next_start_bits", 0, next_start_bits_kernel, grid_for(n_words, 256), 256, 0, ctx->st, ctx->end_bits.p, ctx->n, sb.p);
         BitmapCompactor bc;
         const u64 ns = bc.count(sb.p, ctx->n, ctx->st);
         if (ns != ctx->n_strings) throw Error(GRLGPU_ERR_STATE, "string count changed between rounds");
@@ -701,6 +675,31 @@ int grlgpu_fetch_dictionary(grlgpu_ctx* ctx, uint64_t* syms, uint64_t* lens, uin
             k++;
         }
     });
+}
+
+int grlgpu_profile_enable(grlgpu_ctx* ctx, int on) {
+    if (!ctx) return GRLGPU_ERR_ARG;
+    ctx->prof.resolve();
+    ctx->prof.timing = on != 0;
+    return GRLGPU_OK;
+}
+int grlgpu_profile_reset(grlgpu_ctx* ctx) {
+    if (!ctx) return GRLGPU_ERR_ARG;
+    ctx->prof.reset();
+    return GRLGPU_OK;
+}
+uint64_t grlgpu_launch_count(const grlgpu_ctx* ctx) { return ctx ? ctx->prof.launches : 0; }
+int grlgpu_profile_entry(grlgpu_ctx* ctx, int index, char* name, int name_cap, uint64_t* launches, double* total_ms, uint64_t* model_bytes) {
+    if (!ctx || !name || name_cap <= 0) return GRLGPU_ERR_ARG;
+    ctx->prof.resolve();
+    if (index < 0 || (size_t)index >= ctx->prof.acc.size()) return 1;
+    auto it = ctx->prof.acc.begin();
+    std::advance(it, index);
+    snprintf(name, (size_t)name_cap, "%s", it->first.c_str());
+    if (launches) *launches = it->second.launches;
+    if (total_ms) *total_ms = it->second.ms;
+    if (model_bytes) *model_bytes = it->second.bytes;
+    return GRLGPU_OK;
 }
 
 const char* grlgpu_strerror(int status) {

@@ -76,17 +76,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const TIn* in,
 template <class TIn, class TOut>
 void exclusive_scan(const TIn* in, TOut* out, u64 n, TOut* total_dev, cudaStream_t st) {
     if (n <= (u64)SCAN_TILE * 4) {
-        scan_single_block_kernel<TIn, TOut><<<1, SCAN_THREADS, 0, st>>>(in, out, n, total_dev);
-        GRL_KERNEL_CHECK();
+        GRL_LAUNCH("scan_single_block", n * (sizeof(TIn) + sizeof(TOut)), (scan_single_block_kernel<TIn, TOut>), 1, SCAN_THREADS, 0, st, in, out, n, total_dev);
         return;
     }
     const u64 tiles = div_up(n, SCAN_TILE);
     DevBuf<TOut> partial(tiles, st);
-    scan_tile_sums_kernel<TIn, TOut><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, partial.p, n);
-    GRL_KERNEL_CHECK();
+    GRL_LAUNCH("scan_tile_sums", n * sizeof(TIn), (scan_tile_sums_kernel<TIn, TOut>), (unsigned)tiles, SCAN_THREADS, 0, st, in, partial.p, n);
     exclusive_scan<TOut, TOut>(partial.p, partial.p, tiles, total_dev, st);
-    scan_apply_kernel<TIn, TOut><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, out, partial.p, n);
-    GRL_KERNEL_CHECK();
+    GRL_LAUNCH("scan_apply", n * (sizeof(TIn) + sizeof(TOut)), (scan_apply_kernel<TIn, TOut>), (unsigned)tiles, SCAN_THREADS, 0, st, in, out, partial.p, n);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -172,8 +169,7 @@ struct BitmapCompactor {
         tile_count.alloc(tiles, st);
         tile_off.alloc(tiles, st);
         total.alloc(1, st);
-        bitmap_count_kernel<<<(unsigned)tiles, BC_THREADS, 0, st>>>(bits, n_bits, tile_count.p);
-        GRL_KERNEL_CHECK();
+        GRL_LAUNCH("bitmap_count", n_bits / 8, bitmap_count_kernel, (unsigned)tiles, BC_THREADS, 0, st, bits, n_bits, tile_count.p);
         exclusive_scan<u32, u64>(tile_count.p, tile_off.p, tiles, total.p, st);
         u64 h = 0;
         GRL_CUDA(cudaMemcpyAsync(&h, total.p, sizeof(u64), cudaMemcpyDeviceToHost, st));
@@ -183,8 +179,7 @@ struct BitmapCompactor {
     // phase 2: write positions
     template <class PosT>
     void write(const u32* prev_bits, PosT* out) {
-        bitmap_write_kernel<PosT><<<(unsigned)tiles, BC_THREADS, 0, st>>>(bits, prev_bits, n_bits, tile_off.p, out);
-        GRL_KERNEL_CHECK();
+        GRL_LAUNCH("bitmap_write", n_bits / 4, (bitmap_write_kernel<PosT>), (unsigned)tiles, BC_THREADS, 0, st, bits, prev_bits, n_bits, tile_off.p, out);
     }
 };
 
@@ -300,11 +295,10 @@ inline void radix_sort_pairs(u64** keys, u32** vals, u64** keys_alt, u32** vals_
     DevBuf<u32> hist(256 * tiles, st);
     DevBuf<u64> goff(256 * tiles, st);
     for (int shift = 0; shift < n_bits; shift += 8) {
-        radix_hist_kernel<<<(unsigned)tiles, RS_THREADS, 0, st>>>(*keys, n, shift, hist.p, tiles);
-        GRL_KERNEL_CHECK();
+        GRL_LAUNCH("radix_hist", n * 8, radix_hist_kernel, (unsigned)tiles, RS_THREADS, 0, st, *keys, n, shift, hist.p, tiles);
         exclusive_scan<u32, u64>(hist.p, goff.p, 256 * tiles, nullptr, st);
-        radix_scatter_kernel<<<(unsigned)tiles, RS_THREADS, RS_SMEM, st>>>(*keys, *vals, *keys_alt, *vals_alt, n, shift, goff.p, tiles);
-        GRL_KERNEL_CHECK();
+        GRL_LAUNCH("radix_scatter", n * 24, radix_scatter_kernel, (unsigned)tiles, RS_THREADS, RS_SMEM, st, *keys, *vals, *keys_alt, *vals_alt, n, shift,
+                   goff.p, tiles);
         u64* tk = *keys; *keys = *keys_alt; *keys_alt = tk;
         u32* tv = *vals; *vals = *vals_alt; *vals_alt = tv;
     }

@@ -70,6 +70,9 @@ typedef struct {
 
 /* context on one device. replaces: construction of the parse strategy (exact_par_phase.cpp:265-283) */
 int grlgpu_create(grlgpu_ctx** ctx, int device, uint64_t flags);
+/* same, but every kernel and copy is issued on the caller's CUDA stream (a cudaStream_t), so the
+ * caller can bracket calls with its own events (bench.py passes torch's current stream) */
+int grlgpu_create_on_stream(grlgpu_ctx** ctx, int device, uint64_t flags, void* cuda_stream);
 int grlgpu_destroy(grlgpu_ctx* ctx);
 
 /* round-1 input, caller-owned HOST memory, copied to the device. replaces: i_file_stream over the
@@ -108,6 +111,14 @@ int grlgpu_fetch_dictionary(grlgpu_ctx* ctx, uint64_t* syms, uint64_t* lens, uin
 
 const char* grlgpu_strerror(int status);
 const char* grlgpu_last_error(const grlgpu_ctx* ctx);
+
+/* launch accounting: number of kernel launches issued by this context so far, and (after
+ * grlgpu_profile_enable(ctx, 1)) per-kernel CUDA-event durations measured live on the launch stream.
+ * grlgpu_profile_entry returns 1 past the last entry; model_bytes = expected DRAM bytes of the launches. */
+int grlgpu_profile_enable(grlgpu_ctx* ctx, int on);
+int grlgpu_profile_reset(grlgpu_ctx* ctx);
+uint64_t grlgpu_launch_count(const grlgpu_ctx* ctx);
+int grlgpu_profile_entry(grlgpu_ctx* ctx, int index, char* name, int name_cap, uint64_t* launches, double* total_ms, uint64_t* model_bytes);
 
 /* self-test hooks for the device primitives the path is built from (host buffers in / out) */
 int grlgpu_selftest_scan(const uint32_t* in, uint64_t n, uint64_t* out_exclusive, uint64_t* total);
