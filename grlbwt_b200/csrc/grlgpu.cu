@@ -190,17 +190,19 @@ void stage_dedup(Round& R) {
 
     R.slot_of_phrase.alloc(R.p, R.st);
     DevBuf<u32> overflow(1, R.st);
-    // capacity: power of two >= 2p when that is affordable, else grow on demand
-    u64 cap = 1024;
-    const u64 want = 2 * R.p;
-    const u64 start_cap = (c->flags & GRLGPU_FLAG_SMALL_TABLE) ? 1024 : (1ull << 28);
-    while (cap < want && cap < start_cap) cap <<= 1;
+    // capacity (any multiple of 256; slot = mulhi(hash, cap)): 1.6 p slots, so that load <= 0.625 and the pass
+    // cannot overflow, while that stays below 2^31 slots (slot ids are 31 bits); beyond that (p > 1.3e9, e.g.
+    // round 1 of a multi-GB text whose dictionary is tiny) start at 2^28 slots and regrow on demand
+    const u64 cap_max = (1ull << 31) - 256;
+    u64 want = std::max<u64>(1024, (R.p + R.p / 2 + R.p / 10 + 255) / 256 * 256);
+    u64 cap = want <= cap_max ? want : (1ull << 28);
+    if (c->flags & GRLGPU_FLAG_SMALL_TABLE) cap = 1024;
     for (;;) {
-        if (cap > (1ull << 31)) throw Error(GRLGPU_ERR_LIMIT, "phrase table would exceed 2^31 slots");
+        if (cap > cap_max) throw Error(GRLGPU_ERR_LIMIT, "phrase table would exceed 2^31 slots");
         R.table.alloc(cap, R.st);
         GRL_LAUNCH("table_init", cap * 16, table_init_kernel, grid_for(cap, 256), 256, 0, R.st, R.table.p, cap);
         overflow.zero();
-        GRL_LAUNCH("phrase_insert", (R.n + R.p) * sizeof(CellT) + R.p * (2 * sizeof(PosT) + 4 + 32), (phrase_insert_kernel<CellT, PosT>), grid_for(R.p, 256), 256, 0, R.st, text, ps, R.p, R.table.p, cap - 1, R.slot_of_phrase.p, overflow.p);
+        GRL_LAUNCH("phrase_insert", (R.n + R.p) * sizeof(CellT) + R.p * (2 * sizeof(PosT) + 4 + 32), (phrase_insert_kernel<CellT, PosT>), grid_for(R.p, 256), 256, 0, R.st, text, ps, R.p, R.table.p, cap, R.slot_of_phrase.p, overflow.p);
         bool ovf = d2h_scalar(overflow.p, R.st) != 0;
         u64 d = 0;
         if (!ovf) {
@@ -216,7 +218,8 @@ void stage_dedup(Round& R) {
                 break;
             }
         }
-        cap <<= 2;  // too full: regrow and redo the pass
+        if (cap >= cap_max) throw Error(GRLGPU_ERR_LIMIT, "phrase table would exceed 2^31 slots");
+        cap = std::min<u64>(cap * 4, std::min<u64>(want, cap_max));  // too full: regrow and redo the pass
     }
     R.ph_pos.alloc(R.d, R.st);
     R.ph_len.alloc(R.d, R.st);
@@ -291,7 +294,10 @@ void stage_dict(Round& R) {
         h *= 2;
     }
     R.G = G;
-    const u32* order = vp;
+    // keep only the sorted order; the sort's key / flag buffers go back to the pool before the group stage
+    if (vp != vals.p) std::swap(vals, vals_alt);
+    const u32* order = vals.p;
+    keys.release(); keys_alt.release(); vals_alt.release(); flags.release(); excl.release();
 
     // -- group aggregates --
     DevBuf<u32> gcnt(G, st), grep(G, st), rflag(G, st), vflag(G, st), rrank(G, st), vidx(G, st);
@@ -540,6 +546,7 @@ int grlgpu_create_on_stream(grlgpu_ctx** ctx, int device, uint64_t flags, void* 
     c->device = device;
     c->flags = flags;
     int rc = guarded(c.get(), [&] {
+        c->pool.init(device);
         if (cuda_stream) { c->st = (cudaStream_t)cuda_stream; c->own_stream = false; }
         else GRL_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     });

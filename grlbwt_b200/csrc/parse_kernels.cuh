@@ -219,7 +219,7 @@ static __global__ void lms_resolve_kernel(const u8* __restrict__ block_state, u8
 // ------------------------------------------------------------------------------------------------
 constexpr u64 HT_EMPTY = ~0ULL;
 constexpr u64 HT_LEN_SAT = 0xFFFFFFULL;
-constexpr int HT_MAX_PROBES = 4096;
+constexpr int HT_MAX_PROBES = 512;
 
 template <class PosT>
 struct PosFlag {
@@ -258,15 +258,16 @@ __device__ __forceinline__ u64 phrase_hash(const CellT* __restrict__ text, u64 s
 
 template <class CellT, class PosT>
 __global__ void __launch_bounds__(256) phrase_insert_kernel(const CellT* __restrict__ text, const PosT* __restrict__ ps, u64 p, ulonglong2* table,
-                                                            u64 cap_mask, u32* __restrict__ slot_of_phrase, u32* overflow) {
+                                                            u64 cap, u32* __restrict__ slot_of_phrase, u32* overflow) {
     const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= p) return;
+    if (*reinterpret_cast<volatile u32*>(overflow)) return;  // the table is too small: the host regrows it and redoes the pass
     u64 s, e; bool fin;
     phrase_span<PosT>(ps, j, s, e, fin);
     const u64 len = e - s + 1;
     const u64 lenf = len < HT_LEN_SAT ? len : HT_LEN_SAT;
     const u64 mykey = (s << 24) | lenf;
-    u64 slot = phrase_hash<CellT>(text, s, len) & cap_mask;
+    u64 slot = __umul64hi(phrase_hash<CellT>(text, s, len), cap);  // uniform over [0, cap), cap need not be a power of two
     for (int probes = 0; probes < HT_MAX_PROBES; probes++) {
         u64 k = *reinterpret_cast<volatile u64*>(&table[slot].x);
         if (k == HT_EMPTY) {
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(256) phrase_insert_kernel(const CellT* __restr
             slot_of_phrase[j] = (u32)slot | (fin ? 0x80000000u : 0u);
             return;
         }
-        slot = (slot + 1) & cap_mask;
+        if (++slot == cap) slot = 0;
     }
     atomicExch(overflow, 1u);
 }

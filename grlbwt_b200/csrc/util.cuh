@@ -1,5 +1,6 @@
 // Shared device/host helpers for the grlgpu kernels (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -35,67 +36,133 @@ struct Error : public std::runtime_error {
 static inline u64 div_up(u64 a, u64 b) { return (a + b - 1) / b; }
 static inline int bit_width64(u64 v) { return v == 0 ? 0 : 64 - __builtin_clzll(v); }  // = reference sym_width()
 
-// Device memory of one context: a few large cudaMalloc'ed slabs carved by a first-fit free list with
-// coalescing. Every buffer of every round comes from here, so after the first step no allocation
-// reaches the driver (HBM is laid out once and reused round after round). All work of a context is
-// issued on one stream, so a block freed on the host may be handed out again immediately: the
-// kernels that used it were enqueued before the kernels that will.
+// Device memory of one context: ONE contiguous virtual address range (CUDA virtual memory
+// management: cuMemAddressReserve + cuMemCreate/cuMemMap) whose physical backing grows in 256 MB
+// chunks up to what the rounds need, carved by a best-fit free list with coalescing. Every buffer
+// of every round comes from here, so after the first step no allocation reaches the driver and a
+// multi-GB buffer never fails because of fragmentation across separately malloc'ed slabs (HBM is
+// laid out once and reused round after round). All work of a context is issued on one stream, so a
+// block freed on the host may be handed out again immediately: the kernels that used it were
+// enqueued before the kernels that will. The driver entry points are resolved through the runtime
+// (cudaGetDriverEntryPoint), so the library does not link libcuda and still loads on a CPU-only box.
 struct DevicePool {
-    struct Slab { char* base; u64 size; std::map<u64, u64> free_ranges; };  // offset -> length
-    std::vector<Slab> slabs;
-    std::map<void*, std::pair<int, u64>> live;  // ptr -> (slab, size)
-    u64 reserved = 0, in_use = 0, peak = 0;
-    static constexpr u64 ALIGN = 512, MIN_SLAB = 1ull << 28;
+    typedef CUresult (*fn_reserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long);
+    typedef CUresult (*fn_create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long);
+    typedef CUresult (*fn_map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long);
+    typedef CUresult (*fn_access)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t);
+    typedef CUresult (*fn_unmap)(CUdeviceptr, size_t);
+    typedef CUresult (*fn_release)(CUmemGenericAllocationHandle);
+    typedef CUresult (*fn_addrfree)(CUdeviceptr, size_t);
+    typedef CUresult (*fn_gran)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags);
+    fn_reserve p_reserve = nullptr; fn_create p_create = nullptr; fn_map p_map = nullptr; fn_access p_access = nullptr;
+    fn_unmap p_unmap = nullptr; fn_release p_release = nullptr; fn_addrfree p_addrfree = nullptr; fn_gran p_gran = nullptr;
+
+    int device = 0;
+    CUdeviceptr base = 0;
+    u64 va_size = 0, mapped = 0, chunk = 0;
+    std::vector<CUmemGenericAllocationHandle> handles;
+    std::map<u64, u64> free_ranges;       // offset -> length, inside [0, mapped)
+    std::map<u64, u64> live;              // offset -> length
+    u64 in_use = 0, peak = 0;
+    static constexpr u64 ALIGN = 512;
+
+    template <class F>
+    static void resolve(const char* name, F& f) {
+        void* q = nullptr;
+        cudaDriverEntryPointQueryResult st;
+        if (cudaGetDriverEntryPoint(name, &q, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess || !q)
+            throw Error(-3, std::string("driver entry point unavailable: ") + name);
+        f = (F)q;
+    }
+    void init(int dev) {
+        if (base) return;
+        device = dev;
+        resolve("cuMemAddressReserve", p_reserve); resolve("cuMemCreate", p_create); resolve("cuMemMap", p_map);
+        resolve("cuMemSetAccess", p_access); resolve("cuMemUnmap", p_unmap); resolve("cuMemRelease", p_release);
+        resolve("cuMemAddressFree", p_addrfree); resolve("cuMemGetAllocationGranularity", p_gran);
+        CUmemAllocationProp prop = {};
+        prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+        prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        prop.location.id = device;
+        size_t gran = 0;
+        if (p_gran(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || gran == 0) gran = 2ull << 20;
+        chunk = ((256ull << 20) + gran - 1) / gran * gran;
+        size_t free_b = 0, total_b = 0;
+        GRL_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        va_size = ((u64)total_b + chunk - 1) / chunk * chunk;   // never more physical memory than the device has
+        if (p_reserve(&base, va_size, 0, 0, 0) != CUDA_SUCCESS) { base = 0; throw Error(-3, "cuMemAddressReserve failed"); }
+    }
+    void grow(u64 need_bytes) {  // map more physical chunks so that a free range of need_bytes exists at the top
+        u64 top_free = 0;
+        if (!free_ranges.empty()) {
+            auto last = std::prev(free_ranges.end());
+            if (last->first + last->second == mapped) top_free = last->second;
+        }
+        u64 add = need_bytes > top_free ? need_bytes - top_free : 0;
+        add = (add + chunk - 1) / chunk * chunk;
+        if (mapped + add > va_size)
+            throw Error(-4, "out of device memory: request of " + std::to_string(need_bytes) + " bytes with " + std::to_string(mapped) + " mapped");
+        CUmemAllocationProp prop = {};
+        prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+        prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        prop.location.id = device;
+        CUmemAccessDesc acc = {};
+        acc.location = prop.location;
+        acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        for (u64 done = 0; done < add; done += chunk) {
+            CUmemGenericAllocationHandle h;
+            if (p_create(&h, chunk, &prop, 0) != CUDA_SUCCESS)
+                throw Error(-4, "out of device memory: request of " + std::to_string(need_bytes) + " bytes with " + std::to_string(mapped) + " mapped");
+            if (p_map(base + mapped, chunk, 0, h, 0) != CUDA_SUCCESS || p_access(base + mapped, chunk, &acc, 1) != CUDA_SUCCESS) {
+                p_release(h);
+                throw Error(-3, "cuMemMap failed");
+            }
+            handles.push_back(h);
+            add_free(mapped, chunk);
+            mapped += chunk;
+        }
+    }
+    void add_free(u64 off, u64 len) {
+        auto nx = free_ranges.lower_bound(off);
+        if (nx != free_ranges.end() && off + len == nx->first) { len += nx->second; nx = free_ranges.erase(nx); }
+        if (nx != free_ranges.begin()) {
+            auto pv = std::prev(nx);
+            if (pv->first + pv->second == off) { pv->second += len; return; }
+        }
+        free_ranges[off] = len;
+    }
     void* alloc(u64 bytes) {
         bytes = (std::max<u64>(bytes, 1) + ALIGN - 1) / ALIGN * ALIGN;
         for (int pass = 0; pass < 2; pass++) {
-            int best_s = -1; u64 best_off = 0, best_len = ~0ULL;
-            for (int si = 0; si < (int)slabs.size(); si++)
-                for (auto& fr : slabs[si].free_ranges)
-                    if (fr.second >= bytes && fr.second < best_len) { best_s = si; best_off = fr.first; best_len = fr.second; }
-            if (best_s >= 0) {
-                Slab& sl = slabs[best_s];
-                sl.free_ranges.erase(best_off);
-                if (best_len > bytes) sl.free_ranges[best_off + bytes] = best_len - bytes;
-                void* p = sl.base + best_off;
-                live[p] = {best_s, bytes};
+            u64 best_off = 0, best_len = ~0ULL;
+            for (auto& fr : free_ranges)
+                if (fr.second >= bytes && fr.second < best_len) { best_off = fr.first; best_len = fr.second; }
+            if (best_len != ~0ULL) {
+                free_ranges.erase(best_off);
+                if (best_len > bytes) free_ranges[best_off + bytes] = best_len - bytes;
+                live[best_off] = bytes;
                 in_use += bytes; peak = std::max(peak, in_use);
-                return p;
+                return (void*)(base + best_off);
             }
-            // grow: a new slab at least as large as the request (and as what is already reserved, up to 16 GB)
-            u64 sz = std::max<u64>({bytes, MIN_SLAB, std::min<u64>(reserved, 16ull << 30)});
-            void* q = nullptr;
-            cudaError_t e = cudaMalloc(&q, sz);
-            if (e != cudaSuccess && sz > bytes) { cudaGetLastError(); sz = bytes; e = cudaMalloc(&q, sz); }
-            if (e != cudaSuccess) {
-                cudaGetLastError();
-                throw Error(-4 /*GRLGPU_ERR_NOMEM*/, "out of device memory: request of " + std::to_string(bytes) + " bytes with " +
-                                                         std::to_string(reserved) + " reserved");
-            }
-            Slab sl; sl.base = (char*)q; sl.size = sz; sl.free_ranges[0] = sz;
-            slabs.push_back(std::move(sl));
-            reserved += sz;
+            grow(bytes);
         }
         throw Error(-4, "device pool: allocation failed");
     }
     void free(void* p) {
-        auto it = live.find(p);
+        const u64 off = (u64)((CUdeviceptr)p - base);
+        auto it = live.find(off);
         if (it == live.end()) return;
-        Slab& sl = slabs[it->second.first];
-        u64 off = (u64)((char*)p - sl.base), len = it->second.second;
-        in_use -= len;
+        const u64 len = it->second;
         live.erase(it);
-        auto nx = sl.free_ranges.lower_bound(off);
-        if (nx != sl.free_ranges.end() && off + len == nx->first) { len += nx->second; nx = sl.free_ranges.erase(nx); }
-        if (nx != sl.free_ranges.begin()) {
-            auto pv = std::prev(nx);
-            if (pv->first + pv->second == off) { pv->second += len; return; }
-        }
-        sl.free_ranges[off] = len;
+        in_use -= len;
+        add_free(off, len);
     }
     void release_all() {  // caller guarantees the device is idle
-        for (auto& sl : slabs) cudaFree(sl.base);
-        slabs.clear(); live.clear(); reserved = in_use = 0;
+        if (!base) return;
+        for (size_t i = 0; i < handles.size(); i++) { p_unmap(base + (u64)i * chunk, chunk); p_release(handles[i]); }
+        p_addrfree(base, va_size);
+        handles.clear(); free_ranges.clear(); live.clear();
+        base = 0; mapped = 0; in_use = 0;
     }
     ~DevicePool() { release_all(); }
 };
