@@ -101,6 +101,79 @@ static __global__ void __launch_bounds__(256) sfx_double_key_kernel(const u32* _
     keys[i] = ((u64)rank[e] << bits) | second;
 }
 
+// ---- refinement of the unresolved groups only (Larsson-Sadakane style prefix doubling) ----
+// During refinement rank[e] is position-based: 1 + the position (in the sorted order) of the head of e's
+// group, so refining one group never changes the rank of another. A group is unresolved while it has more
+// than one member and the compared prefix (h codes) holds no terminator yet.
+
+// after the first sort: head flags, head bitmap, and bitmap of the positions that belong to unresolved groups
+static __global__ void __launch_bounds__(256) first_heads_kernel(const u64* __restrict__ keys, u64 n, int bits, u64 term_code, u32* __restrict__ flags,
+                                                                 u32* __restrict__ head_bits, u32* __restrict__ active_bits) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    bool head = false, active = false;
+    if (i < n) {
+        const u64 k = keys[i];
+        head = i == 0 || keys[i - 1] != k;
+        const bool next_head = i + 1 == n || keys[i + 1] != k;
+        const u64 last = bits >= 64 ? k : (k & ((1ULL << bits) - 1ULL));
+        const bool finished = last == 0 || last == term_code;  // the key already holds the terminator
+        active = !(head && next_head) && !finished;
+        flags[i] = head ? 1u : 0u;
+    }
+    const u32 hb = __ballot_sync(0xffffffffu, head), ab = __ballot_sync(0xffffffffu, active);
+    if (lane_id() == 0 && (i >> 5) < ((n + 31) >> 5)) { head_bits[i >> 5] = hb; active_bits[i >> 5] = ab; }
+}
+// head_pos[dense group id] = position of the group's head (pos == nullptr: the index itself)
+static __global__ void __launch_bounds__(256) head_pos_kernel(const u32* __restrict__ flags, const u32* __restrict__ excl, const u32* __restrict__ pos, u64 n,
+                                                              u32* __restrict__ head_pos) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n && flags[j]) head_pos[excl[j]] = pos ? pos[j] : (u32)j;
+}
+static __global__ void __launch_bounds__(256) assign_hrank_kernel(const u32* __restrict__ flags, const u32* __restrict__ excl, const u32* __restrict__ head_pos,
+                                                                  const u32* __restrict__ entries, u64 n, u32* __restrict__ hrank) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) hrank[entries[j]] = head_pos[excl[j] + flags[j] - 1] + 1;
+}
+static __global__ void __launch_bounds__(256) active_keys_kernel(const u32* __restrict__ apos, const u32* __restrict__ order, const u32* __restrict__ hrank,
+                                                                 const u32* __restrict__ rem, u64 nA, u64 h, u32 term_rank, int bits, u64* __restrict__ keys,
+                                                                 u32* __restrict__ vals) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nA) return;
+    const u32 e = order[apos[j]];
+    const u64 r = rem[e];
+    u64 second = 0;
+    if (h <= r) second = hrank[e + h];
+    else if (h == r + 1) second = term_rank;
+    keys[j] = ((u64)hrank[e] << bits) | second;
+    vals[j] = e;
+}
+static __global__ void __launch_bounds__(256) refine_writeback_kernel(const u32* __restrict__ apos, const u32* __restrict__ vals, const u32* __restrict__ flags,
+                                                                      u64 nA, u32* __restrict__ order, u32* head_bits) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nA) return;
+    const u32 i = apos[j];
+    order[i] = vals[j];
+    if (flags[j]) atomicOr(&head_bits[i >> 5], 1u << (i & 31));
+}
+static __global__ void __launch_bounds__(256) active_next_kernel(const u32* __restrict__ apos, const u32* __restrict__ vals, const u32* __restrict__ head_bits,
+                                                                 const u32* __restrict__ rem, u64 nA, u64 nE, u64 h2, u32* __restrict__ aflag) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nA) return;
+    const u64 i = apos[j];
+    const bool hd = (head_bits[i >> 5] >> (i & 31)) & 1u;
+    const bool nh = i + 1 == nE || ((head_bits[(i + 1) >> 5] >> ((i + 1) & 31)) & 1u);
+    aflag[j] = (!(hd && nh) && (u64)rem[vals[j]] + 1 >= h2) ? 1u : 0u;
+}
+static __global__ void __launch_bounds__(256) compact_apos_kernel(const u32* __restrict__ aflag, const u32* __restrict__ excl, const u32* __restrict__ apos, u64 nA,
+                                                                  u32* __restrict__ apos_next) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nA && aflag[j]) apos_next[excl[j]] = apos[j];
+}
+static __global__ void __launch_bounds__(256) popc_words_kernel(const u32* __restrict__ bits, u64 n_words, u32* __restrict__ cnt) {
+    const u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < n_words) cnt[w] = __popc(bits[w]);
+}
+
 // ---- segmented warp reductions over runs of equal keys that are contiguous across lanes ----
 template <class T, class Op>
 __device__ __forceinline__ T seg_reduce(T v, u32 seg_last, Op op) {
@@ -119,16 +192,19 @@ struct OpMax { template <class T> __device__ __forceinline__ T operator()(T a, T
 // G1: per-group aggregates over the sorted entries (produce_pre_bwt exact_par_phase.cpp:159-187).
 // gcnt = entries | full<<31 ; gmin/gmax over (left symbol + 1) of the non-full entries (0 = none).
 template <class SymT>
-__global__ void __launch_bounds__(256) group_reduce_kernel(const u32* __restrict__ order, const u32* __restrict__ rank, const SymT* __restrict__ D,
-                                                           const u32* __restrict__ rem, const u32* __restrict__ phr_of, const u32* __restrict__ ph_off,
-                                                           const u64* __restrict__ ph_freq, u64 nE, IsSuffix is_suffix, u32* gcnt, u64* gacc, u64* gmin,
-                                                           u64* gmax, u32* __restrict__ grep) {
+__global__ void __launch_bounds__(256) group_reduce_kernel(const u32* __restrict__ order, const u32* __restrict__ head_bits, const u32* __restrict__ head_pref,
+                                                           u32* __restrict__ rank, const SymT* __restrict__ D, const u32* __restrict__ rem,
+                                                           const u32* __restrict__ phr_of, const u32* __restrict__ ph_off, const u64* __restrict__ ph_freq, u64 nE,
+                                                           IsSuffix is_suffix, u32* gcnt, u64* gacc, u64* gmin, u64* gmax, u32* __restrict__ grep) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     u32 g = 0xffffffffu, cnt = 0;
     u64 acc = 0, mn = ~0ULL, mx = 0;
     if (i < nE) {
         const u32 e = order[i];
-        g = rank[e] - 1;
+        const u32 hw = head_bits[i >> 5];
+        const u32 upto = hw & (0xffffffffu >> (31 - (i & 31)));  // heads at positions <= i inside the word
+        g = head_pref[i >> 5] + __popc(upto) - 1;                // dense group index in sorted order
+        rank[e] = g + 1;                                         // position-based ranks become dense group ids
         const bool valid = rem[e] > 0 || is_suffix((u64)D[e]);  // exact_par_phase.cpp:163
         if (valid) {
             const u32 ph = phr_of[e];
@@ -137,7 +213,7 @@ __global__ void __launch_bounds__(256) group_reduce_kernel(const u32* __restrict
             acc = ph_freq[ph];
             if (!full) { mn = mx = (u64)D[e - 1] + 1; }
         }
-        if (i == 0 || rank[order[i - 1]] != rank[e]) grep[g] = e;
+        if ((hw >> (i & 31)) & 1u) grep[g] = e;
     }
     const u32 m = __match_any_sync(0xffffffffu, g);
     const u32 first = __ffs(m) - 1, last = 31 - __clz(m);

@@ -267,43 +267,83 @@ void stage_dict(Round& R) {
     const SymT* D = (const SymT*)R.D_raw.p;
     IsSuffix isuf{c->is_suffix.p, c->sep, c->first};
 
-    // -- suffix order by prefix doubling --
-    DevBuf<u64> keys(nE, st), keys_alt(nE, st);
-    DevBuf<u32> vals(nE, st), vals_alt(nE, st), flags(nE, st), excl(nE, st), gcount(1, st);
+    // -- suffix order: one full sort on the packed first key, then prefix doubling on the unresolved groups only --
+    const u64 n_words = div_up(nE, 32);
+    DevBuf<u32> order_buf, head_bits(n_words, st);
     R.rank.alloc(nE, st);
-    u64 *kp = keys.p, *ka = keys_alt.p;
-    u32 *vp = vals.p, *va = vals_alt.p;
-    const int sym_bits = bit_width64(A + 1);
-    const int K = std::max(1, 64 / sym_bits);
-    GRL_LAUNCH("sfx_first_key", nE * (sizeof(SymT) + 4 + 12), (sfx_first_key_kernel<SymT>), grid_for(nE, 256), 256, 0, st, D, R.rem.p, nE, A + 1, sym_bits, K, kp, vp);
-    radix_sort_pairs(&kp, &vp, &ka, &va, nE, std::min(64, sym_bits * K), st);
     u64 G = 0;
-    u64 h = (u64)K;
-    for (;;) {
-        GRL_LAUNCH("key_head_flags", 0, key_head_flags_kernel, grid_for(nE, 256), 256, 0, st, kp, nE, flags.p);
-        exclusive_scan<u32, u32>(flags.p, excl.p, nE, gcount.p, st);
-        GRL_LAUNCH("scatter_rank", nE * 16, scatter_rank_kernel, grid_for(nE, 256), 256, 0, st, flags.p, excl.p, vp, nE, R.rank.p);
-        const u64 Gn = d2h_scalar(gcount.p, st);
-        const bool stable = (Gn == G);
-        G = Gn;
-        // a key of h codes covers any suffix (<= max_len symbols + terminator) once h > max_len
-        if (stable || G == nE || h > R.max_len) break;
-        const int rb = bit_width64(G + 1);
-        GRL_LAUNCH("sfx_double_key", nE * (4 + 4 + 4 + 4 + 8), sfx_double_key_kernel, grid_for(nE, 256), 256, 0, st, R.rank.p, R.rem.p, vp, nE, (u32)std::min<u64>(h, 0xffffffffull), (u32)(G + 1), rb, kp);
-        radix_sort_pairs(&kp, &vp, &ka, &va, nE, 2 * rb, st);
-        h *= 2;
+    {
+        DevBuf<u64> keys(nE, st), keys_alt(nE, st);
+        DevBuf<u32> vals(nE, st), vals_alt(nE, st);
+        u64 *kp = keys.p, *ka = keys_alt.p;
+        u32 *vp = vals.p, *va = vals_alt.p;
+        const int sym_bits = bit_width64(A + 1);
+        const int K = std::max(1, 64 / sym_bits);
+        GRL_LAUNCH("sfx_first_key", nE * (sizeof(SymT) + 4 + 12), (sfx_first_key_kernel<SymT>), grid_for(nE, 256), 256, 0, st, D, R.rem.p, nE, A + 1, sym_bits, K, kp, vp);
+        radix_sort_pairs(&kp, &vp, &ka, &va, nE, std::min(64, sym_bits * K), st);
+        if (vp != vals.p) std::swap(vals, vals_alt);
+        order_buf = std::move(vals);
+        vals_alt.release();
+        u32* order_w = order_buf.p;
+        u64 nA = 0;
+        DevBuf<u32> apos;
+        {   // heads, position-based ranks and the first active set
+            DevBuf<u32> flags(nE, st), excl(nE, st), active_bits(n_words, st), gcount(1, st);
+            GRL_LAUNCH("first_heads", nE * 12, first_heads_kernel, grid_for(nE, 256), 256, 0, st, kp, nE, sym_bits, A + 1, flags.p, head_bits.p, active_bits.p);
+            keys.release(); keys_alt.release();
+            exclusive_scan<u32, u32>(flags.p, excl.p, nE, gcount.p, st);
+            const u64 G0 = d2h_scalar(gcount.p, st);
+            DevBuf<u32> head_pos(G0, st);
+            GRL_LAUNCH("head_pos", nE * 8, head_pos_kernel, grid_for(nE, 256), 256, 0, st, flags.p, excl.p, (const u32*)nullptr, nE, head_pos.p);
+            GRL_LAUNCH("assign_hrank", nE * 20, assign_hrank_kernel, grid_for(nE, 256), 256, 0, st, flags.p, excl.p, head_pos.p, order_w, nE, R.rank.p);
+            BitmapCompactor ac;
+            nA = ac.count(active_bits.p, nE, st);
+            apos.alloc(nA, st);
+            if (nA) ac.write<u32>(nullptr, apos.p);
+        }
+        const int rb = bit_width64(nE + 1);
+        u64 h = (u64)K;
+        while (nA > 0) {  // a key of h codes covers any suffix (<= max_len symbols + terminator) once h > max_len
+            if (h > R.max_len + 1) throw Error(GRLGPU_ERR_STATE, "suffix refinement did not converge");
+            DevBuf<u64> ak(nA, st), ak_alt(nA, st);
+            DevBuf<u32> av(nA, st), av_alt(nA, st), flags(nA, st), excl(nA, st), cnt(1, st);
+            u64 *akp = ak.p, *aka = ak_alt.p;
+            u32 *avp = av.p, *ava = av_alt.p;
+            GRL_LAUNCH("active_keys", nA * 36, active_keys_kernel, grid_for(nA, 256), 256, 0, st, apos.p, order_w, R.rank.p, R.rem.p, nA, h, (u32)(nE + 1), rb, akp, avp);
+            radix_sort_pairs(&akp, &avp, &aka, &ava, nA, 2 * rb, st);
+            GRL_LAUNCH("key_head_flags", nA * 12, key_head_flags_kernel, grid_for(nA, 256), 256, 0, st, akp, nA, flags.p);
+            exclusive_scan<u32, u32>(flags.p, excl.p, nA, cnt.p, st);
+            const u64 nH = d2h_scalar(cnt.p, st);
+            DevBuf<u32> head_pos(nH, st);
+            GRL_LAUNCH("head_pos", nA * 12, head_pos_kernel, grid_for(nA, 256), 256, 0, st, flags.p, excl.p, apos.p, nA, head_pos.p);
+            GRL_LAUNCH("assign_hrank", nA * 20, assign_hrank_kernel, grid_for(nA, 256), 256, 0, st, flags.p, excl.p, head_pos.p, avp, nA, R.rank.p);
+            GRL_LAUNCH("refine_writeback", nA * 16, refine_writeback_kernel, grid_for(nA, 256), 256, 0, st, apos.p, avp, flags.p, nA, order_w, head_bits.p);
+            h *= 2;
+            GRL_LAUNCH("active_next", nA * 16, active_next_kernel, grid_for(nA, 256), 256, 0, st, apos.p, avp, head_bits.p, R.rem.p, nA, nE, h, flags.p);
+            exclusive_scan<u32, u32>(flags.p, excl.p, nA, cnt.p, st);
+            const u64 nA2 = d2h_scalar(cnt.p, st);
+            DevBuf<u32> apos2(nA2, st);
+            if (nA2) GRL_LAUNCH("compact_apos", nA * 12, compact_apos_kernel, grid_for(nA, 256), 256, 0, st, flags.p, excl.p, apos.p, nA, apos2.p);
+            apos = std::move(apos2);
+            nA = nA2;
+        }
+    }
+    const u32* order = order_buf.p;
+    // dense group ids from the head bitmap: per-word prefix counts
+    DevBuf<u32> head_pref(n_words, st);
+    {
+        DevBuf<u32> wc(n_words, st), gtot(1, st);
+        GRL_LAUNCH("popc_words", n_words * 8, popc_words_kernel, grid_for(n_words, 256), 256, 0, st, head_bits.p, n_words, wc.p);
+        exclusive_scan<u32, u32>(wc.p, head_pref.p, n_words, gtot.p, st);
+        G = d2h_scalar(gtot.p, st);
     }
     R.G = G;
-    // keep only the sorted order; the sort's key / flag buffers go back to the pool before the group stage
-    if (vp != vals.p) std::swap(vals, vals_alt);
-    const u32* order = vals.p;
-    keys.release(); keys_alt.release(); vals_alt.release(); flags.release(); excl.release();
 
     // -- group aggregates --
     DevBuf<u32> gcnt(G, st), grep(G, st), rflag(G, st), vflag(G, st), rrank(G, st), vidx(G, st);
     DevBuf<u64> gacc(G, st), gmin(G, st), gmax(G, st), psym(G, st);
     gcnt.zero(); gacc.zero(); gmax.zero(); gmin.fill_ff();
-    GRL_LAUNCH("group_reduce", nE * 40, (group_reduce_kernel<SymT>), grid_for(nE, 256), 256, 0, st, order, R.rank.p, D, R.rem.p, R.phr_of.p, R.ph_off.p, R.ph_freq.p, nE, isuf, gcnt.p, gacc.p, gmin.p, gmax.p, grep.p);
+    GRL_LAUNCH("group_reduce", nE * 44, (group_reduce_kernel<SymT>), grid_for(nE, 256), 256, 0, st, order, head_bits.p, head_pref.p, R.rank.p, D, R.rem.p, R.phr_of.p, R.ph_off.p, R.ph_freq.p, nE, isuf, gcnt.p, gacc.p, gmin.p, gmax.p, grep.p);
     const u64 bwt_dummy = A + 1, hocc_dummy = A + 2;  // exact_par_phase.hpp:113-115
     GRL_LAUNCH("group_finalize", 0, group_finalize_kernel, grid_for(G, 256), 256, 0, st, gcnt.p, gmin.p, gmax.p, G, bwt_dummy, hocc_dummy, rflag.p, vflag.p, psym.p);
     DevBuf<u32> cnt2(2, st);
