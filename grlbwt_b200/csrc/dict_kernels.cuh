@@ -40,18 +40,29 @@ __global__ void __launch_bounds__(256) dict_meta_kernel(const ulonglong2* __rest
     ph_freq[i] = ent.y;
 }
 
+// einfo[e] = { left symbol + 1 (0 for the first symbol of a phrase), phrase frequency | valid << 63 | full << 62 }:
+// everything the group stage needs about an entry, in one 16-byte record, so that the pass over the
+// sorted order does a single random gather per entry.
+constexpr u64 EI_VALID = 1ULL << 63, EI_FULL = 1ULL << 62, EI_FREQ = (1ULL << 62) - 1;
+
 template <class CellT, bool FIRST, class SymT>
 __global__ void __launch_bounds__(256) dict_gather_kernel(const CellT* __restrict__ text, const u64* __restrict__ ph_pos, const u32* __restrict__ ph_len,
-                                                          const u32* __restrict__ ph_off, u64 d, SymT* __restrict__ D, u32* __restrict__ phr_of,
-                                                          u32* __restrict__ rem) {
+                                                          const u32* __restrict__ ph_off, const u64* __restrict__ ph_freq, u64 d, IsSuffix is_suffix,
+                                                          SymT* __restrict__ D, u32* __restrict__ phr_of, u32* __restrict__ rem,
+                                                          ulonglong2* __restrict__ einfo) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d) return;
-    const u64 pos = ph_pos[i];
+    const u64 pos = ph_pos[i], freq = ph_freq[i];
     const u32 len = ph_len[i], off = ph_off[i];
+    u64 prev = 0;
     for (u32 k = 0; k < len; k++) {
-        D[off + k] = (SymT)cell_value<CellT, FIRST>(text[pos + k]);
+        const u64 v = cell_value<CellT, FIRST>(text[pos + k]);
+        D[off + k] = (SymT)v;
         phr_of[off + k] = (u32)i;
         rem[off + k] = len - 1 - k;
+        const bool valid = k + 1 < len || is_suffix(v);  // exact_par_phase.cpp:163
+        einfo[off + k] = make_ulonglong2(k ? prev + 1 : 0ULL, freq | (valid ? EI_VALID : 0ULL) | (k == 0 ? EI_FULL : 0ULL));
+        prev = v;
     }
 }
 
@@ -191,29 +202,28 @@ struct OpMax { template <class T> __device__ __forceinline__ T operator()(T a, T
 
 // G1: per-group aggregates over the sorted entries (produce_pre_bwt exact_par_phase.cpp:159-187).
 // gcnt = entries | full<<31 ; gmin/gmax over (left symbol + 1) of the non-full entries (0 = none).
-template <class SymT>
-__global__ void __launch_bounds__(256) group_reduce_kernel(const u32* __restrict__ order, const u32* __restrict__ head_bits, const u32* __restrict__ head_pref,
-                                                           u32* __restrict__ rank, const SymT* __restrict__ D, const u32* __restrict__ rem,
-                                                           const u32* __restrict__ phr_of, const u32* __restrict__ ph_off, const u64* __restrict__ ph_freq, u64 nE,
-                                                           IsSuffix is_suffix, u32* gcnt, u64* gacc, u64* gmin, u64* gmax, u32* __restrict__ grep) {
+static __global__ void __launch_bounds__(256) group_reduce_kernel(const u32* __restrict__ order, const u32* __restrict__ head_bits, const u32* __restrict__ head_pref,
+                                                                  u32* __restrict__ rank, const ulonglong2* __restrict__ einfo, u64 nE, u32* gcnt, u64* gacc,
+                                                                  u64* gmin, u64* gmax, u32* __restrict__ grep) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     u32 g = 0xffffffffu, cnt = 0;
     u64 acc = 0, mn = ~0ULL, mx = 0;
+    bool hd = false, nh = true;
     if (i < nE) {
         const u32 e = order[i];
         const u32 hw = head_bits[i >> 5];
         const u32 upto = hw & (0xffffffffu >> (31 - (i & 31)));  // heads at positions <= i inside the word
         g = head_pref[i >> 5] + __popc(upto) - 1;                // dense group index in sorted order
         rank[e] = g + 1;                                         // position-based ranks become dense group ids
-        const bool valid = rem[e] > 0 || is_suffix((u64)D[e]);  // exact_par_phase.cpp:163
-        if (valid) {
-            const u32 ph = phr_of[e];
-            const bool full = e == ph_off[ph];
-            cnt = 1u | (full ? 0x80000000u : 0u);
-            acc = ph_freq[ph];
-            if (!full) { mn = mx = (u64)D[e - 1] + 1; }
+        hd = (hw >> (i & 31)) & 1u;
+        nh = i + 1 == nE || ((head_bits[(i + 1) >> 5] >> ((i + 1) & 31)) & 1u);
+        const ulonglong2 ei = einfo[e];
+        if (ei.y & EI_VALID) {
+            cnt = 1u | ((ei.y & EI_FULL) ? 0x80000000u : 0u);
+            acc = ei.y & EI_FREQ;
+            if (ei.x) mn = mx = ei.x;
         }
-        if ((hw >> (i & 31)) & 1u) grep[g] = e;
+        if (hd) grep[g] = e;
     }
     const u32 m = __match_any_sync(0xffffffffu, g);
     const u32 first = __ffs(m) - 1, last = 31 - __clz(m);
@@ -221,10 +231,19 @@ __global__ void __launch_bounds__(256) group_reduce_kernel(const u32* __restrict
     acc = seg_reduce(acc, last, OpSum());
     mn = seg_reduce(mn, last, OpMin());
     mx = seg_reduce(mx, last, OpMax());
+    // a group that starts and ends inside this warp is stored directly (consecutive groups -> consecutive
+    // addresses); only groups that straddle warps accumulate with atomics on the zero-initialised arrays
+    const bool whole = __shfl_sync(0xffffffffu, hd, first) && __shfl_sync(0xffffffffu, nh, last);
     if (lane_id() == first && g != 0xffffffffu && (cnt & 0x7fffffffu)) {
-        atomicAdd(&gcnt[g], cnt);
-        atomicAdd(&gacc[g], acc);
-        if (mx) { atomicMin(&gmin[g], mn); atomicMax(&gmax[g], mx); }
+        if (whole) {
+            gcnt[g] = cnt;
+            gacc[g] = acc;
+            if (mx) { gmin[g] = mn; gmax[g] = mx; }
+        } else {
+            atomicAdd(&gcnt[g], cnt);
+            atomicAdd(&gacc[g], acc);
+            if (mx) { atomicMin(&gmin[g], mn); atomicMax(&gmax[g], mx); }
+        }
     }
 }
 
@@ -270,23 +289,28 @@ __global__ void __launch_bounds__(256) prebwt_runs_kernel(const u64* __restrict_
 
 // G4: per entry: metasymbol of full phrases (exact_par_phase.cpp:174-176, :437-444), is_suffix of the
 // next round (:443), rank marks of entries in hocc groups (phr_marks + new_phrases_ht, :190-207)
+// ginfo[g] = rank << 2 | hocc << 1 | ranked : one gather per entry in entry_finalize
+static __global__ void __launch_bounds__(256) pack_ginfo_kernel(const u32* __restrict__ gcnt, const u32* __restrict__ rflag, const u32* __restrict__ rrank, u64 G,
+                                                                u32* __restrict__ ginfo) {
+    const u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < G) ginfo[g] = (rrank[g] << 2) | (((gcnt[g] & 0x7fffffffu) > 1) ? 2u : 0u) | (rflag[g] ? 1u : 0u);
+}
 template <class SymT>
 __global__ void __launch_bounds__(256) entry_finalize_kernel(const u32* __restrict__ rank, const SymT* __restrict__ D, const u32* __restrict__ rem,
                                                              const u32* __restrict__ phr_of, const u32* __restrict__ ph_off, const u64* __restrict__ ph_freq,
-                                                             const u32* __restrict__ occ_slots, u64 nE, IsSuffix is_suffix, const u32* __restrict__ gcnt,
-                                                             const u32* __restrict__ rflag, const u32* __restrict__ rrank, ulonglong2* table,
-                                                             u8* __restrict__ is_suffix_next, u32* __restrict__ erank) {
+                                                             const u32* __restrict__ occ_slots, u64 nE, IsSuffix is_suffix, const u32* __restrict__ ginfo,
+                                                             ulonglong2* table, u8* __restrict__ is_suffix_next, u32* __restrict__ erank) {
     const u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nE) return;
-    const u32 g = rank[e] - 1;
-    if (!rflag[g]) return;  // invalid and unranked groups carry no rank
-    const u32 r = rrank[g];
+    const u32 gi = ginfo[rank[e] - 1];
+    if (!(gi & 1u)) return;  // invalid and unranked groups carry no rank
+    const u32 r = gi >> 2;
     const u32 ph = phr_of[e];
     if (e == ph_off[ph]) {
         table[occ_slots[ph]].y = ((u64)r << 1) | (ph_freq[ph] > 1 ? 1ULL : 0ULL);
         is_suffix_next[r] = is_suffix((u64)D[e + rem[e]]) ? 1 : 0;
     }
-    if ((gcnt[g] & 0x7fffffffu) > 1) erank[e] = r;
+    if (gi & 2u) erank[e] = r;
 }
 
 // G5: grammar rule of every ranked group from its representative entry (produce_grammar exact_par_phase.cpp:33-87)

@@ -141,6 +141,7 @@ struct Round {
     DevBuf<u32> ph_len, ph_off;
     DevBuf<u8> D_raw;
     DevBuf<u32> phr_of, rem, rank, order;
+    DevBuf<ulonglong2> einfo;
     explicit Round(grlgpu_ctx* ctx) : c(ctx), st(ctx->st), n(ctx->n) {}
 };
 
@@ -255,7 +256,9 @@ void stage_gather(Round& R) {
     R.D_raw.alloc((R.nE + 1) * sizeof(SymT), R.st);
     R.phr_of.alloc(R.nE, R.st);
     R.rem.alloc(R.nE, R.st);
-    GRL_LAUNCH("dict_gather", R.nE * (sizeof(CellT) + sizeof(SymT) + 8) + R.d * 16, (dict_gather_kernel<CellT, FIRST, SymT>), grid_for(R.d, 256), 256, 0, R.st, (const CellT*)R.c->text, R.ph_pos.p, R.ph_len.p, R.ph_off.p, R.d, (SymT*)R.D_raw.p, R.phr_of.p, R.rem.p);
+    R.einfo.alloc(R.nE, R.st);
+    IsSuffix isuf{R.c->is_suffix.p, R.c->sep, R.c->first};
+    GRL_LAUNCH("dict_gather", R.nE * (sizeof(CellT) + sizeof(SymT) + 8) + R.d * 16, (dict_gather_kernel<CellT, FIRST, SymT>), grid_for(R.d, 256), 256, 0, R.st, (const CellT*)R.c->text, R.ph_pos.p, R.ph_len.p, R.ph_off.p, R.ph_freq.p, R.d, isuf, (SymT*)R.D_raw.p, R.phr_of.p, R.rem.p, R.einfo.p);
 }
 
 // ---------------- dictionary stage: suffix order, groups, ranks, pre-BWT, rules, metasymbols ----------------
@@ -343,7 +346,8 @@ void stage_dict(Round& R) {
     DevBuf<u32> gcnt(G, st), grep(G, st), rflag(G, st), vflag(G, st), rrank(G, st), vidx(G, st);
     DevBuf<u64> gacc(G, st), gmin(G, st), gmax(G, st), psym(G, st);
     gcnt.zero(); gacc.zero(); gmax.zero(); gmin.fill_ff();
-    GRL_LAUNCH("group_reduce", nE * 44, (group_reduce_kernel<SymT>), grid_for(nE, 256), 256, 0, st, order, head_bits.p, head_pref.p, R.rank.p, D, R.rem.p, R.phr_of.p, R.ph_off.p, R.ph_freq.p, nE, isuf, gcnt.p, gacc.p, gmin.p, gmax.p, grep.p);
+    GRL_LAUNCH("group_reduce", nE * 28 + G * 28, group_reduce_kernel, grid_for(nE, 256), 256, 0, st, order, head_bits.p, head_pref.p, R.rank.p, R.einfo.p, nE, gcnt.p, gacc.p, gmin.p, gmax.p, grep.p);
+    R.einfo.release();
     const u64 bwt_dummy = A + 1, hocc_dummy = A + 2;  // exact_par_phase.hpp:113-115
     GRL_LAUNCH("group_finalize", 0, group_finalize_kernel, grid_for(G, 256), 256, 0, st, gcnt.p, gmin.p, gmax.p, G, bwt_dummy, hocc_dummy, rflag.p, vflag.p, psym.p);
     DevBuf<u32> cnt2(2, st);
@@ -353,6 +357,7 @@ void stage_dict(Round& R) {
     GRL_CUDA(cudaMemcpyAsync(hc, cnt2.p, 8, cudaMemcpyDeviceToHost, st));
     GRL_CUDA(cudaStreamSynchronize(st));
     const u64 tot = hc[0], nV = hc[1];
+    if (tot >= (1ull << 30)) throw Error(GRLGPU_ERR_LIMIT, "more than 2^30 ranks in one round");
     R.tot = tot;
 
     // -- preliminary BWT: maximal runs over the valid groups --
@@ -375,7 +380,9 @@ void stage_dict(Round& R) {
     is_suffix_next.zero();
     DevBuf<u32> erank(nE, st);
     erank.fill_ff();
-    GRL_LAUNCH("entry_finalize", nE * 32, (entry_finalize_kernel<SymT>), grid_for(nE, 256), 256, 0, st, R.rank.p, D, R.rem.p, R.phr_of.p, R.ph_off.p, R.ph_freq.p, R.occ_slots.p, nE, isuf, gcnt.p, rflag.p, rrank.p, R.table.p, is_suffix_next.p, erank.p);
+    DevBuf<u32> ginfo(G, st);
+    GRL_LAUNCH("pack_ginfo", G * 16, pack_ginfo_kernel, grid_for(G, 256), 256, 0, st, gcnt.p, rflag.p, rrank.p, G, ginfo.p);
+    GRL_LAUNCH("entry_finalize", nE * 24, (entry_finalize_kernel<SymT>), grid_for(nE, 256), 256, 0, st, R.rank.p, D, R.rem.p, R.phr_of.p, R.ph_off.p, R.ph_freq.p, R.occ_slots.p, nE, isuf, ginfo.p, R.table.p, is_suffix_next.p, erank.p);
     c->rule_l.alloc(tot * sizeof(SymT), st);
     c->rule_r.alloc(tot * sizeof(SymT), st);
     c->has_hocc.alloc(tot, st);
