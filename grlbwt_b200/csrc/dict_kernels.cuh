@@ -25,16 +25,15 @@ struct IsSuffix {  // phrase_desc bit-vector of the round (exact_par_phase.cpp:3
 };
 
 // per distinct phrase: first-occurrence position, true length, frequency
-template <class PosT>
-__global__ void __launch_bounds__(256) dict_meta_kernel(const ulonglong2* __restrict__ table, const u32* __restrict__ occ_slots, u64 d,
-                                                        const PosT* __restrict__ ps, u64 p, u64* __restrict__ ph_pos, u32* __restrict__ ph_len,
-                                                        u64* __restrict__ ph_freq) {
+static __global__ void __launch_bounds__(256) dict_meta_kernel(const ulonglong2* __restrict__ table, const u32* __restrict__ occ_slots, u64 d,
+                                                               const u32* __restrict__ start_bits, const u32* __restrict__ end_bits, u64 n,
+                                                               u64* __restrict__ ph_pos, u32* __restrict__ ph_len, u64* __restrict__ ph_freq) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d) return;
     const ulonglong2 ent = table[occ_slots[i]];
     const u64 pos = ent.x >> 24;
     u64 len = ent.x & HT_LEN_SAT;
-    if (len == HT_LEN_SAT) len = phrase_len_at<PosT>(ps, p, pos);
+    if (len == HT_LEN_SAT) len = phrase_len_bits(start_bits, end_bits, n, pos);
     ph_pos[i] = pos;
     ph_len[i] = (u32)len;
     ph_freq[i] = ent.y;

@@ -86,15 +86,6 @@ static __global__ void table_init_kernel(ulonglong2* table, u64 cap) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < cap) table[i] = make_ulonglong2(HT_EMPTY, 0ULL);
 }
-template <class PosT>
-__global__ void set_sentinel_kernel(PosT* ps, u64 p, u64 n) {
-    ps[p] = (PosT)n | PosFlag<PosT>::FLAG;
-}
-template <class PosT>
-__global__ void strip_flag_kernel(const PosT* __restrict__ in, u64 cnt, u64* __restrict__ out) {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < cnt) out[i] = (u64)(in[i] & ~PosFlag<PosT>::FLAG);
-}
 static __global__ void next_start_bits_kernel(const u32* __restrict__ end_bits, u64 n, u32* __restrict__ start_bits) {
     // start_bits[q] = (q == 0) || end_bits[q-1]   (string starts of the current text)
     const u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -134,7 +125,6 @@ struct Round {
     u64 n, p = 0, d = 0, nE = 0, cap = 0, G = 0, tot = 0, n_pre = 0, max_freq = 0, max_len = 0;
     DevBuf<u32> start_bits, end_bits_first;
     const u32* end_bits = nullptr;  // of the input text
-    DevBuf<u8> ps_raw;              // PosT[p+1]
     DevBuf<ulonglong2> table;
     DevBuf<u32> slot_of_phrase, occ_slots;
     DevBuf<u64> ph_pos, ph_freq;
@@ -177,17 +167,25 @@ void stage_flags(Round& R) {
     }
 }
 
-template <class CellT, class PosT>
+template <class CellT>
 void stage_dedup(Round& R) {
     grlgpu_ctx* c = R.c;
     const CellT* text = (const CellT*)c->text;
-    BitmapCompactor bc;
-    R.p = bc.count(R.start_bits.p, R.n, R.st);
-    R.ps_raw.alloc((R.p + 1) * sizeof(PosT), R.st);
-    PosT* ps = (PosT*)R.ps_raw.p;
-    bc.write<PosT>(R.end_bits, ps);
-    GRL_LAUNCH("set_sentinel", 0, (set_sentinel_kernel<PosT>), 1, 1, 0, R.st, ps, R.p, R.n);
-    R.start_bits.release();
+    // phrase numbering: per-tile popcounts of the start bitmap -> exclusive scan = index of a tile's first phrase
+    const u64 n_words = div_up(R.n, 32), n_tiles = div_up(n_words, FD_THREADS);
+    DevBuf<u32> tile_cnt(n_tiles, R.st);
+    DevBuf<u64> tile_base(n_tiles, R.st), ptot(1, R.st);
+    GRL_LAUNCH("tile_popc", R.n / 8, tile_popc_kernel, (unsigned)n_tiles, FD_THREADS, 0, R.st, R.start_bits.p, n_words, tile_cnt.p);
+    exclusive_scan<u32, u64>(tile_cnt.p, tile_base.p, n_tiles, ptot.p, R.st);
+    R.p = d2h_scalar(ptot.p, R.st);
+    static int fd_blocks_per_sm = 0, n_sm = 0;  // one pair per CellT instantiation
+    if (!fd_blocks_per_sm) {
+        GRL_CUDA(cudaFuncSetAttribute(dedup_kernel<CellT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fd_smem_bytes<CellT>()));
+        GRL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fd_blocks_per_sm, dedup_kernel<CellT>, FD_THREADS, fd_smem_bytes<CellT>()));
+        GRL_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device));
+        if (fd_blocks_per_sm < 1) fd_blocks_per_sm = 1;
+    }
+    const unsigned fd_grid = (unsigned)std::min<u64>(n_tiles, (u64)n_sm * fd_blocks_per_sm);  // persistent CTAs, tiles strided
 
     R.slot_of_phrase.alloc(R.p, R.st);
     DevBuf<u32> overflow(1, R.st);
@@ -203,7 +201,7 @@ void stage_dedup(Round& R) {
         R.table.alloc(cap, R.st);
         GRL_LAUNCH("table_init", cap * 16, table_init_kernel, grid_for(cap, 256), 256, 0, R.st, R.table.p, cap);
         overflow.zero();
-        GRL_LAUNCH("phrase_insert", (R.n + R.p) * sizeof(CellT) + R.p * (2 * sizeof(PosT) + 4 + 32), (phrase_insert_kernel<CellT, PosT>), grid_for(R.p, 256), 256, 0, R.st, text, ps, R.p, R.table.p, cap, R.slot_of_phrase.p, overflow.p);
+        GRL_LAUNCH("dedup", R.n * sizeof(CellT) + R.n / 4 + R.p * 4, (dedup_kernel<CellT>), fd_grid, FD_THREADS, fd_smem_bytes<CellT>(), R.st, text, R.n, R.start_bits.p, R.end_bits, tile_base.p, n_tiles, R.table.p, cap, R.slot_of_phrase.p, overflow.p);
         bool ovf = d2h_scalar(overflow.p, R.st) != 0;
         u64 d = 0;
         if (!ovf) {
@@ -225,7 +223,7 @@ void stage_dedup(Round& R) {
     R.ph_pos.alloc(R.d, R.st);
     R.ph_len.alloc(R.d, R.st);
     R.ph_freq.alloc(R.d, R.st);
-    GRL_LAUNCH("dict_meta", 0, (dict_meta_kernel<PosT>), grid_for(R.d, 256), 256, 0, R.st, R.table.p, R.occ_slots.p, R.d, ps, R.p, R.ph_pos.p, R.ph_len.p, R.ph_freq.p);
+    GRL_LAUNCH("dict_meta", 0, dict_meta_kernel, grid_for(R.d, 256), 256, 0, R.st, R.table.p, R.occ_slots.p, R.d, R.start_bits.p, R.end_bits, R.n, R.ph_pos.p, R.ph_len.p, R.ph_freq.p);
     R.ph_off.alloc(R.d + 1, R.st);
     DevBuf<u64> tot64(1, R.st);
     {   // offsets as u64 first to detect overflow of the 32-bit entry index space
@@ -248,7 +246,7 @@ void stage_dedup(Round& R) {
     GRL_CUDA(cudaStreamSynchronize(R.st));
     R.max_freq = hmx[0];
     R.max_len = hmx[1];
-    R.ps_raw.release();
+    R.start_bits.release();
 }
 
 template <class CellT, bool FIRST, class SymT>
@@ -414,7 +412,7 @@ void run_round_t(grlgpu_ctx* c, grlgpu_round_t* out) {
     t_all.start();
     t_text.start();
     stage_flags<CellT, FIRST>(R);
-    if (R.n < (1ull << 31)) stage_dedup<CellT, u32>(R); else stage_dedup<CellT, u64>(R);
+    stage_dedup<CellT>(R);
     t_text.stop();
     t_dict.start();
     const u64 A = c->alphabet;

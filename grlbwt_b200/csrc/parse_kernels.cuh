@@ -213,40 +213,44 @@ static __global__ void lms_resolve_kernel(const u8* __restrict__ block_state, u8
 
 // ------------------------------------------------------------------------------------------------
 // K3  phrase deduplication + counting (ext_hash_functor exact_par_phase.hpp:33-39; replaces the
-// XXH3-keyed Robin-Hood table hash_table.hpp:451-539). Open addressing, linear probing, 16-byte
-// entries {key = first-occurrence position << 24 | min(len, LEN_SAT), count}; a key is claimed
-// with one 64-bit CAS and is immediately complete because it points into the immutable text.
+// XXH3-keyed Robin-Hood table hash_table.hpp:451-539).
+//
+// Global table: open addressing, linear probing, 16-byte entries {key = first-occurrence position << 24 |
+// min(len, LEN_SAT), count}; a key is claimed with one 64-bit CAS and is immediately complete because it
+// points into the immutable text.
+//
+// dedup_kernel is the fused text pass: persistent CTAs walk tiles of 8192 cells staged in shared memory
+// (cells + look-ahead halo, start/end bitmap words); a thread owns one bitmap word, numbers its phrases
+// from the tile's scanned base and, for phrases of at most 15 bytes, packs the cells into a 128-bit key
+// and looks it up in a per-CTA shared-memory cache of hot phrases (key -> global slot, local count).
+// Hits cost shared memory only; counts are flushed to the global table once per CTA. Misses and longer
+// phrases take the global path (hash of the cells, probe, compare against the first occurrence).
 // ------------------------------------------------------------------------------------------------
 constexpr u64 HT_EMPTY = ~0ULL;
 constexpr u64 HT_LEN_SAT = 0xFFFFFFULL;
 constexpr int HT_MAX_PROBES = 512;
+constexpr u32 HT_OVERFLOW = 0xffffffffu;
 
-template <class PosT>
-struct PosFlag {
-    static constexpr PosT FLAG = PosT(1) << (sizeof(PosT) * 8 - 1);
-};
-
-// phrase j covers [s, e] (closed); fin = it is the last phrase of its string (parsing_strategies.h:126,141)
-template <class PosT>
-__device__ __forceinline__ void phrase_span(const PosT* __restrict__ ps, u64 j, u64& s, u64& e, bool& fin) {
-    constexpr PosT FLAG = PosFlag<PosT>::FLAG;
-    const PosT a = ps[j], b = ps[j + 1];
-    s = (u64)(a & ~FLAG);
-    fin = (b & FLAG) != 0;
-    e = fin ? (u64)(b & ~FLAG) - 1 : (u64)(b & ~FLAG);
-}
-
-template <class PosT>
-__device__ u64 phrase_len_at(const PosT* __restrict__ ps, u64 p, u64 pos) {  // true length of the phrase starting at pos
-    constexpr PosT FLAG = PosFlag<PosT>::FLAG;
-    u64 lo = 0, hi = p;
-    while (lo < hi) {
-        const u64 mid = (lo + hi) >> 1;
-        if ((u64)(ps[mid] & ~FLAG) < pos) lo = mid + 1; else hi = mid;
+// smallest position q > pos that starts a phrase, or n (the virtual start after the last cell)
+__device__ __forceinline__ u64 next_start_after(const u32* __restrict__ start_bits, u64 n, u64 pos) {
+    const u64 n_words = (n + 31) >> 5;
+    u64 q = pos + 1;
+    if (q >= n) return n;
+    u64 w = q >> 5;
+    u32 x = start_bits[w] & (0xffffffffu << (q & 31));
+    while (!x) {
+        if (++w >= n_words) return n;
+        x = start_bits[w];
     }
-    u64 s, e; bool f;
-    phrase_span<PosT>(ps, lo, s, e, f);
-    return e - s + 1;
+    q = (w << 5) + (u64)(__ffs(x) - 1);
+    return q < n ? q : n;
+}
+__device__ __forceinline__ bool bit_at(const u32* __restrict__ bits, u64 i) { return (bits[i >> 5] >> (i & 31)) & 1u; }
+
+// true length of the phrase that starts at pos (closed interval; the last phrase of a string stops at the string end)
+__device__ __forceinline__ u64 phrase_len_bits(const u32* __restrict__ start_bits, const u32* __restrict__ end_bits, u64 n, u64 pos) {
+    const u64 q = next_start_after(start_bits, n, pos);
+    return bit_at(end_bits, q - 1) ? q - pos : q - pos + 1;
 }
 
 template <class CellT>
@@ -256,15 +260,10 @@ __device__ __forceinline__ u64 phrase_hash(const CellT* __restrict__ text, u64 s
     return mix64(h);
 }
 
-template <class CellT, class PosT>
-__global__ void __launch_bounds__(256) phrase_insert_kernel(const CellT* __restrict__ text, const PosT* __restrict__ ps, u64 p, ulonglong2* table,
-                                                            u64 cap, u32* __restrict__ slot_of_phrase, u32* overflow) {
-    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= p) return;
-    if (*reinterpret_cast<volatile u32*>(overflow)) return;  // the table is too small: the host regrows it and redoes the pass
-    u64 s, e; bool fin;
-    phrase_span<PosT>(ps, j, s, e, fin);
-    const u64 len = e - s + 1;
+// global path: returns the slot of phrase text[s, s+len) (claiming it if new) and adds one occurrence
+template <class CellT>
+__device__ u32 table_insert_global(const CellT* __restrict__ text, u64 s, u64 len, ulonglong2* table, u64 cap, const u32* __restrict__ start_bits,
+                                   const u32* __restrict__ end_bits, u64 n, u32* overflow) {
     const u64 lenf = len < HT_LEN_SAT ? len : HT_LEN_SAT;
     const u64 mykey = (s << 24) | lenf;
     u64 slot = __umul64hi(phrase_hash<CellT>(text, s, len), cap);  // uniform over [0, cap), cap need not be a power of two
@@ -280,16 +279,154 @@ __global__ void __launch_bounds__(256) phrase_insert_kernel(const CellT* __restr
             match = true;
             for (u64 i = 0; i < len; i++)
                 if (text[kpos + i] != text[s + i]) { match = false; break; }
-            if (match && lenf == HT_LEN_SAT) match = phrase_len_at<PosT>(ps, p, kpos) == len;
+            if (match && lenf == HT_LEN_SAT) match = phrase_len_bits(start_bits, end_bits, n, kpos) == len;
         }
         if (match) {
             atomicAdd(&table[slot].y, 1ULL);
-            slot_of_phrase[j] = (u32)slot | (fin ? 0x80000000u : 0u);
-            return;
+            return (u32)slot;
         }
         if (++slot == cap) slot = 0;
     }
     atomicExch(overflow, 1u);
+    return HT_OVERFLOW;
+}
+
+constexpr int FD_THREADS = 256;
+constexpr int FD_TILE = FD_THREADS * 32;       // cells per tile: one bitmap word per thread
+constexpr int FD_HALO_WORDS = 4;               // look-ahead for the end of a phrase: 128 cells
+constexpr int FD_HALO = FD_HALO_WORDS * 32;
+constexpr int FD_WORDS = FD_THREADS + FD_HALO_WORDS;
+constexpr int FD_CACHE = 2048;                 // hot-phrase cache entries per CTA
+constexpr int FD_CACHE_BITS = 11;
+
+template <class CellT>
+__host__ __device__ constexpr size_t fd_cell_bytes() { return sizeof(CellT) < 8 ? (size_t)(FD_TILE + FD_HALO) * sizeof(CellT) + 32 : 0; }  // + slack for the 3 x u64 window
+template <class CellT>
+constexpr size_t fd_smem_bytes() {
+    return fd_cell_bytes<CellT>()                                          // staged cells
+           + 2 * FD_WORDS * sizeof(u32)                                    // start / end words
+           + (size_t)FD_CACHE * (8 + 8 + 4 + 4 + 4)                        // cache: k0, k1, slot, count, state
+           + 40 * sizeof(u32);                                             // scan scratch + flags
+}
+
+// per-tile phrase counts (tile = FD_THREADS bitmap words)
+static __global__ void __launch_bounds__(FD_THREADS) tile_popc_kernel(const u32* __restrict__ start_bits, u64 n_words, u32* __restrict__ tile_cnt) {
+    __shared__ u32 sm[33];
+    const u64 w = (u64)blockIdx.x * FD_THREADS + threadIdx.x;
+    u32 c = w < n_words ? __popc(start_bits[w]) : 0u, tot;
+    block_exclusive_sum<u32>(c, sm, tot);
+    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = tot;
+}
+
+template <class CellT>
+__global__ void __launch_bounds__(FD_THREADS) dedup_kernel(const CellT* __restrict__ text, u64 n, const u32* __restrict__ start_bits,
+                                                           const u32* __restrict__ end_bits, const u64* __restrict__ tile_base, u64 n_tiles,
+                                                           ulonglong2* table, u64 cap, u32* __restrict__ slot_of_phrase, u32* overflow) {
+    extern __shared__ __align__(16) unsigned char fd_smem[];
+    constexpr int W = sizeof(CellT);
+    constexpr bool USE_SMEM = W < 8;  // 8-byte cells never fit a 15-byte key: global path only
+    unsigned char* s_cells = fd_smem;
+    u32* s_start = reinterpret_cast<u32*>(fd_smem + fd_cell_bytes<CellT>());
+    u32* s_end = s_start + FD_WORDS;
+    volatile u64* c_k0 = reinterpret_cast<volatile u64*>(s_end + FD_WORDS + (((FD_WORDS * 2) & 1) ? 1 : 0));
+    volatile u64* c_k1 = c_k0 + FD_CACHE;
+    volatile u32* c_slot = reinterpret_cast<volatile u32*>(c_k1 + FD_CACHE);
+    volatile u32* c_cnt = c_slot + FD_CACHE;
+    volatile u32* c_state = c_cnt + FD_CACHE;
+    u32* s_scan = const_cast<u32*>(c_state) + FD_CACHE;  // 33 words scratch, [34] = abort flag
+
+    const u64 n_words = (n + 31) >> 5;
+    for (int i = threadIdx.x; i < FD_CACHE; i += FD_THREADS) { c_state[i] = 0; c_cnt[i] = 0; }
+
+    for (u64 t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        if (threadIdx.x == 0) s_scan[34] = *reinterpret_cast<volatile u32*>(overflow);
+        __syncthreads();  // also orders the previous tile's shared-memory reads before this tile's loads
+        if (s_scan[34]) break;  // the table is too small: the host regrows it and redoes the pass
+        const u64 tile0 = t * FD_TILE, word0 = t * FD_THREADS;
+        // ---- stage cells (16-byte vectors), bitmap words ----
+        if (USE_SMEM) {
+            const u64 cells_here = (n - tile0) < (u64)(FD_TILE + FD_HALO) ? (n - tile0) : (u64)(FD_TILE + FD_HALO);
+            const u64 bytes = cells_here * W, nvec = bytes >> 4;
+            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(text) + tile0 * W);
+            uint4* dst = reinterpret_cast<uint4*>(s_cells);
+            for (u64 v = threadIdx.x; v < nvec; v += FD_THREADS) dst[v] = src[v];
+            const unsigned char* tsrc = reinterpret_cast<const unsigned char*>(text) + tile0 * W;
+            for (u64 b = (nvec << 4) + threadIdx.x; b < bytes; b += FD_THREADS) s_cells[b] = tsrc[b];
+        }
+        for (int k = threadIdx.x; k < FD_WORDS; k += FD_THREADS) {
+            const u64 wi = word0 + k;
+            s_start[k] = wi < n_words ? start_bits[wi] : 0u;
+            s_end[k] = wi < n_words ? end_bits[wi] : 0u;
+        }
+        const u32 mine = (word0 + threadIdx.x) < n_words ? start_bits[word0 + threadIdx.x] : 0u;  // real starts of my 32 cells
+        __syncthreads();
+        if (threadIdx.x == 0) {  // position n acts as a start so the last phrase finds its end
+            const u64 vw = n >> 5;
+            if (vw >= word0 && vw < word0 + FD_WORDS) s_start[vw - word0] |= 1u << (n & 31);
+        }
+        u32 tot;
+        const u32 pre = block_exclusive_sum<u32>(__popc(mine), s_scan, tot);  // contains __syncthreads: the virtual bit is visible after it
+        u64 j = tile_base[t] + pre;
+        u32 x = mine;
+        while (x) {
+            const u32 b = __ffs(x) - 1;
+            x &= x - 1;
+            const u32 sl = threadIdx.x * 32 + b;  // tile-local start
+            // ---- end of the phrase: next start (shared words incl. halo), else global scan ----
+            u32 wq = threadIdx.x;
+            u32 y = b == 31 ? 0u : (s_start[wq] & (0xffffffffu << (b + 1)));
+            while (!y && wq + 1 < FD_WORDS) y = s_start[++wq];
+            u64 len;
+            bool fin, staged = false;
+            if (y) {
+                const u32 nl = wq * 32 + (__ffs(y) - 1);
+                fin = (s_end[(nl - 1) >> 5] >> ((nl - 1) & 31)) & 1u;
+                len = (u64)(fin ? nl - 1 : nl) - sl + 1;
+                staged = true;
+            } else {
+                const u64 q = next_start_after(start_bits, n, tile0 + sl);
+                fin = bit_at(end_bits, q - 1);
+                len = (fin ? q - 1 : q) - (tile0 + sl) + 1;
+            }
+            u32 slot;
+            const u64 nb = len * W;
+            if (USE_SMEM && staged && nb <= 15) {
+                // ---- 128-bit key: the phrase's bytes, little endian, length in the top byte ----
+                const u32 bo = sl * W, sh = (bo & 7u) * 8u;
+                const u64* q8 = reinterpret_cast<const u64*>(s_cells + (bo & ~7u));
+                const u64 w0 = q8[0], w1 = q8[1], w2 = q8[2];
+                u64 k0 = sh ? ((w0 >> sh) | (w1 << (64 - sh))) : w0;
+                u64 k1 = sh ? ((w1 >> sh) | (w2 << (64 - sh))) : w1;
+                if (nb < 8) { k0 &= (1ULL << (nb * 8)) - 1ULL; k1 = 0; }
+                else if (nb == 8) k1 = 0;
+                else k1 &= (1ULL << ((nb - 8) * 8)) - 1ULL;
+                k1 |= len << 56;
+                const u32 ci = (u32)(((k0 ^ (k1 * 0x9E3779B97F4A7C15ULL)) * 0xff51afd7ed558ccdULL) >> (64 - FD_CACHE_BITS));
+                const u32 stt = c_state[ci];
+                if (stt == 2u && c_k0[ci] == k0 && c_k1[ci] == k1) {
+                    atomicAdd(const_cast<u32*>(&c_cnt[ci]), 1u);
+                    slot = c_slot[ci];
+                } else {
+                    const bool claimed = stt == 0u && atomicCAS(const_cast<u32*>(&c_state[ci]), 0u, 1u) == 0u;
+                    slot = table_insert_global<CellT>(text, tile0 + sl, len, table, cap, start_bits, end_bits, n, overflow);
+                    if (claimed) {
+                        if (slot != HT_OVERFLOW) {
+                            c_k0[ci] = k0; c_k1[ci] = k1; c_slot[ci] = slot;
+                            __threadfence_block();
+                            c_state[ci] = 2u;
+                        } else c_state[ci] = 0u;
+                    }
+                }
+            } else {
+                slot = table_insert_global<CellT>(text, tile0 + sl, len, table, cap, start_bits, end_bits, n, overflow);
+            }
+            slot_of_phrase[j++] = (slot & 0x7fffffffu) | (fin ? 0x80000000u : 0u);
+        }
+    }
+    // ---- flush the cached counts ----
+    __syncthreads();
+    for (int i = threadIdx.x; i < FD_CACHE; i += FD_THREADS)
+        if (c_state[i] == 2u && c_cnt[i]) atomicAdd(&table[c_slot[i]].y, (u64)c_cnt[i]);
 }
 
 static __global__ void __launch_bounds__(256) table_occupancy_kernel(const ulonglong2* __restrict__ table, u64 cap, u32* __restrict__ occ_bits) {
