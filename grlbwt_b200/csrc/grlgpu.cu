@@ -167,28 +167,52 @@ void stage_flags(Round& R) {
     }
 }
 
+template <class CellT, class PosT>
+void insert_uncached(Round& R, BitmapCompactor& bc, DevBuf<u8>& ps_raw, u64 j0, u64 cap, u32* overflow) {
+    grlgpu_ctx* c = R.c;
+    if (!ps_raw.p) {  // compacted phrase starts (top bit: starts a string), sentinel ps[p] = n | FLAG
+        ps_raw.alloc((R.p + 1) * sizeof(PosT), R.st);
+        bc.write<PosT>(R.end_bits, (PosT*)ps_raw.p);
+        const PosT sentinel = (PosT)R.n | PosFlag<PosT>::FLAG;
+        GRL_CUDA(cudaMemcpyAsync((PosT*)ps_raw.p + R.p, &sentinel, sizeof(PosT), cudaMemcpyHostToDevice, R.st));
+        GRL_CUDA(cudaStreamSynchronize(R.st));
+    }
+    const u64 cnt = R.p - j0;
+    GRL_LAUNCH("phrase_insert", (R.n + cnt) * sizeof(CellT) + cnt * (2 * sizeof(PosT) + 4 + 32), (phrase_insert_kernel<CellT, PosT>), grid_for(cnt, 256), 256, 0, R.st,
+               (const CellT*)c->text, R.n, (const PosT*)ps_raw.p, j0, R.p, R.start_bits.p, R.end_bits, R.table.p, cap, R.slot_of_phrase.p, overflow);
+}
+
 template <class CellT>
 void stage_dedup(Round& R) {
     grlgpu_ctx* c = R.c;
     const CellT* text = (const CellT*)c->text;
     // phrase numbering: per-tile popcounts of the start bitmap -> exclusive scan = index of a tile's first phrase
-    const u64 n_words = div_up(R.n, 32), n_tiles = div_up(n_words, FD_THREADS);
+    constexpr int TW = fd_tile_words<CellT>();
+    const u64 n_words = div_up(R.n, 32), n_tiles = div_up(n_words, TW);
     DevBuf<u32> tile_cnt(n_tiles, R.st);
     DevBuf<u64> tile_base(n_tiles, R.st), ptot(1, R.st);
-    GRL_LAUNCH("tile_popc", R.n / 8, tile_popc_kernel, (unsigned)n_tiles, FD_THREADS, 0, R.st, R.start_bits.p, n_words, tile_cnt.p);
+    GRL_LAUNCH("tile_popc", R.n / 8, tile_popc_kernel, (unsigned)n_tiles, 256, 0, R.st, R.start_bits.p, n_words, TW, tile_cnt.p);
     exclusive_scan<u32, u64>(tile_cnt.p, tile_base.p, n_tiles, ptot.p, R.st);
     R.p = d2h_scalar(ptot.p, R.st);
-    static int fd_blocks_per_sm = 0, n_sm = 0;  // one pair per CellT instantiation
-    if (!fd_blocks_per_sm) {
-        GRL_CUDA(cudaFuncSetAttribute(dedup_kernel<CellT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fd_smem_bytes<CellT>()));
-        GRL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fd_blocks_per_sm, dedup_kernel<CellT>, FD_THREADS, fd_smem_bytes<CellT>()));
+    static int n_sm = 0;  // one per CellT instantiation
+    if (!n_sm) {
+        GRL_CUDA(cudaFuncSetAttribute(dedup_cached_kernel<CellT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fd_smem_bytes<CellT>()));
         GRL_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device));
-        if (fd_blocks_per_sm < 1) fd_blocks_per_sm = 1;
     }
-    const unsigned fd_grid = (unsigned)std::min<u64>(n_tiles, (u64)n_sm * fd_blocks_per_sm);  // persistent CTAs, tiles strided
+    const unsigned fd_grid = (unsigned)std::min<u64>(n_tiles, (u64)n_sm);  // persistent CTAs (one per SM), tiles strided
+    // the first tiles always run through the cached kernel and report how many phrases missed the caches;
+    // the rest of the text takes the cached kernel (duplicate-heavy) or the thread-per-phrase kernel (unique-heavy)
+    const bool force_uncached = (c->flags & GRLGPU_FLAG_FORCE_UNCACHED) != 0;
+    const u64 t_pilot = force_uncached ? 0 : std::min<u64>(n_tiles, (c->flags & GRLGPU_FLAG_SMALL_PILOT) ? 1ull : 4ull * fd_grid);
+    u64 j_pilot = R.p;
+    if (t_pilot < n_tiles) j_pilot = t_pilot ? d2h_scalar(tile_base.p + t_pilot, R.st) : 0;
+    BitmapCompactor bc;
+    DevBuf<u8> ps_raw;
+    bool counted = false;
 
     R.slot_of_phrase.alloc(R.p, R.st);
     DevBuf<u32> overflow(1, R.st);
+    DevBuf<u64> stats(2, R.st);
     // capacity (any multiple of 256; slot = mulhi(hash, cap)): 1.6 p slots, so that load <= 0.625 and the pass
     // cannot overflow, while that stays below 2^31 slots (slot ids are 31 bits); beyond that (p > 1.3e9, e.g.
     // round 1 of a multi-GB text whose dictionary is tiny) start at 2^28 slots and regrow on demand
@@ -201,7 +225,34 @@ void stage_dedup(Round& R) {
         R.table.alloc(cap, R.st);
         GRL_LAUNCH("table_init", cap * 16, table_init_kernel, grid_for(cap, 256), 256, 0, R.st, R.table.p, cap);
         overflow.zero();
-        GRL_LAUNCH("dedup", R.n * sizeof(CellT) + R.n / 4 + R.p * 4, (dedup_kernel<CellT>), fd_grid, FD_THREADS, fd_smem_bytes<CellT>(), R.st, text, R.n, R.start_bits.p, R.end_bits, tile_base.p, n_tiles, R.table.p, cap, R.slot_of_phrase.p, overflow.p);
+        stats.zero();
+        bool cached_rest = true;
+        if (t_pilot) {
+            const u64 cells = std::min<u64>(R.n, t_pilot * TW * 32);
+            GRL_LAUNCH("dedup_cached", cells * sizeof(CellT) + cells / 4 + j_pilot * 4, (dedup_cached_kernel<CellT>), fd_grid, FD_THREADS, fd_smem_bytes<CellT>(), R.st,
+                       text, R.n, R.start_bits.p, R.end_bits, tile_base.p, (u64)0, t_pilot, R.table.p, cap, R.slot_of_phrase.p, overflow.p, stats.p);
+        }
+        if (t_pilot < n_tiles) {
+            if (t_pilot) {
+                u64 hs[2];
+                GRL_CUDA(cudaMemcpyAsync(hs, stats.p, 16, cudaMemcpyDeviceToHost, R.st));
+                GRL_CUDA(cudaStreamSynchronize(R.st));
+                cached_rest = hs[0] * 2 <= hs[1];  // at most half of the pilot's phrases had to go to the global table
+            } else cached_rest = false;
+            if (cached_rest) {
+                const u64 cells = R.n - t_pilot * TW * 32;
+                GRL_LAUNCH("dedup_cached", cells * sizeof(CellT) + cells / 4 + (R.p - j_pilot) * 4, (dedup_cached_kernel<CellT>), fd_grid, FD_THREADS, fd_smem_bytes<CellT>(),
+                           R.st, text, R.n, R.start_bits.p, R.end_bits, tile_base.p, t_pilot, n_tiles, R.table.p, cap, R.slot_of_phrase.p, overflow.p, (u64*)nullptr);
+            } else {
+                if (!counted) {
+                    const u64 pc = bc.count(R.start_bits.p, R.n, R.st);
+                    if (pc != R.p) throw Error(GRLGPU_ERR_STATE, "phrase count mismatch between tile counts and compaction");
+                    counted = true;
+                }
+                if (R.n < (1ull << 31)) insert_uncached<CellT, u32>(R, bc, ps_raw, j_pilot, cap, overflow.p);
+                else insert_uncached<CellT, u64>(R, bc, ps_raw, j_pilot, cap, overflow.p);
+            }
+        }
         bool ovf = d2h_scalar(overflow.p, R.st) != 0;
         u64 d = 0;
         if (!ovf) {
@@ -220,6 +271,7 @@ void stage_dedup(Round& R) {
         if (cap >= cap_max) throw Error(GRLGPU_ERR_LIMIT, "phrase table would exceed 2^31 slots");
         cap = std::min<u64>(cap * 4, std::min<u64>(want, cap_max));  // too full: regrow and redo the pass
     }
+    ps_raw.release();
     R.ph_pos.alloc(R.d, R.st);
     R.ph_len.alloc(R.d, R.st);
     R.ph_freq.alloc(R.d, R.st);

@@ -291,142 +291,239 @@ __device__ u32 table_insert_global(const CellT* __restrict__ text, u64 s, u64 le
     return HT_OVERFLOW;
 }
 
-constexpr int FD_THREADS = 256;
-constexpr int FD_TILE = FD_THREADS * 32;       // cells per tile: one bitmap word per thread
-constexpr int FD_HALO_WORDS = 4;               // look-ahead for the end of a phrase: 128 cells
-constexpr int FD_HALO = FD_HALO_WORDS * 32;
-constexpr int FD_WORDS = FD_THREADS + FD_HALO_WORDS;
-constexpr int FD_CACHE = 2048;                 // hot-phrase cache entries per CTA
-constexpr int FD_CACHE_BITS = 11;
-
-template <class CellT>
-__host__ __device__ constexpr size_t fd_cell_bytes() { return sizeof(CellT) < 8 ? (size_t)(FD_TILE + FD_HALO) * sizeof(CellT) + 32 : 0; }  // + slack for the 3 x u64 window
-template <class CellT>
-constexpr size_t fd_smem_bytes() {
-    return fd_cell_bytes<CellT>()                                          // staged cells
-           + 2 * FD_WORDS * sizeof(u32)                                    // start / end words
-           + (size_t)FD_CACHE * (8 + 8 + 4 + 4 + 4)                        // cache: k0, k1, slot, count, state
-           + 40 * sizeof(u32);                                             // scan scratch + flags
+// ---- thread-per-phrase variant over a compacted start array (unique-heavy rounds: maximum memory-level parallelism) ----
+template <class PosT>
+struct PosFlag {
+    static constexpr PosT FLAG = PosT(1) << (sizeof(PosT) * 8 - 1);
+};
+// phrase j covers [s, e] (closed); fin = it is the last phrase of its string (parsing_strategies.h:126,141)
+template <class PosT>
+__device__ __forceinline__ void phrase_span(const PosT* __restrict__ ps, u64 j, u64& s, u64& e, bool& fin) {
+    constexpr PosT FLAG = PosFlag<PosT>::FLAG;
+    const PosT a = ps[j], b = ps[j + 1];
+    s = (u64)(a & ~FLAG);
+    fin = (b & FLAG) != 0;
+    e = fin ? (u64)(b & ~FLAG) - 1 : (u64)(b & ~FLAG);
+}
+template <class CellT, class PosT>
+__global__ void __launch_bounds__(256) phrase_insert_kernel(const CellT* __restrict__ text, u64 n, const PosT* __restrict__ ps, u64 j0, u64 p,
+                                                            const u32* __restrict__ start_bits, const u32* __restrict__ end_bits, ulonglong2* table,
+                                                            u64 cap, u32* __restrict__ slot_of_phrase, u32* overflow) {
+    const u64 j = j0 + (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p) return;
+    if (*reinterpret_cast<volatile u32*>(overflow)) return;  // the table is too small: the host regrows it and redoes the pass
+    u64 s, e; bool fin;
+    phrase_span<PosT>(ps, j, s, e, fin);
+    const u32 slot = table_insert_global<CellT>(text, s, e - s + 1, table, cap, start_bits, end_bits, n, overflow);
+    slot_of_phrase[j] = (slot & 0x7fffffffu) | (fin ? 0x80000000u : 0u);
 }
 
-// per-tile phrase counts (tile = FD_THREADS bitmap words)
-static __global__ void __launch_bounds__(FD_THREADS) tile_popc_kernel(const u32* __restrict__ start_bits, u64 n_words, u32* __restrict__ tile_cnt) {
+// ---- fused, cached variant (duplicate-heavy rounds) ----
+constexpr int FD_THREADS = 1024;               // one CTA per SM
+constexpr int FD_TILE_BYTES = 32768;           // staged cells per tile: 32768 / sizeof(CellT) cells
+constexpr int FD_HALO_WORDS = 4;               // look-ahead for the end of a tile's last phrases: 128 cells
+constexpr int FD_HALO = FD_HALO_WORDS * 32;
+constexpr int FD_LIST_CAP = 16384;             // phrase starts of one tile (u16 tile-local positions)
+constexpr int FD_MISS_CAP = 8192;              // deferred phrases of one tile
+constexpr int FD_CACHE = 4096;                 // hot-phrase cache entries per CTA, 2-way
+constexpr int FD_CACHE_BITS = 12;
+constexpr u32 FD_NONE = 0xffffffffu;
+
+template <class CellT>
+__host__ __device__ constexpr int fd_tile_words() { return FD_TILE_BYTES / 32 / (int)sizeof(CellT); }  // bitmap words per tile
+template <class CellT>
+__host__ __device__ constexpr size_t fd_cell_bytes() { return (size_t)FD_TILE_BYTES + (size_t)FD_HALO * sizeof(CellT) + 32; }  // + slack for the 3 x u64 window
+template <class CellT>
+__host__ __device__ constexpr size_t fd_smem_bytes() {
+    return fd_cell_bytes<CellT>() + 2 * (size_t)(fd_tile_words<CellT>() + FD_HALO_WORDS) * sizeof(u32)  // cells, start / end words
+           + (size_t)FD_LIST_CAP * 2 + (size_t)FD_MISS_CAP * 2                                         // start list, deferred list
+           + (size_t)FD_CACHE * (8 + 8 + 4 + 4 + 4)                                                     // cache: k0, k1, slot, count, state
+           + 64 * sizeof(u32);                                                                          // scan scratch + scalars
+}
+
+// per-tile phrase counts (tile = words_per_tile bitmap words)
+static __global__ void __launch_bounds__(256) tile_popc_kernel(const u32* __restrict__ start_bits, u64 n_words, int words_per_tile, u32* __restrict__ tile_cnt) {
     __shared__ u32 sm[33];
-    const u64 w = (u64)blockIdx.x * FD_THREADS + threadIdx.x;
-    u32 c = w < n_words ? __popc(start_bits[w]) : 0u, tot;
+    const u64 w0 = (u64)blockIdx.x * words_per_tile;
+    u32 c = 0, tot;
+    for (int k = threadIdx.x; k < words_per_tile; k += 256)
+        if (w0 + k < n_words) c += __popc(start_bits[w0 + k]);
     block_exclusive_sum<u32>(c, sm, tot);
     if (threadIdx.x == 0) tile_cnt[blockIdx.x] = tot;
 }
 
+// 128-bit key of the phrase cells[sl, sl+len): its bytes, little endian, length in the top byte (len * W <= 15)
+template <int W>
+__device__ __forceinline__ void fd_pack_key(const unsigned char* s_cells, u32 sl, u64 len, u64& k0, u64& k1) {
+    const u32 bo = sl * W, sh = (bo & 7u) * 8u;
+    const u64 nb = len * W;
+    const u64* q8 = reinterpret_cast<const u64*>(s_cells + (bo & ~7u));
+    const u64 w0 = q8[0], w1 = q8[1], w2 = q8[2];
+    k0 = sh ? ((w0 >> sh) | (w1 << (64 - sh))) : w0;
+    k1 = sh ? ((w1 >> sh) | (w2 << (64 - sh))) : w1;
+    if (nb < 8) { k0 &= (1ULL << (nb * 8)) - 1ULL; k1 = 0; }
+    else if (nb == 8) k1 = 0;
+    else k1 &= (1ULL << ((nb - 8) * 8)) - 1ULL;
+    k1 |= len << 56;
+}
+
+// stats[0] += phrases that took the global path, stats[1] += phrases seen (the host reads them after a pilot launch)
 template <class CellT>
-__global__ void __launch_bounds__(FD_THREADS) dedup_kernel(const CellT* __restrict__ text, u64 n, const u32* __restrict__ start_bits,
-                                                           const u32* __restrict__ end_bits, const u64* __restrict__ tile_base, u64 n_tiles,
-                                                           ulonglong2* table, u64 cap, u32* __restrict__ slot_of_phrase, u32* overflow) {
+__global__ void __launch_bounds__(FD_THREADS, 1) dedup_cached_kernel(const CellT* __restrict__ text, u64 n, const u32* __restrict__ start_bits,
+                                                                     const u32* __restrict__ end_bits, const u64* __restrict__ tile_base, u64 t_begin,
+                                                                     u64 t_end, ulonglong2* table, u64 cap, u32* __restrict__ slot_of_phrase,
+                                                                     u32* overflow, u64* stats) {
     extern __shared__ __align__(16) unsigned char fd_smem[];
     constexpr int W = sizeof(CellT);
-    constexpr bool USE_SMEM = W < 8;  // 8-byte cells never fit a 15-byte key: global path only
+    constexpr int TW = fd_tile_words<CellT>();
+    constexpr int NW = TW + FD_HALO_WORDS;
+    constexpr int TILE = TW * 32;
     unsigned char* s_cells = fd_smem;
     u32* s_start = reinterpret_cast<u32*>(fd_smem + fd_cell_bytes<CellT>());
-    u32* s_end = s_start + FD_WORDS;
-    volatile u64* c_k0 = reinterpret_cast<volatile u64*>(s_end + FD_WORDS + (((FD_WORDS * 2) & 1) ? 1 : 0));
+    u32* s_end = s_start + NW;
+    u16* s_list = reinterpret_cast<u16*>(s_end + NW);
+    u16* s_miss = s_list + FD_LIST_CAP;
+    volatile u64* c_k0 = reinterpret_cast<volatile u64*>(s_miss + FD_MISS_CAP);
     volatile u64* c_k1 = c_k0 + FD_CACHE;
     volatile u32* c_slot = reinterpret_cast<volatile u32*>(c_k1 + FD_CACHE);
     volatile u32* c_cnt = c_slot + FD_CACHE;
     volatile u32* c_state = c_cnt + FD_CACHE;
-    u32* s_scan = const_cast<u32*>(c_state) + FD_CACHE;  // 33 words scratch, [34] = abort flag
-
+    u32* s_scan = const_cast<u32*>(c_state) + FD_CACHE;  // [0..32] scan scratch, [40] abort, [41] tail next, [42] deferred count
     const u64 n_words = (n + 31) >> 5;
+    u64 my_global = 0, my_seen = 0;
     for (int i = threadIdx.x; i < FD_CACHE; i += FD_THREADS) { c_state[i] = 0; c_cnt[i] = 0; }
 
-    for (u64 t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        if (threadIdx.x == 0) s_scan[34] = *reinterpret_cast<volatile u32*>(overflow);
+    for (u64 t = t_begin + blockIdx.x; t < t_end; t += gridDim.x) {
+        if (threadIdx.x == 0) { s_scan[40] = *reinterpret_cast<volatile u32*>(overflow); s_scan[42] = 0; }
         __syncthreads();  // also orders the previous tile's shared-memory reads before this tile's loads
-        if (s_scan[34]) break;  // the table is too small: the host regrows it and redoes the pass
-        const u64 tile0 = t * FD_TILE, word0 = t * FD_THREADS;
-        // ---- stage cells (16-byte vectors), bitmap words ----
-        if (USE_SMEM) {
-            const u64 cells_here = (n - tile0) < (u64)(FD_TILE + FD_HALO) ? (n - tile0) : (u64)(FD_TILE + FD_HALO);
+        if (s_scan[40]) break;  // the table is too small: the host regrows it and redoes the pass
+        const u64 tile0 = t * TILE, word0 = t * TW;
+        // ---- P0: stage cells (16-byte vectors) and bitmap words ----
+        {
+            const u64 cells_here = (n - tile0) < (u64)(TILE + FD_HALO) ? (n - tile0) : (u64)(TILE + FD_HALO);
             const u64 bytes = cells_here * W, nvec = bytes >> 4;
-            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(text) + tile0 * W);
+            const unsigned char* tsrc = reinterpret_cast<const unsigned char*>(text) + tile0 * W;
+            const uint4* src = reinterpret_cast<const uint4*>(tsrc);
             uint4* dst = reinterpret_cast<uint4*>(s_cells);
             for (u64 v = threadIdx.x; v < nvec; v += FD_THREADS) dst[v] = src[v];
-            const unsigned char* tsrc = reinterpret_cast<const unsigned char*>(text) + tile0 * W;
             for (u64 b = (nvec << 4) + threadIdx.x; b < bytes; b += FD_THREADS) s_cells[b] = tsrc[b];
         }
-        for (int k = threadIdx.x; k < FD_WORDS; k += FD_THREADS) {
+        for (int k = threadIdx.x; k < NW; k += FD_THREADS) {
             const u64 wi = word0 + k;
             s_start[k] = wi < n_words ? start_bits[wi] : 0u;
             s_end[k] = wi < n_words ? end_bits[wi] : 0u;
         }
-        const u32 mine = (word0 + threadIdx.x) < n_words ? start_bits[word0 + threadIdx.x] : 0u;  // real starts of my 32 cells
         __syncthreads();
-        if (threadIdx.x == 0) {  // position n acts as a start so the last phrase finds its end
-            const u64 vw = n >> 5;
-            if (vw >= word0 && vw < word0 + FD_WORDS) s_start[vw - word0] |= 1u << (n & 31);
-        }
+        // ---- P1: tile-local positions of the phrase starts, in order ----
+        const u32 mine = (int)threadIdx.x < TW ? s_start[threadIdx.x] : 0u;  // real starts (bits >= n are zero in the bitmap)
         u32 tot;
-        const u32 pre = block_exclusive_sum<u32>(__popc(mine), s_scan, tot);  // contains __syncthreads: the virtual bit is visible after it
-        u64 j = tile_base[t] + pre;
-        u32 x = mine;
-        while (x) {
-            const u32 b = __ffs(x) - 1;
-            x &= x - 1;
-            const u32 sl = threadIdx.x * 32 + b;  // tile-local start
-            // ---- end of the phrase: next start (shared words incl. halo), else global scan ----
-            u32 wq = threadIdx.x;
-            u32 y = b == 31 ? 0u : (s_start[wq] & (0xffffffffu << (b + 1)));
-            while (!y && wq + 1 < FD_WORDS) y = s_start[++wq];
-            u64 len;
-            bool fin, staged = false;
-            if (y) {
-                const u32 nl = wq * 32 + (__ffs(y) - 1);
-                fin = (s_end[(nl - 1) >> 5] >> ((nl - 1) & 31)) & 1u;
-                len = (u64)(fin ? nl - 1 : nl) - sl + 1;
-                staged = true;
-            } else {
-                const u64 q = next_start_after(start_bits, n, tile0 + sl);
-                fin = bit_at(end_bits, q - 1);
-                len = (fin ? q - 1 : q) - (tile0 + sl) + 1;
+        const u32 pre = block_exclusive_sum<u32>(__popc(mine), s_scan, tot);
+        if (threadIdx.x == 0) {
+            const u64 vw = n >> 5;  // position n acts as a start so the last phrase finds its end
+            if (vw >= word0 && vw < word0 + NW) s_start[vw - word0] |= 1u << (n & 31);
+            u32 tn = FD_NONE;
+            for (int k = TW; k < NW; k++)
+                if (s_start[k]) { tn = k * 32 + (__ffs(s_start[k]) - 1); break; }
+            s_scan[41] = tn;
+        }
+        const u64 jbase = tile_base[t];
+        if (tot <= (u32)FD_LIST_CAP) {
+            u32 x = mine, o = pre;
+            while (x) { s_list[o++] = (u16)(threadIdx.x * 32 + (__ffs(x) - 1)); x &= x - 1; }
+        }
+        __syncthreads();
+        my_seen += (threadIdx.x == 0) ? tot : 0;
+        if (tot > (u32)FD_LIST_CAP) {
+            // pathological tile (more starts than the list holds, e.g. runs of empty strings): owner-thread loop, global path
+            u32 x = mine;
+            u64 j = jbase + pre;
+            while (x) {
+                const u32 b = __ffs(x) - 1;
+                x &= x - 1;
+                const u64 s = tile0 + threadIdx.x * 32 + b;
+                const u64 q = next_start_after(start_bits, n, s);
+                const bool fin = bit_at(end_bits, q - 1);
+                const u32 slot = table_insert_global<CellT>(text, s, (fin ? q - 1 : q) - s + 1, table, cap, start_bits, end_bits, n, overflow);
+                slot_of_phrase[j++] = (slot & 0x7fffffffu) | (fin ? 0x80000000u : 0u);
+                my_global++;
             }
-            u32 slot;
-            const u64 nb = len * W;
-            if (USE_SMEM && staged && nb <= 15) {
-                // ---- 128-bit key: the phrase's bytes, little endian, length in the top byte ----
-                const u32 bo = sl * W, sh = (bo & 7u) * 8u;
-                const u64* q8 = reinterpret_cast<const u64*>(s_cells + (bo & ~7u));
-                const u64 w0 = q8[0], w1 = q8[1], w2 = q8[2];
-                u64 k0 = sh ? ((w0 >> sh) | (w1 << (64 - sh))) : w0;
-                u64 k1 = sh ? ((w1 >> sh) | (w2 << (64 - sh))) : w1;
-                if (nb < 8) { k0 &= (1ULL << (nb * 8)) - 1ULL; k1 = 0; }
-                else if (nb == 8) k1 = 0;
-                else k1 &= (1ULL << ((nb - 8) * 8)) - 1ULL;
-                k1 |= len << 56;
-                const u32 ci = (u32)(((k0 ^ (k1 * 0x9E3779B97F4A7C15ULL)) * 0xff51afd7ed558ccdULL) >> (64 - FD_CACHE_BITS));
-                const u32 stt = c_state[ci];
-                if (stt == 2u && c_k0[ci] == k0 && c_k1[ci] == k1) {
-                    atomicAdd(const_cast<u32*>(&c_cnt[ci]), 1u);
-                    slot = c_slot[ci];
-                } else {
-                    const bool claimed = stt == 0u && atomicCAS(const_cast<u32*>(&c_state[ci]), 0u, 1u) == 0u;
-                    slot = table_insert_global<CellT>(text, tile0 + sl, len, table, cap, start_bits, end_bits, n, overflow);
-                    if (claimed) {
-                        if (slot != HT_OVERFLOW) {
-                            c_k0[ci] = k0; c_k1[ci] = k1; c_slot[ci] = slot;
-                            __threadfence_block();
-                            c_state[ci] = 2u;
-                        } else c_state[ci] = 0u;
+            continue;
+        }
+        const u32 tail_next = s_scan[41];
+        // ---- P2a: one phrase per thread and step; cache hits finish here, everything else is deferred ----
+        for (u32 k = threadIdx.x; k < tot; k += FD_THREADS) {
+            const u32 sl = s_list[k];
+            const u32 nl = k + 1 < tot ? (u32)s_list[k + 1] : tail_next;
+            bool done = false;
+            if (nl != FD_NONE) {
+                const bool fin = (s_end[(nl - 1) >> 5] >> ((nl - 1) & 31)) & 1u;
+                const u64 len = (u64)(fin ? nl - 1 : nl) - sl + 1;
+                if (len * W <= 15) {
+                    u64 k0, k1;
+                    fd_pack_key<W>(s_cells, sl, len, k0, k1);
+                    const u32 ci = (u32)(((k0 ^ (k1 * 0x9E3779B97F4A7C15ULL)) * 0xff51afd7ed558ccdULL) >> (64 - FD_CACHE_BITS));
+#pragma unroll
+                    for (int way = 0; way < 2; way++) {
+                        const u32 c = ci ^ (u32)way;
+                        if (!done && c_state[c] == 2u && c_k0[c] == k0 && c_k1[c] == k1) {
+                            atomicAdd(const_cast<u32*>(&c_cnt[c]), 1u);
+                            slot_of_phrase[jbase + k] = (c_slot[c] & 0x7fffffffu) | (fin ? 0x80000000u : 0u);
+                            done = true;
+                        }
                     }
                 }
-            } else {
-                slot = table_insert_global<CellT>(text, tile0 + sl, len, table, cap, start_bits, end_bits, n, overflow);
             }
-            slot_of_phrase[j++] = (slot & 0x7fffffffu) | (fin ? 0x80000000u : 0u);
+            if (!done) {
+                const u32 m = atomicAdd(&s_scan[42], 1u);
+                if (m < (u32)FD_MISS_CAP) s_miss[m] = (u16)k;
+                else {  // deferred list full: take the global path right away
+                    u64 s = tile0 + sl, q = nl != FD_NONE ? tile0 + nl : next_start_after(start_bits, n, s);
+                    const bool fin = bit_at(end_bits, q - 1);
+                    const u32 slot = table_insert_global<CellT>(text, s, (fin ? q - 1 : q) - s + 1, table, cap, start_bits, end_bits, n, overflow);
+                    slot_of_phrase[jbase + k] = (slot & 0x7fffffffu) | (fin ? 0x80000000u : 0u);
+                    my_global++;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- P2b: deferred phrases: global table, then try to cache the key ----
+        const u32 n_def = s_scan[42] < (u32)FD_MISS_CAP ? s_scan[42] : (u32)FD_MISS_CAP;
+        for (u32 m = threadIdx.x; m < n_def; m += FD_THREADS) {
+            const u32 k = s_miss[m];
+            const u32 sl = s_list[k];
+            const u32 nl = k + 1 < tot ? (u32)s_list[k + 1] : tail_next;
+            const u64 s = tile0 + sl, q = nl != FD_NONE ? tile0 + nl : next_start_after(start_bits, n, s);
+            const bool fin = bit_at(end_bits, q - 1);
+            const u64 len = (fin ? q - 1 : q) - s + 1;
+            const u32 slot = table_insert_global<CellT>(text, s, len, table, cap, start_bits, end_bits, n, overflow);
+            slot_of_phrase[jbase + k] = (slot & 0x7fffffffu) | (fin ? 0x80000000u : 0u);
+            my_global++;
+            if (nl != FD_NONE && len * W <= 15 && slot != HT_OVERFLOW) {
+                u64 k0, k1;
+                fd_pack_key<W>(s_cells, sl, len, k0, k1);
+                const u32 ci = (u32)(((k0 ^ (k1 * 0x9E3779B97F4A7C15ULL)) * 0xff51afd7ed558ccdULL) >> (64 - FD_CACHE_BITS));
+                for (int way = 0; way < 2; way++) {
+                    const u32 c = ci ^ (u32)way;
+                    const u32 stt = c_state[c];
+                    if (stt == 2u && c_k0[c] == k0 && c_k1[c] == k1) break;  // somebody cached it meanwhile
+                    if (stt == 0u && atomicCAS(const_cast<u32*>(&c_state[c]), 0u, 1u) == 0u) {
+                        c_k0[c] = k0; c_k1[c] = k1; c_slot[c] = slot;
+                        __threadfence_block();
+                        c_state[c] = 2u;
+                        break;
+                    }
+                }
+            }
         }
     }
-    // ---- flush the cached counts ----
+    // ---- flush the cached counts and the pilot statistics ----
     __syncthreads();
     for (int i = threadIdx.x; i < FD_CACHE; i += FD_THREADS)
         if (c_state[i] == 2u && c_cnt[i]) atomicAdd(&table[c_slot[i]].y, (u64)c_cnt[i]);
+    if (stats) {
+        if (my_global) atomicAdd(&stats[0], my_global);
+        if (my_seen) atomicAdd(&stats[1], my_seen);
+    }
 }
 
 static __global__ void __launch_bounds__(256) table_occupancy_kernel(const ulonglong2* __restrict__ table, u64 cap, u32* __restrict__ occ_bits) {

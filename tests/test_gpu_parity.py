@@ -132,6 +132,22 @@ def test_rounds_small_table_and_slow_scan(golden, all_cases):
         compare_rounds(name, all_cases[name], golden[name], flags=G.FLAG_SMALL_TABLE | G.FLAG_FORCE_SLOW_SCAN)
 
 
+def test_rounds_dedup_variants(golden, all_cases):
+    """thread-per-phrase dedup for every phrase, and one-tile pilot + remainder (cached or not, chosen by the data)"""
+    for name in ("mutated_200x5k", "u16_rand", "with_empty", "only_empty", "long_phrases", "reads_2000x150", "u64_rand", "fuzz_7"):
+        compare_rounds(name, all_cases[name], golden[name], flags=G.FLAG_FORCE_UNCACHED)
+    for name in ("mutated_200x5k", "u16_rand", "reads_2000x150", "u32_rand", "homopolymers_multi", "ac_short_3000"):
+        compare_rounds(name, all_cases[name], golden[name], flags=G.FLAG_SMALL_PILOT)
+    for name in ("rep_50x200k", "u16_2M"):
+        compare_rounds(name, all_cases[name], golden[name], flags=G.FLAG_SMALL_PILOT | G.FLAG_SMALL_TABLE, check_dict=False)
+
+
+def test_many_empty_strings_overflow_the_tile_list():
+    """more phrase starts in one tile than the shared-memory list holds (runs of empty strings)"""
+    arr = np.frombuffer(b"\n" * 70000 + b"ACGT\n" * 3000 + b"\n" * 40000, np.uint8).copy()
+    compare_rounds("empty_runs", arr, None)
+
+
 def test_long_equal_runs_cross_cta_boundaries():
     """homopolymer stretches longer than a CTA tile (8192 cells) + look-ahead: the summary/resolve path must kick in by itself"""
     parts = [b"ACGT" * 100 + b"A" * 20000 + b"C" + b"\n", b"T" * 50000 + b"\n", b"G" * 8192 + b"\n", b"CA" * 5000 + b"A" * 9000 + b"\n"]
