@@ -138,19 +138,36 @@ class GrlGpu:
         self.last = r
         return r
 
-    def fetch_level(self):
-        """-> dict(rule_l, rule_r, has_hocc, pre_sym, pre_len) as numpy arrays (u64 / u8)"""
+    def fetch_level(self, arena: np.ndarray | None = None, widen: bool = True):
+        """-> dict(rule_l, rule_r, has_hocc, pre_sym, pre_len) as numpy arrays.
+        arena: optional uint8 buffer (e.g. pinned host memory) the arrays are carved from, so the copies are
+        direct DMA; widen=False keeps rule/pre_sym in the device's element width (sym_bytes) instead of u64."""
         r = self.last
         st = np.uint32 if r.sym_bytes == 4 else np.uint64
-        rl, rr = np.zeros(r.tot_phrases, st), np.zeros(r.tot_phrases, st)
-        hh = np.zeros(r.tot_phrases, np.uint8)
-        ps, pl = np.zeros(r.n_pre_runs, st), np.zeros(r.n_pre_runs, np.uint64)
+        sizes = [(r.tot_phrases, st), (r.tot_phrases, st), (r.tot_phrases, np.uint8), (r.n_pre_runs, st), (r.n_pre_runs, np.uint64)]
+        if arena is None:
+            arrs = [np.zeros(n, dt) for n, dt in sizes]
+        else:
+            arrs, off = [], 0
+            for n, dt in sizes:
+                nb = n * np.dtype(dt).itemsize
+                off = (off + 15) & ~15
+                if off + nb > arena.size:
+                    raise GrlGpuError(-1, "fetch arena too small")
+                arrs.append(arena[off:off + nb].view(dt))
+                off += nb
+        rl, rr, hh, ps, pl = arrs
         self._check(self._L.grlgpu_fetch_level(self._h, _ptr(rl), _ptr(rr), _ptr(hh), _ptr(ps), _ptr(pl)))
-        return {"rule_l": rl.astype(np.uint64), "rule_r": rr.astype(np.uint64), "has_hocc": hh, "pre_sym": ps.astype(np.uint64), "pre_len": pl}
+        if widen and arena is None:
+            rl, rr, ps = rl.astype(np.uint64), rr.astype(np.uint64), ps.astype(np.uint64)
+        return {"rule_l": rl, "rule_r": rr, "has_hocc": hh, "pre_sym": ps, "pre_len": pl}
 
-    def fetch_parse(self) -> np.ndarray:
+    def fetch_parse(self, arena: np.ndarray | None = None) -> np.ndarray:
         r = self.last
-        out = np.zeros(r.parse_len, CELL[r.cell_bytes_out])
+        if arena is None:
+            out = np.zeros(r.parse_len, CELL[r.cell_bytes_out])
+        else:
+            out = arena[: r.parse_len * r.cell_bytes_out].view(CELL[r.cell_bytes_out])
         self._check(self._L.grlgpu_fetch_parse(self._h, _ptr(out)))
         return out
 
