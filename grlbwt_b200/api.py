@@ -72,6 +72,13 @@ def lib_gpu():
         L.grlgpu_launch_count.argtypes = [vp]
         L.grlgpu_launch_count.restype = u64
         L.grlgpu_profile_entry.argtypes = [vp, C.c_int, C.c_char_p, C.c_int, C.POINTER(u64), C.POINTER(C.c_double), C.POINTER(u64)]
+        L.grlgpu_histogram.argtypes = [vp, vp]
+        L.grlgpu_mg_set_alphabet.argtypes = [vp, u64]
+        L.grlgpu_mg_local.argtypes = [vp, C.c_int, vp, vp]
+        L.grlgpu_mg_pack.argtypes = [vp, vp, vp, vp]
+        L.grlgpu_mg_merge.argtypes = [vp, vp, vp, vp, u64, u64, vp]
+        L.grlgpu_mg_pack_part.argtypes = [vp, vp, vp, vp]
+        L.grlgpu_mg_global.argtypes = [vp, vp, vp, vp, u64, u64, C.c_int, C.POINTER(Round)]
         L.grlgpu_selftest_scan.argtypes = [vp, u64, vp, vp]
         L.grlgpu_selftest_sort.argtypes = [vp, vp, u64, C.c_int]
         L.grlgpu_selftest_compact.argtypes = [vp, vp, u64, vp, vp]
@@ -109,6 +116,8 @@ class GrlGpu:
         self._check(self._L.grlgpu_create_on_stream(C.byref(self._h), device, flags, C.c_void_p(stream) if stream else None), ctx=False)
         self.last = None
         self._keep = None
+        self._sym_bytes = 1
+        self._round_started = False
 
     def _check(self, rc, ctx=True):
         if rc != 0:
@@ -122,9 +131,11 @@ class GrlGpu:
         if text.dtype not in (np.uint8, np.uint16, np.uint32, np.uint64):
             raise GrlGpuError(-1, "symbol width must be 1, 2, 4 or 8 bytes")
         self._keep = text
+        self._sym_bytes, self._round_started, self.last = text.dtype.itemsize, False, None
         self._check(self._L.grlgpu_set_text(self._h, _ptr(text) if text.size else None, text.size, text.dtype.itemsize))
 
     def set_text_device(self, dev_ptr: int, n_syms: int, sym_bytes: int):
+        self._keep, self._sym_bytes, self._round_started, self.last = None, sym_bytes, False, None
         self._check(self._L.grlgpu_set_text_device(self._h, C.c_void_p(dev_ptr), n_syms, sym_bytes))
 
     def stats(self) -> Stats:
@@ -136,6 +147,7 @@ class GrlGpu:
         r = Round()
         self._check(self._L.grlgpu_round(self._h, C.byref(r)))
         self.last = r
+        self._round_started = True
         return r
 
     def fetch_level(self, arena: np.ndarray | None = None, widen: bool = True):
@@ -182,6 +194,42 @@ class GrlGpu:
         freqs, metas = np.zeros(r.n_phrases, np.uint64), np.zeros(r.n_phrases, np.uint64)
         self._check(self._L.grlgpu_fetch_dictionary(self._h, _ptr(syms), _ptr(lens), _ptr(freqs), _ptr(metas)))
         return syms, lens, freqs, metas
+
+    # ---- multi-GPU rounds (raw device pointers; the caller owns the exchange, see multigpu.py) ----
+    def histogram(self) -> np.ndarray:
+        h = np.zeros(256, np.uint64)
+        self._check(self._L.grlgpu_histogram(self._h, _ptr(h)))
+        return h
+
+    def cell_bytes(self) -> int:
+        return int(self.last.cell_bytes_out) if self.last is not None and self._round_started else int(self._keep.dtype.itemsize if self._keep is not None else self._sym_bytes)
+
+    def mg_set_alphabet(self, max_sym: int):
+        self._check(self._L.grlgpu_mg_set_alphabet(self._h, max_sym))
+
+    def mg_local(self, n_ranks: int):
+        per = np.zeros((n_ranks, 2), np.uint64)
+        pl = np.zeros(1, np.uint64)
+        self._check(self._L.grlgpu_mg_local(self._h, n_ranks, _ptr(per), _ptr(pl)))
+        return [(int(a), int(b)) for a, b in per], int(pl[0])
+
+    def mg_pack(self, lens_ptr: int, counts_ptr: int, cells_ptr: int):
+        self._check(self._L.grlgpu_mg_pack(self._h, C.c_void_p(lens_ptr), C.c_void_p(counts_ptr), C.c_void_p(cells_ptr)))
+
+    def mg_merge(self, lens_ptr: int, counts_ptr: int, cells_ptr: int, m: int, n_cells: int):
+        part = np.zeros(2, np.uint64)
+        self._check(self._L.grlgpu_mg_merge(self._h, C.c_void_p(lens_ptr), C.c_void_p(counts_ptr), C.c_void_p(cells_ptr), m, n_cells, _ptr(part)))
+        return int(part[0]), int(part[1])
+
+    def mg_pack_part(self, lens_ptr: int, freqs_ptr: int, cells_ptr: int):
+        self._check(self._L.grlgpu_mg_pack_part(self._h, C.c_void_p(lens_ptr), C.c_void_p(freqs_ptr), C.c_void_p(cells_ptr)))
+
+    def mg_global(self, lens_ptr: int, freqs_ptr: int, cells_ptr: int, d: int, n_cells: int, done: bool):
+        r = Round()
+        self._check(self._L.grlgpu_mg_global(self._h, C.c_void_p(lens_ptr), C.c_void_p(freqs_ptr), C.c_void_p(cells_ptr), d, n_cells, int(done), C.byref(r)))
+        self.last = r
+        self._round_started = True
+        return r.as_dict()
 
     def profile_enable(self, on: bool = True):
         self._check(self._L.grlgpu_profile_enable(self._h, int(on)))

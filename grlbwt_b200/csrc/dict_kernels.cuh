@@ -298,7 +298,8 @@ template <class SymT>
 __global__ void __launch_bounds__(256) entry_finalize_kernel(const u32* __restrict__ rank, const SymT* __restrict__ D, const u32* __restrict__ rem,
                                                              const u32* __restrict__ phr_of, const u32* __restrict__ ph_off, const u64* __restrict__ ph_freq,
                                                              const u32* __restrict__ occ_slots, u64 nE, IsSuffix is_suffix, const u32* __restrict__ ginfo,
-                                                             ulonglong2* table, u8* __restrict__ is_suffix_next, u32* __restrict__ erank) {
+                                                             ulonglong2* table, u64* __restrict__ ph_meta, u8* __restrict__ is_suffix_next,
+                                                             u32* __restrict__ erank) {
     const u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nE) return;
     const u32 gi = ginfo[rank[e] - 1];
@@ -306,7 +307,9 @@ __global__ void __launch_bounds__(256) entry_finalize_kernel(const u32* __restri
     const u32 r = gi >> 2;
     const u32 ph = phr_of[e];
     if (e == ph_off[ph]) {
-        table[occ_slots[ph]].y = ((u64)r << 1) | (ph_freq[ph] > 1 ? 1ULL : 0ULL);
+        const u64 meta = ((u64)r << 1) | (ph_freq[ph] > 1 ? 1ULL : 0ULL);
+        if (ph_meta) ph_meta[ph] = meta;  // multi-GPU: the dictionary is global, the tables are per rank
+        else table[occ_slots[ph]].y = meta;
         is_suffix_next[r] = is_suffix((u64)D[e + rem[e]]) ? 1 : 0;
     }
     if (gi & 2u) erank[e] = r;

@@ -14,6 +14,8 @@
 using namespace grl;
 
 
+namespace { struct MgRound; }
+
 struct grlgpu_ctx {
     int device = 0;
     u64 flags = 0;
@@ -38,12 +40,17 @@ struct grlgpu_ctx {
     bool done = false;
     bool have_stats = false;
     grlgpu_stats_t stats{};
+    u64 hist[256] = {0};  // byte alphabets: histogram of the (local) text
 
     // artefacts of the last round (device)
     int lvl_sym_bytes = 4;
     u64 lvl_tot = 0, lvl_npre = 0;
     DevBuf<u8> rule_l, rule_r, has_hocc, pre_sym;
     DevBuf<u64> pre_len;
+
+    // multi-GPU round in flight (between grlgpu_mg_local and grlgpu_mg_global)
+    MgRound* mg = nullptr;
+    int mg_ranks = 0;
 
     // optional: dictionary of the last round kept for tests (GRLGPU_FLAG_KEEP_DICT)
     u64 kd_d = 0, kd_nE = 0;
@@ -132,6 +139,8 @@ struct Round {
     DevBuf<u8> D_raw;
     DevBuf<u32> phr_of, rem, rank, order;
     DevBuf<ulonglong2> einfo;
+    const void* dict_text = nullptr;  // text the dictionary's ph_pos point into (default: the context's text)
+    u64* ph_meta = nullptr;           // if set, metasymbols go here (per phrase) instead of into the table
     explicit Round(grlgpu_ctx* ctx) : c(ctx), st(ctx->st), n(ctx->n) {}
 };
 
@@ -166,6 +175,8 @@ void stage_flags(Round& R) {
         GRL_CUDA(cudaStreamSynchronize(R.st));
     }
 }
+
+void dict_offsets(Round& R);
 
 template <class CellT, class PosT>
 void insert_uncached(Round& R, BitmapCompactor& bc, DevBuf<u8>& ps_raw, u64 j0, u64 cap, u32* overflow) {
@@ -276,6 +287,12 @@ void stage_dedup(Round& R) {
     R.ph_len.alloc(R.d, R.st);
     R.ph_freq.alloc(R.d, R.st);
     GRL_LAUNCH("dict_meta", 0, dict_meta_kernel, grid_for(R.d, 256), 256, 0, R.st, R.table.p, R.occ_slots.p, R.d, R.start_bits.p, R.end_bits, R.n, R.ph_pos.p, R.ph_len.p, R.ph_freq.p);
+    dict_offsets(R);
+    R.start_bits.release();
+}
+
+// phrase offsets inside the dictionary, number of entries, highest frequency, longest phrase
+void dict_offsets(Round& R) {
     R.ph_off.alloc(R.d + 1, R.st);
     DevBuf<u64> tot64(1, R.st);
     {   // offsets as u64 first to detect overflow of the 32-bit entry index space
@@ -298,7 +315,6 @@ void stage_dedup(Round& R) {
     GRL_CUDA(cudaStreamSynchronize(R.st));
     R.max_freq = hmx[0];
     R.max_len = hmx[1];
-    R.start_bits.release();
 }
 
 template <class CellT, bool FIRST, class SymT>
@@ -308,7 +324,7 @@ void stage_gather(Round& R) {
     R.rem.alloc(R.nE, R.st);
     R.einfo.alloc(R.nE, R.st);
     IsSuffix isuf{R.c->is_suffix.p, R.c->sep, R.c->first};
-    GRL_LAUNCH("dict_gather", R.nE * (sizeof(CellT) + sizeof(SymT) + 8) + R.d * 16, (dict_gather_kernel<CellT, FIRST, SymT>), grid_for(R.d, 256), 256, 0, R.st, (const CellT*)R.c->text, R.ph_pos.p, R.ph_len.p, R.ph_off.p, R.ph_freq.p, R.d, isuf, (SymT*)R.D_raw.p, R.phr_of.p, R.rem.p, R.einfo.p);
+    GRL_LAUNCH("dict_gather", R.nE * (sizeof(CellT) + sizeof(SymT) + 8) + R.d * 16, (dict_gather_kernel<CellT, FIRST, SymT>), grid_for(R.d, 256), 256, 0, R.st, (const CellT*)(R.dict_text ? R.dict_text : R.c->text), R.ph_pos.p, R.ph_len.p, R.ph_off.p, R.ph_freq.p, R.d, isuf, (SymT*)R.D_raw.p, R.phr_of.p, R.rem.p, R.einfo.p);
 }
 
 // ---------------- dictionary stage: suffix order, groups, ranks, pre-BWT, rules, metasymbols ----------------
@@ -432,7 +448,7 @@ void stage_dict(Round& R) {
     erank.fill_ff();
     DevBuf<u32> ginfo(G, st);
     GRL_LAUNCH("pack_ginfo", G * 16, pack_ginfo_kernel, grid_for(G, 256), 256, 0, st, gcnt.p, rflag.p, rrank.p, G, ginfo.p);
-    GRL_LAUNCH("entry_finalize", nE * 24, (entry_finalize_kernel<SymT>), grid_for(nE, 256), 256, 0, st, R.rank.p, D, R.rem.p, R.phr_of.p, R.ph_off.p, R.ph_freq.p, R.occ_slots.p, nE, isuf, ginfo.p, R.table.p, is_suffix_next.p, erank.p);
+    GRL_LAUNCH("entry_finalize", nE * 24, (entry_finalize_kernel<SymT>), grid_for(nE, 256), 256, 0, st, R.rank.p, D, R.rem.p, R.phr_of.p, R.ph_off.p, R.ph_freq.p, R.occ_slots.p, nE, isuf, ginfo.p, R.table.p, R.ph_meta, is_suffix_next.p, erank.p);
     c->rule_l.alloc(tot * sizeof(SymT), st);
     c->rule_r.alloc(tot * sizeof(SymT), st);
     c->has_hocc.alloc(tot, st);
@@ -457,10 +473,72 @@ void stage_rewrite(Round& R, DevBuf<u8>& new_text, DevBuf<u32>& new_end_bits) {
     GRL_LAUNCH("rewrite", R.p * (4 + 16 + sizeof(OutT)), (rewrite_kernel<OutT>), grid_for(R.p, 256), 256, 0, R.st, R.slot_of_phrase.p, R.p, R.table.p, (OutT*)new_text.p, new_end_bits.p);
 }
 
+// rewrite the local text with the metasymbols now stored in the local table, report, and make the parse
+// the text of the next round. `tot` / `n_pre` / dictionary sizes describe the round's (global) dictionary.
+struct RoundTimes { float all = 0, text = 0, dict = 0; };
+void finish_round(grlgpu_ctx* c, Round& R, u64 tot, u64 n_pre, u64 dict_d, u64 dict_nE, u64 max_freq, const RoundTimes& tm, Timer* t_all, grlgpu_round_t* out) {
+    Timer t_rw(c->st);
+    t_rw.start();
+    const int bps = bit_width64(tot) + 1;  // exact_par_phase.cpp:456-465
+    const int w_out = bps <= 8 ? 1 : bps <= 16 ? 2 : bps <= 32 ? 4 : 8;
+    DevBuf<u8> new_text;
+    DevBuf<u32> new_end;
+    if (w_out == 1) stage_rewrite<u8>(R, new_text, new_end);
+    else if (w_out == 2) stage_rewrite<u16>(R, new_text, new_end);
+    else if (w_out == 4) stage_rewrite<u32>(R, new_text, new_end);
+    else stage_rewrite<u64>(R, new_text, new_end);
+    t_rw.stop();
+    if (t_all) t_all->stop();
+
+    memset(out, 0, sizeof(*out));
+    out->round = (u64)c->round + 1;
+    out->n_in = R.n;
+    out->n_strings = c->n_strings;
+    out->parse_len = R.p;
+    out->n_phrases = dict_d;
+    out->dict_syms = dict_nE;
+    out->max_freq = max_freq;
+    out->alphabet = c->alphabet;
+    out->tot_phrases = tot;
+    out->n_pre_runs = n_pre;
+    out->cell_bytes_in = (u32)c->w;
+    out->cell_bytes_out = (u32)w_out;
+    out->sym_bytes = (u32)c->lvl_sym_bytes;
+    out->done = R.p == c->n_strings;
+    out->algorithmic_bytes = R.n * (u64)c->w + R.p * (u64)w_out + dict_nE * (u64)c->w + 8 * dict_d;
+    out->device_ms = t_all ? t_all->ms() : tm.all;
+    out->text_pass_ms = tm.text;
+    out->dict_ms = tm.dict;
+    out->rewrite_ms = t_rw.ms();
+
+    if ((c->flags & GRLGPU_FLAG_KEEP_DICT) && !R.ph_meta && c->kd_meta.p) {  // metasymbol per distinct phrase, for tests
+        std::vector<u32> slots(R.d);
+        GRL_CUDA(cudaMemcpy(slots.data(), R.occ_slots.p, R.d * 4, cudaMemcpyDeviceToHost));
+        std::vector<ulonglong2> tab(R.cap);
+        GRL_CUDA(cudaMemcpy(tab.data(), R.table.p, R.cap * sizeof(ulonglong2), cudaMemcpyDeviceToHost));
+        std::vector<u64> metas(R.d);
+        for (u64 i = 0; i < R.d; i++) metas[i] = tab[slots[i]].y;
+        GRL_CUDA(cudaMemcpy(c->kd_meta.p, metas.data(), R.d * 8, cudaMemcpyHostToDevice));
+    }
+
+    // the parse becomes the text of the next round
+    GRL_CUDA(cudaStreamSynchronize(c->st));
+    c->prof.resolve();
+    c->text_own = std::move(new_text);
+    c->text = c->text_own.p;
+    c->end_bits = std::move(new_end);
+    c->n = R.p;
+    c->w = w_out;
+    c->first = false;
+    c->alphabet = tot;
+    c->round++;
+    c->done = out->done != 0;
+}
+
 template <class CellT, bool FIRST>
 void run_round_t(grlgpu_ctx* c, grlgpu_round_t* out) {
     Round R(c);
-    Timer t_all(c->st), t_text(c->st), t_dict(c->st), t_rw(c->st);
+    Timer t_all(c->st), t_text(c->st), t_dict(c->st);
     t_all.start();
     t_text.start();
     stage_flags<CellT, FIRST>(R);
@@ -481,61 +559,167 @@ void run_round_t(grlgpu_ctx* c, grlgpu_round_t* out) {
         c->kd_phr_of = std::move(R.phr_of);
         c->kd_meta.alloc(R.d, c->st);
     }
-    t_rw.start();
-    const int bps = bit_width64(R.tot) + 1;  // exact_par_phase.cpp:456-465
-    const int w_out = bps <= 8 ? 1 : bps <= 16 ? 2 : bps <= 32 ? 4 : 8;
-    DevBuf<u8> new_text;
-    DevBuf<u32> new_end;
-    if (w_out == 1) stage_rewrite<u8>(R, new_text, new_end);
-    else if (w_out == 2) stage_rewrite<u16>(R, new_text, new_end);
-    else if (w_out == 4) stage_rewrite<u32>(R, new_text, new_end);
-    else stage_rewrite<u64>(R, new_text, new_end);
-    t_rw.stop();
-    t_all.stop();
+    RoundTimes tm;
+    tm.text = t_text.ms();
+    tm.dict = t_dict.ms();
+    finish_round(c, R, R.tot, R.n_pre, R.d, R.nE, R.max_freq, tm, &t_all, out);
+}
 
-    memset(out, 0, sizeof(*out));
-    out->round = (u64)c->round + 1;
-    out->n_in = R.n;
-    out->n_strings = c->n_strings;
-    out->parse_len = R.p;
-    out->n_phrases = R.d;
-    out->dict_syms = R.nE;
-    out->max_freq = R.max_freq;
-    out->alphabet = A;
-    out->tot_phrases = R.tot;
-    out->n_pre_runs = R.n_pre;
-    out->cell_bytes_in = (u32)c->w;
-    out->cell_bytes_out = (u32)w_out;
-    out->sym_bytes = (u32)c->lvl_sym_bytes;
-    out->done = R.p == c->n_strings;
-    out->algorithmic_bytes = R.n * (u64)c->w + R.p * (u64)w_out + R.nE * (u64)c->w + 8 * R.d;
-    out->device_ms = t_all.ms();
-    out->text_pass_ms = t_text.ms();
-    out->dict_ms = t_dict.ms();
-    out->rewrite_ms = t_rw.ms();
+// ---------------- multi-GPU round: the caller owns the exchange between the calls ----------------
+struct MgRound {
+    Round R;                        // this rank's shard
+    DevBuf<u32> perm;               // local distinct phrases ordered by owner
+    DevBuf<u64> offs;               // cell offset of each packed phrase (+ total)
+    // owner side: dedup of what the other ranks sent
+    DevBuf<ulonglong2> ptable;
+    DevBuf<u32> pslots, p_len;
+    DevBuf<u64> p_pos, p_freq, p_offs;
+    u64 d_part = 0, cells_part = 0;
+    const void* recv_cells = nullptr;
+    Timer t_text, t_dict;
+    float ms_text = 0;
+    explicit MgRound(grlgpu_ctx* c) : R(c), t_text(c->st), t_dict(c->st) {}
+};
 
-    if ((c->flags & GRLGPU_FLAG_KEEP_DICT)) {  // metasymbol per distinct phrase, for tests
-        std::vector<u32> slots(R.d);
-        GRL_CUDA(cudaMemcpy(slots.data(), R.occ_slots.p, R.d * 4, cudaMemcpyDeviceToHost));
-        std::vector<ulonglong2> tab(R.cap);
-        GRL_CUDA(cudaMemcpy(tab.data(), R.table.p, R.cap * sizeof(ulonglong2), cudaMemcpyDeviceToHost));
-        std::vector<u64> metas(R.d);
-        for (u64 i = 0; i < R.d; i++) metas[i] = tab[slots[i]].y;
-        GRL_CUDA(cudaMemcpy(c->kd_meta.p, metas.data(), R.d * 8, cudaMemcpyHostToDevice));
+template <class CellT, bool FIRST>
+void mg_local_t(grlgpu_ctx* c, int G, grlgpu_part_t* per_owner, u64* parse_len_local) {
+    delete c->mg;
+    c->mg = nullptr;
+    c->mg = new MgRound(c);
+    c->mg_ranks = G;
+    MgRound& M = *c->mg;
+    Round& R = M.R;
+    M.t_text.start();
+    stage_flags<CellT, FIRST>(R);
+    stage_dedup<CellT>(R);
+    // owner of every local distinct phrase = content hash % G; order the phrases by owner
+    DevBuf<u64> keys(R.d, R.st), keys_alt(R.d, R.st);
+    DevBuf<u32> vals(R.d, R.st), vals_alt(R.d, R.st);
+    GRL_LAUNCH("phrase_owner", 0, (phrase_owner_kernel<CellT>), grid_for(R.d, 256), 256, 0, R.st, (const CellT*)c->text, R.ph_pos.p, R.ph_len.p, R.d, (u32)G, keys.p, vals.p);
+    u64 *kp = keys.p, *ka = keys_alt.p;
+    u32 *vp = vals.p, *va = vals_alt.p;
+    radix_sort_pairs(&kp, &vp, &ka, &va, R.d, std::max(1, bit_width64((u64)G - 1)), R.st);
+    if (vp != vals.p) std::swap(vals, vals_alt);
+    M.perm = std::move(vals);
+    DevBuf<u32> lens_sorted(R.d, R.st);
+    GRL_LAUNCH("gather_u32", 0, gather_u32_kernel, grid_for(R.d, 256), 256, 0, R.st, R.ph_len.p, M.perm.p, R.d, lens_sorted.p);
+    M.offs.alloc(R.d + 1, R.st);
+    exclusive_scan<u32, u64>(lens_sorted.p, M.offs.p, R.d, M.offs.p + R.d, R.st);
+    DevBuf<u64> first(G + 1, R.st);
+    GRL_LAUNCH("owner_bounds", 0, owner_bounds_kernel, 1, 32, 0, R.st, kp, R.d, (u32)G, first.p);
+    std::vector<u64> hf(G + 1), ho(G + 1);
+    GRL_CUDA(cudaMemcpyAsync(hf.data(), first.p, (G + 1) * 8, cudaMemcpyDeviceToHost, R.st));
+    GRL_CUDA(cudaStreamSynchronize(R.st));
+    for (int g = 0; g <= G; g++) ho[g] = d2h_scalar(M.offs.p + hf[g], R.st);
+    for (int g = 0; g < G; g++) { per_owner[g].n_phrases = hf[g + 1] - hf[g]; per_owner[g].n_cells = ho[g + 1] - ho[g]; }
+    *parse_len_local = R.p;
+    M.t_text.stop();
+    M.ms_text = M.t_text.ms();
+}
+
+template <class CellT>
+void mg_pack_t(grlgpu_ctx* c, u32* d_lens, u64* d_counts, void* d_cells) {
+    MgRound& M = *c->mg;
+    Round& R = M.R;
+    GRL_LAUNCH("pack_phrases", 0, (pack_phrases_kernel<CellT>), grid_for(R.d, 256), 256, 0, R.st, (const CellT*)c->text, R.ph_pos.p, R.ph_len.p, R.ph_freq.p, M.perm.p, M.offs.p, R.d, d_lens, d_counts, (CellT*)d_cells);
+    GRL_CUDA(cudaStreamSynchronize(R.st));
+}
+
+template <class CellT>
+void mg_merge_t(grlgpu_ctx* c, const u32* lens, const u64* counts, const void* cells, u64 m, u64 n_cells, grlgpu_part_t* part) {
+    MgRound& M = *c->mg;
+    cudaStream_t st = c->st;
+    M.recv_cells = cells;
+    DevBuf<u64> offs(m + 1, st);
+    exclusive_scan<u32, u64>(lens, offs.p, m, offs.p + m, st);
+    {   // the pack tables cannot tell apart lengths >= 2^24-1 (no bitmap to consult)
+        DevBuf<u64> len64(m, st), mx(1, st);
+        mx.zero();
+        GRL_LAUNCH("u32_to_u64", 0, u32_to_u64_kernel, grid_for(m, 256), 256, 0, st, lens, m, len64.p);
+        GRL_LAUNCH("reduce_max_u64", 0, reduce_max_u64_kernel, 296, 256, 0, st, len64.p, m, mx.p);
+        if (d2h_scalar(mx.p, st) >= HT_LEN_SAT) throw Error(GRLGPU_ERR_LIMIT, "multi-GPU rounds support phrases shorter than 2^24-1 cells");
+        if (d2h_scalar(offs.p + m, st) != n_cells) throw Error(GRLGPU_ERR_ARG, "received cell count does not match the received lengths");
     }
+    const u64 cap = std::max<u64>(1024, (m + m / 2 + m / 10 + 255) / 256 * 256);
+    if (cap > (1ull << 31) - 256) throw Error(GRLGPU_ERR_LIMIT, "phrase table would exceed 2^31 slots");
+    M.ptable.alloc(cap, st);
+    GRL_LAUNCH("table_init", cap * 16, table_init_kernel, grid_for(cap, 256), 256, 0, st, M.ptable.p, cap);
+    DevBuf<u32> overflow(1, st);
+    overflow.zero();
+    GRL_LAUNCH("pack_insert", 0, (pack_insert_kernel<CellT>), grid_for(m, 256), 256, 0, st, (const CellT*)cells, offs.p, lens, counts, m, M.ptable.p, cap, overflow.p);
+    if (d2h_scalar(overflow.p, st)) throw Error(GRLGPU_ERR_STATE, "partition table overflow");
+    DevBuf<u32> occ_bits(cap / 32, st);
+    GRL_LAUNCH("table_occupancy", cap * 16, table_occupancy_kernel, (unsigned)(cap / 256), 256, 0, st, M.ptable.p, cap, occ_bits.p);
+    BitmapCompactor oc;
+    M.d_part = oc.count(occ_bits.p, cap, st);
+    M.pslots.alloc(M.d_part, st);
+    oc.write<u32>(nullptr, M.pslots.p);
+    M.p_pos.alloc(M.d_part, st);
+    M.p_len.alloc(M.d_part, st);
+    M.p_freq.alloc(M.d_part, st);
+    GRL_LAUNCH("dict_meta", 0, dict_meta_kernel, grid_for(M.d_part, 256), 256, 0, st, M.ptable.p, M.pslots.p, M.d_part, (const u32*)nullptr, (const u32*)nullptr, (u64)0, M.p_pos.p, M.p_len.p, M.p_freq.p);
+    M.p_offs.alloc(M.d_part + 1, st);
+    exclusive_scan<u32, u64>(M.p_len.p, M.p_offs.p, M.d_part, M.p_offs.p + M.d_part, st);
+    M.cells_part = d2h_scalar(M.p_offs.p + M.d_part, st);
+    part->n_phrases = M.d_part;
+    part->n_cells = M.cells_part;
+}
 
-    // the parse becomes the text of the next round
+template <class CellT>
+void mg_pack_part_t(grlgpu_ctx* c, u32* d_lens, u64* d_freqs, void* d_cells) {
+    MgRound& M = *c->mg;
+    GRL_LAUNCH("pack_phrases", 0, (pack_phrases_kernel<CellT>), grid_for(M.d_part, 256), 256, 0, c->st, (const CellT*)M.recv_cells, M.p_pos.p, M.p_len.p, M.p_freq.p, (const u32*)nullptr, M.p_offs.p, M.d_part, d_lens, d_freqs, (CellT*)d_cells);
     GRL_CUDA(cudaStreamSynchronize(c->st));
-    c->prof.resolve();
-    c->text_own = std::move(new_text);
-    c->text = c->text_own.p;
-    c->end_bits = std::move(new_end);
-    c->n = R.p;
-    c->w = w_out;
-    c->first = false;
-    c->alphabet = R.tot;
-    c->round++;
-    c->done = out->done != 0;
+    M.ptable.release(); M.pslots.release(); M.p_pos.release(); M.p_len.release(); M.p_freq.release(); M.p_offs.release();
+}
+
+template <class CellT, bool FIRST>
+void mg_global_t(grlgpu_ctx* c, const u32* lens, const u64* freqs, const void* cells, u64 d, u64 n_cells, int done_global, grlgpu_round_t* out) {
+    MgRound& M = *c->mg;
+    Round& R = M.R;
+    cudaStream_t st = c->st;
+    M.t_dict.start();
+    // the global dictionary (identical on every rank) as a Round of its own: "text" = the gathered cells
+    Round GR(c);
+    GR.dict_text = cells;
+    GR.d = d;
+    GR.ph_len.alloc(d, st);
+    GR.ph_freq.alloc(d, st);
+    GR.ph_pos.alloc(d + 1, st);
+    GRL_CUDA(cudaMemcpyAsync(GR.ph_len.p, lens, d * 4, cudaMemcpyDeviceToDevice, st));
+    GRL_CUDA(cudaMemcpyAsync(GR.ph_freq.p, freqs, d * 8, cudaMemcpyDeviceToDevice, st));
+    exclusive_scan<u32, u64>(GR.ph_len.p, GR.ph_pos.p, d, GR.ph_pos.p + d, st);
+    if (d2h_scalar(GR.ph_pos.p + d, st) != n_cells) throw Error(GRLGPU_ERR_ARG, "gathered cell count does not match the gathered lengths");
+    dict_offsets(GR);
+    DevBuf<u64> g_meta(d, st);
+    GR.ph_meta = g_meta.p;
+    const bool wide = (c->alphabet + GR.nE + 8) >= (1ull << 32);
+    if (wide) { stage_gather<CellT, FIRST, u64>(GR); stage_dict<u64>(GR); }
+    else { stage_gather<CellT, FIRST, u32>(GR); stage_dict<u32>(GR); }
+    // content -> global phrase index, then the metasymbol of every local distinct phrase
+    const u64 gcap = std::max<u64>(1024, (d + d / 2 + d / 10 + 255) / 256 * 256);
+    if (gcap > (1ull << 31) - 256) throw Error(GRLGPU_ERR_LIMIT, "phrase table would exceed 2^31 slots");
+    DevBuf<ulonglong2> gtable(gcap, st);
+    GRL_LAUNCH("table_init", gcap * 16, table_init_kernel, grid_for(gcap, 256), 256, 0, st, gtable.p, gcap);
+    DevBuf<u32> flag(2, st);
+    flag.zero();
+    GRL_LAUNCH("pack_insert", 0, (pack_insert_kernel<CellT>), grid_for(d, 256), 256, 0, st, (const CellT*)cells, GR.ph_pos.p, GR.ph_len.p, (const u64*)nullptr, d, gtable.p, gcap, flag.p);
+    GRL_LAUNCH("map_local", 0, (map_local_kernel<CellT>), grid_for(R.d, 256), 256, 0, st, (const CellT*)c->text, R.ph_pos.p, R.ph_len.p, R.occ_slots.p, R.d, (const CellT*)cells, gtable.p, gcap, g_meta.p, R.table.p, flag.p + 1);
+    u32 hflag[2];
+    GRL_CUDA(cudaMemcpyAsync(hflag, flag.p, 8, cudaMemcpyDeviceToHost, st));
+    GRL_CUDA(cudaStreamSynchronize(st));
+    if (hflag[0]) throw Error(GRLGPU_ERR_STATE, "global table overflow");
+    if (hflag[1]) throw Error(GRLGPU_ERR_STATE, "a local phrase is missing from the global dictionary");
+    M.t_dict.stop();
+    RoundTimes tm;
+    tm.text = M.ms_text;
+    tm.dict = M.t_dict.ms();
+    tm.all = tm.text + tm.dict;
+    finish_round(c, R, GR.tot, GR.n_pre, GR.d, GR.nE, GR.max_freq, tm, nullptr, out);
+    out->done = done_global ? 1u : 0u;  // the phase ends when EVERY rank's strings are single cells
+    c->done = done_global != 0;
+    delete c->mg;
+    c->mg = nullptr;
 }
 
 void run_round(grlgpu_ctx* c, grlgpu_round_t* out) {
@@ -576,6 +760,7 @@ void compute_stats(grlgpu_ctx* c) {
     s.n_strings = h.n_sep;
     s.max_sym_freq = c->n;  // utils.cpp:117
     if (sizeof(CellT) == 1) {  // utils.cpp:161-175
+        memcpy(c->hist, h.hist, sizeof(c->hist));
         int lo = 0, hi = 255;
         while (h.hist[lo] == 0) lo++;
         while (h.hist[hi] == 0) hi--;
@@ -659,6 +844,8 @@ int grlgpu_destroy(grlgpu_ctx* ctx) {
     cudaStream_t st = ctx->st;
     const bool own = ctx->own_stream;
     ctx->prof.resolve();
+    delete ctx->mg;
+    ctx->mg = nullptr;
     delete ctx;  // the stream was synchronised above: the pool's slabs are idle
     if (own) cudaStreamDestroy(st);
     return GRLGPU_OK;
@@ -779,6 +966,76 @@ int grlgpu_fetch_dictionary(grlgpu_ctx* ctx, uint64_t* syms, uint64_t* lens, uin
             k++;
         }
     });
+}
+
+int grlgpu_histogram(grlgpu_ctx* ctx, uint64_t* hist256) {
+    if (!ctx || !hist256) return GRLGPU_ERR_ARG;
+    if (!ctx->have_stats) return GRLGPU_ERR_STATE;
+    memcpy(hist256, ctx->hist, sizeof(ctx->hist));
+    return GRLGPU_OK;
+}
+
+// ---- multi-GPU rounds ----
+#define MG_DISPATCH_FIRST(fn, ...)                                                     \
+    do {                                                                               \
+        if (ctx->first) switch (ctx->w) {                                              \
+            case 1: fn<u8, true>(__VA_ARGS__); break;                                  \
+            case 2: fn<u16, true>(__VA_ARGS__); break;                                 \
+            case 4: fn<u32, true>(__VA_ARGS__); break;                                 \
+            default: fn<u64, true>(__VA_ARGS__); break;                                \
+        } else switch (ctx->w) {                                                       \
+            case 1: fn<u8, false>(__VA_ARGS__); break;                                 \
+            case 2: fn<u16, false>(__VA_ARGS__); break;                                \
+            case 4: fn<u32, false>(__VA_ARGS__); break;                                \
+            default: fn<u64, false>(__VA_ARGS__); break;                               \
+        }                                                                              \
+    } while (0)
+#define MG_DISPATCH(fn, ...)                                                           \
+    do {                                                                               \
+        switch (ctx->w) {                                                              \
+            case 1: fn<u8>(__VA_ARGS__); break;                                        \
+            case 2: fn<u16>(__VA_ARGS__); break;                                       \
+            case 4: fn<u32>(__VA_ARGS__); break;                                       \
+            default: fn<u64>(__VA_ARGS__); break;                                      \
+        }                                                                              \
+    } while (0)
+
+int grlgpu_mg_set_alphabet(grlgpu_ctx* ctx, uint64_t global_max_sym) {
+    if (!ctx) return GRLGPU_ERR_ARG;
+    if (!ctx->have_stats || !ctx->first) return GRLGPU_ERR_STATE;
+    if (global_max_sym < ctx->stats.max_sym) return GRLGPU_ERR_ARG;
+    ctx->alphabet = global_max_sym + 1;
+    return GRLGPU_OK;
+}
+int grlgpu_mg_local(grlgpu_ctx* ctx, int n_ranks, grlgpu_part_t* per_owner, uint64_t* parse_len_local) {
+    if (!ctx || !per_owner || !parse_len_local || n_ranks < 1 || n_ranks > 31) return GRLGPU_ERR_ARG;
+    if (!ctx->text || ctx->done || !ctx->have_stats) return GRLGPU_ERR_STATE;
+    return guarded(ctx, [&] {
+        u64 pl = 0;
+        MG_DISPATCH_FIRST(mg_local_t, ctx, n_ranks, per_owner, &pl);
+        *parse_len_local = pl;
+    });
+}
+int grlgpu_mg_pack(grlgpu_ctx* ctx, uint32_t* d_lens, uint64_t* d_counts, void* d_cells) {
+    if (!ctx || !d_lens || !d_counts || !d_cells) return GRLGPU_ERR_ARG;
+    if (!ctx->mg) return GRLGPU_ERR_STATE;
+    return guarded(ctx, [&] { MG_DISPATCH(mg_pack_t, ctx, d_lens, (u64*)d_counts, d_cells); });
+}
+int grlgpu_mg_merge(grlgpu_ctx* ctx, const uint32_t* d_lens, const uint64_t* d_counts, const void* d_cells, uint64_t m, uint64_t n_cells, grlgpu_part_t* part) {
+    if (!ctx || !part || !d_lens || !d_counts || !d_cells) return GRLGPU_ERR_ARG;
+    if (!ctx->mg) return GRLGPU_ERR_STATE;
+    return guarded(ctx, [&] { MG_DISPATCH(mg_merge_t, ctx, d_lens, (const u64*)d_counts, d_cells, (u64)m, (u64)n_cells, part); });
+}
+int grlgpu_mg_pack_part(grlgpu_ctx* ctx, uint32_t* d_lens, uint64_t* d_freqs, void* d_cells) {
+    if (!ctx || !d_lens || !d_freqs || !d_cells) return GRLGPU_ERR_ARG;
+    if (!ctx->mg) return GRLGPU_ERR_STATE;
+    return guarded(ctx, [&] { MG_DISPATCH(mg_pack_part_t, ctx, d_lens, (u64*)d_freqs, d_cells); });
+}
+int grlgpu_mg_global(grlgpu_ctx* ctx, const uint32_t* d_lens, const uint64_t* d_freqs, const void* d_cells, uint64_t d, uint64_t n_cells, int done_global,
+                     grlgpu_round_t* out) {
+    if (!ctx || !out || !d_lens || !d_freqs || !d_cells || d == 0) return GRLGPU_ERR_ARG;
+    if (!ctx->mg) return GRLGPU_ERR_STATE;
+    return guarded(ctx, [&] { MG_DISPATCH_FIRST(mg_global_t, ctx, d_lens, (const u64*)d_freqs, d_cells, (u64)d, (u64)n_cells, done_global, out); });
 }
 
 int grlgpu_profile_enable(grlgpu_ctx* ctx, int on) {

@@ -260,35 +260,43 @@ __device__ __forceinline__ u64 phrase_hash(const CellT* __restrict__ text, u64 s
     return mix64(h);
 }
 
-// global path: returns the slot of phrase text[s, s+len) (claiming it if new) and adds one occurrence
-template <class CellT>
-__device__ u32 table_insert_global(const CellT* __restrict__ text, u64 s, u64 len, ulonglong2* table, u64 cap, const u32* __restrict__ start_bits,
-                                   const u32* __restrict__ end_bits, u64 n, u32* overflow) {
+// global path: probes `table` (whose keys point into ttext) for the phrase qtext[s, s+len). INSERT: claims a
+// slot if the phrase is new (then qtext must be ttext) and adds `add` to its count; returns the slot, or
+// HT_OVERFLOW when the probe limit is hit (insert) / the phrase is absent (find).
+template <class CellT, bool INSERT>
+__device__ u32 table_probe(const CellT* __restrict__ qtext, u64 s, u64 len, const CellT* __restrict__ ttext, ulonglong2* table, u64 cap, u64 add,
+                           const u32* __restrict__ start_bits, const u32* __restrict__ end_bits, u64 n, u32* overflow) {
     const u64 lenf = len < HT_LEN_SAT ? len : HT_LEN_SAT;
     const u64 mykey = (s << 24) | lenf;
-    u64 slot = __umul64hi(phrase_hash<CellT>(text, s, len), cap);  // uniform over [0, cap), cap need not be a power of two
+    u64 slot = __umul64hi(phrase_hash<CellT>(qtext, s, len), cap);  // uniform over [0, cap), cap need not be a power of two
     for (int probes = 0; probes < HT_MAX_PROBES; probes++) {
         u64 k = *reinterpret_cast<volatile u64*>(&table[slot].x);
         if (k == HT_EMPTY) {
+            if (!INSERT) return HT_OVERFLOW;
             const u64 old = atomicCAS(&table[slot].x, HT_EMPTY, mykey);
             k = old == HT_EMPTY ? mykey : old;
         }
-        bool match = k == mykey;
+        bool match = INSERT && k == mykey;
         if (!match && (k & HT_LEN_SAT) == lenf) {
             const u64 kpos = k >> 24;
             match = true;
             for (u64 i = 0; i < len; i++)
-                if (text[kpos + i] != text[s + i]) { match = false; break; }
-            if (match && lenf == HT_LEN_SAT) match = phrase_len_bits(start_bits, end_bits, n, kpos) == len;
+                if (ttext[kpos + i] != qtext[s + i]) { match = false; break; }
+            if (match && lenf == HT_LEN_SAT) match = start_bits != nullptr && phrase_len_bits(start_bits, end_bits, n, kpos) == len;
         }
         if (match) {
-            atomicAdd(&table[slot].y, 1ULL);
+            if (INSERT) atomicAdd(&table[slot].y, add);
             return (u32)slot;
         }
         if (++slot == cap) slot = 0;
     }
-    atomicExch(overflow, 1u);
+    if (INSERT) atomicExch(overflow, 1u);
     return HT_OVERFLOW;
+}
+template <class CellT>
+__device__ __forceinline__ u32 table_insert_global(const CellT* __restrict__ text, u64 s, u64 len, ulonglong2* table, u64 cap, const u32* __restrict__ start_bits,
+                                                   const u32* __restrict__ end_bits, u64 n, u32* overflow) {
+    return table_probe<CellT, true>(text, s, len, text, table, cap, 1ULL, start_bits, end_bits, n, overflow);
 }
 
 // ---- thread-per-phrase variant over a compacted start array (unique-heavy rounds: maximum memory-level parallelism) ----
@@ -530,6 +538,69 @@ static __global__ void __launch_bounds__(256) table_occupancy_kernel(const ulong
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;  // cap is a multiple of 256
     const u32 b = __ballot_sync(0xffffffffu, table[i].x != HT_EMPTY);
     if (lane_id() == 0) occ_bits[i >> 5] = b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU exchange helpers: a "pack" is a list of phrases as (lens[m], counts[m], cells
+// concatenated); packs travel between ranks, and the same table code dedups them by treating the pack's
+// cell buffer as the text the keys point into.
+// ------------------------------------------------------------------------------------------------
+template <class CellT>
+__global__ void __launch_bounds__(256) phrase_owner_kernel(const CellT* __restrict__ text, const u64* __restrict__ ph_pos, const u32* __restrict__ ph_len, u64 d,
+                                                           u32 n_ranks, u64* __restrict__ keys, u32* __restrict__ vals) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d) return;
+    keys[i] = phrase_hash<CellT>(text, ph_pos[i], ph_len[i]) % n_ranks;  // content hash: the same owner on every rank
+    vals[i] = (u32)i;
+}
+static __global__ void gather_u32_kernel(const u32* __restrict__ src, const u32* __restrict__ perm, u64 m, u32* __restrict__ dst) {
+    const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < m) dst[k] = src[perm[k]];
+}
+// first[g] = number of sorted keys < g, for g = 0..n_ranks
+static __global__ void owner_bounds_kernel(const u64* __restrict__ keys, u64 m, u32 n_ranks, u64* __restrict__ first) {
+    const u32 g = threadIdx.x;
+    if (g > n_ranks) return;
+    u64 lo = 0, hi = m;
+    while (lo < hi) {
+        const u64 mid = (lo + hi) >> 1;
+        if (keys[mid] < g) lo = mid + 1; else hi = mid;
+    }
+    first[g] = lo;
+}
+// out[k] = phrase perm[k] (or k) of (src_text, ph_pos, ph_len, ph_cnt); cells at offs[k]
+template <class CellT>
+__global__ void __launch_bounds__(256) pack_phrases_kernel(const CellT* __restrict__ src_text, const u64* __restrict__ ph_pos, const u32* __restrict__ ph_len,
+                                                           const u64* __restrict__ ph_cnt, const u32* __restrict__ perm, const u64* __restrict__ offs, u64 m,
+                                                           u32* __restrict__ out_lens, u64* __restrict__ out_counts, CellT* __restrict__ out_cells) {
+    const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    const u32 i = perm ? perm[k] : (u32)k;
+    const u32 len = ph_len[i];
+    const u64 pos = ph_pos[i], o = offs[k];
+    out_lens[k] = len;
+    out_counts[k] = ph_cnt[i];
+    for (u32 t = 0; t < len; t++) out_cells[o + t] = src_text[pos + t];
+}
+// dedup of a pack into a table whose keys point into the pack's own cells; count += counts[k] (or the index k when counts == nullptr)
+template <class CellT>
+__global__ void __launch_bounds__(256) pack_insert_kernel(const CellT* __restrict__ cells, const u64* __restrict__ offs, const u32* __restrict__ lens,
+                                                          const u64* __restrict__ counts, u64 m, ulonglong2* table, u64 cap, u32* overflow) {
+    const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    if (*reinterpret_cast<volatile u32*>(overflow)) return;
+    table_probe<CellT, true>(cells, offs[k], lens[k], cells, table, cap, counts ? counts[k] : k, nullptr, nullptr, 0, overflow);
+}
+// metasymbol of every local distinct phrase: look its cells up in the global dictionary's table
+template <class CellT>
+__global__ void __launch_bounds__(256) map_local_kernel(const CellT* __restrict__ text, const u64* __restrict__ ph_pos, const u32* __restrict__ ph_len,
+                                                        const u32* __restrict__ occ_slots, u64 d, const CellT* __restrict__ gcells, ulonglong2* gtable,
+                                                        u64 gcap, const u64* __restrict__ g_meta, ulonglong2* ltable, u32* missing) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d) return;
+    const u32 gs = table_probe<CellT, false>(text, ph_pos[i], ph_len[i], gcells, gtable, gcap, 0, nullptr, nullptr, 0, nullptr);
+    if (gs == HT_OVERFLOW) { atomicExch(missing, 1u); return; }
+    ltable[occ_slots[i]].y = g_meta[gtable[gs].y];
 }
 
 // ------------------------------------------------------------------------------------------------

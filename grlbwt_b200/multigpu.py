@@ -1,0 +1,237 @@
+"""Multi-GPU parse phase: one process per GPU, shards of whole strings, one
+hash-partitioned all-to-all-v + one all-gather-v of the round's dictionary over NCCL per round.
+
+torch.distributed is plumbing here: every device step before, between and after the collectives is a
+call into libgrlgpu.so (grlgpu_mg_* in include/grlgpu.h). The orchestration is written against a small
+engine interface so that the same code runs under gloo on CPU tensors with a test double
+(tests/cpu_engine.py) -- that is how the N>1 logic is covered without GPUs.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+CELL_T = {1: torch.uint8, 2: torch.int16, 4: torch.int32, 8: torch.int64}
+
+
+def shard_bounds(text: np.ndarray, n_ranks: int):
+    """Contiguous ranges of WHOLE strings balanced by symbol count (the reference's mt split,
+    parsing_strategies.h:208-214, but byte-balanced). -> list of (begin, end) cell offsets."""
+    sep = text[-1]
+    ends = np.flatnonzero(text == sep) + 1  # one past each string
+    if ends.size < n_ranks:
+        raise ValueError(f"{ends.size} strings cannot be split over {n_ranks} ranks")
+    bounds, begin = [], 0
+    for r in range(n_ranks):
+        if r == n_ranks - 1:
+            end = int(text.size)
+        else:
+            target = (r + 1) * text.size // n_ranks
+            k = int(np.searchsorted(ends, target))
+            k = min(max(k, r), ends.size - (n_ranks - r))  # every remaining rank keeps at least one string
+            end = int(ends[k])
+            if end <= begin:
+                end = int(ends[np.searchsorted(ends, begin + 1)])
+        bounds.append((begin, end))
+        begin = end
+    return bounds
+
+
+class GpuEngine:
+    """The device side of one rank: a thin adapter from tensors to the C ABI."""
+
+    def __init__(self, ctx, device):
+        self.ctx, self.device = ctx, device
+
+    def alloc(self, n, dtype):
+        return torch.empty(max(int(n), 1), dtype=dtype, device=self.device)
+
+    def stats(self):
+        s = self.ctx.stats()
+        return {k: getattr(s, k) for k, _ in s._fields_}
+
+    def histogram(self):
+        return self.ctx.histogram()
+
+    def set_alphabet(self, max_sym):
+        self.ctx.mg_set_alphabet(max_sym)
+
+    def cell_bytes(self):
+        return self.ctx.cell_bytes()
+
+    def local(self, n_ranks):
+        return self.ctx.mg_local(n_ranks)
+
+    def pack(self, lens, counts, cells):
+        self.ctx.mg_pack(lens.data_ptr(), counts.data_ptr(), cells.data_ptr())
+
+    def merge(self, lens, counts, cells, m, n_cells):
+        return self.ctx.mg_merge(lens.data_ptr(), counts.data_ptr(), cells.data_ptr(), m, n_cells)
+
+    def pack_part(self, lens, freqs, cells):
+        self.ctx.mg_pack_part(lens.data_ptr(), freqs.data_ptr(), cells.data_ptr())
+
+    def global_round(self, lens, freqs, cells, d, n_cells, done):
+        return self.ctx.mg_global(lens.data_ptr(), freqs.data_ptr(), cells.data_ptr(), d, n_cells, done)
+
+    def fetch_level(self):
+        return self.ctx.fetch_level()
+
+    def fetch_parse(self):
+        return self.ctx.fetch_parse()
+
+
+def _staged():
+    """gloo cannot move CUDA tensors in every collective: stage through the host there (tests on a 1-GPU box)"""
+    return dist.get_backend() == "gloo"
+
+
+def _all_reduce(t, op=dist.ReduceOp.SUM):
+    if _staged() and t.is_cuda:
+        c = t.cpu()
+        dist.all_reduce(c, op=op)
+        t.copy_(c)
+    else:
+        dist.all_reduce(t, op=op)
+
+
+def _broadcast(t, src):
+    if _staged() and t.is_cuda:
+        c = t.cpu()
+        dist.broadcast(c, src=src)
+        t.copy_(c)
+    else:
+        dist.broadcast(t, src=src)
+
+
+def _all_gather_small(t):
+    c = t.cpu() if (_staged() and t.is_cuda) else t
+    out = [torch.empty_like(c) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, c)
+    return [x.cpu().tolist() for x in out]
+
+
+def _all_to_all_single(recv, send, recv_counts=None, send_counts=None):
+    if _staged() and send.is_cuda:
+        cs, cr = send.cpu(), torch.empty(recv.shape, dtype=recv.dtype)
+        dist.all_to_all_single(cr, cs, recv_counts, send_counts)
+        recv.copy_(cr)
+    else:
+        dist.all_to_all_single(recv, send, recv_counts, send_counts)
+
+
+def _all_to_all_v(send, send_counts, recv_counts, engine):
+    recv = engine.alloc(sum(recv_counts), send.dtype)
+    _all_to_all_single(recv[: sum(recv_counts)], send[: sum(send_counts)], list(recv_counts), list(send_counts))
+    return recv
+
+
+def _all_gather_v(part, counts, engine):
+    """concatenation of every rank's `part[:counts[rank]]`, in rank order, on every rank"""
+    out = engine.alloc(sum(counts), part.dtype)
+    off = 0
+    me = dist.get_rank()
+    for r, c in enumerate(counts):
+        if c:
+            sl = out[off: off + c]
+            if r == me:
+                sl.copy_(part[:c])
+            _broadcast(sl, r)
+        off += c
+    return out
+
+
+def distributed_round(engine, n_strings_global: int, timings: dict | None = None):
+    """One parse round over all ranks. -> (round info dict, done)"""
+    G = dist.get_world_size()
+    w = engine.cell_bytes()
+    per_owner, parse_len_local = engine.local(G)  # [(n_phrases, n_cells)] * G
+    t = torch.tensor([parse_len_local], dtype=torch.int64, device=engine.device)
+    _all_reduce(t)
+    done = int(t.item()) == n_strings_global
+
+    # ---- hash-partitioned all-to-all-v of the local dictionaries ----
+    n_phr = [p[0] for p in per_owner]
+    n_cel = [p[1] for p in per_owner]
+    lens = engine.alloc(sum(n_phr), torch.int32)
+    counts = engine.alloc(sum(n_phr), torch.int64)
+    cells = engine.alloc(sum(n_cel) * w, torch.uint8)
+    engine.pack(lens, counts, cells)
+    sizes = torch.tensor([[a, b] for a, b in zip(n_phr, n_cel)], dtype=torch.int64, device=engine.device)
+    rsizes = torch.empty_like(sizes)
+    _all_to_all_single(rsizes, sizes)
+    rs = rsizes.cpu().tolist()
+    r_phr = [int(x[0]) for x in rs]
+    r_cel = [int(x[1]) for x in rs]
+    rlens = _all_to_all_v(lens, n_phr, r_phr, engine)
+    rcounts = _all_to_all_v(counts, n_phr, r_phr, engine)
+    rcells = _all_to_all_v(cells, [c * w for c in n_cel], [c * w for c in r_cel], engine)
+    exchanged = (sum(n_phr) * 12 + sum(n_cel) * w)
+
+    # ---- owner-side dedup, then all-gather-v of the deduplicated partitions ----
+    d_part, c_part = engine.merge(rlens, rcounts, rcells, sum(r_phr), sum(r_cel))
+    plens = engine.alloc(d_part, torch.int32)
+    pfreqs = engine.alloc(d_part, torch.int64)
+    pcells = engine.alloc(c_part * w, torch.uint8)
+    engine.pack_part(plens, pfreqs, pcells)
+    mine = torch.tensor([d_part, c_part], dtype=torch.int64, device=engine.device)
+    allsz = _all_gather_small(mine)
+    g_phr = [int(x[0]) for x in allsz]
+    g_cel = [int(x[1]) for x in allsz]
+    glens = _all_gather_v(plens, g_phr, engine)
+    gfreqs = _all_gather_v(pfreqs, g_phr, engine)
+    gcells = _all_gather_v(pcells, [c * w for c in g_cel], engine)
+    gathered = (sum(g_phr) * 12 + sum(g_cel) * w)
+
+    info = engine.global_round(glens, gfreqs, gcells, sum(g_phr), sum(g_cel), done)
+    info["exchange_bytes_sent"] = exchanged
+    info["gather_bytes"] = gathered
+    if timings is not None:
+        timings.setdefault("rounds", []).append(info)
+    return info, done
+
+
+def par_phase_distributed(engine, collect_levels: bool = True):
+    """The whole parse phase over all ranks. Every rank must have its shard set in the engine already.
+    -> dict(stats, levels (rank 0 only), final_parse (rank 0 only, string order), rounds)"""
+    G, me = dist.get_world_size(), dist.get_rank()
+    st = engine.stats()
+    dev = engine.device
+    red = torch.tensor([st["max_sym"], -int(st["min_sym"]), -int(st["sep_sym"]), int(st["sep_sym"])], dtype=torch.int64, device=dev)
+    _all_reduce(red, dist.ReduceOp.MAX)
+    max_sym, min_sym, sep_lo, sep_hi = int(red[0]), -int(red[1]), -int(red[2]), int(red[3])
+    if sep_lo != sep_hi or sep_lo != min_sym:
+        raise ValueError("the collection is ill formed: ranks disagree on the separator or it is not the smallest symbol")
+    sums = torch.tensor([st["n_syms"], st["n_strings"]], dtype=torch.int64, device=dev)
+    _all_reduce(sums)
+    n_syms, n_strings = int(sums[0]), int(sums[1])
+    longest = torch.tensor([st["longest_string"]], dtype=torch.int64, device=dev)
+    _all_reduce(longest, dist.ReduceOp.MAX)
+    if engine.cell_bytes() == 1:  # byte alphabet: highest count of the GLOBAL histogram (utils.cpp:161-175)
+        h = torch.from_numpy(engine.histogram().astype(np.int64)).to(dev)
+        _all_reduce(h)
+        max_sym_freq = int(h.max())
+    else:
+        max_sym_freq = n_syms  # utils.cpp:117
+    engine.set_alphabet(max_sym)
+    gstats = {"n_syms": n_syms, "n_strings": n_strings, "longest_string": int(longest[0]), "min_sym": min_sym, "max_sym": max_sym,
+              "max_sym_freq": max_sym_freq, "sep_sym": sep_lo}
+    levels, rounds = [], []
+    while True:
+        info, done = distributed_round(engine, n_strings)
+        rounds.append(info)
+        if collect_levels and me == 0:
+            L = engine.fetch_level()
+            L["alphabet"], L["tot"] = info["alphabet"], info["tot_phrases"]
+            levels.append(L)
+        if done:
+            break
+    # final parse: one cell per string, gathered to rank 0 in rank (= string) order
+    fp = np.ascontiguousarray(engine.fetch_parse()).astype(np.int64)
+    mine = torch.tensor([fp.size], dtype=torch.int64, device=dev)
+    cnts = [int(x[0]) for x in _all_gather_small(mine)]
+    part = torch.from_numpy(fp).to(dev)
+    full = _all_gather_v(part, cnts, engine)
+    final_parse = full[: sum(cnts)].cpu().numpy().astype(np.uint64) if me == 0 else None
+    return {"stats": gstats, "levels": levels, "final_parse": final_parse, "rounds": rounds}

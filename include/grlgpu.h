@@ -114,6 +114,36 @@ int grlgpu_fetch_dictionary(grlgpu_ctx* ctx, uint64_t* syms, uint64_t* lens, uin
 const char* grlgpu_strerror(int status);
 const char* grlgpu_last_error(const grlgpu_ctx* ctx);
 
+/* ---- multi-GPU rounds ---------------------------------------------------------------------
+ * One context per GPU, each holding a shard of WHOLE strings (the reference's own split,
+ * include/parsing_strategies.h:208-214, so no phrase crosses a shard). The caller owns the exchange (NCCL
+ * through torch.distributed in bench.py / grlbwt_b200/multigpu.py); the library does every device step
+ * before, between and after. Per round, on every rank, in this order:
+ *   grlgpu_mg_local      boundary scan + local dedup; per owner rank (content hash % n_ranks) how many distinct
+ *                        local phrases / cells go there; local parse length (caller all-reduces termination)
+ *   grlgpu_mg_pack       fill caller-allocated DEVICE send buffers, ordered by owner   -> all-to-all-v
+ *   grlgpu_mg_merge      owner side: dedup what arrived, sum the counts                -> partition sizes
+ *   grlgpu_mg_pack_part  fill DEVICE buffers with this rank's partition               -> all-gather-v
+ *   grlgpu_mg_global     the gathered dictionary (identical on every rank, rank order) is ranked exactly as in
+ *                        grlgpu_round; local phrases get their metasymbols; the shard is rewritten.
+ * Level artefacts are identical on every rank (fetch them on one). Before the first round every rank calls
+ * grlgpu_stats and then grlgpu_mg_set_alphabet with the maximum symbol over all ranks.
+ * replaces: mt_parse_strat_t's thread fan-out + serial join_thread_phrases (parsing_strategies.h:244-386). */
+typedef struct {
+    uint64_t n_phrases;
+    uint64_t n_cells;
+} grlgpu_part_t;
+/* byte alphabets: the 256-bin symbol histogram behind grlgpu_stats (ranks sum theirs to get the global max_sym_freq) */
+int grlgpu_histogram(grlgpu_ctx* ctx, uint64_t* hist256);
+int grlgpu_mg_set_alphabet(grlgpu_ctx* ctx, uint64_t global_max_sym);
+int grlgpu_mg_local(grlgpu_ctx* ctx, int n_ranks, grlgpu_part_t* per_owner, uint64_t* parse_len_local);
+int grlgpu_mg_pack(grlgpu_ctx* ctx, uint32_t* d_lens, uint64_t* d_counts, void* d_cells);
+int grlgpu_mg_merge(grlgpu_ctx* ctx, const uint32_t* d_lens, const uint64_t* d_counts, const void* d_cells, uint64_t m, uint64_t n_cells,
+                    grlgpu_part_t* part);
+int grlgpu_mg_pack_part(grlgpu_ctx* ctx, uint32_t* d_lens, uint64_t* d_freqs, void* d_cells);
+int grlgpu_mg_global(grlgpu_ctx* ctx, const uint32_t* d_lens, const uint64_t* d_freqs, const void* d_cells, uint64_t d, uint64_t n_cells,
+                     int done_global, grlgpu_round_t* out);
+
 /* launch accounting: number of kernel launches issued by this context so far, and (after
  * grlgpu_profile_enable(ctx, 1)) per-kernel CUDA-event durations measured live on the launch stream.
  * grlgpu_profile_entry returns 1 past the last entry; model_bytes = expected DRAM bytes of the launches. */
