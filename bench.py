@@ -154,6 +154,7 @@ def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     import grlbwt_b200 as G
+    from grlbwt_b200 import multigpu as M
 
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the parse phase has no CPU fallback")
@@ -168,35 +169,64 @@ def run_ours(args, rank, world, local_rank):
         pass
     hbm_peak, peak_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json (measured copy)") if "hbm_gbs" in peaks else (6650.0, "fallback 6.65 TB/s")
 
-    text = make_reads_on_device(torch, args.reads, 42 + rank, dev)
+    # strong scaling: the C2 collection (args.reads reads) is split into contiguous ranges of whole reads, one per rank
+    my_reads = args.reads // world + (1 if rank < args.reads % world else 0)
+    text = make_reads_on_device(torch, my_reads, 42 + rank, dev)
     n = text.numel()
+    n_total = args.reads * (READ_LEN + 1)
     torch.cuda.synchronize()
     stream = torch.cuda.Stream(device=dev)   # the library issues every kernel on this stream, so torch events bracket it
     torch.cuda.set_stream(stream)
     ctx = G.GrlGpu(local_rank, 0, stream=stream.cuda_stream)
+    engine = M.GpuEngine(ctx, dev)
+    arena = [None]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def run_phase(fetch, collect=None):
+        """all rounds on the text set in ctx; fetch: copy every level's artefacts + the final parse to the host"""
+        d2h = 0
+        if world == 1:
+            ctx.stats()
+            while True:
+                r = ctx.round()
+                if collect is not None:
+                    collect.append(r.as_dict())
+                if fetch:
+                    ctx.fetch_level(arena[0])
+                    d2h += r.tot_phrases * (2 * r.sym_bytes + 1) + r.n_pre_runs * (r.sym_bytes + 8)
+                if r.done:
+                    if fetch:
+                        d2h += ctx.fetch_parse(arena[0]).nbytes
+                    return d2h
+        st = M.global_stats(engine)
+        while True:
+            info, done = M.distributed_round(engine, st["n_strings"])
+            if collect is not None:
+                collect.append(info)
+            if fetch and rank == 0:
+                ctx.fetch_level(arena[0])
+                d2h += info["tot_phrases"] * (2 * info["sym_bytes"] + 1) + info["n_pre_runs"] * (info["sym_bytes"] + 8)
+            if done:
+                if fetch:
+                    fp = M.gather_final_parse(engine)
+                    d2h += 0 if fp is None else fp.nbytes
+                return d2h
+
     def step_resident(collect=None):
         ctx.set_text_device(text.data_ptr(), n, 1)
-        ctx.stats()
-        while True:
-            r = ctx.round()
-            if collect is not None:
-                collect.append(r.as_dict())
-            if r.done:
-                return
+        run_phase(False, collect)
 
     # ---- value: text resident in HBM ----
     for _ in range(args.warmup):
         step_resident()
     rounds_info = []
-    step_resident(rounds_info)           # untimed: per-round figures with per-kernel CUDA-event timing enabled
+    step_resident(rounds_info)           # untimed: per-round figures
     ctx.profile_reset(); ctx.profile_enable(True)
-    step_resident()
+    step_resident()                      # untimed: per-kernel CUDA-event timing enabled
     prof = ctx.profile()
     ctx.profile_enable(False); ctx.profile_reset()
 
@@ -217,7 +247,7 @@ def run_ours(args, rank, world, local_rank):
         t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
-    value = world * n * args.steps / 1e6 / (ms_total / 1e3)
+    value = n_total * args.steps / 1e6 / (ms_total / 1e3)
 
     # ---- e2e: host buffers through the C ABI ----
     e2e = None
@@ -226,42 +256,33 @@ def run_ours(args, rank, world, local_rank):
         host_text.copy_(text)
         torch.cuda.synchronize()
         host_np = host_text.numpy()
-        d2h_bytes = [0]
         # pinned landing zone for the level artefacts (largest level of the workload, measured in the resident steps)
-        need = max(r["tot_phrases"] * 17 + r["n_pre_runs"] * 16 + 256 for r in rounds_info) + rounds_info[-1]["parse_len"] * 8 + (1 << 20)
-        arena = torch.empty(int(need), dtype=torch.uint8, pin_memory=True).numpy()
+        need = max(r["tot_phrases"] * 17 + r["n_pre_runs"] * 16 + 256 for r in rounds_info) + args.reads * 8 + (1 << 20)
+        arena[0] = torch.empty(int(need), dtype=torch.uint8, pin_memory=True).numpy()
+        d2h_bytes = [0]
 
         def step_e2e():
             ctx.set_text(host_np)
-            ctx.stats()
-            b = 0
-            while True:
-                r = ctx.round()
-                ctx.fetch_level(arena)
-                b += r.tot_phrases * (2 * r.sym_bytes + 1) + r.n_pre_runs * (r.sym_bytes + 8)
-                if r.done:
-                    fp = ctx.fetch_parse(arena)
-                    b += fp.nbytes
-                    d2h_bytes[0] = b
-                    return
+            d2h_bytes[0] = run_phase(True)
 
-        for _ in range(max(1, min(args.warmup, 1))):
-            step_e2e()
+        step_e2e()
         barrier()
         t0 = time.perf_counter()
-        e0.record(stream)
         for _ in range(args.steps):
             step_e2e()
-        e1.record(stream)
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
         if world > 1:
-            t = torch.tensor([wall_ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            wall_ms = float(t.item())
-        e2e = {"value": round(world * n * args.steps / 1e6 / (wall_ms / 1e3), 3), "unit": "MB/s", "h2d_bytes_per_step": int(n),
-               "d2h_bytes_per_step": int(d2h_bytes[0]), "ms_per_step": round(wall_ms / args.steps, 3),
-               "timing": "host wall clock between stream synchronisations (fetches are host-blocking)"}
+            t = torch.tensor([wall_ms, float(n), float(d2h_bytes[0])], device=dev, dtype=torch.float64)
+            tm = t.clone()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            wall_ms, h2d_b, d2h_b = float(tm[0]), int(t[1]), int(t[2])
+        else:
+            h2d_b, d2h_b = n, d2h_bytes[0]
+        e2e = {"value": round(n_total * args.steps / 1e6 / (wall_ms / 1e3), 3), "unit": "MB/s", "h2d_bytes_per_step": int(h2d_b),
+               "d2h_bytes_per_step": int(d2h_b), "ms_per_step": round(wall_ms / args.steps, 3),
+               "timing": "host wall clock between stream synchronisations, max over ranks (fetches are host-blocking)"}
     ctx.close()
 
     # ---- roofline of the dominant kernel (CUDA events on the launch stream, live, one profiled step) ----
@@ -275,15 +296,16 @@ def run_ours(args, rank, world, local_rank):
                 "bytes_model": "expected DRAM bytes of the kernel's launches (SURVEY.md 8d traffic table; DESIGN.md kernels section)"}
     alg_bytes = sum(r["algorithmic_bytes"] for r in rounds_info)
     round_ms = sum(r["device_ms"] for r in rounds_info)
+    keys = ("round", "n_in", "parse_len", "n_phrases", "dict_syms", "tot_phrases", "n_pre_runs", "device_ms", "text_pass_ms", "dict_ms", "rewrite_ms",
+            "algorithmic_bytes", "exchange_bytes_sent", "gather_bytes")
     parse_rounds = {"algorithmic_GB": round(alg_bytes / 1e9, 3), "device_ms": round(round_ms, 3),
                     "achieved_GBps": round(alg_bytes / 1e6 / round_ms, 1) if round_ms else None,
                     "frac_of_measured_peak": round(alg_bytes / 1e6 / round_ms / hbm_peak, 4) if round_ms else None,
                     "frac_of_nominal_8TBps": round(alg_bytes / 1e6 / round_ms / 8000.0, 4) if round_ms else None,
-                    "per_round": [{k: (round(v, 3) if isinstance(v, float) else v) for k, v in r.items()
-                                   if k in ("round", "n_in", "parse_len", "n_phrases", "dict_syms", "tot_phrases", "n_pre_runs", "device_ms", "text_pass_ms", "dict_ms",
-                                            "rewrite_ms", "algorithmic_bytes")} for r in rounds_info]}
+                    "scope": "rank 0" if world > 1 else "whole job",
+                    "per_round": [{k: (round(v, 3) if isinstance(v, float) else v) for k, v in r.items() if k in keys} for r in rounds_info]}
     kernels = {k: {"launches": v[0], "ms": round(v[1], 3), "model_GBps": round(v[2] / 1e6 / v[1], 1) if v[1] > 0 else None}
-               for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:10]}
+               for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -295,11 +317,13 @@ def run_ours(args, rank, world, local_rank):
 
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 3), "unit": "MB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+                "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
                 "data": "synthetic",
-                "config": {"workload": f"C2: {args.reads} reads x {READ_LEN} bp uniform ACGT + newline per GPU ({n / 1e9:.3f} GB), BASELINE.json configs[1]",
-                           "reads_per_gpu": args.reads, "cache": "inputs (>= 302 MB per round-1 pass at the default size 7.55 GB) exceed the 126 MB L2",
-                           "parallelism": "1 GPU" if world == 1 else f"{world} ranks, one independent collection per rank (no cross-rank dictionary exchange yet)"},
+                "config": {"workload": f"C2: {args.reads} reads x {READ_LEN} bp uniform ACGT + newline ({n_total / 1e9:.3f} GB), BASELINE.json configs[1]",
+                           "reads": args.reads, "cache": "the text of every round-1 pass (7.55 GB at the default size) exceeds the 126 MB L2",
+                           "parallelism": "1 GPU" if world == 1 else
+                           f"{world} ranks: contiguous ranges of whole reads per rank; per round one hash-partitioned all-to-all-v of the local "
+                           f"dictionaries + one all-gather-v of the deduplicated global dictionary over NCCL; the dictionary ranking is replicated"},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parse_rounds": parse_rounds,
                 "kernels": kernels}
         print(json.dumps(line), flush=True)

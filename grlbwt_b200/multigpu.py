@@ -87,6 +87,13 @@ def _staged():
     return dist.get_backend() == "gloo"
 
 
+def _fence(t):
+    """NCCL collectives are ordered on torch's stream only; the library may run on another stream, so make the
+    result visible to the host (and thereby to any stream) before it is handed to the library"""
+    if t.is_cuda:
+        torch.cuda.synchronize(t.device)
+
+
 def _all_reduce(t, op=dist.ReduceOp.SUM):
     if _staged() and t.is_cuda:
         c = t.cpu()
@@ -103,6 +110,7 @@ def _broadcast(t, src):
         t.copy_(c)
     else:
         dist.broadcast(t, src=src)
+        _fence(t)
 
 
 def _all_gather_small(t):
@@ -119,6 +127,7 @@ def _all_to_all_single(recv, send, recv_counts=None, send_counts=None):
         recv.copy_(cr)
     else:
         dist.all_to_all_single(recv, send, recv_counts, send_counts)
+        _fence(recv)
 
 
 def _all_to_all_v(send, send_counts, recv_counts, engine):
@@ -192,10 +201,8 @@ def distributed_round(engine, n_strings_global: int, timings: dict | None = None
     return info, done
 
 
-def par_phase_distributed(engine, collect_levels: bool = True):
-    """The whole parse phase over all ranks. Every rank must have its shard set in the engine already.
-    -> dict(stats, levels (rank 0 only), final_parse (rank 0 only, string order), rounds)"""
-    G, me = dist.get_world_size(), dist.get_rank()
+def global_stats(engine):
+    """collection statistics over all ranks (collection_stats, utils.cpp:100-189) + the global alphabet set in the engine"""
     st = engine.stats()
     dev = engine.device
     red = torch.tensor([st["max_sym"], -int(st["min_sym"]), -int(st["sep_sym"]), int(st["sep_sym"])], dtype=torch.int64, device=dev)
@@ -215,11 +222,29 @@ def par_phase_distributed(engine, collect_levels: bool = True):
     else:
         max_sym_freq = n_syms  # utils.cpp:117
     engine.set_alphabet(max_sym)
-    gstats = {"n_syms": n_syms, "n_strings": n_strings, "longest_string": int(longest[0]), "min_sym": min_sym, "max_sym": max_sym,
-              "max_sym_freq": max_sym_freq, "sep_sym": sep_lo}
+    return {"n_syms": n_syms, "n_strings": n_strings, "longest_string": int(longest[0]), "min_sym": min_sym, "max_sym": max_sym,
+            "max_sym_freq": max_sym_freq, "sep_sym": sep_lo}
+
+
+def gather_final_parse(engine):
+    """final parse: one cell per string, gathered to rank 0 in rank (= string) order"""
+    dev = engine.device
+    fp = np.ascontiguousarray(engine.fetch_parse()).astype(np.int64)
+    mine = torch.tensor([fp.size], dtype=torch.int64, device=dev)
+    cnts = [int(x[0]) for x in _all_gather_small(mine)]
+    part = torch.from_numpy(fp).to(dev)
+    full = _all_gather_v(part, cnts, engine)
+    return full[: sum(cnts)].cpu().numpy().astype(np.uint64) if dist.get_rank() == 0 else None
+
+
+def par_phase_distributed(engine, collect_levels: bool = True):
+    """The whole parse phase over all ranks. Every rank must have its shard set in the engine already.
+    -> dict(stats, levels (rank 0 only), final_parse (rank 0 only, string order), rounds)"""
+    me = dist.get_rank()
+    gstats = global_stats(engine)
     levels, rounds = [], []
     while True:
-        info, done = distributed_round(engine, n_strings)
+        info, done = distributed_round(engine, gstats["n_strings"])
         rounds.append(info)
         if collect_levels and me == 0:
             L = engine.fetch_level()
@@ -227,11 +252,4 @@ def par_phase_distributed(engine, collect_levels: bool = True):
             levels.append(L)
         if done:
             break
-    # final parse: one cell per string, gathered to rank 0 in rank (= string) order
-    fp = np.ascontiguousarray(engine.fetch_parse()).astype(np.int64)
-    mine = torch.tensor([fp.size], dtype=torch.int64, device=dev)
-    cnts = [int(x[0]) for x in _all_gather_small(mine)]
-    part = torch.from_numpy(fp).to(dev)
-    full = _all_gather_v(part, cnts, engine)
-    final_parse = full[: sum(cnts)].cpu().numpy().astype(np.uint64) if me == 0 else None
-    return {"stats": gstats, "levels": levels, "final_parse": final_parse, "rounds": rounds}
+    return {"stats": gstats, "levels": levels, "final_parse": gather_final_parse(engine), "rounds": rounds}

@@ -66,7 +66,9 @@ def _worker(rank, world, port, backend, engine_kind, names, out_path):
             else:
                 dev = rank if backend == "nccl" else 0
                 torch.cuda.set_device(dev)
-                ctx = G.GrlGpu(dev)
+                stream = torch.cuda.Stream(device=dev)  # the library and torch's collectives share one stream
+                torch.cuda.set_stream(stream)
+                ctx = G.GrlGpu(dev, 0, stream=stream.cuda_stream)
                 ctx.set_text(shard)
                 eng = M.GpuEngine(ctx, torch.device("cuda", dev))
             res = M.par_phase_distributed(eng)
