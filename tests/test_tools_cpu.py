@@ -1,0 +1,62 @@
+"""CPU suite: the .rl_bwt consumer tools (grl2plain, grlbwt2rle, reverse_bwt, bwt_stats) -- SURVEY.md 8(f)-4.
+Round trip text -> BWT (oracle) -> .rl_bwt -> reverse_bwt == text."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import grlbwt_b200 as G
+from oracle import oracle as O
+
+NAMES = ["mississippi", "with_empty", "only_empty", "dna_500", "ac_short_3000", "high_bytes", "homopolymer", "u16_small_sigma", "u32_small_sigma",
+         "fuzz_5", "fuzz_19", "fuzz_60"]
+
+
+def tool(name):
+    return os.path.join(G.LIB_DIR, name)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_tools_round_trip(all_cases, tmp_path, name):
+    arr = all_cases[name]
+    o = O.Oracle(arr)
+    o.par_phase()
+    syms, lens, sb, fb = o.ind_phase()
+    rl = tmp_path / "x.rl_bwt"
+    rl.write_bytes(O.rl_bwt_bytes(syms, lens, sb, fb))
+    w = arr.dtype.itemsize
+    # reverse_bwt: the original collection, string by string
+    out = tmp_path / "rev.bin"
+    r = subprocess.run([tool("reverse_bwt"), str(rl), str(out), "-a", str(w)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert np.array_equal(np.fromfile(out, arr.dtype), arr)
+    # first two strings only
+    n_str = int((arr == arr[-1]).sum())
+    if n_str >= 2:
+        r = subprocess.run([tool("reverse_bwt"), str(rl), str(out), "2", "-a", str(w)], capture_output=True, text=True)
+        got = np.fromfile(out, arr.dtype)
+        ends = np.flatnonzero(arr == arr[-1])
+        assert np.array_equal(got, arr[: ends[1] + 1])
+    # grl2plain: the expanded BWT
+    plain = tmp_path / "plain.bin"
+    r = subprocess.run([tool("grl2plain"), str(rl), str(plain)], capture_output=True, text=True)
+    assert r.returncode == 0
+    cell = {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[1 if sb <= 1 else 2 if sb <= 2 else 4 if sb <= 4 else 8]
+    assert np.array_equal(np.fromfile(plain, cell).astype(np.uint64), np.repeat(syms, lens.astype(np.int64)))
+    # bwt_stats
+    r = subprocess.run([tool("bwt_stats"), str(rl)], capture_output=True, text=True)
+    assert f"BWT size (n):            {arr.size}" in r.stdout and f"Number of runs (r):      {len(syms)}" in r.stdout
+    assert f"Number of strings:       {n_str}" in r.stdout
+    if w == 1:
+        pre = tmp_path / "rle"
+        r = subprocess.run([tool("grlbwt2rle"), str(rl), str(pre)], capture_output=True, text=True)
+        assert r.returncode == 0
+        assert np.array_equal(np.fromfile(str(pre) + ".syms", np.uint8).astype(np.uint64), syms)
+        assert np.array_equal(np.fromfile(str(pre) + ".len", np.uint32).astype(np.uint64), lens)
+
+
+def test_tools_usage_messages():
+    for t in ("grl2plain", "grlbwt2rle", "reverse_bwt", "bwt_stats"):
+        r = subprocess.run([tool(t)], capture_output=True, text=True)
+        assert r.returncode == 0 and "usage:" in r.stdout
