@@ -292,7 +292,7 @@ def build_bwt_file(inp: str, out: str, sym_bytes: int = 1, device: int = 0, n_th
         raise GrlGpuError(rc, L.grlbwt_last_error().decode())
 
 
-def selftest_induce(levels, final_parse: np.ndarray):
+def selftest_induce(levels, final_parse: np.ndarray, n_threads: int = 0):
     """levels: list of dicts with alphabet, tot, rule_l, rule_r (u64), has_hocc (u8), pre_sym, pre_len (u64). CPU only."""
     L = lib_host()
     n = len(levels)
@@ -315,10 +315,10 @@ def selftest_induce(levels, final_parse: np.ndarray):
     fp = np.ascontiguousarray(final_parse, np.uint64)
     res = BwtResult()
     L.grlbwt_selftest_induce.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(u64p), C.POINTER(u64p), C.POINTER(u8p), C.c_void_p,
-                                         C.POINTER(u64p), C.POINTER(u64p), C.c_void_p, C.c_uint64, C.POINTER(BwtResult)]
+                                         C.POINTER(u64p), C.POINTER(u64p), C.c_void_p, C.c_uint64, C.c_int, C.POINTER(BwtResult)]
     rc = L.grlbwt_selftest_induce(n, _ptr(alph), _ptr(tot), arr("rule_l", np.uint64, u64p), arr("rule_r", np.uint64, u64p),
                                   arr("has_hocc", np.uint8, u8p), _ptr(npre), arr("pre_sym", np.uint64, u64p), arr("pre_len", np.uint64, u64p),
-                                  _ptr(fp), fp.size, C.byref(res))
+                                  _ptr(fp), fp.size, n_threads, C.byref(res))
     if rc != 0:
         raise RuntimeError(L.grlbwt_last_error().decode())
     try:

@@ -17,6 +17,7 @@
 
 #include "../../include/grlgpu.h"
 #include "ind_phase.hpp"
+#include "ind_phase_mt.hpp"
 #include "rl_bwt_io.hpp"
 
 // same role as the reference's tmp_workspace (external/cdt/include/utils.h:52-104): a private folder
@@ -49,7 +50,9 @@ namespace grlbwt {
 
 struct ParseResult {
     grlgpu_stats_t stats{};
-    std::vector<Level> levels;
+    std::vector<Level> levels;        // 64-bit symbols: only filled when some level needs them
+    std::vector<Level32> levels32;    // 32-bit symbols (the usual case), consumed by the multi-threaded induction
+    bool wide = false;
     std::vector<grlgpu_round_t> rounds;
     std::vector<uint64_t> final_parse;  // one cell per string, cells = rank<<1|rep
     double h2d_ms = 0, par_ms = 0;
@@ -92,23 +95,49 @@ inline ParseResult gpu_par_phase(const void* text, uint64_t n_syms, int sym_byte
     for (;;) {
         grlgpu_round_t r;
         if ((rc = grlgpu_round(ctx, &r)) != GRLGPU_OK) fail("grlgpu_round", rc);
-        Level L;
-        L.alphabet = r.alphabet;
-        L.tot_phrases = r.tot_phrases;
-        L.has_hocc.resize(r.tot_phrases);
-        L.pre_len.resize(r.n_pre_runs);
-        L.rule_l.resize(r.tot_phrases);
-        L.rule_r.resize(r.tot_phrases);
-        L.pre_sym.resize(r.n_pre_runs);
-        if (r.sym_bytes == 8) {
+        if (r.sym_bytes == 8 && !res.wide) {  // first wide level: move what was collected so far to 64-bit symbols
+            res.wide = true;
+            for (const Level32& s : res.levels32) {
+                Level L;
+                L.alphabet = s.alphabet; L.tot_phrases = s.tot_phrases; L.has_hocc = s.has_hocc; L.pre_len = s.pre_len;
+                L.rule_l.assign(s.rule_l.begin(), s.rule_l.end()); L.rule_r.assign(s.rule_r.begin(), s.rule_r.end());
+                L.pre_sym.assign(s.pre_sym.begin(), s.pre_sym.end());
+                res.levels.push_back(std::move(L));
+            }
+            res.levels32.clear();
+        }
+        if (!res.wide) {
+            Level32 L;
+            L.alphabet = r.alphabet;
+            L.tot_phrases = r.tot_phrases;
+            L.has_hocc.resize(r.tot_phrases);
+            L.pre_len.resize(r.n_pre_runs);
+            L.rule_l.resize(r.tot_phrases);
+            L.rule_r.resize(r.tot_phrases);
+            L.pre_sym.resize(r.n_pre_runs);
             rc = grlgpu_fetch_level(ctx, L.rule_l.data(), L.rule_r.data(), L.has_hocc.data(), L.pre_sym.data(), L.pre_len.data());
             if (rc != GRLGPU_OK) fail("grlgpu_fetch_level", rc);
+            res.levels32.push_back(std::move(L));
         } else {
-            std::vector<uint32_t> l32(r.tot_phrases), r32(r.tot_phrases), p32(r.n_pre_runs);
-            rc = grlgpu_fetch_level(ctx, l32.data(), r32.data(), L.has_hocc.data(), p32.data(), L.pre_len.data());
-            if (rc != GRLGPU_OK) fail("grlgpu_fetch_level", rc);
-            for (uint64_t i = 0; i < r.tot_phrases; i++) { L.rule_l[i] = l32[i]; L.rule_r[i] = r32[i]; }
-            for (uint64_t i = 0; i < r.n_pre_runs; i++) L.pre_sym[i] = p32[i];
+            Level L;
+            L.alphabet = r.alphabet;
+            L.tot_phrases = r.tot_phrases;
+            L.has_hocc.resize(r.tot_phrases);
+            L.pre_len.resize(r.n_pre_runs);
+            L.rule_l.resize(r.tot_phrases);
+            L.rule_r.resize(r.tot_phrases);
+            L.pre_sym.resize(r.n_pre_runs);
+            if (r.sym_bytes == 8) {
+                rc = grlgpu_fetch_level(ctx, L.rule_l.data(), L.rule_r.data(), L.has_hocc.data(), L.pre_sym.data(), L.pre_len.data());
+                if (rc != GRLGPU_OK) fail("grlgpu_fetch_level", rc);
+            } else {
+                std::vector<uint32_t> l32(r.tot_phrases), r32(r.tot_phrases), p32(r.n_pre_runs);
+                rc = grlgpu_fetch_level(ctx, l32.data(), r32.data(), L.has_hocc.data(), p32.data(), L.pre_len.data());
+                if (rc != GRLGPU_OK) fail("grlgpu_fetch_level", rc);
+                for (uint64_t i = 0; i < r.tot_phrases; i++) { L.rule_l[i] = l32[i]; L.rule_r[i] = r32[i]; }
+                for (uint64_t i = 0; i < r.n_pre_runs; i++) L.pre_sym[i] = p32[i];
+            }
+            res.levels.push_back(std::move(L));
         }
         if (verbose) {
             std::cout << "  Parsing round " << r.round << std::endl;
@@ -120,7 +149,6 @@ inline ParseResult gpu_par_phase(const void* text, uint64_t n_syms, int sym_byte
             std::cout << "      Device time (ms):                 " << r.device_ms << " (text " << r.text_pass_ms << ", dictionary " << r.dict_ms
                       << ", rewrite " << r.rewrite_ms << ")" << std::endl;
         }
-        res.levels.push_back(std::move(L));
         res.rounds.push_back(r);
         if (r.done) {
             res.final_parse.resize(r.parse_len);
@@ -140,19 +168,29 @@ inline ParseResult gpu_par_phase(const void* text, uint64_t n_syms, int sym_byte
 }
 
 struct BwtResult {
-    RunList runs;
+    RunList runs;        // 64-bit symbols (wide alphabets)
+    RunArr runs32;       // 32-bit symbols (the usual case), filled when narrow
+    bool narrow = false;
+    size_t n_runs() const { return narrow ? runs32.size() : runs.size(); }
+    void write(const std::string& path) const {
+        if (narrow) write_rl_bwt(path, runs32.sym.data(), runs32.len.data(), runs32.size(), sb, fb);
+        else write_rl_bwt(path, runs.sym.data(), runs.len.data(), runs.size(), sb, fb);
+    }
     uint64_t sb = 0, fb = 0;
     ParseResult parse;
     double ind_ms = 0;
 };
 
 inline BwtResult build_bwt(const void* text, uint64_t n_syms, int sym_bytes, int device, size_t n_threads, bool verbose) {
-    (void)n_threads;
     BwtResult out;
     out.parse = gpu_par_phase(text, n_syms, sym_bytes, device, verbose);
     auto t0 = std::chrono::steady_clock::now();
     if (verbose) std::cout << "Inferring the BWT" << std::endl;
-    out.runs = ind_phase<uint64_t>(out.parse.levels, out.parse.final_parse.data(), out.parse.final_parse.size());
+    if (out.parse.wide) out.runs = ind_phase<uint64_t>(out.parse.levels, out.parse.final_parse.data(), out.parse.final_parse.size());
+    else {  // -t host threads drive the induction
+        out.runs32 = ind_phase_mt(out.parse.levels32, out.parse.final_parse.data(), out.parse.final_parse.size(), std::max<size_t>(1, n_threads));
+        out.narrow = true;
+    }
     out.ind_ms = ms_since(t0);
     // header widths of the level-0 BWT (exact_ind_phase.cpp:274-276 with the level-0 dictionary: alphabet =
     // max_sym+1+3, prev_alphabet = 0, max_sym_freq from collection_stats)
@@ -198,7 +236,7 @@ void grl_bwt_algo(std::string& i_file, std::string& o_file, tmp_workspace& tmp_w
         throw;
     }
     std::string tmp_out = tmp_ws.get_file("bwt_lev_0");
-    grlbwt::write_rl_bwt(tmp_out, res.runs.sym.data(), res.runs.len.data(), res.runs.size(), res.sb, res.fb);
+    res.write(tmp_out);
     std::error_code ec;
     std::filesystem::rename(tmp_out, o_file, ec);
     if (ec) {  // the reference fails across filesystems (grl_bwt.hpp:77); copy instead

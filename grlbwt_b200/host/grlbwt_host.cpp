@@ -17,14 +17,20 @@ int grlbwt_build(const void* text, uint64_t n_syms, int sym_bytes, int device, i
     memset(out, 0, sizeof(*out));
     try {
         grlbwt::BwtResult r = grlbwt::build_bwt(text, n_syms, sym_bytes, device, (size_t)(n_threads > 0 ? n_threads : 1), verbose != 0);
-        out->n_runs = r.runs.size();
+        const size_t nr = r.n_runs();
+        out->n_runs = nr;
         out->sb = r.sb;
         out->fb = r.fb;
-        out->syms = (uint64_t*)malloc((r.runs.size() ? r.runs.size() : 1) * sizeof(uint64_t));
-        out->lens = (uint64_t*)malloc((r.runs.size() ? r.runs.size() : 1) * sizeof(uint64_t));
+        out->syms = (uint64_t*)malloc((nr ? nr : 1) * sizeof(uint64_t));
+        out->lens = (uint64_t*)malloc((nr ? nr : 1) * sizeof(uint64_t));
         if (!out->syms || !out->lens) { free(out->syms); free(out->lens); g_last_error = "out of host memory"; return -100; }
-        memcpy(out->syms, r.runs.sym.data(), r.runs.size() * sizeof(uint64_t));
-        memcpy(out->lens, r.runs.len.data(), r.runs.size() * sizeof(uint64_t));
+        if (r.narrow) {
+            for (size_t k = 0; k < nr; k++) out->syms[k] = r.runs32.sym[k];
+            memcpy(out->lens, r.runs32.len.data(), nr * sizeof(uint64_t));
+        } else {
+            memcpy(out->syms, r.runs.sym.data(), nr * sizeof(uint64_t));
+            memcpy(out->lens, r.runs.len.data(), nr * sizeof(uint64_t));
+        }
         out->n_rounds = r.parse.rounds.size();
         out->h2d_ms = r.parse.h2d_ms;
         out->par_phase_ms = r.parse.par_ms;
@@ -54,7 +60,7 @@ int grlbwt_build_file(const char* input_file, const char* output_file, int sym_b
         std::vector<unsigned char> buf = grlbwt::read_whole_file(input_file);
         if (buf.empty() || buf.size() % (size_t)sym_bytes) return GRLGPU_ERR_ILL_FORMED;
         grlbwt::BwtResult r = grlbwt::build_bwt(buf.data(), buf.size() / (size_t)sym_bytes, sym_bytes, device, (size_t)(n_threads > 0 ? n_threads : 1), verbose != 0);
-        grlbwt::write_rl_bwt(output_file, r.runs.sym.data(), r.runs.len.data(), r.runs.size(), r.sb, r.fb);
+        r.write(output_file);
         return GRLGPU_OK;
     } catch (const grlbwt::GpuError& e) {
         g_last_error = e.what();
@@ -70,8 +76,28 @@ const char* grlbwt_last_error(void) { return g_last_error.c_str(); }
 // host induction alone, from caller-provided level artefacts (CPU-only self test of ind_phase.hpp)
 int grlbwt_selftest_induce(int n_levels, const uint64_t* alphabet, const uint64_t* tot, const uint64_t* const* rule_l, const uint64_t* const* rule_r,
                            const uint8_t* const* has_hocc, const uint64_t* n_pre, const uint64_t* const* pre_sym, const uint64_t* const* pre_len,
-                           const uint64_t* final_parse, uint64_t n_strings, grlbwt_result_t* out) {
+                           const uint64_t* final_parse, uint64_t n_strings, int n_threads, grlbwt_result_t* out) {
     try {
+        if (n_threads > 0) {  // multi-threaded 32-bit path (ind_phase_mt.hpp)
+            std::vector<grlbwt::Level32> lv((size_t)n_levels);
+            for (int i = 0; i < n_levels; i++) {
+                grlbwt::Level32& L = lv[(size_t)i];
+                L.alphabet = alphabet[i];
+                L.tot_phrases = tot[i];
+                L.rule_l.assign(rule_l[i], rule_l[i] + tot[i]);
+                L.rule_r.assign(rule_r[i], rule_r[i] + tot[i]);
+                L.has_hocc.assign(has_hocc[i], has_hocc[i] + tot[i]);
+                L.pre_sym.assign(pre_sym[i], pre_sym[i] + n_pre[i]);
+                L.pre_len.assign(pre_len[i], pre_len[i] + n_pre[i]);
+            }
+            grlbwt::RunArr r = grlbwt::ind_phase_mt(lv, final_parse, n_strings, (size_t)n_threads);
+            memset(out, 0, sizeof(*out));
+            out->n_runs = r.size();
+            out->syms = (uint64_t*)malloc((r.size() ? r.size() : 1) * sizeof(uint64_t));
+            out->lens = (uint64_t*)malloc((r.size() ? r.size() : 1) * sizeof(uint64_t));
+            for (size_t k = 0; k < r.size(); k++) { out->syms[k] = r.sym[k]; out->lens[k] = r.len[k]; }
+            return 0;
+        }
         std::vector<grlbwt::Level> levels((size_t)n_levels);
         for (int i = 0; i < n_levels; i++) {
             grlbwt::Level& L = levels[(size_t)i];

@@ -26,7 +26,8 @@ struct RunList {
     }
 };
 
-inline void write_rl_bwt(const std::string& path, const uint64_t* sym, const uint64_t* len, uint64_t n_runs, uint64_t sb, uint64_t fb) {
+template <class SymT>
+inline void write_rl_bwt(const std::string& path, const SymT* sym, const uint64_t* len, uint64_t n_runs, uint64_t sb, uint64_t fb) {
     FILE* f = fopen(path.c_str(), "wb");
     if (!f) throw std::runtime_error("cannot open " + path + " for writing");
     const size_t rec = sb + fb;
@@ -36,7 +37,8 @@ inline void write_rl_bwt(const std::string& path, const uint64_t* sym, const uin
     bool ok = fwrite(hdr, 8, 2, f) == 2;
     for (uint64_t i = 0; i < n_runs && ok; i++) {
         unsigned char tmp[16];
-        memcpy(tmp, &sym[i], sb);       // little endian hosts only
+        const uint64_t s64 = (uint64_t)sym[i];
+        memcpy(tmp, &s64, sb);          // little endian hosts only
         memcpy(tmp + sb, &len[i], fb);
         buf.insert(buf.end(), tmp, tmp + rec);
         if (buf.size() + rec > buf.capacity()) { ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size(); buf.clear(); }

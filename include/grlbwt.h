@@ -34,11 +34,12 @@ int grlbwt_build_file(const char* input_file, const char* output_file, int sym_b
 
 const char* grlbwt_last_error(void);
 
-/* self test of the host induction phase alone (no device): levels given as parallel arrays,
+/* self test of the host induction phase alone (no device): levels given as parallel arrays (u64 symbols; the
+ * multi-threaded path narrows them to 32 bits),
  * level 0 = round 1; fills out->syms / out->lens / out->n_runs */
 int grlbwt_selftest_induce(int n_levels, const uint64_t* alphabet, const uint64_t* tot, const uint64_t* const* rule_l, const uint64_t* const* rule_r,
                            const uint8_t* const* has_hocc, const uint64_t* n_pre, const uint64_t* const* pre_sym, const uint64_t* const* pre_len,
-                           const uint64_t* final_parse, uint64_t n_strings, grlbwt_result_t* out);
+                           const uint64_t* final_parse, uint64_t n_strings, int n_threads /* 0 = sequential 64-bit path */, grlbwt_result_t* out);
 
 #ifdef __cplusplus
 }

@@ -33,10 +33,25 @@ def test_host_induction_matches_oracle_and_reference(golden, all_cases):
         arr = all_cases[name]
         o = O.Oracle(arr)
         R = o.par_phase()
-        syms, lens = G.selftest_induce(oracle_levels(o, R), o.array(R - 1, O.A_PARSE))
-        g = golden[name]
+        levels, fp, g = oracle_levels(o, R), o.array(R - 1, O.A_PARSE), golden[name]
+        wide = any(int(L["rule_l"].max(initial=0)) >= 2**32 or int(L["rule_r"].max(initial=0)) >= 2**32 for L in levels)
+        for threads in ((0,) if wide else (0, 1, 4)):   # 0 = sequential 64-bit path, else ind_phase_mt.hpp
+            syms, lens = G.selftest_induce(levels, fp, threads)
+            raw = O.rl_bwt_bytes(syms, lens, g["sb"], g["fb"])
+            assert hashlib.sha256(raw).hexdigest() == g["rl_bwt_sha256"], (name, threads)
+
+
+@pytest.mark.parametrize("name", ["reads_100k", "rep_50x200k", "u16_2M", "mixed_reads"])
+def test_multithreaded_induction_config_shapes(golden, all_cases, name):
+    """every parallel step (tuple emission, radix distribution, prefix sums, range assembly, boundary merging) on inputs
+    large enough to split across threads"""
+    o = O.Oracle(all_cases[name])
+    R = o.par_phase()
+    levels, fp, g = oracle_levels(o, R), o.array(R - 1, O.A_PARSE), golden[name]
+    for threads in (3, 8):
+        syms, lens = G.selftest_induce(levels, fp, threads)
         raw = O.rl_bwt_bytes(syms, lens, g["sb"], g["fb"])
-        assert hashlib.sha256(raw).hexdigest() == g["rl_bwt_sha256"], name
+        assert hashlib.sha256(raw).hexdigest() == g["rl_bwt_sha256"], (name, threads)
 
 
 def declared_symbols(header):
