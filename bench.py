@@ -80,6 +80,20 @@ def run_reference(args, rank):
     total = args.warmup + args.steps
     rates, kind, desc, cores = cpu_parse_phase(args.sample_reads, threads, repeats=total)
     timed = rates[args.warmup:]
+    # the reference's whole program (parse + induction + output) on the same sample, once, for context
+    bwt_total = None
+    exe = os.path.join(ROOT, "oracle", "_ref", "grlbwt_ref")
+    if os.path.exists(exe):
+        import gen
+        arr = gen.dna_reads(args.sample_reads, READ_LEN, seed=42)
+        with tempfile.TemporaryDirectory(dir="/tmp") as td:
+            inp = os.path.join(td, "sample.txt")
+            arr.tofile(inp)
+            t0 = time.time()
+            r = subprocess.run([exe, inp, "-t", str(threads), "-T", td], cwd=td, capture_output=True, text=True)
+            dt = time.time() - t0
+            if r.returncode == 0:
+                bwt_total = {"value": round(arr.nbytes / 1e6 / dt, 3), "unit": "MB/s", "sample": desc, "what": "reference grlbwt CLI, text file -> .rl_bwt file"}
     sample_mb = args.sample_reads * (READ_LEN + 1) / 1e6
     ms = [sample_mb / r * 1e3 for r in timed]
     val = sample_mb * len(timed) / (sum(ms) / 1e3)
@@ -87,7 +101,8 @@ def run_reference(args, rank):
             "warmup": args.warmup, "ms_per_step": round(sum(ms) / len(ms), 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic", "config": {"workload": f"C2-shaped sample: {desc}", "timing": "host wall clock inside the harness"},
             "cpu_baseline": {"value": round(val, 3), "unit": "MB/s", "cores": cores, "kind": kind, "sample": desc},
-            "e2e": {"value": round(val, 3), "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+            "e2e": {"value": round(val, 3), "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "bwt_total": bwt_total}
     print(json.dumps(line), flush=True)
 
 
@@ -307,6 +322,22 @@ def run_ours(args, rank, world, local_rank):
     kernels = {k: {"launches": v[0], "ms": round(v[1], 3), "model_GBps": round(v[2] / 1e6 / v[1], 1) if v[1] > 0 else None}
                for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]}
 
+    # ---- whole construction (device parse phase + multi-threaded host induction) on a bounded sample, for context ----
+    bwt_total = None
+    if rank == 0 and world == 1 and not args.no_e2e:
+        try:
+            import gen
+            sample = gen.dna_reads(min(args.reads, 2_000_000), READ_LEN, seed=42)
+            thr = os.cpu_count() or 1
+            G.build_bwt(sample[: 151 * 1000], n_threads=thr)  # warm the host library
+            _, lens_, _, _, info = G.build_bwt(sample, device=local_rank, n_threads=thr)
+            tot_ms = info["h2d_ms"] + info["par_phase_ms"] + info["ind_phase_ms"]
+            bwt_total = {"value": round(sample.nbytes / 1e6 / (tot_ms / 1e3), 3), "unit": "MB/s", "sample": f"{sample.size // 151} reads x {READ_LEN} bp ({sample.nbytes / 1e6:.0f} MB)",
+                         "h2d_ms": round(info["h2d_ms"], 1), "parse_phase_ms": round(info["par_phase_ms"], 1), "induction_ms": round(info["ind_phase_ms"], 1),
+                         "host_threads": thr, "bwt_runs": int(lens_.size), "what": "host text -> run-length BCR BWT in host memory (grlbwt_build), file I/O excluded"}
+        except Exception as e:
+            bwt_total = {"value": None, "error": str(e)[:200]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -324,8 +355,8 @@ def run_ours(args, rank, world, local_rank):
                            "parallelism": "1 GPU" if world == 1 else
                            f"{world} ranks: contiguous ranges of whole reads per rank; per round one hash-partitioned all-to-all-v of the local "
                            f"dictionaries + one all-gather-v of the deduplicated global dictionary over NCCL; the dictionary ranking is replicated"},
-                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parse_rounds": parse_rounds,
-                "kernels": kernels}
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "bwt_total": bwt_total,
+                "parse_rounds": parse_rounds, "kernels": kernels}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
