@@ -36,7 +36,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reads", type=int, default=50_000_000, help="reads per GPU (C2: 50M x 150 bp = 7.55 GB)")
+    ap.add_argument("--reads", type=int, default=50_000_000, help="reads of the collection (C2: 50M x 150 bp = 7.55 GB)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"], help="c2: random reads (the metric's config); c3: repetitive genomes (BASELINE.json configs[2])")
+    ap.add_argument("--copies", type=int, default=1000, help="c3: genome copies")
+    ap.add_argument("--genome", type=int, default=4_000_000, help="c3: genome length")
     ap.add_argument("--sample-reads", type=int, default=100_000, help="reads of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -164,6 +167,27 @@ def make_reads_on_device(torch, n_reads, seed, device):
     return out.reshape(-1)
 
 
+def make_genomes_on_device(torch, n_copies, genome_len, seed, device, snp=1e-3, dele=1e-4):
+    """C3 generator on the device: copies of one random genome with substitutions and single-base deletions
+    (same shape as tests/gen.repetitive_genomes; every rank derives the SAME base genome from `seed`)"""
+    gb = torch.Generator(device=device)
+    gb.manual_seed(7)
+    base = torch.randint(0, 4, (genome_len,), generator=gb, device=device, dtype=torch.int64)
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=device)
+    nl = torch.tensor([10], dtype=torch.uint8, device=device)
+    parts = []
+    for _ in range(n_copies):
+        s = base.clone()
+        m = torch.rand(genome_len, generator=g, device=device) < snp
+        s[m] = (s[m] + torch.randint(1, 4, (int(m.sum()),), generator=g, device=device)) % 4
+        keep = torch.rand(genome_len, generator=g, device=device) >= dele
+        parts.append(lut[s[keep]])
+        parts.append(nl)
+    return torch.cat(parts)
+
+
 def run_ours(args, rank, world, local_rank):
     import numpy as np
     import torch
@@ -185,10 +209,21 @@ def run_ours(args, rank, world, local_rank):
     hbm_peak, peak_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json (measured copy)") if "hbm_gbs" in peaks else (6650.0, "fallback 6.65 TB/s")
 
     # strong scaling: the C2 collection (args.reads reads) is split into contiguous ranges of whole reads, one per rank
-    my_reads = args.reads // world + (1 if rank < args.reads % world else 0)
-    text = make_reads_on_device(torch, my_reads, 42 + rank, dev)
-    n = text.numel()
-    n_total = args.reads * (READ_LEN + 1)
+    if args.workload == "c2":
+        my_reads = args.reads // world + (1 if rank < args.reads % world else 0)
+        text = make_reads_on_device(torch, my_reads, 42 + rank, dev)
+        n = text.numel()
+        n_total = args.reads * (READ_LEN + 1)
+        wl_desc = f"C2: {args.reads} reads x {READ_LEN} bp uniform ACGT + newline ({n_total / 1e9:.3f} GB), BASELINE.json configs[1]"
+    else:
+        my_copies = args.copies // world + (1 if rank < args.copies % world else 0)
+        text = make_genomes_on_device(torch, my_copies, args.genome, 1000 + rank, dev)
+        n = text.numel()
+        tot = torch.tensor([n], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(tot)
+        n_total = int(tot.item())
+        wl_desc = f"C3: {args.copies} copies of a {args.genome} bp genome, 0.1% SNPs + 0.01% deletions ({n_total / 1e9:.3f} GB), BASELINE.json configs[2]"
     torch.cuda.synchronize()
     stream = torch.cuda.Stream(device=dev)   # the library issues every kernel on this stream, so torch events bracket it
     torch.cuda.set_stream(stream)
@@ -203,19 +238,21 @@ def run_ours(args, rank, world, local_rank):
 
     def run_phase(fetch, collect=None):
         """all rounds on the text set in ctx; fetch: copy every level's artefacts + the final parse to the host"""
-        d2h = 0
+        d2h, a_off = 0, 0
         if world == 1:
             ctx.stats()
             while True:
                 r = ctx.round()
                 if collect is not None:
                     collect.append(r.as_dict())
-                if fetch:
-                    ctx.fetch_level(arena[0])
+                if fetch:  # every level lands in its own slice of the pinned arena while the next round computes
+                    ctx.fetch_level(arena[0], async_=True, offset=a_off)
+                    a_off = ctx.arena_end
                     d2h += r.tot_phrases * (2 * r.sym_bytes + 1) + r.n_pre_runs * (r.sym_bytes + 8)
                 if r.done:
                     if fetch:
-                        d2h += ctx.fetch_parse(arena[0]).nbytes
+                        ctx.fetch_wait()
+                        d2h += ctx.fetch_parse(arena[0][a_off:]).nbytes
                     return d2h
         st = M.global_stats(engine)
         while True:
@@ -272,7 +309,7 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
         host_np = host_text.numpy()
         # pinned landing zone for the level artefacts (largest level of the workload, measured in the resident steps)
-        need = max(r["tot_phrases"] * 17 + r["n_pre_runs"] * 16 + 256 for r in rounds_info) + args.reads * 8 + (1 << 20)
+        need = sum(r["tot_phrases"] * 17 + r["n_pre_runs"] * 16 + 256 for r in rounds_info) + rounds_info[-1]["parse_len"] * 8 * world + (1 << 20)
         arena[0] = torch.empty(int(need), dtype=torch.uint8, pin_memory=True).numpy()
         d2h_bytes = [0]
 
@@ -324,7 +361,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- whole construction (device parse phase + multi-threaded host induction) on a bounded sample, for context ----
     bwt_total = None
-    if rank == 0 and world == 1 and not args.no_e2e:
+    if rank == 0 and world == 1 and not args.no_e2e and args.workload == "c2":
         try:
             import gen
             sample = gen.dna_reads(min(args.reads, 2_000_000), READ_LEN, seed=42)
@@ -350,8 +387,8 @@ def run_ours(args, rank, world, local_rank):
         line = {"metric": METRIC, "value": round(value, 3), "unit": "MB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
                 "data": "synthetic",
-                "config": {"workload": f"C2: {args.reads} reads x {READ_LEN} bp uniform ACGT + newline ({n_total / 1e9:.3f} GB), BASELINE.json configs[1]",
-                           "reads": args.reads, "cache": "the text of every round-1 pass (7.55 GB at the default size) exceeds the 126 MB L2",
+                "config": {"workload": wl_desc,
+                           "reads": args.reads if args.workload == "c2" else None, "cache": "the text of every round-1 pass (7.55 GB at the default size) exceeds the 126 MB L2",
                            "parallelism": "1 GPU" if world == 1 else
                            f"{world} ranks: contiguous ranges of whole reads per rank; per round one hash-partitioned all-to-all-v of the local "
                            f"dictionaries + one all-gather-v of the deduplicated global dictionary over NCCL; the dictionary ranking is replicated"},

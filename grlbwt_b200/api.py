@@ -59,6 +59,8 @@ def lib_gpu():
         L.grlgpu_stats.argtypes = [vp, C.POINTER(Stats)]
         L.grlgpu_round.argtypes = [vp, C.POINTER(Round)]
         L.grlgpu_fetch_level.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.grlgpu_fetch_level_async.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.grlgpu_fetch_wait.argtypes = [vp]
         L.grlgpu_fetch_parse.argtypes = [vp, vp]
         L.grlgpu_fetch_str_ptrs.argtypes = [vp, vp]
         L.grlgpu_fetch_dictionary.argtypes = [vp, vp, vp, vp, vp]
@@ -150,7 +152,10 @@ class GrlGpu:
         self._round_started = True
         return r
 
-    def fetch_level(self, arena: np.ndarray | None = None, widen: bool = True):
+    def fetch_wait(self):
+        self._check(self._L.grlgpu_fetch_wait(self._h))
+
+    def fetch_level(self, arena: np.ndarray | None = None, widen: bool = True, async_: bool = False, offset: int = 0):
         """-> dict(rule_l, rule_r, has_hocc, pre_sym, pre_len) as numpy arrays.
         arena: optional uint8 buffer (e.g. pinned host memory) the arrays are carved from, so the copies are
         direct DMA; widen=False keeps rule/pre_sym in the device's element width (sym_bytes) instead of u64."""
@@ -160,7 +165,7 @@ class GrlGpu:
         if arena is None:
             arrs = [np.zeros(n, dt) for n, dt in sizes]
         else:
-            arrs, off = [], 0
+            arrs, off = [], int(offset)
             for n, dt in sizes:
                 nb = n * np.dtype(dt).itemsize
                 off = (off + 15) & ~15
@@ -169,7 +174,10 @@ class GrlGpu:
                 arrs.append(arena[off:off + nb].view(dt))
                 off += nb
         rl, rr, hh, ps, pl = arrs
-        self._check(self._L.grlgpu_fetch_level(self._h, _ptr(rl), _ptr(rr), _ptr(hh), _ptr(ps), _ptr(pl)))
+        fn = self._L.grlgpu_fetch_level_async if async_ else self._L.grlgpu_fetch_level
+        self._check(fn(self._h, _ptr(rl), _ptr(rr), _ptr(hh), _ptr(ps), _ptr(pl)))
+        if arena is not None:
+            self.arena_end = (off + 15) & ~15
         if widen and arena is None:
             rl, rr, ps = rl.astype(np.uint64), rr.astype(np.uint64), ps.astype(np.uint64)
         return {"rule_l": rl, "rule_r": rr, "has_hocc": hh, "pre_sym": ps, "pre_len": pl}

@@ -202,8 +202,8 @@ struct OpMax { template <class T> __device__ __forceinline__ T operator()(T a, T
 // G1: per-group aggregates over the sorted entries (produce_pre_bwt exact_par_phase.cpp:159-187).
 // gcnt = entries | full<<31 ; gmin/gmax over (left symbol + 1) of the non-full entries (0 = none).
 static __global__ void __launch_bounds__(256) group_reduce_kernel(const u32* __restrict__ order, const u32* __restrict__ head_bits, const u32* __restrict__ head_pref,
-                                                                  u32* __restrict__ rank, const ulonglong2* __restrict__ einfo, u64 nE, u32* gcnt, u64* gacc,
-                                                                  u64* gmin, u64* gmax, u32* __restrict__ grep) {
+                                                                  const ulonglong2* __restrict__ einfo, u64 nE, u32* gcnt, u64* gacc, u64* gmin, u64* gmax,
+                                                                  u32* __restrict__ grep, u32* __restrict__ ghead) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     u32 g = 0xffffffffu, cnt = 0;
     u64 acc = 0, mn = ~0ULL, mx = 0;
@@ -213,7 +213,6 @@ static __global__ void __launch_bounds__(256) group_reduce_kernel(const u32* __r
         const u32 hw = head_bits[i >> 5];
         const u32 upto = hw & (0xffffffffu >> (31 - (i & 31)));  // heads at positions <= i inside the word
         g = head_pref[i >> 5] + __popc(upto) - 1;                // dense group index in sorted order
-        rank[e] = g + 1;                                         // position-based ranks become dense group ids
         hd = (hw >> (i & 31)) & 1u;
         nh = i + 1 == nE || ((head_bits[(i + 1) >> 5] >> ((i + 1) & 31)) & 1u);
         const ulonglong2 ei = einfo[e];
@@ -222,7 +221,7 @@ static __global__ void __launch_bounds__(256) group_reduce_kernel(const u32* __r
             acc = ei.y & EI_FREQ;
             if (ei.x) mn = mx = ei.x;
         }
-        if (hd) grep[g] = e;
+        if (hd) { grep[g] = e; ghead[g] = (u32)i; }  // entries keep their position-based rank = head position + 1
     }
     const u32 m = __match_any_sync(0xffffffffu, g);
     const u32 first = __ffs(m) - 1, last = 31 - __clz(m);
@@ -288,21 +287,22 @@ __global__ void __launch_bounds__(256) prebwt_runs_kernel(const u64* __restrict_
 
 // G4: per entry: metasymbol of full phrases (exact_par_phase.cpp:174-176, :437-444), is_suffix of the
 // next round (:443), rank marks of entries in hocc groups (phr_marks + new_phrases_ht, :190-207)
-// ginfo[g] = rank << 2 | hocc << 1 | ranked : one gather per entry in entry_finalize
-static __global__ void __launch_bounds__(256) pack_ginfo_kernel(const u32* __restrict__ gcnt, const u32* __restrict__ rflag, const u32* __restrict__ rrank, u64 G,
-                                                                u32* __restrict__ ginfo) {
+// ginfo_pos[head position of the group] = rank << 2 | hocc << 1 | ranked : entries reach it through their
+// position-based rank, so the sorted pass never has to scatter a dense group id back to the entries
+static __global__ void __launch_bounds__(256) pack_ginfo_kernel(const u32* __restrict__ gcnt, const u32* __restrict__ rflag, const u32* __restrict__ rrank,
+                                                                const u32* __restrict__ ghead, u64 G, u32* __restrict__ ginfo_pos) {
     const u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < G) ginfo[g] = (rrank[g] << 2) | (((gcnt[g] & 0x7fffffffu) > 1) ? 2u : 0u) | (rflag[g] ? 1u : 0u);
+    if (g < G) ginfo_pos[ghead[g]] = (rrank[g] << 2) | (((gcnt[g] & 0x7fffffffu) > 1) ? 2u : 0u) | (rflag[g] ? 1u : 0u);
 }
 template <class SymT>
 __global__ void __launch_bounds__(256) entry_finalize_kernel(const u32* __restrict__ rank, const SymT* __restrict__ D, const u32* __restrict__ rem,
                                                              const u32* __restrict__ phr_of, const u32* __restrict__ ph_off, const u64* __restrict__ ph_freq,
-                                                             const u32* __restrict__ occ_slots, u64 nE, IsSuffix is_suffix, const u32* __restrict__ ginfo,
+                                                             const u32* __restrict__ occ_slots, u64 nE, IsSuffix is_suffix, const u32* __restrict__ ginfo_pos,
                                                              ulonglong2* table, u64* __restrict__ ph_meta, u8* __restrict__ is_suffix_next,
                                                              u32* __restrict__ erank) {
     const u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nE) return;
-    const u32 gi = ginfo[rank[e] - 1];
+    const u32 gi = ginfo_pos[rank[e] - 1];  // rank[e] - 1 = position of the head of e's group in the sorted order
     if (!(gi & 1u)) return;  // invalid and unranked groups carry no rank
     const u32 r = gi >> 2;
     const u32 ph = phr_of[e];

@@ -48,6 +48,13 @@ struct grlgpu_ctx {
     DevBuf<u8> rule_l, rule_r, has_hocc, pre_sym;
     DevBuf<u64> pre_len;
 
+    // asynchronous level fetches: a second stream copies while the next round computes; the level's device buffers
+    // are parked here (not returned to the pool) until grlgpu_fetch_wait
+    cudaStream_t copy_st = nullptr;
+    cudaEvent_t copy_ev = nullptr;
+    std::vector<DevBuf<u8>> parked_u8;
+    std::vector<DevBuf<u64>> parked_u64;
+
     // multi-GPU round in flight (between grlgpu_mg_local and grlgpu_mg_global)
     MgRound* mg = nullptr;
     int mg_ranks = 0;
@@ -409,10 +416,10 @@ void stage_dict(Round& R) {
     R.G = G;
 
     // -- group aggregates --
-    DevBuf<u32> gcnt(G, st), grep(G, st), rflag(G, st), vflag(G, st), rrank(G, st), vidx(G, st);
+    DevBuf<u32> gcnt(G, st), grep(G, st), ghead(G, st), rflag(G, st), vflag(G, st), rrank(G, st), vidx(G, st);
     DevBuf<u64> gacc(G, st), gmin(G, st), gmax(G, st), psym(G, st);
     gcnt.zero(); gacc.zero(); gmax.zero(); gmin.fill_ff();
-    GRL_LAUNCH("group_reduce", nE * 28 + G * 28, group_reduce_kernel, grid_for(nE, 256), 256, 0, st, order, head_bits.p, head_pref.p, R.rank.p, R.einfo.p, nE, gcnt.p, gacc.p, gmin.p, gmax.p, grep.p);
+    GRL_LAUNCH("group_reduce", nE * 24 + G * 32, group_reduce_kernel, grid_for(nE, 256), 256, 0, st, order, head_bits.p, head_pref.p, R.einfo.p, nE, gcnt.p, gacc.p, gmin.p, gmax.p, grep.p, ghead.p);
     R.einfo.release();
     const u64 bwt_dummy = A + 1, hocc_dummy = A + 2;  // exact_par_phase.hpp:113-115
     GRL_LAUNCH("group_finalize", 0, group_finalize_kernel, grid_for(G, 256), 256, 0, st, gcnt.p, gmin.p, gmax.p, G, bwt_dummy, hocc_dummy, rflag.p, vflag.p, psym.p);
@@ -446,8 +453,8 @@ void stage_dict(Round& R) {
     is_suffix_next.zero();
     DevBuf<u32> erank(nE, st);
     erank.fill_ff();
-    DevBuf<u32> ginfo(G, st);
-    GRL_LAUNCH("pack_ginfo", G * 16, pack_ginfo_kernel, grid_for(G, 256), 256, 0, st, gcnt.p, rflag.p, rrank.p, G, ginfo.p);
+    DevBuf<u32> ginfo(nE, st);  // indexed by head position
+    GRL_LAUNCH("pack_ginfo", G * 20, pack_ginfo_kernel, grid_for(G, 256), 256, 0, st, gcnt.p, rflag.p, rrank.p, ghead.p, G, ginfo.p);
     GRL_LAUNCH("entry_finalize", nE * 24, (entry_finalize_kernel<SymT>), grid_for(nE, 256), 256, 0, st, R.rank.p, D, R.rem.p, R.phr_of.p, R.ph_off.p, R.ph_freq.p, R.occ_slots.p, nE, isuf, ginfo.p, R.table.p, R.ph_meta, is_suffix_next.p, erank.p);
     c->rule_l.alloc(tot * sizeof(SymT), st);
     c->rule_r.alloc(tot * sizeof(SymT), st);
@@ -846,6 +853,7 @@ int grlgpu_destroy(grlgpu_ctx* ctx) {
     ctx->prof.resolve();
     delete ctx->mg;
     ctx->mg = nullptr;
+    if (ctx->copy_st) { cudaStreamSynchronize(ctx->copy_st); cudaStreamDestroy(ctx->copy_st); cudaEventDestroy(ctx->copy_ev); }
     delete ctx;  // the stream was synchronised above: the pool's slabs are idle
     if (own) cudaStreamDestroy(st);
     return GRLGPU_OK;
@@ -898,7 +906,7 @@ int grlgpu_round(grlgpu_ctx* ctx, grlgpu_round_t* out) {
 
 int grlgpu_fetch_level(grlgpu_ctx* ctx, void* rule_l, void* rule_r, uint8_t* has_hocc, void* pre_sym, uint64_t* pre_len) {
     if (!ctx) return GRLGPU_ERR_ARG;
-    if (ctx->round == 0) return GRLGPU_ERR_STATE;
+    if (ctx->round == 0 || !ctx->rule_l.p) return GRLGPU_ERR_STATE;
     return guarded(ctx, [&] {
         const u64 sb = (u64)ctx->lvl_sym_bytes;
         if (rule_l) GRL_CUDA(cudaMemcpyAsync(rule_l, ctx->rule_l.p, ctx->lvl_tot * sb, cudaMemcpyDeviceToHost, ctx->st));
@@ -907,6 +915,40 @@ int grlgpu_fetch_level(grlgpu_ctx* ctx, void* rule_l, void* rule_r, uint8_t* has
         if (pre_sym) GRL_CUDA(cudaMemcpyAsync(pre_sym, ctx->pre_sym.p, ctx->lvl_npre * sb, cudaMemcpyDeviceToHost, ctx->st));
         if (pre_len) GRL_CUDA(cudaMemcpyAsync(pre_len, ctx->pre_len.p, ctx->lvl_npre * 8, cudaMemcpyDeviceToHost, ctx->st));
         GRL_CUDA(cudaStreamSynchronize(ctx->st));
+    });
+}
+
+int grlgpu_fetch_level_async(grlgpu_ctx* ctx, void* rule_l, void* rule_r, uint8_t* has_hocc, void* pre_sym, uint64_t* pre_len) {
+    if (!ctx) return GRLGPU_ERR_ARG;
+    if (ctx->round == 0 || !ctx->rule_l.p) return GRLGPU_ERR_STATE;
+    return guarded(ctx, [&] {
+        if (!ctx->copy_st) {
+            GRL_CUDA(cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking));
+            GRL_CUDA(cudaEventCreateWithFlags(&ctx->copy_ev, cudaEventDisableTiming));
+        }
+        // the round that produced the level has been synchronised already; order the copy stream after it anyway
+        GRL_CUDA(cudaEventRecord(ctx->copy_ev, ctx->st));
+        GRL_CUDA(cudaStreamWaitEvent(ctx->copy_st, ctx->copy_ev, 0));
+        const u64 sb = (u64)ctx->lvl_sym_bytes;
+        if (rule_l) GRL_CUDA(cudaMemcpyAsync(rule_l, ctx->rule_l.p, ctx->lvl_tot * sb, cudaMemcpyDeviceToHost, ctx->copy_st));
+        if (rule_r) GRL_CUDA(cudaMemcpyAsync(rule_r, ctx->rule_r.p, ctx->lvl_tot * sb, cudaMemcpyDeviceToHost, ctx->copy_st));
+        if (has_hocc) GRL_CUDA(cudaMemcpyAsync(has_hocc, ctx->has_hocc.p, ctx->lvl_tot, cudaMemcpyDeviceToHost, ctx->copy_st));
+        if (pre_sym) GRL_CUDA(cudaMemcpyAsync(pre_sym, ctx->pre_sym.p, ctx->lvl_npre * sb, cudaMemcpyDeviceToHost, ctx->copy_st));
+        if (pre_len) GRL_CUDA(cudaMemcpyAsync(pre_len, ctx->pre_len.p, ctx->lvl_npre * 8, cudaMemcpyDeviceToHost, ctx->copy_st));
+        ctx->parked_u8.push_back(std::move(ctx->rule_l));
+        ctx->parked_u8.push_back(std::move(ctx->rule_r));
+        ctx->parked_u8.push_back(std::move(ctx->has_hocc));
+        ctx->parked_u8.push_back(std::move(ctx->pre_sym));
+        ctx->parked_u64.push_back(std::move(ctx->pre_len));
+    });
+}
+
+int grlgpu_fetch_wait(grlgpu_ctx* ctx) {
+    if (!ctx) return GRLGPU_ERR_ARG;
+    return guarded(ctx, [&] {
+        if (ctx->copy_st) GRL_CUDA(cudaStreamSynchronize(ctx->copy_st));
+        ctx->parked_u8.clear();
+        ctx->parked_u64.clear();
     });
 }
 

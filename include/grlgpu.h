@@ -101,6 +101,13 @@ int grlgpu_round(grlgpu_ctx* ctx, grlgpu_round_t* out);
  * any pointer may be NULL to skip that array. */
 int grlgpu_fetch_level(grlgpu_ctx* ctx, void* rule_l, void* rule_r, uint8_t* has_hocc, void* pre_sym, uint64_t* pre_len);
 
+/* same copies, issued on a second stream: the call returns at once and the NEXT round may run while they are in
+ * flight (give pinned host buffers, or the driver stages and the overlap is lost). The level's device buffers
+ * stay parked until grlgpu_fetch_wait, which must be called before the host buffers are read. After this call the
+ * level can no longer be fetched again. */
+int grlgpu_fetch_level_async(grlgpu_ctx* ctx, void* rule_l, void* rule_r, uint8_t* has_hocc, void* pre_sym, uint64_t* pre_len);
+int grlgpu_fetch_wait(grlgpu_ctx* ctx);
+
 /* current parse (output of the last round): parse_len cells of cell_bytes_out bytes, cells = rank<<1|rep.
  * replaces: file tmp_input (exact_par_phase.cpp:307-308); after the last round this is the final parse
  * consumed by parse2bwt (exact_ind_phase.cpp:603-672) */

@@ -170,6 +170,36 @@ def test_full_bwt_all_cases(golden, all_cases):
         assert info["n_rounds"] == len(g["rounds"]), name
 
 
+def test_async_level_fetch_matches_sync(golden, all_cases):
+    """levels fetched on the copy stream while later rounds run equal the synchronously fetched ones"""
+    for name in ("mutated_200x5k", "u16_rand", "reads_2000x150"):
+        arr = all_cases[name]
+        sync_levels = []
+        with G.GrlGpu(0) as ctx:
+            ctx.set_text(arr)
+            while True:
+                r = ctx.round()
+                sync_levels.append(ctx.fetch_level())
+                if r.done:
+                    break
+        arena = np.zeros(sum(L["rule_l"].size * 17 + L["pre_sym"].size * 16 + 256 for L in sync_levels), np.uint8)
+        got, off = [], 0
+        with G.GrlGpu(0) as ctx:
+            ctx.set_text(arr)
+            while True:
+                r = ctx.round()
+                got.append(ctx.fetch_level(arena, async_=True, offset=off))
+                off = ctx.arena_end
+                with pytest.raises(G.GrlGpuError):
+                    ctx.fetch_level()            # the level was handed to the copy stream
+                if r.done:
+                    break
+            ctx.fetch_wait()
+        for a, b in zip(sync_levels, got):
+            for k in ("rule_l", "rule_r", "has_hocc", "pre_sym", "pre_len"):
+                assert np.array_equal(a[k], b[k].astype(a[k].dtype)), (name, k)
+
+
 def test_ill_formed_rejected():
     for bad in (b"ACGT\nAC", b"AC\x01GT\nAC\n"):
         with G.GrlGpu(0) as ctx:
@@ -198,3 +228,22 @@ def test_cli_end_to_end(tmp_path, golden, all_cases):
     bad.write_bytes(b"ACGT\nAC")
     r = subprocess.run([exe, str(bad)], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode == 1 and "ill formed" in r.stdout
+
+
+# ------------------------------------------------------------------ sizes the oracle does not reach: BWT invariants
+@pytest.mark.parametrize("name,a,threads", [("reads_2M", 1, 16), ("rep_100x1M", 1, 4), ("u16_20M", 2, 8), ("mixed_200k", 1, 8)])
+def test_cli_at_scale_satisfies_bwt_invariants(tmp_path, name, a, threads):
+    """CLI end to end on config-shaped inputs of 40-300 MB, then bwt_check: header, sum of lengths, maximal runs,
+    per-symbol totals, the separator block, and LF-inversion of 1000 strings against the text"""
+    import gen
+    arr = {"reads_2M": lambda: gen.dna_reads(2000000, 150, seed=42), "rep_100x1M": lambda: gen.repetitive_genomes(100, 1000000, seed=7),
+           "u16_20M": lambda: gen.int_alphabet(20000000, np.uint16, 65535, 1000, seed=11),
+           "mixed_200k": lambda: gen.mixed_reads(200000, 300, 150, 10000, seed=5)}[name]()
+    inp = tmp_path / (name + ".txt")
+    arr.tofile(inp)
+    exe = os.path.join(G.LIB_DIR, "grlbwt")
+    r = subprocess.run([exe, str(inp), "-a", str(a), "-t", str(threads), "-T", str(tmp_path)], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-600:]
+    r = subprocess.run([os.path.join(G.LIB_DIR, "bwt_check"), str(inp), str(tmp_path / (name + ".rl_bwt")), "-a", str(a), "-k", "1000"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout

@@ -56,7 +56,29 @@ def test_tools_round_trip(all_cases, tmp_path, name):
         assert np.array_equal(np.fromfile(str(pre) + ".len", np.uint32).astype(np.uint64), lens)
 
 
+def test_bwt_check_accepts_reference_bwts_and_rejects_corrupted(all_cases, tmp_path):
+    for name in ("dna_500", "with_empty", "u16_small_sigma", "test_byte_alphabet"):
+        arr = all_cases[name]
+        o = O.Oracle(arr)
+        o.par_phase()
+        syms, lens, sb, fb = o.ind_phase()
+        txt, rl = tmp_path / "t.bin", tmp_path / "t.rl_bwt"
+        arr.tofile(txt)
+        rl.write_bytes(O.rl_bwt_bytes(syms, lens, sb, fb))
+        w = str(arr.dtype.itemsize)
+        r = subprocess.run([tool("bwt_check"), str(txt), str(rl), "-a", w, "-k", "50"], capture_output=True, text=True)
+        assert r.returncode == 0 and r.stdout.startswith("OK"), (name, r.stdout)
+        if len(syms) > 8:
+            bad_s, bad_l = syms.copy(), lens.copy()
+            i = len(syms) // 2
+            bad_s[[i, i + 1]] = bad_s[[i + 1, i]]          # two runs swapped: totals and maximality still hold
+            bad_l[[i, i + 1]] = bad_l[[i + 1, i]]
+            rl.write_bytes(O.rl_bwt_bytes(bad_s, bad_l, sb, fb))
+            r = subprocess.run([tool("bwt_check"), str(txt), str(rl), "-a", w, "-k", "100000"], capture_output=True, text=True)
+            assert r.returncode == 1 and "FAILED" in r.stdout, (name, r.stdout)
+
+
 def test_tools_usage_messages():
-    for t in ("grl2plain", "grlbwt2rle", "reverse_bwt", "bwt_stats"):
+    for t in ("grl2plain", "grlbwt2rle", "reverse_bwt", "bwt_stats", "bwt_check"):
         r = subprocess.run([tool(t)], capture_output=True, text=True)
         assert r.returncode == 0 and "usage:" in r.stdout
