@@ -112,11 +112,25 @@ static __global__ void next_start_bits_kernel(const u32* __restrict__ end_bits, 
     start_bits[w] = s;
 }
 template <class CellT>
-__global__ void first_round_end_bits_kernel(const CellT* __restrict__ text, u64 n, CellT sep, u32* __restrict__ end_bits) {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool e = i < n && text[i] == sep;
-    const u32 b = __ballot_sync(0xffffffffu, e);
-    if (lane_id() == 0 && (i >> 5) < ((n + 31) >> 5)) end_bits[i >> 5] = b;
+__global__ void __launch_bounds__(256) first_round_end_bits_kernel(const CellT* __restrict__ text, u64 n, CellT sep, u32* __restrict__ end_bits) {
+    // thread = 32 cells = one bitmap word, 16-byte vector loads
+    const u64 word = (u64)blockIdx.x * blockDim.x + threadIdx.x, base = word * 32;
+    if (base >= n) return;
+    const u64 cnt = n - base;
+    u32 bits = 0;
+    if (cnt >= 32) {
+        __align__(16) CellT c[32];
+        constexpr int NV = 32 * sizeof(CellT) / 16;
+        const uint4* src = reinterpret_cast<const uint4*>(text + base);
+        uint4* dst = reinterpret_cast<uint4*>(c);
+#pragma unroll
+        for (int k = 0; k < NV; k++) dst[k] = src[k];
+#pragma unroll
+        for (int k = 0; k < 32; k++) bits |= (u32)(c[k] == sep) << k;
+    } else {
+        for (u64 k = 0; k < cnt; k++) bits |= (u32)(text[base + k] == sep) << k;
+    }
+    end_bits[word] = bits;
 }
 static __global__ void adjacent_max_diff_kernel(const u64* __restrict__ ptrs, u64 n_str, u64* out) {
     u64 m = 0;
@@ -231,33 +245,40 @@ void stage_dedup(Round& R) {
     R.slot_of_phrase.alloc(R.p, R.st);
     DevBuf<u32> overflow(1, R.st);
     DevBuf<u64> stats(2, R.st);
-    // capacity (any multiple of 256; slot = mulhi(hash, cap)): 1.6 p slots, so that load <= 0.625 and the pass
-    // cannot overflow, while that stays below 2^31 slots (slot ids are 31 bits); beyond that (p > 1.3e9, e.g.
-    // round 1 of a multi-GB text whose dictionary is tiny) start at 2^28 slots and regrow on demand
+    // capacity (any multiple of 256; slot = mulhi(hash, cap)). "full" = 1.6 p slots: load <= 0.625, the pass cannot
+    // overflow (beyond 2^31 slots, i.e. p > 1.3e9: start at 2^28 and regrow on demand). A text long enough to have a
+    // pilot starts SMALL instead (1.6 x the pilot's phrases): if the pilot says duplicate-heavy the dictionary is tiny
+    // next to p and the small table is kept (no 30 GB init + occupancy scan for a 16 k-phrase dictionary); if it says
+    // unique-heavy the pass restarts on the full table with the thread-per-phrase kernel.
     const u64 cap_max = (1ull << 31) - 256;
-    u64 want = std::max<u64>(1024, (R.p + R.p / 2 + R.p / 10 + 255) / 256 * 256);
-    u64 cap = want <= cap_max ? want : (1ull << 28);
+    const u64 want = std::max<u64>(1024, (R.p + R.p / 2 + R.p / 10 + 255) / 256 * 256);
+    const u64 cap_full = want <= cap_max ? want : (1ull << 28);
+    const bool has_rest = t_pilot < n_tiles;
+    u64 cap = cap_full;
+    if (t_pilot && has_rest) cap = std::min<u64>(cap_full, std::max<u64>(1ull << 20, (j_pilot + j_pilot / 2 + j_pilot / 10 + 255) / 256 * 256));
     if (c->flags & GRLGPU_FLAG_SMALL_TABLE) cap = 1024;
+    int decided = has_rest ? (t_pilot ? -1 : 0) : 1;  // -1: ask the pilot, 1: cached kernel for the rest, 0: thread-per-phrase
     for (;;) {
         if (cap > cap_max) throw Error(GRLGPU_ERR_LIMIT, "phrase table would exceed 2^31 slots");
         R.table.alloc(cap, R.st);
         GRL_LAUNCH("table_init", cap * 16, table_init_kernel, grid_for(cap, 256), 256, 0, R.st, R.table.p, cap);
         overflow.zero();
         stats.zero();
-        bool cached_rest = true;
-        if (t_pilot) {
+        const bool run_pilot = t_pilot && decided != 0;
+        if (run_pilot) {
             const u64 cells = std::min<u64>(R.n, t_pilot * TW * 32);
             GRL_LAUNCH("dedup_cached", cells * sizeof(CellT) + cells / 4 + j_pilot * 4, (dedup_cached_kernel<CellT>), fd_grid, FD_THREADS, fd_smem_bytes<CellT>(), R.st,
                        text, R.n, R.start_bits.p, R.end_bits, tile_base.p, (u64)0, t_pilot, R.table.p, cap, R.slot_of_phrase.p, overflow.p, stats.p);
         }
-        if (t_pilot < n_tiles) {
-            if (t_pilot) {
+        if (has_rest) {
+            if (decided == -1) {
                 u64 hs[2];
                 GRL_CUDA(cudaMemcpyAsync(hs, stats.p, 16, cudaMemcpyDeviceToHost, R.st));
                 GRL_CUDA(cudaStreamSynchronize(R.st));
-                cached_rest = hs[0] * 2 <= hs[1];  // at most half of the pilot's phrases had to go to the global table
-            } else cached_rest = false;
-            if (cached_rest) {
+                decided = hs[0] * 2 <= hs[1] ? 1 : 0;  // cached: at most half of the pilot's phrases had to go to the global table
+                if (decided == 0 && cap < cap_full && !(c->flags & GRLGPU_FLAG_SMALL_TABLE)) { cap = cap_full; continue; }
+            }
+            if (decided == 1) {
                 const u64 cells = R.n - t_pilot * TW * 32;
                 GRL_LAUNCH("dedup_cached", cells * sizeof(CellT) + cells / 4 + (R.p - j_pilot) * 4, (dedup_cached_kernel<CellT>), fd_grid, FD_THREADS, fd_smem_bytes<CellT>(),
                            R.st, text, R.n, R.start_bits.p, R.end_bits, tile_base.p, t_pilot, n_tiles, R.table.p, cap, R.slot_of_phrase.p, overflow.p, (u64*)nullptr);
@@ -267,8 +288,9 @@ void stage_dedup(Round& R) {
                     if (pc != R.p) throw Error(GRLGPU_ERR_STATE, "phrase count mismatch between tile counts and compaction");
                     counted = true;
                 }
-                if (R.n < (1ull << 31)) insert_uncached<CellT, u32>(R, bc, ps_raw, j_pilot, cap, overflow.p);
-                else insert_uncached<CellT, u64>(R, bc, ps_raw, j_pilot, cap, overflow.p);
+                const u64 j0 = run_pilot ? j_pilot : 0;
+                if (R.n < (1ull << 31)) insert_uncached<CellT, u32>(R, bc, ps_raw, j0, cap, overflow.p);
+                else insert_uncached<CellT, u64>(R, bc, ps_raw, j0, cap, overflow.p);
             }
         }
         bool ovf = d2h_scalar(overflow.p, R.st) != 0;
@@ -287,7 +309,7 @@ void stage_dedup(Round& R) {
             }
         }
         if (cap >= cap_max) throw Error(GRLGPU_ERR_LIMIT, "phrase table would exceed 2^31 slots");
-        cap = std::min<u64>(cap * 4, std::min<u64>(want, cap_max));  // too full: regrow and redo the pass
+        cap = std::min<u64>(cap * 8, std::min<u64>(want, cap_max));  // too full: regrow and redo the pass
     }
     ps_raw.release();
     R.ph_pos.alloc(R.d, R.st);
@@ -781,7 +803,7 @@ void compute_stats(grlgpu_ctx* c) {
     {
         const u64 n_words = div_up(c->n, 32);
         DevBuf<u32> eb(n_words, c->st), sb(n_words, c->st);
-        GRL_LAUNCH("first_round_end_bits", 0, (first_round_end_bits_kernel<CellT>), grid_for(c->n, 256), 256, 0, c->st, text, c->n, sep_c, eb.p);
+        GRL_LAUNCH("first_round_end_bits", c->n * sizeof(CellT), (first_round_end_bits_kernel<CellT>), grid_for(n_words, 256), 256, 0, c->st, text, c->n, sep_c, eb.p);
         GRL_LAUNCH("next_start_bits", 0, next_start_bits_kernel, grid_for(n_words, 256), 256, 0, c->st, eb.p, c->n, sb.p);
         BitmapCompactor bc;
         const u64 ns = bc.count(sb.p, c->n, c->st);

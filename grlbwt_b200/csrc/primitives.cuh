@@ -189,19 +189,20 @@ struct BitmapCompactor {
 // through shared memory (writes of one digit from one tile are contiguous).
 // ------------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 256;
-constexpr int RS_ITEMS = 16;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_WARP_ITEMS = RS_TILE / RS_WARPS;  // 512
-constexpr size_t RS_SMEM = (size_t)RS_TILE * (sizeof(u64) + sizeof(u32)) + (size_t)RS_WARPS * 257 * sizeof(u32) + 2 * 256 * sizeof(u32) + 34 * sizeof(u32);
+template <int ITEMS>
+constexpr size_t rs_smem_bytes() {
+    return (size_t)RS_THREADS * ITEMS * (sizeof(u64) + sizeof(u32)) + (size_t)RS_WARPS * 257 * sizeof(u32) + 2 * 256 * sizeof(u32) + 34 * sizeof(u32);
+}
 
-static __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const u64* __restrict__ keys, u64 n, int shift, u32* __restrict__ hist, u64 tiles) {
+template <int ITEMS>
+__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const u64* __restrict__ keys, u64 n, int shift, u32* __restrict__ hist, u64 tiles) {
     __shared__ u32 cnt[256];
     cnt[threadIdx.x] = 0;
     __syncthreads();
-    const u64 base = (u64)blockIdx.x * RS_TILE;
+    const u64 base = (u64)blockIdx.x * (RS_THREADS * ITEMS);
 #pragma unroll 4
-    for (int i = 0; i < RS_ITEMS; i++) {
+    for (int i = 0; i < ITEMS; i++) {
         const u64 idx = base + (u64)i * RS_THREADS + threadIdx.x;
         if (idx < n) atomicAdd(&cnt[(u32)(keys[idx] >> shift) & 255u], 1u);
     }
@@ -209,29 +210,30 @@ static __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const u64
     hist[(u64)threadIdx.x * tiles + blockIdx.x] = cnt[threadIdx.x];
 }
 
-static __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in,
-                                                                          u64* __restrict__ keys_out, u32* __restrict__ vals_out, u64 n, int shift,
-                                                                          const u64* __restrict__ goff, u64 tiles) {
+template <int ITEMS>
+__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in, u64* __restrict__ keys_out,
+                                                                   u32* __restrict__ vals_out, u64 n, int shift, const u64* __restrict__ goff, u64 tiles) {
+    constexpr int TILE = RS_THREADS * ITEMS, WARP_ITEMS = TILE / RS_WARPS;
     extern __shared__ __align__(16) unsigned char rs_smem[];
     u64* s_keys = (u64*)rs_smem;
-    u32* s_vals = (u32*)(s_keys + RS_TILE);
-    u32* s_cnt = s_vals + RS_TILE;            // [RS_WARPS][257]
+    u32* s_vals = (u32*)(s_keys + TILE);
+    u32* s_cnt = s_vals + TILE;               // [RS_WARPS][257]
     u32* s_dstart = s_cnt + RS_WARPS * 257;   // [256] tile-local start of each digit
-    u32* s_scan = s_dstart + 256;             // 33 scratch  (then s_goff_lo.. below)
+    u32* s_scan = s_dstart + 256;             // 33 scratch
     __shared__ u64 s_goff[256];
 
     const u32 lane = lane_id(), warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < RS_WARPS * 257; i += RS_THREADS) s_cnt[i] = 0;
     __syncthreads();
 
-    const u64 tile_base = (u64)blockIdx.x * RS_TILE;
-    u64 key[RS_ITEMS];
-    u32 val[RS_ITEMS];
-    u32 rnk[RS_ITEMS];
+    const u64 tile_base = (u64)blockIdx.x * TILE;
+    u64 key[ITEMS];
+    u32 val[ITEMS];
+    u32 rnk[ITEMS];
     u32* wc = s_cnt + warp * 257;
 #pragma unroll
-    for (int r = 0; r < RS_ITEMS; r++) {
-        const u64 idx = tile_base + (u64)warp * RS_WARP_ITEMS + (u64)r * 32 + lane;
+    for (int r = 0; r < ITEMS; r++) {
+        const u64 idx = tile_base + (u64)warp * WARP_ITEMS + (u64)r * 32 + lane;
         const bool ok = idx < n;
         key[r] = ok ? keys_in[idx] : ~0ULL;
         val[r] = ok ? vals_in[idx] : 0u;
@@ -261,8 +263,8 @@ static __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const 
     }
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < RS_ITEMS; r++) {
-        const u64 idx = tile_base + (u64)warp * RS_WARP_ITEMS + (u64)r * 32 + lane;
+    for (int r = 0; r < ITEMS; r++) {
+        const u64 idx = tile_base + (u64)warp * WARP_ITEMS + (u64)r * 32 + lane;
         if (idx < n) {
             const u32 d = (u32)(key[r] >> shift) & 255u;
             const u32 pos = s_dstart[d] + wc[d] + rnk[r];
@@ -272,7 +274,7 @@ static __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const 
     }
     __syncthreads();
     const u64 rem = n - tile_base;
-    const u32 valid = rem < (u64)RS_TILE ? (u32)rem : (u32)RS_TILE;
+    const u32 valid = rem < (u64)TILE ? (u32)rem : (u32)TILE;
     for (u32 i = threadIdx.x; i < valid; i += RS_THREADS) {
         const u64 k = s_keys[i];
         const u32 d = (u32)(k >> shift) & 255u;
@@ -284,23 +286,37 @@ static __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const 
 
 // Sorts in place logically: on return *keys / *vals point at the buffers holding the sorted data
 // (either the inputs or the alternates).
-inline void radix_sort_pairs(u64** keys, u32** vals, u64** keys_alt, u32** vals_alt, u64 n, int n_bits, cudaStream_t st) {
-    if (n <= 1 || n_bits <= 0) return;
+template <int ITEMS>
+inline void radix_sort_pairs_t(u64** keys, u32** vals, u64** keys_alt, u32** vals_alt, u64 n, int n_bits, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        GRL_CUDA(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM));
+        GRL_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<ITEMS>()));
         attr_set = true;
     }
-    const u64 tiles = div_up(n, RS_TILE);
+    const u64 tiles = div_up(n, RS_THREADS * ITEMS);
     DevBuf<u32> hist(256 * tiles, st);
     DevBuf<u64> goff(256 * tiles, st);
     for (int shift = 0; shift < n_bits; shift += 8) {
-        GRL_LAUNCH("radix_hist", n * 8, radix_hist_kernel, (unsigned)tiles, RS_THREADS, 0, st, *keys, n, shift, hist.p, tiles);
+        GRL_LAUNCH("radix_hist", n * 8, (radix_hist_kernel<ITEMS>), (unsigned)tiles, RS_THREADS, 0, st, *keys, n, shift, hist.p, tiles);
         exclusive_scan<u32, u64>(hist.p, goff.p, 256 * tiles, nullptr, st);
-        GRL_LAUNCH("radix_scatter", n * 24, radix_scatter_kernel, (unsigned)tiles, RS_THREADS, RS_SMEM, st, *keys, *vals, *keys_alt, *vals_alt, n, shift,
+        GRL_LAUNCH("radix_scatter", n * 24, (radix_scatter_kernel<ITEMS>), (unsigned)tiles, RS_THREADS, rs_smem_bytes<ITEMS>(), st, *keys, *vals, *keys_alt, *vals_alt, n, shift,
                    goff.p, tiles);
         u64* tk = *keys; *keys = *keys_alt; *keys_alt = tk;
         u32* tv = *vals; *vals = *vals_alt; *vals_alt = tv;
+    }
+}
+inline int rs_items_setting() {
+    static int v = 0;
+    if (!v) { const char* e = getenv("GRL_RS_ITEMS"); v = e ? atoi(e) : 8; if (v != 4 && v != 8 && v != 12 && v != 16) v = 8; }  // 8 items/thread: 59 registers, 4 CTAs/SM (measured best on B200)
+    return v;
+}
+inline void radix_sort_pairs(u64** keys, u32** vals, u64** keys_alt, u32** vals_alt, u64 n, int n_bits, cudaStream_t st) {
+    if (n <= 1 || n_bits <= 0) return;
+    switch (rs_items_setting()) {
+        case 4: radix_sort_pairs_t<4>(keys, vals, keys_alt, vals_alt, n, n_bits, st); break;
+        case 16: radix_sort_pairs_t<16>(keys, vals, keys_alt, vals_alt, n, n_bits, st); break;
+        case 12: radix_sort_pairs_t<12>(keys, vals, keys_alt, vals_alt, n, n_bits, st); break;
+        default: radix_sort_pairs_t<8>(keys, vals, keys_alt, vals_alt, n, n_bits, st); break;
     }
 }
 
