@@ -90,27 +90,6 @@ static __global__ void __launch_bounds__(256) key_head_flags_kernel(const u64* _
     flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
 }
 
-// rank[order[i]] = 1-based dense rank of the key at sorted index i
-static __global__ void __launch_bounds__(256) scatter_rank_kernel(const u32* __restrict__ flags, const u32* __restrict__ excl, const u32* __restrict__ order, u64 n,
-                                                                  u32* __restrict__ rank) {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    rank[order[i]] = excl[i] + flags[i];
-}
-
-// doubling key: (rank[e] << bits) | rank of the suffix h symbols further (0 past the terminator, term at it)
-static __global__ void __launch_bounds__(256) sfx_double_key_kernel(const u32* __restrict__ rank, const u32* __restrict__ rem, const u32* __restrict__ order, u64 nE,
-                                                                    u32 h, u32 term_rank, int bits, u64* __restrict__ keys) {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nE) return;
-    const u32 e = order[i];
-    const u32 r = rem[e];
-    u64 second = 0;
-    if (h <= r) second = rank[e + h];
-    else if (h == r + 1) second = term_rank;
-    keys[i] = ((u64)rank[e] << bits) | second;
-}
-
 // ---- refinement of the unresolved groups only (Larsson-Sadakane style prefix doubling) ----
 // During refinement rank[e] is position-based: 1 + the position (in the sorted order) of the head of e's
 // group, so refining one group never changes the rank of another. A group is unresolved while it has more
