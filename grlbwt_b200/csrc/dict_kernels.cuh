@@ -123,6 +123,16 @@ static __global__ void __launch_bounds__(256) assign_hrank_kernel(const u32* __r
     const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (j < n) hrank[entries[j]] = head_pos[excl[j] + flags[j] - 1] + 1;
 }
+// (entry, rank) pairs of the first sort, and their L2-local scatter after a partition by the entry's high bits
+static __global__ void __launch_bounds__(256) hrank_pairs_kernel(const u32* __restrict__ flags, const u32* __restrict__ excl, const u32* __restrict__ head_pos,
+                                                                 const u32* __restrict__ entries, u64 n, u32* __restrict__ keys, u32* __restrict__ vals) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) { keys[j] = entries[j]; vals[j] = head_pos[excl[j] + flags[j] - 1] + 1; }
+}
+static __global__ void __launch_bounds__(256) scatter_pairs_kernel(const u32* __restrict__ keys, const u32* __restrict__ vals, u64 n, u32* __restrict__ dst) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) dst[keys[j]] = vals[j];
+}
 static __global__ void __launch_bounds__(256) active_keys_kernel(const u32* __restrict__ apos, const u32* __restrict__ order, const u32* __restrict__ hrank,
                                                                  const u32* __restrict__ rem, u64 nA, u64 h, u32 term_rank, int bits, u64* __restrict__ keys,
                                                                  u32* __restrict__ vals) {

@@ -393,7 +393,17 @@ void stage_dict(Round& R) {
             const u64 G0 = d2h_scalar(gcount.p, st);
             DevBuf<u32> head_pos(G0, st);
             GRL_LAUNCH("head_pos", nE * 8, head_pos_kernel, grid_for(nE, 256), 256, 0, st, flags.p, excl.p, (const u32*)nullptr, nE, head_pos.p);
-            GRL_LAUNCH("assign_hrank", nE * 20, assign_hrank_kernel, grid_for(nE, 256), 256, 0, st, flags.p, excl.p, head_pos.p, order_w, nE, R.rank.p);
+            if (nE <= (1ull << 24)) {  // the whole rank array fits the L2: scatter directly
+                GRL_LAUNCH("assign_hrank", nE * 20, assign_hrank_kernel, grid_for(nE, 256), 256, 0, st, flags.p, excl.p, head_pos.p, order_w, nE, R.rank.p);
+            } else {
+                // a random 4-byte scatter over GBs costs ~78 B of DRAM traffic per entry (sector read-modify-write); partition the
+                // (entry, rank) pairs by the entry's top byte first, so that every stretch of pairs lands in one 64 MB window
+                DevBuf<u32> pk(nE, st), pv(nE, st), pk2(nE, st), pv2(nE, st);
+                GRL_LAUNCH("hrank_pairs", nE * 20, hrank_pairs_kernel, grid_for(nE, 256), 256, 0, st, flags.p, excl.p, head_pos.p, order_w, nE, pk.p, pv.p);
+                u32 *k1 = pk.p, *v1 = pv.p, *k2 = pk2.p, *v2 = pv2.p;
+                radix_partition_u32(&k1, &v1, &k2, &v2, nE, 24, st);
+                GRL_LAUNCH("scatter_pairs", nE * 12, scatter_pairs_kernel, grid_for(nE, 256), 256, 0, st, k1, v1, nE, R.rank.p);
+            }
             BitmapCompactor ac;
             nA = ac.count(active_bits.p, nE, st);
             apos.alloc(nA, st);

@@ -190,13 +190,13 @@ struct BitmapCompactor {
 // ------------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-template <int ITEMS>
+template <class KeyT, int ITEMS>
 constexpr size_t rs_smem_bytes() {
-    return (size_t)RS_THREADS * ITEMS * (sizeof(u64) + sizeof(u32)) + (size_t)RS_WARPS * 257 * sizeof(u32) + 2 * 256 * sizeof(u32) + 34 * sizeof(u32);
+    return (size_t)RS_THREADS * ITEMS * (sizeof(KeyT) + sizeof(u32)) + (size_t)RS_WARPS * 257 * sizeof(u32) + 2 * 256 * sizeof(u32) + 34 * sizeof(u32);
 }
 
-template <int ITEMS>
-__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const u64* __restrict__ keys, u64 n, int shift, u32* __restrict__ hist, u64 tiles) {
+template <class KeyT, int ITEMS>
+__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const KeyT* __restrict__ keys, u64 n, int shift, u32* __restrict__ hist, u64 tiles) {
     __shared__ u32 cnt[256];
     cnt[threadIdx.x] = 0;
     __syncthreads();
@@ -210,12 +210,12 @@ __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const u64* __res
     hist[(u64)threadIdx.x * tiles + blockIdx.x] = cnt[threadIdx.x];
 }
 
-template <int ITEMS>
-__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in, u64* __restrict__ keys_out,
+template <class KeyT, int ITEMS>
+__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const KeyT* __restrict__ keys_in, const u32* __restrict__ vals_in, KeyT* __restrict__ keys_out,
                                                                    u32* __restrict__ vals_out, u64 n, int shift, const u64* __restrict__ goff, u64 tiles) {
     constexpr int TILE = RS_THREADS * ITEMS, WARP_ITEMS = TILE / RS_WARPS;
     extern __shared__ __align__(16) unsigned char rs_smem[];
-    u64* s_keys = (u64*)rs_smem;
+    KeyT* s_keys = (KeyT*)rs_smem;
     u32* s_vals = (u32*)(s_keys + TILE);
     u32* s_cnt = s_vals + TILE;               // [RS_WARPS][257]
     u32* s_dstart = s_cnt + RS_WARPS * 257;   // [256] tile-local start of each digit
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const u64* __
     __syncthreads();
 
     const u64 tile_base = (u64)blockIdx.x * TILE;
-    u64 key[ITEMS];
+    KeyT key[ITEMS];
     u32 val[ITEMS];
     u32 rnk[ITEMS];
     u32* wc = s_cnt + warp * 257;
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const u64* __
     for (int r = 0; r < ITEMS; r++) {
         const u64 idx = tile_base + (u64)warp * WARP_ITEMS + (u64)r * 32 + lane;
         const bool ok = idx < n;
-        key[r] = ok ? keys_in[idx] : ~0ULL;
+        key[r] = ok ? keys_in[idx] : (KeyT)~(KeyT)0;
         val[r] = ok ? vals_in[idx] : 0u;
         const u32 d = ok ? ((u32)(key[r] >> shift) & 255u) : 256u;
         const u32 m = __match_any_sync(0xffffffffu, d);
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const u64* __
     const u64 rem = n - tile_base;
     const u32 valid = rem < (u64)TILE ? (u32)rem : (u32)TILE;
     for (u32 i = threadIdx.x; i < valid; i += RS_THREADS) {
-        const u64 k = s_keys[i];
+        const KeyT k = s_keys[i];
         const u32 d = (u32)(k >> shift) & 255u;
         const u64 g = s_goff[d] + (i - s_dstart[d]);
         keys_out[g] = k;
@@ -284,26 +284,37 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const u64* __
     }
 }
 
+// one stable partition pass on the 8-bit digit at `shift` (also the building block of the LSD sort below)
+template <class KeyT, int ITEMS>
+inline void radix_pass(KeyT** keys, u32** vals, KeyT** keys_alt, u32** vals_alt, u64 n, int shift, DevBuf<u32>& hist, DevBuf<u64>& goff, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        GRL_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<KeyT, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<KeyT, ITEMS>()));
+        attr_set = true;
+    }
+    const u64 tiles = div_up(n, RS_THREADS * ITEMS);
+    GRL_LAUNCH("radix_hist", n * sizeof(KeyT), (radix_hist_kernel<KeyT, ITEMS>), (unsigned)tiles, RS_THREADS, 0, st, *keys, n, shift, hist.p, tiles);
+    exclusive_scan<u32, u64>(hist.p, goff.p, 256 * tiles, nullptr, st);
+    GRL_LAUNCH("radix_scatter", n * 2 * (sizeof(KeyT) + 4), (radix_scatter_kernel<KeyT, ITEMS>), (unsigned)tiles, RS_THREADS, (rs_smem_bytes<KeyT, ITEMS>()), st, *keys, *vals,
+               *keys_alt, *vals_alt, n, shift, goff.p, tiles);
+    KeyT* tk = *keys; *keys = *keys_alt; *keys_alt = tk;
+    u32* tv = *vals; *vals = *vals_alt; *vals_alt = tv;
+}
 // Sorts in place logically: on return *keys / *vals point at the buffers holding the sorted data
 // (either the inputs or the alternates).
 template <int ITEMS>
 inline void radix_sort_pairs_t(u64** keys, u32** vals, u64** keys_alt, u32** vals_alt, u64 n, int n_bits, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        GRL_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<ITEMS>()));
-        attr_set = true;
-    }
     const u64 tiles = div_up(n, RS_THREADS * ITEMS);
     DevBuf<u32> hist(256 * tiles, st);
     DevBuf<u64> goff(256 * tiles, st);
-    for (int shift = 0; shift < n_bits; shift += 8) {
-        GRL_LAUNCH("radix_hist", n * 8, (radix_hist_kernel<ITEMS>), (unsigned)tiles, RS_THREADS, 0, st, *keys, n, shift, hist.p, tiles);
-        exclusive_scan<u32, u64>(hist.p, goff.p, 256 * tiles, nullptr, st);
-        GRL_LAUNCH("radix_scatter", n * 24, (radix_scatter_kernel<ITEMS>), (unsigned)tiles, RS_THREADS, rs_smem_bytes<ITEMS>(), st, *keys, *vals, *keys_alt, *vals_alt, n, shift,
-                   goff.p, tiles);
-        u64* tk = *keys; *keys = *keys_alt; *keys_alt = tk;
-        u32* tv = *vals; *vals = *vals_alt; *vals_alt = tv;
-    }
+    for (int shift = 0; shift < n_bits; shift += 8) radix_pass<u64, ITEMS>(keys, vals, keys_alt, vals_alt, n, shift, hist, goff, st);
+}
+// (u32 key, u32 value) pairs partitioned by the key's digit at `shift`: used to make a big random scatter L2-local
+inline void radix_partition_u32(u32** keys, u32** vals, u32** keys_alt, u32** vals_alt, u64 n, int shift, cudaStream_t st) {
+    const u64 tiles = div_up(n, RS_THREADS * 8);
+    DevBuf<u32> hist(256 * tiles, st);
+    DevBuf<u64> goff(256 * tiles, st);
+    radix_pass<u32, 8>(keys, vals, keys_alt, vals_alt, n, shift, hist, goff, st);
 }
 inline int rs_items_setting() {
     static int v = 0;
