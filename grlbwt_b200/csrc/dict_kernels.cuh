@@ -168,6 +168,92 @@ static __global__ void __launch_bounds__(256) compact_apos_kernel(const u32* __r
     const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (j < nA && aflag[j]) apos_next[excl[j]] = apos[j];
 }
+// ---- refinement by key extension (no rank array): an unresolved group is split by the K codes that follow the
+// `dpt` codes its members already share; every pass is local to the dictionary text, so it also works when the
+// suffix entries are partitioned over several GPUs. Used when ceil((longest phrase + 1) / K) passes are few. ----
+template <class SymT>
+__global__ void __launch_bounds__(256) ext_keys_kernel(const u32* __restrict__ apos, const u32* __restrict__ order, const SymT* __restrict__ D,
+                                                       const u32* __restrict__ rem, const u32* __restrict__ head_bits, u64 nA, u64 dpt, u64 term_code, int bits,
+                                                       int K, u64* __restrict__ keys, u32* __restrict__ vals, u64* __restrict__ nk, u32* __restrict__ ev,
+                                                       u32* __restrict__ gflag) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nA) return;
+    const u32 i = apos[j], e = order[i];
+    const u64 r = rem[e];
+    u64 key = 0;
+    for (int t = 0; t < K; t++) {
+        const u64 pos = dpt + (u64)t;
+        u64 code = 0;
+        if (pos <= r) code = (u64)D[e + pos] + 1;
+        else if (pos == r + 1) code = term_code;
+        key = (bits >= 64) ? code : ((key << bits) | code);
+    }
+    keys[j] = key;
+    nk[j] = key;
+    vals[j] = (u32)j;
+    ev[j] = e;
+    gflag[j] = (head_bits[i >> 5] >> (i & 31)) & 1u;
+}
+// second sort key: index of the (unresolved) group the active element belongs to
+static __global__ void __launch_bounds__(256) ext_group_keys_kernel(const u32* __restrict__ vals, const u32* __restrict__ gflag, const u32* __restrict__ gexcl, u64 nA,
+                                                                    u64* __restrict__ keys) {
+    const u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nA) { const u32 j = vals[q]; keys[q] = (u64)(gexcl[j] + gflag[j] - 1); }
+}
+static __global__ void __launch_bounds__(256) ext_heads_kernel(const u32* __restrict__ vals, const u64* __restrict__ gkeys, const u64* __restrict__ nk, u64 nA,
+                                                               u32* __restrict__ flags) {
+    const u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nA) return;
+    flags[q] = (q == 0 || gkeys[q] != gkeys[q - 1] || nk[vals[q]] != nk[vals[q - 1]]) ? 1u : 0u;
+}
+static __global__ void __launch_bounds__(256) ext_writeback_kernel(const u32* __restrict__ apos, const u32* __restrict__ vals, const u32* __restrict__ ev,
+                                                                   const u32* __restrict__ flags, u64 nA, u32* __restrict__ order, u32* head_bits) {
+    const u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nA) return;
+    const u32 i = apos[q];
+    order[i] = ev[vals[q]];
+    if (flags[q]) atomicOr(&head_bits[i >> 5], 1u << (i & 31));
+}
+static __global__ void __launch_bounds__(256) ext_next_kernel(const u32* __restrict__ apos, const u32* __restrict__ vals, const u32* __restrict__ ev,
+                                                              const u32* __restrict__ head_bits, const u32* __restrict__ rem, u64 nA, u64 nE, u64 dpt_next,
+                                                              u32* __restrict__ aflag) {
+    const u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nA) return;
+    const u64 i = apos[q];
+    const bool hd = (head_bits[i >> 5] >> (i & 31)) & 1u;
+    const bool nh = i + 1 == nE || ((head_bits[(i + 1) >> 5] >> ((i + 1) & 31)) & 1u);
+    aflag[q] = (!(hd && nh) && (u64)rem[ev[vals[q]]] + 1 >= dpt_next) ? 1u : 0u;
+}
+// dense variant of ginfo (indexed by group) and the per-entry finalisation done in sorted order: no per-entry rank needed
+static __global__ void __launch_bounds__(256) pack_ginfo_dense_kernel(const u32* __restrict__ gcnt, const u32* __restrict__ rflag, const u32* __restrict__ rrank, u64 G,
+                                                                      u32* __restrict__ ginfo) {
+    const u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < G) ginfo[g] = (rrank[g] << 2) | (((gcnt[g] & 0x7fffffffu) > 1) ? 2u : 0u) | (rflag[g] ? 1u : 0u);
+}
+template <class SymT>
+__global__ void __launch_bounds__(256) group_apply_kernel(const u32* __restrict__ order, const u32* __restrict__ head_bits, const u32* __restrict__ head_pref,
+                                                          const u32* __restrict__ full_bits, const u32* __restrict__ ginfo, const SymT* __restrict__ D,
+                                                          const u32* __restrict__ rem, const u32* __restrict__ phr_of, const u64* __restrict__ ph_freq,
+                                                          const u32* __restrict__ occ_slots, u64 nE, IsSuffix is_suffix, u64 rank_base, ulonglong2* table,
+                                                          u64* __restrict__ ph_meta, u8* __restrict__ is_suffix_next, u32* __restrict__ erank) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nE) return;
+    const u32 hw = head_bits[i >> 5];
+    const u32 g = head_pref[i >> 5] + __popc(hw & (0xffffffffu >> (31 - (i & 31)))) - 1;
+    const u32 gi = ginfo[g];
+    if (!(gi & 1u)) return;  // invalid and unranked groups carry no rank
+    const u64 r = (u64)(gi >> 2) + rank_base;
+    const u32 e = order[i];
+    if (gi & 2u) erank[e] = (u32)r;
+    if ((full_bits[i >> 5] >> (i & 31)) & 1u) {
+        const u32 ph = phr_of[e];
+        const u64 meta = (r << 1) | (ph_freq[ph] > 1 ? 1ULL : 0ULL);
+        if (ph_meta) ph_meta[ph] = meta;
+        else table[occ_slots[ph]].y = meta;
+        is_suffix_next[r] = is_suffix((u64)D[e + rem[e]]) ? 1 : 0;
+    }
+}
+
 static __global__ void __launch_bounds__(256) popc_words_kernel(const u32* __restrict__ bits, u64 n_words, u32* __restrict__ cnt) {
     const u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (w < n_words) cnt[w] = __popc(bits[w]);
@@ -192,11 +278,11 @@ struct OpMax { template <class T> __device__ __forceinline__ T operator()(T a, T
 // gcnt = entries | full<<31 ; gmin/gmax over (left symbol + 1) of the non-full entries (0 = none).
 static __global__ void __launch_bounds__(256) group_reduce_kernel(const u32* __restrict__ order, const u32* __restrict__ head_bits, const u32* __restrict__ head_pref,
                                                                   const ulonglong2* __restrict__ einfo, u64 nE, u32* gcnt, u64* gacc, u64* gmin, u64* gmax,
-                                                                  u32* __restrict__ grep, u32* __restrict__ ghead) {
+                                                                  u32* __restrict__ grep, u32* __restrict__ ghead, u32* __restrict__ full_bits) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     u32 g = 0xffffffffu, cnt = 0;
     u64 acc = 0, mn = ~0ULL, mx = 0;
-    bool hd = false, nh = true;
+    bool hd = false, nh = true, is_full = false;
     if (i < nE) {
         const u32 e = order[i];
         const u32 hw = head_bits[i >> 5];
@@ -206,11 +292,16 @@ static __global__ void __launch_bounds__(256) group_reduce_kernel(const u32* __r
         nh = i + 1 == nE || ((head_bits[(i + 1) >> 5] >> ((i + 1) & 31)) & 1u);
         const ulonglong2 ei = einfo[e];
         if (ei.y & EI_VALID) {
-            cnt = 1u | ((ei.y & EI_FULL) ? 0x80000000u : 0u);
+            is_full = (ei.y & EI_FULL) != 0;
+            cnt = 1u | (is_full ? 0x80000000u : 0u);
             acc = ei.y & EI_FREQ;
             if (ei.x) mn = mx = ei.x;
         }
         if (hd) { grep[g] = e; ghead[g] = (u32)i; }  // entries keep their position-based rank = head position + 1
+    }
+    if (full_bits) {  // which sorted positions hold a whole phrase (used by the sorted-order finalisation)
+        const u32 fb = __ballot_sync(0xffffffffu, is_full);
+        if (lane_id() == 0 && (i >> 5) < ((nE + 31) >> 5)) full_bits[i >> 5] = fb;
     }
     const u32 m = __match_any_sync(0xffffffffu, g);
     const u32 first = __ffs(m) - 1, last = 31 - __clz(m);

@@ -368,8 +368,8 @@ void stage_dict(Round& R) {
     // -- suffix order: one full sort on the packed first key, then prefix doubling on the unresolved groups only --
     const u64 n_words = div_up(nE, 32);
     DevBuf<u32> order_buf, head_bits(n_words, st);
-    R.rank.alloc(nE, st);
     u64 G = 0;
+    bool ext_mode = false;
     {
         DevBuf<u64> keys(nE, st), keys_alt(nE, st);
         DevBuf<u32> vals(nE, st), vals_alt(nE, st);
@@ -385,6 +385,46 @@ void stage_dict(Round& R) {
         u32* order_w = order_buf.p;
         u64 nA = 0;
         DevBuf<u32> apos;
+        // refinement by key extension needs ceil((longest phrase + 1) / K) passes at most; beyond 64 passes (or when a
+        // test forces it) the groups are refined by prefix doubling on position-based ranks instead
+        ext_mode = !(c->flags & GRLGPU_FLAG_FORCE_DOUBLING) && (R.max_len + 1 + (u64)K - 1) / (u64)K <= 64;
+        if (ext_mode) {
+            {
+                DevBuf<u32> flags(nE, st), active_bits(n_words, st);
+                GRL_LAUNCH("first_heads", nE * 12, first_heads_kernel, grid_for(nE, 256), 256, 0, st, kp, nE, sym_bits, A + 1, flags.p, head_bits.p, active_bits.p);
+                keys.release(); keys_alt.release();
+                BitmapCompactor ac;
+                nA = ac.count(active_bits.p, nE, st);
+                apos.alloc(nA, st);
+                if (nA) ac.write<u32>(nullptr, apos.p);
+            }
+            u64 dpt = (u64)K;  // codes already compared
+            while (nA > 0) {
+                if (dpt > R.max_len + 1) throw Error(GRLGPU_ERR_STATE, "suffix refinement did not converge");
+                DevBuf<u64> ak(nA, st), ak_alt(nA, st), nk(nA, st);
+                DevBuf<u32> av(nA, st), av_alt(nA, st), ev(nA, st), gflag(nA, st), gexcl(nA, st), flags(nA, st), excl(nA, st), cnt(1, st);
+                u64 *akp = ak.p, *aka = ak_alt.p;
+                u32 *avp = av.p, *ava = av_alt.p;
+                GRL_LAUNCH("ext_keys", nA * 48, (ext_keys_kernel<SymT>), grid_for(nA, 256), 256, 0, st, apos.p, order_w, D, R.rem.p, head_bits.p, nA, dpt, A + 1, sym_bits, K, akp,
+                           avp, nk.p, ev.p, gflag.p);
+                exclusive_scan<u32, u32>(gflag.p, gexcl.p, nA, cnt.p, st);
+                const u64 n_groups = d2h_scalar(cnt.p, st);
+                radix_sort_pairs(&akp, &avp, &aka, &ava, nA, std::min(64, sym_bits * K), st);  // by the extension key ...
+                GRL_LAUNCH("ext_group_keys", nA * 16, ext_group_keys_kernel, grid_for(nA, 256), 256, 0, st, avp, gflag.p, gexcl.p, nA, akp);
+                radix_sort_pairs(&akp, &avp, &aka, &ava, nA, std::max(1, bit_width64(n_groups)), st);  // ... then, stably, by group
+                GRL_LAUNCH("ext_heads", nA * 24, ext_heads_kernel, grid_for(nA, 256), 256, 0, st, avp, akp, nk.p, nA, flags.p);
+                GRL_LAUNCH("ext_writeback", nA * 16, ext_writeback_kernel, grid_for(nA, 256), 256, 0, st, apos.p, avp, ev.p, flags.p, nA, order_w, head_bits.p);
+                dpt += (u64)K;
+                GRL_LAUNCH("ext_next", nA * 16, ext_next_kernel, grid_for(nA, 256), 256, 0, st, apos.p, avp, ev.p, head_bits.p, R.rem.p, nA, nE, dpt, flags.p);
+                exclusive_scan<u32, u32>(flags.p, excl.p, nA, cnt.p, st);
+                const u64 nA2 = d2h_scalar(cnt.p, st);
+                DevBuf<u32> apos2(nA2, st);
+                if (nA2) GRL_LAUNCH("compact_apos", nA * 12, compact_apos_kernel, grid_for(nA, 256), 256, 0, st, flags.p, excl.p, apos.p, nA, apos2.p);
+                apos = std::move(apos2);
+                nA = nA2;
+            }
+        } else {
+        R.rank.alloc(nE, st);
         {   // heads, position-based ranks and the first active set
             DevBuf<u32> flags(nE, st), excl(nE, st), active_bits(n_words, st), gcount(1, st);
             GRL_LAUNCH("first_heads", nE * 12, first_heads_kernel, grid_for(nE, 256), 256, 0, st, kp, nE, sym_bits, A + 1, flags.p, head_bits.p, active_bits.p);
@@ -435,6 +475,7 @@ void stage_dict(Round& R) {
             apos = std::move(apos2);
             nA = nA2;
         }
+            }  // doubling
     }
     const u32* order = order_buf.p;
     // dense group ids from the head bitmap: per-word prefix counts
@@ -451,7 +492,8 @@ void stage_dict(Round& R) {
     DevBuf<u32> gcnt(G, st), grep(G, st), ghead(G, st), rflag(G, st), vflag(G, st), rrank(G, st), vidx(G, st);
     DevBuf<u64> gacc(G, st), gmin(G, st), gmax(G, st), psym(G, st);
     gcnt.zero(); gacc.zero(); gmax.zero(); gmin.fill_ff();
-    GRL_LAUNCH("group_reduce", nE * 24 + G * 32, group_reduce_kernel, grid_for(nE, 256), 256, 0, st, order, head_bits.p, head_pref.p, R.einfo.p, nE, gcnt.p, gacc.p, gmin.p, gmax.p, grep.p, ghead.p);
+    DevBuf<u32> full_bits(ext_mode ? n_words : 1, st);
+    GRL_LAUNCH("group_reduce", nE * 24 + G * 32, group_reduce_kernel, grid_for(nE, 256), 256, 0, st, order, head_bits.p, head_pref.p, R.einfo.p, nE, gcnt.p, gacc.p, gmin.p, gmax.p, grep.p, ghead.p, ext_mode ? full_bits.p : (u32*)nullptr);
     R.einfo.release();
     const u64 bwt_dummy = A + 1, hocc_dummy = A + 2;  // exact_par_phase.hpp:113-115
     GRL_LAUNCH("group_finalize", 0, group_finalize_kernel, grid_for(G, 256), 256, 0, st, gcnt.p, gmin.p, gmax.p, G, bwt_dummy, hocc_dummy, rflag.p, vflag.p, psym.p);
@@ -485,9 +527,16 @@ void stage_dict(Round& R) {
     is_suffix_next.zero();
     DevBuf<u32> erank(nE, st);
     erank.fill_ff();
-    DevBuf<u32> ginfo(nE, st);  // indexed by head position
-    GRL_LAUNCH("pack_ginfo", G * 20, pack_ginfo_kernel, grid_for(G, 256), 256, 0, st, gcnt.p, rflag.p, rrank.p, ghead.p, G, ginfo.p);
-    GRL_LAUNCH("entry_finalize", nE * 24, (entry_finalize_kernel<SymT>), grid_for(nE, 256), 256, 0, st, R.rank.p, D, R.rem.p, R.phr_of.p, R.ph_off.p, R.ph_freq.p, R.occ_slots.p, nE, isuf, ginfo.p, R.table.p, R.ph_meta, is_suffix_next.p, erank.p);
+    if (ext_mode) {  // finalisation in sorted order: group info is read sequentially, entries need no rank of their own
+        DevBuf<u32> ginfo(G, st);
+        GRL_LAUNCH("pack_ginfo_dense", G * 16, pack_ginfo_dense_kernel, grid_for(G, 256), 256, 0, st, gcnt.p, rflag.p, rrank.p, G, ginfo.p);
+        GRL_LAUNCH("group_apply", nE * 16, (group_apply_kernel<SymT>), grid_for(nE, 256), 256, 0, st, order, head_bits.p, head_pref.p, full_bits.p, ginfo.p, D, R.rem.p, R.phr_of.p,
+                   R.ph_freq.p, R.occ_slots.p, nE, isuf, (u64)0, R.table.p, R.ph_meta, is_suffix_next.p, erank.p);
+    } else {
+        DevBuf<u32> ginfo(nE, st);  // indexed by head position
+        GRL_LAUNCH("pack_ginfo", G * 20, pack_ginfo_kernel, grid_for(G, 256), 256, 0, st, gcnt.p, rflag.p, rrank.p, ghead.p, G, ginfo.p);
+        GRL_LAUNCH("entry_finalize", nE * 24, (entry_finalize_kernel<SymT>), grid_for(nE, 256), 256, 0, st, R.rank.p, D, R.rem.p, R.phr_of.p, R.ph_off.p, R.ph_freq.p, R.occ_slots.p, nE, isuf, ginfo.p, R.table.p, R.ph_meta, is_suffix_next.p, erank.p);
+    }
     c->rule_l.alloc(tot * sizeof(SymT), st);
     c->rule_r.alloc(tot * sizeof(SymT), st);
     c->has_hocc.alloc(tot, st);

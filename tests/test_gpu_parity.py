@@ -142,6 +142,13 @@ def test_rounds_dedup_variants(golden, all_cases):
         compare_rounds(name, all_cases[name], golden[name], flags=G.FLAG_SMALL_PILOT | G.FLAG_SMALL_TABLE, check_dict=False)
 
 
+def test_rounds_refinement_by_doubling(golden, all_cases):
+    """suffix groups refined by prefix doubling on position-based ranks (the path long phrases take) on ordinary inputs too"""
+    for name in ("test_byte_alphabet", "mutated_200x5k", "u16_rand", "ac_short_3000", "reads_2000x150", "with_empty", "fuzz_9", "fuzz_33"):
+        compare_rounds(name, all_cases[name], golden[name], flags=G.FLAG_FORCE_DOUBLING)
+    compare_rounds("rep_50x200k", all_cases["rep_50x200k"], golden["rep_50x200k"], flags=G.FLAG_FORCE_DOUBLING, check_dict=False)
+
+
 def test_many_empty_strings_overflow_the_tile_list():
     """more phrase starts in one tile than the shared-memory list holds (runs of empty strings)"""
     arr = np.frombuffer(b"\n" * 70000 + b"ACGT\n" * 3000 + b"\n" * 40000, np.uint8).copy()
