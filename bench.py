@@ -256,11 +256,11 @@ def run_ours(args, rank, world, local_rank):
                     return d2h
         st = M.global_stats(engine)
         while True:
-            info, done = M.distributed_round(engine, st["n_strings"])
+            info, done = M.distributed_round(engine, st["n_strings"], want_level=fetch)
             if collect is not None:
                 collect.append(info)
             if fetch and rank == 0:
-                ctx.fetch_level(arena[0])
+                engine.fetch_level(arena[0])
                 d2h += info["tot_phrases"] * (2 * info["sym_bytes"] + 1) + info["n_pre_runs"] * (info["sym_bytes"] + 8)
             if done:
                 if fetch:
@@ -349,7 +349,7 @@ def run_ours(args, rank, world, local_rank):
     alg_bytes = sum(r["algorithmic_bytes"] for r in rounds_info)
     round_ms = sum(r["device_ms"] for r in rounds_info)
     keys = ("round", "n_in", "parse_len", "n_phrases", "dict_syms", "tot_phrases", "n_pre_runs", "device_ms", "text_pass_ms", "dict_ms", "rewrite_ms",
-            "algorithmic_bytes", "exchange_bytes_sent", "gather_bytes")
+            "algorithmic_bytes", "exchange_bytes_sent", "gather_bytes", "ranking")
     parse_rounds = {"algorithmic_GB": round(alg_bytes / 1e9, 3), "device_ms": round(round_ms, 3),
                     "achieved_GBps": round(alg_bytes / 1e6 / round_ms, 1) if round_ms else None,
                     "frac_of_measured_peak": round(alg_bytes / 1e6 / round_ms / hbm_peak, 4) if round_ms else None,
@@ -391,7 +391,8 @@ def run_ours(args, rank, world, local_rank):
                            "reads": args.reads if args.workload == "c2" else None, "cache": "the text of every round-1 pass (7.55 GB at the default size) exceeds the 126 MB L2",
                            "parallelism": "1 GPU" if world == 1 else
                            f"{world} ranks: contiguous ranges of whole reads per rank; per round one hash-partitioned all-to-all-v of the local "
-                           f"dictionaries + one all-gather-v of the deduplicated global dictionary over NCCL; the dictionary ranking is replicated"},
+                           f"dictionaries + one all-gather-v of the deduplicated global dictionary over NCCL; large dictionaries are ranked "
+                           f"distributed (suffix entries partitioned by first-key range, three all-reduces), small ones replicated"},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "bwt_total": bwt_total,
                 "parse_rounds": parse_rounds, "kernels": kernels}
         print(json.dumps(line), flush=True)

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 LIB_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
-FLAG_SMALL_TABLE, FLAG_FORCE_SLOW_SCAN, FLAG_KEEP_DICT, FLAG_FORCE_UNCACHED, FLAG_SMALL_PILOT, FLAG_FORCE_DOUBLING = 1, 2, 4, 8, 16, 32
+FLAG_SMALL_TABLE, FLAG_FORCE_SLOW_SCAN, FLAG_KEEP_DICT, FLAG_FORCE_UNCACHED, FLAG_SMALL_PILOT, FLAG_FORCE_DOUBLING, FLAG_FORCE_DIST_RANK = 1, 2, 4, 8, 16, 32, 64
 CELL = {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}
 
 
@@ -81,6 +81,10 @@ def lib_gpu():
         L.grlgpu_mg_merge.argtypes = [vp, vp, vp, vp, u64, u64, vp]
         L.grlgpu_mg_pack_part.argtypes = [vp, vp, vp, vp]
         L.grlgpu_mg_global.argtypes = [vp, vp, vp, vp, u64, u64, C.c_int, C.POINTER(Round)]
+        L.grlgpu_mg_rank_sort.argtypes = [vp, vp, vp, vp, u64, u64, C.c_int, C.c_int, vp]
+        L.grlgpu_mg_rank_apply.argtypes = [vp, u64, vp, vp, vp]
+        L.grlgpu_mg_rank_finish.argtypes = [vp, u64, u64, u64, vp, vp, vp, C.c_int, C.POINTER(Round)]
+        L.grlgpu_mg_level_slice.argtypes = [vp, vp, vp, vp, vp, vp]
         L.grlgpu_selftest_scan.argtypes = [vp, u64, vp, vp]
         L.grlgpu_selftest_sort.argtypes = [vp, vp, u64, C.c_int]
         L.grlgpu_selftest_compact.argtypes = [vp, vp, u64, vp, vp]
@@ -238,6 +242,24 @@ class GrlGpu:
         self.last = r
         self._round_started = True
         return r.as_dict()
+
+    def mg_rank_sort(self, lens_ptr, freqs_ptr, cells_ptr, d, n_cells, rank_id, n_ranks):
+        info = np.zeros(5, np.uint64)
+        self._check(self._L.grlgpu_mg_rank_sort(self._h, C.c_void_p(lens_ptr), C.c_void_p(freqs_ptr), C.c_void_p(cells_ptr), d, n_cells, rank_id, n_ranks, _ptr(info)))
+        return [int(x) for x in info]
+
+    def mg_rank_apply(self, rank_base, meta_ptr, isn_ptr, erank_ptr):
+        self._check(self._L.grlgpu_mg_rank_apply(self._h, rank_base, C.c_void_p(meta_ptr), C.c_void_p(isn_ptr), C.c_void_p(erank_ptr)))
+
+    def mg_rank_finish(self, rank_base, tot, n_pre, meta_ptr, isn_ptr, erank_ptr, done):
+        r = Round()
+        self._check(self._L.grlgpu_mg_rank_finish(self._h, rank_base, tot, n_pre, C.c_void_p(meta_ptr), C.c_void_p(isn_ptr), C.c_void_p(erank_ptr), int(done), C.byref(r)))
+        self.last = r
+        self._round_started = True
+        return r.as_dict()
+
+    def mg_level_slice(self, rl_ptr, rr_ptr, hh_ptr, ps_ptr, pl_ptr):
+        self._check(self._L.grlgpu_mg_level_slice(self._h, C.c_void_p(rl_ptr), C.c_void_p(rr_ptr), C.c_void_p(hh_ptr), C.c_void_p(ps_ptr), C.c_void_p(pl_ptr)))
 
     def profile_enable(self, on: bool = True):
         self._check(self._L.grlgpu_profile_enable(self._h, int(on)))

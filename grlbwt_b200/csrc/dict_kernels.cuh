@@ -234,8 +234,9 @@ template <class SymT>
 __global__ void __launch_bounds__(256) group_apply_kernel(const u32* __restrict__ order, const u32* __restrict__ head_bits, const u32* __restrict__ head_pref,
                                                           const u32* __restrict__ full_bits, const u32* __restrict__ ginfo, const SymT* __restrict__ D,
                                                           const u32* __restrict__ rem, const u32* __restrict__ phr_of, const u64* __restrict__ ph_freq,
-                                                          const u32* __restrict__ occ_slots, u64 nE, IsSuffix is_suffix, u64 rank_base, ulonglong2* table,
-                                                          u64* __restrict__ ph_meta, u8* __restrict__ is_suffix_next, u32* __restrict__ erank) {
+                                                          const u32* __restrict__ occ_slots, u64 nE, IsSuffix is_suffix, u64 rank_base, u32 erank_bias,
+                                                          ulonglong2* table, u64* __restrict__ ph_meta, u8* __restrict__ is_suffix_next,
+                                                          u32* __restrict__ erank) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nE) return;
     const u32 hw = head_bits[i >> 5];
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(256) group_apply_kernel(const u32* __restrict_
     if (!(gi & 1u)) return;  // invalid and unranked groups carry no rank
     const u64 r = (u64)(gi >> 2) + rank_base;
     const u32 e = order[i];
-    if (gi & 2u) erank[e] = (u32)r;
+    if (gi & 2u) erank[e] = (u32)r + erank_bias;  // bias 1 in distributed rounds (0 = none, merged by all-reduce MAX)
     if ((full_bits[i >> 5] >> (i & 31)) & 1u) {
         const u32 ph = phr_of[e];
         const u64 meta = (r << 1) | (ph_freq[ph] > 1 ? 1ULL : 0ULL);
@@ -252,6 +253,30 @@ __global__ void __launch_bounds__(256) group_apply_kernel(const u32* __restrict_
         else table[occ_slots[ph]].y = meta;
         is_suffix_next[r] = is_suffix((u64)D[e + rem[e]]) ? 1 : 0;
     }
+}
+
+// ---- distributed ranking: every rank owns the suffix entries whose first key falls in its range [lo, hi) ----
+static __global__ void __launch_bounds__(256) key_sample_kernel(const u64* __restrict__ keys, u64 n, u64 stride, u64 n_samples, u64* __restrict__ out, u32* __restrict__ vals) {
+    const u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n_samples) { const u64 i = s * stride; out[s] = keys[i < n ? i : n - 1]; vals[s] = (u32)s; }
+}
+static __global__ void __launch_bounds__(256) key_range_flags_kernel(const u64* __restrict__ keys, u64 n, u64 lo, u64 hi, int hi_open, u32* __restrict__ flags) {
+    const u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) flags[e] = (keys[e] >= lo && (hi_open || keys[e] < hi)) ? 1u : 0u;
+}
+static __global__ void __launch_bounds__(256) key_range_compact_kernel(const u64* __restrict__ keys, const u32* __restrict__ flags, const u32* __restrict__ excl, u64 n,
+                                                                       u64* __restrict__ okeys, u32* __restrict__ ovals) {
+    const u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n && flags[e]) { okeys[excl[e]] = keys[e]; ovals[excl[e]] = (u32)e; }
+}
+// hocc marks travel between ranks as rank+1 (0 = none) so that an all-reduce(MAX) merges them; decode in place
+static __global__ void __launch_bounds__(256) erank_decode_kernel(u32* __restrict__ erank, u64 n) {
+    const u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) erank[e] = erank[e] ? erank[e] - 1 : 0xffffffffu;
+}
+static __global__ void __launch_bounds__(256) u8_to_u64max_kernel(const u64* __restrict__ in, u64 n, u8* __restrict__ out) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] ? 1 : 0;
 }
 
 static __global__ void __launch_bounds__(256) popc_words_kernel(const u32* __restrict__ bits, u64 n_words, u32* __restrict__ cnt) {

@@ -531,7 +531,7 @@ void stage_dict(Round& R) {
         DevBuf<u32> ginfo(G, st);
         GRL_LAUNCH("pack_ginfo_dense", G * 16, pack_ginfo_dense_kernel, grid_for(G, 256), 256, 0, st, gcnt.p, rflag.p, rrank.p, G, ginfo.p);
         GRL_LAUNCH("group_apply", nE * 16, (group_apply_kernel<SymT>), grid_for(nE, 256), 256, 0, st, order, head_bits.p, head_pref.p, full_bits.p, ginfo.p, D, R.rem.p, R.phr_of.p,
-                   R.ph_freq.p, R.occ_slots.p, nE, isuf, (u64)0, R.table.p, R.ph_meta, is_suffix_next.p, erank.p);
+                   R.ph_freq.p, R.occ_slots.p, nE, isuf, (u64)0, 0u, R.table.p, R.ph_meta, is_suffix_next.p, erank.p);
     } else {
         DevBuf<u32> ginfo(nE, st);  // indexed by head position
         GRL_LAUNCH("pack_ginfo", G * 20, pack_ginfo_kernel, grid_for(G, 256), 256, 0, st, gcnt.p, rflag.p, rrank.p, ghead.p, G, ginfo.p);
@@ -666,6 +666,15 @@ struct MgRound {
     const void* recv_cells = nullptr;
     Timer t_text, t_dict;
     float ms_text = 0;
+    // distributed ranking: this rank's slice of the suffix order of the GLOBAL dictionary and its group results
+    std::unique_ptr<Round> GR;      // the global dictionary
+    DevBuf<u64> g_meta;
+    const void* g_cells = nullptr;
+    u64 nL = 0, G = 0, tot_local = 0, n_pre_local = 0;
+    int sym_bytes = 4;
+    DevBuf<u32> order, head_bits, head_pref, full_bits, gcnt, grep, rflag, rrank;
+    DevBuf<u8> sl_rule_l, sl_rule_r, sl_has_hocc, sl_pre_sym;  // this rank's slice of the level artefacts
+    DevBuf<u64> sl_pre_len;
     explicit MgRound(grlgpu_ctx* c) : R(c), t_text(c->st), t_dict(c->st) {}
 };
 
@@ -762,13 +771,11 @@ void mg_pack_part_t(grlgpu_ctx* c, u32* d_lens, u64* d_freqs, void* d_cells) {
 }
 
 template <class CellT, bool FIRST>
-void mg_global_t(grlgpu_ctx* c, const u32* lens, const u64* freqs, const void* cells, u64 d, u64 n_cells, int done_global, grlgpu_round_t* out) {
-    MgRound& M = *c->mg;
-    Round& R = M.R;
+void mg_global_t(grlgpu_ctx* c, const u32* lens, const u64* freqs, const void* cells, u64 d, u64 n_cells, int done_global, grlgpu_round_t* out);
+
+// global dictionary as a Round: "text" = the gathered cells (shared by the replicated and the distributed ranking)
+void mg_setup_global(grlgpu_ctx* c, Round& GR, const u32* lens, const u64* freqs, const void* cells, u64 d, u64 n_cells) {
     cudaStream_t st = c->st;
-    M.t_dict.start();
-    // the global dictionary (identical on every rank) as a Round of its own: "text" = the gathered cells
-    Round GR(c);
     GR.dict_text = cells;
     GR.d = d;
     GR.ph_len.alloc(d, st);
@@ -779,12 +786,14 @@ void mg_global_t(grlgpu_ctx* c, const u32* lens, const u64* freqs, const void* c
     exclusive_scan<u32, u64>(GR.ph_len.p, GR.ph_pos.p, d, GR.ph_pos.p + d, st);
     if (d2h_scalar(GR.ph_pos.p + d, st) != n_cells) throw Error(GRLGPU_ERR_ARG, "gathered cell count does not match the gathered lengths");
     dict_offsets(GR);
-    DevBuf<u64> g_meta(d, st);
-    GR.ph_meta = g_meta.p;
-    const bool wide = (c->alphabet + GR.nE + 8) >= (1ull << 32);
-    if (wide) { stage_gather<CellT, FIRST, u64>(GR); stage_dict<u64>(GR); }
-    else { stage_gather<CellT, FIRST, u32>(GR); stage_dict<u32>(GR); }
-    // content -> global phrase index, then the metasymbol of every local distinct phrase
+}
+
+// content -> global phrase index table, metasymbol of every local distinct phrase, rewrite of the shard
+template <class CellT>
+void mg_map_and_rewrite(grlgpu_ctx* c, MgRound& M, Round& GR, const void* cells, const u64* g_meta, u64 tot, u64 n_pre, int done_global, grlgpu_round_t* out) {
+    Round& R = M.R;
+    cudaStream_t st = c->st;
+    const u64 d = GR.d;
     const u64 gcap = std::max<u64>(1024, (d + d / 2 + d / 10 + 255) / 256 * 256);
     if (gcap > (1ull << 31) - 256) throw Error(GRLGPU_ERR_LIMIT, "phrase table would exceed 2^31 slots");
     DevBuf<ulonglong2> gtable(gcap, st);
@@ -792,7 +801,7 @@ void mg_global_t(grlgpu_ctx* c, const u32* lens, const u64* freqs, const void* c
     DevBuf<u32> flag(2, st);
     flag.zero();
     GRL_LAUNCH("pack_insert", 0, (pack_insert_kernel<CellT>), grid_for(d, 256), 256, 0, st, (const CellT*)cells, GR.ph_pos.p, GR.ph_len.p, (const u64*)nullptr, d, gtable.p, gcap, flag.p);
-    GRL_LAUNCH("map_local", 0, (map_local_kernel<CellT>), grid_for(R.d, 256), 256, 0, st, (const CellT*)c->text, R.ph_pos.p, R.ph_len.p, R.occ_slots.p, R.d, (const CellT*)cells, gtable.p, gcap, g_meta.p, R.table.p, flag.p + 1);
+    GRL_LAUNCH("map_local", 0, (map_local_kernel<CellT>), grid_for(R.d, 256), 256, 0, st, (const CellT*)c->text, R.ph_pos.p, R.ph_len.p, R.occ_slots.p, R.d, (const CellT*)cells, gtable.p, gcap, g_meta, R.table.p, flag.p + 1);
     u32 hflag[2];
     GRL_CUDA(cudaMemcpyAsync(hflag, flag.p, 8, cudaMemcpyDeviceToHost, st));
     GRL_CUDA(cudaStreamSynchronize(st));
@@ -803,9 +812,232 @@ void mg_global_t(grlgpu_ctx* c, const u32* lens, const u64* freqs, const void* c
     tm.text = M.ms_text;
     tm.dict = M.t_dict.ms();
     tm.all = tm.text + tm.dict;
-    finish_round(c, R, GR.tot, GR.n_pre, GR.d, GR.nE, GR.max_freq, tm, nullptr, out);
+    finish_round(c, R, tot, n_pre, GR.d, GR.nE, GR.max_freq, tm, nullptr, out);
     out->done = done_global ? 1u : 0u;  // the phase ends when EVERY rank's strings are single cells
     c->done = done_global != 0;
+}
+
+// Distributed ranking, step 1: this rank sorts and groups the suffix entries whose first key falls in its range.
+// info[0] = 1 if the distributed path was taken (0: nothing was done, call grlgpu_mg_global), info[1] = ranked groups
+// of this rank, info[2] = preliminary-BWT runs of this rank, info[3] = dictionary entries nE, info[4] = symbol bytes.
+template <class CellT, bool FIRST, class SymT>
+void mg_rank_sort_sym(grlgpu_ctx* c, const u32* lens, const u64* freqs, const void* cells, u64 d, u64 n_cells, int rank_id, int n_ranks, u64* info) {
+    MgRound& M = *c->mg;
+    cudaStream_t st = c->st;
+    Round& GR = *M.GR;
+    const u64 nE = GR.nE, A = c->alphabet;
+    stage_gather<CellT, FIRST, SymT>(GR);
+    const SymT* D = (const SymT*)GR.D_raw.p;
+    const int sym_bits = bit_width64(A + 1);
+    const int K = std::max(1, 64 / sym_bits);
+    const int key_bits = std::min(64, sym_bits * K);
+    M.sym_bytes = sizeof(SymT);
+    // first keys of ALL entries (cheap, sequential); splitters from a regular sample, identical on every rank
+    DevBuf<u64> keys(nE, st);
+    {
+        DevBuf<u32> ids(nE, st);
+        GRL_LAUNCH("sfx_first_key", nE * (sizeof(SymT) + 16), (sfx_first_key_kernel<SymT>), grid_for(nE, 256), 256, 0, st, D, GR.rem.p, nE, A + 1, sym_bits, K, keys.p, ids.p);
+    }
+    u64 lo = 0, hi = 0;
+    int hi_open = 1;
+    {
+        const u64 ns = std::min<u64>(nE, 1ull << 16), stride = std::max<u64>(1, nE / ns);
+        DevBuf<u64> sk(ns, st), sk2(ns, st);
+        DevBuf<u32> sv(ns, st), sv2(ns, st);
+        GRL_LAUNCH("key_sample", 0, key_sample_kernel, grid_for(ns, 256), 256, 0, st, keys.p, nE, stride, ns, sk.p, sv.p);
+        u64 *a = sk.p, *b = sk2.p;
+        u32 *av = sv.p, *bv = sv2.p;
+        radix_sort_pairs(&a, &av, &b, &bv, ns, key_bits, st);
+        std::vector<u64> hs(ns);
+        GRL_CUDA(cudaMemcpyAsync(hs.data(), a, ns * 8, cudaMemcpyDeviceToHost, st));
+        GRL_CUDA(cudaStreamSynchronize(st));
+        auto splitter = [&](int r) { return hs[(size_t)((u64)r * ns / (u64)n_ranks)]; };
+        lo = rank_id == 0 ? 0 : splitter(rank_id);
+        if (rank_id + 1 < n_ranks) { hi = splitter(rank_id + 1); hi_open = 0; }
+    }
+    // my entries
+    DevBuf<u64> mk, mk_alt;
+    DevBuf<u32> mv, mv_alt;
+    u64 nL = 0;
+    {
+        DevBuf<u32> flags(nE, st), excl(nE, st), cnt(1, st);
+        GRL_LAUNCH("key_range_flags", nE * 12, key_range_flags_kernel, grid_for(nE, 256), 256, 0, st, keys.p, nE, lo, hi, hi_open, flags.p);
+        exclusive_scan<u32, u32>(flags.p, excl.p, nE, cnt.p, st);
+        nL = d2h_scalar(cnt.p, st);
+        mk.alloc(nL, st); mk_alt.alloc(nL, st); mv.alloc(nL, st); mv_alt.alloc(nL, st);
+        GRL_LAUNCH("key_range_compact", nE * 16, key_range_compact_kernel, grid_for(nE, 256), 256, 0, st, keys.p, flags.p, excl.p, nE, mk.p, mv.p);
+    }
+    keys.release();
+    M.nL = nL;
+    const u64 n_words = div_up(std::max<u64>(nL, 1), 32);
+    M.head_bits.alloc(n_words, st);
+    M.head_bits.zero();
+    u64 *kp = mk.p, *ka = mk_alt.p;
+    u32 *vp = mv.p, *va = mv_alt.p;
+    radix_sort_pairs(&kp, &vp, &ka, &va, nL, key_bits, st);
+    if (vp != mv.p) std::swap(mv, mv_alt);
+    M.order = std::move(mv);
+    mv_alt.release();
+    u32* order_w = M.order.p;
+    u64 nA = 0;
+    DevBuf<u32> apos;
+    if (nL) {
+        DevBuf<u32> flags(nL, st), active_bits(n_words, st);
+        GRL_LAUNCH("first_heads", nL * 12, first_heads_kernel, grid_for(nL, 256), 256, 0, st, kp, nL, sym_bits, A + 1, flags.p, M.head_bits.p, active_bits.p);
+        BitmapCompactor ac;
+        nA = ac.count(active_bits.p, nL, st);
+        apos.alloc(nA, st);
+        if (nA) ac.write<u32>(nullptr, apos.p);
+    }
+    mk.release(); mk_alt.release();
+    u64 dpt = (u64)K;
+    while (nA > 0) {  // refinement by key extension: local to the dictionary text, no exchange needed
+        if (dpt > GR.max_len + 1) throw Error(GRLGPU_ERR_STATE, "suffix refinement did not converge");
+        DevBuf<u64> ak(nA, st), ak_alt(nA, st), nk(nA, st);
+        DevBuf<u32> av(nA, st), av_alt(nA, st), ev(nA, st), gflag(nA, st), gexcl(nA, st), flags(nA, st), excl(nA, st), cnt(1, st);
+        u64 *akp = ak.p, *aka = ak_alt.p;
+        u32 *avp = av.p, *ava = av_alt.p;
+        GRL_LAUNCH("ext_keys", nA * 48, (ext_keys_kernel<SymT>), grid_for(nA, 256), 256, 0, st, apos.p, order_w, D, GR.rem.p, M.head_bits.p, nA, dpt, A + 1, sym_bits, K, akp, avp,
+                   nk.p, ev.p, gflag.p);
+        exclusive_scan<u32, u32>(gflag.p, gexcl.p, nA, cnt.p, st);
+        const u64 n_groups = d2h_scalar(cnt.p, st);
+        radix_sort_pairs(&akp, &avp, &aka, &ava, nA, key_bits, st);
+        GRL_LAUNCH("ext_group_keys", nA * 16, ext_group_keys_kernel, grid_for(nA, 256), 256, 0, st, avp, gflag.p, gexcl.p, nA, akp);
+        radix_sort_pairs(&akp, &avp, &aka, &ava, nA, std::max(1, bit_width64(n_groups)), st);
+        GRL_LAUNCH("ext_heads", nA * 24, ext_heads_kernel, grid_for(nA, 256), 256, 0, st, avp, akp, nk.p, nA, flags.p);
+        GRL_LAUNCH("ext_writeback", nA * 16, ext_writeback_kernel, grid_for(nA, 256), 256, 0, st, apos.p, avp, ev.p, flags.p, nA, order_w, M.head_bits.p);
+        dpt += (u64)K;
+        GRL_LAUNCH("ext_next", nA * 16, ext_next_kernel, grid_for(nA, 256), 256, 0, st, apos.p, avp, ev.p, M.head_bits.p, GR.rem.p, nA, nL, dpt, flags.p);
+        exclusive_scan<u32, u32>(flags.p, excl.p, nA, cnt.p, st);
+        const u64 nA2 = d2h_scalar(cnt.p, st);
+        DevBuf<u32> apos2(nA2, st);
+        if (nA2) GRL_LAUNCH("compact_apos", nA * 12, compact_apos_kernel, grid_for(nA, 256), 256, 0, st, flags.p, excl.p, apos.p, nA, apos2.p);
+        apos = std::move(apos2);
+        nA = nA2;
+    }
+    // groups of my slice
+    M.head_pref.alloc(n_words, st);
+    u64 G = 0;
+    {
+        DevBuf<u32> wc(n_words, st), gtot(1, st);
+        GRL_LAUNCH("popc_words", n_words * 8, popc_words_kernel, grid_for(n_words, 256), 256, 0, st, M.head_bits.p, n_words, wc.p);
+        exclusive_scan<u32, u32>(wc.p, M.head_pref.p, n_words, gtot.p, st);
+        G = nL ? d2h_scalar(gtot.p, st) : 0;
+    }
+    M.G = G;
+    M.gcnt.alloc(G, st); M.grep.alloc(G, st); M.rflag.alloc(G, st); M.rrank.alloc(G, st);
+    M.full_bits.alloc(n_words, st);
+    M.full_bits.zero();
+    DevBuf<u32> ghead(G, st), vflag(G, st), vidx(G, st);
+    DevBuf<u64> gacc(G, st), gmin(G, st), gmax(G, st), psym(G, st);
+    M.gcnt.zero(); gacc.zero(); gmax.zero(); gmin.fill_ff();
+    GRL_LAUNCH("group_reduce", nL * 24 + G * 32, group_reduce_kernel, grid_for(nL, 256), 256, 0, st, M.order.p, M.head_bits.p, M.head_pref.p, GR.einfo.p, nL, M.gcnt.p, gacc.p, gmin.p,
+               gmax.p, M.grep.p, ghead.p, M.full_bits.p);
+    GR.einfo.release();
+    const u64 bwt_dummy = A + 1, hocc_dummy = A + 2;
+    GRL_LAUNCH("group_finalize", 0, group_finalize_kernel, grid_for(G, 256), 256, 0, st, M.gcnt.p, gmin.p, gmax.p, G, bwt_dummy, hocc_dummy, M.rflag.p, vflag.p, psym.p);
+    DevBuf<u32> cnt2(2, st);
+    exclusive_scan<u32, u32>(M.rflag.p, M.rrank.p, G, cnt2.p, st);
+    exclusive_scan<u32, u32>(vflag.p, vidx.p, G, cnt2.p + 1, st);
+    u32 hc[2];
+    GRL_CUDA(cudaMemcpyAsync(hc, cnt2.p, 8, cudaMemcpyDeviceToHost, st));
+    GRL_CUDA(cudaStreamSynchronize(st));
+    M.tot_local = hc[0];
+    const u64 nV = hc[1];
+    {   // preliminary BWT of my slice: maximal runs over my valid groups (the caller merges across rank boundaries)
+        DevBuf<u64> csym(nV, st), clen(nV, st);
+        GRL_LAUNCH("prebwt_compact", 0, prebwt_compact_kernel, grid_for(G, 256), 256, 0, st, vflag.p, vidx.p, psym.p, gacc.p, G, csym.p, clen.p);
+        DevBuf<u32> hflag(nV, st), hexcl(nV, st), nrun(1, st);
+        GRL_LAUNCH("key_head_flags", 0, key_head_flags_kernel, grid_for(nV, 256), 256, 0, st, csym.p, nV, hflag.p);
+        exclusive_scan<u32, u32>(hflag.p, hexcl.p, nV, nrun.p, st);
+        M.n_pre_local = nV ? d2h_scalar(nrun.p, st) : 0;
+        M.sl_pre_sym.alloc(M.n_pre_local * sizeof(SymT), st);
+        M.sl_pre_len.alloc(M.n_pre_local, st);
+        M.sl_pre_len.zero();
+        GRL_LAUNCH("prebwt_runs", 0, (prebwt_runs_kernel<SymT>), grid_for(nV, 256), 256, 0, st, csym.p, clen.p, hflag.p, hexcl.p, nV, (SymT*)M.sl_pre_sym.p, M.sl_pre_len.p);
+    }
+    GRL_CUDA(cudaStreamSynchronize(st));
+    info[0] = 1; info[1] = M.tot_local; info[2] = M.n_pre_local; info[3] = nE; info[4] = sizeof(SymT);
+}
+
+template <class CellT, bool FIRST>
+void mg_rank_sort_t(grlgpu_ctx* c, const u32* lens, const u64* freqs, const void* cells, u64 d, u64 n_cells, int rank_id, int n_ranks, u64* info) {
+    MgRound& M = *c->mg;
+    M.t_dict.start();
+    M.GR.reset(new Round(c));
+    Round& GR = *M.GR;
+    mg_setup_global(c, GR, lens, freqs, cells, d, n_cells);
+    M.g_cells = cells;
+    const int sym_bits = bit_width64(c->alphabet + 1);
+    const u64 K = (u64)std::max(1, 64 / sym_bits);
+    const bool ext_ok = (GR.max_len + 1 + K - 1) / K <= 64;
+    const bool big = GR.nE >= (1ull << 22) || (c->flags & GRLGPU_FLAG_FORCE_DIST_RANK);
+    info[0] = 0; info[1] = info[2] = 0; info[3] = GR.nE; info[4] = 4;
+    if (!ext_ok || !big || n_ranks < 2) { M.GR.reset(); return; }  // small or long-phrase dictionaries: replicated ranking
+    const bool wide = (c->alphabet + GR.nE + 8) >= (1ull << 32);
+    if (wide) mg_rank_sort_sym<CellT, FIRST, u64>(c, lens, freqs, cells, d, n_cells, rank_id, n_ranks, info);
+    else mg_rank_sort_sym<CellT, FIRST, u32>(c, lens, freqs, cells, d, n_cells, rank_id, n_ranks, info);
+}
+
+// step 2: with the global rank offset of this rank known, write my share of the global per-phrase metasymbols, of the
+// next round's is_suffix and of the hocc marks (rank + 1) into caller-owned, zero-initialised device arrays
+template <class SymT>
+void mg_rank_apply_sym(grlgpu_ctx* c, u64 rank_base, u64* g_meta, u8* is_suffix_next, u32* erank1) {
+    MgRound& M = *c->mg;
+    Round& GR = *M.GR;
+    cudaStream_t st = c->st;
+    IsSuffix isuf{c->is_suffix.p, c->sep, c->first};
+    DevBuf<u32> ginfo(M.G, st);
+    GRL_LAUNCH("pack_ginfo_dense", M.G * 16, pack_ginfo_dense_kernel, grid_for(M.G, 256), 256, 0, st, M.gcnt.p, M.rflag.p, M.rrank.p, M.G, ginfo.p);
+    GRL_LAUNCH("group_apply", M.nL * 16, (group_apply_kernel<SymT>), grid_for(M.nL, 256), 256, 0, st, M.order.p, M.head_bits.p, M.head_pref.p, M.full_bits.p, ginfo.p,
+               (const SymT*)GR.D_raw.p, GR.rem.p, GR.phr_of.p, GR.ph_freq.p, (const u32*)nullptr, M.nL, isuf, rank_base, 1u, (ulonglong2*)nullptr, g_meta, is_suffix_next, erank1);
+    GRL_CUDA(cudaStreamSynchronize(st));
+}
+
+// step 3 (after the caller all-reduced the three arrays with MAX): rules of my ranked groups, local rewrite
+template <class CellT, class SymT>
+void mg_rank_finish_sym(grlgpu_ctx* c, u64 rank_base, u64 tot, u64 n_pre_global, const u64* g_meta, const u8* is_suffix_next, u32* erank1, int done_global, grlgpu_round_t* out) {
+    MgRound& M = *c->mg;
+    Round& GR = *M.GR;
+    cudaStream_t st = c->st;
+    const u64 A = c->alphabet;
+    IsSuffix isuf{c->is_suffix.p, c->sep, c->first};
+    GRL_LAUNCH("erank_decode", GR.nE * 8, erank_decode_kernel, grid_for(GR.nE, 256), 256, 0, st, erank1, GR.nE);
+    M.sl_rule_l.alloc(M.tot_local * sizeof(SymT), st);
+    M.sl_rule_r.alloc(M.tot_local * sizeof(SymT), st);
+    M.sl_has_hocc.alloc(M.tot_local, st);
+    const u64 alph3 = A + 3, metasym_dummy = alph3 + tot + 1;
+    GRL_LAUNCH("rules", 0, (rules_kernel<SymT>), grid_for(M.G, 256), 256, 0, st, M.gcnt.p, M.rflag.p, M.rrank.p, M.grep.p, M.G, (const SymT*)GR.D_raw.p, GR.rem.p, erank1, isuf, alph3,
+               metasym_dummy, (SymT*)M.sl_rule_l.p, (SymT*)M.sl_rule_r.p, M.sl_has_hocc.p);
+    (void)rank_base;
+    // the next round's is_suffix is global
+    DevBuf<u8> isn(tot, st);
+    GRL_CUDA(cudaMemcpyAsync(isn.p, is_suffix_next, tot, cudaMemcpyDeviceToDevice, st));
+    c->lvl_sym_bytes = sizeof(SymT);
+    mg_map_and_rewrite<CellT>(c, M, GR, M.g_cells, g_meta, tot, n_pre_global, done_global, out);
+    c->is_suffix = std::move(isn);
+    c->rule_l.release(); c->rule_r.release(); c->has_hocc.release(); c->pre_sym.release(); c->pre_len.release();  // level artefacts live in slices this round
+    c->lvl_tot = 0; c->lvl_npre = 0;
+    // keep only the slices (until grlgpu_mg_level_slice / the next round)
+    M.GR.reset();
+    M.order.release(); M.head_bits.release(); M.head_pref.release(); M.full_bits.release();
+    M.gcnt.release(); M.grep.release(); M.rflag.release(); M.rrank.release();
+}
+
+template <class CellT, bool FIRST>
+void mg_global_t(grlgpu_ctx* c, const u32* lens, const u64* freqs, const void* cells, u64 d, u64 n_cells, int done_global, grlgpu_round_t* out) {
+    MgRound& M = *c->mg;
+    cudaStream_t st = c->st;
+    if (!M.GR) M.t_dict.start();
+    // the global dictionary (identical on every rank), ranked here in full (replicated ranking)
+    Round GR(c);
+    mg_setup_global(c, GR, lens, freqs, cells, d, n_cells);
+    DevBuf<u64> g_meta(d, st);
+    GR.ph_meta = g_meta.p;
+    const bool wide = (c->alphabet + GR.nE + 8) >= (1ull << 32);
+    if (wide) { stage_gather<CellT, FIRST, u64>(GR); stage_dict<u64>(GR); }
+    else { stage_gather<CellT, FIRST, u32>(GR); stage_dict<u32>(GR); }
+    mg_map_and_rewrite<CellT>(c, M, GR, cells, g_meta.p, GR.tot, GR.n_pre, done_global, out);
     delete c->mg;
     c->mg = nullptr;
 }
@@ -1159,6 +1391,48 @@ int grlgpu_mg_global(grlgpu_ctx* ctx, const uint32_t* d_lens, const uint64_t* d_
     if (!ctx || !out || !d_lens || !d_freqs || !d_cells || d == 0) return GRLGPU_ERR_ARG;
     if (!ctx->mg) return GRLGPU_ERR_STATE;
     return guarded(ctx, [&] { MG_DISPATCH_FIRST(mg_global_t, ctx, d_lens, (const u64*)d_freqs, d_cells, (u64)d, (u64)n_cells, done_global, out); });
+}
+
+int grlgpu_mg_rank_sort(grlgpu_ctx* ctx, const uint32_t* d_lens, const uint64_t* d_freqs, const void* d_cells, uint64_t d, uint64_t n_cells, int rank_id, int n_ranks,
+                        uint64_t* info5) {
+    if (!ctx || !info5 || !d_lens || !d_freqs || !d_cells || d == 0 || rank_id < 0 || rank_id >= n_ranks) return GRLGPU_ERR_ARG;
+    if (!ctx->mg) return GRLGPU_ERR_STATE;
+    return guarded(ctx, [&] { MG_DISPATCH_FIRST(mg_rank_sort_t, ctx, d_lens, (const u64*)d_freqs, d_cells, (u64)d, (u64)n_cells, rank_id, n_ranks, (u64*)info5); });
+}
+int grlgpu_mg_rank_apply(grlgpu_ctx* ctx, uint64_t rank_base, uint64_t* d_ph_meta, uint8_t* d_is_suffix_next, uint32_t* d_erank1) {
+    if (!ctx || !d_ph_meta || !d_is_suffix_next || !d_erank1) return GRLGPU_ERR_ARG;
+    if (!ctx->mg || !ctx->mg->GR) return GRLGPU_ERR_STATE;
+    return guarded(ctx, [&] {
+        if (ctx->mg->sym_bytes == 8) mg_rank_apply_sym<u64>(ctx, rank_base, (u64*)d_ph_meta, d_is_suffix_next, d_erank1);
+        else mg_rank_apply_sym<u32>(ctx, rank_base, (u64*)d_ph_meta, d_is_suffix_next, d_erank1);
+    });
+}
+extern "C++" {
+template <class CellT>
+static void mg_rank_finish_cell(grlgpu_ctx* ctx, u64 rank_base, u64 tot, u64 n_pre, const u64* m, const u8* s, u32* e, int done, grlgpu_round_t* out) {
+    if (ctx->mg->sym_bytes == 8) mg_rank_finish_sym<CellT, u64>(ctx, rank_base, tot, n_pre, m, s, e, done, out);
+    else mg_rank_finish_sym<CellT, u32>(ctx, rank_base, tot, n_pre, m, s, e, done, out);
+}
+}
+int grlgpu_mg_rank_finish(grlgpu_ctx* ctx, uint64_t rank_base, uint64_t tot, uint64_t n_pre_runs, const uint64_t* d_ph_meta, const uint8_t* d_is_suffix_next,
+                          uint32_t* d_erank1, int done_global, grlgpu_round_t* out) {
+    if (!ctx || !out || !d_ph_meta || !d_is_suffix_next || !d_erank1) return GRLGPU_ERR_ARG;
+    if (!ctx->mg || !ctx->mg->GR) return GRLGPU_ERR_STATE;
+    return guarded(ctx, [&] { MG_DISPATCH(mg_rank_finish_cell, ctx, (u64)rank_base, (u64)tot, (u64)n_pre_runs, (const u64*)d_ph_meta, d_is_suffix_next, d_erank1, done_global, out); });
+}
+int grlgpu_mg_level_slice(grlgpu_ctx* ctx, void* d_rule_l, void* d_rule_r, uint8_t* d_has_hocc, void* d_pre_sym, uint64_t* d_pre_len) {
+    if (!ctx) return GRLGPU_ERR_ARG;
+    if (!ctx->mg) return GRLGPU_ERR_STATE;
+    return guarded(ctx, [&] {
+        MgRound& M = *ctx->mg;
+        const u64 sb = (u64)M.sym_bytes;
+        if (d_rule_l) GRL_CUDA(cudaMemcpyAsync(d_rule_l, M.sl_rule_l.p, M.tot_local * sb, cudaMemcpyDeviceToDevice, ctx->st));
+        if (d_rule_r) GRL_CUDA(cudaMemcpyAsync(d_rule_r, M.sl_rule_r.p, M.tot_local * sb, cudaMemcpyDeviceToDevice, ctx->st));
+        if (d_has_hocc) GRL_CUDA(cudaMemcpyAsync(d_has_hocc, M.sl_has_hocc.p, M.tot_local, cudaMemcpyDeviceToDevice, ctx->st));
+        if (d_pre_sym) GRL_CUDA(cudaMemcpyAsync(d_pre_sym, M.sl_pre_sym.p, M.n_pre_local * sb, cudaMemcpyDeviceToDevice, ctx->st));
+        if (d_pre_len) GRL_CUDA(cudaMemcpyAsync(d_pre_len, M.sl_pre_len.p, M.n_pre_local * 8, cudaMemcpyDeviceToDevice, ctx->st));
+        GRL_CUDA(cudaStreamSynchronize(ctx->st));
+    });
 }
 
 int grlgpu_profile_enable(grlgpu_ctx* ctx, int on) {

@@ -75,8 +75,24 @@ class GpuEngine:
     def global_round(self, lens, freqs, cells, d, n_cells, done):
         return self.ctx.mg_global(lens.data_ptr(), freqs.data_ptr(), cells.data_ptr(), d, n_cells, done)
 
-    def fetch_level(self):
-        return self.ctx.fetch_level()
+    def rank_sort(self, lens, freqs, cells, d, n_cells, rank_id, n_ranks):
+        return self.ctx.mg_rank_sort(lens.data_ptr(), freqs.data_ptr(), cells.data_ptr(), d, n_cells, rank_id, n_ranks)
+
+    def rank_apply(self, rank_base, ph_meta, isn, erank1):
+        self.ctx.mg_rank_apply(rank_base, ph_meta.data_ptr(), isn.data_ptr(), erank1.data_ptr())
+
+    def rank_finish(self, rank_base, tot, n_pre, ph_meta, isn, erank1, done):
+        return self.ctx.mg_rank_finish(rank_base, tot, n_pre, ph_meta.data_ptr(), isn.data_ptr(), erank1.data_ptr(), done)
+
+    def level_slice(self, rl, rr, hh, ps, pl):
+        self.ctx.mg_level_slice(rl.data_ptr(), rr.data_ptr(), hh.data_ptr(), ps.data_ptr(), pl.data_ptr())
+
+    level_override = None  # set by distributed_round when the level was assembled from per-rank slices
+
+    def fetch_level(self, *a, **k):
+        if self.level_override is not None:
+            return self.level_override
+        return self.ctx.fetch_level(*a, **k)
 
     def fetch_parse(self):
         return self.ctx.fetch_parse()
@@ -151,7 +167,52 @@ def _all_gather_v(part, counts, engine):
     return out
 
 
-def distributed_round(engine, n_strings_global: int, timings: dict | None = None):
+def _ranked_distributed(engine, glens, gfreqs, gcells, d, n_cells, done, info5, want_level):
+    """the dictionary ranking split over the ranks by first-key range (grlgpu_mg_rank_*): two small all-gathers,
+    three all-reduce(MAX), and -- only when the level is wanted -- an all-gather-v of the level slices"""
+    G, me = dist.get_world_size(), dist.get_rank()
+    n_ranked, n_pre_loc, nE, sym_bytes = info5[1:5]
+    allc = _all_gather_small(torch.tensor([n_ranked, n_pre_loc], dtype=torch.int64, device=engine.device))
+    ranked_counts = [int(x[0]) for x in allc]
+    pre_counts = [int(x[1]) for x in allc]
+    base, tot = sum(ranked_counts[:me]), sum(ranked_counts)
+    ph_meta = engine.alloc(d, torch.int64).zero_()
+    isn = engine.alloc(tot, torch.uint8).zero_()
+    erank1 = engine.alloc(nE, torch.int32).zero_()
+    if ph_meta.is_cuda:
+        torch.cuda.synchronize(ph_meta.device)
+    engine.rank_apply(base, ph_meta, isn, erank1)
+    for t in (ph_meta, isn, erank1):
+        _all_reduce(t, dist.ReduceOp.MAX)
+        _fence(t)
+    info = engine.rank_finish(base, tot, sum(pre_counts), ph_meta, isn, erank1, done)
+    engine.level_override = None
+    if want_level:
+        st = torch.int32 if sym_bytes == 4 else torch.int64
+        rl, rr = engine.alloc(n_ranked, st), engine.alloc(n_ranked, st)
+        hh = engine.alloc(n_ranked, torch.uint8)
+        ps, pl = engine.alloc(n_pre_loc, st), engine.alloc(n_pre_loc, torch.int64)
+        engine.level_slice(rl, rr, hh, ps, pl)
+        RL, RR, HH = _all_gather_v(rl, ranked_counts, engine), _all_gather_v(rr, ranked_counts, engine), _all_gather_v(hh, ranked_counts, engine)
+        PS, PL = _all_gather_v(ps, pre_counts, engine), _all_gather_v(pl, pre_counts, engine)
+        if me == 0:
+            npre = sum(pre_counts)
+            mask = 0xFFFFFFFF if sym_bytes == 4 else 0x7FFFFFFFFFFFFFFF  # int32 tensors carry u32 bit patterns
+            s = PS[:npre].cpu().numpy().astype(np.int64) & mask
+            l = PL[:npre].cpu().numpy().astype(np.uint64)
+            if npre:  # equal symbols can only meet where two ranks' slices meet
+                keep = np.flatnonzero(np.concatenate(([True], s[1:] != s[:-1])))
+                l = np.add.reduceat(l, keep)
+                s = s[keep]
+            engine.level_override = {"rule_l": (RL[:tot].cpu().numpy().astype(np.int64) & mask).astype(np.uint64),
+                                     "rule_r": (RR[:tot].cpu().numpy().astype(np.int64) & mask).astype(np.uint64),
+                                     "has_hocc": HH[:tot].cpu().numpy().astype(np.uint8), "pre_sym": s.astype(np.uint64), "pre_len": l}
+            info["n_pre_runs"] = int(s.size)
+    info["ranking"] = "distributed"
+    return info
+
+
+def distributed_round(engine, n_strings_global: int, timings: dict | None = None, want_level: bool = True):
     """One parse round over all ranks. -> (round info dict, done)"""
     G = dist.get_world_size()
     w = engine.cell_bytes()
@@ -193,7 +254,14 @@ def distributed_round(engine, n_strings_global: int, timings: dict | None = None
     gcells = _all_gather_v(pcells, [c * w for c in g_cel], engine)
     gathered = (sum(g_phr) * 12 + sum(g_cel) * w)
 
-    info = engine.global_round(glens, gfreqs, gcells, sum(g_phr), sum(g_cel), done)
+    info5 = engine.rank_sort(glens, gfreqs, gcells, sum(g_phr), sum(g_cel), dist.get_rank(), G) if hasattr(engine, "rank_sort") else [0] * 5
+    if info5[0]:
+        info = _ranked_distributed(engine, glens, gfreqs, gcells, sum(g_phr), sum(g_cel), done, info5, want_level)
+    else:
+        info = engine.global_round(glens, gfreqs, gcells, sum(g_phr), sum(g_cel), done)
+        info["ranking"] = "replicated"
+        if hasattr(engine, "level_override"):
+            engine.level_override = None
     info["exchange_bytes_sent"] = exchanged
     info["gather_bytes"] = gathered
     if timings is not None:
@@ -244,7 +312,7 @@ def par_phase_distributed(engine, collect_levels: bool = True):
     gstats = global_stats(engine)
     levels, rounds = [], []
     while True:
-        info, done = distributed_round(engine, gstats["n_strings"])
+        info, done = distributed_round(engine, gstats["n_strings"], want_level=collect_levels)
         rounds.append(info)
         if collect_levels and me == 0:
             L = engine.fetch_level()

@@ -34,6 +34,7 @@ enum grlgpu_status {
 #define GRLGPU_FLAG_FORCE_UNCACHED 8ull /* tests: dedup every phrase with the thread-per-phrase kernel (no cached tiles) */
 #define GRLGPU_FLAG_SMALL_PILOT 16ull /* tests: one pilot tile, so small inputs exercise pilot + remainder */
 #define GRLGPU_FLAG_FORCE_DOUBLING 32ull /* tests: refine suffix groups by prefix doubling even when key extension would do */
+#define GRLGPU_FLAG_FORCE_DIST_RANK 64ull /* tests: distribute the dictionary ranking over the ranks even for tiny dictionaries */
 #define GRLGPU_FLAG_KEEP_DICT 4ull /* tests: keep the last round's dictionary for grlgpu_fetch_dictionary */
 
 /* = str_collection (external/cdt/include/utils.h:20-28) as filled by collection_stats (utils.cpp:100-189) */
@@ -151,6 +152,25 @@ int grlgpu_mg_merge(grlgpu_ctx* ctx, const uint32_t* d_lens, const uint64_t* d_c
 int grlgpu_mg_pack_part(grlgpu_ctx* ctx, uint32_t* d_lens, uint64_t* d_freqs, void* d_cells);
 int grlgpu_mg_global(grlgpu_ctx* ctx, const uint32_t* d_lens, const uint64_t* d_freqs, const void* d_cells, uint64_t d, uint64_t n_cells,
                      int done_global, grlgpu_round_t* out);
+
+/* Distributed ranking of the gathered dictionary (optional; replaces grlgpu_mg_global when info5[0] comes back 1).
+ * Every rank sorts, refines and groups only the suffix entries whose first key falls in its range (splitters from
+ * a regular sample, identical on every rank), so the dominant cost of unique-heavy rounds shrinks with the ranks:
+ *   grlgpu_mg_rank_sort    -> info5 = {distributed?, ranked groups here, pre-BWT runs here, dictionary entries nE, symbol bytes}
+ *                             (0 in info5[0]: nothing was done -- small or long-phrase dictionary -- call grlgpu_mg_global)
+ *   caller: rank_base = exclusive prefix of the ranked-group counts over the ranks, tot = their sum; allocates
+ *           zero-filled device arrays ph_meta[d] (u64), is_suffix_next[tot] (u8), erank1[nE] (u32)
+ *   grlgpu_mg_rank_apply   writes this rank's share into them (hocc marks as rank + 1)   -> all-reduce(MAX) of the three
+ *   grlgpu_mg_rank_finish  rules of this rank's groups, metasymbols of the local phrases, rewrite of the shard
+ *   grlgpu_mg_level_slice  this rank's slice of the level artefacts into caller DEVICE buffers (rules / has_hocc: info5[1]
+ *                          entries, positions [rank_base, rank_base + info5[1]); pre-BWT: info5[2] runs, to be
+ *                          concatenated in rank order, merging equal symbols where two ranks meet) */
+int grlgpu_mg_rank_sort(grlgpu_ctx* ctx, const uint32_t* d_lens, const uint64_t* d_freqs, const void* d_cells, uint64_t d, uint64_t n_cells, int rank_id,
+                        int n_ranks, uint64_t* info5);
+int grlgpu_mg_rank_apply(grlgpu_ctx* ctx, uint64_t rank_base, uint64_t* d_ph_meta, uint8_t* d_is_suffix_next, uint32_t* d_erank1);
+int grlgpu_mg_rank_finish(grlgpu_ctx* ctx, uint64_t rank_base, uint64_t tot, uint64_t n_pre_runs, const uint64_t* d_ph_meta, const uint8_t* d_is_suffix_next,
+                          uint32_t* d_erank1, int done_global, grlgpu_round_t* out);
+int grlgpu_mg_level_slice(grlgpu_ctx* ctx, void* d_rule_l, void* d_rule_r, uint8_t* d_has_hocc, void* d_pre_sym, uint64_t* d_pre_len);
 
 /* launch accounting: number of kernel launches issued by this context so far, and (after
  * grlgpu_profile_enable(ctx, 1)) per-kernel CUDA-event durations measured live on the launch stream.

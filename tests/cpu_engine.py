@@ -206,7 +206,112 @@ class CpuEngine:
         self.A, self.is_suffix = tot, new_suffix
         return info
 
+    # ---- the same round with the ranking split over the ranks (contiguous slices of the sorted suffix groups) ----
+    def _global_groups(self, lens, freqs, cells, d, n_cells):
+        ph, fr = self._unpack(lens, freqs, cells, d, n_cells)
+        vals = [tuple(self._val(c) for c in p) for p in ph]
+        off, o = [], 0
+        for p in vals:
+            off.append(o)
+            o += len(p)
+        groups = {}
+        for idx, (p, f) in enumerate(zip(vals, fr)):
+            for k in range(len(p)):
+                suf = p[k:]
+                if len(suf) == 1 and not self._suffix(suf[0]):
+                    continue
+                g = groups.setdefault(suf, {"left": set(), "full": None, "n": 0, "freq": 0, "members": []})
+                g["n"] += 1
+                g["freq"] += f
+                g["members"].append(off[idx] + k)
+                if k == 0:
+                    g["full"] = idx
+                    g["left"].add(-1)
+                else:
+                    g["left"].add(p[k - 1])
+        order = sorted(groups, key=functools.cmp_to_key(cmp_pg))
+        return ph, vals, fr, off, o, groups, order
+
+    def rank_sort(self, lens, freqs, cells, d, n_cells, rank_id, n_ranks):
+        if not getattr(self, "distribute", False):
+            return [0, 0, 0, 0, 8]
+        ph, vals, fr, off, nE, groups, order = self._global_groups(lens, freqs, cells, d, n_cells)
+        lo, hi = rank_id * len(order) // n_ranks, (rank_id + 1) * len(order) // n_ranks
+        A = self.A
+        mine, pre = [], []
+        for suf in order[lo:hi]:
+            g = groups[suf]
+            ranked = len(g["left"]) > 1 or g["full"] is not None
+            sym = (A + 2 if g["n"] > 1 else A + 1) if ranked else next(iter(g["left"]))
+            if ranked:
+                mine.append(suf)
+            if pre and pre[-1][0] == sym:
+                pre[-1][1] += g["freq"]
+            else:
+                pre.append([sym, g["freq"]])
+        self._dist = {"ph": ph, "vals": vals, "fr": fr, "off": off, "groups": groups, "mine": mine, "pre": pre}
+        return [1, len(mine), len(pre), nE, 8]
+
+    def rank_apply(self, rank_base, ph_meta, isn, erank1):
+        D = self._dist
+        for u, suf in enumerate(D["mine"]):
+            g, r = D["groups"][suf], rank_base + u
+            if g["full"] is not None:
+                idx = g["full"]
+                ph_meta[idx] = (r << 1) | (1 if D["fr"][idx] > 1 else 0)
+                isn[r] = 1 if self._suffix(suf[-1]) else 0
+            if g["n"] > 1:
+                for e in g["members"]:
+                    erank1[e] = r + 1
+
+    def rank_finish(self, rank_base, tot, n_pre, ph_meta, isn, erank1, done):
+        D, A = self._dist, self.A
+        alph3, dummy = A + 3, A + 3 + tot + 1
+        rl, rr, hh = [], [], []
+        for suf in D["mine"]:
+            g = D["groups"][suf]
+            hh.append(1 if g["n"] > 1 else 0)
+            e0 = g["members"][0]
+            if len(suf) == 1:
+                rl.append(dummy); rr.append(suf[0]); continue
+            k = 1
+            while True:
+                marked = int(erank1[e0 + k]) != 0
+                if marked or k == len(suf) - 1:
+                    break
+                k += 1
+            if marked:
+                rl.append(suf[k - 1]); rr.append(alph3 + int(erank1[e0 + k]) - 1)
+            else:
+                rl.append(dummy); rr.append(suf[-1] if self._suffix(suf[-1]) else suf[-2])
+        self._slice = {"rule_l": rl, "rule_r": rr, "has_hocc": hh, "pre_sym": [p[0] for p in D["pre"]], "pre_len": [p[1] for p in D["pre"]]}
+        gidx = {p: i for i, p in enumerate(D["ph"])}
+        per_str, cnt, _ = self._local
+        new_cells, new_ptrs = [], [0]
+        for phs in per_str:
+            for p in phs:
+                new_cells.append(int(ph_meta[gidx[p]]))
+            new_ptrs.append(len(new_cells))
+        bps = sym_width(tot) + 1
+        info = {"alphabet": A, "tot_phrases": tot, "n_phrases": len(D["ph"]), "dict_syms": sum(len(p) for p in D["ph"]), "parse_len": len(new_cells),
+                "n_in": len(self.cells), "done": int(done), "n_pre_runs": n_pre, "cell_bytes_out": 1 if bps <= 8 else 2 if bps <= 16 else 4 if bps <= 32 else 8}
+        self.cells, self.str_ptrs, self.first = new_cells, new_ptrs, False
+        self.w = info["cell_bytes_out"]
+        self.A = tot
+        self.is_suffix = {r: bool(int(isn[r])) for r in range(tot)}
+        return info
+
+    def level_slice(self, rl, rr, hh, ps, pl):
+        S = self._slice
+        for t, key in ((rl, "rule_l"), (rr, "rule_r"), (hh, "has_hocc"), (ps, "pre_sym"), (pl, "pre_len")):
+            if S[key]:
+                t[: len(S[key])] = torch.tensor(S[key], dtype=t.dtype)
+
+    level_override = None
+
     def fetch_level(self):
+        if self.level_override is not None:
+            return self.level_override
         return dict(self._level)
 
     def fetch_parse(self):

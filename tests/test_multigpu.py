@@ -46,7 +46,7 @@ def _case(name):
     raise KeyError(name)
 
 
-def _worker(rank, world, port, backend, engine_kind, names, out_path):
+def _worker(rank, world, port, backend, engine_kind, names, out_path, dist_rank=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import grlbwt_b200 as G
     from grlbwt_b200 import multigpu as M
@@ -63,12 +63,13 @@ def _worker(rank, world, port, backend, engine_kind, names, out_path):
             if engine_kind == "cpu":
                 from cpu_engine import CpuEngine
                 eng, ctx = CpuEngine(shard), None
+                eng.distribute = dist_rank
             else:
                 dev = rank if backend == "nccl" else 0
                 torch.cuda.set_device(dev)
                 stream = torch.cuda.Stream(device=dev)  # the library and torch's collectives share one stream
                 torch.cuda.set_stream(stream)
-                ctx = G.GrlGpu(dev, 0, stream=stream.cuda_stream)
+                ctx = G.GrlGpu(dev, G.FLAG_FORCE_DIST_RANK if dist_rank else 0, stream=stream.cuda_stream)
                 ctx.set_text(shard)
                 eng = M.GpuEngine(ctx, torch.device("cuda", dev))
             res = M.par_phase_distributed(eng)
@@ -81,7 +82,8 @@ def _worker(rank, world, port, backend, engine_kind, names, out_path):
                 fb = -(-int(st["max_sym_freq"]).bit_length() // 8)
                 raw = O.rl_bwt_bytes(syms, lens, sb, fb)
                 results[name] = {"sha": hashlib.sha256(raw).hexdigest(), "sb": sb, "fb": fb, "rounds": len(res["rounds"]),
-                                 "tot": [r["tot_phrases"] for r in res["rounds"]], "d": [r["n_phrases"] for r in res["rounds"]]}
+                                 "tot": [r["tot_phrases"] for r in res["rounds"]], "d": [r["n_phrases"] for r in res["rounds"]],
+                                 "ranking": [r.get("ranking") for r in res["rounds"]]}
             if ctx is not None:
                 ctx.close()
         if rank == 0:
@@ -92,9 +94,9 @@ def _worker(rank, world, port, backend, engine_kind, names, out_path):
         dist.destroy_process_group()
 
 
-def run_ranks(world, backend, engine_kind, names, tmp_path):
-    out = str(tmp_path / f"mg_{engine_kind}_{world}.json")
-    mp.spawn(_worker, args=(world, free_port(), backend, engine_kind, names, out), nprocs=world, join=True)
+def run_ranks(world, backend, engine_kind, names, tmp_path, dist_rank=False):
+    out = str(tmp_path / f"mg_{engine_kind}_{world}_{int(dist_rank)}.json")
+    mp.spawn(_worker, args=(world, free_port(), backend, engine_kind, names, out, dist_rank), nprocs=world, join=True)
     import json
     return json.load(open(out))
 
@@ -119,6 +121,15 @@ def test_distributed_rounds_gloo_cpu(golden, tmp_path, world):
     check(run_ranks(world, "gloo", "cpu", names, tmp_path), golden)
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_distributed_ranking_gloo_cpu(golden, tmp_path, world):
+    """the ranking itself split over the ranks (rank_sort / rank_apply / all-reduce / rank_finish / level slices)"""
+    names = [n for n in CPU_NAMES if not (world == 3 and n in ("long_phrases",))]
+    res = run_ranks(world, "gloo", "cpu", names, tmp_path, dist_rank=True)
+    check(res, golden)
+    assert all(r == "distributed" for v in res.values() for r in v["ranking"])
+
+
 def test_shard_bounds_whole_strings():
     from grlbwt_b200 import multigpu as M
     rng = np.random.default_rng(0)
@@ -140,3 +151,12 @@ GPU_NAMES = ["dna_500", "mutated_200x5k", "ac_short_3000", "with_empty", "only_e
 def test_distributed_rounds_gpu_two_ranks(golden, tmp_path):
     backend = "nccl" if torch.cuda.device_count() >= 2 else "gloo"
     check(run_ranks(2, backend, "gpu", GPU_NAMES, tmp_path), golden)
+
+
+@pytest.mark.gpu
+def test_distributed_ranking_gpu_two_ranks(golden, tmp_path):
+    """dictionary ranking partitioned by first-key range over 2 ranks, forced on small dictionaries too"""
+    backend = "nccl" if torch.cuda.device_count() >= 2 else "gloo"
+    res = run_ranks(2, backend, "gpu", GPU_NAMES, tmp_path, dist_rank=True)
+    check(res, golden)
+    assert any(r == "distributed" for v in res.values() for r in v["ranking"])
