@@ -342,8 +342,15 @@ def run_ours(args, rank, world, local_rank):
     if prof:
         name, (nl, ms, by) = max(prof.items(), key=lambda kv: kv[1][1])
         achieved = by / 1e9 / (ms / 1e3) if ms > 0 else 0.0
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+        if os.path.exists(tpath) and args.workload == "c2" and args.reads == 50_000_000 and world == 1:
+            tj = json.load(open(tpath))
+            if tj.get("kernel") == name:   # ncu DRAM bytes of the same kernel on the same workload, per launch
+                traffic, traffic_src = round(tj["traffic_bytes_per_launch"]), "profiles/r01_ncu_traffic.json (ncu dram__bytes_read+write, mean over the step's launches)"
         roof = {"bound": "hbm", "kernel": name, "launches_per_step": nl, "avg_launch_ms": round(ms / max(nl, 1), 4), "achieved": round(achieved, 1),
-                "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+                "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+                "bytes_per_launch": round(by / max(nl, 1)), "peak_source": peak_src,
                 "share_of_step": round(ms / sum(v[1] for v in prof.values()), 4),
                 "bytes_model": "expected DRAM bytes of the kernel's launches (SURVEY.md 8d traffic table; DESIGN.md kernels section)"}
     alg_bytes = sum(r["algorithmic_bytes"] for r in rounds_info)

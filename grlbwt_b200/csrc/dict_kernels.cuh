@@ -39,29 +39,55 @@ static __global__ void __launch_bounds__(256) dict_meta_kernel(const ulonglong2*
     ph_freq[i] = ent.y;
 }
 
-// einfo[e] = { left symbol + 1 (0 for the first symbol of a phrase), phrase frequency | valid << 63 | full << 62 }:
-// everything the group stage needs about an entry, in one 16-byte record, so that the pass over the
-// sorted order does a single random gather per entry.
-constexpr u64 EI_VALID = 1ULL << 63, EI_FULL = 1ULL << 62, EI_FREQ = (1ULL << 62) - 1;
+// einfo[e] = { left symbol + 1, phrase frequency | valid << 63 | full << 62 }: everything the group stage needs
+// about an entry, in one 16-byte record, so that the pass over the sorted order does a single random gather per
+// entry. The first symbol of a phrase has no left symbol; its first word carries instead where the phrase's
+// metasymbol goes (table slot, or phrase index in multi-GPU rounds) | is_suffix(last symbol) << 63.
+constexpr u64 EI_VALID = 1ULL << 63, EI_FULL = 1ULL << 62, EI_FREQ = (1ULL << 62) - 1, EI_SFX = 1ULL << 63;
 
+// One lane per phrase for the per-phrase reads; the entries of a warp's 32 consecutive phrases are consecutive too, so
+// the warp then walks them 32 at a time (lane = entry, owner phrase found by a 5-step search over the lanes' offsets)
+// and every store is fully coalesced.
 template <class CellT, bool FIRST, class SymT>
 __global__ void __launch_bounds__(256) dict_gather_kernel(const CellT* __restrict__ text, const u64* __restrict__ ph_pos, const u32* __restrict__ ph_len,
-                                                          const u32* __restrict__ ph_off, const u64* __restrict__ ph_freq, u64 d, IsSuffix is_suffix,
-                                                          SymT* __restrict__ D, u32* __restrict__ phr_of, u32* __restrict__ rem,
-                                                          ulonglong2* __restrict__ einfo) {
+                                                          const u32* __restrict__ ph_off, const u64* __restrict__ ph_freq,
+                                                          const u32* __restrict__ target_slots, u64 d, IsSuffix is_suffix, SymT* __restrict__ D,
+                                                          u32* __restrict__ phr_of, u32* __restrict__ rem, ulonglong2* __restrict__ einfo) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= d) return;
-    const u64 pos = ph_pos[i], freq = ph_freq[i];
-    const u32 len = ph_len[i], off = ph_off[i];
-    u64 prev = 0;
-    for (u32 k = 0; k < len; k++) {
-        const u64 v = cell_value<CellT, FIRST>(text[pos + k]);
-        D[off + k] = (SymT)v;
-        phr_of[off + k] = (u32)i;
-        rem[off + k] = len - 1 - k;
-        const bool valid = k + 1 < len || is_suffix(v);  // exact_par_phase.cpp:163
-        einfo[off + k] = make_ulonglong2(k ? prev + 1 : 0ULL, freq | (valid ? EI_VALID : 0ULL) | (k == 0 ? EI_FULL : 0ULL));
-        prev = v;
+    const u32 lane = lane_id();
+    const u32 nvalid = __popc(__ballot_sync(0xffffffffu, i < d));  // valid lanes are a prefix of the warp
+    if (nvalid == 0) return;
+    u64 pos = 0, freq = 0, tgt = 0;
+    u32 len = 0, off = 0;
+    if (i < d) {
+        pos = ph_pos[i]; freq = ph_freq[i]; len = ph_len[i]; off = ph_off[i];
+        const bool sfx_last = len && is_suffix(cell_value<CellT, FIRST>(text[pos + len - 1]));  // :443
+        tgt = (target_slots ? (u64)target_slots[i] : i) | (sfx_last ? EI_SFX : 0ULL);
+    }
+    const u32 base = __shfl_sync(0xffffffffu, off, 0);
+    const u32 total = __shfl_sync(0xffffffffu, off + len, nvalid - 1) - base;
+    const u32 rel = off - base;
+    for (u32 j0 = 0; j0 < total; j0 += 32) {
+        const u32 j = j0 + lane;
+        u32 q = 0;
+#pragma unroll
+        for (int s = 16; s; s >>= 1) {
+            const u32 cand = q + s;
+            const u32 r = __shfl_sync(0xffffffffu, rel, cand & 31);
+            if (cand < nvalid && r <= j) q = cand;
+        }
+        const u64 qpos = __shfl_sync(0xffffffffu, pos, q), qfreq = __shfl_sync(0xffffffffu, freq, q), qtgt = __shfl_sync(0xffffffffu, tgt, q);
+        const u32 qlen = __shfl_sync(0xffffffffu, len, q), qrel = __shfl_sync(0xffffffffu, rel, q);
+        if (j >= total) continue;
+        const u32 k = j - qrel;
+        const u64 v = cell_value<CellT, FIRST>(text[qpos + k]);
+        const u64 left = k ? cell_value<CellT, FIRST>(text[qpos + k - 1]) + 1 : qtgt;
+        const bool valid = k + 1 < qlen || (qtgt & EI_SFX);  // exact_par_phase.cpp:163
+        const u64 e = (u64)base + j;
+        D[e] = (SymT)v;
+        if (phr_of) phr_of[e] = (u32)(i - lane + q);
+        rem[e] = qlen - 1 - k;
+        einfo[e] = make_ulonglong2(left, qfreq | (valid ? EI_VALID : 0ULL) | (k == 0 ? EI_FULL : 0ULL));
     }
 }
 
@@ -230,29 +256,29 @@ static __global__ void __launch_bounds__(256) pack_ginfo_dense_kernel(const u32*
     const u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (g < G) ginfo[g] = (rrank[g] << 2) | (((gcnt[g] & 0x7fffffffu) > 1) ? 2u : 0u) | (rflag[g] ? 1u : 0u);
 }
-template <class SymT>
-__global__ void __launch_bounds__(256) group_apply_kernel(const u32* __restrict__ order, const u32* __restrict__ head_bits, const u32* __restrict__ head_pref,
-                                                          const u32* __restrict__ full_bits, const u32* __restrict__ ginfo, const SymT* __restrict__ D,
-                                                          const u32* __restrict__ rem, const u32* __restrict__ phr_of, const u64* __restrict__ ph_freq,
-                                                          const u32* __restrict__ occ_slots, u64 nE, IsSuffix is_suffix, u64 rank_base, u32 erank_bias,
-                                                          ulonglong2* table, u64* __restrict__ ph_meta, u8* __restrict__ is_suffix_next,
-                                                          u32* __restrict__ erank) {
+// metasymbol of every whole phrase (exact_par_phase.cpp:174-176, :437-444) and is_suffix of the next round (:443): a group
+// of equal suffixes holds at most one whole phrase, whose destination group_reduce left in gfull
+static __global__ void __launch_bounds__(256) full_apply_kernel(const u32* __restrict__ gcnt, const u32* __restrict__ rflag, const u32* __restrict__ rrank,
+                                                                const u64* __restrict__ gfull, u64 G, u64 rank_base, ulonglong2* table, u64* __restrict__ ph_meta,
+                                                                u8* __restrict__ is_suffix_next) {
+    const u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G || !rflag[g] || !(gcnt[g] >> 31)) return;
+    const u64 r = (u64)rrank[g] + rank_base, f = gfull[g];
+    const u64 meta = (r << 1) | (f & 1ULL);
+    if (ph_meta) ph_meta[f >> 2] = meta;  // multi-GPU: the dictionary is global, the tables are per rank
+    else table[f >> 2].y = meta;
+    is_suffix_next[r] = (u8)((f >> 1) & 1ULL);
+}
+// rank marks of the entries of hocc groups (phr_marks + new_phrases_ht, :190-207), pass in sorted order
+static __global__ void __launch_bounds__(256) group_apply_kernel(const u32* __restrict__ order, const u32* __restrict__ head_bits, const u32* __restrict__ head_pref,
+                                                                 const u32* __restrict__ ginfo, u64 nE, u64 rank_base, u32 erank_bias, u32* __restrict__ erank) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nE) return;
     const u32 hw = head_bits[i >> 5];
     const u32 g = head_pref[i >> 5] + __popc(hw & (0xffffffffu >> (31 - (i & 31)))) - 1;
     const u32 gi = ginfo[g];
-    if (!(gi & 1u)) return;  // invalid and unranked groups carry no rank
-    const u64 r = (u64)(gi >> 2) + rank_base;
-    const u32 e = order[i];
-    if (gi & 2u) erank[e] = (u32)r + erank_bias;  // bias 1 in distributed rounds (0 = none, merged by all-reduce MAX)
-    if ((full_bits[i >> 5] >> (i & 31)) & 1u) {
-        const u32 ph = phr_of[e];
-        const u64 meta = (r << 1) | (ph_freq[ph] > 1 ? 1ULL : 0ULL);
-        if (ph_meta) ph_meta[ph] = meta;
-        else table[occ_slots[ph]].y = meta;
-        is_suffix_next[r] = is_suffix((u64)D[e + rem[e]]) ? 1 : 0;
-    }
+    if ((gi & 3u) != 3u) return;  // only ranked groups with more than one entry
+    erank[order[i]] = (u32)((u64)(gi >> 2) + rank_base) + erank_bias;  // bias 1 in distributed rounds (0 = none, merged by all-reduce MAX)
 }
 
 // ---- distributed ranking: every rank owns the suffix entries whose first key falls in its range [lo, hi) ----
@@ -303,7 +329,7 @@ struct OpMax { template <class T> __device__ __forceinline__ T operator()(T a, T
 // gcnt = entries | full<<31 ; gmin/gmax over (left symbol + 1) of the non-full entries (0 = none).
 static __global__ void __launch_bounds__(256) group_reduce_kernel(const u32* __restrict__ order, const u32* __restrict__ head_bits, const u32* __restrict__ head_pref,
                                                                   const ulonglong2* __restrict__ einfo, u64 nE, u32* gcnt, u64* gacc, u64* gmin, u64* gmax,
-                                                                  u32* __restrict__ grep, u32* __restrict__ ghead, u32* __restrict__ full_bits) {
+                                                                  u32* __restrict__ grep, u32* __restrict__ ghead, u64* __restrict__ gfull) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     u32 g = 0xffffffffu, cnt = 0;
     u64 acc = 0, mn = ~0ULL, mx = 0;
@@ -320,13 +346,10 @@ static __global__ void __launch_bounds__(256) group_reduce_kernel(const u32* __r
             is_full = (ei.y & EI_FULL) != 0;
             cnt = 1u | (is_full ? 0x80000000u : 0u);
             acc = ei.y & EI_FREQ;
-            if (ei.x) mn = mx = ei.x;
+            if (is_full) gfull[g] = ((ei.x & ~EI_SFX) << 2) | ((ei.x >> 63) << 1) | (acc > 1 ? 1ULL : 0ULL);  // at most one per group
+            else if (ei.x) mn = mx = ei.x;
         }
         if (hd) { grep[g] = e; ghead[g] = (u32)i; }  // entries keep their position-based rank = head position + 1
-    }
-    if (full_bits) {  // which sorted positions hold a whole phrase (used by the sorted-order finalisation)
-        const u32 fb = __ballot_sync(0xffffffffu, is_full);
-        if (lane_id() == 0 && (i >> 5) < ((nE + 31) >> 5)) full_bits[i >> 5] = fb;
     }
     const u32 m = __match_any_sync(0xffffffffu, g);
     const u32 first = __ffs(m) - 1, last = 31 - __clz(m);
@@ -390,8 +413,7 @@ __global__ void __launch_bounds__(256) prebwt_runs_kernel(const u64* __restrict_
     if (lane_id() == first && rid != 0xffffffffu) atomicAdd(&run_len[rid], len);
 }
 
-// G4: per entry: metasymbol of full phrases (exact_par_phase.cpp:174-176, :437-444), is_suffix of the
-// next round (:443), rank marks of entries in hocc groups (phr_marks + new_phrases_ht, :190-207)
+// G4 (prefix-doubling fallback): rank marks of entries in hocc groups (phr_marks + new_phrases_ht, :190-207)
 // ginfo_pos[head position of the group] = rank << 2 | hocc << 1 | ranked : entries reach it through their
 // position-based rank, so the sorted pass never has to scatter a dense group id back to the entries
 static __global__ void __launch_bounds__(256) pack_ginfo_kernel(const u32* __restrict__ gcnt, const u32* __restrict__ rflag, const u32* __restrict__ rrank,
@@ -399,25 +421,11 @@ static __global__ void __launch_bounds__(256) pack_ginfo_kernel(const u32* __res
     const u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (g < G) ginfo_pos[ghead[g]] = (rrank[g] << 2) | (((gcnt[g] & 0x7fffffffu) > 1) ? 2u : 0u) | (rflag[g] ? 1u : 0u);
 }
-template <class SymT>
-__global__ void __launch_bounds__(256) entry_finalize_kernel(const u32* __restrict__ rank, const SymT* __restrict__ D, const u32* __restrict__ rem,
-                                                             const u32* __restrict__ phr_of, const u32* __restrict__ ph_off, const u64* __restrict__ ph_freq,
-                                                             const u32* __restrict__ occ_slots, u64 nE, IsSuffix is_suffix, const u32* __restrict__ ginfo_pos,
-                                                             ulonglong2* table, u64* __restrict__ ph_meta, u8* __restrict__ is_suffix_next,
-                                                             u32* __restrict__ erank) {
+static __global__ void __launch_bounds__(256) entry_finalize_kernel(const u32* __restrict__ rank, u64 nE, const u32* __restrict__ ginfo_pos, u32* __restrict__ erank) {
     const u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nE) return;
     const u32 gi = ginfo_pos[rank[e] - 1];  // rank[e] - 1 = position of the head of e's group in the sorted order
-    if (!(gi & 1u)) return;  // invalid and unranked groups carry no rank
-    const u32 r = gi >> 2;
-    const u32 ph = phr_of[e];
-    if (e == ph_off[ph]) {
-        const u64 meta = ((u64)r << 1) | (ph_freq[ph] > 1 ? 1ULL : 0ULL);
-        if (ph_meta) ph_meta[ph] = meta;  // multi-GPU: the dictionary is global, the tables are per rank
-        else table[occ_slots[ph]].y = meta;
-        is_suffix_next[r] = is_suffix((u64)D[e + rem[e]]) ? 1 : 0;
-    }
-    if (gi & 2u) erank[e] = r;
+    if ((gi & 3u) == 3u) erank[e] = gi >> 2;
 }
 
 // G5: grammar rule of every ranked group from its representative entry (produce_grammar exact_par_phase.cpp:33-87)

@@ -349,11 +349,12 @@ void dict_offsets(Round& R) {
 template <class CellT, bool FIRST, class SymT>
 void stage_gather(Round& R) {
     R.D_raw.alloc((R.nE + 1) * sizeof(SymT), R.st);
-    R.phr_of.alloc(R.nE, R.st);
+    if (R.c->flags & GRLGPU_FLAG_KEEP_DICT) R.phr_of.alloc(R.nE, R.st);  // only the test hooks read it
     R.rem.alloc(R.nE, R.st);
     R.einfo.alloc(R.nE, R.st);
     IsSuffix isuf{R.c->is_suffix.p, R.c->sep, R.c->first};
-    GRL_LAUNCH("dict_gather", R.nE * (sizeof(CellT) + sizeof(SymT) + 8) + R.d * 16, (dict_gather_kernel<CellT, FIRST, SymT>), grid_for(R.d, 256), 256, 0, R.st, (const CellT*)(R.dict_text ? R.dict_text : R.c->text), R.ph_pos.p, R.ph_len.p, R.ph_off.p, R.ph_freq.p, R.d, isuf, (SymT*)R.D_raw.p, R.phr_of.p, R.rem.p, R.einfo.p);
+    // metasymbols go to the phrase's table slot, or to the global per-phrase array in multi-GPU rounds
+    GRL_LAUNCH("dict_gather", R.nE * (sizeof(CellT) + sizeof(SymT) + 20) + R.d * 28, (dict_gather_kernel<CellT, FIRST, SymT>), grid_for(R.d, 256), 256, 0, R.st, (const CellT*)(R.dict_text ? R.dict_text : R.c->text), R.ph_pos.p, R.ph_len.p, R.ph_off.p, R.ph_freq.p, R.ph_meta ? (const u32*)nullptr : (const u32*)R.occ_slots.p, R.d, isuf, (SymT*)R.D_raw.p, R.phr_of.p, R.rem.p, R.einfo.p);
 }
 
 // ---------------- dictionary stage: suffix order, groups, ranks, pre-BWT, rules, metasymbols ----------------
@@ -490,10 +491,9 @@ void stage_dict(Round& R) {
 
     // -- group aggregates --
     DevBuf<u32> gcnt(G, st), grep(G, st), ghead(G, st), rflag(G, st), vflag(G, st), rrank(G, st), vidx(G, st);
-    DevBuf<u64> gacc(G, st), gmin(G, st), gmax(G, st), psym(G, st);
+    DevBuf<u64> gacc(G, st), gmin(G, st), gmax(G, st), psym(G, st), gfull(G, st);
     gcnt.zero(); gacc.zero(); gmax.zero(); gmin.fill_ff();
-    DevBuf<u32> full_bits(ext_mode ? n_words : 1, st);
-    GRL_LAUNCH("group_reduce", nE * 24 + G * 32, group_reduce_kernel, grid_for(nE, 256), 256, 0, st, order, head_bits.p, head_pref.p, R.einfo.p, nE, gcnt.p, gacc.p, gmin.p, gmax.p, grep.p, ghead.p, ext_mode ? full_bits.p : (u32*)nullptr);
+    GRL_LAUNCH("group_reduce", nE * 24 + G * 32, group_reduce_kernel, grid_for(nE, 256), 256, 0, st, order, head_bits.p, head_pref.p, R.einfo.p, nE, gcnt.p, gacc.p, gmin.p, gmax.p, grep.p, ghead.p, gfull.p);
     R.einfo.release();
     const u64 bwt_dummy = A + 1, hocc_dummy = A + 2;  // exact_par_phase.hpp:113-115
     GRL_LAUNCH("group_finalize", 0, group_finalize_kernel, grid_for(G, 256), 256, 0, st, gcnt.p, gmin.p, gmax.p, G, bwt_dummy, hocc_dummy, rflag.p, vflag.p, psym.p);
@@ -527,15 +527,16 @@ void stage_dict(Round& R) {
     is_suffix_next.zero();
     DevBuf<u32> erank(nE, st);
     erank.fill_ff();
-    if (ext_mode) {  // finalisation in sorted order: group info is read sequentially, entries need no rank of their own
+    GRL_LAUNCH("full_apply", G * 20 + R.d * 40, full_apply_kernel, grid_for(G, 256), 256, 0, st, gcnt.p, rflag.p, rrank.p, gfull.p, G, (u64)0, R.table.p, R.ph_meta, is_suffix_next.p);
+    gfull.release();
+    if (ext_mode) {  // hocc marks in sorted order: group info is read sequentially, entries need no rank of their own
         DevBuf<u32> ginfo(G, st);
         GRL_LAUNCH("pack_ginfo_dense", G * 16, pack_ginfo_dense_kernel, grid_for(G, 256), 256, 0, st, gcnt.p, rflag.p, rrank.p, G, ginfo.p);
-        GRL_LAUNCH("group_apply", nE * 16, (group_apply_kernel<SymT>), grid_for(nE, 256), 256, 0, st, order, head_bits.p, head_pref.p, full_bits.p, ginfo.p, D, R.rem.p, R.phr_of.p,
-                   R.ph_freq.p, R.occ_slots.p, nE, isuf, (u64)0, 0u, R.table.p, R.ph_meta, is_suffix_next.p, erank.p);
+        GRL_LAUNCH("group_apply", nE * 12, group_apply_kernel, grid_for(nE, 256), 256, 0, st, order, head_bits.p, head_pref.p, ginfo.p, nE, (u64)0, 0u, erank.p);
     } else {
         DevBuf<u32> ginfo(nE, st);  // indexed by head position
         GRL_LAUNCH("pack_ginfo", G * 20, pack_ginfo_kernel, grid_for(G, 256), 256, 0, st, gcnt.p, rflag.p, rrank.p, ghead.p, G, ginfo.p);
-        GRL_LAUNCH("entry_finalize", nE * 24, (entry_finalize_kernel<SymT>), grid_for(nE, 256), 256, 0, st, R.rank.p, D, R.rem.p, R.phr_of.p, R.ph_off.p, R.ph_freq.p, R.occ_slots.p, nE, isuf, ginfo.p, R.table.p, R.ph_meta, is_suffix_next.p, erank.p);
+        GRL_LAUNCH("entry_finalize", nE * 12, entry_finalize_kernel, grid_for(nE, 256), 256, 0, st, R.rank.p, nE, ginfo.p, erank.p);
     }
     c->rule_l.alloc(tot * sizeof(SymT), st);
     c->rule_r.alloc(tot * sizeof(SymT), st);
@@ -672,7 +673,8 @@ struct MgRound {
     const void* g_cells = nullptr;
     u64 nL = 0, G = 0, tot_local = 0, n_pre_local = 0;
     int sym_bytes = 4;
-    DevBuf<u32> order, head_bits, head_pref, full_bits, gcnt, grep, rflag, rrank;
+    DevBuf<u32> order, head_bits, head_pref, gcnt, grep, rflag, rrank;
+    DevBuf<u64> gfull;
     DevBuf<u8> sl_rule_l, sl_rule_r, sl_has_hocc, sl_pre_sym;  // this rank's slice of the level artefacts
     DevBuf<u64> sl_pre_len;
     explicit MgRound(grlgpu_ctx* c) : R(c), t_text(c->st), t_dict(c->st) {}
@@ -926,13 +928,12 @@ void mg_rank_sort_sym(grlgpu_ctx* c, const u32* lens, const u64* freqs, const vo
     }
     M.G = G;
     M.gcnt.alloc(G, st); M.grep.alloc(G, st); M.rflag.alloc(G, st); M.rrank.alloc(G, st);
-    M.full_bits.alloc(n_words, st);
-    M.full_bits.zero();
+    M.gfull.alloc(G, st);
     DevBuf<u32> ghead(G, st), vflag(G, st), vidx(G, st);
     DevBuf<u64> gacc(G, st), gmin(G, st), gmax(G, st), psym(G, st);
     M.gcnt.zero(); gacc.zero(); gmax.zero(); gmin.fill_ff();
     GRL_LAUNCH("group_reduce", nL * 24 + G * 32, group_reduce_kernel, grid_for(nL, 256), 256, 0, st, M.order.p, M.head_bits.p, M.head_pref.p, GR.einfo.p, nL, M.gcnt.p, gacc.p, gmin.p,
-               gmax.p, M.grep.p, ghead.p, M.full_bits.p);
+               gmax.p, M.grep.p, ghead.p, M.gfull.p);
     GR.einfo.release();
     const u64 bwt_dummy = A + 1, hocc_dummy = A + 2;
     GRL_LAUNCH("group_finalize", 0, group_finalize_kernel, grid_for(G, 256), 256, 0, st, M.gcnt.p, gmin.p, gmax.p, G, bwt_dummy, hocc_dummy, M.rflag.p, vflag.p, psym.p);
@@ -986,11 +987,11 @@ void mg_rank_apply_sym(grlgpu_ctx* c, u64 rank_base, u64* g_meta, u8* is_suffix_
     MgRound& M = *c->mg;
     Round& GR = *M.GR;
     cudaStream_t st = c->st;
-    IsSuffix isuf{c->is_suffix.p, c->sep, c->first};
     DevBuf<u32> ginfo(M.G, st);
+    GRL_LAUNCH("full_apply", M.G * 20, full_apply_kernel, grid_for(M.G, 256), 256, 0, st, M.gcnt.p, M.rflag.p, M.rrank.p, M.gfull.p, M.G, rank_base, (ulonglong2*)nullptr, g_meta, is_suffix_next);
+    M.gfull.release();
     GRL_LAUNCH("pack_ginfo_dense", M.G * 16, pack_ginfo_dense_kernel, grid_for(M.G, 256), 256, 0, st, M.gcnt.p, M.rflag.p, M.rrank.p, M.G, ginfo.p);
-    GRL_LAUNCH("group_apply", M.nL * 16, (group_apply_kernel<SymT>), grid_for(M.nL, 256), 256, 0, st, M.order.p, M.head_bits.p, M.head_pref.p, M.full_bits.p, ginfo.p,
-               (const SymT*)GR.D_raw.p, GR.rem.p, GR.phr_of.p, GR.ph_freq.p, (const u32*)nullptr, M.nL, isuf, rank_base, 1u, (ulonglong2*)nullptr, g_meta, is_suffix_next, erank1);
+    GRL_LAUNCH("group_apply", M.nL * 12, group_apply_kernel, grid_for(M.nL, 256), 256, 0, st, M.order.p, M.head_bits.p, M.head_pref.p, ginfo.p, M.nL, rank_base, 1u, erank1);
     GRL_CUDA(cudaStreamSynchronize(st));
 }
 
@@ -1020,7 +1021,7 @@ void mg_rank_finish_sym(grlgpu_ctx* c, u64 rank_base, u64 tot, u64 n_pre_global,
     c->lvl_tot = 0; c->lvl_npre = 0;
     // keep only the slices (until grlgpu_mg_level_slice / the next round)
     M.GR.reset();
-    M.order.release(); M.head_bits.release(); M.head_pref.release(); M.full_bits.release();
+    M.order.release(); M.head_bits.release(); M.head_pref.release(); M.gfull.release();
     M.gcnt.release(); M.grep.release(); M.rflag.release(); M.rrank.release();
 }
 

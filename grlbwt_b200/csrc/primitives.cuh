@@ -114,41 +114,59 @@ static __global__ void __launch_bounds__(BC_THREADS) bitmap_count_kernel(const u
     if (threadIdx.x == 0) tile_count[blockIdx.x] = tot;
 }
 
+// A warp owns 32 * BC_WORDS consecutive words and walks them 32 at a time (lane = word): the positions of one step go
+// through a 1024-entry shared-memory stage (10-bit offset | flag << 15) so that the stores to `out` are coalesced.
 template <class PosT>
 __global__ void __launch_bounds__(BC_THREADS) bitmap_write_kernel(const u32* __restrict__ bits, const u32* __restrict__ prev_bits, u64 n_bits,
                                                                   const u64* __restrict__ tile_off, PosT* __restrict__ out) {
-    __shared__ u32 sm[33];
+    __shared__ u32 wtot[BC_THREADS / 32];
+    __shared__ unsigned short stage[BC_THREADS / 32][1024];
     constexpr PosT FLAG = PosT(1) << (sizeof(PosT) * 8 - 1);
+    const u32 lane = lane_id(), warp = threadIdx.x >> 5;
     const u64 n_words = (n_bits + 31) / 32;
-    const u64 w0 = (u64)blockIdx.x * BC_TILE_WORDS + (u64)threadIdx.x * BC_WORDS;
+    const u64 wbase = (u64)blockIdx.x * BC_TILE_WORDS + (u64)warp * (32 * BC_WORDS);
     u32 wd[BC_WORDS];
     u32 c = 0;
 #pragma unroll
     for (int i = 0; i < BC_WORDS; i++) {
-        wd[i] = bc_load_word(bits, w0 + i, n_words, n_bits);
+        wd[i] = bc_load_word(bits, wbase + (u64)i * 32 + lane, n_words, n_bits);
         c += __popc(wd[i]);
     }
-    u32 tot;
-    u32 ex = block_exclusive_sum<u32>(c, sm, tot);
-    u64 o = tile_off[blockIdx.x] + ex;
+    c = warp_sum(c);
+    if (lane == 0) wtot[warp] = c;
+    __syncthreads();
+    u64 o = tile_off[blockIdx.x];
+    for (u32 w2 = 0; w2 < warp; w2++) o += wtot[w2];
 #pragma unroll
     for (int i = 0; i < BC_WORDS; i++) {
         u32 x = wd[i];
-        if (!x) continue;
-        const u64 w = w0 + i;
+        const u32 cnt = __popc(x);
+        const u32 inc = warp_inclusive_sum(cnt);
+        const u32 T = __shfl_sync(0xffffffffu, inc, 31);
+        if (T == 0) continue;
+        u32 ex = inc - cnt;
         u32 fl = 0;
-        if (prev_bits) {
-            u32 pw = bc_load_word(prev_bits, w, n_words, n_bits);
-            u32 pp = w ? bc_load_word(prev_bits, w - 1, n_words, n_bits) : 0x80000000u;  // position 0 starts a string
+        if (prev_bits && x) {
+            const u64 w = wbase + (u64)i * 32 + lane;
+            const u32 pw = bc_load_word(prev_bits, w, n_words, n_bits);
+            const u32 pp = w ? bc_load_word(prev_bits, w - 1, n_words, n_bits) : 0x80000000u;  // position 0 starts a string
             fl = (pw << 1) | (pp >> 31);
         }
         while (x) {
             const int b = __ffs(x) - 1;
             x &= x - 1;
-            PosT q = (PosT)(w * 32 + b);
-            if ((fl >> b) & 1u) q |= FLAG;
-            out[o++] = q;
+            stage[warp][ex++] = (unsigned short)((lane << 5) | (u32)b | (((fl >> b) & 1u) << 15));
         }
+        __syncwarp();
+        const u64 bit_base = (wbase + (u64)i * 32) * 32;
+        for (u32 j = lane; j < T; j += 32) {
+            const u32 sv = stage[warp][j];
+            PosT q = (PosT)(bit_base + (sv & 0x3ffu));
+            if (sv >> 15) q |= FLAG;
+            out[o + j] = q;
+        }
+        __syncwarp();
+        o += T;
     }
 }
 

@@ -39,8 +39,11 @@ def run(name, arr, prof=False):
 
 if __name__ == "__main__":
     scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
+    which = sys.argv[2] if len(sys.argv) > 2 else "all"
     reads = gen.dna_reads(int(2000000 * scale), 150, seed=42)
     run("reads", reads)
     run("reads", reads, prof=True)
+    if which == "reads":
+        sys.exit(0)
     run("repetitive", gen.repetitive_genomes(int(100 * scale), 1000000, seed=7), prof=True)
     run("u16", gen.int_alphabet(int(50000000 * scale), np.uint16, 65535, 1000, seed=11), prof=True)
