@@ -230,6 +230,7 @@ def run_ours(args, rank, world, local_rank):
     ctx = G.GrlGpu(local_rank, 0, stream=stream.cuda_stream)
     engine = M.GpuEngine(ctx, dev)
     arena = [None]
+    e2e_parts = {}
 
     def barrier():
         if world > 1:
@@ -246,13 +247,16 @@ def run_ours(args, rank, world, local_rank):
                 if collect is not None:
                     collect.append(r.as_dict())
                 if fetch:  # every level lands in its own slice of the pinned arena while the next round computes
+                    e2e_parts.setdefault("round_ms", []).append(round(r.device_ms, 1))
                     ctx.fetch_level(arena[0], async_=True, offset=a_off)
                     a_off = ctx.arena_end
                     d2h += r.tot_phrases * (2 * r.sym_bytes + 1) + r.n_pre_runs * (r.sym_bytes + 8)
                 if r.done:
                     if fetch:
+                        t_tail = time.perf_counter()
                         ctx.fetch_wait()
                         d2h += ctx.fetch_parse(arena[0][a_off:]).nbytes
+                        e2e_parts["tail_wait_ms"] = (time.perf_counter() - t_tail) * 1e3
                     return d2h
         st = M.global_stats(engine)
         while True:
@@ -314,8 +318,13 @@ def run_ours(args, rank, world, local_rank):
         d2h_bytes = [0]
 
         def step_e2e():
+            e2e_parts.clear()
+            t_a = time.perf_counter()
             ctx.set_text(host_np)
+            t_b = time.perf_counter()
             d2h_bytes[0] = run_phase(True)
+            e2e_parts["h2d_ms"] = (t_b - t_a) * 1e3
+            e2e_parts["rounds_and_fetch_ms"] = (time.perf_counter() - t_b) * 1e3
 
         step_e2e()
         barrier()
@@ -334,7 +343,8 @@ def run_ours(args, rank, world, local_rank):
             h2d_b, d2h_b = n, d2h_bytes[0]
         e2e = {"value": round(n_total * args.steps / 1e6 / (wall_ms / 1e3), 3), "unit": "MB/s", "h2d_bytes_per_step": int(h2d_b),
                "d2h_bytes_per_step": int(d2h_b), "ms_per_step": round(wall_ms / args.steps, 3),
-               "timing": "host wall clock between stream synchronisations, max over ranks (fetches are host-blocking)"}
+               "timing": "host wall clock between stream synchronisations, max over ranks (fetches are host-blocking)",
+               "last_step_parts_ms": {k: (v if isinstance(v, list) else round(v, 1)) for k, v in e2e_parts.items()}}
     ctx.close()
 
     # ---- roofline of the dominant kernel (CUDA events on the launch stream, live, one profiled step) ----

@@ -45,23 +45,39 @@ static __global__ void __launch_bounds__(256) dict_meta_kernel(const ulonglong2*
 // metasymbol goes (table slot, or phrase index in multi-GPU rounds) | is_suffix(last symbol) << 63.
 constexpr u64 EI_VALID = 1ULL << 63, EI_FULL = 1ULL << 62, EI_FREQ = (1ULL << 62) - 1, EI_SFX = 1ULL << 63;
 
+// entries of a phrase that take part in the suffix order: all but a last symbol that is not is_suffix (exact_par_phase.cpp:163)
+template <class CellT, bool FIRST>
+__global__ void __launch_bounds__(256) phrase_vlen_kernel(const CellT* __restrict__ text, const u64* __restrict__ ph_pos, const u32* __restrict__ ph_len, u64 d,
+                                                          IsSuffix is_suffix, u32* __restrict__ vlen) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d) return;
+    const u32 len = ph_len[i];
+    vlen[i] = len - ((len && is_suffix(cell_value<CellT, FIRST>(text[ph_pos[i] + len - 1]))) ? 0u : 1u);
+}
+
 // One lane per phrase for the per-phrase reads; the entries of a warp's 32 consecutive phrases are consecutive too, so
 // the warp then walks them 32 at a time (lane = entry, owner phrase found by a 5-step search over the lanes' offsets)
-// and every store is fully coalesced.
+// and every store is fully coalesced. With ph_voff (offsets of the phrases among the VALID entries, d + 1 values) the
+// kernel also emits the first sort key of every valid entry (K symbol codes of `bits` bits, most significant first:
+// 0 = past the end, symbol + 1, term_code = terminator, so that a proper prefix compares greater) and its entry id.
 template <class CellT, bool FIRST, class SymT>
 __global__ void __launch_bounds__(256) dict_gather_kernel(const CellT* __restrict__ text, const u64* __restrict__ ph_pos, const u32* __restrict__ ph_len,
                                                           const u32* __restrict__ ph_off, const u64* __restrict__ ph_freq,
                                                           const u32* __restrict__ target_slots, u64 d, IsSuffix is_suffix, SymT* __restrict__ D,
-                                                          u32* __restrict__ phr_of, u32* __restrict__ rem, ulonglong2* __restrict__ einfo) {
+                                                          u32* __restrict__ phr_of, u32* __restrict__ rem, ulonglong2* __restrict__ einfo,
+                                                          const u32* __restrict__ ph_voff, u64 term_code, int bits, int K, u64* __restrict__ keys,
+                                                          u32* __restrict__ vals) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     const u32 lane = lane_id();
     const u32 nvalid = __popc(__ballot_sync(0xffffffffu, i < d));  // valid lanes are a prefix of the warp
     if (nvalid == 0) return;
     u64 pos = 0, freq = 0, tgt = 0;
-    u32 len = 0, off = 0;
+    u32 len = 0, off = 0, voff = 0;
     if (i < d) {
         pos = ph_pos[i]; freq = ph_freq[i]; len = ph_len[i]; off = ph_off[i];
-        const bool sfx_last = len && is_suffix(cell_value<CellT, FIRST>(text[pos + len - 1]));  // :443
+        bool sfx_last;
+        if (ph_voff) { voff = ph_voff[i]; sfx_last = ph_voff[i + 1] - voff == len; }
+        else sfx_last = len && is_suffix(cell_value<CellT, FIRST>(text[pos + len - 1]));  // :443
         tgt = (target_slots ? (u64)target_slots[i] : i) | (sfx_last ? EI_SFX : 0ULL);
     }
     const u32 base = __shfl_sync(0xffffffffu, off, 0);
@@ -77,17 +93,28 @@ __global__ void __launch_bounds__(256) dict_gather_kernel(const CellT* __restric
             if (cand < nvalid && r <= j) q = cand;
         }
         const u64 qpos = __shfl_sync(0xffffffffu, pos, q), qfreq = __shfl_sync(0xffffffffu, freq, q), qtgt = __shfl_sync(0xffffffffu, tgt, q);
-        const u32 qlen = __shfl_sync(0xffffffffu, len, q), qrel = __shfl_sync(0xffffffffu, rel, q);
+        const u32 qlen = __shfl_sync(0xffffffffu, len, q), qrel = __shfl_sync(0xffffffffu, rel, q), qvoff = __shfl_sync(0xffffffffu, voff, q);
         if (j >= total) continue;
-        const u32 k = j - qrel;
+        const u32 k = j - qrel, r = qlen - 1 - k;
         const u64 v = cell_value<CellT, FIRST>(text[qpos + k]);
         const u64 left = k ? cell_value<CellT, FIRST>(text[qpos + k - 1]) + 1 : qtgt;
-        const bool valid = k + 1 < qlen || (qtgt & EI_SFX);  // exact_par_phase.cpp:163
+        const bool valid = r > 0 || (qtgt & EI_SFX);  // exact_par_phase.cpp:163
         const u64 e = (u64)base + j;
         D[e] = (SymT)v;
         if (phr_of) phr_of[e] = (u32)(i - lane + q);
-        rem[e] = qlen - 1 - k;
+        rem[e] = r;
         einfo[e] = make_ulonglong2(left, qfreq | (valid ? EI_VALID : 0ULL) | (k == 0 ? EI_FULL : 0ULL));
+        if (ph_voff && valid) {
+            u64 key = v + 1;
+            for (int t = 1; t < K; t++) {
+                u64 code = 0;
+                if ((u32)t <= r) code = cell_value<CellT, FIRST>(text[qpos + k + t]) + 1;
+                else if ((u32)t == r + 1) code = term_code;
+                key = (key << bits) | code;
+            }
+            keys[(u64)qvoff + k] = key;
+            vals[(u64)qvoff + k] = (u32)e;
+        }
     }
 }
 
@@ -290,10 +317,10 @@ static __global__ void __launch_bounds__(256) key_range_flags_kernel(const u64* 
     const u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (e < n) flags[e] = (keys[e] >= lo && (hi_open || keys[e] < hi)) ? 1u : 0u;
 }
-static __global__ void __launch_bounds__(256) key_range_compact_kernel(const u64* __restrict__ keys, const u32* __restrict__ flags, const u32* __restrict__ excl, u64 n,
-                                                                       u64* __restrict__ okeys, u32* __restrict__ ovals) {
+static __global__ void __launch_bounds__(256) key_range_compact_kernel(const u64* __restrict__ keys, const u32* __restrict__ vals, const u32* __restrict__ flags,
+                                                                       const u32* __restrict__ excl, u64 n, u64* __restrict__ okeys, u32* __restrict__ ovals) {
     const u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < n && flags[e]) { okeys[excl[e]] = keys[e]; ovals[excl[e]] = (u32)e; }
+    if (e < n && flags[e]) { okeys[excl[e]] = keys[e]; ovals[excl[e]] = vals[e]; }
 }
 // hocc marks travel between ranks as rank+1 (0 = none) so that an all-reduce(MAX) merges them; decode in place
 static __global__ void __launch_bounds__(256) erank_decode_kernel(u32* __restrict__ erank, u64 n) {

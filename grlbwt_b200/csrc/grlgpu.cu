@@ -60,7 +60,7 @@ struct grlgpu_ctx {
     int mg_ranks = 0;
 
     // optional: dictionary of the last round kept for tests (GRLGPU_FLAG_KEEP_DICT)
-    u64 kd_d = 0, kd_nE = 0;
+    u64 kd_d = 0, kd_nE = 0, kd_nS = 0;
     DevBuf<u8> kd_D;
     DevBuf<u32> kd_off, kd_len, kd_order, kd_phr_of;
     DevBuf<u64> kd_freq, kd_meta;
@@ -88,9 +88,9 @@ struct Timer {
 
 template <class T>
 T d2h_scalar(const T* dptr, cudaStream_t st) {
+    static_assert(sizeof(T) % 4 == 0, "d2h_scalar reads whole words");
     T h;
-    GRL_CUDA(cudaMemcpyAsync(&h, dptr, sizeof(T), cudaMemcpyDeviceToHost, st));
-    GRL_CUDA(cudaStreamSynchronize(st));
+    d2h_small(&h, dptr, sizeof(T), st);
     return h;
 }
 
@@ -160,6 +160,13 @@ struct Round {
     DevBuf<u8> D_raw;
     DevBuf<u32> phr_of, rem, rank, order;
     DevBuf<ulonglong2> einfo;
+    // suffix-order plan: K symbol codes of sym_bits bits per 64-bit key; ext_mode = refinement by key extension, over the
+    // nS valid entries only (first keys + entry ids come out of the dictionary gather); else prefix doubling over all nE
+    int sym_bits = 0, K = 1;
+    bool ext_mode = false;
+    u64 nS = 0;
+    DevBuf<u64> keys;
+    DevBuf<u32> vals;
     const void* dict_text = nullptr;  // text the dictionary's ph_pos point into (default: the context's text)
     u64* ph_meta = nullptr;           // if set, metasymbols go here (per phrase) instead of into the table
     explicit Round(grlgpu_ctx* ctx) : c(ctx), st(ctx->st), n(ctx->n) {}
@@ -273,7 +280,7 @@ void stage_dedup(Round& R) {
         if (has_rest) {
             if (decided == -1) {
                 u64 hs[2];
-                GRL_CUDA(cudaMemcpyAsync(hs, stats.p, 16, cudaMemcpyDeviceToHost, R.st));
+                d2h_small(hs, stats.p, 16, R.st);
                 GRL_CUDA(cudaStreamSynchronize(R.st));
                 decided = hs[0] * 2 <= hs[1] ? 1 : 0;  // cached: at most half of the pilot's phrases had to go to the global table
                 if (decided == 0 && cap < cap_full && !(c->flags & GRLGPU_FLAG_SMALL_TABLE)) { cap = cap_full; continue; }
@@ -340,21 +347,41 @@ void dict_offsets(Round& R) {
         GRL_LAUNCH("reduce_max_u64", 0, reduce_max_u64_kernel, 296, 256, 0, R.st, len64.p, R.d, mx.p + 1);
     }
     u64 hmx[2];
-    GRL_CUDA(cudaMemcpyAsync(hmx, mx.p, 16, cudaMemcpyDeviceToHost, R.st));
-    GRL_CUDA(cudaStreamSynchronize(R.st));
+    d2h_small(hmx, mx.p, 16, R.st);
     R.max_freq = hmx[0];
     R.max_len = hmx[1];
 }
 
 template <class CellT, bool FIRST, class SymT>
-void stage_gather(Round& R) {
+void stage_gather(Round& R, bool force_ext = false) {
+    grlgpu_ctx* c = R.c;
+    R.sym_bits = bit_width64(c->alphabet + 1);
+    R.K = std::max(1, 64 / R.sym_bits);
+    // refinement by key extension needs ceil((longest phrase + 1) / K) passes at most; beyond 64 passes (or when a test
+    // forces it) the groups are refined by prefix doubling on position-based ranks instead
+    R.ext_mode = force_ext || (!(c->flags & GRLGPU_FLAG_FORCE_DOUBLING) && (R.max_len + 1 + (u64)R.K - 1) / (u64)R.K <= 64);
+    const CellT* dtext = (const CellT*)(R.dict_text ? R.dict_text : c->text);
+    DevBuf<u32> voff;
+    R.nS = R.nE;
+    if (R.ext_mode) {
+        voff.alloc(R.d + 1, R.st);
+        DevBuf<u32> tot(1, R.st);
+        IsSuffix isuf0{c->is_suffix.p, c->sep, c->first};
+        GRL_LAUNCH("phrase_vlen", R.d * 48, (phrase_vlen_kernel<CellT, FIRST>), grid_for(R.d, 256), 256, 0, R.st, dtext, R.ph_pos.p, R.ph_len.p, R.d, isuf0, voff.p);
+        exclusive_scan<u32, u32>(voff.p, voff.p, R.d, voff.p + R.d, R.st);
+        R.nS = d2h_scalar(voff.p + R.d, R.st);
+        R.keys.alloc(R.nS, R.st);
+        R.vals.alloc(R.nS, R.st);
+    }
     R.D_raw.alloc((R.nE + 1) * sizeof(SymT), R.st);
     if (R.c->flags & GRLGPU_FLAG_KEEP_DICT) R.phr_of.alloc(R.nE, R.st);  // only the test hooks read it
     R.rem.alloc(R.nE, R.st);
     R.einfo.alloc(R.nE, R.st);
     IsSuffix isuf{R.c->is_suffix.p, R.c->sep, R.c->first};
     // metasymbols go to the phrase's table slot, or to the global per-phrase array in multi-GPU rounds
-    GRL_LAUNCH("dict_gather", R.nE * (sizeof(CellT) + sizeof(SymT) + 20) + R.d * 28, (dict_gather_kernel<CellT, FIRST, SymT>), grid_for(R.d, 256), 256, 0, R.st, (const CellT*)(R.dict_text ? R.dict_text : R.c->text), R.ph_pos.p, R.ph_len.p, R.ph_off.p, R.ph_freq.p, R.ph_meta ? (const u32*)nullptr : (const u32*)R.occ_slots.p, R.d, isuf, (SymT*)R.D_raw.p, R.phr_of.p, R.rem.p, R.einfo.p);
+    GRL_LAUNCH("dict_gather", R.nE * (sizeof(CellT) + sizeof(SymT) + 20) + R.nS * 12 + R.d * 32, (dict_gather_kernel<CellT, FIRST, SymT>), grid_for(R.d, 256), 256, 0, R.st, dtext,
+               R.ph_pos.p, R.ph_len.p, R.ph_off.p, R.ph_freq.p, R.ph_meta ? (const u32*)nullptr : (const u32*)R.occ_slots.p, R.d, isuf, (SymT*)R.D_raw.p, R.phr_of.p, R.rem.p,
+               R.einfo.p, (const u32*)voff.p, c->alphabet + 1, R.sym_bits, R.K, R.keys.p, R.vals.p);
 }
 
 // ---------------- dictionary stage: suffix order, groups, ranks, pre-BWT, rules, metasymbols ----------------
@@ -366,36 +393,37 @@ void stage_dict(Round& R) {
     const SymT* D = (const SymT*)R.D_raw.p;
     IsSuffix isuf{c->is_suffix.p, c->sep, c->first};
 
-    // -- suffix order: one full sort on the packed first key, then prefix doubling on the unresolved groups only --
-    const u64 n_words = div_up(nE, 32);
+    // -- suffix order: one full sort on the packed first key, then refinement of the unresolved groups only --
+    const bool ext_mode = R.ext_mode;
+    const u64 nS = R.nS;  // sorted items: the valid entries (key extension) or every entry (prefix doubling)
+    const u64 n_words = div_up(nS, 32);
     DevBuf<u32> order_buf, head_bits(n_words, st);
     u64 G = 0;
-    bool ext_mode = false;
     {
-        DevBuf<u64> keys(nE, st), keys_alt(nE, st);
-        DevBuf<u32> vals(nE, st), vals_alt(nE, st);
+        DevBuf<u64> keys = std::move(R.keys), keys_alt(nS, st);
+        DevBuf<u32> vals = std::move(R.vals), vals_alt(nS, st);
+        const int sym_bits = R.sym_bits, K = R.K;
+        if (!ext_mode) {
+            keys.alloc(nS, st);
+            vals.alloc(nS, st);
+            GRL_LAUNCH("sfx_first_key", nE * (sizeof(SymT) + 4 + 12), (sfx_first_key_kernel<SymT>), grid_for(nE, 256), 256, 0, st, D, R.rem.p, nE, A + 1, sym_bits, K, keys.p, vals.p);
+        }
         u64 *kp = keys.p, *ka = keys_alt.p;
         u32 *vp = vals.p, *va = vals_alt.p;
-        const int sym_bits = bit_width64(A + 1);
-        const int K = std::max(1, 64 / sym_bits);
-        GRL_LAUNCH("sfx_first_key", nE * (sizeof(SymT) + 4 + 12), (sfx_first_key_kernel<SymT>), grid_for(nE, 256), 256, 0, st, D, R.rem.p, nE, A + 1, sym_bits, K, kp, vp);
-        radix_sort_pairs(&kp, &vp, &ka, &va, nE, std::min(64, sym_bits * K), st);
+        radix_sort_pairs(&kp, &vp, &ka, &va, nS, std::min(64, sym_bits * K), st);
         if (vp != vals.p) std::swap(vals, vals_alt);
         order_buf = std::move(vals);
         vals_alt.release();
         u32* order_w = order_buf.p;
         u64 nA = 0;
         DevBuf<u32> apos;
-        // refinement by key extension needs ceil((longest phrase + 1) / K) passes at most; beyond 64 passes (or when a
-        // test forces it) the groups are refined by prefix doubling on position-based ranks instead
-        ext_mode = !(c->flags & GRLGPU_FLAG_FORCE_DOUBLING) && (R.max_len + 1 + (u64)K - 1) / (u64)K <= 64;
         if (ext_mode) {
             {
-                DevBuf<u32> flags(nE, st), active_bits(n_words, st);
-                GRL_LAUNCH("first_heads", nE * 12, first_heads_kernel, grid_for(nE, 256), 256, 0, st, kp, nE, sym_bits, A + 1, flags.p, head_bits.p, active_bits.p);
+                DevBuf<u32> flags(nS, st), active_bits(n_words, st);
+                GRL_LAUNCH("first_heads", nS * 12, first_heads_kernel, grid_for(nS, 256), 256, 0, st, kp, nS, sym_bits, A + 1, flags.p, head_bits.p, active_bits.p);
                 keys.release(); keys_alt.release();
                 BitmapCompactor ac;
-                nA = ac.count(active_bits.p, nE, st);
+                nA = ac.count(active_bits.p, nS, st);
                 apos.alloc(nA, st);
                 if (nA) ac.write<u32>(nullptr, apos.p);
             }
@@ -416,7 +444,7 @@ void stage_dict(Round& R) {
                 GRL_LAUNCH("ext_heads", nA * 24, ext_heads_kernel, grid_for(nA, 256), 256, 0, st, avp, akp, nk.p, nA, flags.p);
                 GRL_LAUNCH("ext_writeback", nA * 16, ext_writeback_kernel, grid_for(nA, 256), 256, 0, st, apos.p, avp, ev.p, flags.p, nA, order_w, head_bits.p);
                 dpt += (u64)K;
-                GRL_LAUNCH("ext_next", nA * 16, ext_next_kernel, grid_for(nA, 256), 256, 0, st, apos.p, avp, ev.p, head_bits.p, R.rem.p, nA, nE, dpt, flags.p);
+                GRL_LAUNCH("ext_next", nA * 16, ext_next_kernel, grid_for(nA, 256), 256, 0, st, apos.p, avp, ev.p, head_bits.p, R.rem.p, nA, nS, dpt, flags.p);
                 exclusive_scan<u32, u32>(flags.p, excl.p, nA, cnt.p, st);
                 const u64 nA2 = d2h_scalar(cnt.p, st);
                 DevBuf<u32> apos2(nA2, st);
@@ -493,7 +521,7 @@ void stage_dict(Round& R) {
     DevBuf<u32> gcnt(G, st), grep(G, st), ghead(G, st), rflag(G, st), vflag(G, st), rrank(G, st), vidx(G, st);
     DevBuf<u64> gacc(G, st), gmin(G, st), gmax(G, st), psym(G, st), gfull(G, st);
     gcnt.zero(); gacc.zero(); gmax.zero(); gmin.fill_ff();
-    GRL_LAUNCH("group_reduce", nE * 24 + G * 32, group_reduce_kernel, grid_for(nE, 256), 256, 0, st, order, head_bits.p, head_pref.p, R.einfo.p, nE, gcnt.p, gacc.p, gmin.p, gmax.p, grep.p, ghead.p, gfull.p);
+    GRL_LAUNCH("group_reduce", nS * 24 + G * 32, group_reduce_kernel, grid_for(nS, 256), 256, 0, st, order, head_bits.p, head_pref.p, R.einfo.p, nS, gcnt.p, gacc.p, gmin.p, gmax.p, grep.p, ghead.p, gfull.p);
     R.einfo.release();
     const u64 bwt_dummy = A + 1, hocc_dummy = A + 2;  // exact_par_phase.hpp:113-115
     GRL_LAUNCH("group_finalize", 0, group_finalize_kernel, grid_for(G, 256), 256, 0, st, gcnt.p, gmin.p, gmax.p, G, bwt_dummy, hocc_dummy, rflag.p, vflag.p, psym.p);
@@ -501,8 +529,7 @@ void stage_dict(Round& R) {
     exclusive_scan<u32, u32>(rflag.p, rrank.p, G, cnt2.p, st);
     exclusive_scan<u32, u32>(vflag.p, vidx.p, G, cnt2.p + 1, st);
     u32 hc[2];
-    GRL_CUDA(cudaMemcpyAsync(hc, cnt2.p, 8, cudaMemcpyDeviceToHost, st));
-    GRL_CUDA(cudaStreamSynchronize(st));
+    d2h_small(hc, cnt2.p, 8, st);
     const u64 tot = hc[0], nV = hc[1];
     if (tot >= (1ull << 30)) throw Error(GRLGPU_ERR_LIMIT, "more than 2^30 ranks in one round");
     R.tot = tot;
@@ -532,7 +559,7 @@ void stage_dict(Round& R) {
     if (ext_mode) {  // hocc marks in sorted order: group info is read sequentially, entries need no rank of their own
         DevBuf<u32> ginfo(G, st);
         GRL_LAUNCH("pack_ginfo_dense", G * 16, pack_ginfo_dense_kernel, grid_for(G, 256), 256, 0, st, gcnt.p, rflag.p, rrank.p, G, ginfo.p);
-        GRL_LAUNCH("group_apply", nE * 12, group_apply_kernel, grid_for(nE, 256), 256, 0, st, order, head_bits.p, head_pref.p, ginfo.p, nE, (u64)0, 0u, erank.p);
+        GRL_LAUNCH("group_apply", nS * 12, group_apply_kernel, grid_for(nS, 256), 256, 0, st, order, head_bits.p, head_pref.p, ginfo.p, nS, (u64)0, 0u, erank.p);
     } else {
         DevBuf<u32> ginfo(nE, st);  // indexed by head position
         GRL_LAUNCH("pack_ginfo", G * 20, pack_ginfo_kernel, grid_for(G, 256), 256, 0, st, gcnt.p, rflag.p, rrank.p, ghead.p, G, ginfo.p);
@@ -547,9 +574,9 @@ void stage_dict(Round& R) {
     c->lvl_npre = R.n_pre;
 
     if (c->flags & GRLGPU_FLAG_KEEP_DICT) {
-        c->kd_d = R.d; c->kd_nE = nE;
-        c->kd_order.alloc(nE, st);
-        GRL_CUDA(cudaMemcpyAsync(c->kd_order.p, order, nE * 4, cudaMemcpyDeviceToDevice, st));
+        c->kd_d = R.d; c->kd_nE = nE; c->kd_nS = nS;
+        c->kd_order.alloc(nS, st);
+        GRL_CUDA(cudaMemcpyAsync(c->kd_order.p, order, nS * 4, cudaMemcpyDeviceToDevice, st));
     }
     GRL_CUDA(cudaStreamSynchronize(st));  // temporaries above are released in stream order
     c->is_suffix = std::move(is_suffix_next);
@@ -805,8 +832,7 @@ void mg_map_and_rewrite(grlgpu_ctx* c, MgRound& M, Round& GR, const void* cells,
     GRL_LAUNCH("pack_insert", 0, (pack_insert_kernel<CellT>), grid_for(d, 256), 256, 0, st, (const CellT*)cells, GR.ph_pos.p, GR.ph_len.p, (const u64*)nullptr, d, gtable.p, gcap, flag.p);
     GRL_LAUNCH("map_local", 0, (map_local_kernel<CellT>), grid_for(R.d, 256), 256, 0, st, (const CellT*)c->text, R.ph_pos.p, R.ph_len.p, R.occ_slots.p, R.d, (const CellT*)cells, gtable.p, gcap, g_meta, R.table.p, flag.p + 1);
     u32 hflag[2];
-    GRL_CUDA(cudaMemcpyAsync(hflag, flag.p, 8, cudaMemcpyDeviceToHost, st));
-    GRL_CUDA(cudaStreamSynchronize(st));
+    d2h_small(hflag, flag.p, 8, st);
     if (hflag[0]) throw Error(GRLGPU_ERR_STATE, "global table overflow");
     if (hflag[1]) throw Error(GRLGPU_ERR_STATE, "a local phrase is missing from the global dictionary");
     M.t_dict.stop();
@@ -828,25 +854,22 @@ void mg_rank_sort_sym(grlgpu_ctx* c, const u32* lens, const u64* freqs, const vo
     cudaStream_t st = c->st;
     Round& GR = *M.GR;
     const u64 nE = GR.nE, A = c->alphabet;
-    stage_gather<CellT, FIRST, SymT>(GR);
+    stage_gather<CellT, FIRST, SymT>(GR, true);  // first keys + entry ids of the valid entries come with it
     const SymT* D = (const SymT*)GR.D_raw.p;
-    const int sym_bits = bit_width64(A + 1);
-    const int K = std::max(1, 64 / sym_bits);
+    const int sym_bits = GR.sym_bits, K = GR.K;
     const int key_bits = std::min(64, sym_bits * K);
+    const u64 nS = GR.nS;
     M.sym_bytes = sizeof(SymT);
-    // first keys of ALL entries (cheap, sequential); splitters from a regular sample, identical on every rank
-    DevBuf<u64> keys(nE, st);
-    {
-        DevBuf<u32> ids(nE, st);
-        GRL_LAUNCH("sfx_first_key", nE * (sizeof(SymT) + 16), (sfx_first_key_kernel<SymT>), grid_for(nE, 256), 256, 0, st, D, GR.rem.p, nE, A + 1, sym_bits, K, keys.p, ids.p);
-    }
+    // splitters from a regular sample of the first keys, identical on every rank
+    DevBuf<u64> keys = std::move(GR.keys);
+    DevBuf<u32> ids = std::move(GR.vals);
     u64 lo = 0, hi = 0;
     int hi_open = 1;
-    {
-        const u64 ns = std::min<u64>(nE, 1ull << 16), stride = std::max<u64>(1, nE / ns);
+    if (nS) {
+        const u64 ns = std::min<u64>(nS, 1ull << 16), stride = std::max<u64>(1, nS / ns);
         DevBuf<u64> sk(ns, st), sk2(ns, st);
         DevBuf<u32> sv(ns, st), sv2(ns, st);
-        GRL_LAUNCH("key_sample", 0, key_sample_kernel, grid_for(ns, 256), 256, 0, st, keys.p, nE, stride, ns, sk.p, sv.p);
+        GRL_LAUNCH("key_sample", 0, key_sample_kernel, grid_for(ns, 256), 256, 0, st, keys.p, nS, stride, ns, sk.p, sv.p);
         u64 *a = sk.p, *b = sk2.p;
         u32 *av = sv.p, *bv = sv2.p;
         radix_sort_pairs(&a, &av, &b, &bv, ns, key_bits, st);
@@ -862,14 +885,14 @@ void mg_rank_sort_sym(grlgpu_ctx* c, const u32* lens, const u64* freqs, const vo
     DevBuf<u32> mv, mv_alt;
     u64 nL = 0;
     {
-        DevBuf<u32> flags(nE, st), excl(nE, st), cnt(1, st);
-        GRL_LAUNCH("key_range_flags", nE * 12, key_range_flags_kernel, grid_for(nE, 256), 256, 0, st, keys.p, nE, lo, hi, hi_open, flags.p);
-        exclusive_scan<u32, u32>(flags.p, excl.p, nE, cnt.p, st);
-        nL = d2h_scalar(cnt.p, st);
+        DevBuf<u32> flags(nS, st), excl(nS, st), cnt(1, st);
+        GRL_LAUNCH("key_range_flags", nS * 12, key_range_flags_kernel, grid_for(nS, 256), 256, 0, st, keys.p, nS, lo, hi, hi_open, flags.p);
+        exclusive_scan<u32, u32>(flags.p, excl.p, nS, cnt.p, st);
+        nL = nS ? d2h_scalar(cnt.p, st) : 0;
         mk.alloc(nL, st); mk_alt.alloc(nL, st); mv.alloc(nL, st); mv_alt.alloc(nL, st);
-        GRL_LAUNCH("key_range_compact", nE * 16, key_range_compact_kernel, grid_for(nE, 256), 256, 0, st, keys.p, flags.p, excl.p, nE, mk.p, mv.p);
+        GRL_LAUNCH("key_range_compact", nS * 20, key_range_compact_kernel, grid_for(nS, 256), 256, 0, st, keys.p, ids.p, flags.p, excl.p, nS, mk.p, mv.p);
     }
-    keys.release();
+    keys.release(); ids.release();
     M.nL = nL;
     const u64 n_words = div_up(std::max<u64>(nL, 1), 32);
     M.head_bits.alloc(n_words, st);
@@ -941,8 +964,7 @@ void mg_rank_sort_sym(grlgpu_ctx* c, const u32* lens, const u64* freqs, const vo
     exclusive_scan<u32, u32>(M.rflag.p, M.rrank.p, G, cnt2.p, st);
     exclusive_scan<u32, u32>(vflag.p, vidx.p, G, cnt2.p + 1, st);
     u32 hc[2];
-    GRL_CUDA(cudaMemcpyAsync(hc, cnt2.p, 8, cudaMemcpyDeviceToHost, st));
-    GRL_CUDA(cudaStreamSynchronize(st));
+    d2h_small(hc, cnt2.p, 8, st);
     M.tot_local = hc[0];
     const u64 nV = hc[1];
     {   // preliminary BWT of my slice: maximal runs over my valid groups (the caller merges across rank boundaries)
@@ -1297,11 +1319,11 @@ int grlgpu_fetch_dictionary(grlgpu_ctx* ctx, uint64_t* syms, uint64_t* lens, uin
     if (!ctx) return GRLGPU_ERR_ARG;
     if (ctx->round == 0 || !(ctx->flags & GRLGPU_FLAG_KEEP_DICT) || !ctx->kd_order.p) return GRLGPU_ERR_STATE;
     return guarded(ctx, [&] {
-        const u64 d = ctx->kd_d, nE = ctx->kd_nE;
-        std::vector<u32> order(nE), phr_of(nE), off(d + 1), len(d);
+        const u64 d = ctx->kd_d, nE = ctx->kd_nE, nS = ctx->kd_nS;
+        std::vector<u32> order(nS), phr_of(nE), off(d + 1), len(d);
         std::vector<u64> freq(d), meta(d);
         std::vector<u8> Draw(nE * (u64)ctx->lvl_sym_bytes);
-        GRL_CUDA(cudaMemcpy(order.data(), ctx->kd_order.p, nE * 4, cudaMemcpyDeviceToHost));
+        GRL_CUDA(cudaMemcpy(order.data(), ctx->kd_order.p, nS * 4, cudaMemcpyDeviceToHost));
         GRL_CUDA(cudaMemcpy(phr_of.data(), ctx->kd_phr_of.p, nE * 4, cudaMemcpyDeviceToHost));
         GRL_CUDA(cudaMemcpy(off.data(), ctx->kd_off.p, (d + 1) * 4, cudaMemcpyDeviceToHost));
         GRL_CUDA(cudaMemcpy(len.data(), ctx->kd_len.p, d * 4, cudaMemcpyDeviceToHost));
@@ -1309,7 +1331,7 @@ int grlgpu_fetch_dictionary(grlgpu_ctx* ctx, uint64_t* syms, uint64_t* lens, uin
         GRL_CUDA(cudaMemcpy(meta.data(), ctx->kd_meta.p, d * 8, cudaMemcpyDeviceToHost));
         GRL_CUDA(cudaMemcpy(Draw.data(), ctx->kd_D.p, Draw.size(), cudaMemcpyDeviceToHost));
         u64 k = 0, so = 0;
-        for (u64 i = 0; i < nE; i++) {  // full-phrase entries in suffix order = phrases in A.2 order
+        for (u64 i = 0; i < nS; i++) {  // full-phrase entries in suffix order = phrases in A.2 order
             const u32 e = order[i], ph = phr_of[e];
             if (e != off[ph]) continue;
             if (lens) lens[k] = len[ph];

@@ -190,8 +190,7 @@ struct BitmapCompactor {
         GRL_LAUNCH("bitmap_count", n_bits / 8, bitmap_count_kernel, (unsigned)tiles, BC_THREADS, 0, st, bits, n_bits, tile_count.p);
         exclusive_scan<u32, u64>(tile_count.p, tile_off.p, tiles, total.p, st);
         u64 h = 0;
-        GRL_CUDA(cudaMemcpyAsync(&h, total.p, sizeof(u64), cudaMemcpyDeviceToHost, st));
-        GRL_CUDA(cudaStreamSynchronize(st));
+        d2h_small(&h, total.p, sizeof(u64), st);
         return h;
     }
     // phase 2: write positions

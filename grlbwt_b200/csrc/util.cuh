@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <algorithm>
 #include <map>
 #include <stdexcept>
@@ -244,6 +245,23 @@ struct Profiler {
     ~Profiler() { resolve(); for (auto e : pool) cudaEventDestroy(e); }
 };
 inline thread_local Profiler* g_prof = nullptr;
+
+// Small device -> host readbacks (counts, flags) between the stages of a round. They go through a kernel that writes
+// to mapped pinned memory instead of a copy-engine transfer: a DMA job would queue behind the multi-GB asynchronous
+// level copies of grlgpu_fetch_level_async and stall the round for their whole duration.
+static __global__ void copy_small_kernel(const u32* __restrict__ src, u32* __restrict__ dst, u32 n_words) {
+    if (threadIdx.x < n_words) dst[threadIdx.x] = src[threadIdx.x];
+}
+inline void d2h_small(void* host_dst, const void* dev_src, size_t bytes, cudaStream_t st) {
+    static thread_local u32* slots = nullptr;
+    if (bytes % 4 || bytes > 256) throw Error(GRLGPU_ERR_ARG, "d2h_small: unsupported size");
+    if (!slots) GRL_CUDA(cudaHostAlloc((void**)&slots, 256, cudaHostAllocMapped | cudaHostAllocPortable));
+    copy_small_kernel<<<1, 64, 0, st>>>((const u32*)dev_src, slots, (u32)(bytes / 4));
+    GRL_CUDA(cudaGetLastError());
+    GRL_CUDA(cudaStreamSynchronize(st));
+    memcpy(host_dst, slots, bytes);
+}
+
 
 struct ProfScope {
     Profiler* p; cudaStream_t st; cudaEvent_t a{}, b{}; const char* name; u64 bytes;

@@ -28,7 +28,7 @@ def run(name, arr, prof=False):
                   f"B_r={r.algorithmic_bytes / 1e6:.1f}MB -> {r.algorithmic_bytes / r.device_ms / 1e6:.1f} GB/s", flush=True)
             if prof:
                 pr = ctx.profile()
-                for k, (nl, ms, by) in sorted(pr.items(), key=lambda kv: -kv[1][1])[:12]:
+                for k, (nl, ms, by) in sorted(pr.items(), key=lambda kv: -kv[1][1])[:int(__import__('os').environ.get('QT_TOP', '12'))]:
                     print(f"      {k:22s} x{nl:4d} {ms:9.3f} ms  model {by / 1e6:10.1f} MB  {by / max(ms, 1e-9) / 1e6:8.1f} GB/s")
                 ctx.profile_reset()
             if r.done:
