@@ -216,19 +216,25 @@ template <class KeyT, int ITEMS>
 __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const KeyT* __restrict__ keys, u64 n, int shift, u32* __restrict__ hist, u64 tiles) {
     __shared__ u32 cnt[256];
     cnt[threadIdx.x] = 0;
-    __syncthreads();
     const u64 base = (u64)blockIdx.x * (RS_THREADS * ITEMS);
-#pragma unroll 4
+    KeyT k[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {  // all loads in flight before the first atomic
+        const u64 idx = base + (u64)i * RS_THREADS + threadIdx.x;
+        k[i] = idx < n ? keys[idx] : (KeyT)0;
+    }
+    __syncthreads();
+#pragma unroll
     for (int i = 0; i < ITEMS; i++) {
         const u64 idx = base + (u64)i * RS_THREADS + threadIdx.x;
-        if (idx < n) atomicAdd(&cnt[(u32)(keys[idx] >> shift) & 255u], 1u);
+        if (idx < n) atomicAdd(&cnt[(u32)(k[i] >> shift) & 255u], 1u);
     }
     __syncthreads();
     hist[(u64)threadIdx.x * tiles + blockIdx.x] = cnt[threadIdx.x];
 }
 
-template <class KeyT, int ITEMS>
-__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const KeyT* __restrict__ keys_in, const u32* __restrict__ vals_in, KeyT* __restrict__ keys_out,
+template <class KeyT, int ITEMS, int MINB>
+__global__ void __launch_bounds__(RS_THREADS, MINB) radix_scatter_kernel(const KeyT* __restrict__ keys_in, const u32* __restrict__ vals_in, KeyT* __restrict__ keys_out,
                                                                    u32* __restrict__ vals_out, u64 n, int shift, const u64* __restrict__ goff, u64 tiles) {
     constexpr int TILE = RS_THREADS * ITEMS, WARP_ITEMS = TILE / RS_WARPS;
     extern __shared__ __align__(16) unsigned char rs_smem[];
@@ -237,7 +243,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const KeyT* _
     u32* s_cnt = s_vals + TILE;               // [RS_WARPS][257]
     u32* s_dstart = s_cnt + RS_WARPS * 257;   // [256] tile-local start of each digit
     u32* s_scan = s_dstart + 256;             // 33 scratch
-    __shared__ u64 s_goff[256];
+    __shared__ u64 s_delta[256];              // global offset of digit d minus its tile-local start
 
     const u32 lane = lane_id(), warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < RS_WARPS * 257; i += RS_THREADS) s_cnt[i] = 0;
@@ -266,17 +272,15 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const KeyT* _
     // per digit: exclusive prefix over warps, tile count
     {
         const u32 d = threadIdx.x;
-        u32 run = 0;
+        const u64 my_goff = goff[(u64)d * tiles + blockIdx.x];
+        u32 c[RS_WARPS], run = 0;
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; w++) {
-            u32 t = s_cnt[w * 257 + d];
-            s_cnt[w * 257 + d] = run;
-            run += t;
-        }
+        for (int w = 0; w < RS_WARPS; w++) { c[w] = s_cnt[w * 257 + d]; run += c[w]; }
         u32 tot;
         u32 ex = block_exclusive_sum<u32>(run, s_scan, tot);
-        s_dstart[d] = ex;
-        s_goff[d] = goff[(u64)d * tiles + blockIdx.x];
+        s_delta[d] = my_goff - ex;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) { s_cnt[w * 257 + d] = ex; ex += c[w]; }  // tile-local start of (warp, digit)
     }
     __syncthreads();
 #pragma unroll
@@ -284,7 +288,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const KeyT* _
         const u64 idx = tile_base + (u64)warp * WARP_ITEMS + (u64)r * 32 + lane;
         if (idx < n) {
             const u32 d = (u32)(key[r] >> shift) & 255u;
-            const u32 pos = s_dstart[d] + wc[d] + rnk[r];
+            const u32 pos = wc[d] + rnk[r];
             s_keys[pos] = key[r];
             s_vals[pos] = val[r];
         }
@@ -295,10 +299,132 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const KeyT* _
     for (u32 i = threadIdx.x; i < valid; i += RS_THREADS) {
         const KeyT k = s_keys[i];
         const u32 d = (u32)(k >> shift) & 255u;
-        const u64 g = s_goff[d] + (i - s_dstart[d]);
+        const u64 g = s_delta[d] + i;
         keys_out[g] = k;
         vals_out[g] = s_vals[i];
     }
+}
+
+// Pipelined variant: persistent CTAs; the NEXT tile of a CTA streams into shared memory with 16-byte cp.async copies while
+// the current one is ranked, permuted and written out, so every resident CTA always has a tile of loads in flight
+// (the one-tile-per-CTA kernel above is load-latency-bound: all warps of a CTA wait for the same loads). The input
+// buffer of a tile doubles as its sorted staging area once the items sit in registers: two buffers per CTA.
+template <class KeyT, int ITEMS>
+constexpr size_t rsp_smem_bytes() {
+    return 2 * (size_t)RS_THREADS * ITEMS * (sizeof(KeyT) + sizeof(u32)) + (size_t)RS_WARPS * 257 * sizeof(u32) + 256 * sizeof(u64) + 256 * sizeof(u32) + 34 * sizeof(u32);
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, u32 src_bytes) {
+    const u32 d = (u32)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+template <class T, int TILE>
+__device__ __forceinline__ void rsp_prefetch(T* sdst, const T* __restrict__ gsrc, u64 base, u64 n) {
+    constexpr int PER = 16 / sizeof(T), CHUNKS = TILE / PER;
+    const u64 left = n - base;  // items of this tile that exist (>= 1)
+    for (int c = threadIdx.x; c < CHUNKS; c += RS_THREADS) {
+        const u64 first = (u64)c * PER;
+        const u32 bytes = first >= left ? 0u : (left - first >= (u64)PER ? 16u : (u32)((left - first) * sizeof(T)));
+        cp_async16(sdst + first, gsrc + (bytes ? base + first : base), bytes);  // missing bytes are zero-filled
+    }
+}
+template <class KeyT, int ITEMS>
+__global__ void __launch_bounds__(RS_THREADS) radix_scatter_pipe_kernel(const KeyT* __restrict__ keys_in, const u32* __restrict__ vals_in, KeyT* __restrict__ keys_out,
+                                                                        u32* __restrict__ vals_out, u64 n, int shift, const u64* __restrict__ goff, u64 tiles) {
+    constexpr int TILE = RS_THREADS * ITEMS, WARP_ITEMS = TILE / RS_WARPS;
+    constexpr size_t BUF = (size_t)TILE * (sizeof(KeyT) + sizeof(u32));
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    u32* s_cnt = (u32*)(rs_smem + 2 * BUF);                 // [RS_WARPS][257]
+    u64* s_delta = (u64*)(s_cnt + RS_WARPS * 257);          // [256] global offset of digit d minus its tile-local start (8 * 257 words: 8-byte aligned)
+    u32* s_dstart = (u32*)(s_delta + 256);                  // [256]
+    u32* s_scan = s_dstart + 256;                           // 33 scratch
+
+    const u32 lane = lane_id(), warp = threadIdx.x >> 5;
+    u32* wc = s_cnt + warp * 257;
+    u64 tile = blockIdx.x;
+    if (tile >= tiles) return;
+    rsp_prefetch<KeyT, TILE>((KeyT*)rs_smem, keys_in, tile * TILE, n);
+    rsp_prefetch<u32, TILE>((u32*)(rs_smem + (size_t)TILE * sizeof(KeyT)), vals_in, tile * TILE, n);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    for (u32 it = 0; tile < tiles; tile += gridDim.x, it ^= 1u) {
+        KeyT* s_keys = (KeyT*)(rs_smem + it * BUF);
+        u32* s_vals = (u32*)(s_keys + TILE);
+        for (int i = threadIdx.x; i < RS_WARPS * 257; i += RS_THREADS) s_cnt[i] = 0;
+        const u64 my_goff = goff[(u64)threadIdx.x * tiles + tile];
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();  // this tile has landed; everyone is done with the other buffer (output of the previous tile)
+        const u64 next = tile + gridDim.x;
+        if (next < tiles) {
+            unsigned char* nb = rs_smem + (it ^ 1u) * BUF;
+            rsp_prefetch<KeyT, TILE>((KeyT*)nb, keys_in, next * TILE, n);
+            rsp_prefetch<u32, TILE>((u32*)(nb + (size_t)TILE * sizeof(KeyT)), vals_in, next * TILE, n);
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+
+        const u64 tile_base = tile * TILE;
+        KeyT key[ITEMS];
+        u32 val[ITEMS];
+        u32 rnk[ITEMS];
+#pragma unroll
+        for (int r = 0; r < ITEMS; r++) {
+            const u32 li = warp * WARP_ITEMS + r * 32 + lane;
+            const bool ok = tile_base + li < n;
+            key[r] = s_keys[li];
+            val[r] = s_vals[li];
+            const u32 d = ok ? ((u32)(key[r] >> shift) & 255u) : 256u;
+            const u32 m = __match_any_sync(0xffffffffu, d);
+            const u32 b = wc[d];
+            __syncwarp();
+            if (lane == (u32)(__ffs(m) - 1)) wc[d] = b + __popc(m);
+            __syncwarp();
+            rnk[r] = b + __popc(m & lanemask_lt());
+        }
+        __syncthreads();  // items sit in registers: the buffer is free to become the sorted staging area
+        {
+            const u32 d = threadIdx.x;
+            u32 run = 0;
+#pragma unroll
+            for (int w = 0; w < RS_WARPS; w++) {
+                const u32 t = s_cnt[w * 257 + d];
+                s_cnt[w * 257 + d] = run;
+                run += t;
+            }
+            u32 tot;
+            const u32 ex = block_exclusive_sum<u32>(run, s_scan, tot);
+            s_dstart[d] = ex;
+            s_delta[d] = my_goff - ex;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < ITEMS; r++) {
+            const u32 li = warp * WARP_ITEMS + r * 32 + lane;
+            if (tile_base + li < n) {
+                const u32 d = (u32)(key[r] >> shift) & 255u;
+                const u32 pos = s_dstart[d] + wc[d] + rnk[r];
+                s_keys[pos] = key[r];
+                s_vals[pos] = val[r];
+            }
+        }
+        __syncthreads();
+        const u64 rem = n - tile_base;
+        const u32 valid = rem < (u64)TILE ? (u32)rem : (u32)TILE;
+        for (u32 i = threadIdx.x; i < valid; i += RS_THREADS) {
+            const KeyT k = s_keys[i];
+            const u32 d = (u32)(k >> shift) & 255u;
+            const u64 g = s_delta[d] + i;
+            keys_out[g] = k;
+            vals_out[g] = s_vals[i];
+        }
+    }
+}
+inline int rs_pipe_setting() {  // measured on B200: the pipelined variant is slower (2.4 vs 3.5 TB/s), the shared-memory pipe is what binds
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GRL_RS_PIPE"); v = e ? atoi(e) : 0; }
+    return v;
+}
+inline int rs_minb_setting() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GRL_RS_MINB"); v = e ? atoi(e) : 1; }
+    return v;
 }
 
 // one stable partition pass on the 8-bit digit at `shift` (also the building block of the LSD sort below)
@@ -306,14 +432,34 @@ template <class KeyT, int ITEMS>
 inline void radix_pass(KeyT** keys, u32** vals, KeyT** keys_alt, u32** vals_alt, u64 n, int shift, DevBuf<u32>& hist, DevBuf<u64>& goff, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        GRL_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<KeyT, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<KeyT, ITEMS>()));
+        GRL_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<KeyT, ITEMS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<KeyT, ITEMS>()));
+        GRL_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<KeyT, ITEMS, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<KeyT, ITEMS>()));
+        GRL_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<KeyT, ITEMS, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
     const u64 tiles = div_up(n, RS_THREADS * ITEMS);
     GRL_LAUNCH("radix_hist", n * sizeof(KeyT), (radix_hist_kernel<KeyT, ITEMS>), (unsigned)tiles, RS_THREADS, 0, st, *keys, n, shift, hist.p, tiles);
     exclusive_scan<u32, u64>(hist.p, goff.p, 256 * tiles, nullptr, st);
-    GRL_LAUNCH("radix_scatter", n * 2 * (sizeof(KeyT) + 4), (radix_scatter_kernel<KeyT, ITEMS>), (unsigned)tiles, RS_THREADS, (rs_smem_bytes<KeyT, ITEMS>()), st, *keys, *vals,
-               *keys_alt, *vals_alt, n, shift, goff.p, tiles);
+    if (rs_pipe_setting()) {
+        static int pipe_grid = 0;
+        if (!pipe_grid) {
+            GRL_CUDA(cudaFuncSetAttribute(radix_scatter_pipe_kernel<KeyT, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsp_smem_bytes<KeyT, ITEMS>()));
+            GRL_CUDA(cudaFuncSetAttribute(radix_scatter_pipe_kernel<KeyT, ITEMS>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+            int dev = 0, sms = 0, per_sm = 0;
+            GRL_CUDA(cudaGetDevice(&dev));
+            GRL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            GRL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, radix_scatter_pipe_kernel<KeyT, ITEMS>, RS_THREADS, rsp_smem_bytes<KeyT, ITEMS>()));
+            pipe_grid = sms * std::max(1, per_sm);
+        }
+        GRL_LAUNCH("radix_scatter", n * 2 * (sizeof(KeyT) + 4), (radix_scatter_pipe_kernel<KeyT, ITEMS>), (unsigned)std::min<u64>(tiles, (u64)pipe_grid), RS_THREADS,
+                   (rsp_smem_bytes<KeyT, ITEMS>()), st, *keys, *vals, *keys_alt, *vals_alt, n, shift, goff.p, tiles);
+    } else if (rs_minb_setting() == 5) {
+        GRL_LAUNCH("radix_scatter", n * 2 * (sizeof(KeyT) + 4), (radix_scatter_kernel<KeyT, ITEMS, 5>), (unsigned)tiles, RS_THREADS, (rs_smem_bytes<KeyT, ITEMS>()), st, *keys, *vals,
+                   *keys_alt, *vals_alt, n, shift, goff.p, tiles);
+    } else {
+        GRL_LAUNCH("radix_scatter", n * 2 * (sizeof(KeyT) + 4), (radix_scatter_kernel<KeyT, ITEMS, 4>), (unsigned)tiles, RS_THREADS, (rs_smem_bytes<KeyT, ITEMS>()), st, *keys, *vals,
+                   *keys_alt, *vals_alt, n, shift, goff.p, tiles);
+    }
     KeyT* tk = *keys; *keys = *keys_alt; *keys_alt = tk;
     u32* tv = *vals; *vals = *vals_alt; *vals_alt = tv;
 }

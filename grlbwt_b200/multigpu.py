@@ -157,6 +157,20 @@ def _all_gather_v(part, counts, engine):
     out = engine.alloc(sum(counts), part.dtype)
     off = 0
     me = dist.get_rank()
+    if not _staged() and part.is_cuda and max(counts) > 0:
+        # NCCL: ONE all-gather of slices padded to the longest part (hash partitions are near-equal), then a
+        # device-side compaction; one collective at NVSwitch bandwidth instead of a chain of broadcasts
+        mx = max(counts)
+        send = torch.empty(mx, dtype=part.dtype, device=part.device)
+        send[: counts[me]].copy_(part[: counts[me]])
+        padded = torch.empty(mx * len(counts), dtype=part.dtype, device=part.device)
+        dist.all_gather_into_tensor(padded, send)
+        for r, c in enumerate(counts):
+            if c:
+                out[off: off + c].copy_(padded[r * mx: r * mx + c])
+            off += c
+        _fence(out)
+        return out
     for r, c in enumerate(counts):
         if c:
             sl = out[off: off + c]

@@ -26,7 +26,7 @@ def test_scan(n):
     assert np.array_equal(out, ref)
 
 
-@pytest.mark.parametrize("n,bits", [(2, 8), (100, 16), (4096, 64), (4097, 24), (100000, 40), ((1 << 20) + 17, 64), (300000, 3)])
+@pytest.mark.parametrize("n,bits", [(2, 8), (100, 16), (4096, 64), (4097, 24), (100000, 40), ((1 << 20) + 17, 64), (300000, 3), (5_000_003, 33)])
 def test_radix_sort(n, bits):
     rng = np.random.default_rng(n + bits)
     keys = rng.integers(0, 1 << 63, size=n, dtype=np.uint64)
