@@ -13,14 +13,49 @@ constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
+// a thread's SCAN_ITEMS consecutive items move as 16-byte vectors when the whole run exists and the array is 16-byte aligned
+template <class T>
+__device__ __forceinline__ void scan_load(const T* in, u64 base, u64 n, bool vec, T (&v)[SCAN_ITEMS]) {
+    constexpr int NV = SCAN_ITEMS * sizeof(T) / 16, PER = 16 / sizeof(T);
+    if (vec && base + SCAN_ITEMS <= n) {
+        const uint4* p = reinterpret_cast<const uint4*>(in + base);
+#pragma unroll
+        for (int q = 0; q < NV; q++) {
+            const uint4 x = p[q];
+            memcpy(&v[q * PER], &x, 16);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++) v[i] = (base + i < n) ? in[base + i] : T(0);
+    }
+}
+template <class T>
+__device__ __forceinline__ void scan_store(T* out, u64 base, u64 n, bool vec, const T (&v)[SCAN_ITEMS]) {
+    constexpr int NV = SCAN_ITEMS * sizeof(T) / 16, PER = 16 / sizeof(T);
+    if (vec && base + SCAN_ITEMS <= n) {
+        uint4* p = reinterpret_cast<uint4*>(out + base);
+#pragma unroll
+        for (int q = 0; q < NV; q++) {
+            uint4 x;
+            memcpy(&x, &v[q * PER], 16);
+            p[q] = x;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++)
+            if (base + i < n) out[base + i] = v[i];
+    }
+}
+
 template <class TIn, class TOut>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums_kernel(const TIn* __restrict__ in, TOut* __restrict__ partial, u64 n) {
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums_kernel(const TIn* __restrict__ in, TOut* __restrict__ partial, u64 n, bool vec) {
     __shared__ TOut sm[33];
     const u64 base = (u64)blockIdx.x * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
+    TIn x[SCAN_ITEMS];
+    scan_load<TIn>(in, base, n, vec, x);
     TOut s = 0;
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++)
-        if (base + i < n) s += (TOut)in[base + i];
+    for (int i = 0; i < SCAN_ITEMS; i++) s += (TOut)x[i];
     TOut tot;
     block_exclusive_sum<TOut>(s, sm, tot);
     if (threadIdx.x == 0) partial[blockIdx.x] = tot;
@@ -53,23 +88,23 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_single_block_kernel(const T
 }
 
 template <class TIn, class TOut>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const TIn* in, TOut* out, const TOut* __restrict__ tile_prefix, u64 n) {
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const TIn* in, TOut* out, const TOut* __restrict__ tile_prefix, u64 n, bool vec) {
     __shared__ TOut sm[33];
     const u64 base = (u64)blockIdx.x * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
-    TOut v[SCAN_ITEMS];
+    TIn x[SCAN_ITEMS];
+    scan_load<TIn>(in, base, n, vec, x);
     TOut s = 0;
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) {
-        v[i] = (base + i < n) ? (TOut)in[base + i] : TOut(0);
-        s += v[i];
-    }
+    for (int i = 0; i < SCAN_ITEMS; i++) s += (TOut)x[i];
     TOut tot;
     TOut ex = block_exclusive_sum<TOut>(s, sm, tot) + tile_prefix[blockIdx.x];
+    TOut v[SCAN_ITEMS];
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; i++) {
-        if (base + i < n) out[base + i] = ex;
-        ex += v[i];
+        v[i] = ex;
+        ex += (TOut)x[i];
     }
+    scan_store<TOut>(out, base, n, vec, v);
 }
 
 // total_dev (optional, device pointer) receives the sum of all inputs.
@@ -81,9 +116,10 @@ void exclusive_scan(const TIn* in, TOut* out, u64 n, TOut* total_dev, cudaStream
     }
     const u64 tiles = div_up(n, SCAN_TILE);
     DevBuf<TOut> partial(tiles, st);
-    GRL_LAUNCH("scan_tile_sums", n * sizeof(TIn), (scan_tile_sums_kernel<TIn, TOut>), (unsigned)tiles, SCAN_THREADS, 0, st, in, partial.p, n);
+    const bool vec = (((uintptr_t)in | (uintptr_t)out) & 15) == 0;
+    GRL_LAUNCH("scan_tile_sums", n * sizeof(TIn), (scan_tile_sums_kernel<TIn, TOut>), (unsigned)tiles, SCAN_THREADS, 0, st, in, partial.p, n, vec);
     exclusive_scan<TOut, TOut>(partial.p, partial.p, tiles, total_dev, st);
-    GRL_LAUNCH("scan_apply", n * (sizeof(TIn) + sizeof(TOut)), (scan_apply_kernel<TIn, TOut>), (unsigned)tiles, SCAN_THREADS, 0, st, in, out, partial.p, n);
+    GRL_LAUNCH("scan_apply", n * (sizeof(TIn) + sizeof(TOut)), (scan_apply_kernel<TIn, TOut>), (unsigned)tiles, SCAN_THREADS, 0, st, in, out, partial.p, n, vec);
 }
 
 // ------------------------------------------------------------------------------------------------
