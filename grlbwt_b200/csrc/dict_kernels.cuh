@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(256) ext_keys_kernel(const u32* __restrict__ a
     const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nA) return;
     const u32 i = apos[j], e = order[i];
-    const u64 r = rem[e];
+    const u64 r = ld_gather4(rem + e);
     u64 key = 0;
     for (int t = 0; t < K; t++) {
         const u64 pos = dpt + (u64)t;
@@ -248,10 +248,14 @@ __global__ void __launch_bounds__(256) ext_keys_kernel(const u32* __restrict__ a
     gflag[j] = (head_bits[i >> 5] >> (i & 31)) & 1u;
 }
 // second sort key: index of the (unresolved) group the active element belongs to
-static __global__ void __launch_bounds__(256) ext_group_keys_kernel(const u32* __restrict__ vals, const u32* __restrict__ gflag, const u32* __restrict__ gexcl, u64 nA,
-                                                                    u64* __restrict__ keys) {
+// (gid[j] = exclusive count of group heads + own flag - 1, folded in place first so that the random gather reads ONE array)
+static __global__ void __launch_bounds__(256) ext_gid_kernel(const u32* __restrict__ gflag, u32* __restrict__ gexcl, u64 nA) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nA) gexcl[j] = gexcl[j] + gflag[j] - 1;
+}
+static __global__ void __launch_bounds__(256) ext_group_keys_kernel(const u32* __restrict__ vals, const u32* __restrict__ gid, u64 nA, u64* __restrict__ keys) {
     const u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < nA) { const u32 j = vals[q]; keys[q] = (u64)(gexcl[j] + gflag[j] - 1); }
+    if (q < nA) keys[q] = (u64)ld_gather4(gid + vals[q]);
 }
 static __global__ void __launch_bounds__(256) ext_heads_kernel(const u32* __restrict__ vals, const u64* __restrict__ gkeys, const u64* __restrict__ nk, u64 nA,
                                                                u32* __restrict__ flags) {
@@ -368,7 +372,7 @@ static __global__ void __launch_bounds__(256) group_reduce_kernel(const u32* __r
         g = head_pref[i >> 5] + __popc(upto) - 1;                // dense group index in sorted order
         hd = (hw >> (i & 31)) & 1u;
         nh = i + 1 == nE || ((head_bits[(i + 1) >> 5] >> ((i + 1) & 31)) & 1u);
-        const ulonglong2 ei = einfo[e];
+        const ulonglong2 ei = ld_gather16(einfo + e);
         if (ei.y & EI_VALID) {
             is_full = (ei.y & EI_FULL) != 0;
             cnt = 1u | (is_full ? 0x80000000u : 0u);
@@ -466,19 +470,20 @@ __global__ void __launch_bounds__(256) rules_kernel(const u32* __restrict__ gcnt
     const u32 u = rrank[g];
     has_hocc[u] = (gcnt[g] & 0x7fffffffu) > 1;
     u32 pos = grep[g];
-    if (rem[pos] == 0) {  // :38-41 one-symbol suffix
+    if (ld_gather(rem + pos) == 0) {  // :38-41 one-symbol suffix
         rule_l[u] = (SymT)metasym_dummy;
-        rule_r[u] = D[pos];
+        rule_r[u] = ld_gather(D + pos);
         return;
     }
     pos++;
-    while (erank[pos] == 0xffffffffu && rem[pos] != 0) pos++;  // :43-44
-    const SymT l_sym = D[pos - 1];
-    if (erank[pos] != 0xffffffffu) {  // :49-80
+    u32 er = ld_gather(erank + pos);
+    while (er == 0xffffffffu && ld_gather(rem + pos) != 0) { pos++; er = ld_gather(erank + pos); }  // :43-44
+    const SymT l_sym = ld_gather(D + pos - 1);
+    if (er != 0xffffffffu) {  // :49-80
         rule_l[u] = l_sym;
-        rule_r[u] = (SymT)(alph3 + erank[pos]);
+        rule_r[u] = (SymT)(alph3 + er);
     } else {  // :81-85
-        const SymT r_sym = D[pos];
+        const SymT r_sym = ld_gather(D + pos);
         rule_l[u] = (SymT)metasym_dummy;
         rule_r[u] = is_suffix((u64)r_sym) ? r_sym : l_sym;
     }

@@ -236,9 +236,10 @@ void stage_dedup(Round& R) {
     static int n_sm = 0;  // one per CellT instantiation
     if (!n_sm) {
         GRL_CUDA(cudaFuncSetAttribute(dedup_cached_kernel<CellT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fd_smem_bytes<CellT>()));
+        GRL_CUDA(cudaFuncSetAttribute(dedup_cached_kernel<CellT>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         GRL_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device));
     }
-    const unsigned fd_grid = (unsigned)std::min<u64>(n_tiles, (u64)n_sm);  // persistent CTAs (one per SM), tiles strided
+    const unsigned fd_grid = (unsigned)std::min<u64>(n_tiles, (u64)n_sm * FD_CTAS_PER_SM);  // persistent CTAs, tiles strided
     // the first tiles always run through the cached kernel and report how many phrases missed the caches;
     // the rest of the text takes the cached kernel (duplicate-heavy) or the thread-per-phrase kernel (unique-heavy)
     const bool force_uncached = (c->flags & GRLGPU_FLAG_FORCE_UNCACHED) != 0;
@@ -439,7 +440,8 @@ void stage_dict(Round& R) {
                 exclusive_scan<u32, u32>(gflag.p, gexcl.p, nA, cnt.p, st);
                 const u64 n_groups = d2h_scalar(cnt.p, st);
                 radix_sort_pairs(&akp, &avp, &aka, &ava, nA, std::min(64, sym_bits * K), st);  // by the extension key ...
-                GRL_LAUNCH("ext_group_keys", nA * 16, ext_group_keys_kernel, grid_for(nA, 256), 256, 0, st, avp, gflag.p, gexcl.p, nA, akp);
+                GRL_LAUNCH("ext_gid", nA * 12, ext_gid_kernel, grid_for(nA, 256), 256, 0, st, gflag.p, gexcl.p, nA);
+                GRL_LAUNCH("ext_group_keys", nA * 16, ext_group_keys_kernel, grid_for(nA, 256), 256, 0, st, avp, gexcl.p, nA, akp);
                 radix_sort_pairs(&akp, &avp, &aka, &ava, nA, std::max(1, bit_width64(n_groups)), st);  // ... then, stably, by group
                 GRL_LAUNCH("ext_heads", nA * 24, ext_heads_kernel, grid_for(nA, 256), 256, 0, st, avp, akp, nk.p, nA, flags.p);
                 GRL_LAUNCH("ext_writeback", nA * 16, ext_writeback_kernel, grid_for(nA, 256), 256, 0, st, apos.p, avp, ev.p, flags.p, nA, order_w, head_bits.p);
@@ -927,7 +929,8 @@ void mg_rank_sort_sym(grlgpu_ctx* c, const u32* lens, const u64* freqs, const vo
         exclusive_scan<u32, u32>(gflag.p, gexcl.p, nA, cnt.p, st);
         const u64 n_groups = d2h_scalar(cnt.p, st);
         radix_sort_pairs(&akp, &avp, &aka, &ava, nA, key_bits, st);
-        GRL_LAUNCH("ext_group_keys", nA * 16, ext_group_keys_kernel, grid_for(nA, 256), 256, 0, st, avp, gflag.p, gexcl.p, nA, akp);
+        GRL_LAUNCH("ext_gid", nA * 12, ext_gid_kernel, grid_for(nA, 256), 256, 0, st, gflag.p, gexcl.p, nA);
+        GRL_LAUNCH("ext_group_keys", nA * 16, ext_group_keys_kernel, grid_for(nA, 256), 256, 0, st, avp, gexcl.p, nA, akp);
         radix_sort_pairs(&akp, &avp, &aka, &ava, nA, std::max(1, bit_width64(n_groups)), st);
         GRL_LAUNCH("ext_heads", nA * 24, ext_heads_kernel, grid_for(nA, 256), 256, 0, st, avp, akp, nk.p, nA, flags.p);
         GRL_LAUNCH("ext_writeback", nA * 16, ext_writeback_kernel, grid_for(nA, 256), 256, 0, st, apos.p, avp, ev.p, flags.p, nA, order_w, M.head_bits.p);

@@ -327,7 +327,8 @@ __global__ void __launch_bounds__(256) phrase_insert_kernel(const CellT* __restr
 }
 
 // ---- fused, cached variant (duplicate-heavy rounds) ----
-constexpr int FD_THREADS = 1024;               // one CTA per SM
+constexpr int FD_THREADS = 1024;               // one CTA per SM (2 x 512 threads with half-size tiles and caches measured the same)
+constexpr int FD_CTAS_PER_SM = 1;
 constexpr int FD_TILE_BYTES = 32768;           // staged cells per tile: 32768 / sizeof(CellT) cells
 constexpr int FD_HALO_WORDS = 4;               // look-ahead for the end of a tile's last phrases: 128 cells
 constexpr int FD_HALO = FD_HALO_WORDS * 32;
@@ -377,7 +378,7 @@ __device__ __forceinline__ void fd_pack_key(const unsigned char* s_cells, u32 sl
 
 // stats[0] += phrases that took the global path, stats[1] += phrases seen (the host reads them after a pilot launch)
 template <class CellT>
-__global__ void __launch_bounds__(FD_THREADS, 1) dedup_cached_kernel(const CellT* __restrict__ text, u64 n, const u32* __restrict__ start_bits,
+__global__ void __launch_bounds__(FD_THREADS, FD_CTAS_PER_SM) dedup_cached_kernel(const CellT* __restrict__ text, u64 n, const u32* __restrict__ start_bits,
                                                                      const u32* __restrict__ end_bits, const u64* __restrict__ tile_base, u64 t_begin,
                                                                      u64 t_end, ulonglong2* table, u64 cap, u32* __restrict__ slot_of_phrase,
                                                                      u32* overflow, u64* stats) {
@@ -616,7 +617,7 @@ __global__ void __launch_bounds__(256) rewrite_kernel(const u32* __restrict__ sl
     if (j < p) {
         const u32 sv = slot_of_phrase[j];
         fin = sv >> 31;
-        out[j] = (OutT)table[sv & 0x7fffffffu].y;
+        out[j] = (OutT)ld_gather8(&table[sv & 0x7fffffffu].y);
     }
     const u32 b = __ballot_sync(0xffffffffu, fin);
     if (lane_id() == 0 && (j >> 5) < ((p + 31) >> 5)) end_bits_out[j >> 5] = b;

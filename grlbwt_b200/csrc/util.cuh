@@ -291,6 +291,31 @@ __device__ __forceinline__ u32 lanemask_lt() {
     return m;
 }
 
+// Random gathers: a plain load that misses the L2 pulls the whole 128-byte line from DRAM (4 sectors looked up per
+// 1-sector request in ncu); the 64-byte prefetch-size hint halves that for records read once at random.
+__device__ __forceinline__ ulonglong2 ld_gather16(const ulonglong2* p) {
+    ulonglong2 v;
+    asm volatile("ld.global.nc.L2::64B.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ u32 ld_gather4(const u32* p) {
+    u32 v;
+    asm volatile("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ u64 ld_gather8(const u64* p) {
+    u64 v;
+    asm volatile("ld.global.nc.L2::64B.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+template <class T>
+__device__ __forceinline__ T ld_gather(const T* p) {
+    static_assert(sizeof(T) == 4 || sizeof(T) == 8, "ld_gather: 4- or 8-byte types");
+    if constexpr (sizeof(T) == 4) return (T)ld_gather4(reinterpret_cast<const u32*>(p));
+    else return (T)ld_gather8(reinterpret_cast<const u64*>(p));
+}
+
 template <class T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll
