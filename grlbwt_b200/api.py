@@ -83,7 +83,8 @@ def lib_gpu():
         L.grlgpu_mg_global.argtypes = [vp, vp, vp, vp, u64, u64, C.c_int, C.POINTER(Round)]
         L.grlgpu_mg_rank_sort.argtypes = [vp, vp, vp, vp, u64, u64, C.c_int, C.c_int, vp]
         L.grlgpu_mg_rank_apply.argtypes = [vp, u64, vp, vp, vp]
-        L.grlgpu_mg_rank_finish.argtypes = [vp, u64, u64, u64, vp, vp, vp, C.c_int, C.POINTER(Round)]
+        L.grlgpu_mg_reply.argtypes = [vp, u64, vp, vp]
+        L.grlgpu_mg_rank_finish.argtypes = [vp, u64, u64, u64, vp, vp, vp, vp, C.c_int, C.POINTER(Round)]
         L.grlgpu_mg_level_slice.argtypes = [vp, vp, vp, vp, vp, vp]
         L.grlgpu_selftest_scan.argtypes = [vp, u64, vp, vp]
         L.grlgpu_selftest_sort.argtypes = [vp, vp, u64, C.c_int]
@@ -251,9 +252,13 @@ class GrlGpu:
     def mg_rank_apply(self, rank_base, meta_ptr, isn_ptr, erank_ptr):
         self._check(self._L.grlgpu_mg_rank_apply(self._h, rank_base, C.c_void_p(meta_ptr), C.c_void_p(isn_ptr), C.c_void_p(erank_ptr)))
 
-    def mg_rank_finish(self, rank_base, tot, n_pre, meta_ptr, isn_ptr, erank_ptr, done):
+    def mg_reply(self, part_base, meta_ptr, reply_ptr):
+        self._check(self._L.grlgpu_mg_reply(self._h, part_base, C.c_void_p(meta_ptr), C.c_void_p(reply_ptr)))
+
+    def mg_rank_finish(self, rank_base, tot, n_pre, meta_ptr, isn_ptr, erank_ptr, done, local_meta_ptr=None):
         r = Round()
-        self._check(self._L.grlgpu_mg_rank_finish(self._h, rank_base, tot, n_pre, C.c_void_p(meta_ptr), C.c_void_p(isn_ptr), C.c_void_p(erank_ptr), int(done), C.byref(r)))
+        self._check(self._L.grlgpu_mg_rank_finish(self._h, rank_base, tot, n_pre, C.c_void_p(meta_ptr), C.c_void_p(isn_ptr), C.c_void_p(erank_ptr),
+                                                  C.c_void_p(local_meta_ptr) if local_meta_ptr else None, int(done), C.byref(r)))
         self.last = r
         self._round_started = True
         return r.as_dict()

@@ -692,6 +692,8 @@ struct MgRound {
     DevBuf<ulonglong2> ptable;
     DevBuf<u32> pslots, p_len;
     DevBuf<u64> p_pos, p_freq, p_offs;
+    DevBuf<u32> recv_dense;         // partition-local index of every phrase this rank received as an owner (for the metasymbol return)
+    u64 m_recv = 0;
     u64 d_part = 0, cells_part = 0;
     const void* recv_cells = nullptr;
     Timer t_text, t_dict;
@@ -774,7 +776,8 @@ void mg_merge_t(grlgpu_ctx* c, const u32* lens, const u64* counts, const void* c
     GRL_LAUNCH("table_init", cap * 16, table_init_kernel, grid_for(cap, 256), 256, 0, st, M.ptable.p, cap);
     DevBuf<u32> overflow(1, st);
     overflow.zero();
-    GRL_LAUNCH("pack_insert", 0, (pack_insert_kernel<CellT>), grid_for(m, 256), 256, 0, st, (const CellT*)cells, offs.p, lens, counts, m, M.ptable.p, cap, overflow.p);
+    DevBuf<u32> recv_slot(m, st);
+    GRL_LAUNCH("pack_insert", 0, (pack_insert_kernel<CellT>), grid_for(m, 256), 256, 0, st, (const CellT*)cells, offs.p, lens, counts, m, M.ptable.p, cap, overflow.p, recv_slot.p);
     if (d2h_scalar(overflow.p, st)) throw Error(GRLGPU_ERR_STATE, "partition table overflow");
     DevBuf<u32> occ_bits(cap / 32, st);
     GRL_LAUNCH("table_occupancy", cap * 16, table_occupancy_kernel, (unsigned)(cap / 256), 256, 0, st, M.ptable.p, cap, occ_bits.p);
@@ -789,6 +792,11 @@ void mg_merge_t(grlgpu_ctx* c, const u32* lens, const u64* counts, const void* c
     M.p_offs.alloc(M.d_part + 1, st);
     exclusive_scan<u32, u64>(M.p_len.p, M.p_offs.p, M.d_part, M.p_offs.p + M.d_part, st);
     M.cells_part = d2h_scalar(M.p_offs.p + M.d_part, st);
+    // the frequencies have been read: the count field now holds the slot's dense index, which every received phrase inherits
+    M.m_recv = m;
+    M.recv_dense.alloc(m, st);
+    GRL_LAUNCH("slot_dense", 0, slot_dense_kernel, grid_for(M.d_part, 256), 256, 0, st, M.pslots.p, M.d_part, M.ptable.p);
+    GRL_LAUNCH("recv_dense", 0, recv_dense_kernel, grid_for(m, 256), 256, 0, st, recv_slot.p, m, M.ptable.p, M.recv_dense.p);
     part->n_phrases = M.d_part;
     part->n_cells = M.cells_part;
 }
@@ -821,17 +829,30 @@ void mg_setup_global(grlgpu_ctx* c, Round& GR, const u32* lens, const u64* freqs
 
 // content -> global phrase index table, metasymbol of every local distinct phrase, rewrite of the shard
 template <class CellT>
-void mg_map_and_rewrite(grlgpu_ctx* c, MgRound& M, Round& GR, const void* cells, const u64* g_meta, u64 tot, u64 n_pre, int done_global, grlgpu_round_t* out) {
+void mg_map_and_rewrite(grlgpu_ctx* c, MgRound& M, Round& GR, const void* cells, const u64* g_meta, u64 tot, u64 n_pre, int done_global, grlgpu_round_t* out,
+                        const u64* local_meta = nullptr) {
     Round& R = M.R;
     cudaStream_t st = c->st;
     const u64 d = GR.d;
+    if (local_meta) {  // the owners returned the metasymbols in pack order: no global table, no content lookups
+        GRL_LAUNCH("apply_reply", R.d * 24, apply_reply_kernel, grid_for(R.d, 256), 256, 0, st, M.perm.p, R.occ_slots.p, local_meta, R.d, R.table.p);
+        M.t_dict.stop();
+        RoundTimes tm;
+        tm.text = M.ms_text;
+        tm.dict = M.t_dict.ms();
+        tm.all = tm.text + tm.dict;
+        finish_round(c, R, tot, n_pre, GR.d, GR.nE, GR.max_freq, tm, nullptr, out);
+        out->done = done_global ? 1u : 0u;
+        c->done = done_global != 0;
+        return;
+    }
     const u64 gcap = std::max<u64>(1024, (d + d / 2 + d / 10 + 255) / 256 * 256);
     if (gcap > (1ull << 31) - 256) throw Error(GRLGPU_ERR_LIMIT, "phrase table would exceed 2^31 slots");
     DevBuf<ulonglong2> gtable(gcap, st);
     GRL_LAUNCH("table_init", gcap * 16, table_init_kernel, grid_for(gcap, 256), 256, 0, st, gtable.p, gcap);
     DevBuf<u32> flag(2, st);
     flag.zero();
-    GRL_LAUNCH("pack_insert", 0, (pack_insert_kernel<CellT>), grid_for(d, 256), 256, 0, st, (const CellT*)cells, GR.ph_pos.p, GR.ph_len.p, (const u64*)nullptr, d, gtable.p, gcap, flag.p);
+    GRL_LAUNCH("pack_insert", 0, (pack_insert_kernel<CellT>), grid_for(d, 256), 256, 0, st, (const CellT*)cells, GR.ph_pos.p, GR.ph_len.p, (const u64*)nullptr, d, gtable.p, gcap, flag.p, (u32*)nullptr);
     GRL_LAUNCH("map_local", 0, (map_local_kernel<CellT>), grid_for(R.d, 256), 256, 0, st, (const CellT*)c->text, R.ph_pos.p, R.ph_len.p, R.occ_slots.p, R.d, (const CellT*)cells, gtable.p, gcap, g_meta, R.table.p, flag.p + 1);
     u32 hflag[2];
     d2h_small(hflag, flag.p, 8, st);
@@ -1022,7 +1043,8 @@ void mg_rank_apply_sym(grlgpu_ctx* c, u64 rank_base, u64* g_meta, u8* is_suffix_
 
 // step 3 (after the caller all-reduced the three arrays with MAX): rules of my ranked groups, local rewrite
 template <class CellT, class SymT>
-void mg_rank_finish_sym(grlgpu_ctx* c, u64 rank_base, u64 tot, u64 n_pre_global, const u64* g_meta, const u8* is_suffix_next, u32* erank1, int done_global, grlgpu_round_t* out) {
+void mg_rank_finish_sym(grlgpu_ctx* c, u64 rank_base, u64 tot, u64 n_pre_global, const u64* g_meta, const u8* is_suffix_next, u32* erank1, int done_global, grlgpu_round_t* out,
+                        const u64* local_meta) {
     MgRound& M = *c->mg;
     Round& GR = *M.GR;
     cudaStream_t st = c->st;
@@ -1040,7 +1062,7 @@ void mg_rank_finish_sym(grlgpu_ctx* c, u64 rank_base, u64 tot, u64 n_pre_global,
     DevBuf<u8> isn(tot, st);
     GRL_CUDA(cudaMemcpyAsync(isn.p, is_suffix_next, tot, cudaMemcpyDeviceToDevice, st));
     c->lvl_sym_bytes = sizeof(SymT);
-    mg_map_and_rewrite<CellT>(c, M, GR, M.g_cells, g_meta, tot, n_pre_global, done_global, out);
+    mg_map_and_rewrite<CellT>(c, M, GR, M.g_cells, g_meta, tot, n_pre_global, done_global, out, local_meta);
     c->is_suffix = std::move(isn);
     c->rule_l.release(); c->rule_r.release(); c->has_hocc.release(); c->pre_sym.release(); c->pre_len.release();  // level artefacts live in slices this round
     c->lvl_tot = 0; c->lvl_npre = 0;
@@ -1435,16 +1457,28 @@ int grlgpu_mg_rank_apply(grlgpu_ctx* ctx, uint64_t rank_base, uint64_t* d_ph_met
 }
 extern "C++" {
 template <class CellT>
-static void mg_rank_finish_cell(grlgpu_ctx* ctx, u64 rank_base, u64 tot, u64 n_pre, const u64* m, const u8* s, u32* e, int done, grlgpu_round_t* out) {
-    if (ctx->mg->sym_bytes == 8) mg_rank_finish_sym<CellT, u64>(ctx, rank_base, tot, n_pre, m, s, e, done, out);
-    else mg_rank_finish_sym<CellT, u32>(ctx, rank_base, tot, n_pre, m, s, e, done, out);
+static void mg_rank_finish_cell(grlgpu_ctx* ctx, u64 rank_base, u64 tot, u64 n_pre, const u64* m, const u8* s, u32* e, int done, grlgpu_round_t* out, const u64* lm) {
+    if (ctx->mg->sym_bytes == 8) mg_rank_finish_sym<CellT, u64>(ctx, rank_base, tot, n_pre, m, s, e, done, out, lm);
+    else mg_rank_finish_sym<CellT, u32>(ctx, rank_base, tot, n_pre, m, s, e, done, out, lm);
 }
+}
+int grlgpu_mg_reply(grlgpu_ctx* ctx, uint64_t part_base, const uint64_t* d_ph_meta, uint64_t* d_reply) {
+    if (!ctx || !d_ph_meta || !d_reply) return GRLGPU_ERR_ARG;
+    if (!ctx->mg || !ctx->mg->recv_dense.p) return GRLGPU_ERR_STATE;
+    return guarded(ctx, [&] {
+        MgRound& M = *ctx->mg;
+        GRL_LAUNCH("reply_meta", M.m_recv * 20, reply_meta_kernel, grid_for(M.m_recv, 256), 256, 0, ctx->st, M.recv_dense.p, M.m_recv, (u64)part_base, (const u64*)d_ph_meta,
+                   (u64*)d_reply);
+        GRL_CUDA(cudaStreamSynchronize(ctx->st));
+    });
 }
 int grlgpu_mg_rank_finish(grlgpu_ctx* ctx, uint64_t rank_base, uint64_t tot, uint64_t n_pre_runs, const uint64_t* d_ph_meta, const uint8_t* d_is_suffix_next,
-                          uint32_t* d_erank1, int done_global, grlgpu_round_t* out) {
+                          uint32_t* d_erank1, const uint64_t* d_local_meta, int done_global, grlgpu_round_t* out) {
     if (!ctx || !out || !d_ph_meta || !d_is_suffix_next || !d_erank1) return GRLGPU_ERR_ARG;
     if (!ctx->mg || !ctx->mg->GR) return GRLGPU_ERR_STATE;
-    return guarded(ctx, [&] { MG_DISPATCH(mg_rank_finish_cell, ctx, (u64)rank_base, (u64)tot, (u64)n_pre_runs, (const u64*)d_ph_meta, d_is_suffix_next, d_erank1, done_global, out); });
+    return guarded(ctx, [&] {
+        MG_DISPATCH(mg_rank_finish_cell, ctx, (u64)rank_base, (u64)tot, (u64)n_pre_runs, (const u64*)d_ph_meta, d_is_suffix_next, d_erank1, done_global, out, (const u64*)d_local_meta);
+    });
 }
 int grlgpu_mg_level_slice(grlgpu_ctx* ctx, void* d_rule_l, void* d_rule_r, uint8_t* d_has_hocc, void* d_pre_sym, uint64_t* d_pre_len) {
     if (!ctx) return GRLGPU_ERR_ARG;

@@ -586,11 +586,32 @@ __global__ void __launch_bounds__(256) pack_phrases_kernel(const CellT* __restri
 // dedup of a pack into a table whose keys point into the pack's own cells; count += counts[k] (or the index k when counts == nullptr)
 template <class CellT>
 __global__ void __launch_bounds__(256) pack_insert_kernel(const CellT* __restrict__ cells, const u64* __restrict__ offs, const u32* __restrict__ lens,
-                                                          const u64* __restrict__ counts, u64 m, ulonglong2* table, u64 cap, u32* overflow) {
+                                                          const u64* __restrict__ counts, u64 m, ulonglong2* table, u64 cap, u32* overflow,
+                                                          u32* __restrict__ slot_out) {
     const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= m) return;
     if (*reinterpret_cast<volatile u32*>(overflow)) return;
-    table_probe<CellT, true>(cells, offs[k], lens[k], cells, table, cap, counts ? counts[k] : k, nullptr, nullptr, 0, overflow);
+    const u32 slot = table_probe<CellT, true>(cells, offs[k], lens[k], cells, table, cap, counts ? counts[k] : k, nullptr, nullptr, 0, overflow);
+    if (slot_out) slot_out[k] = slot;
+}
+// owner side of the metasymbol return: dense partition index of every table slot, then of every received phrase
+static __global__ void __launch_bounds__(256) slot_dense_kernel(const u32* __restrict__ pslots, u64 d_part, ulonglong2* table) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < d_part) table[pslots[i]].y = i;
+}
+static __global__ void __launch_bounds__(256) recv_dense_kernel(const u32* __restrict__ recv_slot, u64 m, const ulonglong2* __restrict__ table, u32* __restrict__ dense) {
+    const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < m) dense[k] = (u32)table[recv_slot[k]].y;
+}
+static __global__ void __launch_bounds__(256) reply_meta_kernel(const u32* __restrict__ dense, u64 m, u64 part_base, const u64* __restrict__ g_meta, u64* __restrict__ reply) {
+    const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < m) reply[k] = g_meta[part_base + dense[k]];
+}
+// requester side: the k-th returned metasymbol belongs to the k-th phrase of the pack this rank sent (owner order)
+static __global__ void __launch_bounds__(256) apply_reply_kernel(const u32* __restrict__ perm, const u32* __restrict__ occ_slots, const u64* __restrict__ local_meta, u64 d,
+                                                                 ulonglong2* ltable) {
+    const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < d) ltable[occ_slots[perm[k]]].y = local_meta[k];
 }
 // metasymbol of every local distinct phrase: look its cells up in the global dictionary's table
 template <class CellT>

@@ -81,8 +81,12 @@ class GpuEngine:
     def rank_apply(self, rank_base, ph_meta, isn, erank1):
         self.ctx.mg_rank_apply(rank_base, ph_meta.data_ptr(), isn.data_ptr(), erank1.data_ptr())
 
-    def rank_finish(self, rank_base, tot, n_pre, ph_meta, isn, erank1, done):
-        return self.ctx.mg_rank_finish(rank_base, tot, n_pre, ph_meta.data_ptr(), isn.data_ptr(), erank1.data_ptr(), done)
+    def reply(self, part_base, ph_meta, reply):
+        self.ctx.mg_reply(part_base, ph_meta.data_ptr(), reply.data_ptr())
+
+    def rank_finish(self, rank_base, tot, n_pre, ph_meta, isn, erank1, done, local_meta=None):
+        return self.ctx.mg_rank_finish(rank_base, tot, n_pre, ph_meta.data_ptr(), isn.data_ptr(), erank1.data_ptr(), done,
+                                       None if local_meta is None else local_meta.data_ptr())
 
     def level_slice(self, rl, rr, hh, ps, pl):
         self.ctx.mg_level_slice(rl.data_ptr(), rr.data_ptr(), hh.data_ptr(), ps.data_ptr(), pl.data_ptr())
@@ -181,9 +185,10 @@ def _all_gather_v(part, counts, engine):
     return out
 
 
-def _ranked_distributed(engine, glens, gfreqs, gcells, d, n_cells, done, info5, want_level):
+def _ranked_distributed(engine, glens, gfreqs, gcells, d, n_cells, done, info5, want_level, exch):
     """the dictionary ranking split over the ranks by first-key range (grlgpu_mg_rank_*): two small all-gathers,
-    three all-reduce(MAX), and -- only when the level is wanted -- an all-gather-v of the level slices"""
+    three all-reduce(MAX), the metasymbol return (owners answer the packs they received: reverse all-to-all-v), and
+    -- only when the level is wanted -- an all-gather-v of the level slices"""
     G, me = dist.get_world_size(), dist.get_rank()
     n_ranked, n_pre_loc, nE, sym_bytes = info5[1:5]
     allc = _all_gather_small(torch.tensor([n_ranked, n_pre_loc], dtype=torch.int64, device=engine.device))
@@ -199,7 +204,13 @@ def _ranked_distributed(engine, glens, gfreqs, gcells, d, n_cells, done, info5, 
     for t in (ph_meta, isn, erank1):
         _all_reduce(t, dist.ReduceOp.MAX)
         _fence(t)
-    info = engine.rank_finish(base, tot, sum(pre_counts), ph_meta, isn, erank1, done)
+    sent_phr, recv_phr, part_phr = exch  # phrases per peer: sent to / received from as an owner; partition sizes in rank order
+    local_meta = None
+    if hasattr(engine, "reply"):
+        reply = engine.alloc(sum(recv_phr), torch.int64)
+        engine.reply(sum(part_phr[:me]), ph_meta, reply)
+        local_meta = _all_to_all_v(reply, recv_phr, sent_phr, engine)
+    info = engine.rank_finish(base, tot, sum(pre_counts), ph_meta, isn, erank1, done, local_meta)
     engine.level_override = None
     if want_level:
         st = torch.int32 if sym_bytes == 4 else torch.int64
@@ -270,7 +281,7 @@ def distributed_round(engine, n_strings_global: int, timings: dict | None = None
 
     info5 = engine.rank_sort(glens, gfreqs, gcells, sum(g_phr), sum(g_cel), dist.get_rank(), G) if hasattr(engine, "rank_sort") else [0] * 5
     if info5[0]:
-        info = _ranked_distributed(engine, glens, gfreqs, gcells, sum(g_phr), sum(g_cel), done, info5, want_level)
+        info = _ranked_distributed(engine, glens, gfreqs, gcells, sum(g_phr), sum(g_cel), done, info5, want_level, (n_phr, r_phr, g_phr))
     else:
         info = engine.global_round(glens, gfreqs, gcells, sum(g_phr), sum(g_cel), done)
         info["ranking"] = "replicated"

@@ -161,15 +161,20 @@ int grlgpu_mg_global(grlgpu_ctx* ctx, const uint32_t* d_lens, const uint64_t* d_
  *   caller: rank_base = exclusive prefix of the ranked-group counts over the ranks, tot = their sum; allocates
  *           zero-filled device arrays ph_meta[d] (u64), is_suffix_next[tot] (u8), erank1[nE] (u32)
  *   grlgpu_mg_rank_apply   writes this rank's share into them (hocc marks as rank + 1)   -> all-reduce(MAX) of the three
- *   grlgpu_mg_rank_finish  rules of this rank's groups, metasymbols of the local phrases, rewrite of the shard
+ *   grlgpu_mg_reply        owner side of the metasymbol return (optional): reply[k] = metasymbol of the k-th phrase this rank
+ *                          RECEIVED in grlgpu_mg_merge; part_base = global index of this rank's first partition phrase
+ *                          -> reverse all-to-all-v: every rank gets the metasymbols of the pack it sent, in pack order
+ *   grlgpu_mg_rank_finish  rules of this rank's groups, metasymbols of the local phrases (from d_local_meta when the owners
+ *                          returned them, else -- NULL -- by content lookup in a table of the whole dictionary), rewrite
  *   grlgpu_mg_level_slice  this rank's slice of the level artefacts into caller DEVICE buffers (rules / has_hocc: info5[1]
  *                          entries, positions [rank_base, rank_base + info5[1]); pre-BWT: info5[2] runs, to be
  *                          concatenated in rank order, merging equal symbols where two ranks meet) */
 int grlgpu_mg_rank_sort(grlgpu_ctx* ctx, const uint32_t* d_lens, const uint64_t* d_freqs, const void* d_cells, uint64_t d, uint64_t n_cells, int rank_id,
                         int n_ranks, uint64_t* info5);
 int grlgpu_mg_rank_apply(grlgpu_ctx* ctx, uint64_t rank_base, uint64_t* d_ph_meta, uint8_t* d_is_suffix_next, uint32_t* d_erank1);
+int grlgpu_mg_reply(grlgpu_ctx* ctx, uint64_t part_base, const uint64_t* d_ph_meta, uint64_t* d_reply);
 int grlgpu_mg_rank_finish(grlgpu_ctx* ctx, uint64_t rank_base, uint64_t tot, uint64_t n_pre_runs, const uint64_t* d_ph_meta, const uint8_t* d_is_suffix_next,
-                          uint32_t* d_erank1, int done_global, grlgpu_round_t* out);
+                          uint32_t* d_erank1, const uint64_t* d_local_meta, int done_global, grlgpu_round_t* out);
 int grlgpu_mg_level_slice(grlgpu_ctx* ctx, void* d_rule_l, void* d_rule_r, uint8_t* d_has_hocc, void* d_pre_sym, uint64_t* d_pre_len);
 
 /* launch accounting: number of kernel launches issued by this context so far, and (after

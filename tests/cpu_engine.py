@@ -124,6 +124,8 @@ class CpuEngine:
         for p, c in zip(ph, nums):
             acc[p] += c
         self._part = acc
+        dense = {p: i for i, p in enumerate(acc)}  # pack_part emits the partition in this order
+        self._recv_dense = [dense[p] for p in ph]
         return len(acc), sum(len(p) for p in acc)
 
     def pack_part(self, lens, freqs, cells):
@@ -264,7 +266,11 @@ class CpuEngine:
                 for e in g["members"]:
                     erank1[e] = r + 1
 
-    def rank_finish(self, rank_base, tot, n_pre, ph_meta, isn, erank1, done):
+    def reply(self, part_base, ph_meta, reply):
+        for k, i in enumerate(self._recv_dense):
+            reply[k] = int(ph_meta[part_base + i])
+
+    def rank_finish(self, rank_base, tot, n_pre, ph_meta, isn, erank1, done, local_meta=None):
         D, A = self._dist, self.A
         alph3, dummy = A + 3, A + 3 + tot + 1
         rl, rr, hh = [], [], []
@@ -285,12 +291,16 @@ class CpuEngine:
             else:
                 rl.append(dummy); rr.append(suf[-1] if self._suffix(suf[-1]) else suf[-2])
         self._slice = {"rule_l": rl, "rule_r": rr, "has_hocc": hh, "pre_sym": [p[0] for p in D["pre"]], "pre_len": [p[1] for p in D["pre"]]}
-        gidx = {p: i for i, p in enumerate(D["ph"])}
-        per_str, cnt, _ = self._local
+        per_str, cnt, order = self._local
+        if local_meta is not None:  # the owners returned the metasymbols in pack order
+            meta_of = {p: int(local_meta[k]) for k, p in enumerate(order)}
+        else:
+            gidx = {p: i for i, p in enumerate(D["ph"])}
+            meta_of = {p: int(ph_meta[gidx[p]]) for p in cnt}
         new_cells, new_ptrs = [], [0]
         for phs in per_str:
             for p in phs:
-                new_cells.append(int(ph_meta[gidx[p]]))
+                new_cells.append(meta_of[p])
             new_ptrs.append(len(new_cells))
         bps = sym_width(tot) + 1
         info = {"alphabet": A, "tot_phrases": tot, "n_phrases": len(D["ph"]), "dict_syms": sum(len(p) for p in D["ph"]), "parse_len": len(new_cells),
