@@ -65,8 +65,8 @@ __global__ void __launch_bounds__(256) dict_gather_kernel(const CellT* __restric
                                                           const u32* __restrict__ ph_off, const u64* __restrict__ ph_freq,
                                                           const u32* __restrict__ target_slots, u64 d, IsSuffix is_suffix, SymT* __restrict__ D,
                                                           u32* __restrict__ phr_of, u32* __restrict__ rem, ulonglong2* __restrict__ einfo,
-                                                          const u32* __restrict__ ph_voff, u64 term_code, int bits, int K, u64* __restrict__ keys,
-                                                          u32* __restrict__ vals) {
+                                                          const u32* __restrict__ ph_voff, u64 term_code, int bits, int K, int spare,
+                                                          u64* __restrict__ keys, u32* __restrict__ vals) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     const u32 lane = lane_id();
     const u32 nvalid = __popc(__ballot_sync(0xffffffffu, i < d));  // valid lanes are a prefix of the warp
@@ -106,11 +106,16 @@ __global__ void __launch_bounds__(256) dict_gather_kernel(const CellT* __restric
         einfo[e] = make_ulonglong2(left, qfreq | (valid ? EI_VALID : 0ULL) | (k == 0 ? EI_FULL : 0ULL));
         if (ph_voff && valid) {
             u64 key = v + 1;
-            for (int t = 1; t < K; t++) {
+            for (int t = 1; t <= K; t++) {  // t == K: the bits that are left take the TOP `spare` bits of the next code (order-preserving)
+                if (t == K && spare == 0) break;
                 u64 code = 0;
                 if ((u32)t <= r) code = cell_value<CellT, FIRST>(text[qpos + k + t]) + 1;
                 else if ((u32)t == r + 1) code = term_code;
-                key = (key << bits) | code;
+                if (t < K) key = (key << bits) | code;
+                else {  // monotone squeeze of code K + 1 into `spare` bits; the terminator keeps a value of its own (all ones)
+                    const u64 top = (1ULL << spare) - 1ULL, sq = code >> (bits - spare);
+                    key = (key << spare) | (code == term_code ? top : (sq < top ? sq : top - 1ULL));
+                }
             }
             keys[(u64)qvoff + k] = key;
             vals[(u64)qvoff + k] = (u32)e;
@@ -149,7 +154,7 @@ static __global__ void __launch_bounds__(256) key_head_flags_kernel(const u64* _
 // than one member and the compared prefix (h codes) holds no terminator yet.
 
 // after the first sort: head flags, head bitmap, and bitmap of the positions that belong to unresolved groups
-static __global__ void __launch_bounds__(256) first_heads_kernel(const u64* __restrict__ keys, u64 n, int bits, u64 term_code, u32* __restrict__ flags,
+static __global__ void __launch_bounds__(256) first_heads_kernel(const u64* __restrict__ keys, u64 n, int bits, int spare, u64 term_code, u32* __restrict__ flags,
                                                                  u32* __restrict__ head_bits, u32* __restrict__ active_bits) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     bool head = false, active = false;
@@ -157,8 +162,9 @@ static __global__ void __launch_bounds__(256) first_heads_kernel(const u64* __re
         const u64 k = keys[i];
         head = i == 0 || keys[i - 1] != k;
         const bool next_head = i + 1 == n || keys[i + 1] != k;
-        const u64 last = bits >= 64 ? k : (k & ((1ULL << bits) - 1ULL));
-        const bool finished = last == 0 || last == term_code;  // the key already holds the terminator
+        const u64 last = bits >= 64 ? k : ((k >> spare) & ((1ULL << bits) - 1ULL));  // the K-th (last whole) code
+        const u64 top = (1ULL << spare) - 1ULL;
+        const bool finished = last == 0 || last == term_code || (spare > 0 && (k & top) == top);  // the key already holds the terminator
         active = !(head && next_head) && !finished;
         flags[i] = head ? 1u : 0u;
     }

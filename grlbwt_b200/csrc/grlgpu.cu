@@ -162,7 +162,7 @@ struct Round {
     DevBuf<ulonglong2> einfo;
     // suffix-order plan: K symbol codes of sym_bits bits per 64-bit key; ext_mode = refinement by key extension, over the
     // nS valid entries only (first keys + entry ids come out of the dictionary gather); else prefix doubling over all nE
-    int sym_bits = 0, K = 1;
+    int sym_bits = 0, K = 1, spare = 0;  // spare: bits of the first key beyond the K whole codes (key extension only)
     bool ext_mode = false;
     u64 nS = 0;
     DevBuf<u64> keys;
@@ -361,6 +361,7 @@ void stage_gather(Round& R, bool force_ext = false) {
     // refinement by key extension needs ceil((longest phrase + 1) / K) passes at most; beyond 64 passes (or when a test
     // forces it) the groups are refined by prefix doubling on position-based ranks instead
     R.ext_mode = force_ext || (!(c->flags & GRLGPU_FLAG_FORCE_DOUBLING) && (R.max_len + 1 + (u64)R.K - 1) / (u64)R.K <= 64);
+    R.spare = (R.ext_mode && R.sym_bits * R.K < 64) ? 64 - R.sym_bits * R.K : 0;
     const CellT* dtext = (const CellT*)(R.dict_text ? R.dict_text : c->text);
     DevBuf<u32> voff;
     R.nS = R.nE;
@@ -382,7 +383,7 @@ void stage_gather(Round& R, bool force_ext = false) {
     // metasymbols go to the phrase's table slot, or to the global per-phrase array in multi-GPU rounds
     GRL_LAUNCH("dict_gather", R.nE * (sizeof(CellT) + sizeof(SymT) + 20) + R.nS * 12 + R.d * 32, (dict_gather_kernel<CellT, FIRST, SymT>), grid_for(R.d, 256), 256, 0, R.st, dtext,
                R.ph_pos.p, R.ph_len.p, R.ph_off.p, R.ph_freq.p, R.ph_meta ? (const u32*)nullptr : (const u32*)R.occ_slots.p, R.d, isuf, (SymT*)R.D_raw.p, R.phr_of.p, R.rem.p,
-               R.einfo.p, (const u32*)voff.p, c->alphabet + 1, R.sym_bits, R.K, R.keys.p, R.vals.p);
+               R.einfo.p, (const u32*)voff.p, c->alphabet + 1, R.sym_bits, R.K, R.spare, R.keys.p, R.vals.p);
 }
 
 // ---------------- dictionary stage: suffix order, groups, ranks, pre-BWT, rules, metasymbols ----------------
@@ -411,7 +412,7 @@ void stage_dict(Round& R) {
         }
         u64 *kp = keys.p, *ka = keys_alt.p;
         u32 *vp = vals.p, *va = vals_alt.p;
-        radix_sort_pairs(&kp, &vp, &ka, &va, nS, std::min(64, sym_bits * K), st);
+        radix_sort_pairs(&kp, &vp, &ka, &va, nS, std::min(64, sym_bits * K + R.spare), st);
         if (vp != vals.p) std::swap(vals, vals_alt);
         order_buf = std::move(vals);
         vals_alt.release();
@@ -421,7 +422,7 @@ void stage_dict(Round& R) {
         if (ext_mode) {
             {
                 DevBuf<u32> flags(nS, st), active_bits(n_words, st);
-                GRL_LAUNCH("first_heads", nS * 12, first_heads_kernel, grid_for(nS, 256), 256, 0, st, kp, nS, sym_bits, A + 1, flags.p, head_bits.p, active_bits.p);
+                GRL_LAUNCH("first_heads", nS * 12, first_heads_kernel, grid_for(nS, 256), 256, 0, st, kp, nS, sym_bits, R.spare, A + 1, flags.p, head_bits.p, active_bits.p);
                 keys.release(); keys_alt.release();
                 BitmapCompactor ac;
                 nA = ac.count(active_bits.p, nS, st);
@@ -439,6 +440,7 @@ void stage_dict(Round& R) {
                            avp, nk.p, ev.p, gflag.p);
                 exclusive_scan<u32, u32>(gflag.p, gexcl.p, nA, cnt.p, st);
                 const u64 n_groups = d2h_scalar(cnt.p, st);
+                if (getenv("GRLGPU_TRACE")) fprintf(stderr, "[grlgpu] round %d refine: depth %llu, active %llu in %llu groups (of %llu sorted)\n", c->round + 1, dpt, nA, n_groups, nS);
                 radix_sort_pairs(&akp, &avp, &aka, &ava, nA, std::min(64, sym_bits * K), st);  // by the extension key ...
                 GRL_LAUNCH("ext_gid", nA * 12, ext_gid_kernel, grid_for(nA, 256), 256, 0, st, gflag.p, gexcl.p, nA);
                 GRL_LAUNCH("ext_group_keys", nA * 16, ext_group_keys_kernel, grid_for(nA, 256), 256, 0, st, avp, gexcl.p, nA, akp);
@@ -458,7 +460,7 @@ void stage_dict(Round& R) {
         R.rank.alloc(nE, st);
         {   // heads, position-based ranks and the first active set
             DevBuf<u32> flags(nE, st), excl(nE, st), active_bits(n_words, st), gcount(1, st);
-            GRL_LAUNCH("first_heads", nE * 12, first_heads_kernel, grid_for(nE, 256), 256, 0, st, kp, nE, sym_bits, A + 1, flags.p, head_bits.p, active_bits.p);
+            GRL_LAUNCH("first_heads", nE * 12, first_heads_kernel, grid_for(nE, 256), 256, 0, st, kp, nE, sym_bits, 0, A + 1, flags.p, head_bits.p, active_bits.p);
             keys.release(); keys_alt.release();
             exclusive_scan<u32, u32>(flags.p, excl.p, nE, gcount.p, st);
             const u64 G0 = d2h_scalar(gcount.p, st);
@@ -880,7 +882,7 @@ void mg_rank_sort_sym(grlgpu_ctx* c, const u32* lens, const u64* freqs, const vo
     stage_gather<CellT, FIRST, SymT>(GR, true);  // first keys + entry ids of the valid entries come with it
     const SymT* D = (const SymT*)GR.D_raw.p;
     const int sym_bits = GR.sym_bits, K = GR.K;
-    const int key_bits = std::min(64, sym_bits * K);
+    const int key_bits = std::min(64, sym_bits * K), first_bits = std::min(64, sym_bits * K + GR.spare);
     const u64 nS = GR.nS;
     M.sym_bytes = sizeof(SymT);
     // splitters from a regular sample of the first keys, identical on every rank
@@ -895,7 +897,7 @@ void mg_rank_sort_sym(grlgpu_ctx* c, const u32* lens, const u64* freqs, const vo
         GRL_LAUNCH("key_sample", 0, key_sample_kernel, grid_for(ns, 256), 256, 0, st, keys.p, nS, stride, ns, sk.p, sv.p);
         u64 *a = sk.p, *b = sk2.p;
         u32 *av = sv.p, *bv = sv2.p;
-        radix_sort_pairs(&a, &av, &b, &bv, ns, key_bits, st);
+        radix_sort_pairs(&a, &av, &b, &bv, ns, first_bits, st);
         std::vector<u64> hs(ns);
         GRL_CUDA(cudaMemcpyAsync(hs.data(), a, ns * 8, cudaMemcpyDeviceToHost, st));
         GRL_CUDA(cudaStreamSynchronize(st));
@@ -922,7 +924,7 @@ void mg_rank_sort_sym(grlgpu_ctx* c, const u32* lens, const u64* freqs, const vo
     M.head_bits.zero();
     u64 *kp = mk.p, *ka = mk_alt.p;
     u32 *vp = mv.p, *va = mv_alt.p;
-    radix_sort_pairs(&kp, &vp, &ka, &va, nL, key_bits, st);
+    radix_sort_pairs(&kp, &vp, &ka, &va, nL, first_bits, st);
     if (vp != mv.p) std::swap(mv, mv_alt);
     M.order = std::move(mv);
     mv_alt.release();
@@ -931,7 +933,7 @@ void mg_rank_sort_sym(grlgpu_ctx* c, const u32* lens, const u64* freqs, const vo
     DevBuf<u32> apos;
     if (nL) {
         DevBuf<u32> flags(nL, st), active_bits(n_words, st);
-        GRL_LAUNCH("first_heads", nL * 12, first_heads_kernel, grid_for(nL, 256), 256, 0, st, kp, nL, sym_bits, A + 1, flags.p, M.head_bits.p, active_bits.p);
+        GRL_LAUNCH("first_heads", nL * 12, first_heads_kernel, grid_for(nL, 256), 256, 0, st, kp, nL, sym_bits, GR.spare, A + 1, flags.p, M.head_bits.p, active_bits.p);
         BitmapCompactor ac;
         nA = ac.count(active_bits.p, nL, st);
         apos.alloc(nA, st);
