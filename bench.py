@@ -248,9 +248,9 @@ def run_ours(args, rank, world, local_rank):
                     collect.append(r.as_dict())
                 if fetch:  # every level lands in its own slice of the pinned arena while the next round computes
                     e2e_parts.setdefault("round_ms", []).append(round(r.device_ms, 1))
-                    ctx.fetch_level(arena[0], async_=True, offset=a_off)
+                    ctx.fetch_level(arena[0], async_=True, offset=a_off, narrow_len=True)  # 32-bit run lengths where they fit, as the C++ host does
                     a_off = ctx.arena_end
-                    d2h += r.tot_phrases * (2 * r.sym_bytes + 1) + r.n_pre_runs * (r.sym_bytes + 8)
+                    d2h += r.tot_phrases * (2 * r.sym_bytes + 1) + r.n_pre_runs * (r.sym_bytes + (4 if r.n_in + r.parse_len < (1 << 32) else 8))
                 if r.done:
                     if fetch:
                         t_tail = time.perf_counter()

@@ -60,6 +60,7 @@ def lib_gpu():
         L.grlgpu_round.argtypes = [vp, C.POINTER(Round)]
         L.grlgpu_fetch_level.argtypes = [vp, vp, vp, vp, vp, vp]
         L.grlgpu_fetch_level_async.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.grlgpu_fetch_level32.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int]
         L.grlgpu_fetch_wait.argtypes = [vp]
         L.grlgpu_fetch_parse.argtypes = [vp, vp]
         L.grlgpu_fetch_str_ptrs.argtypes = [vp, vp]
@@ -160,13 +161,15 @@ class GrlGpu:
     def fetch_wait(self):
         self._check(self._L.grlgpu_fetch_wait(self._h))
 
-    def fetch_level(self, arena: np.ndarray | None = None, widen: bool = True, async_: bool = False, offset: int = 0):
+    def fetch_level(self, arena: np.ndarray | None = None, widen: bool = True, async_: bool = False, offset: int = 0, narrow_len: bool = False):
         """-> dict(rule_l, rule_r, has_hocc, pre_sym, pre_len) as numpy arrays.
         arena: optional uint8 buffer (e.g. pinned host memory) the arrays are carved from, so the copies are
-        direct DMA; widen=False keeps rule/pre_sym in the device's element width (sym_bytes) instead of u64."""
+        direct DMA; widen=False keeps rule/pre_sym in the device's element width (sym_bytes) instead of u64;
+        narrow_len: 32-bit run lengths (grlgpu_fetch_level32) whenever the round's n_in + parse_len < 2^32."""
         r = self.last
         st = np.uint32 if r.sym_bytes == 4 else np.uint64
-        sizes = [(r.tot_phrases, st), (r.tot_phrases, st), (r.tot_phrases, np.uint8), (r.n_pre_runs, st), (r.n_pre_runs, np.uint64)]
+        narrow = bool(narrow_len) and r.n_in + r.parse_len < (1 << 32)
+        sizes = [(r.tot_phrases, st), (r.tot_phrases, st), (r.tot_phrases, np.uint8), (r.n_pre_runs, st), (r.n_pre_runs, np.uint32 if narrow else np.uint64)]
         if arena is None:
             arrs = [np.zeros(n, dt) for n, dt in sizes]
         else:
@@ -179,8 +182,11 @@ class GrlGpu:
                 arrs.append(arena[off:off + nb].view(dt))
                 off += nb
         rl, rr, hh, ps, pl = arrs
-        fn = self._L.grlgpu_fetch_level_async if async_ else self._L.grlgpu_fetch_level
-        self._check(fn(self._h, _ptr(rl), _ptr(rr), _ptr(hh), _ptr(ps), _ptr(pl)))
+        if narrow:
+            self._check(self._L.grlgpu_fetch_level32(self._h, _ptr(rl), _ptr(rr), _ptr(hh), _ptr(ps), _ptr(pl), int(async_)))
+        else:
+            fn = self._L.grlgpu_fetch_level_async if async_ else self._L.grlgpu_fetch_level
+            self._check(fn(self._h, _ptr(rl), _ptr(rr), _ptr(hh), _ptr(ps), _ptr(pl)))
         if arena is not None:
             self.arena_end = (off + 15) & ~15
         if widen and arena is None:

@@ -44,7 +44,7 @@ struct grlgpu_ctx {
 
     // artefacts of the last round (device)
     int lvl_sym_bytes = 4;
-    u64 lvl_tot = 0, lvl_npre = 0;
+    u64 lvl_tot = 0, lvl_npre = 0, lvl_n_in = ~0ull;  // upper bound of the sum of the level's run lengths (all ones: unknown)
     DevBuf<u8> rule_l, rule_r, has_hocc, pre_sym;
     DevBuf<u64> pre_len;
 
@@ -54,6 +54,7 @@ struct grlgpu_ctx {
     cudaEvent_t copy_ev = nullptr;
     std::vector<DevBuf<u8>> parked_u8;
     std::vector<DevBuf<u64>> parked_u64;
+    std::vector<DevBuf<u32>> parked_u32;
 
     // multi-GPU round in flight (between grlgpu_mg_local and grlgpu_mg_global)
     MgRound* mg = nullptr;
@@ -576,6 +577,9 @@ void stage_dict(Round& R) {
     GRL_LAUNCH("rules", 0, (rules_kernel<SymT>), grid_for(G, 256), 256, 0, st, gcnt.p, rflag.p, rrank.p, grep.p, G, D, R.rem.p, erank.p, isuf, alph3, metasym_dummy, (SymT*)c->rule_l.p, (SymT*)c->rule_r.p, c->has_hocc.p);
     c->lvl_tot = tot;
     c->lvl_npre = R.n_pre;
+    // every valid dictionary entry contributes its phrase's frequency to exactly one run: the lengths of a level sum to at most
+    // n + p (phrases overlap by one cell). Multi-GPU: the frequencies are global, the local sizes bound nothing.
+    c->lvl_n_in = R.ph_meta ? ~0ull : R.n + R.p;
 
     if (c->flags & GRLGPU_FLAG_KEEP_DICT) {
         c->kd_d = R.d; c->kd_nE = nE; c->kd_nS = nS;
@@ -1067,7 +1071,7 @@ void mg_rank_finish_sym(grlgpu_ctx* c, u64 rank_base, u64 tot, u64 n_pre_global,
     mg_map_and_rewrite<CellT>(c, M, GR, M.g_cells, g_meta, tot, n_pre_global, done_global, out, local_meta);
     c->is_suffix = std::move(isn);
     c->rule_l.release(); c->rule_r.release(); c->has_hocc.release(); c->pre_sym.release(); c->pre_len.release();  // level artefacts live in slices this round
-    c->lvl_tot = 0; c->lvl_npre = 0;
+    c->lvl_tot = 0; c->lvl_npre = 0; c->lvl_n_in = ~0ull;
     // keep only the slices (until grlgpu_mg_level_slice / the next round)
     M.GR.reset();
     M.order.release(); M.head_bits.release(); M.head_pref.release(); M.gfull.release();
@@ -1281,6 +1285,47 @@ int grlgpu_fetch_level(grlgpu_ctx* ctx, void* rule_l, void* rule_r, uint8_t* has
     });
 }
 
+static __global__ void __launch_bounds__(256) narrow_u64_kernel(const u64* __restrict__ in, u64 n, u32* __restrict__ out) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (u32)in[i];
+}
+// Same as grlgpu_fetch_level / _async with 32-bit run lengths (the run lengths of a level sum to at most n_in + parse_len,
+// so this applies whenever that is < 2^32): 4 bytes less per preliminary-BWT run over PCIe.
+int grlgpu_fetch_level32(grlgpu_ctx* ctx, void* rule_l, void* rule_r, uint8_t* has_hocc, void* pre_sym, uint32_t* pre_len32, int async) {
+    if (!ctx) return GRLGPU_ERR_ARG;
+    if (ctx->round == 0 || !ctx->rule_l.p) return GRLGPU_ERR_STATE;
+    if (ctx->lvl_n_in >= (1ull << 32)) return GRLGPU_ERR_LIMIT;
+    return guarded(ctx, [&] {
+        cudaStream_t cs = ctx->st;
+        DevBuf<u32> len32(pre_len32 ? ctx->lvl_npre : 0, ctx->st);
+        if (pre_len32 && ctx->lvl_npre)
+            GRL_LAUNCH("narrow_u64", ctx->lvl_npre * 12, narrow_u64_kernel, grid_for(ctx->lvl_npre, 256), 256, 0, ctx->st, ctx->pre_len.p, ctx->lvl_npre, len32.p);
+        if (async) {
+            if (!ctx->copy_st) {
+                GRL_CUDA(cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking));
+                GRL_CUDA(cudaEventCreateWithFlags(&ctx->copy_ev, cudaEventDisableTiming));
+            }
+            GRL_CUDA(cudaEventRecord(ctx->copy_ev, ctx->st));
+            GRL_CUDA(cudaStreamWaitEvent(ctx->copy_st, ctx->copy_ev, 0));
+            cs = ctx->copy_st;
+        }
+        const u64 sb = (u64)ctx->lvl_sym_bytes;
+        if (pre_sym) GRL_CUDA(cudaMemcpyAsync(pre_sym, ctx->pre_sym.p, ctx->lvl_npre * sb, cudaMemcpyDeviceToHost, cs));
+        if (pre_len32) GRL_CUDA(cudaMemcpyAsync(pre_len32, len32.p, ctx->lvl_npre * 4, cudaMemcpyDeviceToHost, cs));
+        if (rule_l) GRL_CUDA(cudaMemcpyAsync(rule_l, ctx->rule_l.p, ctx->lvl_tot * sb, cudaMemcpyDeviceToHost, cs));
+        if (rule_r) GRL_CUDA(cudaMemcpyAsync(rule_r, ctx->rule_r.p, ctx->lvl_tot * sb, cudaMemcpyDeviceToHost, cs));
+        if (has_hocc) GRL_CUDA(cudaMemcpyAsync(has_hocc, ctx->has_hocc.p, ctx->lvl_tot, cudaMemcpyDeviceToHost, cs));
+        if (async) {
+            ctx->parked_u8.push_back(std::move(ctx->rule_l));
+            ctx->parked_u8.push_back(std::move(ctx->rule_r));
+            ctx->parked_u8.push_back(std::move(ctx->has_hocc));
+            ctx->parked_u8.push_back(std::move(ctx->pre_sym));
+            ctx->parked_u32.push_back(std::move(len32));
+            ctx->pre_len.release();
+        } else GRL_CUDA(cudaStreamSynchronize(ctx->st));
+    });
+}
+
 int grlgpu_fetch_level_async(grlgpu_ctx* ctx, void* rule_l, void* rule_r, uint8_t* has_hocc, void* pre_sym, uint64_t* pre_len) {
     if (!ctx) return GRLGPU_ERR_ARG;
     if (ctx->round == 0 || !ctx->rule_l.p) return GRLGPU_ERR_STATE;
@@ -1312,6 +1357,7 @@ int grlgpu_fetch_wait(grlgpu_ctx* ctx) {
         if (ctx->copy_st) GRL_CUDA(cudaStreamSynchronize(ctx->copy_st));
         ctx->parked_u8.clear();
         ctx->parked_u64.clear();
+        ctx->parked_u32.clear();
     });
 }
 

@@ -100,6 +100,7 @@ inline ParseResult gpu_par_phase(const void* text, uint64_t n_syms, int sym_byte
             for (const Level32& s : res.levels32) {
                 Level L;
                 L.alphabet = s.alphabet; L.tot_phrases = s.tot_phrases; L.has_hocc = s.has_hocc; L.pre_len = s.pre_len;
+                if (!s.pre_len32.empty()) L.pre_len.assign(s.pre_len32.begin(), s.pre_len32.end());
                 L.rule_l.assign(s.rule_l.begin(), s.rule_l.end()); L.rule_r.assign(s.rule_r.begin(), s.rule_r.end());
                 L.pre_sym.assign(s.pre_sym.begin(), s.pre_sym.end());
                 res.levels.push_back(std::move(L));
@@ -111,11 +112,16 @@ inline ParseResult gpu_par_phase(const void* text, uint64_t n_syms, int sym_byte
             L.alphabet = r.alphabet;
             L.tot_phrases = r.tot_phrases;
             L.has_hocc.resize(r.tot_phrases);
-            L.pre_len.resize(r.n_pre_runs);
             L.rule_l.resize(r.tot_phrases);
             L.rule_r.resize(r.tot_phrases);
             L.pre_sym.resize(r.n_pre_runs);
-            rc = grlgpu_fetch_level(ctx, L.rule_l.data(), L.rule_r.data(), L.has_hocc.data(), L.pre_sym.data(), L.pre_len.data());
+            if (r.n_in + r.parse_len < (1ull << 32)) {  // run lengths fit 32 bits: 4 bytes less per run over PCIe and in memory
+                L.pre_len32.resize(r.n_pre_runs);
+                rc = grlgpu_fetch_level32(ctx, L.rule_l.data(), L.rule_r.data(), L.has_hocc.data(), L.pre_sym.data(), L.pre_len32.data(), 0);
+            } else {
+                L.pre_len.resize(r.n_pre_runs);
+                rc = grlgpu_fetch_level(ctx, L.rule_l.data(), L.rule_r.data(), L.has_hocc.data(), L.pre_sym.data(), L.pre_len.data());
+            }
             if (rc != GRLGPU_OK) fail("grlgpu_fetch_level", rc);
             res.levels32.push_back(std::move(L));
         } else {

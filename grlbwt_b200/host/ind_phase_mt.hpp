@@ -33,7 +33,9 @@ struct Level32 {
     std::vector<uint32_t> rule_l, rule_r;
     std::vector<uint8_t> has_hocc;
     std::vector<uint32_t> pre_sym;
-    std::vector<uint64_t> pre_len;
+    std::vector<uint64_t> pre_len;    // run lengths, 64-bit ...
+    std::vector<uint32_t> pre_len32;  // ... or 32-bit when the level came through grlgpu_fetch_level32 (one of the two is empty)
+    inline uint64_t len(size_t i) const { return pre_len32.empty() ? pre_len[i] : (uint64_t)pre_len32[i]; }
 };
 
 // uninitialised array: pages are first touched by the worker threads that fill them, not zeroed serially
@@ -232,15 +234,15 @@ inline RunArr induce_level_mt(RunArr& bwt, const Level32& L, size_t n_threads) {
     };
     const size_t n_pre = L.pre_sym.size();
     RawBuf<uint64_t> pre_h, pre_s, pre_o;  // hocc offset, stream offset, output symbol offset at the start of pre-run i
-    parallel_prefix(T, n_pre, [&](size_t i) { return L.pre_sym[i] == hocc_dummy ? L.pre_len[i] : 0; }, pre_h);
+    parallel_prefix(T, n_pre, [&](size_t i) { return L.pre_sym[i] == hocc_dummy ? L.len(i) : 0; }, pre_h);
     if (pre_h[n_pre] != cum_h[n_tuples]) throw std::runtime_error("induction: hocc buffer and preliminary BWT disagree");
     parallel_prefix(T, n_pre, [&](size_t i) -> uint64_t {
-        if (L.pre_sym[i] == bwt_dummy) return L.pre_len[i];
-        if (L.pre_sym[i] == hocc_dummy) return from_bwt_before(pre_h[i] + L.pre_len[i]) - from_bwt_before(pre_h[i]);
+        if (L.pre_sym[i] == bwt_dummy) return L.len(i);
+        if (L.pre_sym[i] == hocc_dummy) return from_bwt_before(pre_h[i] + L.len(i)) - from_bwt_before(pre_h[i]);
         return 0;
     }, pre_s);
     if (pre_s[n_pre] != cum_s[m]) throw std::runtime_error("induction: stream and preliminary BWT disagree");
-    parallel_prefix(T, n_pre, [&](size_t i) { return L.pre_len[i]; }, pre_o);
+    parallel_prefix(T, n_pre, [&](size_t i) { return L.len(i); }, pre_o);
     clk.lap("offsets", n_pre);
 
     // ---- D: assembly. Parts are ranges of OUTPUT symbols of equal size (a long pre-run may be cut in the middle), so
@@ -277,7 +279,7 @@ inline RunArr induce_level_mt(RunArr& bwt, const Level32& L, size_t n_threads) {
         uint64_t o = o_beg;
         for (; o < o_end; i++) {
             const uint32_t s = L.pre_sym[i];
-            uint64_t f = L.pre_len[i] - skip;
+            uint64_t f = L.len(i) - skip;
             skip = 0;
             if (f > o_end - o) f = o_end - o;
             o += f;

@@ -205,6 +205,22 @@ def test_async_level_fetch_matches_sync(golden, all_cases):
         for a, b in zip(sync_levels, got):
             for k in ("rule_l", "rule_r", "has_hocc", "pre_sym", "pre_len"):
                 assert np.array_equal(a[k], b[k].astype(a[k].dtype)), (name, k)
+        # 32-bit run lengths (grlgpu_fetch_level32), synchronous and on the copy stream
+        for async_ in (False, True):
+            got32, off = [], 0
+            with G.GrlGpu(0) as ctx:
+                ctx.set_text(arr)
+                while True:
+                    r = ctx.round()
+                    got32.append(ctx.fetch_level(arena, async_=async_, offset=off, narrow_len=True))
+                    assert got32[-1]["pre_len"].dtype == np.uint32
+                    off = ctx.arena_end
+                    if r.done:
+                        break
+                ctx.fetch_wait()
+            for a, b in zip(sync_levels, got32):
+                for k in ("rule_l", "rule_r", "has_hocc", "pre_sym", "pre_len"):
+                    assert np.array_equal(a[k], b[k].astype(a[k].dtype)), (name, k, async_)
 
 
 def test_ill_formed_rejected():
