@@ -91,15 +91,74 @@ class GpuEngine:
     def level_slice(self, rl, rr, hh, ps, pl):
         self.ctx.mg_level_slice(rl.data_ptr(), rr.data_ptr(), hh.data_ptr(), ps.data_ptr(), pl.data_ptr())
 
-    level_override = None  # set by distributed_round when the level was assembled from per-rank slices
+    level_override = None  # set by distributed_round when the level was assembled from per-rank slices (device tensors)
 
-    def fetch_level(self, *a, **k):
-        if self.level_override is not None:
-            return self.level_override
-        return self.ctx.fetch_level(*a, **k)
+    def fetch_level(self, arena=None, **k):
+        """level artefacts as numpy arrays; with `arena` (pinned uint8 numpy buffer) the copies land there directly"""
+        ov = self.level_override
+        if ov is None:
+            return self.ctx.fetch_level(arena, **k) if arena is not None else self.ctx.fetch_level(**k)
+        out, off = {}, 0
+        for key in LEVEL_KEYS:
+            t = ov[key]
+            if arena is not None and t.is_cuda and t.numel():
+                nb = t.numel() * t.element_size()
+                off = (off + 15) & ~15
+                if off + nb > arena.size:
+                    raise ValueError("fetch arena too small")
+                torch.from_numpy(arena[off:off + nb]).view(t.dtype).copy_(t)  # device -> (pinned) host, no staging copy
+                out[key] = arena[off:off + nb].view(_UNSIGNED[t.dtype])
+                off += nb
+            else:
+                out[key] = unsigned_numpy(t)
+        return out
 
     def fetch_parse(self):
         return self.ctx.fetch_parse()
+
+
+LEVEL_KEYS = ("rule_l", "rule_r", "has_hocc", "pre_sym", "pre_len")
+_UNSIGNED = {torch.int32: np.uint32, torch.int64: np.uint64, torch.uint8: np.uint8}
+
+
+def unsigned_numpy(t):
+    """torch tensors carry the library's u32 / u64 values as int32 / int64 bit patterns: host copy, reinterpreted"""
+    return t.cpu().numpy().view(_UNSIGNED[t.dtype])
+
+
+def merge_seams(PS, PL, counts):
+    """PS / PL: concatenation, in rank order, of every rank's preliminary-BWT runs (each slice maximal on its own).
+    Equal symbols can only meet where two slices meet: at most len(counts) - 1 merges, decided from 2 symbols per slice."""
+    n = sum(counts)
+    PS, PL = PS[:n], PL[:n]
+    spans, off = [], 0
+    for c in counts:
+        if c:
+            spans.append((off, off + c - 1))
+        off += c
+    if len(spans) < 2:
+        return PS, PL
+    idx = torch.tensor([x for ab in spans for x in ab], dtype=torch.int64, device=PS.device)
+    sy = PS[idx].cpu().tolist()
+    drops, target, last_sym = [], spans[0][1], sy[1]
+    for k in range(1, len(spans)):
+        f, l = spans[k]
+        if sy[2 * k] == last_sym:
+            drops.append((f, target))      # the slice's first run continues the run `target`
+            if l == f:
+                continue                   # a one-run slice: the open run stays the same
+        target, last_sym = l, sy[2 * k + 1]
+    if not drops:
+        return PS, PL
+    PL = PL.clone()
+    for j, t in drops:
+        PL[t] += PL[j]
+    pieces, a = [], 0
+    for j, _ in drops:
+        pieces.append((a, j))
+        a = j + 1
+    pieces.append((a, n))
+    return torch.cat([PS[a:b] for a, b in pieces]), torch.cat([PL[a:b] for a, b in pieces])
 
 
 def _staged():
@@ -220,19 +279,10 @@ def _ranked_distributed(engine, glens, gfreqs, gcells, d, n_cells, done, info5, 
         engine.level_slice(rl, rr, hh, ps, pl)
         RL, RR, HH = _all_gather_v(rl, ranked_counts, engine), _all_gather_v(rr, ranked_counts, engine), _all_gather_v(hh, ranked_counts, engine)
         PS, PL = _all_gather_v(ps, pre_counts, engine), _all_gather_v(pl, pre_counts, engine)
-        if me == 0:
-            npre = sum(pre_counts)
-            mask = 0xFFFFFFFF if sym_bytes == 4 else 0x7FFFFFFFFFFFFFFF  # int32 tensors carry u32 bit patterns
-            s = PS[:npre].cpu().numpy().astype(np.int64) & mask
-            l = PL[:npre].cpu().numpy().astype(np.uint64)
-            if npre:  # equal symbols can only meet where two ranks' slices meet
-                keep = np.flatnonzero(np.concatenate(([True], s[1:] != s[:-1])))
-                l = np.add.reduceat(l, keep)
-                s = s[keep]
-            engine.level_override = {"rule_l": (RL[:tot].cpu().numpy().astype(np.int64) & mask).astype(np.uint64),
-                                     "rule_r": (RR[:tot].cpu().numpy().astype(np.int64) & mask).astype(np.uint64),
-                                     "has_hocc": HH[:tot].cpu().numpy().astype(np.uint8), "pre_sym": s.astype(np.uint64), "pre_len": l}
-            info["n_pre_runs"] = int(s.size)
+        if me == 0:  # stays on the device until somebody fetches it
+            S, Ln = merge_seams(PS, PL, pre_counts)
+            engine.level_override = {"rule_l": RL[:tot], "rule_r": RR[:tot], "has_hocc": HH[:tot], "pre_sym": S, "pre_len": Ln}
+            info["n_pre_runs"] = int(S.numel())
     info["ranking"] = "distributed"
     return info
 

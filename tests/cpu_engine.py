@@ -320,8 +320,9 @@ class CpuEngine:
     level_override = None
 
     def fetch_level(self):
-        if self.level_override is not None:
-            return self.level_override
+        if self.level_override is not None:  # assembled from per-rank slices by multigpu._ranked_distributed (tensors)
+            from grlbwt_b200.multigpu import LEVEL_KEYS, unsigned_numpy
+            return {k: unsigned_numpy(self.level_override[k]) for k in LEVEL_KEYS}
         return dict(self._level)
 
     def fetch_parse(self):
