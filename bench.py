@@ -314,6 +314,8 @@ def run_ours(args, rank, world, local_rank):
         host_np = host_text.numpy()
         # pinned landing zone for the level artefacts (largest level of the workload, measured in the resident steps)
         need = sum(r["tot_phrases"] * 17 + r["n_pre_runs"] * 16 + 256 for r in rounds_info) + rounds_info[-1]["parse_len"] * 8 * world + (1 << 20)
+        if world > 1 and rank != 0:
+            need = 1 << 20  # the levels of a multi-rank job are assembled and fetched on rank 0 only
         arena[0] = torch.empty(int(need), dtype=torch.uint8, pin_memory=True).numpy()
         d2h_bytes = [0]
 
@@ -409,7 +411,8 @@ def run_ours(args, rank, world, local_rank):
                            "parallelism": "1 GPU" if world == 1 else
                            f"{world} ranks: contiguous ranges of whole reads per rank; per round one hash-partitioned all-to-all-v of the local "
                            f"dictionaries + one all-gather-v of the deduplicated global dictionary over NCCL; large dictionaries are ranked "
-                           f"distributed (suffix entries partitioned by first-key range, three all-reduces), small ones replicated"},
+                           f"distributed (suffix entries partitioned by first-key range, three all-reduces, metasymbols returned to the "
+                           f"requesters by a reverse all-to-all-v), small ones replicated"},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "bwt_total": bwt_total,
                 "parse_rounds": parse_rounds, "kernels": kernels}
         print(json.dumps(line), flush=True)
