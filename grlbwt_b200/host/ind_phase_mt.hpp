@@ -225,8 +225,29 @@ inline RunArr induce_level_mt(RunArr& bwt, const Level32& L, size_t n_threads) {
     // ---- C: offsets ----
     RawBuf<uint64_t> cum_s, cum_h, cum_hb;  // stream symbols before run i; hocc symbols before entry k; of which from the stream
     parallel_prefix(T, m, [&](size_t i) { return blen[i]; }, cum_s);
-    parallel_prefix(T, n_tuples, [&](size_t k) { return hocc[k].f; }, cum_h);
-    parallel_prefix(T, n_tuples, [&](size_t k) { return hocc[k].l == FROM_BWT32 ? hocc[k].f : 0; }, cum_hb);
+    {   // both prefix sums over the tuples in one two-pass sweep (the tuples are the big array of a level)
+        cum_h.alloc(n_tuples + 1);
+        cum_hb.alloc(n_tuples + 1);
+        const size_t Tp = (T <= 1 || n_tuples < 4096) ? 1 : T;
+        const size_t per = (n_tuples + Tp - 1) / Tp;
+        std::vector<uint64_t> ph(Tp + 1, 0), pb(Tp + 1, 0);
+        parallel_chunks(Tp, n_tuples, [&](size_t, size_t b, size_t e) {
+            uint64_t sh = 0, sb = 0;
+            for (size_t k = b; k < e; k++) { sh += hocc[k].f; sb += hocc[k].l == FROM_BWT32 ? hocc[k].f : 0; }
+            const size_t c = Tp == 1 ? 0 : b / per;
+            ph[c + 1] = sh; pb[c + 1] = sb;
+        });
+        for (size_t t = 0; t < Tp; t++) { ph[t + 1] += ph[t]; pb[t + 1] += pb[t]; }
+        parallel_chunks(Tp, n_tuples, [&](size_t, size_t b, size_t e) {
+            const size_t c = Tp == 1 ? 0 : b / per;
+            uint64_t sh = ph[c], sb = pb[c];
+            for (size_t k = b; k < e; k++) {
+                cum_h[k] = sh; cum_hb[k] = sb;
+                sh += hocc[k].f; sb += hocc[k].l == FROM_BWT32 ? hocc[k].f : 0;
+            }
+        });
+        cum_h[n_tuples] = ph[Tp]; cum_hb[n_tuples] = pb[Tp];
+    }
     auto from_bwt_before = [&](uint64_t x) -> uint64_t {  // stream symbols consumed by the first x symbols of the hocc buffer
         if (x == 0) return 0;
         const size_t k = (size_t)(std::upper_bound(cum_h.data(), cum_h.data() + n_tuples + 1, x - 1) - cum_h.data()) - 1;  // entry holding symbol x-1
@@ -254,6 +275,11 @@ inline RunArr induce_level_mt(RunArr& bwt, const Level32& L, size_t n_threads) {
         Runs32& out = parts[p];
         const uint64_t o_beg = n_out / n_parts * p, o_end = p + 1 == n_parts ? n_out : n_out / n_parts * (p + 1);
         if (o_beg >= o_end) return;
+        {   // a part cannot hold more runs than output symbols, and the level cannot hold more than its sources together
+            const uint64_t guess = std::min<uint64_t>(o_end - o_beg, (uint64_t)(n_tuples + m + n_pre) / n_parts + 1024);
+            out.sym.reserve(guess);
+            out.len.reserve(guess);
+        }
         // first pre-run that reaches into [o_beg, o_end), and how many of its symbols lie before o_beg
         size_t i = (size_t)(std::upper_bound(pre_o.data(), pre_o.data() + n_pre + 1, o_beg) - pre_o.data()) - 1;
         uint64_t skip = o_beg - pre_o[i];
