@@ -6,11 +6,13 @@
 // metasymbol assignment (:427-450).
 //
 // Dictionary layout in HBM (structure of arrays over the nE = sum of phrase lengths entries):
-//   D[e]       symbol value          phr_of[e]  index of the phrase the entry belongs to
-//   rem[e]     symbols after e inside its phrase (0 for the last symbol)
-// The suffix order is computed by prefix doubling on packed keys: a first key packs the first K
-// symbols (code 0 = past the terminator, 1..A = symbol+1, A+1 = terminator, so a proper prefix
-// compares greater), then (rank[e], rank[e+h]) pairs are re-sorted until the grouping is stable.
+//   D[e]       symbol value          rem[e]   symbols after e inside its phrase (0 for the last symbol)
+//   einfo[e]   16-byte record read once by the group stage (left symbol + 1, frequency, valid / full flags)
+//   phr_of[e]  phrase of the entry -- only under GRLGPU_FLAG_KEEP_DICT (test hooks)
+// Suffix order: ONE radix sort of the valid entries on a packed first key (K symbol codes: 0 = past the
+// terminator, 1..A = symbol+1, A+1 = terminator, so a proper prefix compares greater; spare bits = top bits of
+// code K+1), then only the groups that are still ambiguous are refined -- by key extension (the next K codes,
+// straight from D), or by prefix doubling on position-based ranks when phrases are very long.
 #pragma once
 #include "util.cuh"
 #include "parse_kernels.cuh"

@@ -88,7 +88,12 @@ int grlbwt_selftest_induce(int n_levels, const uint64_t* alphabet, const uint64_
                 L.rule_r.assign(rule_r[i], rule_r[i] + tot[i]);
                 L.has_hocc.assign(has_hocc[i], has_hocc[i] + tot[i]);
                 L.pre_sym.assign(pre_sym[i], pre_sym[i] + n_pre[i]);
-                L.pre_len.assign(pre_len[i], pre_len[i] + n_pre[i]);
+                // both storage widths of the run lengths get exercised: odd levels keep them in 32 bits when they fit (what
+                // gpu_par_phase does for every level that came through grlgpu_fetch_level32)
+                bool fits = (i & 1) != 0;
+                for (uint64_t k = 0; fits && k < n_pre[i]; k++) fits = pre_len[i][k] < (1ull << 32);
+                if (fits) L.pre_len32.assign(pre_len[i], pre_len[i] + n_pre[i]);
+                else L.pre_len.assign(pre_len[i], pre_len[i] + n_pre[i]);
             }
             grlbwt::RunArr r = grlbwt::ind_phase_mt(lv, final_parse, n_strings, (size_t)n_threads);
             memset(out, 0, sizeof(*out));

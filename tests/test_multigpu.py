@@ -19,6 +19,35 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 
+def test_merge_seams_equals_a_sequential_merge():
+    """the O(ranks) merge of per-rank preliminary-BWT slices (two symbols per slice decide) == merging run by run"""
+    import numpy as np
+    import torch
+    from grlbwt_b200.multigpu import merge_seams
+    rng = np.random.default_rng(5)
+    for _ in range(2000):
+        slices = []
+        for _r in range(int(rng.integers(1, 7))):
+            syms = []
+            for _k in range(int(rng.integers(0, 4))):
+                x = int(rng.integers(0, 3))
+                while syms and syms[-1] == x:
+                    x = int(rng.integers(0, 3))
+                syms.append(x)
+            slices.append((syms, [int(v) for v in rng.integers(1, 9, size=len(syms))]))
+        PS = torch.tensor([x for s, _ in slices for x in s] + [99], dtype=torch.int32)   # + padding as alloc() leaves it
+        PL = torch.tensor([x for _, l in slices for x in l] + [7], dtype=torch.int64)
+        S, L = merge_seams(PS, PL, [len(s) for s, _ in slices])
+        es, el = [], []
+        for s_, l_ in slices:
+            for x, y in zip(s_, l_):
+                if es and es[-1] == x:
+                    el[-1] += y
+                else:
+                    es.append(x); el.append(y)
+        assert S.tolist() == es and L.tolist() == el
+
+
 def free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
