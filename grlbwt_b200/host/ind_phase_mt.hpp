@@ -24,6 +24,8 @@
 #include <thread>
 #include <vector>
 
+#include <sys/mman.h>
+
 #include "rl_bwt_io.hpp"
 
 namespace grlbwt {
@@ -52,7 +54,12 @@ struct RawBuf {
     void alloc(size_t count) {
         release();
         n = count;
-        p = (T*)malloc((count ? count : 1) * sizeof(T));
+        const size_t bytes = (count ? count : 1) * sizeof(T);
+        constexpr size_t HUGE = (size_t)2 << 20;
+        if (bytes >= 2 * HUGE && !getenv("GRLBWT_NO_HUGE")) {  // big arrays: 2 MB pages (512 x fewer first-touch faults and TLB misses in the scatter passes)
+            p = (T*)aligned_alloc(HUGE, (bytes + HUGE - 1) / HUGE * HUGE);
+            if (p) madvise((void*)p, (bytes + HUGE - 1) / HUGE * HUGE, MADV_HUGEPAGE);
+        } else p = (T*)malloc(bytes);
         if (!p) throw std::bad_alloc();
     }
     void release() { free(p); p = nullptr; n = 0; }
@@ -280,6 +287,7 @@ inline RunArr induce_level_mt(RunArr& bwt, const Level32& L, size_t n_threads) {
             out.sym.reserve(guess);
             out.len.reserve(guess);
         }
+
         // first pre-run that reaches into [o_beg, o_end), and how many of its symbols lie before o_beg
         size_t i = (size_t)(std::upper_bound(pre_o.data(), pre_o.data() + n_pre + 1, o_beg) - pre_o.data()) - 1;
         uint64_t skip = o_beg - pre_o[i];
