@@ -124,17 +124,23 @@ inline void parallel_prefix(size_t n_threads, size_t n, GetT&& get, RawBuf<uint6
     out[n] = part[T];
 }
 
-struct HTuple { uint32_t g, l; uint64_t f; };
+// one entry of a level's hocc buffer: bucket g, symbol l (or FROM_BWT32), run length f. FT = uint32_t (12-byte tuples: a
+// quarter less traffic in the sort and the prefix passes) whenever every run length of the level fits, else uint64_t
+template <class FT>
+struct HTupleT { uint32_t g, l; FT f; };
 constexpr uint32_t FROM_BWT32 = 0xffffffffu;
 
 // stable LSD radix sort of tuples by g (11-bit digits)
+template <class HTuple>
 inline void radix_sort_tuples(size_t n_threads, RawBuf<HTuple>& a, uint64_t max_key) {
     const size_t n = a.size();
     if (n < 2) return;
     RawBuf<HTuple> b(n);
-    constexpr int BITS = 11, NB = 1 << BITS;
     int key_bits = 0;
     while (key_bits < 32 && (max_key >> key_bits)) key_bits++;
+    // as few passes as 11-bit digits allow, then digits of equal width: 15 key bits sort as 8 + 7, not 11 + 4 (fewer open
+    // cache lines per thread in each scatter)
+    const int n_pass = std::max(1, (key_bits + 10) / 11), BITS = std::max(1, (key_bits + n_pass - 1) / n_pass), NB = 1 << BITS;
     const size_t T = (n_threads <= 1 || n < (1u << 16)) ? 1 : n_threads;
     const size_t per = (n + T - 1) / T;
     std::vector<uint64_t> hist(T * NB);
@@ -171,7 +177,9 @@ struct PhaseClock {  // GRLBWT_TRACE=1 prints the time of every step of every le
 };
 
 // one level step BWT_{i+1} -> BWT_i
-inline RunArr induce_level_mt(RunArr& bwt, const Level32& L, size_t n_threads) {
+template <class FT>
+inline RunArr induce_level_t(RunArr& bwt, const Level32& L, size_t n_threads) {
+    typedef HTupleT<FT> HTuple;
     PhaseClock clk;
     const uint64_t A = L.alphabet, alph3 = A + 3, bwt_dummy = A + 1, hocc_dummy = A + 2;
     const size_t m = bwt.size();
@@ -212,11 +220,11 @@ inline RunArr induce_level_mt(RunArr& bwt, const Level32& L, size_t n_threads) {
         for (size_t i = b; i < e; i++) {
             const uint32_t P = bsym[i];
             const uint64_t f = blen[i];
-            if (L.has_hocc[P]) *out++ = {P, FROM_BWT32, f};
+            if (L.has_hocc[P]) *out++ = {P, FROM_BWT32, (FT)f};
             uint32_t l = L.rule_l[P], r = L.rule_r[P];
             while (r >= alph3) {
                 const uint32_t g = (uint32_t)(r - alph3);
-                *out++ = {g, l, f};
+                *out++ = {g, l, (FT)f};
                 l = L.rule_l[g];
                 r = L.rule_r[g];
             }
@@ -389,6 +397,12 @@ inline RunArr parse_to_bwt32(const uint64_t* parse, uint64_t n) {
 }
 
 // ind_phase (exact_ind_phase.cpp:674-697): levels[0] is round 1
+inline RunArr induce_level_mt(RunArr& bwt, const Level32& L, size_t n_threads) {
+    uint64_t longest = 0;  // the tuples copy run lengths of BWT_{i+1}
+    for (size_t i = 0; i < bwt.size(); i++) longest = std::max(longest, bwt.len[i]);
+    return longest < (1ull << 32) ? induce_level_t<uint32_t>(bwt, L, n_threads) : induce_level_t<uint64_t>(bwt, L, n_threads);
+}
+
 inline RunArr ind_phase_mt(const std::vector<Level32>& levels, const uint64_t* final_parse, uint64_t n_strings, size_t n_threads) {
     RunArr bwt = parse_to_bwt32(final_parse, n_strings);
     for (size_t lv = levels.size(); lv-- > 0;) {
