@@ -71,6 +71,20 @@ int grlbwt_build_file(const char* input_file, const char* output_file, int sym_b
     }
 }
 
+int grlbwt_selftest_write(const char* path, const uint64_t* syms, const uint64_t* lens, uint64_t n_runs, uint64_t sb, uint64_t fb, int narrow) {
+    try {
+        if (!path || sb == 0 || sb > 8 || fb == 0 || fb > 8) throw std::runtime_error("bad arguments");
+        if (narrow) {
+            std::vector<uint32_t> s32(syms, syms + n_runs);
+            grlbwt::write_rl_bwt(path, s32.data(), lens, n_runs, sb, fb);
+        } else grlbwt::write_rl_bwt(path, syms, lens, n_runs, sb, fb);
+        return 0;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return -100;
+    }
+}
+
 const char* grlbwt_last_error(void) { return g_last_error.c_str(); }
 
 // host induction alone, from caller-provided level artefacts (CPU-only self test of ind_phase.hpp)

@@ -31,19 +31,19 @@ inline void write_rl_bwt(const std::string& path, const SymT* sym, const uint64_
     FILE* f = fopen(path.c_str(), "wb");
     if (!f) throw std::runtime_error("cannot open " + path + " for writing");
     const size_t rec = sb + fb;
-    std::vector<unsigned char> buf;
-    buf.reserve((size_t)1 << 24);
+    const size_t CAP = (size_t)1 << 24;           // records are packed with two 8-byte stores each, hence 16 bytes of slack
+    std::vector<unsigned char> buf(CAP + 16);
+    unsigned char* p = buf.data();
     uint64_t hdr[2] = {sb, fb};
     bool ok = fwrite(hdr, 8, 2, f) == 2;
     for (uint64_t i = 0; i < n_runs && ok; i++) {
-        unsigned char tmp[16];
-        const uint64_t s64 = (uint64_t)sym[i];
-        memcpy(tmp, &s64, sb);          // little endian hosts only
-        memcpy(tmp + sb, &len[i], fb);
-        buf.insert(buf.end(), tmp, tmp + rec);
-        if (buf.size() + rec > buf.capacity()) { ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size(); buf.clear(); }
+        const uint64_t s64 = (uint64_t)sym[i], l64 = len[i];
+        memcpy(p, &s64, 8);                       // little endian hosts only: the low sb bytes are the record's symbol ...
+        memcpy(p + sb, &l64, 8);                  // ... overwritten from offset sb on by the low fb bytes of the length
+        p += rec;
+        if ((size_t)(p - buf.data()) + rec > CAP) { ok = fwrite(buf.data(), 1, (size_t)(p - buf.data()), f) == (size_t)(p - buf.data()); p = buf.data(); }
     }
-    if (ok && !buf.empty()) ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+    if (ok && p != buf.data()) ok = fwrite(buf.data(), 1, (size_t)(p - buf.data()), f) == (size_t)(p - buf.data());
     ok = (fclose(f) == 0) && ok;
     if (!ok) throw std::runtime_error("short write on " + path);
 }

@@ -41,6 +41,10 @@ int grlbwt_selftest_induce(int n_levels, const uint64_t* alphabet, const uint64_
                            const uint8_t* const* has_hocc, const uint64_t* n_pre, const uint64_t* const* pre_sym, const uint64_t* const* pre_len,
                            const uint64_t* final_parse, uint64_t n_strings, int n_threads /* 0 = sequential 64-bit path */, grlbwt_result_t* out);
 
+/* self test of the .rl_bwt writer alone (no device; format of include/bwt_io.h:377-382,448-490): runs given as u64
+ * symbols / lengths; narrow != 0 routes through the 32-bit-symbol instantiation the multi-threaded host uses */
+int grlbwt_selftest_write(const char* path, const uint64_t* syms, const uint64_t* lens, uint64_t n_runs, uint64_t sb, uint64_t fb, int narrow);
+
 #ifdef __cplusplus
 }
 #endif

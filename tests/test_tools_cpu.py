@@ -82,3 +82,21 @@ def test_tools_usage_messages():
     for t in ("grl2plain", "grlbwt2rle", "reverse_bwt", "bwt_stats", "bwt_check"):
         r = subprocess.run([tool(t)], capture_output=True, text=True)
         assert r.returncode == 0 and "usage:" in r.stdout
+
+
+@pytest.mark.parametrize("sb,fb", [(1, 1), (1, 4), (2, 2), (3, 4), (4, 5), (8, 8), (1, 8), (5, 3)])
+def test_rl_bwt_writer_matches_the_format(tmp_path, sb, fb):
+    """the host's .rl_bwt writer (two 8-byte stores per record into a slack buffer) == the byte-by-byte definition"""
+    import ctypes as C
+    from grlbwt_b200.api import lib_host
+    rng = np.random.default_rng(sb * 10 + fb)
+    L = lib_host()
+    L.grlbwt_selftest_write.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int]
+    for n in (0, 1, 7, 100003, (1 << 24) // (sb + fb) + 5):   # the last size crosses the writer's flush boundary
+        syms = rng.integers(0, 1 << min(8 * sb, 63), size=n, dtype=np.uint64)
+        lens = rng.integers(1, 1 << min(8 * fb, 63), size=n, dtype=np.uint64)
+        for narrow in ((0, 1) if sb <= 4 else (0,)):
+            path = tmp_path / f"w_{sb}_{fb}_{n}_{narrow}.rl_bwt"
+            rc = L.grlbwt_selftest_write(str(path).encode(), syms.ctypes.data, lens.ctypes.data, n, sb, fb, narrow)
+            assert rc == 0
+            assert path.read_bytes() == O.rl_bwt_bytes(syms, lens, sb, fb), (n, narrow)
