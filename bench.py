@@ -26,7 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-METRIC = "input MB/s to BCR BWT (parse phase: all rounds on device)"
+METRIC = "input MB/s through the parse phase of the BCR BWT construction (all grammar rounds on device); whole construction: bwt_total"
 READ_LEN = 150
 
 
@@ -40,10 +40,17 @@ def parse_args():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3"], help="c2: random reads (the metric's config); c3: repetitive genomes (BASELINE.json configs[2])")
     ap.add_argument("--copies", type=int, default=1000, help="c3: genome copies")
     ap.add_argument("--genome", type=int, default=4_000_000, help="c3: genome length")
-    ap.add_argument("--sample-reads", type=int, default=100_000, help="reads of the bounded CPU-baseline sample")
+    ap.add_argument("--sample-reads", type=int, default=1_000_000, help="reads of the bounded CPU-baseline / same-sample leg (151 MB)")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0, help="--impl reference: wall-clock budget of the whole run; the per-step sample is sized to fit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bwt-reads", type=int, default=8_000_000, help="reads of the whole-construction leg (bwt_total); 0 skips it")
+    ap.add_argument("--write-digest", action="store_true", help="1 GPU: store the output digest under profiles/ as the value every rank count must reproduce")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
+
+
+def c2_workload_desc(reads):
+    return f"C2: {reads} reads x {READ_LEN} bp uniform ACGT + newline ({reads * (READ_LEN + 1) / 1e9:.3f} GB), BASELINE.json configs[1]"
 
 
 # ---------------------------------------------------------------- reference / CPU baseline
@@ -52,10 +59,11 @@ def cpu_parse_phase(sample_reads, threads, repeats=1):
     import numpy as np
     import gen
     arr = gen.dna_reads(sample_reads, READ_LEN, seed=42)
-    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
-    desc = f"{sample_reads} reads x {READ_LEN} bp ({arr.nbytes / 1e6:.1f} MB) of the same generator"
+    from oracle import refbin
+    harness = refbin.ref_path("ref_harness")
+    desc = f"{sample_reads} reads x {READ_LEN} bp ({arr.nbytes / 1e6:.1f} MB), tests/gen.dna_reads seed 42"
     secs = []
-    if os.path.exists(harness):
+    if harness:
         with tempfile.TemporaryDirectory(dir="/tmp") as td:
             inp = os.path.join(td, "sample.txt")
             arr.tofile(inp)
@@ -65,7 +73,7 @@ def cpu_parse_phase(sample_reads, threads, repeats=1):
                 if r.returncode != 0 or not t:
                     raise RuntimeError("reference harness failed: " + (r.stdout + r.stderr)[-400:])
                 secs.append(float(t[0].split()[1]))
-        return [arr.nbytes / 1e6 / s for s in secs], "reference", desc + f"; reference par_phase, -t {threads}", threads
+        return [arr.nbytes / 1e6 / s for s in secs], "reference", desc + f"; unmodified reference par_phase, -t {threads}, built {refbin.ref_flags()}", threads
     from oracle import oracle as O  # port (single thread)
     for _ in range(repeats):
         t0 = time.time()
@@ -81,12 +89,17 @@ def run_reference(args, rank):
         return
     threads = os.cpu_count() or 1
     total = args.warmup + args.steps
+    # every step is one run of the reference's parse phase on a bounded sample; the sample is as large as the budget of the
+    # whole run allows (the reference parses ~5 MB/s on reads and gets slower with size, so larger samples flatter it less)
+    per_step_s = max(2.0, args.ref_budget_s / max(1, total) - 1.0)
+    args.sample_reads = int(min(args.sample_reads, max(100_000, per_step_s * 4.0e6 / (READ_LEN + 1))))
     rates, kind, desc, cores = cpu_parse_phase(args.sample_reads, threads, repeats=total)
     timed = rates[args.warmup:]
     # the reference's whole program (parse + induction + output) on the same sample, once, for context
     bwt_total = None
-    exe = os.path.join(ROOT, "oracle", "_ref", "grlbwt_ref")
-    if os.path.exists(exe):
+    from oracle import refbin
+    exe = refbin.ref_path("grlbwt_ref")
+    if exe and args.ref_budget_s >= 60:
         import gen
         arr = gen.dna_reads(args.sample_reads, READ_LEN, seed=42)
         with tempfile.TemporaryDirectory(dir="/tmp") as td:
@@ -102,7 +115,9 @@ def run_reference(args, rank):
     val = sample_mb * len(timed) / (sum(ms) / 1e3)
     line = {"impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": "MB/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(sum(ms) / len(ms), 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8", "data": "synthetic", "config": {"workload": f"C2-shaped sample: {desc}", "timing": "host wall clock inside the harness"},
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": c2_workload_desc(args.reads), "sample": desc, "same_config": False,
+                       "timing": "host wall clock around par_phase inside the harness; each step = one bounded sample of the workload"},
             "cpu_baseline": {"value": round(val, 3), "unit": "MB/s", "cores": cores, "kind": kind, "sample": desc},
             "e2e": {"value": round(val, 3), "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
             "bwt_total": bwt_total}
@@ -151,34 +166,41 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------- our arm
-def make_reads_on_device(torch, n_reads, seed, device):
-    """C2 generator on the device (uniform ACGT + '\\n'); same shape as tests/gen.dna_reads, torch RNG"""
+GEN_BLOCK_READS = 250_000
+
+
+def make_reads_on_device(torch, first_read, n_reads, seed, device):
+    """Reads [first_read, first_read + n_reads) of THE collection defined by `seed` (uniform ACGT + '\\n'; shape of
+    tests/gen.dna_reads, torch RNG). The collection is generated in fixed blocks of GEN_BLOCK_READS reads, block b from
+    the generator state seed * 1000003 + b, whatever slice is asked for: N ranks build slices of the SAME global text,
+    so the output of an N-rank job can be compared with the 1-rank job (digest in the JSON line)."""
     g = torch.Generator(device=device)
-    g.manual_seed(seed)
     lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=device)
     out = torch.empty((n_reads, READ_LEN + 1), dtype=torch.uint8, device=device)
-    chunk = 2_000_000
-    for i in range(0, n_reads, chunk):
-        j = min(n_reads, i + chunk)
-        idx = torch.randint(0, 4, (j - i, READ_LEN), generator=g, device=device, dtype=torch.int64)
-        out[i:j, :READ_LEN] = lut[idx]
+    B = GEN_BLOCK_READS
+    for b in range(first_read // B, (first_read + n_reads - 1) // B + 1):
+        g.manual_seed(seed * 1_000_003 + b)
+        idx = torch.randint(0, 4, (B, READ_LEN), generator=g, device=device, dtype=torch.int64)  # always the whole block
+        lo, hi = max(first_read, b * B), min(first_read + n_reads, (b + 1) * B)
+        out[lo - first_read: hi - first_read, :READ_LEN] = lut[idx[lo - b * B: hi - b * B]]
         del idx
     out[:, READ_LEN] = 10
     return out.reshape(-1)
 
 
-def make_genomes_on_device(torch, n_copies, genome_len, seed, device, snp=1e-3, dele=1e-4):
-    """C3 generator on the device: copies of one random genome with substitutions and single-base deletions
-    (same shape as tests/gen.repetitive_genomes; every rank derives the SAME base genome from `seed`)"""
+def make_genomes_on_device(torch, first_copy, n_copies, genome_len, seed, device, snp=1e-3, dele=1e-4):
+    """Copies [first_copy, first_copy + n_copies) of the C3 collection: one random genome (seed 7), copy i mutated from the
+    generator state seed * 1000003 + i (substitutions + single-base deletions; shape of tests/gen.repetitive_genomes), so
+    every rank count sees the same global text"""
     gb = torch.Generator(device=device)
     gb.manual_seed(7)
     base = torch.randint(0, 4, (genome_len,), generator=gb, device=device, dtype=torch.int64)
     g = torch.Generator(device=device)
-    g.manual_seed(seed)
     lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=device)
     nl = torch.tensor([10], dtype=torch.uint8, device=device)
     parts = []
-    for _ in range(n_copies):
+    for i in range(first_copy, first_copy + n_copies):
+        g.manual_seed(seed * 1_000_003 + i)
         s = base.clone()
         m = torch.rand(genome_len, generator=g, device=device) < snp
         s[m] = (s[m] + torch.randint(1, 4, (int(m.sum()),), generator=g, device=device)) % 4
@@ -188,12 +210,20 @@ def make_genomes_on_device(torch, n_copies, genome_len, seed, device, snp=1e-3, 
     return torch.cat(parts)
 
 
+def split_range(total, world, rank):
+    """contiguous ranges of whole strings, as even as possible (the reference's mt split, parsing_strategies.h:208-214)"""
+    per, extra = divmod(total, world)
+    first = rank * per + min(rank, extra)
+    return first, per + (1 if rank < extra else 0)
+
+
 def run_ours(args, rank, world, local_rank):
+    import hashlib
     import numpy as np
     import torch
     import torch.distributed as dist
     import grlbwt_b200 as G
-    from grlbwt_b200 import multigpu as M
+    from grlbwt_b200 import mg
 
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the parse phase has no CPU fallback")
@@ -208,27 +238,29 @@ def run_ours(args, rank, world, local_rank):
         pass
     hbm_peak, peak_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json (measured copy)") if "hbm_gbs" in peaks else (6650.0, "fallback 6.65 TB/s")
 
-    # strong scaling: the C2 collection (args.reads reads) is split into contiguous ranges of whole reads, one per rank
+    # strong scaling: ONE global collection (rank-independent generator), split into contiguous ranges of whole strings
     if args.workload == "c2":
-        my_reads = args.reads // world + (1 if rank < args.reads % world else 0)
-        text = make_reads_on_device(torch, my_reads, 42 + rank, dev)
+        first_read, my_reads = split_range(args.reads, world, rank)
+        text = make_reads_on_device(torch, first_read, my_reads, 42, dev)
         n = text.numel()
         n_total = args.reads * (READ_LEN + 1)
-        wl_desc = f"C2: {args.reads} reads x {READ_LEN} bp uniform ACGT + newline ({n_total / 1e9:.3f} GB), BASELINE.json configs[1]"
+        wl_desc = c2_workload_desc(args.reads)
+        wl_key = f"c2_{args.reads}"
     else:
-        my_copies = args.copies // world + (1 if rank < args.copies % world else 0)
-        text = make_genomes_on_device(torch, my_copies, args.genome, 1000 + rank, dev)
+        first_copy, my_copies = split_range(args.copies, world, rank)
+        text = make_genomes_on_device(torch, first_copy, my_copies, args.genome, 1000, dev)
         n = text.numel()
         tot = torch.tensor([n], dtype=torch.int64, device=dev)
         if world > 1:
             dist.all_reduce(tot)
         n_total = int(tot.item())
         wl_desc = f"C3: {args.copies} copies of a {args.genome} bp genome, 0.1% SNPs + 0.01% deletions ({n_total / 1e9:.3f} GB), BASELINE.json configs[2]"
+        wl_key = f"c3_{args.copies}x{args.genome}"
     torch.cuda.synchronize()
-    stream = torch.cuda.Stream(device=dev)   # the library issues every kernel on this stream, so torch events bracket it
+    stream = torch.cuda.Stream(device=dev)   # the library issues every kernel (and NCCL call) on this stream, so torch events bracket it
     torch.cuda.set_stream(stream)
     ctx = G.GrlGpu(local_rank, 0, stream=stream.cuda_stream)
-    engine = M.GpuEngine(ctx, dev)
+    comm = mg.nccl_comm_from_torch(dist, rank, world, local_rank, torch) if world > 1 else None
     arena = [None]
     e2e_parts = {}
 
@@ -237,50 +269,67 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run_phase(fetch, collect=None):
-        """all rounds on the text set in ctx; fetch: copy every level's artefacts + the final parse to the host"""
+    def run_phase(fetch, collect=None, digest=None, slices=None):
+        """all rounds on the text set in ctx. fetch: copy this rank's part of every level + its final parse to the host
+        (pinned arena, copies overlapped with the next round); digest: per-round checksums + final parse for the N-identity check"""
         d2h, a_off = 0, 0
         if world == 1:
             ctx.stats()
-            while True:
-                r = ctx.round()
-                if collect is not None:
-                    collect.append(r.as_dict())
-                if fetch:  # every level lands in its own slice of the pinned arena while the next round computes
-                    e2e_parts.setdefault("round_ms", []).append(round(r.device_ms, 1))
-                    ctx.fetch_level(arena[0], async_=True, offset=a_off, narrow_len=True)  # 32-bit run lengths where they fit, as the C++ host does
-                    a_off = ctx.arena_end
-                    d2h += r.tot_phrases * (2 * r.sym_bytes + 1) + r.n_pre_runs * (r.sym_bytes + (4 if r.n_in + r.parse_len < (1 << 32) else 8))
-                if r.done:
-                    if fetch:
-                        t_tail = time.perf_counter()
-                        ctx.fetch_wait()
-                        d2h += ctx.fetch_parse(arena[0][a_off:]).nbytes
-                        e2e_parts["tail_wait_ms"] = (time.perf_counter() - t_tail) * 1e3
-                    return d2h
-        st = M.global_stats(engine)
+        else:
+            ctx.mg_stats(comm)
         while True:
-            info, done = M.distributed_round(engine, st["n_strings"], want_level=fetch)
+            r = ctx.round() if world == 1 else ctx.mg_round(comm)
             if collect is not None:
-                collect.append(info)
-            if fetch and rank == 0:
-                engine.fetch_level(arena[0])
-                d2h += info["tot_phrases"] * (2 * info["sym_bytes"] + 1) + info["n_pre_runs"] * (info["sym_bytes"] + 8)
-            if done:
+                collect.append(r.as_dict())
+            narrow = r.n_in + r.parse_len < (1 << 32)  # run lengths of the level fit 32 bits, as the C++ host fetches them
+            if world == 1:
+                tot_l, pre_l, plen_l = r.tot_phrases, r.n_pre_runs, r.parse_len
+            else:
+                sl = ctx.mg_slice_info()
+                tot_l, pre_l, plen_l = sl.tot_local, sl.n_pre_local, sl.parse_len_local
+                if collect is not None:
+                    collect[-1]["exchange_bytes_sent"] = sl.exchange_bytes
+                if slices is not None:
+                    slices.append((tot_l, pre_l))
+            if digest is not None:
+                cs = ctx.level_checksum() if world == 1 else ctx.mg_slice_checksum()
+                if world > 1:
+                    t = torch.from_numpy(np.array(cs, np.uint64).view(np.int64)).to(dev)
+                    dist.all_reduce(t)   # sums mod 2^64: the slices of a level add up to the single-GPU value
+                    cs = [int(x) for x in t.cpu().numpy().view(np.uint64)]
+                digest.append([r.tot_phrases, r.n_pre_runs, r.parse_len, r.n_phrases, r.dict_syms] + cs)
+            if fetch:
+                e2e_parts.setdefault("round_ms", []).append(round(r.device_ms, 1))
+                if world == 1:
+                    ctx.fetch_level(arena[0], async_=True, offset=a_off, narrow_len=True)
+                else:
+                    ctx.mg_fetch_slice(arena[0], offset=a_off, narrow_len=narrow, async_=True)
+                a_off = ctx.arena_end
+                d2h += tot_l * (2 * r.sym_bytes + 1) + pre_l * (r.sym_bytes + (4 if narrow else 8))
+            if r.done:
                 if fetch:
-                    fp = M.gather_final_parse(engine)
-                    d2h += 0 if fp is None else fp.nbytes
+                    t_tail = time.perf_counter()
+                    ctx.fetch_wait()
+                    d2h += ctx.fetch_parse_local(plen_l, arena[0][a_off:]).nbytes
+                    e2e_parts["tail_wait_ms"] = (time.perf_counter() - t_tail) * 1e3
+                if digest is not None:
+                    part = ctx.fetch_parse_local(plen_l).astype(np.uint64)
+                    if world > 1:
+                        parts = [None] * world if rank == 0 else None
+                        dist.gather_object(part, parts, dst=0)
+                        part = np.concatenate(parts) if rank == 0 else None
+                    digest.append(hashlib.sha256(part.tobytes()).hexdigest() if part is not None else None)
                 return d2h
 
-    def step_resident(collect=None):
+    def step_resident(collect=None, digest=None, slices=None):
         ctx.set_text_device(text.data_ptr(), n, 1)
-        run_phase(False, collect)
+        run_phase(False, collect, digest, slices)
 
     # ---- value: text resident in HBM ----
     for _ in range(args.warmup):
         step_resident()
-    rounds_info = []
-    step_resident(rounds_info)           # untimed: per-round figures
+    rounds_info, digest, slice_sizes = [], [], []
+    step_resident(rounds_info, digest, slice_sizes)   # untimed: per-round figures, output digest
     ctx.profile_reset(); ctx.profile_enable(True)
     step_resident()                      # untimed: per-kernel CUDA-event timing enabled
     prof = ctx.profile()
@@ -305,17 +354,18 @@ def run_ours(args, rank, world, local_rank):
         ms_total = float(t.item())
     value = n_total * args.steps / 1e6 / (ms_total / 1e3)
 
-    # ---- e2e: host buffers through the C ABI ----
+    # ---- e2e: host buffers through the C ABI (pinned text -> device; this rank's levels + final parse -> pinned host) ----
     e2e = None
     if not args.no_e2e:
         host_text = torch.empty(n, dtype=torch.uint8, pin_memory=True)
         host_text.copy_(text)
         torch.cuda.synchronize()
         host_np = host_text.numpy()
-        # pinned landing zone for the level artefacts (largest level of the workload, measured in the resident steps)
-        need = sum(r["tot_phrases"] * 17 + r["n_pre_runs"] * 16 + 256 for r in rounds_info) + rounds_info[-1]["parse_len"] * 8 * world + (1 << 20)
-        if world > 1 and rank != 0:
-            need = 1 << 20  # the levels of a multi-rank job are assembled and fetched on rank 0 only
+        if world == 1:
+            need = sum(r["tot_phrases"] * 9 + r["n_pre_runs"] * 12 + 256 for r in rounds_info)
+        else:
+            need = sum(int(t_ * 9 * 1.05) + int(p_ * 12 * 1.05) + 4096 for t_, p_ in slice_sizes)
+        need += (n // (READ_LEN + 1) + 1024) * 8 + (1 << 20)
         arena[0] = torch.empty(int(need), dtype=torch.uint8, pin_memory=True).numpy()
         d2h_bytes = [0]
 
@@ -345,9 +395,45 @@ def run_ours(args, rank, world, local_rank):
             h2d_b, d2h_b = n, d2h_bytes[0]
         e2e = {"value": round(n_total * args.steps / 1e6 / (wall_ms / 1e3), 3), "unit": "MB/s", "h2d_bytes_per_step": int(h2d_b),
                "d2h_bytes_per_step": int(d2h_b), "ms_per_step": round(wall_ms / args.steps, 3),
-               "timing": "host wall clock between stream synchronisations, max over ranks (fetches are host-blocking)",
+               "what": "every rank copies its shard from pinned host memory to its GPU and copies its part of every level (rules, hocc marks, "
+                       "preliminary BWT) and of the final parse back to pinned host memory; bytes are summed over the ranks",
+               "timing": "host wall clock between stream synchronisations, max over ranks",
                "last_step_parts_ms": {k: (v if isinstance(v, list) else round(v, 1)) for k, v in e2e_parts.items()}}
+        del host_text
+
+    # ---- same sample as the reference arm / cpu_baseline (numpy generator, host buffers), 1 GPU only ----
+    same_sample = None
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            import gen
+            sample = gen.dna_reads(args.sample_reads, READ_LEN, seed=42)
+            pin = torch.from_numpy(sample).pin_memory().numpy()
+            need = 40 * sample.nbytes // 10 + (1 << 22)
+            arena[0] = torch.empty(int(need), dtype=torch.uint8, pin_memory=True).numpy()
+            ts = []
+            for _ in range(4):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                ctx.set_text(pin)
+                run_phase(True)
+                torch.cuda.synchronize()
+                ts.append(time.perf_counter() - t0)
+            ours = sample.nbytes / 1e6 / min(ts[1:])
+            rates, kind, desc, cores = cpu_parse_phase(args.sample_reads, os.cpu_count() or 1, repeats=1)
+            cpu = {"value": round(rates[0], 3), "unit": "MB/s", "cores": cores, "kind": kind, "sample": desc}
+            same_sample = {"sample": f"{args.sample_reads} reads x {READ_LEN} bp ({sample.nbytes / 1e6:.1f} MB), tests/gen.dna_reads seed 42: the identical bytes for both",
+                           "ours_e2e_MBps": round(ours, 1), "reference_MBps": round(rates[0], 3), "ratio": round(ours / rates[0], 1),
+                           "what": "parse phase, host buffers in / levels out (ours, best of 3 after one warm-up) vs the reference's par_phase with -t = all host cores"}
+        except Exception as e:  # the baseline is reporting only
+            cpu = {"value": None, "unit": "MB/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
+    info_comm = comm.info() if comm is not None else None
+    if comm is not None:
+        comm.close()
     ctx.close()
+    arena[0] = None
+    del text
+    torch.cuda.empty_cache()
 
     # ---- roofline of the dominant kernel (CUDA events on the launch stream, live, one profiled step) ----
     roof = None
@@ -355,11 +441,11 @@ def run_ours(args, rank, world, local_rank):
         name, (nl, ms, by) = max(prof.items(), key=lambda kv: kv[1][1])
         achieved = by / 1e9 / (ms / 1e3) if ms > 0 else 0.0
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
         if os.path.exists(tpath) and args.workload == "c2" and args.reads == 50_000_000 and world == 1:
             tj = json.load(open(tpath))
             if tj.get("kernel") == name:   # ncu DRAM bytes of the same kernel on the same workload, per launch
-                traffic, traffic_src = round(tj["traffic_bytes_per_launch"]), "profiles/r01_ncu_traffic.json (ncu dram__bytes_read+write, mean over the step's launches)"
+                traffic, traffic_src = round(tj["traffic_bytes_per_launch"]), "profiles/r02_ncu_traffic.json (ncu dram__bytes_read+write, mean over the step's launches)"
         roof = {"bound": "hbm", "kernel": name, "launches_per_step": nl, "avg_launch_ms": round(ms / max(nl, 1), 4), "achieved": round(achieved, 1),
                 "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": traffic, "traffic_source": traffic_src,
                 "bytes_per_launch": round(by / max(nl, 1)), "peak_source": peak_src,
@@ -367,40 +453,64 @@ def run_ours(args, rank, world, local_rank):
                 "bytes_model": "expected DRAM bytes of the kernel's launches (SURVEY.md 8d traffic table; DESIGN.md kernels section)"}
     alg_bytes = sum(r["algorithmic_bytes"] for r in rounds_info)
     round_ms = sum(r["device_ms"] for r in rounds_info)
+    if world > 1:   # B_r is a per-rank share in multi-GPU rounds: aggregate GB/s = sum over ranks / max time
+        t = torch.tensor([float(alg_bytes)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t)
+        alg_bytes = float(t.item())
+        t = torch.tensor([round_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        round_ms = float(t.item())
     keys = ("round", "n_in", "parse_len", "n_phrases", "dict_syms", "tot_phrases", "n_pre_runs", "device_ms", "text_pass_ms", "dict_ms", "rewrite_ms",
-            "algorithmic_bytes", "exchange_bytes_sent", "gather_bytes", "ranking")
+            "algorithmic_bytes", "exchange_bytes_sent")
     parse_rounds = {"algorithmic_GB": round(alg_bytes / 1e9, 3), "device_ms": round(round_ms, 3),
                     "achieved_GBps": round(alg_bytes / 1e6 / round_ms, 1) if round_ms else None,
-                    "frac_of_measured_peak": round(alg_bytes / 1e6 / round_ms / hbm_peak, 4) if round_ms else None,
-                    "frac_of_nominal_8TBps": round(alg_bytes / 1e6 / round_ms / 8000.0, 4) if round_ms else None,
-                    "scope": "rank 0" if world > 1 else "whole job",
+                    "frac_of_measured_peak": round(alg_bytes / 1e6 / round_ms / (hbm_peak * world), 4) if round_ms else None,
+                    "frac_of_nominal_8TBps": round(alg_bytes / 1e6 / round_ms / (8000.0 * world), 4) if round_ms else None,
+                    "scope": "bytes summed over the ranks, time = max over ranks; per_round lists rank 0's share" if world > 1 else "whole job",
                     "per_round": [{k: (round(v, 3) if isinstance(v, float) else v) for k, v in r.items() if k in keys} for r in rounds_info]}
     kernels = {k: {"launches": v[0], "ms": round(v[1], 3), "model_GBps": round(v[2] / 1e6 / v[1], 1) if v[1] > 0 else None}
-               for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]}
+               for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:14]}
 
-    # ---- whole construction (device parse phase + multi-threaded host induction) on a bounded sample, for context ----
+    # ---- output digest: equal for every number of ranks (per-round level checksums + sha256 of the final parse) ----
+    dg = None
+    if rank == 0:
+        h = hashlib.sha256(json.dumps(digest).encode()).hexdigest()
+        dpath = os.path.join(ROOT, "profiles", f"digest_{wl_key}.json")
+        expected = None
+        if os.path.exists(dpath):
+            expected = json.load(open(dpath)).get("sha256")
+        elif world == 1 and args.write_digest:
+            json.dump({"workload": wl_desc, "n_gpus": 1, "sha256": h, "per_round": digest[:-1], "final_parse_sha256": digest[-1]}, open(dpath, "w"), indent=1)
+        dg = {"sha256": h, "rounds": len(digest) - 1, "final_parse_sha256": digest[-1], "per_round_tot_phrases": [d[0] for d in digest[:-1]],
+              "expected_from_1_gpu": expected, "matches_1_gpu": (h == expected) if expected else None,
+              "what": "sha256 over [tot_phrases, pre-BWT runs, parse length, distinct phrases, dictionary symbols, 4 checksums of rules/hocc/pre-BWT] of every "
+                      "round + sha256 of the final parse in string order; the N-rank job parses slices of the same global text, so the value is the same for "
+                      "1, 2, 4 and 8 GPUs (profiles/digest_*.json holds the 1-GPU value)"}
+
+    # ---- whole construction: device parse phase + multi-threaded host induction (C++ host, host text -> run-length BCR BWT) ----
     bwt_total = None
-    if rank == 0 and world == 1 and not args.no_e2e and args.workload == "c2":
+    if world > 1:
+        dist.barrier()   # every rank has released its device memory
+    if rank == 0 and not args.no_e2e and args.workload == "c2" and args.bwt_reads > 0:
         try:
             import gen
-            sample = gen.dna_reads(min(args.reads, 2_000_000), READ_LEN, seed=42)
             thr = os.cpu_count() or 1
+            sample = gen.dna_reads(min(args.reads, args.bwt_reads), READ_LEN, seed=42)
+            devs = list(range(world))
             G.build_bwt(sample[: 151 * 1000], n_threads=thr)  # warm the host library
-            _, lens_, _, _, info = G.build_bwt(sample, device=local_rank, n_threads=thr)
+            if world == 1:
+                _, lens_, _, _, info = G.build_bwt(sample, device=0, n_threads=thr)
+            else:
+                _, lens_, _, _, info = mg.build_bwt_mg(sample, devs, n_threads=thr, comm=mg.COMM_AUTO)
             tot_ms = info["h2d_ms"] + info["par_phase_ms"] + info["ind_phase_ms"]
-            bwt_total = {"value": round(sample.nbytes / 1e6 / (tot_ms / 1e3), 3), "unit": "MB/s", "sample": f"{sample.size // 151} reads x {READ_LEN} bp ({sample.nbytes / 1e6:.0f} MB)",
+            bwt_total = {"value": round(sample.nbytes / 1e6 / (tot_ms / 1e3), 3), "unit": "MB/s", "n_gpus": world,
+                         "sample": f"{sample.size // 151} reads x {READ_LEN} bp ({sample.nbytes / 1e6:.0f} MB)",
                          "h2d_ms": round(info["h2d_ms"], 1), "parse_phase_ms": round(info["par_phase_ms"], 1), "induction_ms": round(info["ind_phase_ms"], 1),
-                         "host_threads": thr, "bwt_runs": int(lens_.size), "what": "host text -> run-length BCR BWT in host memory (grlbwt_build), file I/O excluded"}
+                         "host_threads": thr, "bwt_runs": int(lens_.size), "exchange": info.get("comm"),
+                         "what": "input MB/s to BCR BWT: host text -> run-length BCR BWT in host memory through the C++ host (grlbwt_build / grlbwt_build_mg: "
+                                 "one host thread per GPU), file I/O excluded"}
         except Exception as e:
-            bwt_total = {"value": None, "error": str(e)[:200]}
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        try:
-            rates, kind, desc, cores = cpu_parse_phase(args.sample_reads, os.cpu_count() or 1, repeats=1)
-            cpu = {"value": round(rates[0], 3), "unit": "MB/s", "cores": cores, "kind": kind, "sample": desc}
-        except Exception as e:  # the baseline is reporting only
-            cpu = {"value": None, "unit": "MB/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
+            bwt_total = {"value": None, "error": str(e)[:300]}
 
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 3), "unit": "MB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -408,15 +518,16 @@ def run_ours(args, rank, world, local_rank):
                 "data": "synthetic",
                 "config": {"workload": wl_desc,
                            "reads": args.reads if args.workload == "c2" else None, "cache": "the text of every round-1 pass (7.55 GB at the default size) exceeds the 126 MB L2",
+                           "generator": "torch CUDA RNG in fixed blocks of reads seeded per block: every rank count parses slices of the same global text",
                            "parallelism": "1 GPU" if world == 1 else
-                           f"{world} ranks: contiguous ranges of whole reads per rank; per round one hash-partitioned all-to-all-v of the local "
-                           f"dictionaries + one all-gather-v of the deduplicated global dictionary over NCCL; large dictionaries are ranked "
-                           f"distributed (suffix entries partitioned by first-key range, three all-reduces, metasymbols returned to the "
-                           f"requesters by a reverse all-to-all-v), small ones replicated"},
-                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "bwt_total": bwt_total,
-                "parse_rounds": parse_rounds, "kernels": kernels}
+                           f"{world} ranks, contiguous ranges of whole reads; the round's dictionary is PARTITIONED, never replicated: phrases by owner (content hash), "
+                           f"suffix entries by first-key range, rules by rank range; all exchanges are NCCL grouped send/recv issued by libgrlgpu.so",
+                           "exchange": info_comm},
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "same_sample": same_sample,
+                "digest": dg, "bwt_total": bwt_total, "parse_rounds": parse_rounds, "kernels": kernels}
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

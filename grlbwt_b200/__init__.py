@@ -5,4 +5,4 @@ and bench.py); the product is lib/libgrlgpu.so, lib/libgrlbwt.so and the lib/grl
 """
 from .api import (GrlGpu, GrlGpuError, Round, Stats, build_bwt, build_bwt_file, lib_gpu, lib_host,  # noqa: F401
                   selftest_compact, selftest_induce, selftest_scan, selftest_sort, FLAG_SMALL_TABLE,
-                  FLAG_FORCE_SLOW_SCAN, FLAG_KEEP_DICT, FLAG_FORCE_UNCACHED, FLAG_SMALL_PILOT, FLAG_FORCE_DOUBLING, FLAG_FORCE_DIST_RANK, LIB_DIR)
+                  FLAG_FORCE_SLOW_SCAN, FLAG_KEEP_DICT, FLAG_FORCE_UNCACHED, FLAG_SMALL_PILOT, FLAG_FORCE_DOUBLING, LIB_DIR, Slice)

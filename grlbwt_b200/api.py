@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 LIB_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
-FLAG_SMALL_TABLE, FLAG_FORCE_SLOW_SCAN, FLAG_KEEP_DICT, FLAG_FORCE_UNCACHED, FLAG_SMALL_PILOT, FLAG_FORCE_DOUBLING, FLAG_FORCE_DIST_RANK = 1, 2, 4, 8, 16, 32, 64
+FLAG_SMALL_TABLE, FLAG_FORCE_SLOW_SCAN, FLAG_KEEP_DICT, FLAG_FORCE_UNCACHED, FLAG_SMALL_PILOT, FLAG_FORCE_DOUBLING = 1, 2, 4, 8, 16, 32
 CELL = {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}
 
 
@@ -32,6 +32,11 @@ class Round(C.Structure):
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Slice(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in ("rank_base", "tot_local", "pre_first", "n_pre_local", "exchange_bytes", "n_in_local", "parse_len_local")] + \
+               [("sym_bytes", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class BwtResult(C.Structure):
@@ -62,6 +67,7 @@ def lib_gpu():
         L.grlgpu_fetch_level_async.argtypes = [vp, vp, vp, vp, vp, vp]
         L.grlgpu_fetch_level32.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int]
         L.grlgpu_fetch_wait.argtypes = [vp]
+        L.grlgpu_level_checksum.argtypes = [vp, vp]
         L.grlgpu_fetch_parse.argtypes = [vp, vp]
         L.grlgpu_fetch_str_ptrs.argtypes = [vp, vp]
         L.grlgpu_fetch_dictionary.argtypes = [vp, vp, vp, vp, vp]
@@ -76,17 +82,26 @@ def lib_gpu():
         L.grlgpu_launch_count.restype = u64
         L.grlgpu_profile_entry.argtypes = [vp, C.c_int, C.c_char_p, C.c_int, C.POINTER(u64), C.POINTER(C.c_double), C.POINTER(u64)]
         L.grlgpu_histogram.argtypes = [vp, vp]
-        L.grlgpu_mg_set_alphabet.argtypes = [vp, u64]
-        L.grlgpu_mg_local.argtypes = [vp, C.c_int, vp, vp]
-        L.grlgpu_mg_pack.argtypes = [vp, vp, vp, vp]
-        L.grlgpu_mg_merge.argtypes = [vp, vp, vp, vp, u64, u64, vp]
-        L.grlgpu_mg_pack_part.argtypes = [vp, vp, vp, vp]
-        L.grlgpu_mg_global.argtypes = [vp, vp, vp, vp, u64, u64, C.c_int, C.POINTER(Round)]
-        L.grlgpu_mg_rank_sort.argtypes = [vp, vp, vp, vp, u64, u64, C.c_int, C.c_int, vp]
-        L.grlgpu_mg_rank_apply.argtypes = [vp, u64, vp, vp, vp]
-        L.grlgpu_mg_reply.argtypes = [vp, u64, vp, vp]
-        L.grlgpu_mg_rank_finish.argtypes = [vp, u64, u64, u64, vp, vp, vp, vp, C.c_int, C.POINTER(Round)]
-        L.grlgpu_mg_level_slice.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.grlgpu_nccl_unique_id.argtypes = [vp]
+        L.grlgpu_comm_create_nccl.argtypes = [C.POINTER(vp), vp, C.c_int, C.c_int, C.c_int]
+        L.grlgpu_local_group_create.argtypes = [C.POINTER(vp), C.c_int]
+        L.grlgpu_local_group_abort.argtypes = [vp]
+        L.grlgpu_local_group_destroy.argtypes = [vp]
+        L.grlgpu_comm_create_local.argtypes = [C.POINTER(vp), vp, C.c_int, C.c_int]
+        L.grlgpu_comm_destroy.argtypes = [vp]
+        L.grlgpu_comm_info.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.c_char_p, C.c_int]
+        L.grlgpu_set_peers.argtypes = [vp, vp, C.c_int]
+        L.grlgpu_mg_stats.argtypes = [vp, vp, C.POINTER(Stats)]
+        L.grlgpu_mg_round.argtypes = [vp, vp, C.POINTER(Round)]
+        L.grlgpu_mg_slice_info.argtypes = [vp, C.POINTER(Slice)]
+        L.grlgpu_mg_fetch_slice.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int]
+        L.grlgpu_mg_slice_checksum.argtypes = [vp, vp]
+        L.grlgpu_text_begin.argtypes = [vp, u64, C.c_int, u64]
+        L.grlgpu_text_stage.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
+        L.grlgpu_text_commit.argtypes = [vp, u64]
+        L.grlgpu_text_end.argtypes = [vp]
+        L.grlgpu_level_park.argtypes = [vp, C.c_int, vp]
+        L.grlgpu_copy_to_host.argtypes = [C.c_int, vp, vp, u64]
         L.grlgpu_selftest_scan.argtypes = [vp, u64, vp, vp]
         L.grlgpu_selftest_sort.argtypes = [vp, vp, u64, C.c_int]
         L.grlgpu_selftest_compact.argtypes = [vp, vp, u64, vp, vp]
@@ -106,6 +121,11 @@ def lib_host():
         L.grlbwt_free_result.argtypes = [C.POINTER(BwtResult)]
         L.grlbwt_build_file.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.grlbwt_last_error.restype = C.c_char_p
+        L.grlbwt_build_mg.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(BwtResult)]
+        L.grlbwt_last_digests.argtypes = [C.c_void_p, C.c_uint64]
+        L.grlbwt_last_digests.restype = C.c_uint64
+        L.grlbwt_last_exchange_bytes.restype = C.c_uint64
+        L.grlbwt_last_comm.restype = C.c_char_p
         _host = L
     return _host
 
@@ -157,6 +177,12 @@ class GrlGpu:
         self.last = r
         self._round_started = True
         return r
+
+    def level_checksum(self):
+        """four order-insensitive sums over the last round's rules / hocc marks / preliminary BWT (see grlgpu.h)"""
+        out = np.zeros(4, np.uint64)
+        self._check(self._L.grlgpu_level_checksum(self._h, _ptr(out)))
+        return [int(x) for x in out]
 
     def fetch_wait(self):
         self._check(self._L.grlgpu_fetch_wait(self._h))
@@ -214,63 +240,65 @@ class GrlGpu:
         self._check(self._L.grlgpu_fetch_dictionary(self._h, _ptr(syms), _ptr(lens), _ptr(freqs), _ptr(metas)))
         return syms, lens, freqs, metas
 
-    # ---- multi-GPU rounds (raw device pointers; the caller owns the exchange, see multigpu.py) ----
+    # ---- multi-GPU rounds: every rank makes the same calls in the same order (include/grlgpu.h) ----
     def histogram(self) -> np.ndarray:
         h = np.zeros(256, np.uint64)
         self._check(self._L.grlgpu_histogram(self._h, _ptr(h)))
         return h
 
-    def cell_bytes(self) -> int:
-        return int(self.last.cell_bytes_out) if self.last is not None and self._round_started else int(self._keep.dtype.itemsize if self._keep is not None else self._sym_bytes)
+    def set_peers(self, devices):
+        d = np.asarray(devices, np.int32)
+        self._check(self._L.grlgpu_set_peers(self._h, _ptr(d), d.size))
 
-    def mg_set_alphabet(self, max_sym: int):
-        self._check(self._L.grlgpu_mg_set_alphabet(self._h, max_sym))
+    def mg_stats(self, comm) -> Stats:
+        s = Stats()
+        self._check(self._L.grlgpu_mg_stats(self._h, comm.handle, C.byref(s)))
+        return s
 
-    def mg_local(self, n_ranks: int):
-        per = np.zeros((n_ranks, 2), np.uint64)
-        pl = np.zeros(1, np.uint64)
-        self._check(self._L.grlgpu_mg_local(self._h, n_ranks, _ptr(per), _ptr(pl)))
-        return [(int(a), int(b)) for a, b in per], int(pl[0])
-
-    def mg_pack(self, lens_ptr: int, counts_ptr: int, cells_ptr: int):
-        self._check(self._L.grlgpu_mg_pack(self._h, C.c_void_p(lens_ptr), C.c_void_p(counts_ptr), C.c_void_p(cells_ptr)))
-
-    def mg_merge(self, lens_ptr: int, counts_ptr: int, cells_ptr: int, m: int, n_cells: int):
-        part = np.zeros(2, np.uint64)
-        self._check(self._L.grlgpu_mg_merge(self._h, C.c_void_p(lens_ptr), C.c_void_p(counts_ptr), C.c_void_p(cells_ptr), m, n_cells, _ptr(part)))
-        return int(part[0]), int(part[1])
-
-    def mg_pack_part(self, lens_ptr: int, freqs_ptr: int, cells_ptr: int):
-        self._check(self._L.grlgpu_mg_pack_part(self._h, C.c_void_p(lens_ptr), C.c_void_p(freqs_ptr), C.c_void_p(cells_ptr)))
-
-    def mg_global(self, lens_ptr: int, freqs_ptr: int, cells_ptr: int, d: int, n_cells: int, done: bool):
+    def mg_round(self, comm) -> Round:
         r = Round()
-        self._check(self._L.grlgpu_mg_global(self._h, C.c_void_p(lens_ptr), C.c_void_p(freqs_ptr), C.c_void_p(cells_ptr), d, n_cells, int(done), C.byref(r)))
+        self._check(self._L.grlgpu_mg_round(self._h, comm.handle, C.byref(r)))
         self.last = r
         self._round_started = True
-        return r.as_dict()
+        return r
 
-    def mg_rank_sort(self, lens_ptr, freqs_ptr, cells_ptr, d, n_cells, rank_id, n_ranks):
-        info = np.zeros(5, np.uint64)
-        self._check(self._L.grlgpu_mg_rank_sort(self._h, C.c_void_p(lens_ptr), C.c_void_p(freqs_ptr), C.c_void_p(cells_ptr), d, n_cells, rank_id, n_ranks, _ptr(info)))
-        return [int(x) for x in info]
+    def mg_slice_info(self) -> Slice:
+        s = Slice()
+        self._check(self._L.grlgpu_mg_slice_info(self._h, C.byref(s)))
+        return s
 
-    def mg_rank_apply(self, rank_base, meta_ptr, isn_ptr, erank_ptr):
-        self._check(self._L.grlgpu_mg_rank_apply(self._h, rank_base, C.c_void_p(meta_ptr), C.c_void_p(isn_ptr), C.c_void_p(erank_ptr)))
+    def mg_slice_checksum(self):
+        out = np.zeros(4, np.uint64)
+        self._check(self._L.grlgpu_mg_slice_checksum(self._h, _ptr(out)))
+        return [int(x) for x in out]
 
-    def mg_reply(self, part_base, meta_ptr, reply_ptr):
-        self._check(self._L.grlgpu_mg_reply(self._h, part_base, C.c_void_p(meta_ptr), C.c_void_p(reply_ptr)))
+    def mg_fetch_slice(self, arena: np.ndarray | None = None, offset: int = 0, narrow_len: bool = False, async_: bool = False):
+        """this rank's part of the last level -> dict of numpy arrays (carved from `arena`, e.g. pinned memory, when given)"""
+        sl = self.mg_slice_info()
+        st = np.uint32 if sl.sym_bytes == 4 else np.uint64
+        sizes = [(sl.tot_local, st), (sl.tot_local, st), (sl.tot_local, np.uint8), (sl.n_pre_local, st), (sl.n_pre_local, np.uint32 if narrow_len else np.uint64)]
+        if arena is None:
+            arrs = [np.zeros(n, dt) for n, dt in sizes]
+        else:
+            arrs, off = [], int(offset)
+            for n, dt in sizes:
+                nb = n * np.dtype(dt).itemsize
+                off = (off + 15) & ~15
+                if off + nb > arena.size:
+                    raise GrlGpuError(-1, "fetch arena too small")
+                arrs.append(arena[off:off + nb].view(dt))
+                off += nb
+            self.arena_end = (off + 15) & ~15
+        rl, rr, hh, ps, pl = arrs
+        self._check(self._L.grlgpu_mg_fetch_slice(self._h, _ptr(rl), _ptr(rr), _ptr(hh), _ptr(ps), _ptr(pl), 4 if narrow_len else 8, int(async_)))
+        return {"rule_l": rl, "rule_r": rr, "has_hocc": hh, "pre_sym": ps, "pre_len": pl, "rank_base": sl.rank_base, "pre_first": sl.pre_first}
 
-    def mg_rank_finish(self, rank_base, tot, n_pre, meta_ptr, isn_ptr, erank_ptr, done, local_meta_ptr=None):
-        r = Round()
-        self._check(self._L.grlgpu_mg_rank_finish(self._h, rank_base, tot, n_pre, C.c_void_p(meta_ptr), C.c_void_p(isn_ptr), C.c_void_p(erank_ptr),
-                                                  C.c_void_p(local_meta_ptr) if local_meta_ptr else None, int(done), C.byref(r)))
-        self.last = r
-        self._round_started = True
-        return r.as_dict()
-
-    def mg_level_slice(self, rl_ptr, rr_ptr, hh_ptr, ps_ptr, pl_ptr):
-        self._check(self._L.grlgpu_mg_level_slice(self._h, C.c_void_p(rl_ptr), C.c_void_p(rr_ptr), C.c_void_p(hh_ptr), C.c_void_p(ps_ptr), C.c_void_p(pl_ptr)))
+    def fetch_parse_local(self, n_cells: int, arena: np.ndarray | None = None) -> np.ndarray:
+        """multi-GPU: this rank's part of the current parse (parse_len_local cells of grlgpu_slice_t)"""
+        r = self.last
+        out = np.zeros(n_cells, CELL[r.cell_bytes_out]) if arena is None else arena[: n_cells * r.cell_bytes_out].view(CELL[r.cell_bytes_out])
+        self._check(self._L.grlgpu_fetch_parse(self._h, _ptr(out)))
+        return out
 
     def profile_enable(self, on: bool = True):
         self._check(self._L.grlgpu_profile_enable(self._h, int(on)))

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) dict_gather_kernel(const CellT* __restric
         D[e] = (SymT)v;
         if (phr_of) phr_of[e] = (u32)(i - lane + q);
         rem[e] = r;
-        einfo[e] = make_ulonglong2(left, qfreq | (valid ? EI_VALID : 0ULL) | (k == 0 ? EI_FULL : 0ULL));
+        if (einfo) einfo[e] = make_ulonglong2(left, qfreq | (valid ? EI_VALID : 0ULL) | (k == 0 ? EI_FULL : 0ULL));
         if (ph_voff && valid) {
             u64 key = v + 1;
             for (int t = 1; t <= K; t++) {  // t == K: the bits that are left take the TOP `spare` bits of the next code (order-preserving)

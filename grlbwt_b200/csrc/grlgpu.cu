@@ -5,6 +5,7 @@
 #include "primitives.cuh"
 #include "parse_kernels.cuh"
 #include "dict_kernels.cuh"
+#include "comm.hpp"
 
 #include <algorithm>
 #include <cstring>
@@ -14,10 +15,19 @@
 using namespace grl;
 
 
-namespace { struct MgRound; }
+// level slices of the last multi-GPU round (owned by the context until the next round / fetch)
+struct Mg2Slices {
+    int sym_bytes = 4;
+    u64 rank_base = 0, tot_local = 0, tot = 0;
+    u64 pre_drop = 0, n_pre_local = 0, pre_first = 0, n_pre_global = 0;  // runs [pre_drop, pre_drop + n_pre_local) of pre_* are this rank's
+    DevBuf<u8> rule_l, rule_r, has_hocc, pre_sym;
+    DevBuf<u64> pre_len;
+    bool valid = false;
+};
 
 struct grlgpu_ctx {
     int device = 0;
+    int n_sm = 148;
     u64 flags = 0;
     cudaStream_t st = nullptr;
     bool own_stream = true;
@@ -56,9 +66,17 @@ struct grlgpu_ctx {
     std::vector<DevBuf<u64>> parked_u64;
     std::vector<DevBuf<u32>> parked_u32;
 
-    // multi-GPU round in flight (between grlgpu_mg_local and grlgpu_mg_global)
-    MgRound* mg = nullptr;
-    int mg_ranks = 0;
+    // streaming ingest (grlgpu_text_begin / _stage / _commit / _end): two pinned staging buffers, H2D on the copy stream
+    u8* stage_buf[2] = {nullptr, nullptr};
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    u64 stage_cap = 0, ingest_off = 0, ingest_bytes = 0;
+    int stage_cur = 0;
+    bool ingesting = false;
+
+    // multi-GPU rounds (mg2.cuh): global string count, this rank's slices of the last level, bytes it sent in the last round
+    u64 mg_n_strings = 0;
+    Mg2Slices mg_sl;
+    u64 mg_exchange_bytes = 0, mg_parse_len_local = 0, mg_n_in_local = 0;
 
     // optional: dictionary of the last round kept for tests (GRLGPU_FLAG_KEEP_DICT)
     u64 kd_d = 0, kd_nE = 0, kd_nS = 0;
@@ -234,12 +252,10 @@ void stage_dedup(Round& R) {
     GRL_LAUNCH("tile_popc", R.n / 8, tile_popc_kernel, (unsigned)n_tiles, 256, 0, R.st, R.start_bits.p, n_words, TW, tile_cnt.p);
     exclusive_scan<u32, u64>(tile_cnt.p, tile_base.p, n_tiles, ptot.p, R.st);
     R.p = d2h_scalar(ptot.p, R.st);
-    static int n_sm = 0;  // one per CellT instantiation
-    if (!n_sm) {
-        GRL_CUDA(cudaFuncSetAttribute(dedup_cached_kernel<CellT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fd_smem_bytes<CellT>()));
-        GRL_CUDA(cudaFuncSetAttribute(dedup_cached_kernel<CellT>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        GRL_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device));
-    }
+    // function attributes are per device: set them for the current one on every call (a few microseconds), never cached process-wide
+    GRL_CUDA(cudaFuncSetAttribute(dedup_cached_kernel<CellT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fd_smem_bytes<CellT>()));
+    GRL_CUDA(cudaFuncSetAttribute(dedup_cached_kernel<CellT>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    const int n_sm = c->n_sm;
     const unsigned fd_grid = (unsigned)std::min<u64>(n_tiles, (u64)n_sm * FD_CTAS_PER_SM);  // persistent CTAs, tiles strided
     // the first tiles always run through the cached kernel and report how many phrases missed the caches;
     // the rest of the text takes the cached kernel (duplicate-heavy) or the thread-per-phrase kernel (unique-heavy)
@@ -318,7 +334,8 @@ void stage_dedup(Round& R) {
             }
         }
         if (cap >= cap_max) throw Error(GRLGPU_ERR_LIMIT, "phrase table would exceed 2^31 slots");
-        cap = std::min<u64>(cap * 8, std::min<u64>(want, cap_max));  // too full: regrow and redo the pass
+        const u64 grown = std::min<u64>(cap * 8, std::min<u64>(want, cap_max));  // too full: regrow and redo the pass
+        cap = grown > cap ? grown : std::min<u64>(cap * 2, cap_max);              // (a probe-limit overflow at cap == want still has to grow)
     }
     ps_raw.release();
     R.ph_pos.alloc(R.d, R.st);
@@ -689,412 +706,7 @@ void run_round_t(grlgpu_ctx* c, grlgpu_round_t* out) {
     finish_round(c, R, R.tot, R.n_pre, R.d, R.nE, R.max_freq, tm, &t_all, out);
 }
 
-// ---------------- multi-GPU round: the caller owns the exchange between the calls ----------------
-struct MgRound {
-    Round R;                        // this rank's shard
-    DevBuf<u32> perm;               // local distinct phrases ordered by owner
-    DevBuf<u64> offs;               // cell offset of each packed phrase (+ total)
-    // owner side: dedup of what the other ranks sent
-    DevBuf<ulonglong2> ptable;
-    DevBuf<u32> pslots, p_len;
-    DevBuf<u64> p_pos, p_freq, p_offs;
-    DevBuf<u32> recv_dense;         // partition-local index of every phrase this rank received as an owner (for the metasymbol return)
-    u64 m_recv = 0;
-    u64 d_part = 0, cells_part = 0;
-    const void* recv_cells = nullptr;
-    Timer t_text, t_dict;
-    float ms_text = 0;
-    // distributed ranking: this rank's slice of the suffix order of the GLOBAL dictionary and its group results
-    std::unique_ptr<Round> GR;      // the global dictionary
-    DevBuf<u64> g_meta;
-    const void* g_cells = nullptr;
-    u64 nL = 0, G = 0, tot_local = 0, n_pre_local = 0;
-    int sym_bytes = 4;
-    DevBuf<u32> order, head_bits, head_pref, gcnt, grep, rflag, rrank;
-    DevBuf<u64> gfull;
-    DevBuf<u8> sl_rule_l, sl_rule_r, sl_has_hocc, sl_pre_sym;  // this rank's slice of the level artefacts
-    DevBuf<u64> sl_pre_len;
-    explicit MgRound(grlgpu_ctx* c) : R(c), t_text(c->st), t_dict(c->st) {}
-};
-
-template <class CellT, bool FIRST>
-void mg_local_t(grlgpu_ctx* c, int G, grlgpu_part_t* per_owner, u64* parse_len_local) {
-    delete c->mg;
-    c->mg = nullptr;
-    c->mg = new MgRound(c);
-    c->mg_ranks = G;
-    MgRound& M = *c->mg;
-    Round& R = M.R;
-    M.t_text.start();
-    stage_flags<CellT, FIRST>(R);
-    stage_dedup<CellT>(R);
-    // owner of every local distinct phrase = content hash % G; order the phrases by owner
-    DevBuf<u64> keys(R.d, R.st), keys_alt(R.d, R.st);
-    DevBuf<u32> vals(R.d, R.st), vals_alt(R.d, R.st);
-    GRL_LAUNCH("phrase_owner", 0, (phrase_owner_kernel<CellT>), grid_for(R.d, 256), 256, 0, R.st, (const CellT*)c->text, R.ph_pos.p, R.ph_len.p, R.d, (u32)G, keys.p, vals.p);
-    u64 *kp = keys.p, *ka = keys_alt.p;
-    u32 *vp = vals.p, *va = vals_alt.p;
-    radix_sort_pairs(&kp, &vp, &ka, &va, R.d, std::max(1, bit_width64((u64)G - 1)), R.st);
-    if (vp != vals.p) std::swap(vals, vals_alt);
-    M.perm = std::move(vals);
-    DevBuf<u32> lens_sorted(R.d, R.st);
-    GRL_LAUNCH("gather_u32", 0, gather_u32_kernel, grid_for(R.d, 256), 256, 0, R.st, R.ph_len.p, M.perm.p, R.d, lens_sorted.p);
-    M.offs.alloc(R.d + 1, R.st);
-    exclusive_scan<u32, u64>(lens_sorted.p, M.offs.p, R.d, M.offs.p + R.d, R.st);
-    DevBuf<u64> first(G + 1, R.st);
-    GRL_LAUNCH("owner_bounds", 0, owner_bounds_kernel, 1, 32, 0, R.st, kp, R.d, (u32)G, first.p);
-    std::vector<u64> hf(G + 1), ho(G + 1);
-    GRL_CUDA(cudaMemcpyAsync(hf.data(), first.p, (G + 1) * 8, cudaMemcpyDeviceToHost, R.st));
-    GRL_CUDA(cudaStreamSynchronize(R.st));
-    for (int g = 0; g <= G; g++) ho[g] = d2h_scalar(M.offs.p + hf[g], R.st);
-    for (int g = 0; g < G; g++) { per_owner[g].n_phrases = hf[g + 1] - hf[g]; per_owner[g].n_cells = ho[g + 1] - ho[g]; }
-    *parse_len_local = R.p;
-    M.t_text.stop();
-    M.ms_text = M.t_text.ms();
-}
-
-template <class CellT>
-void mg_pack_t(grlgpu_ctx* c, u32* d_lens, u64* d_counts, void* d_cells) {
-    MgRound& M = *c->mg;
-    Round& R = M.R;
-    GRL_LAUNCH("pack_phrases", 0, (pack_phrases_kernel<CellT>), grid_for(R.d, 256), 256, 0, R.st, (const CellT*)c->text, R.ph_pos.p, R.ph_len.p, R.ph_freq.p, M.perm.p, M.offs.p, R.d, d_lens, d_counts, (CellT*)d_cells);
-    GRL_CUDA(cudaStreamSynchronize(R.st));
-}
-
-template <class CellT>
-void mg_merge_t(grlgpu_ctx* c, const u32* lens, const u64* counts, const void* cells, u64 m, u64 n_cells, grlgpu_part_t* part) {
-    MgRound& M = *c->mg;
-    cudaStream_t st = c->st;
-    M.recv_cells = cells;
-    DevBuf<u64> offs(m + 1, st);
-    exclusive_scan<u32, u64>(lens, offs.p, m, offs.p + m, st);
-    {   // the pack tables cannot tell apart lengths >= 2^24-1 (no bitmap to consult)
-        DevBuf<u64> len64(m, st), mx(1, st);
-        mx.zero();
-        GRL_LAUNCH("u32_to_u64", 0, u32_to_u64_kernel, grid_for(m, 256), 256, 0, st, lens, m, len64.p);
-        GRL_LAUNCH("reduce_max_u64", 0, reduce_max_u64_kernel, 296, 256, 0, st, len64.p, m, mx.p);
-        if (d2h_scalar(mx.p, st) >= HT_LEN_SAT) throw Error(GRLGPU_ERR_LIMIT, "multi-GPU rounds support phrases shorter than 2^24-1 cells");
-        if (d2h_scalar(offs.p + m, st) != n_cells) throw Error(GRLGPU_ERR_ARG, "received cell count does not match the received lengths");
-    }
-    const u64 cap = std::max<u64>(1024, (m + m / 2 + m / 10 + 255) / 256 * 256);
-    if (cap > (1ull << 31) - 256) throw Error(GRLGPU_ERR_LIMIT, "phrase table would exceed 2^31 slots");
-    M.ptable.alloc(cap, st);
-    GRL_LAUNCH("table_init", cap * 16, table_init_kernel, grid_for(cap, 256), 256, 0, st, M.ptable.p, cap);
-    DevBuf<u32> overflow(1, st);
-    overflow.zero();
-    DevBuf<u32> recv_slot(m, st);
-    GRL_LAUNCH("pack_insert", 0, (pack_insert_kernel<CellT>), grid_for(m, 256), 256, 0, st, (const CellT*)cells, offs.p, lens, counts, m, M.ptable.p, cap, overflow.p, recv_slot.p);
-    if (d2h_scalar(overflow.p, st)) throw Error(GRLGPU_ERR_STATE, "partition table overflow");
-    DevBuf<u32> occ_bits(cap / 32, st);
-    GRL_LAUNCH("table_occupancy", cap * 16, table_occupancy_kernel, (unsigned)(cap / 256), 256, 0, st, M.ptable.p, cap, occ_bits.p);
-    BitmapCompactor oc;
-    M.d_part = oc.count(occ_bits.p, cap, st);
-    M.pslots.alloc(M.d_part, st);
-    oc.write<u32>(nullptr, M.pslots.p);
-    M.p_pos.alloc(M.d_part, st);
-    M.p_len.alloc(M.d_part, st);
-    M.p_freq.alloc(M.d_part, st);
-    GRL_LAUNCH("dict_meta", 0, dict_meta_kernel, grid_for(M.d_part, 256), 256, 0, st, M.ptable.p, M.pslots.p, M.d_part, (const u32*)nullptr, (const u32*)nullptr, (u64)0, M.p_pos.p, M.p_len.p, M.p_freq.p);
-    M.p_offs.alloc(M.d_part + 1, st);
-    exclusive_scan<u32, u64>(M.p_len.p, M.p_offs.p, M.d_part, M.p_offs.p + M.d_part, st);
-    M.cells_part = d2h_scalar(M.p_offs.p + M.d_part, st);
-    // the frequencies have been read: the count field now holds the slot's dense index, which every received phrase inherits
-    M.m_recv = m;
-    M.recv_dense.alloc(m, st);
-    GRL_LAUNCH("slot_dense", 0, slot_dense_kernel, grid_for(M.d_part, 256), 256, 0, st, M.pslots.p, M.d_part, M.ptable.p);
-    GRL_LAUNCH("recv_dense", 0, recv_dense_kernel, grid_for(m, 256), 256, 0, st, recv_slot.p, m, M.ptable.p, M.recv_dense.p);
-    part->n_phrases = M.d_part;
-    part->n_cells = M.cells_part;
-}
-
-template <class CellT>
-void mg_pack_part_t(grlgpu_ctx* c, u32* d_lens, u64* d_freqs, void* d_cells) {
-    MgRound& M = *c->mg;
-    GRL_LAUNCH("pack_phrases", 0, (pack_phrases_kernel<CellT>), grid_for(M.d_part, 256), 256, 0, c->st, (const CellT*)M.recv_cells, M.p_pos.p, M.p_len.p, M.p_freq.p, (const u32*)nullptr, M.p_offs.p, M.d_part, d_lens, d_freqs, (CellT*)d_cells);
-    GRL_CUDA(cudaStreamSynchronize(c->st));
-    M.ptable.release(); M.pslots.release(); M.p_pos.release(); M.p_len.release(); M.p_freq.release(); M.p_offs.release();
-}
-
-template <class CellT, bool FIRST>
-void mg_global_t(grlgpu_ctx* c, const u32* lens, const u64* freqs, const void* cells, u64 d, u64 n_cells, int done_global, grlgpu_round_t* out);
-
-// global dictionary as a Round: "text" = the gathered cells (shared by the replicated and the distributed ranking)
-void mg_setup_global(grlgpu_ctx* c, Round& GR, const u32* lens, const u64* freqs, const void* cells, u64 d, u64 n_cells) {
-    cudaStream_t st = c->st;
-    GR.dict_text = cells;
-    GR.d = d;
-    GR.ph_len.alloc(d, st);
-    GR.ph_freq.alloc(d, st);
-    GR.ph_pos.alloc(d + 1, st);
-    GRL_CUDA(cudaMemcpyAsync(GR.ph_len.p, lens, d * 4, cudaMemcpyDeviceToDevice, st));
-    GRL_CUDA(cudaMemcpyAsync(GR.ph_freq.p, freqs, d * 8, cudaMemcpyDeviceToDevice, st));
-    exclusive_scan<u32, u64>(GR.ph_len.p, GR.ph_pos.p, d, GR.ph_pos.p + d, st);
-    if (d2h_scalar(GR.ph_pos.p + d, st) != n_cells) throw Error(GRLGPU_ERR_ARG, "gathered cell count does not match the gathered lengths");
-    dict_offsets(GR);
-}
-
-// content -> global phrase index table, metasymbol of every local distinct phrase, rewrite of the shard
-template <class CellT>
-void mg_map_and_rewrite(grlgpu_ctx* c, MgRound& M, Round& GR, const void* cells, const u64* g_meta, u64 tot, u64 n_pre, int done_global, grlgpu_round_t* out,
-                        const u64* local_meta = nullptr) {
-    Round& R = M.R;
-    cudaStream_t st = c->st;
-    const u64 d = GR.d;
-    if (local_meta) {  // the owners returned the metasymbols in pack order: no global table, no content lookups
-        GRL_LAUNCH("apply_reply", R.d * 24, apply_reply_kernel, grid_for(R.d, 256), 256, 0, st, M.perm.p, R.occ_slots.p, local_meta, R.d, R.table.p);
-        M.t_dict.stop();
-        RoundTimes tm;
-        tm.text = M.ms_text;
-        tm.dict = M.t_dict.ms();
-        tm.all = tm.text + tm.dict;
-        finish_round(c, R, tot, n_pre, GR.d, GR.nE, GR.max_freq, tm, nullptr, out);
-        out->done = done_global ? 1u : 0u;
-        c->done = done_global != 0;
-        return;
-    }
-    const u64 gcap = std::max<u64>(1024, (d + d / 2 + d / 10 + 255) / 256 * 256);
-    if (gcap > (1ull << 31) - 256) throw Error(GRLGPU_ERR_LIMIT, "phrase table would exceed 2^31 slots");
-    DevBuf<ulonglong2> gtable(gcap, st);
-    GRL_LAUNCH("table_init", gcap * 16, table_init_kernel, grid_for(gcap, 256), 256, 0, st, gtable.p, gcap);
-    DevBuf<u32> flag(2, st);
-    flag.zero();
-    GRL_LAUNCH("pack_insert", 0, (pack_insert_kernel<CellT>), grid_for(d, 256), 256, 0, st, (const CellT*)cells, GR.ph_pos.p, GR.ph_len.p, (const u64*)nullptr, d, gtable.p, gcap, flag.p, (u32*)nullptr);
-    GRL_LAUNCH("map_local", 0, (map_local_kernel<CellT>), grid_for(R.d, 256), 256, 0, st, (const CellT*)c->text, R.ph_pos.p, R.ph_len.p, R.occ_slots.p, R.d, (const CellT*)cells, gtable.p, gcap, g_meta, R.table.p, flag.p + 1);
-    u32 hflag[2];
-    d2h_small(hflag, flag.p, 8, st);
-    if (hflag[0]) throw Error(GRLGPU_ERR_STATE, "global table overflow");
-    if (hflag[1]) throw Error(GRLGPU_ERR_STATE, "a local phrase is missing from the global dictionary");
-    M.t_dict.stop();
-    RoundTimes tm;
-    tm.text = M.ms_text;
-    tm.dict = M.t_dict.ms();
-    tm.all = tm.text + tm.dict;
-    finish_round(c, R, tot, n_pre, GR.d, GR.nE, GR.max_freq, tm, nullptr, out);
-    out->done = done_global ? 1u : 0u;  // the phase ends when EVERY rank's strings are single cells
-    c->done = done_global != 0;
-}
-
-// Distributed ranking, step 1: this rank sorts and groups the suffix entries whose first key falls in its range.
-// info[0] = 1 if the distributed path was taken (0: nothing was done, call grlgpu_mg_global), info[1] = ranked groups
-// of this rank, info[2] = preliminary-BWT runs of this rank, info[3] = dictionary entries nE, info[4] = symbol bytes.
-template <class CellT, bool FIRST, class SymT>
-void mg_rank_sort_sym(grlgpu_ctx* c, const u32* lens, const u64* freqs, const void* cells, u64 d, u64 n_cells, int rank_id, int n_ranks, u64* info) {
-    MgRound& M = *c->mg;
-    cudaStream_t st = c->st;
-    Round& GR = *M.GR;
-    const u64 nE = GR.nE, A = c->alphabet;
-    stage_gather<CellT, FIRST, SymT>(GR, true);  // first keys + entry ids of the valid entries come with it
-    const SymT* D = (const SymT*)GR.D_raw.p;
-    const int sym_bits = GR.sym_bits, K = GR.K;
-    const int key_bits = std::min(64, sym_bits * K), first_bits = std::min(64, sym_bits * K + GR.spare);
-    const u64 nS = GR.nS;
-    M.sym_bytes = sizeof(SymT);
-    // splitters from a regular sample of the first keys, identical on every rank
-    DevBuf<u64> keys = std::move(GR.keys);
-    DevBuf<u32> ids = std::move(GR.vals);
-    u64 lo = 0, hi = 0;
-    int hi_open = 1;
-    if (nS) {
-        const u64 ns = std::min<u64>(nS, 1ull << 16), stride = std::max<u64>(1, nS / ns);
-        DevBuf<u64> sk(ns, st), sk2(ns, st);
-        DevBuf<u32> sv(ns, st), sv2(ns, st);
-        GRL_LAUNCH("key_sample", 0, key_sample_kernel, grid_for(ns, 256), 256, 0, st, keys.p, nS, stride, ns, sk.p, sv.p);
-        u64 *a = sk.p, *b = sk2.p;
-        u32 *av = sv.p, *bv = sv2.p;
-        radix_sort_pairs(&a, &av, &b, &bv, ns, first_bits, st);
-        std::vector<u64> hs(ns);
-        GRL_CUDA(cudaMemcpyAsync(hs.data(), a, ns * 8, cudaMemcpyDeviceToHost, st));
-        GRL_CUDA(cudaStreamSynchronize(st));
-        auto splitter = [&](int r) { return hs[(size_t)((u64)r * ns / (u64)n_ranks)]; };
-        lo = rank_id == 0 ? 0 : splitter(rank_id);
-        if (rank_id + 1 < n_ranks) { hi = splitter(rank_id + 1); hi_open = 0; }
-    }
-    // my entries
-    DevBuf<u64> mk, mk_alt;
-    DevBuf<u32> mv, mv_alt;
-    u64 nL = 0;
-    {
-        DevBuf<u32> flags(nS, st), excl(nS, st), cnt(1, st);
-        GRL_LAUNCH("key_range_flags", nS * 12, key_range_flags_kernel, grid_for(nS, 256), 256, 0, st, keys.p, nS, lo, hi, hi_open, flags.p);
-        exclusive_scan<u32, u32>(flags.p, excl.p, nS, cnt.p, st);
-        nL = nS ? d2h_scalar(cnt.p, st) : 0;
-        mk.alloc(nL, st); mk_alt.alloc(nL, st); mv.alloc(nL, st); mv_alt.alloc(nL, st);
-        GRL_LAUNCH("key_range_compact", nS * 20, key_range_compact_kernel, grid_for(nS, 256), 256, 0, st, keys.p, ids.p, flags.p, excl.p, nS, mk.p, mv.p);
-    }
-    keys.release(); ids.release();
-    M.nL = nL;
-    const u64 n_words = div_up(std::max<u64>(nL, 1), 32);
-    M.head_bits.alloc(n_words, st);
-    M.head_bits.zero();
-    u64 *kp = mk.p, *ka = mk_alt.p;
-    u32 *vp = mv.p, *va = mv_alt.p;
-    radix_sort_pairs(&kp, &vp, &ka, &va, nL, first_bits, st);
-    if (vp != mv.p) std::swap(mv, mv_alt);
-    M.order = std::move(mv);
-    mv_alt.release();
-    u32* order_w = M.order.p;
-    u64 nA = 0;
-    DevBuf<u32> apos;
-    if (nL) {
-        DevBuf<u32> flags(nL, st), active_bits(n_words, st);
-        GRL_LAUNCH("first_heads", nL * 12, first_heads_kernel, grid_for(nL, 256), 256, 0, st, kp, nL, sym_bits, GR.spare, A + 1, flags.p, M.head_bits.p, active_bits.p);
-        BitmapCompactor ac;
-        nA = ac.count(active_bits.p, nL, st);
-        apos.alloc(nA, st);
-        if (nA) ac.write<u32>(nullptr, apos.p);
-    }
-    mk.release(); mk_alt.release();
-    u64 dpt = (u64)K;
-    while (nA > 0) {  // refinement by key extension: local to the dictionary text, no exchange needed
-        if (dpt > GR.max_len + 1) throw Error(GRLGPU_ERR_STATE, "suffix refinement did not converge");
-        DevBuf<u64> ak(nA, st), ak_alt(nA, st), nk(nA, st);
-        DevBuf<u32> av(nA, st), av_alt(nA, st), ev(nA, st), gflag(nA, st), gexcl(nA, st), flags(nA, st), excl(nA, st), cnt(1, st);
-        u64 *akp = ak.p, *aka = ak_alt.p;
-        u32 *avp = av.p, *ava = av_alt.p;
-        GRL_LAUNCH("ext_keys", nA * 48, (ext_keys_kernel<SymT>), grid_for(nA, 256), 256, 0, st, apos.p, order_w, D, GR.rem.p, M.head_bits.p, nA, dpt, A + 1, sym_bits, K, akp, avp,
-                   nk.p, ev.p, gflag.p);
-        exclusive_scan<u32, u32>(gflag.p, gexcl.p, nA, cnt.p, st);
-        const u64 n_groups = d2h_scalar(cnt.p, st);
-        radix_sort_pairs(&akp, &avp, &aka, &ava, nA, key_bits, st);
-        GRL_LAUNCH("ext_gid", nA * 12, ext_gid_kernel, grid_for(nA, 256), 256, 0, st, gflag.p, gexcl.p, nA);
-        GRL_LAUNCH("ext_group_keys", nA * 16, ext_group_keys_kernel, grid_for(nA, 256), 256, 0, st, avp, gexcl.p, nA, akp);
-        radix_sort_pairs(&akp, &avp, &aka, &ava, nA, std::max(1, bit_width64(n_groups)), st);
-        GRL_LAUNCH("ext_heads", nA * 24, ext_heads_kernel, grid_for(nA, 256), 256, 0, st, avp, akp, nk.p, nA, flags.p);
-        GRL_LAUNCH("ext_writeback", nA * 16, ext_writeback_kernel, grid_for(nA, 256), 256, 0, st, apos.p, avp, ev.p, flags.p, nA, order_w, M.head_bits.p);
-        dpt += (u64)K;
-        GRL_LAUNCH("ext_next", nA * 16, ext_next_kernel, grid_for(nA, 256), 256, 0, st, apos.p, avp, ev.p, M.head_bits.p, GR.rem.p, nA, nL, dpt, flags.p);
-        exclusive_scan<u32, u32>(flags.p, excl.p, nA, cnt.p, st);
-        const u64 nA2 = d2h_scalar(cnt.p, st);
-        DevBuf<u32> apos2(nA2, st);
-        if (nA2) GRL_LAUNCH("compact_apos", nA * 12, compact_apos_kernel, grid_for(nA, 256), 256, 0, st, flags.p, excl.p, apos.p, nA, apos2.p);
-        apos = std::move(apos2);
-        nA = nA2;
-    }
-    // groups of my slice
-    M.head_pref.alloc(n_words, st);
-    u64 G = 0;
-    {
-        DevBuf<u32> wc(n_words, st), gtot(1, st);
-        GRL_LAUNCH("popc_words", n_words * 8, popc_words_kernel, grid_for(n_words, 256), 256, 0, st, M.head_bits.p, n_words, wc.p);
-        exclusive_scan<u32, u32>(wc.p, M.head_pref.p, n_words, gtot.p, st);
-        G = nL ? d2h_scalar(gtot.p, st) : 0;
-    }
-    M.G = G;
-    M.gcnt.alloc(G, st); M.grep.alloc(G, st); M.rflag.alloc(G, st); M.rrank.alloc(G, st);
-    M.gfull.alloc(G, st);
-    DevBuf<u32> ghead(G, st), vflag(G, st), vidx(G, st);
-    DevBuf<u64> gacc(G, st), gmin(G, st), gmax(G, st), psym(G, st);
-    M.gcnt.zero(); gacc.zero(); gmax.zero(); gmin.fill_ff();
-    GRL_LAUNCH("group_reduce", nL * 24 + G * 32, group_reduce_kernel, grid_for(nL, 256), 256, 0, st, M.order.p, M.head_bits.p, M.head_pref.p, GR.einfo.p, nL, M.gcnt.p, gacc.p, gmin.p,
-               gmax.p, M.grep.p, ghead.p, M.gfull.p);
-    GR.einfo.release();
-    const u64 bwt_dummy = A + 1, hocc_dummy = A + 2;
-    GRL_LAUNCH("group_finalize", 0, group_finalize_kernel, grid_for(G, 256), 256, 0, st, M.gcnt.p, gmin.p, gmax.p, G, bwt_dummy, hocc_dummy, M.rflag.p, vflag.p, psym.p);
-    DevBuf<u32> cnt2(2, st);
-    exclusive_scan<u32, u32>(M.rflag.p, M.rrank.p, G, cnt2.p, st);
-    exclusive_scan<u32, u32>(vflag.p, vidx.p, G, cnt2.p + 1, st);
-    u32 hc[2];
-    d2h_small(hc, cnt2.p, 8, st);
-    M.tot_local = hc[0];
-    const u64 nV = hc[1];
-    {   // preliminary BWT of my slice: maximal runs over my valid groups (the caller merges across rank boundaries)
-        DevBuf<u64> csym(nV, st), clen(nV, st);
-        GRL_LAUNCH("prebwt_compact", 0, prebwt_compact_kernel, grid_for(G, 256), 256, 0, st, vflag.p, vidx.p, psym.p, gacc.p, G, csym.p, clen.p);
-        DevBuf<u32> hflag(nV, st), hexcl(nV, st), nrun(1, st);
-        GRL_LAUNCH("key_head_flags", 0, key_head_flags_kernel, grid_for(nV, 256), 256, 0, st, csym.p, nV, hflag.p);
-        exclusive_scan<u32, u32>(hflag.p, hexcl.p, nV, nrun.p, st);
-        M.n_pre_local = nV ? d2h_scalar(nrun.p, st) : 0;
-        M.sl_pre_sym.alloc(M.n_pre_local * sizeof(SymT), st);
-        M.sl_pre_len.alloc(M.n_pre_local, st);
-        M.sl_pre_len.zero();
-        GRL_LAUNCH("prebwt_runs", 0, (prebwt_runs_kernel<SymT>), grid_for(nV, 256), 256, 0, st, csym.p, clen.p, hflag.p, hexcl.p, nV, (SymT*)M.sl_pre_sym.p, M.sl_pre_len.p);
-    }
-    GRL_CUDA(cudaStreamSynchronize(st));
-    info[0] = 1; info[1] = M.tot_local; info[2] = M.n_pre_local; info[3] = nE; info[4] = sizeof(SymT);
-}
-
-template <class CellT, bool FIRST>
-void mg_rank_sort_t(grlgpu_ctx* c, const u32* lens, const u64* freqs, const void* cells, u64 d, u64 n_cells, int rank_id, int n_ranks, u64* info) {
-    MgRound& M = *c->mg;
-    M.t_dict.start();
-    M.GR.reset(new Round(c));
-    Round& GR = *M.GR;
-    mg_setup_global(c, GR, lens, freqs, cells, d, n_cells);
-    M.g_cells = cells;
-    const int sym_bits = bit_width64(c->alphabet + 1);
-    const u64 K = (u64)std::max(1, 64 / sym_bits);
-    const bool ext_ok = (GR.max_len + 1 + K - 1) / K <= 64;
-    const bool big = GR.nE >= (1ull << 22) || (c->flags & GRLGPU_FLAG_FORCE_DIST_RANK);
-    info[0] = 0; info[1] = info[2] = 0; info[3] = GR.nE; info[4] = 4;
-    if (!ext_ok || !big || n_ranks < 2) { M.GR.reset(); return; }  // small or long-phrase dictionaries: replicated ranking
-    const bool wide = (c->alphabet + GR.nE + 8) >= (1ull << 32);
-    if (wide) mg_rank_sort_sym<CellT, FIRST, u64>(c, lens, freqs, cells, d, n_cells, rank_id, n_ranks, info);
-    else mg_rank_sort_sym<CellT, FIRST, u32>(c, lens, freqs, cells, d, n_cells, rank_id, n_ranks, info);
-}
-
-// step 2: with the global rank offset of this rank known, write my share of the global per-phrase metasymbols, of the
-// next round's is_suffix and of the hocc marks (rank + 1) into caller-owned, zero-initialised device arrays
-template <class SymT>
-void mg_rank_apply_sym(grlgpu_ctx* c, u64 rank_base, u64* g_meta, u8* is_suffix_next, u32* erank1) {
-    MgRound& M = *c->mg;
-    Round& GR = *M.GR;
-    cudaStream_t st = c->st;
-    DevBuf<u32> ginfo(M.G, st);
-    GRL_LAUNCH("full_apply", M.G * 20, full_apply_kernel, grid_for(M.G, 256), 256, 0, st, M.gcnt.p, M.rflag.p, M.rrank.p, M.gfull.p, M.G, rank_base, (ulonglong2*)nullptr, g_meta, is_suffix_next);
-    M.gfull.release();
-    GRL_LAUNCH("pack_ginfo_dense", M.G * 16, pack_ginfo_dense_kernel, grid_for(M.G, 256), 256, 0, st, M.gcnt.p, M.rflag.p, M.rrank.p, M.G, ginfo.p);
-    GRL_LAUNCH("group_apply", M.nL * 12, group_apply_kernel, grid_for(M.nL, 256), 256, 0, st, M.order.p, M.head_bits.p, M.head_pref.p, ginfo.p, M.nL, rank_base, 1u, erank1);
-    GRL_CUDA(cudaStreamSynchronize(st));
-}
-
-// step 3 (after the caller all-reduced the three arrays with MAX): rules of my ranked groups, local rewrite
-template <class CellT, class SymT>
-void mg_rank_finish_sym(grlgpu_ctx* c, u64 rank_base, u64 tot, u64 n_pre_global, const u64* g_meta, const u8* is_suffix_next, u32* erank1, int done_global, grlgpu_round_t* out,
-                        const u64* local_meta) {
-    MgRound& M = *c->mg;
-    Round& GR = *M.GR;
-    cudaStream_t st = c->st;
-    const u64 A = c->alphabet;
-    IsSuffix isuf{c->is_suffix.p, c->sep, c->first};
-    GRL_LAUNCH("erank_decode", GR.nE * 8, erank_decode_kernel, grid_for(GR.nE, 256), 256, 0, st, erank1, GR.nE);
-    M.sl_rule_l.alloc(M.tot_local * sizeof(SymT), st);
-    M.sl_rule_r.alloc(M.tot_local * sizeof(SymT), st);
-    M.sl_has_hocc.alloc(M.tot_local, st);
-    const u64 alph3 = A + 3, metasym_dummy = alph3 + tot + 1;
-    GRL_LAUNCH("rules", 0, (rules_kernel<SymT>), grid_for(M.G, 256), 256, 0, st, M.gcnt.p, M.rflag.p, M.rrank.p, M.grep.p, M.G, (const SymT*)GR.D_raw.p, GR.rem.p, erank1, isuf, alph3,
-               metasym_dummy, (SymT*)M.sl_rule_l.p, (SymT*)M.sl_rule_r.p, M.sl_has_hocc.p);
-    (void)rank_base;
-    // the next round's is_suffix is global
-    DevBuf<u8> isn(tot, st);
-    GRL_CUDA(cudaMemcpyAsync(isn.p, is_suffix_next, tot, cudaMemcpyDeviceToDevice, st));
-    c->lvl_sym_bytes = sizeof(SymT);
-    mg_map_and_rewrite<CellT>(c, M, GR, M.g_cells, g_meta, tot, n_pre_global, done_global, out, local_meta);
-    c->is_suffix = std::move(isn);
-    c->rule_l.release(); c->rule_r.release(); c->has_hocc.release(); c->pre_sym.release(); c->pre_len.release();  // level artefacts live in slices this round
-    c->lvl_tot = 0; c->lvl_npre = 0; c->lvl_n_in = ~0ull;
-    // keep only the slices (until grlgpu_mg_level_slice / the next round)
-    M.GR.reset();
-    M.order.release(); M.head_bits.release(); M.head_pref.release(); M.gfull.release();
-    M.gcnt.release(); M.grep.release(); M.rflag.release(); M.rrank.release();
-}
-
-template <class CellT, bool FIRST>
-void mg_global_t(grlgpu_ctx* c, const u32* lens, const u64* freqs, const void* cells, u64 d, u64 n_cells, int done_global, grlgpu_round_t* out) {
-    MgRound& M = *c->mg;
-    cudaStream_t st = c->st;
-    if (!M.GR) M.t_dict.start();
-    // the global dictionary (identical on every rank), ranked here in full (replicated ranking)
-    Round GR(c);
-    mg_setup_global(c, GR, lens, freqs, cells, d, n_cells);
-    DevBuf<u64> g_meta(d, st);
-    GR.ph_meta = g_meta.p;
-    const bool wide = (c->alphabet + GR.nE + 8) >= (1ull << 32);
-    if (wide) { stage_gather<CellT, FIRST, u64>(GR); stage_dict<u64>(GR); }
-    else { stage_gather<CellT, FIRST, u32>(GR); stage_dict<u32>(GR); }
-    mg_map_and_rewrite<CellT>(c, M, GR, cells, g_meta.p, GR.tot, GR.n_pre, done_global, out);
-    delete c->mg;
-    c->mg = nullptr;
-}
+#include "mg2.cuh"
 
 void run_round(grlgpu_ctx* c, grlgpu_round_t* out) {
     if (c->first) {
@@ -1165,10 +777,49 @@ void compute_stats(grlgpu_ctx* c) {
     c->have_stats = true;
 }
 
+// order-insensitive digests of a level's artefacts: sums mod 2^64 that add up across per-rank slices of the same level
+// (rules weighted by their GLOBAL rank, preliminary-BWT runs by symbol so that a run split at a slice seam counts the same)
+template <class SymT>
+static __global__ void __launch_bounds__(256) level_checksum_kernel(const SymT* __restrict__ rule_l, const SymT* __restrict__ rule_r, const u8* __restrict__ has_hocc, u64 tot,
+                                                                    u64 rank_base, const SymT* __restrict__ pre_sym, const u64* __restrict__ pre_len, u64 n_pre, u64* acc) {
+    u64 a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (u64)gridDim.x * blockDim.x) {
+        const u64 u = rank_base + i + 1;
+        a0 += u * (((u64)rule_l[i] * 0x9E3779B97F4A7C15ULL) ^ ((u64)rule_r[i] * 0xC2B2AE3D27D4EB4FULL));
+        a1 += u * (u64)has_hocc[i];
+    }
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_pre; i += (u64)gridDim.x * blockDim.x) {
+        a2 += pre_len[i];
+        a3 += ((u64)pre_sym[i] * 0x9E3779B97F4A7C15ULL + 1) * pre_len[i];
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+    if (lane_id() == 0) { atomicAdd(&acc[0], a0); atomicAdd(&acc[1], a1); atomicAdd(&acc[2], a2); atomicAdd(&acc[3], a3); }
+}
+inline void level_checksum(cudaStream_t st, int sym_bytes, const void* rl, const void* rr, const u8* hh, u64 tot, u64 rank_base, const void* ps, const u64* pl, u64 n_pre,
+                           u64* host_out4) {
+    DevBuf<u64> acc(4, st);
+    acc.zero();
+    if (sym_bytes == 8) GRL_LAUNCH("level_checksum", 0, (level_checksum_kernel<u64>), 296, 256, 0, st, (const u64*)rl, (const u64*)rr, hh, tot, rank_base, (const u64*)ps, pl, n_pre, acc.p);
+    else GRL_LAUNCH("level_checksum", 0, (level_checksum_kernel<u32>), 296, 256, 0, st, (const u32*)rl, (const u32*)rr, hh, tot, rank_base, (const u32*)ps, pl, n_pre, acc.p);
+    d2h_small(host_out4, acc.p, 32, st);
+}
+
+inline void ensure_stats(grlgpu_ctx* ctx) {
+    if (ctx->have_stats) return;
+    switch (ctx->w) {
+        case 1: compute_stats<u8>(ctx); break;
+        case 2: compute_stats<u16>(ctx); break;
+        case 4: compute_stats<u32>(ctx); break;
+        default: compute_stats<u64>(ctx); break;
+    }
+}
+
 template <class F>
 int guarded(grlgpu_ctx* c, F&& f) {
     struct CtxGuard {  // per-call binding of the context's launch accounting and memory pool
-        explicit CtxGuard(grlgpu_ctx* x) { g_prof = x ? &x->prof : nullptr; g_pool = x ? &x->pool : nullptr; }
+        // GRLGPU_NO_POOL=1 (compute-sanitizer runs): every buffer is its own cudaMalloc, so memcheck sees the true bounds
+        explicit CtxGuard(grlgpu_ctx* x) { g_prof = x ? &x->prof : nullptr; g_pool = (x && !no_pool()) ? &x->pool : nullptr; }
+        static bool no_pool() { static const bool v = getenv("GRLGPU_NO_POOL") != nullptr; return v; }
         ~CtxGuard() { g_prof = nullptr; g_pool = nullptr; }
     } cg(c);
     try {
@@ -1188,6 +839,12 @@ int guarded(grlgpu_ctx* c, F&& f) {
 
 }  // namespace
 
+struct grlgpu_comm { std::unique_ptr<grl::Comm> c; };
+struct grlgpu_local_group {
+    grl::LocalGroup g;
+    explicit grlgpu_local_group(int w) : g(w) {}
+};
+
 extern "C" {
 
 int grlgpu_create_on_stream(grlgpu_ctx** ctx, int device, uint64_t flags, void* cuda_stream);
@@ -1203,6 +860,7 @@ int grlgpu_create_on_stream(grlgpu_ctx** ctx, int device, uint64_t flags, void* 
     c->flags = flags;
     int rc = guarded(c.get(), [&] {
         c->pool.init(device);
+        GRL_CUDA(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device));
         if (cuda_stream) { c->st = (cudaStream_t)cuda_stream; c->own_stream = false; }
         else GRL_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     });
@@ -1218,9 +876,11 @@ int grlgpu_destroy(grlgpu_ctx* ctx) {
     cudaStream_t st = ctx->st;
     const bool own = ctx->own_stream;
     ctx->prof.resolve();
-    delete ctx->mg;
-    ctx->mg = nullptr;
     if (ctx->copy_st) { cudaStreamSynchronize(ctx->copy_st); cudaStreamDestroy(ctx->copy_st); cudaEventDestroy(ctx->copy_ev); }
+    for (int k = 0; k < 2; k++) {
+        if (ctx->stage_buf[k]) cudaFreeHost(ctx->stage_buf[k]);
+        if (ctx->stage_ev[k]) cudaEventDestroy(ctx->stage_ev[k]);
+    }
     delete ctx;  // the stream was synchronised above: the pool's slabs are idle
     if (own) cudaStreamDestroy(st);
     return GRLGPU_OK;
@@ -1231,6 +891,7 @@ static int set_text_common(grlgpu_ctx* ctx, const void* text, uint64_t n_syms, i
     if (on_device && ((uintptr_t)text & 15)) return GRLGPU_ERR_ARG;
     return guarded(ctx, [&] {
         ctx->n = n_syms; ctx->w = sym_bytes; ctx->first = true; ctx->round = 0; ctx->done = false; ctx->have_stats = false;
+        ctx->mg_n_strings = 0; ctx->mg_sl = Mg2Slices();
         if (on_device) { ctx->text_own.release(); ctx->text = text; }
         else {
             ctx->text_own.alloc(n_syms * (u64)sym_bytes + 16, ctx->st);
@@ -1246,16 +907,7 @@ int grlgpu_set_text_device(grlgpu_ctx* ctx, const void* dev_text, uint64_t n_sym
 int grlgpu_stats(grlgpu_ctx* ctx, grlgpu_stats_t* out) {
     if (!ctx || !out) return GRLGPU_ERR_ARG;
     if (!ctx->text || !ctx->first) return GRLGPU_ERR_STATE;
-    int rc = guarded(ctx, [&] {
-        if (!ctx->have_stats) {
-            switch (ctx->w) {
-                case 1: compute_stats<u8>(ctx); break;
-                case 2: compute_stats<u16>(ctx); break;
-                case 4: compute_stats<u32>(ctx); break;
-                default: compute_stats<u64>(ctx); break;
-            }
-        }
-    });
+    int rc = guarded(ctx, [&] { ensure_stats(ctx); });
     if (rc == GRLGPU_OK) *out = ctx->stats;
     return rc;
 }
@@ -1351,6 +1003,136 @@ int grlgpu_fetch_level_async(grlgpu_ctx* ctx, void* rule_l, void* rule_r, uint8_
     });
 }
 
+int grlgpu_level_checksum(grlgpu_ctx* ctx, uint64_t* out4) {
+    if (!ctx || !out4) return GRLGPU_ERR_ARG;
+    if (ctx->round == 0 || !ctx->rule_l.p) return GRLGPU_ERR_STATE;
+    return guarded(ctx, [&] {
+        level_checksum(ctx->st, ctx->lvl_sym_bytes, ctx->rule_l.p, ctx->rule_r.p, ctx->has_hocc.p, ctx->lvl_tot, 0, ctx->pre_sym.p, ctx->pre_len.p, ctx->lvl_npre, (u64*)out4);
+    });
+}
+
+// ---- streaming ingest: the caller fills pinned staging buffers (e.g. read() straight from the input file), the copies to the
+// device run on the copy stream while the caller fills the other buffer ----
+static void ensure_copy_stream(grlgpu_ctx* ctx) {
+    if (!ctx->copy_st) {
+        GRL_CUDA(cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking));
+        GRL_CUDA(cudaEventCreateWithFlags(&ctx->copy_ev, cudaEventDisableTiming));
+    }
+}
+int grlgpu_text_begin(grlgpu_ctx* ctx, uint64_t n_syms, int sym_bytes, uint64_t stage_bytes) {
+    if (!ctx || n_syms == 0 || !(sym_bytes == 1 || sym_bytes == 2 || sym_bytes == 4 || sym_bytes == 8)) return GRLGPU_ERR_ARG;
+    return guarded(ctx, [&] {
+        ensure_copy_stream(ctx);
+        const u64 cap = std::max<u64>(1ull << 20, (stage_bytes ? stage_bytes : (64ull << 20)) / 4096 * 4096);
+        if (cap != ctx->stage_cap) {
+            for (int k = 0; k < 2; k++) {
+                if (ctx->stage_buf[k]) { GRL_CUDA(cudaFreeHost(ctx->stage_buf[k])); ctx->stage_buf[k] = nullptr; }
+                GRL_CUDA(cudaHostAlloc((void**)&ctx->stage_buf[k], cap, cudaHostAllocDefault));
+                if (!ctx->stage_ev[k]) GRL_CUDA(cudaEventCreateWithFlags(&ctx->stage_ev[k], cudaEventDisableTiming));
+            }
+            ctx->stage_cap = cap;
+        }
+        ctx->n = n_syms; ctx->w = sym_bytes; ctx->first = true; ctx->round = 0; ctx->done = false; ctx->have_stats = false;
+        ctx->mg_n_strings = 0; ctx->mg_sl = Mg2Slices();
+        ctx->ingest_bytes = n_syms * (u64)sym_bytes;
+        ctx->ingest_off = 0;
+        ctx->stage_cur = 0;
+        ctx->text_own.alloc(ctx->ingest_bytes + 16, ctx->st);
+        ctx->text = ctx->text_own.p;
+        GRL_CUDA(cudaStreamSynchronize(ctx->st));  // the block may have been in use by earlier work of the compute stream
+        ctx->ingesting = true;
+    });
+}
+int grlgpu_text_stage(grlgpu_ctx* ctx, void** buf, uint64_t* cap) {
+    if (!ctx || !buf || !cap) return GRLGPU_ERR_ARG;
+    if (!ctx->ingesting) return GRLGPU_ERR_STATE;
+    return guarded(ctx, [&] {
+        GRL_CUDA(cudaEventSynchronize(ctx->stage_ev[ctx->stage_cur]));  // the previous copy out of this buffer is done
+        *buf = ctx->stage_buf[ctx->stage_cur];
+        *cap = std::min<u64>(ctx->stage_cap, ctx->ingest_bytes - ctx->ingest_off);
+    });
+}
+int grlgpu_text_commit(grlgpu_ctx* ctx, uint64_t bytes) {
+    if (!ctx) return GRLGPU_ERR_ARG;
+    if (!ctx->ingesting || bytes > ctx->stage_cap || ctx->ingest_off + bytes > ctx->ingest_bytes) return GRLGPU_ERR_STATE;
+    return guarded(ctx, [&] {
+        const int k = ctx->stage_cur;
+        GRL_CUDA(cudaMemcpyAsync(ctx->text_own.p + ctx->ingest_off, ctx->stage_buf[k], bytes, cudaMemcpyHostToDevice, ctx->copy_st));
+        GRL_CUDA(cudaEventRecord(ctx->stage_ev[k], ctx->copy_st));
+        ctx->ingest_off += bytes;
+        ctx->stage_cur ^= 1;
+    });
+}
+int grlgpu_text_end(grlgpu_ctx* ctx) {
+    if (!ctx) return GRLGPU_ERR_ARG;
+    if (!ctx->ingesting) return GRLGPU_ERR_STATE;
+    return guarded(ctx, [&] {
+        ctx->ingesting = false;
+        if (ctx->ingest_off != ctx->ingest_bytes) throw Error(GRLGPU_ERR_STATE, "text ingest ended before every byte was committed");
+        GRL_CUDA(cudaStreamSynchronize(ctx->copy_st));
+    });
+}
+
+// ---- level hand-over for host-side fetch threads: the level's device arrays are parked (kept alive, not returned to the pool)
+// and their addresses given out; any host thread may then copy them with grlgpu_copy_to_host while this context computes the
+// next round. grlgpu_fetch_wait releases them. Works for the level of grlgpu_round and for the slice of grlgpu_mg_round. ----
+int grlgpu_level_park(grlgpu_ctx* ctx, int len_bytes, grlgpu_level_ptrs_t* out) {
+    if (!ctx || !out || !(len_bytes == 4 || len_bytes == 8)) return GRLGPU_ERR_ARG;
+    const bool mg = ctx->mg_sl.valid;
+    if (!mg && (ctx->round == 0 || !ctx->rule_l.p)) return GRLGPU_ERR_STATE;
+    if (!mg && len_bytes == 4 && ctx->lvl_n_in >= (1ull << 32)) return GRLGPU_ERR_LIMIT;
+    return guarded(ctx, [&] {
+        memset(out, 0, sizeof(*out));
+        out->device = ctx->device;
+        out->len_bytes = (uint32_t)len_bytes;
+        const u64* len64;
+        u64 n_pre;
+        if (mg) {
+            Mg2Slices& S = ctx->mg_sl;
+            out->sym_bytes = (uint32_t)S.sym_bytes; out->tot = S.tot_local; out->n_pre = S.n_pre_local;
+            out->rule_l = S.rule_l.p; out->rule_r = S.rule_r.p; out->has_hocc = S.has_hocc.p;
+            out->pre_sym = S.pre_sym.p + S.pre_drop * (u64)S.sym_bytes;
+            len64 = S.pre_len.p + S.pre_drop;
+            n_pre = S.n_pre_local;
+        } else {
+            out->sym_bytes = (uint32_t)ctx->lvl_sym_bytes; out->tot = ctx->lvl_tot; out->n_pre = ctx->lvl_npre;
+            out->rule_l = ctx->rule_l.p; out->rule_r = ctx->rule_r.p; out->has_hocc = ctx->has_hocc.p; out->pre_sym = ctx->pre_sym.p;
+            len64 = ctx->pre_len.p;
+            n_pre = ctx->lvl_npre;
+        }
+        out->pre_len = len64;
+        if (len_bytes == 4) {
+            DevBuf<u32> len32(n_pre, ctx->st);
+            if (n_pre) GRL_LAUNCH("narrow_u64", n_pre * 12, narrow_u64_kernel, grid_for(n_pre, 256), 256, 0, ctx->st, len64, n_pre, len32.p);
+            out->pre_len = len32.p;
+            ctx->parked_u32.push_back(std::move(len32));
+        }
+        GRL_CUDA(cudaStreamSynchronize(ctx->st));
+        if (mg) {
+            Mg2Slices& S = ctx->mg_sl;
+            ctx->parked_u8.push_back(std::move(S.rule_l)); ctx->parked_u8.push_back(std::move(S.rule_r));
+            ctx->parked_u8.push_back(std::move(S.has_hocc)); ctx->parked_u8.push_back(std::move(S.pre_sym));
+            ctx->parked_u64.push_back(std::move(S.pre_len));
+            S.valid = false;
+        } else {
+            ctx->parked_u8.push_back(std::move(ctx->rule_l)); ctx->parked_u8.push_back(std::move(ctx->rule_r));
+            ctx->parked_u8.push_back(std::move(ctx->has_hocc)); ctx->parked_u8.push_back(std::move(ctx->pre_sym));
+            ctx->parked_u64.push_back(std::move(ctx->pre_len));
+        }
+    });
+}
+// blocking device -> host copy on a stream private to the calling thread; thread-safe, needs no context
+int grlgpu_copy_to_host(int device, void* dst, const void* dev_src, uint64_t bytes) {
+    if (bytes == 0) return GRLGPU_OK;
+    if (!dst || !dev_src) return GRLGPU_ERR_ARG;
+    static thread_local cudaStream_t s[64] = {nullptr};
+    if (device < 0 || device >= 64) return GRLGPU_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return GRLGPU_ERR_CUDA;
+    if (!s[device] && cudaStreamCreateWithFlags(&s[device], cudaStreamNonBlocking) != cudaSuccess) return GRLGPU_ERR_CUDA;
+    if (cudaMemcpyAsync(dst, dev_src, bytes, cudaMemcpyDeviceToHost, s[device]) != cudaSuccess) return GRLGPU_ERR_CUDA;
+    return cudaStreamSynchronize(s[device]) == cudaSuccess ? GRLGPU_OK : GRLGPU_ERR_CUDA;
+}
+
 int grlgpu_fetch_wait(grlgpu_ctx* ctx) {
     if (!ctx) return GRLGPU_ERR_ARG;
     return guarded(ctx, [&] {
@@ -1426,120 +1208,182 @@ int grlgpu_histogram(grlgpu_ctx* ctx, uint64_t* hist256) {
     return GRLGPU_OK;
 }
 
-// ---- multi-GPU rounds ----
-#define MG_DISPATCH_FIRST(fn, ...)                                                     \
-    do {                                                                               \
-        if (ctx->first) switch (ctx->w) {                                              \
-            case 1: fn<u8, true>(__VA_ARGS__); break;                                  \
-            case 2: fn<u16, true>(__VA_ARGS__); break;                                 \
-            case 4: fn<u32, true>(__VA_ARGS__); break;                                 \
-            default: fn<u64, true>(__VA_ARGS__); break;                                \
-        } else switch (ctx->w) {                                                       \
-            case 1: fn<u8, false>(__VA_ARGS__); break;                                 \
-            case 2: fn<u16, false>(__VA_ARGS__); break;                                \
-            case 4: fn<u32, false>(__VA_ARGS__); break;                                \
-            default: fn<u64, false>(__VA_ARGS__); break;                               \
-        }                                                                              \
-    } while (0)
-#define MG_DISPATCH(fn, ...)                                                           \
-    do {                                                                               \
-        switch (ctx->w) {                                                              \
-            case 1: fn<u8>(__VA_ARGS__); break;                                        \
-            case 2: fn<u16>(__VA_ARGS__); break;                                       \
-            case 4: fn<u32>(__VA_ARGS__); break;                                       \
-            default: fn<u64>(__VA_ARGS__); break;                                      \
-        }                                                                              \
-    } while (0)
-
-int grlgpu_mg_set_alphabet(grlgpu_ctx* ctx, uint64_t global_max_sym) {
-    if (!ctx) return GRLGPU_ERR_ARG;
-    if (!ctx->have_stats || !ctx->first) return GRLGPU_ERR_STATE;
-    if (global_max_sym < ctx->stats.max_sym) return GRLGPU_ERR_ARG;
-    ctx->alphabet = global_max_sym + 1;
+// ---- exchange layer + multi-GPU rounds (comm.hpp, mg2.cuh) ----
+int grlgpu_nccl_unique_id(void* id128) {
+    if (!id128) return GRLGPU_ERR_ARG;
+    return guarded(nullptr, [&] {
+        NcclApi& api = NcclApi::get();
+        ncclUniqueId id;
+        GRL_NCCL(api.GetUniqueId(&id));
+        memcpy(id128, &id, sizeof(id));
+    });
+}
+int grlgpu_comm_create_nccl(grlgpu_comm** comm, const void* id128, int rank, int world, int device) {
+    if (!comm || !id128 || world < 1 || world > 31 || rank < 0 || rank >= world) return GRLGPU_ERR_ARG;
+    *comm = nullptr;
+    return guarded(nullptr, [&] {
+        std::unique_ptr<grlgpu_comm> h(new grlgpu_comm());
+        h->c.reset(new NcclComm(id128, rank, world, device));
+        *comm = h.release();
+    });
+}
+int grlgpu_local_group_create(grlgpu_local_group** group, int world) {
+    if (!group || world < 1 || world > 31) return GRLGPU_ERR_ARG;
+    *group = new grlgpu_local_group(world);
     return GRLGPU_OK;
 }
-int grlgpu_mg_local(grlgpu_ctx* ctx, int n_ranks, grlgpu_part_t* per_owner, uint64_t* parse_len_local) {
-    if (!ctx || !per_owner || !parse_len_local || n_ranks < 1 || n_ranks > 31) return GRLGPU_ERR_ARG;
-    if (!ctx->text || ctx->done || !ctx->have_stats) return GRLGPU_ERR_STATE;
-    return guarded(ctx, [&] {
-        u64 pl = 0;
-        MG_DISPATCH_FIRST(mg_local_t, ctx, n_ranks, per_owner, &pl);
-        *parse_len_local = pl;
-    });
+int grlgpu_local_group_abort(grlgpu_local_group* group) {
+    if (!group) return GRLGPU_ERR_ARG;
+    group->g.abort();
+    return GRLGPU_OK;
 }
-int grlgpu_mg_pack(grlgpu_ctx* ctx, uint32_t* d_lens, uint64_t* d_counts, void* d_cells) {
-    if (!ctx || !d_lens || !d_counts || !d_cells) return GRLGPU_ERR_ARG;
-    if (!ctx->mg) return GRLGPU_ERR_STATE;
-    return guarded(ctx, [&] { MG_DISPATCH(mg_pack_t, ctx, d_lens, (u64*)d_counts, d_cells); });
+int grlgpu_local_group_destroy(grlgpu_local_group* group) {
+    delete group;
+    return GRLGPU_OK;
 }
-int grlgpu_mg_merge(grlgpu_ctx* ctx, const uint32_t* d_lens, const uint64_t* d_counts, const void* d_cells, uint64_t m, uint64_t n_cells, grlgpu_part_t* part) {
-    if (!ctx || !part || !d_lens || !d_counts || !d_cells) return GRLGPU_ERR_ARG;
-    if (!ctx->mg) return GRLGPU_ERR_STATE;
-    return guarded(ctx, [&] { MG_DISPATCH(mg_merge_t, ctx, d_lens, (const u64*)d_counts, d_cells, (u64)m, (u64)n_cells, part); });
+int grlgpu_comm_create_local(grlgpu_comm** comm, grlgpu_local_group* group, int rank, int device) {
+    if (!comm || !group || rank < 0 || rank >= group->g.world) return GRLGPU_ERR_ARG;
+    std::unique_ptr<grlgpu_comm> h(new grlgpu_comm());
+    h->c.reset(new LocalComm(&group->g, rank, device));
+    *comm = h.release();
+    return GRLGPU_OK;
 }
-int grlgpu_mg_pack_part(grlgpu_ctx* ctx, uint32_t* d_lens, uint64_t* d_freqs, void* d_cells) {
-    if (!ctx || !d_lens || !d_freqs || !d_cells) return GRLGPU_ERR_ARG;
-    if (!ctx->mg) return GRLGPU_ERR_STATE;
-    return guarded(ctx, [&] { MG_DISPATCH(mg_pack_part_t, ctx, d_lens, (u64*)d_freqs, d_cells); });
+int grlgpu_comm_destroy(grlgpu_comm* comm) {
+    if (comm) cudaSetDevice(comm->c->device);
+    delete comm;
+    return GRLGPU_OK;
 }
-int grlgpu_mg_global(grlgpu_ctx* ctx, const uint32_t* d_lens, const uint64_t* d_freqs, const void* d_cells, uint64_t d, uint64_t n_cells, int done_global,
-                     grlgpu_round_t* out) {
-    if (!ctx || !out || !d_lens || !d_freqs || !d_cells || d == 0) return GRLGPU_ERR_ARG;
-    if (!ctx->mg) return GRLGPU_ERR_STATE;
-    return guarded(ctx, [&] { MG_DISPATCH_FIRST(mg_global_t, ctx, d_lens, (const u64*)d_freqs, d_cells, (u64)d, (u64)n_cells, done_global, out); });
+int grlgpu_comm_info(const grlgpu_comm* comm, uint64_t* bytes_sent, uint64_t* n_bulk, uint64_t* n_small, char* kind, int kind_cap) {
+    if (!comm) return GRLGPU_ERR_ARG;
+    if (bytes_sent) *bytes_sent = comm->c->bytes_sent;
+    if (n_bulk) *n_bulk = comm->c->n_bulk;
+    if (n_small) *n_small = comm->c->n_small;
+    if (kind && kind_cap > 0) snprintf(kind, (size_t)kind_cap, "%s", comm->c->kind());
+    return GRLGPU_OK;
+}
+int grlgpu_set_peers(grlgpu_ctx* ctx, const int* devices, int n_devices) {
+    if (!ctx || (n_devices > 0 && !devices) || n_devices < 0) return GRLGPU_ERR_ARG;
+    return guarded(ctx, [&] { ctx->pool.set_peers(std::vector<int>(devices, devices + n_devices)); });
 }
 
-int grlgpu_mg_rank_sort(grlgpu_ctx* ctx, const uint32_t* d_lens, const uint64_t* d_freqs, const void* d_cells, uint64_t d, uint64_t n_cells, int rank_id, int n_ranks,
-                        uint64_t* info5) {
-    if (!ctx || !info5 || !d_lens || !d_freqs || !d_cells || d == 0 || rank_id < 0 || rank_id >= n_ranks) return GRLGPU_ERR_ARG;
-    if (!ctx->mg) return GRLGPU_ERR_STATE;
-    return guarded(ctx, [&] { MG_DISPATCH_FIRST(mg_rank_sort_t, ctx, d_lens, (const u64*)d_freqs, d_cells, (u64)d, (u64)n_cells, rank_id, n_ranks, (u64*)info5); });
-}
-int grlgpu_mg_rank_apply(grlgpu_ctx* ctx, uint64_t rank_base, uint64_t* d_ph_meta, uint8_t* d_is_suffix_next, uint32_t* d_erank1) {
-    if (!ctx || !d_ph_meta || !d_is_suffix_next || !d_erank1) return GRLGPU_ERR_ARG;
-    if (!ctx->mg || !ctx->mg->GR) return GRLGPU_ERR_STATE;
+int grlgpu_mg_stats(grlgpu_ctx* ctx, grlgpu_comm* comm, grlgpu_stats_t* out) {
+    if (!ctx || !comm || !out) return GRLGPU_ERR_ARG;
+    if (!ctx->text || !ctx->first) return GRLGPU_ERR_STATE;
     return guarded(ctx, [&] {
-        if (ctx->mg->sym_bytes == 8) mg_rank_apply_sym<u64>(ctx, rank_base, (u64*)d_ph_meta, d_is_suffix_next, d_erank1);
-        else mg_rank_apply_sym<u32>(ctx, rank_base, (u64*)d_ph_meta, d_is_suffix_next, d_erank1);
+        Comm& cm = *comm->c;
+        // local statistics first; a rank whose shard is ill formed reports it so that every rank fails together
+        std::vector<u64> mine(7 + 256, 0);
+        int rc = GRLGPU_OK;
+        try { ensure_stats(ctx); }
+        catch (const Error& e) { rc = e.code; ctx->last_error = e.what(); cudaGetLastError(); }
+        mine[0] = (u64)(int64_t)rc;
+        if (rc == GRLGPU_OK) {
+            const grlgpu_stats_t& s = ctx->stats;
+            mine[1] = s.n_syms; mine[2] = s.n_strings; mine[3] = s.longest_string; mine[4] = s.min_sym; mine[5] = s.max_sym; mine[6] = s.sep_sym;
+            memcpy(mine.data() + 7, ctx->hist, sizeof(ctx->hist));
+        }
+        const std::vector<u64> all = mg2_gather(cm, mine, ctx->st);
+        grlgpu_stats_t g{};
+        g.min_sym = ~0ULL;
+        u64 hist[256] = {0};
+        for (int p = 0; p < cm.world; p++) {
+            const u64* row = all.data() + (size_t)p * mine.size();
+            if ((int)(int64_t)row[0] != GRLGPU_OK) throw Error((int)(int64_t)row[0], "rank " + std::to_string(p) + ": " + grlgpu_strerror((int)(int64_t)row[0]));
+            g.n_syms += row[1]; g.n_strings += row[2];
+            g.longest_string = std::max<u64>(g.longest_string, row[3]);
+            g.min_sym = std::min<u64>(g.min_sym, row[4]);
+            g.max_sym = std::max<u64>(g.max_sym, row[5]);
+            if (p == 0) g.sep_sym = row[6];
+            else if (row[6] != g.sep_sym) throw Error(GRLGPU_ERR_ILL_FORMED, "the collection is ill formed: the shards end in different symbols");
+            for (int k = 0; k < 256; k++) hist[k] += row[7 + k];
+        }
+        if (g.sep_sym != g.min_sym) throw Error(GRLGPU_ERR_ILL_FORMED, "the collection is ill formed: the last symbol is not the smallest symbol");
+        g.max_sym_freq = g.n_syms;  // utils.cpp:117
+        if (ctx->w == 1) {          // utils.cpp:161-175 on the global histogram
+            u64 mx = 0;
+            for (int k = 0; k < 256; k++) mx = std::max(mx, hist[k]);
+            g.max_sym_freq = mx;
+        }
+        ctx->alphabet = g.max_sym + 1;  // exact_par_phase.cpp:316, over the whole collection
+        ctx->mg_n_strings = g.n_strings;
+        *out = g;
     });
 }
-extern "C++" {
-template <class CellT>
-static void mg_rank_finish_cell(grlgpu_ctx* ctx, u64 rank_base, u64 tot, u64 n_pre, const u64* m, const u8* s, u32* e, int done, grlgpu_round_t* out, const u64* lm) {
-    if (ctx->mg->sym_bytes == 8) mg_rank_finish_sym<CellT, u64>(ctx, rank_base, tot, n_pre, m, s, e, done, out, lm);
-    else mg_rank_finish_sym<CellT, u32>(ctx, rank_base, tot, n_pre, m, s, e, done, out, lm);
-}
-}
-int grlgpu_mg_reply(grlgpu_ctx* ctx, uint64_t part_base, const uint64_t* d_ph_meta, uint64_t* d_reply) {
-    if (!ctx || !d_ph_meta || !d_reply) return GRLGPU_ERR_ARG;
-    if (!ctx->mg || !ctx->mg->recv_dense.p) return GRLGPU_ERR_STATE;
+
+int grlgpu_mg_round(grlgpu_ctx* ctx, grlgpu_comm* comm, grlgpu_round_t* out) {
+    if (!ctx || !comm || !out) return GRLGPU_ERR_ARG;
+    if (!ctx->text || ctx->done || !ctx->have_stats || !ctx->mg_n_strings) return GRLGPU_ERR_STATE;
     return guarded(ctx, [&] {
-        MgRound& M = *ctx->mg;
-        GRL_LAUNCH("reply_meta", M.m_recv * 20, reply_meta_kernel, grid_for(M.m_recv, 256), 256, 0, ctx->st, M.recv_dense.p, M.m_recv, (u64)part_base, (const u64*)d_ph_meta,
-                   (u64*)d_reply);
-        GRL_CUDA(cudaStreamSynchronize(ctx->st));
+        Comm& cm = *comm->c;
+        if (ctx->first) switch (ctx->w) {
+            case 1: mg2_round_t<u8, true>(ctx, cm, out); break;
+            case 2: mg2_round_t<u16, true>(ctx, cm, out); break;
+            case 4: mg2_round_t<u32, true>(ctx, cm, out); break;
+            default: mg2_round_t<u64, true>(ctx, cm, out); break;
+        } else switch (ctx->w) {
+            case 1: mg2_round_t<u8, false>(ctx, cm, out); break;
+            case 2: mg2_round_t<u16, false>(ctx, cm, out); break;
+            case 4: mg2_round_t<u32, false>(ctx, cm, out); break;
+            default: mg2_round_t<u64, false>(ctx, cm, out); break;
+        }
     });
 }
-int grlgpu_mg_rank_finish(grlgpu_ctx* ctx, uint64_t rank_base, uint64_t tot, uint64_t n_pre_runs, const uint64_t* d_ph_meta, const uint8_t* d_is_suffix_next,
-                          uint32_t* d_erank1, const uint64_t* d_local_meta, int done_global, grlgpu_round_t* out) {
-    if (!ctx || !out || !d_ph_meta || !d_is_suffix_next || !d_erank1) return GRLGPU_ERR_ARG;
-    if (!ctx->mg || !ctx->mg->GR) return GRLGPU_ERR_STATE;
+
+int grlgpu_mg_slice_info(grlgpu_ctx* ctx, grlgpu_slice_t* out) {
+    if (!ctx || !out) return GRLGPU_ERR_ARG;
+    if (!ctx->mg_n_strings || ctx->round == 0) return GRLGPU_ERR_STATE;
+    const Mg2Slices& S = ctx->mg_sl;
+    out->rank_base = S.rank_base; out->tot_local = S.tot_local; out->pre_first = S.pre_first; out->n_pre_local = S.n_pre_local;
+    out->exchange_bytes = ctx->mg_exchange_bytes; out->sym_bytes = (uint32_t)S.sym_bytes; out->reserved = 0;
+    out->n_in_local = ctx->mg_n_in_local; out->parse_len_local = ctx->mg_parse_len_local;
+    return GRLGPU_OK;
+}
+
+int grlgpu_mg_fetch_slice(grlgpu_ctx* ctx, void* rule_l, void* rule_r, uint8_t* has_hocc, void* pre_sym, void* pre_len, int len_bytes, int async) {
+    if (!ctx || !(len_bytes == 4 || len_bytes == 8)) return GRLGPU_ERR_ARG;
+    if (!ctx->mg_sl.valid) return GRLGPU_ERR_STATE;
     return guarded(ctx, [&] {
-        MG_DISPATCH(mg_rank_finish_cell, ctx, (u64)rank_base, (u64)tot, (u64)n_pre_runs, (const u64*)d_ph_meta, d_is_suffix_next, d_erank1, done_global, out, (const u64*)d_local_meta);
+        Mg2Slices& S = ctx->mg_sl;
+        cudaStream_t cs = ctx->st;
+        const u64 sb = (u64)S.sym_bytes;
+        const u64* len64 = S.pre_len.p + S.pre_drop;
+        DevBuf<u32> len32((pre_len && len_bytes == 4) ? S.n_pre_local : 0, ctx->st);
+        if (pre_len && len_bytes == 4 && S.n_pre_local)
+            GRL_LAUNCH("narrow_u64", S.n_pre_local * 12, narrow_u64_kernel, grid_for(S.n_pre_local, 256), 256, 0, ctx->st, len64, S.n_pre_local, len32.p);
+        if (async) {
+            if (!ctx->copy_st) {
+                GRL_CUDA(cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking));
+                GRL_CUDA(cudaEventCreateWithFlags(&ctx->copy_ev, cudaEventDisableTiming));
+            }
+            GRL_CUDA(cudaEventRecord(ctx->copy_ev, ctx->st));
+            GRL_CUDA(cudaStreamWaitEvent(ctx->copy_st, ctx->copy_ev, 0));
+            cs = ctx->copy_st;
+        }
+        if (pre_sym) GRL_CUDA(cudaMemcpyAsync(pre_sym, S.pre_sym.p + S.pre_drop * sb, S.n_pre_local * sb, cudaMemcpyDeviceToHost, cs));
+        if (pre_len && len_bytes == 4) GRL_CUDA(cudaMemcpyAsync(pre_len, len32.p, S.n_pre_local * 4, cudaMemcpyDeviceToHost, cs));
+        if (pre_len && len_bytes == 8) GRL_CUDA(cudaMemcpyAsync(pre_len, len64, S.n_pre_local * 8, cudaMemcpyDeviceToHost, cs));
+        if (rule_l) GRL_CUDA(cudaMemcpyAsync(rule_l, S.rule_l.p, S.tot_local * sb, cudaMemcpyDeviceToHost, cs));
+        if (rule_r) GRL_CUDA(cudaMemcpyAsync(rule_r, S.rule_r.p, S.tot_local * sb, cudaMemcpyDeviceToHost, cs));
+        if (has_hocc) GRL_CUDA(cudaMemcpyAsync(has_hocc, S.has_hocc.p, S.tot_local, cudaMemcpyDeviceToHost, cs));
+        if (async) {  // parked until grlgpu_fetch_wait; the slices cannot be fetched again
+            ctx->parked_u8.push_back(std::move(S.rule_l));
+            ctx->parked_u8.push_back(std::move(S.rule_r));
+            ctx->parked_u8.push_back(std::move(S.has_hocc));
+            ctx->parked_u8.push_back(std::move(S.pre_sym));
+            ctx->parked_u64.push_back(std::move(S.pre_len));
+            ctx->parked_u32.push_back(std::move(len32));
+            S.valid = false;
+        } else GRL_CUDA(cudaStreamSynchronize(ctx->st));
     });
 }
-int grlgpu_mg_level_slice(grlgpu_ctx* ctx, void* d_rule_l, void* d_rule_r, uint8_t* d_has_hocc, void* d_pre_sym, uint64_t* d_pre_len) {
-    if (!ctx) return GRLGPU_ERR_ARG;
-    if (!ctx->mg) return GRLGPU_ERR_STATE;
+
+int grlgpu_mg_slice_checksum(grlgpu_ctx* ctx, uint64_t* out4) {
+    if (!ctx || !out4) return GRLGPU_ERR_ARG;
+    if (!ctx->mg_sl.valid) return GRLGPU_ERR_STATE;
     return guarded(ctx, [&] {
-        MgRound& M = *ctx->mg;
-        const u64 sb = (u64)M.sym_bytes;
-        if (d_rule_l) GRL_CUDA(cudaMemcpyAsync(d_rule_l, M.sl_rule_l.p, M.tot_local * sb, cudaMemcpyDeviceToDevice, ctx->st));
-        if (d_rule_r) GRL_CUDA(cudaMemcpyAsync(d_rule_r, M.sl_rule_r.p, M.tot_local * sb, cudaMemcpyDeviceToDevice, ctx->st));
-        if (d_has_hocc) GRL_CUDA(cudaMemcpyAsync(d_has_hocc, M.sl_has_hocc.p, M.tot_local, cudaMemcpyDeviceToDevice, ctx->st));
-        if (d_pre_sym) GRL_CUDA(cudaMemcpyAsync(d_pre_sym, M.sl_pre_sym.p, M.n_pre_local * sb, cudaMemcpyDeviceToDevice, ctx->st));
-        if (d_pre_len) GRL_CUDA(cudaMemcpyAsync(d_pre_len, M.sl_pre_len.p, M.n_pre_local * 8, cudaMemcpyDeviceToDevice, ctx->st));
-        GRL_CUDA(cudaStreamSynchronize(ctx->st));
+        const Mg2Slices& S = ctx->mg_sl;
+        level_checksum(ctx->st, S.sym_bytes, S.rule_l.p, S.rule_r.p, S.has_hocc.p, S.tot_local, S.rank_base, S.pre_sym.p + S.pre_drop * (u64)S.sym_bytes, S.pre_len.p + S.pre_drop,
+                       S.n_pre_local, (u64*)out4);
     });
 }
 

@@ -513,12 +513,14 @@ __global__ void __launch_bounds__(FD_THREADS, FD_CTAS_PER_SM) dedup_cached_kerne
                 const u32 ci = (u32)(((k0 ^ (k1 * 0x9E3779B97F4A7C15ULL)) * 0xff51afd7ed558ccdULL) >> (64 - FD_CACHE_BITS));
                 for (int way = 0; way < 2; way++) {
                     const u32 c = ci ^ (u32)way;
-                    const u32 stt = c_state[c];
+                    // the state word is the only location two threads of this phase touch without a barrier in between: every access
+                    // to it is an atomic (acquire: read-modify-write that changes nothing; release: fence, then exchange)
+                    const u32 stt = atomicOr(const_cast<u32*>(&c_state[c]), 0u);
                     if (stt == 2u && c_k0[c] == k0 && c_k1[c] == k1) break;  // somebody cached it meanwhile
                     if (stt == 0u && atomicCAS(const_cast<u32*>(&c_state[c]), 0u, 1u) == 0u) {
                         c_k0[c] = k0; c_k1[c] = k1; c_slot[c] = slot;
                         __threadfence_block();
-                        c_state[c] = 2u;
+                        atomicExch(const_cast<u32*>(&c_state[c]), 2u);
                         break;
                     }
                 }

@@ -466,19 +466,18 @@ inline int rs_minb_setting() {
 // one stable partition pass on the 8-bit digit at `shift` (also the building block of the LSD sort below)
 template <class KeyT, int ITEMS>
 inline void radix_pass(KeyT** keys, u32** vals, KeyT** keys_alt, u32** vals_alt, u64 n, int shift, DevBuf<u32>& hist, DevBuf<u64>& goff, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        GRL_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<KeyT, ITEMS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<KeyT, ITEMS>()));
+    // per-device attributes: (re)applied for the current device, not cached process-wide
+    GRL_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<KeyT, ITEMS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<KeyT, ITEMS>()));
+    if (rs_minb_setting() == 5) {
         GRL_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<KeyT, ITEMS, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<KeyT, ITEMS>()));
         GRL_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<KeyT, ITEMS, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        attr_set = true;
     }
     const u64 tiles = div_up(n, RS_THREADS * ITEMS);
     GRL_LAUNCH("radix_hist", n * sizeof(KeyT), (radix_hist_kernel<KeyT, ITEMS>), (unsigned)tiles, RS_THREADS, 0, st, *keys, n, shift, hist.p, tiles);
     exclusive_scan<u32, u64>(hist.p, goff.p, 256 * tiles, nullptr, st);
     if (rs_pipe_setting()) {
-        static int pipe_grid = 0;
-        if (!pipe_grid) {
+        int pipe_grid = 0;
+        {
             GRL_CUDA(cudaFuncSetAttribute(radix_scatter_pipe_kernel<KeyT, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsp_smem_bytes<KeyT, ITEMS>()));
             GRL_CUDA(cudaFuncSetAttribute(radix_scatter_pipe_kernel<KeyT, ITEMS>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
             int dev = 0, sms = 0, per_sm = 0;

@@ -66,6 +66,7 @@ struct DevicePool {
     std::map<u64, u64> free_ranges;       // offset -> length, inside [0, mapped)
     std::map<u64, u64> live;              // offset -> length
     u64 in_use = 0, peak = 0;
+    std::vector<int> peers;               // other devices that may read / write this pool directly (NVLink P2P, LocalComm pulls)
     static constexpr u64 ALIGN = 512;
 
     template <class F>
@@ -108,20 +109,40 @@ struct DevicePool {
         prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
         prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
         prop.location.id = device;
-        CUmemAccessDesc acc = {};
-        acc.location = prop.location;
-        acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        std::vector<CUmemAccessDesc> acc = access_descs();
         for (u64 done = 0; done < add; done += chunk) {
             CUmemGenericAllocationHandle h;
             if (p_create(&h, chunk, &prop, 0) != CUDA_SUCCESS)
                 throw Error(-4, "out of device memory: request of " + std::to_string(need_bytes) + " bytes with " + std::to_string(mapped) + " mapped");
-            if (p_map(base + mapped, chunk, 0, h, 0) != CUDA_SUCCESS || p_access(base + mapped, chunk, &acc, 1) != CUDA_SUCCESS) {
+            if (p_map(base + mapped, chunk, 0, h, 0) != CUDA_SUCCESS || p_access(base + mapped, chunk, acc.data(), acc.size()) != CUDA_SUCCESS) {
                 p_release(h);
                 throw Error(-3, "cuMemMap failed");
             }
             handles.push_back(h);
             add_free(mapped, chunk);
             mapped += chunk;
+        }
+    }
+    std::vector<CUmemAccessDesc> access_descs() const {
+        std::vector<CUmemAccessDesc> v;
+        CUmemAccessDesc a = {};
+        a.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        a.location.id = device;
+        a.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        v.push_back(a);
+        for (int d : peers) { a.location.id = d; v.push_back(a); }
+        return v;
+    }
+    // devices whose copy engines / kernels may touch this pool over NVLink (only those that report peer capability)
+    void set_peers(const std::vector<int>& devs) {
+        peers.clear();
+        for (int d : devs) {
+            int can = 0;
+            if (d != device && cudaDeviceCanAccessPeer(&can, d, device) == cudaSuccess && can && std::find(peers.begin(), peers.end(), d) == peers.end()) peers.push_back(d);
+        }
+        if (mapped && !peers.empty()) {
+            std::vector<CUmemAccessDesc> acc = access_descs();
+            if (p_access(base, mapped, acc.data(), acc.size()) != CUDA_SUCCESS) peers.clear();  // stay correct (staged copies) if the mapping is refused
         }
     }
     void add_free(u64 off, u64 len) {

@@ -1,0 +1,559 @@
+// Host side of the parse phase: drives the device library (include/grlgpu.h) round by round and collects what the
+// induction phase needs. Replaces exact_algo::par_phase<sym_type> (lib/exact_algo/exact_par_phase.cpp:285-372) and, for
+// several GPUs, the thread fan-out of mt_parse_strat_t (include/parsing_strategies.h:244-275): one host thread per GPU,
+// each owning a shard of whole strings, exchanging through NCCL or peer copies inside the device library.
+//
+// I/O pipeline: the input streams from the file (or from memory) through two pinned staging buffers,
+// so reading chunk k+1 overlaps the host-to-device copy of chunk k (the reference reads 8 MB windows,
+// external/cdt/include/file_streams.hpp:93-105); every level's artefacts are handed to fetch threads that copy them to
+// the host while the device computes the next round (the reference writes dict_lev_k / pre_bwt_lev_k files between
+// rounds, exact_par_phase.cpp:150-155,:402-406).
+#pragma once
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <array>
+#include <chrono>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <functional>
+#include <iostream>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/grlgpu.h"
+#include "ind_phase.hpp"
+#include "ind_phase_mt.hpp"
+
+namespace grlbwt {
+
+struct GpuError : std::runtime_error {
+    int status;
+    GpuError(int st, const std::string& m) : std::runtime_error(m), status(st) {}
+};
+
+inline double ms_since(std::chrono::steady_clock::time_point t0) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// what one round left behind, for parity checks across GPU counts: the level's global sizes and four order-insensitive sums
+// over its rules / hocc marks / preliminary BWT (grlgpu_level_checksum; the slices of a multi-GPU level add up to the same)
+struct RoundDigest {
+    uint64_t tot = 0, n_pre = 0, parse_len = 0, n_phrases = 0, dict_syms = 0;
+    uint64_t cs[4] = {0, 0, 0, 0};
+};
+
+struct ParseResult {
+    grlgpu_stats_t stats{};
+    std::vector<Level> levels;        // 64-bit symbols: only filled when some level needs them
+    std::vector<Level32> levels32;    // 32-bit symbols (the usual case), consumed by the multi-threaded induction
+    bool wide = false;
+    std::vector<grlgpu_round_t> rounds;
+    std::vector<RoundDigest> digests;
+    std::vector<uint64_t> final_parse;  // one cell per string, cells = rank<<1|rep
+    double h2d_ms = 0, par_ms = 0;
+    uint64_t exchange_bytes = 0;        // multi-GPU: bulk bytes sent between the ranks, all rounds, all ranks
+    int n_ranks = 1;
+    std::string comm_kind;
+};
+
+// the input of the parse phase: a buffer in host memory or a byte range of a file
+struct TextSource {
+    const unsigned char* mem = nullptr;
+    std::string file;
+    uint64_t offset = 0, bytes = 0;
+};
+
+// ---------------------------------------------------------------- fetch threads
+class FetchPool {
+    struct Job { int device; void* dst; const void* src; uint64_t bytes; };
+    std::vector<std::thread> th;
+    std::mutex m;
+    std::condition_variable cv, cv_done;
+    std::deque<Job> q;
+    size_t pending = 0;
+    bool stop = false;
+    int err = 0;
+    void work() {
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [&] { return stop || !q.empty(); });
+                if (q.empty()) return;
+                j = q.front();
+                q.pop_front();
+            }
+            // large arrays are cut into pieces so that several threads share one array's copy
+            const int rc = grlgpu_copy_to_host(j.device, j.dst, j.src, j.bytes);
+            std::lock_guard<std::mutex> lk(m);
+            if (rc != GRLGPU_OK && !err) err = rc;
+            if (--pending == 0) cv_done.notify_all();
+        }
+    }
+
+public:
+    explicit FetchPool(size_t n_threads) {
+        for (size_t t = 0; t < std::max<size_t>(1, n_threads); t++) th.emplace_back([this] { work(); });
+    }
+    ~FetchPool() {
+        { std::lock_guard<std::mutex> lk(m); stop = true; }
+        cv.notify_all();
+        for (auto& t : th) t.join();
+    }
+    void enqueue(int device, void* dst, const void* src, uint64_t bytes) {
+        constexpr uint64_t PIECE = 256ull << 20;
+        std::lock_guard<std::mutex> lk(m);
+        for (uint64_t o = 0; o < bytes; o += PIECE) {
+            q.push_back({device, (char*)dst + o, (const char*)src + o, std::min(PIECE, bytes - o)});
+            pending++;
+        }
+        cv.notify_all();
+    }
+    void wait_all() {
+        std::unique_lock<std::mutex> lk(m);
+        cv_done.wait(lk, [&] { return pending == 0; });
+        if (err) { const int e = err; err = 0; throw GpuError(e, std::string("level fetch: ") + grlgpu_strerror(e)); }
+    }
+};
+
+// ---------------------------------------------------------------- small helpers
+struct CtxHandle {  // RAII around grlgpu_ctx
+    grlgpu_ctx* p = nullptr;
+    CtxHandle(int device, uint64_t flags) {
+        const int rc = grlgpu_create(&p, device, flags);
+        if (rc != GRLGPU_OK) throw GpuError(rc, std::string("grlgpu_create: ") + grlgpu_strerror(rc));
+    }
+    CtxHandle(const CtxHandle&) = delete;
+    ~CtxHandle() { if (p) grlgpu_destroy(p); }
+    void check(const char* what, int st) const {
+        if (st != GRLGPU_OK) throw GpuError(st, std::string(what) + ": " + grlgpu_strerror(st) + " (" + grlgpu_last_error(p) + ")");
+    }
+};
+
+// text -> device through the pinned staging buffers; returns the milliseconds it took
+inline double load_text(const CtxHandle& ctx, const TextSource& src, int sym_bytes) {
+    const auto t0 = std::chrono::steady_clock::now();
+    if (src.bytes == 0 || src.bytes % (uint64_t)sym_bytes) throw GpuError(GRLGPU_ERR_ILL_FORMED, "the input is empty or not a whole number of symbols");
+    ctx.check("grlgpu_text_begin", grlgpu_text_begin(ctx.p, src.bytes / (uint64_t)sym_bytes, sym_bytes, 0));
+    int fd = -1;
+    if (!src.mem) {
+        fd = open(src.file.c_str(), O_RDONLY);
+        if (fd < 0) throw std::runtime_error("cannot open " + src.file);
+        posix_fadvise(fd, (off_t)src.offset, (off_t)src.bytes, POSIX_FADV_SEQUENTIAL);
+    }
+    try {
+        for (uint64_t done = 0; done < src.bytes;) {
+            void* buf = nullptr;
+            uint64_t cap = 0;
+            ctx.check("grlgpu_text_stage", grlgpu_text_stage(ctx.p, &buf, &cap));
+            uint64_t got = 0;
+            if (src.mem) { memcpy(buf, src.mem + src.offset + done, cap); got = cap; }
+            else
+                while (got < cap) {
+                    const ssize_t r = pread(fd, (char*)buf + got, cap - got, (off_t)(src.offset + done + got));
+                    if (r <= 0) throw std::runtime_error("cannot read " + src.file);
+                    got += (uint64_t)r;
+                }
+            ctx.check("grlgpu_text_commit", grlgpu_text_commit(ctx.p, got));
+            done += got;
+        }
+        ctx.check("grlgpu_text_end", grlgpu_text_end(ctx.p));
+    } catch (...) {
+        if (fd >= 0) close(fd);
+        throw;
+    }
+    if (fd >= 0) close(fd);
+    return ms_since(t0);
+}
+
+inline uint64_t read_cell(const TextSource& src, int fd, uint64_t cell, int w) {
+    uint64_t v = 0;
+    if (src.mem) memcpy(&v, src.mem + src.offset + cell * (uint64_t)w, (size_t)w);
+    else if (pread(fd, &v, (size_t)w, (off_t)(src.offset + cell * (uint64_t)w)) != (ssize_t)w) throw std::runtime_error("cannot read " + src.file);
+    return v;
+}
+
+// Contiguous ranges of WHOLE strings balanced by symbol count (the reference's mt split, parsing_strategies.h:208-214,
+// byte-balanced): boundary r is the end of the first string that ends at or after cell r*n/G. Fewer ranges than asked
+// come back when the collection has fewer strings than ranks. -> cell offsets [b0=0, b1, ..., n]
+inline std::vector<uint64_t> shard_bounds(const TextSource& src, int sym_bytes, int n_ranks) {
+    const uint64_t w = (uint64_t)sym_bytes, n = src.bytes / w;
+    int fd = -1;
+    if (!src.mem) {
+        fd = open(src.file.c_str(), O_RDONLY);
+        if (fd < 0) throw std::runtime_error("cannot open " + src.file);
+    }
+    std::vector<uint64_t> b{0};
+    try {
+        const uint64_t sep = read_cell(src, fd, n - 1, sym_bytes);
+        std::vector<unsigned char> win((size_t)(1u << 20) * w);
+        for (int r = 1; r < n_ranks; r++) {
+            uint64_t pos = std::max<uint64_t>((uint64_t)r * n / (uint64_t)n_ranks, b.back());
+            uint64_t end = n;  // one past the separator that closes the string holding cell `pos`
+            while (pos < n) {
+                const uint64_t cnt = std::min<uint64_t>((uint64_t)1 << 20, n - pos);
+                const unsigned char* p;
+                if (src.mem) p = src.mem + src.offset + pos * w;
+                else {
+                    uint64_t got = 0;
+                    while (got < cnt * w) {
+                        const ssize_t rr = pread(fd, win.data() + got, cnt * w - got, (off_t)(src.offset + pos * w + got));
+                        if (rr <= 0) throw std::runtime_error("cannot read " + src.file);
+                        got += (uint64_t)rr;
+                    }
+                    p = win.data();
+                }
+                uint64_t k = 0;
+                for (; k < cnt; k++) {
+                    uint64_t v = 0;
+                    memcpy(&v, p + k * w, (size_t)w);
+                    if (v == sep) break;
+                }
+                if (k < cnt) { end = pos + k + 1; break; }
+                pos += cnt;
+            }
+            if (end >= n) break;  // no further string boundary: the remaining ranks would be empty
+            if (end > b.back()) b.push_back(end);
+        }
+    } catch (...) {
+        if (fd >= 0) close(fd);
+        throw;
+    }
+    if (fd >= 0) close(fd);
+    b.push_back(n);
+    return b;
+}
+
+inline void print_stats(const grlgpu_stats_t& s) {
+    std::cout << "Stats: " << std::endl;
+    std::cout << "  Smallest symbol               : " << s.min_sym << std::endl;
+    std::cout << "  Greatest symbol               : " << s.max_sym << std::endl;
+    std::cout << "  Number of symbols in the file : " << s.n_syms << std::endl;
+    std::cout << "  Number of strings             : " << s.n_strings << std::endl;
+    std::cout << "Parsing the text:    " << std::endl;
+}
+inline void print_round(const grlgpu_round_t& r) {
+    std::cout << "  Parsing round " << r.round << std::endl;
+    std::cout << "    Stats:" << std::endl;
+    std::cout << "      Parsing phrases:                  " << r.n_phrases << std::endl;
+    std::cout << "      Number of symbols in the phrases: " << r.dict_syms << std::endl;
+    std::cout << "      Number of unsolved BWT blocks:    " << r.tot_phrases << std::endl;
+    std::cout << "      Parse size:                       " << r.parse_len << std::endl;
+    std::cout << "      Device time (ms):                 " << r.device_ms << " (text " << r.text_pass_ms << ", dictionary " << r.dict_ms << ", rewrite "
+              << r.rewrite_ms << ")" << std::endl;
+}
+
+// storage of one level on the host, shared by the ranks of a multi-GPU run (each fills its own part)
+struct LevelSink {
+    bool wide = false, narrow_len = false;
+    Level32 l32;
+    Level l64;
+    void prepare(const grlgpu_round_t& r, bool wide_) {
+        wide = wide_;
+        narrow_len = !wide && (r.n_in + r.parse_len < (1ull << 32));  // the run lengths of a level sum to at most n_in + parse_len
+        if (!wide) {
+            l32.alphabet = r.alphabet; l32.tot_phrases = r.tot_phrases;
+            l32.rule_l.resize(r.tot_phrases); l32.rule_r.resize(r.tot_phrases); l32.has_hocc.resize(r.tot_phrases);
+            l32.pre_sym.resize(r.n_pre_runs);
+            if (narrow_len) l32.pre_len32.resize(r.n_pre_runs); else l32.pre_len.resize(r.n_pre_runs);
+        } else {
+            l64.alphabet = r.alphabet; l64.tot_phrases = r.tot_phrases;
+            l64.rule_l.resize(r.tot_phrases); l64.rule_r.resize(r.tot_phrases); l64.has_hocc.resize(r.tot_phrases);
+            l64.pre_sym.resize(r.n_pre_runs); l64.pre_len.resize(r.n_pre_runs);
+        }
+    }
+};
+
+// parks the context's current level (or level slice) and queues its copies into `sink` at the given element offsets.
+// 32-bit device symbols into a 64-bit sink (a wide level followed by a narrower one) go through a widening copy.
+inline void queue_level(const CtxHandle& ctx, FetchPool& pool, LevelSink& sink, uint64_t rank_off, uint64_t pre_off, std::vector<std::unique_ptr<RawBuf<uint32_t>>>& tmp32,
+                        std::vector<std::function<void()>>& after) {
+    grlgpu_level_ptrs_t lp;
+    ctx.check("grlgpu_level_park", grlgpu_level_park(ctx.p, sink.narrow_len ? 4 : 8, &lp));
+    if (!sink.wide) {
+        if (lp.sym_bytes != 4) throw std::runtime_error("a 64-bit level reached the 32-bit sink");
+        pool.enqueue(lp.device, sink.l32.rule_l.data() + rank_off, lp.rule_l, lp.tot * 4);
+        pool.enqueue(lp.device, sink.l32.rule_r.data() + rank_off, lp.rule_r, lp.tot * 4);
+        pool.enqueue(lp.device, sink.l32.has_hocc.data() + rank_off, lp.has_hocc, lp.tot);
+        pool.enqueue(lp.device, sink.l32.pre_sym.data() + pre_off, lp.pre_sym, lp.n_pre * 4);
+        if (sink.narrow_len) pool.enqueue(lp.device, sink.l32.pre_len32.data() + pre_off, lp.pre_len, lp.n_pre * 4);
+        else pool.enqueue(lp.device, sink.l32.pre_len.data() + pre_off, lp.pre_len, lp.n_pre * 8);
+        return;
+    }
+    pool.enqueue(lp.device, sink.l64.has_hocc.data() + rank_off, lp.has_hocc, lp.tot);
+    pool.enqueue(lp.device, sink.l64.pre_len.data() + pre_off, lp.pre_len, lp.n_pre * 8);
+    if (lp.sym_bytes == 8) {
+        pool.enqueue(lp.device, sink.l64.rule_l.data() + rank_off, lp.rule_l, lp.tot * 8);
+        pool.enqueue(lp.device, sink.l64.rule_r.data() + rank_off, lp.rule_r, lp.tot * 8);
+        pool.enqueue(lp.device, sink.l64.pre_sym.data() + pre_off, lp.pre_sym, lp.n_pre * 8);
+        return;
+    }
+    struct W { const void* src; uint64_t n; uint64_t* dst; };
+    for (const W& wv : {W{lp.rule_l, lp.tot, sink.l64.rule_l.data() + rank_off}, W{lp.rule_r, lp.tot, sink.l64.rule_r.data() + rank_off},
+                        W{lp.pre_sym, lp.n_pre, sink.l64.pre_sym.data() + pre_off}}) {
+        tmp32.emplace_back(new RawBuf<uint32_t>(wv.n));
+        uint32_t* t = tmp32.back()->data();
+        pool.enqueue(lp.device, t, wv.src, wv.n * 4);
+        uint64_t* dst = wv.dst;
+        const uint64_t n = wv.n;
+        after.push_back([t, dst, n] { for (uint64_t i = 0; i < n; i++) dst[i] = t[i]; });
+    }
+}
+
+// first wide level: what was collected in 32-bit levels moves to 64-bit symbols
+inline void widen_levels(ParseResult& res) {
+    for (const Level32& s : res.levels32) {
+        Level L;
+        L.alphabet = s.alphabet; L.tot_phrases = s.tot_phrases;
+        L.has_hocc.assign(s.has_hocc.begin(), s.has_hocc.end());
+        if (!s.pre_len32.empty()) L.pre_len.assign(s.pre_len32.begin(), s.pre_len32.end());
+        else L.pre_len.assign(s.pre_len.begin(), s.pre_len.end());
+        L.rule_l.assign(s.rule_l.begin(), s.rule_l.end());
+        L.rule_r.assign(s.rule_r.begin(), s.rule_r.end());
+        L.pre_sym.assign(s.pre_sym.begin(), s.pre_sym.end());
+        res.levels.push_back(std::move(L));
+    }
+    res.levels32.clear();
+    res.wide = true;
+}
+
+// ---------------------------------------------------------------- one GPU
+inline ParseResult gpu_par_phase(const TextSource& src, int sym_bytes, int device, bool verbose, size_t fetch_threads = 4) {
+    ParseResult res;
+    res.comm_kind = "single GPU";
+    CtxHandle ctx(device, 0);
+    res.h2d_ms = load_text(ctx, src, sym_bytes);
+    auto t0 = std::chrono::steady_clock::now();
+    ctx.check("grlgpu_stats", grlgpu_stats(ctx.p, &res.stats));
+    if (verbose) print_stats(res.stats);
+    FetchPool pool(fetch_threads);
+    std::vector<std::unique_ptr<LevelSink>> sinks;
+    std::vector<std::unique_ptr<RawBuf<uint32_t>>> tmp32;
+    std::vector<std::function<void()>> after;
+    for (;;) {
+        grlgpu_round_t r;
+        ctx.check("grlgpu_round", grlgpu_round(ctx.p, &r));
+        RoundDigest dg;
+        dg.tot = r.tot_phrases; dg.n_pre = r.n_pre_runs; dg.parse_len = r.parse_len; dg.n_phrases = r.n_phrases; dg.dict_syms = r.dict_syms;
+        ctx.check("grlgpu_level_checksum", grlgpu_level_checksum(ctx.p, dg.cs));
+        res.digests.push_back(dg);
+        // the copies of the previous level ran while this round computed; release its device arrays, then hand this level over
+        pool.wait_all();
+        ctx.check("grlgpu_fetch_wait", grlgpu_fetch_wait(ctx.p));
+        const bool wide = res.wide || r.sym_bytes == 8;
+        sinks.emplace_back(new LevelSink());
+        sinks.back()->prepare(r, wide);
+        res.wide = wide;
+        queue_level(ctx, pool, *sinks.back(), 0, 0, tmp32, after);
+        if (verbose) print_round(r);
+        res.rounds.push_back(r);
+        if (r.done) {
+            std::vector<unsigned char> raw(r.parse_len * (uint64_t)r.cell_bytes_out);
+            ctx.check("grlgpu_fetch_parse", grlgpu_fetch_parse(ctx.p, raw.data()));
+            res.final_parse.resize(r.parse_len);
+            for (uint64_t i = 0; i < r.parse_len; i++) {
+                uint64_t v = 0;
+                memcpy(&v, raw.data() + i * r.cell_bytes_out, r.cell_bytes_out);
+                res.final_parse[i] = v;
+            }
+            break;
+        }
+    }
+    pool.wait_all();
+    ctx.check("grlgpu_fetch_wait", grlgpu_fetch_wait(ctx.p));
+    for (auto& f : after) f();
+    // levels in round order; a wide level anywhere moves every level to 64-bit symbols
+    bool any_wide = false;
+    for (auto& s : sinks) any_wide = any_wide || s->wide;
+    res.wide = false;
+    for (auto& s : sinks) {
+        if (!s->wide) res.levels32.push_back(std::move(s->l32));
+        else {
+            if (!res.wide) widen_levels(res);
+            res.levels.push_back(std::move(s->l64));
+        }
+    }
+    (void)any_wide;
+    res.par_ms = ms_since(t0);
+    return res;
+}
+
+// ---------------------------------------------------------------- several GPUs: one host thread per rank
+struct HostBarrier {
+    std::mutex m;
+    std::condition_variable cv;
+    int n, arrived = 0;
+    uint64_t gen = 0;
+    bool failed = false;
+    explicit HostBarrier(int n_) : n(n_) {}
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        if (failed) throw std::runtime_error("another rank failed");
+        const uint64_t g = gen;
+        if (++arrived == n) { arrived = 0; gen++; cv.notify_all(); }
+        else cv.wait(lk, [&] { return gen != g || failed; });
+        if (failed) throw std::runtime_error("another rank failed");
+    }
+    void abort() {
+        std::lock_guard<std::mutex> lk(m);
+        failed = true;
+        cv.notify_all();
+    }
+};
+
+enum CommKind { COMM_AUTO = 0, COMM_LOCAL = 1, COMM_NCCL = 2 };
+
+// devices: one entry per rank (a device may repeat: several ranks then share it, and the exchange is the in-process one)
+inline ParseResult gpu_par_phase_mg(const TextSource& src, int sym_bytes, const std::vector<int>& devices, int comm_kind, bool verbose, size_t fetch_threads = 2) {
+    const std::vector<uint64_t> bounds = shard_bounds(src, sym_bytes, (int)devices.size());
+    const int G = (int)bounds.size() - 1;
+    if (G <= 1) return gpu_par_phase(src, sym_bytes, devices.at(0), verbose);
+    bool distinct = true;
+    for (int a = 0; a < G; a++)
+        for (int b = a + 1; b < G; b++) distinct = distinct && devices[(size_t)a] != devices[(size_t)b];
+    if (const char* e = getenv("GRLBWT_COMM")) comm_kind = !strcmp(e, "nccl") ? COMM_NCCL : !strcmp(e, "local") ? COMM_LOCAL : comm_kind;
+    unsigned char nccl_id[128];
+    bool use_nccl = comm_kind == COMM_NCCL || (comm_kind == COMM_AUTO && distinct);
+    if (use_nccl && grlgpu_nccl_unique_id(nccl_id) != GRLGPU_OK) {
+        if (comm_kind == COMM_NCCL) throw GpuError(GRLGPU_ERR_CUDA, "NCCL was requested but is not available");
+        use_nccl = false;
+    }
+    if (use_nccl && !distinct) throw GpuError(GRLGPU_ERR_ARG, "NCCL needs one distinct GPU per rank");
+    grlgpu_local_group* group = nullptr;
+    if (!use_nccl && grlgpu_local_group_create(&group, G) != GRLGPU_OK) throw GpuError(GRLGPU_ERR_ARG, "cannot create the rank group");
+
+    ParseResult res;
+    res.n_ranks = G;
+    HostBarrier bar(G);
+    std::vector<std::string> errors((size_t)G);
+    std::vector<int> err_status((size_t)G, 0);
+    std::vector<std::unique_ptr<LevelSink>> sinks;
+    std::vector<uint64_t> str_off((size_t)G + 1, 0);   // strings before each rank (filled after the stats)
+    std::vector<std::array<uint64_t, 4>> cs_part((size_t)G);
+    std::vector<uint64_t> xbytes((size_t)G, 0), local_strings((size_t)G, 0);
+    std::vector<double> h2d((size_t)G, 0);
+    const uint64_t w = (uint64_t)sym_bytes;
+    const auto t_start = std::chrono::steady_clock::now();
+
+    auto rank_main = [&](int me) {
+        grlgpu_comm* comm = nullptr;
+        try {
+            CtxHandle ctx(devices[(size_t)me], 0);
+            ctx.check("grlgpu_set_peers", grlgpu_set_peers(ctx.p, devices.data(), G));
+            int rc = use_nccl ? grlgpu_comm_create_nccl(&comm, nccl_id, me, G, devices[(size_t)me]) : grlgpu_comm_create_local(&comm, group, me, devices[(size_t)me]);
+            if (rc != GRLGPU_OK) throw GpuError(rc, std::string("creating the exchange layer: ") + grlgpu_strerror(rc));
+            TextSource shard = src;
+            shard.offset = src.offset + bounds[(size_t)me] * w;
+            shard.bytes = (bounds[(size_t)me + 1] - bounds[(size_t)me]) * w;
+            h2d[(size_t)me] = load_text(ctx, shard, sym_bytes);
+            grlgpu_stats_t gs;
+            ctx.check("grlgpu_mg_stats", grlgpu_mg_stats(ctx.p, comm, &gs));
+            {
+                grlgpu_stats_t ls;
+                ctx.check("grlgpu_stats", grlgpu_stats(ctx.p, &ls));
+                local_strings[(size_t)me] = ls.n_strings;
+            }
+            if (me == 0) {
+                res.stats = gs;
+                if (verbose) print_stats(gs);
+                char kind[128];
+                grlgpu_comm_info(comm, nullptr, nullptr, nullptr, kind, sizeof(kind));
+                res.comm_kind = kind;
+            }
+            bar.wait();
+            if (me == 0) {
+                for (int p = 0; p < G; p++) str_off[(size_t)p + 1] = str_off[(size_t)p] + local_strings[(size_t)p];
+                res.final_parse.resize(gs.n_strings);
+            }
+            FetchPool pool(fetch_threads);
+            std::vector<std::unique_ptr<RawBuf<uint32_t>>> tmp32;
+            std::vector<std::function<void()>> after;
+            for (;;) {
+                grlgpu_round_t r;
+                ctx.check("grlgpu_mg_round", grlgpu_mg_round(ctx.p, comm, &r));
+                grlgpu_slice_t sl;
+                ctx.check("grlgpu_mg_slice_info", grlgpu_mg_slice_info(ctx.p, &sl));
+                ctx.check("grlgpu_mg_slice_checksum", grlgpu_mg_slice_checksum(ctx.p, cs_part[(size_t)me].data()));
+                xbytes[(size_t)me] += sl.exchange_bytes;
+                pool.wait_all();  // the previous level's copies ran during this round
+                ctx.check("grlgpu_fetch_wait", grlgpu_fetch_wait(ctx.p));
+                bar.wait();
+                if (me == 0) {    // the level's host arrays, sized from the global counts every rank was told
+                    RoundDigest dg;
+                    dg.tot = r.tot_phrases; dg.n_pre = r.n_pre_runs; dg.parse_len = r.parse_len; dg.n_phrases = r.n_phrases; dg.dict_syms = r.dict_syms;
+                    for (int p = 0; p < G; p++)
+                        for (int k = 0; k < 4; k++) dg.cs[k] += cs_part[(size_t)p][(size_t)k];
+                    res.digests.push_back(dg);
+                    res.wide = res.wide || r.sym_bytes == 8;
+                    sinks.emplace_back(new LevelSink());
+                    sinks.back()->prepare(r, res.wide);
+                    if (verbose) print_round(r);
+                    res.rounds.push_back(r);
+                }
+                bar.wait();
+                queue_level(ctx, pool, *sinks.back(), sl.rank_base, sl.pre_first, tmp32, after);
+                if (r.done) {
+                    std::vector<unsigned char> raw(sl.parse_len_local * (uint64_t)r.cell_bytes_out + 8);
+                    ctx.check("grlgpu_fetch_parse", grlgpu_fetch_parse(ctx.p, raw.data()));
+                    if (sl.parse_len_local != local_strings[(size_t)me]) throw std::runtime_error("the final parse of a rank is not one cell per string");
+                    for (uint64_t i = 0; i < sl.parse_len_local; i++) {
+                        uint64_t v = 0;
+                        memcpy(&v, raw.data() + i * r.cell_bytes_out, r.cell_bytes_out);
+                        res.final_parse[str_off[(size_t)me] + i] = v;
+                    }
+                    break;
+                }
+            }
+            pool.wait_all();
+            ctx.check("grlgpu_fetch_wait", grlgpu_fetch_wait(ctx.p));
+            for (auto& f : after) f();
+            bar.wait();
+            grlgpu_comm_destroy(comm);
+            comm = nullptr;
+        } catch (const GpuError& e) {
+            errors[(size_t)me] = e.what();
+            err_status[(size_t)me] = e.status;
+            bar.abort();
+            if (group) grlgpu_local_group_abort(group);
+            if (comm) grlgpu_comm_destroy(comm);
+        } catch (const std::exception& e) {
+            errors[(size_t)me] = e.what();
+            err_status[(size_t)me] = -100;
+            bar.abort();
+            if (group) grlgpu_local_group_abort(group);
+            if (comm) grlgpu_comm_destroy(comm);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int r = 0; r < G; r++) th.emplace_back(rank_main, r);
+    for (auto& t : th) t.join();
+    if (group) grlgpu_local_group_destroy(group);
+    // the first real failure (not the "another rank failed" echoes it caused)
+    int first_bad = -1;
+    for (int r = 0; r < G; r++)
+        if (err_status[(size_t)r] && (first_bad < 0 || (errors[(size_t)first_bad].find("another rank failed") != std::string::npos &&
+                                                         errors[(size_t)r].find("another rank failed") == std::string::npos)))
+            first_bad = r;
+    if (first_bad >= 0) throw GpuError(err_status[(size_t)first_bad], "rank " + std::to_string(first_bad) + ": " + errors[(size_t)first_bad]);
+    res.wide = false;
+    for (auto& s : sinks) {
+        if (!s->wide) res.levels32.push_back(std::move(s->l32));
+        else {
+            if (!res.wide) widen_levels(res);
+            res.levels.push_back(std::move(s->l64));
+        }
+    }
+    for (int r = 0; r < G; r++) { res.exchange_bytes += xbytes[(size_t)r]; res.h2d_ms = std::max(res.h2d_ms, h2d[(size_t)r]); }
+    res.par_ms = ms_since(t_start) - res.h2d_ms;
+    return res;
+}
+
+}  // namespace grlbwt

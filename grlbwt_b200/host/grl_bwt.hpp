@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/grlgpu.h"
+#include "gpu_par_phase.hpp"
 #include "ind_phase.hpp"
 #include "ind_phase_mt.hpp"
 #include "rl_bwt_io.hpp"
@@ -48,131 +49,6 @@ struct tmp_workspace {
 
 namespace grlbwt {
 
-struct ParseResult {
-    grlgpu_stats_t stats{};
-    std::vector<Level> levels;        // 64-bit symbols: only filled when some level needs them
-    std::vector<Level32> levels32;    // 32-bit symbols (the usual case), consumed by the multi-threaded induction
-    bool wide = false;
-    std::vector<grlgpu_round_t> rounds;
-    std::vector<uint64_t> final_parse;  // one cell per string, cells = rank<<1|rep
-    double h2d_ms = 0, par_ms = 0;
-};
-
-struct GpuError : std::runtime_error {
-    int status;
-    GpuError(int st, const std::string& m) : std::runtime_error(m), status(st) {}
-};
-
-inline double ms_since(std::chrono::steady_clock::time_point t0) {
-    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-}
-
-// The parse phase on the device: rounds until every string is one metasymbol
-// (replaces exact_algo::par_phase<sym_type>, exact_par_phase.cpp:285-372).
-inline ParseResult gpu_par_phase(const void* text, uint64_t n_syms, int sym_bytes, int device, bool verbose) {
-    ParseResult res;
-    grlgpu_ctx* ctx = nullptr;
-    int rc = grlgpu_create(&ctx, device, 0);
-    if (rc != GRLGPU_OK) throw GpuError(rc, std::string("grlgpu_create: ") + grlgpu_strerror(rc));
-    auto fail = [&](const char* what, int st) {
-        std::string m = std::string(what) + ": " + grlgpu_strerror(st) + " (" + grlgpu_last_error(ctx) + ")";
-        grlgpu_destroy(ctx);
-        throw GpuError(st, m);
-    };
-    auto t0 = std::chrono::steady_clock::now();
-    if ((rc = grlgpu_set_text(ctx, text, n_syms, sym_bytes)) != GRLGPU_OK) fail("grlgpu_set_text", rc);
-    res.h2d_ms = ms_since(t0);
-    t0 = std::chrono::steady_clock::now();
-    if ((rc = grlgpu_stats(ctx, &res.stats)) != GRLGPU_OK) fail("grlgpu_stats", rc);
-    if (verbose) {
-        std::cout << "Stats: " << std::endl;
-        std::cout << "  Smallest symbol               : " << res.stats.min_sym << std::endl;
-        std::cout << "  Greatest symbol               : " << res.stats.max_sym << std::endl;
-        std::cout << "  Number of symbols in the file : " << res.stats.n_syms << std::endl;
-        std::cout << "  Number of strings             : " << res.stats.n_strings << std::endl;
-        std::cout << "Parsing the text:    " << std::endl;
-    }
-    for (;;) {
-        grlgpu_round_t r;
-        if ((rc = grlgpu_round(ctx, &r)) != GRLGPU_OK) fail("grlgpu_round", rc);
-        if (r.sym_bytes == 8 && !res.wide) {  // first wide level: move what was collected so far to 64-bit symbols
-            res.wide = true;
-            for (const Level32& s : res.levels32) {
-                Level L;
-                L.alphabet = s.alphabet; L.tot_phrases = s.tot_phrases; L.has_hocc = s.has_hocc; L.pre_len = s.pre_len;
-                if (!s.pre_len32.empty()) L.pre_len.assign(s.pre_len32.begin(), s.pre_len32.end());
-                L.rule_l.assign(s.rule_l.begin(), s.rule_l.end()); L.rule_r.assign(s.rule_r.begin(), s.rule_r.end());
-                L.pre_sym.assign(s.pre_sym.begin(), s.pre_sym.end());
-                res.levels.push_back(std::move(L));
-            }
-            res.levels32.clear();
-        }
-        if (!res.wide) {
-            Level32 L;
-            L.alphabet = r.alphabet;
-            L.tot_phrases = r.tot_phrases;
-            L.has_hocc.resize(r.tot_phrases);
-            L.rule_l.resize(r.tot_phrases);
-            L.rule_r.resize(r.tot_phrases);
-            L.pre_sym.resize(r.n_pre_runs);
-            if (r.n_in + r.parse_len < (1ull << 32)) {  // run lengths fit 32 bits: 4 bytes less per run over PCIe and in memory
-                L.pre_len32.resize(r.n_pre_runs);
-                rc = grlgpu_fetch_level32(ctx, L.rule_l.data(), L.rule_r.data(), L.has_hocc.data(), L.pre_sym.data(), L.pre_len32.data(), 0);
-            } else {
-                L.pre_len.resize(r.n_pre_runs);
-                rc = grlgpu_fetch_level(ctx, L.rule_l.data(), L.rule_r.data(), L.has_hocc.data(), L.pre_sym.data(), L.pre_len.data());
-            }
-            if (rc != GRLGPU_OK) fail("grlgpu_fetch_level", rc);
-            res.levels32.push_back(std::move(L));
-        } else {
-            Level L;
-            L.alphabet = r.alphabet;
-            L.tot_phrases = r.tot_phrases;
-            L.has_hocc.resize(r.tot_phrases);
-            L.pre_len.resize(r.n_pre_runs);
-            L.rule_l.resize(r.tot_phrases);
-            L.rule_r.resize(r.tot_phrases);
-            L.pre_sym.resize(r.n_pre_runs);
-            if (r.sym_bytes == 8) {
-                rc = grlgpu_fetch_level(ctx, L.rule_l.data(), L.rule_r.data(), L.has_hocc.data(), L.pre_sym.data(), L.pre_len.data());
-                if (rc != GRLGPU_OK) fail("grlgpu_fetch_level", rc);
-            } else {
-                std::vector<uint32_t> l32(r.tot_phrases), r32(r.tot_phrases), p32(r.n_pre_runs);
-                rc = grlgpu_fetch_level(ctx, l32.data(), r32.data(), L.has_hocc.data(), p32.data(), L.pre_len.data());
-                if (rc != GRLGPU_OK) fail("grlgpu_fetch_level", rc);
-                for (uint64_t i = 0; i < r.tot_phrases; i++) { L.rule_l[i] = l32[i]; L.rule_r[i] = r32[i]; }
-                for (uint64_t i = 0; i < r.n_pre_runs; i++) L.pre_sym[i] = p32[i];
-            }
-            res.levels.push_back(std::move(L));
-        }
-        if (verbose) {
-            std::cout << "  Parsing round " << r.round << std::endl;
-            std::cout << "    Stats:" << std::endl;
-            std::cout << "      Parsing phrases:                  " << r.n_phrases << std::endl;
-            std::cout << "      Number of symbols in the phrases: " << r.dict_syms << std::endl;
-            std::cout << "      Number of unsolved BWT blocks:    " << r.tot_phrases << std::endl;
-            std::cout << "      Parse size:                       " << r.parse_len << std::endl;
-            std::cout << "      Device time (ms):                 " << r.device_ms << " (text " << r.text_pass_ms << ", dictionary " << r.dict_ms
-                      << ", rewrite " << r.rewrite_ms << ")" << std::endl;
-        }
-        res.rounds.push_back(r);
-        if (r.done) {
-            res.final_parse.resize(r.parse_len);
-            std::vector<unsigned char> raw(r.parse_len * (uint64_t)r.cell_bytes_out);
-            if ((rc = grlgpu_fetch_parse(ctx, raw.data())) != GRLGPU_OK) fail("grlgpu_fetch_parse", rc);
-            for (uint64_t i = 0; i < r.parse_len; i++) {
-                uint64_t v = 0;
-                memcpy(&v, raw.data() + i * r.cell_bytes_out, r.cell_bytes_out);
-                res.final_parse[i] = v;
-            }
-            break;
-        }
-    }
-    res.par_ms = ms_since(t0);
-    grlgpu_destroy(ctx);
-    return res;
-}
-
 struct BwtResult {
     RunList runs;        // 64-bit symbols (wide alphabets)
     RunArr runs32;       // 32-bit symbols (the usual case), filled when narrow
@@ -187,9 +63,10 @@ struct BwtResult {
     double ind_ms = 0;
 };
 
-inline BwtResult build_bwt(const void* text, uint64_t n_syms, int sym_bytes, int device, size_t n_threads, bool verbose) {
+// devices: one entry per rank; one entry = the single-GPU path. comm_kind: CommKind of gpu_par_phase.hpp
+inline BwtResult build_bwt(const TextSource& src, int sym_bytes, const std::vector<int>& devices, int comm_kind, size_t n_threads, bool verbose) {
     BwtResult out;
-    out.parse = gpu_par_phase(text, n_syms, sym_bytes, device, verbose);
+    out.parse = devices.size() > 1 ? gpu_par_phase_mg(src, sym_bytes, devices, comm_kind, verbose) : gpu_par_phase(src, sym_bytes, devices.empty() ? 0 : devices[0], verbose);
     auto t0 = std::chrono::steady_clock::now();
     if (verbose) std::cout << "Inferring the BWT" << std::endl;
     if (out.parse.wide) out.runs = ind_phase<uint64_t>(out.parse.levels, out.parse.final_parse.data(), out.parse.final_parse.size());
@@ -204,21 +81,25 @@ inline BwtResult build_bwt(const void* text, uint64_t n_syms, int sym_bytes, int
     out.fb = int_ceil((uint64_t)sym_width(out.parse.stats.max_sym_freq), 8);
     return out;
 }
+inline BwtResult build_bwt(const void* text, uint64_t n_syms, int sym_bytes, int device, size_t n_threads, bool verbose) {
+    TextSource src;
+    src.mem = (const unsigned char*)text;
+    src.bytes = n_syms * (uint64_t)sym_bytes;
+    return build_bwt(src, sym_bytes, std::vector<int>{device}, COMM_AUTO, n_threads, verbose);
+}
 
-inline std::vector<unsigned char> read_whole_file(const std::string& path) {
-    std::ifstream ifs(path, std::ios::binary | std::ios::ate);
-    if (!ifs) throw std::runtime_error("cannot open " + path);
-    const std::streamsize sz = ifs.tellg();
-    ifs.seekg(0);
-    std::vector<unsigned char> buf((size_t)sz);
-    if (sz && !ifs.read((char*)buf.data(), sz)) throw std::runtime_error("cannot read " + path);
-    return buf;
+inline uint64_t file_size_of(const std::string& path) {
+    std::error_code ec;
+    const auto sz = std::filesystem::file_size(path, ec);
+    if (ec) throw std::runtime_error("cannot open " + path);
+    return (uint64_t)sz;
 }
 
 }  // namespace grlbwt
 
 template <class sym_type, bool opt_bwt>
-void grl_bwt_algo(std::string& i_file, std::string& o_file, tmp_workspace& tmp_ws, size_t n_threads, float hbuff_frac, uint8_t b_p_r, int device = 0) {
+void grl_bwt_algo(std::string& i_file, std::string& o_file, tmp_workspace& tmp_ws, size_t n_threads, float hbuff_frac, uint8_t b_p_r,
+                  const std::vector<int>& devices = std::vector<int>{0}, int comm_kind = 0) {
     (void)hbuff_frac;  // -f bounded the CPU hash buffers of the reference; the device table needs no such cap
     (void)b_p_r;       // -b only caps in-RAM run-length bytes in the reference; the output does not depend on it
     if constexpr (opt_bwt) {
@@ -226,14 +107,16 @@ void grl_bwt_algo(std::string& i_file, std::string& o_file, tmp_workspace& tmp_w
         exit(0);
     }
     std::cout << "Reading the file" << std::endl;
-    std::vector<unsigned char> buf = grlbwt::read_whole_file(i_file);
-    if (buf.empty() || buf.size() % sizeof(sym_type)) {
+    grlbwt::TextSource src;
+    src.file = i_file;
+    src.bytes = grlbwt::file_size_of(i_file);  // streamed to the device(s) through pinned staging buffers, never held whole in host memory
+    if (src.bytes == 0 || src.bytes % sizeof(sym_type)) {
         std::cout << "Error: the file is ill formed" << std::endl;
         exit(1);
     }
     grlbwt::BwtResult res;
     try {
-        res = grlbwt::build_bwt(buf.data(), buf.size() / sizeof(sym_type), (int)sizeof(sym_type), device, n_threads, true);
+        res = grlbwt::build_bwt(src, (int)sizeof(sym_type), devices, comm_kind, n_threads, true);
     } catch (const grlbwt::GpuError& e) {
         if (e.status == GRLGPU_ERR_ILL_FORMED) {
             std::cout << "Error: the file is ill formed" << std::endl;  // utils.cpp:177-180

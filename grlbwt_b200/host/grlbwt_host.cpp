@@ -9,34 +9,45 @@
 #include "grl_bwt.hpp"
 
 static thread_local std::string g_last_error;
+static thread_local std::vector<grlbwt::RoundDigest> g_last_digests;
+static thread_local uint64_t g_last_exchange_bytes = 0;
+static thread_local std::string g_last_comm;
+
+static int fill_result(grlbwt::BwtResult& r, grlbwt_result_t* out) {
+    const size_t nr = r.n_runs();
+    out->n_runs = nr;
+    out->sb = r.sb;
+    out->fb = r.fb;
+    out->syms = (uint64_t*)malloc((nr ? nr : 1) * sizeof(uint64_t));
+    out->lens = (uint64_t*)malloc((nr ? nr : 1) * sizeof(uint64_t));
+    if (!out->syms || !out->lens) { free(out->syms); free(out->lens); out->syms = out->lens = nullptr; g_last_error = "out of host memory"; return -100; }
+    if (r.narrow) {
+        for (size_t k = 0; k < nr; k++) out->syms[k] = r.runs32.sym[k];
+        memcpy(out->lens, r.runs32.len.data(), nr * sizeof(uint64_t));
+    } else {
+        memcpy(out->syms, r.runs.sym.data(), nr * sizeof(uint64_t));
+        memcpy(out->lens, r.runs.len.data(), nr * sizeof(uint64_t));
+    }
+    out->n_rounds = r.parse.rounds.size();
+    out->h2d_ms = r.parse.h2d_ms;
+    out->par_phase_ms = r.parse.par_ms;
+    out->ind_phase_ms = r.ind_ms;
+    for (const auto& rd : r.parse.rounds) { out->device_ms += rd.device_ms; out->algorithmic_bytes += rd.algorithmic_bytes; }
+    g_last_digests = r.parse.digests;
+    g_last_exchange_bytes = r.parse.exchange_bytes;
+    g_last_comm = r.parse.comm_kind;
+    return GRLGPU_OK;
+}
 
 extern "C" {
 
 int grlbwt_build(const void* text, uint64_t n_syms, int sym_bytes, int device, int n_threads, int verbose, grlbwt_result_t* out) {
     if (!text || !out || n_syms == 0) return GRLGPU_ERR_ARG;
+    if (!(sym_bytes == 1 || sym_bytes == 2 || sym_bytes == 4 || sym_bytes == 8)) return GRLGPU_ERR_ARG;
     memset(out, 0, sizeof(*out));
     try {
         grlbwt::BwtResult r = grlbwt::build_bwt(text, n_syms, sym_bytes, device, (size_t)(n_threads > 0 ? n_threads : 1), verbose != 0);
-        const size_t nr = r.n_runs();
-        out->n_runs = nr;
-        out->sb = r.sb;
-        out->fb = r.fb;
-        out->syms = (uint64_t*)malloc((nr ? nr : 1) * sizeof(uint64_t));
-        out->lens = (uint64_t*)malloc((nr ? nr : 1) * sizeof(uint64_t));
-        if (!out->syms || !out->lens) { free(out->syms); free(out->lens); g_last_error = "out of host memory"; return -100; }
-        if (r.narrow) {
-            for (size_t k = 0; k < nr; k++) out->syms[k] = r.runs32.sym[k];
-            memcpy(out->lens, r.runs32.len.data(), nr * sizeof(uint64_t));
-        } else {
-            memcpy(out->syms, r.runs.sym.data(), nr * sizeof(uint64_t));
-            memcpy(out->lens, r.runs.len.data(), nr * sizeof(uint64_t));
-        }
-        out->n_rounds = r.parse.rounds.size();
-        out->h2d_ms = r.parse.h2d_ms;
-        out->par_phase_ms = r.parse.par_ms;
-        out->ind_phase_ms = r.ind_ms;
-        for (const auto& rd : r.parse.rounds) { out->device_ms += rd.device_ms; out->algorithmic_bytes += rd.algorithmic_bytes; }
-        return GRLGPU_OK;
+        return fill_result(r, out);
     } catch (const grlbwt::GpuError& e) {
         g_last_error = e.what();
         return e.status;
@@ -45,6 +56,39 @@ int grlbwt_build(const void* text, uint64_t n_syms, int sym_bytes, int device, i
         return -100;
     }
 }
+
+int grlbwt_build_mg(const void* text, uint64_t n_syms, int sym_bytes, const int* devices, int n_ranks, int n_threads, int comm_kind, int verbose,
+                    grlbwt_result_t* out) {
+    if (!text || !out || n_syms == 0 || !devices || n_ranks < 1 || n_ranks > 31) return GRLGPU_ERR_ARG;
+    if (!(sym_bytes == 1 || sym_bytes == 2 || sym_bytes == 4 || sym_bytes == 8)) return GRLGPU_ERR_ARG;
+    memset(out, 0, sizeof(*out));
+    try {
+        grlbwt::TextSource src;
+        src.mem = (const unsigned char*)text;
+        src.bytes = n_syms * (uint64_t)sym_bytes;
+        grlbwt::BwtResult r = grlbwt::build_bwt(src, sym_bytes, std::vector<int>(devices, devices + n_ranks), comm_kind, (size_t)(n_threads > 0 ? n_threads : 1), verbose != 0);
+        return fill_result(r, out);
+    } catch (const grlbwt::GpuError& e) {
+        g_last_error = e.what();
+        return e.status;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return -100;
+    }
+}
+
+uint64_t grlbwt_last_digests(uint64_t* out, uint64_t cap_rounds) {
+    const uint64_t n = g_last_digests.size();
+    for (uint64_t i = 0; i < n && i < cap_rounds && out; i++) {
+        const grlbwt::RoundDigest& d = g_last_digests[i];
+        uint64_t* o = out + i * 9;
+        o[0] = d.tot; o[1] = d.n_pre; o[2] = d.parse_len; o[3] = d.n_phrases; o[4] = d.dict_syms;
+        for (int k = 0; k < 4; k++) o[5 + k] = d.cs[k];
+    }
+    return n;
+}
+uint64_t grlbwt_last_exchange_bytes(void) { return g_last_exchange_bytes; }
+const char* grlbwt_last_comm(void) { return g_last_comm.c_str(); }
 
 void grlbwt_free_result(grlbwt_result_t* r) {
     if (!r) return;
@@ -56,10 +100,13 @@ void grlbwt_free_result(grlbwt_result_t* r) {
 
 int grlbwt_build_file(const char* input_file, const char* output_file, int sym_bytes, int device, int n_threads, int verbose) {
     if (!input_file || !output_file) return GRLGPU_ERR_ARG;
+    if (!(sym_bytes == 1 || sym_bytes == 2 || sym_bytes == 4 || sym_bytes == 8)) return GRLGPU_ERR_ARG;
     try {
-        std::vector<unsigned char> buf = grlbwt::read_whole_file(input_file);
-        if (buf.empty() || buf.size() % (size_t)sym_bytes) return GRLGPU_ERR_ILL_FORMED;
-        grlbwt::BwtResult r = grlbwt::build_bwt(buf.data(), buf.size() / (size_t)sym_bytes, sym_bytes, device, (size_t)(n_threads > 0 ? n_threads : 1), verbose != 0);
+        grlbwt::TextSource src;
+        src.file = input_file;
+        src.bytes = grlbwt::file_size_of(input_file);
+        if (src.bytes == 0 || src.bytes % (uint64_t)sym_bytes) return GRLGPU_ERR_ILL_FORMED;
+        grlbwt::BwtResult r = grlbwt::build_bwt(src, sym_bytes, std::vector<int>{device}, grlbwt::COMM_AUTO, (size_t)(n_threads > 0 ? n_threads : 1), verbose != 0);
         r.write(output_file);
         return GRLGPU_OK;
     } catch (const grlbwt::GpuError& e) {
@@ -86,6 +133,23 @@ int grlbwt_selftest_write(const char* path, const uint64_t* syms, const uint64_t
 }
 
 const char* grlbwt_last_error(void) { return g_last_error.c_str(); }
+
+// the shard boundaries a multi-GPU run would use (CPU-only self test of gpu_par_phase.hpp: shard_bounds)
+int grlbwt_selftest_shard_bounds(const void* text, uint64_t n_syms, int sym_bytes, int n_ranks, uint64_t* bounds_out, int* n_shards) {
+    try {
+        if (!text || !bounds_out || !n_shards || n_syms == 0 || n_ranks < 1) throw std::runtime_error("bad arguments");
+        grlbwt::TextSource src;
+        src.mem = (const unsigned char*)text;
+        src.bytes = n_syms * (uint64_t)sym_bytes;
+        const std::vector<uint64_t> b = grlbwt::shard_bounds(src, sym_bytes, n_ranks);
+        for (size_t i = 0; i < b.size(); i++) bounds_out[i] = b[i];
+        *n_shards = (int)b.size() - 1;
+        return 0;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return -100;
+    }
+}
 
 // host induction alone, from caller-provided level artefacts (CPU-only self test of ind_phase.hpp)
 int grlbwt_selftest_induce(int n_levels, const uint64_t* alphabet, const uint64_t* tot, const uint64_t* const* rule_l, const uint64_t* const* rule_r,

@@ -30,16 +30,6 @@
 
 namespace grlbwt {
 
-struct Level32 {
-    uint64_t alphabet = 0, tot_phrases = 0;
-    std::vector<uint32_t> rule_l, rule_r;
-    std::vector<uint8_t> has_hocc;
-    std::vector<uint32_t> pre_sym;
-    std::vector<uint64_t> pre_len;    // run lengths, 64-bit ...
-    std::vector<uint32_t> pre_len32;  // ... or 32-bit when the level came through grlgpu_fetch_level32 (one of the two is empty)
-    inline uint64_t len(size_t i) const { return pre_len32.empty() ? pre_len[i] : (uint64_t)pre_len32[i]; }
-};
-
 // uninitialised array: pages are first touched by the worker threads that fill them, not zeroed serially
 template <class T>
 struct RawBuf {
@@ -69,6 +59,27 @@ struct RawBuf {
     T* data() { return p; }
     const T* data() const { return p; }
     size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    void resize(size_t count) { alloc(count); }  // contents are NOT preserved and NOT initialised
+    const T* begin() const { return p; }
+    const T* end() const { return p + n; }
+    template <class It>
+    void assign(It first, It last) {
+        alloc((size_t)(last - first));
+        size_t i = 0;
+        for (It it = first; it != last; ++it) p[i++] = (T)*it;
+    }
+};
+
+struct Level32 {
+    uint64_t alphabet = 0, tot_phrases = 0;
+    // uninitialised buffers (no serial zero-fill of GBs before the device copies land in them)
+    RawBuf<uint32_t> rule_l, rule_r;
+    RawBuf<uint8_t> has_hocc;
+    RawBuf<uint32_t> pre_sym;
+    RawBuf<uint64_t> pre_len;    // run lengths, 64-bit ...
+    RawBuf<uint32_t> pre_len32;  // ... or 32-bit when the level's lengths fit (one of the two is empty)
+    inline uint64_t len(size_t i) const { return pre_len32.empty() ? pre_len[i] : (uint64_t)pre_len32[i]; }
 };
 
 struct Runs32 {
@@ -97,6 +108,7 @@ inline void parallel_chunks(size_t n_threads, size_t n_items, F&& fn, size_t min
     const size_t per = (n_items + n_threads - 1) / n_threads;
     for (size_t t = 0; t < n_threads; t++) {
         const size_t b = std::min(n_items, t * per), e = std::min(n_items, b + per);
+        if (b == e) break;  // chunks past the end are empty: no thread, so per-chunk state is only touched by chunks that exist
         th.emplace_back([&fn, t, b, e] { fn(t, b, e); });
     }
     for (auto& x : th) x.join();
@@ -108,18 +120,15 @@ inline void parallel_prefix(size_t n_threads, size_t n, GetT&& get, RawBuf<uint6
     out.alloc(n + 1);
     const size_t T = (n_threads <= 1 || n < 4096) ? 1 : n_threads;
     std::vector<uint64_t> part(T + 1, 0);
-    const size_t per = (n + T - 1) / T;
-    parallel_chunks(T, n, [&](size_t t, size_t b, size_t e) {
+    parallel_chunks(T, n, [&](size_t t, size_t b, size_t e) {  // partials indexed by the chunk id the scheduler hands out
         uint64_t s = 0;
         for (size_t i = b; i < e; i++) s += get(i);
-        part[(T == 1 ? 0 : b / per) + 1] = s;
-        (void)t;
+        part[t + 1] = s;
     });
     for (size_t t = 0; t < T; t++) part[t + 1] += part[t];
     parallel_chunks(T, n, [&](size_t t, size_t b, size_t e) {
-        uint64_t s = part[T == 1 ? 0 : b / per];
+        uint64_t s = part[t];
         for (size_t i = b; i < e; i++) { out[i] = s; s += get(i); }
-        (void)t;
     });
     out[n] = part[T];
 }
@@ -142,21 +151,20 @@ inline void radix_sort_tuples(size_t n_threads, RawBuf<HTuple>& a, uint64_t max_
     // cache lines per thread in each scatter)
     const int n_pass = std::max(1, (key_bits + 10) / 11), BITS = std::max(1, (key_bits + n_pass - 1) / n_pass), NB = 1 << BITS;
     const size_t T = (n_threads <= 1 || n < (1u << 16)) ? 1 : n_threads;
-    const size_t per = (n + T - 1) / T;
     std::vector<uint64_t> hist(T * NB);
     HTuple* src = a.data();
     HTuple* dst = b.data();
     for (int shift = 0; shift < key_bits; shift += BITS) {
         std::fill(hist.begin(), hist.end(), 0);
-        parallel_chunks(T, n, [&](size_t, size_t bg, size_t en) {
-            uint64_t* h = hist.data() + (T == 1 ? 0 : bg / per) * NB;
+        parallel_chunks(T, n, [&](size_t c, size_t bg, size_t en) {
+            uint64_t* h = hist.data() + c * NB;
             for (size_t i = bg; i < en; i++) h[(src[i].g >> shift) & (NB - 1)]++;
         });
         uint64_t acc = 0;
         for (int d = 0; d < NB; d++)
             for (size_t t = 0; t < T; t++) { const uint64_t c = hist[t * NB + d]; hist[t * NB + d] = acc; acc += c; }
-        parallel_chunks(T, n, [&](size_t, size_t bg, size_t en) {
-            uint64_t* h = hist.data() + (T == 1 ? 0 : bg / per) * NB;
+        parallel_chunks(T, n, [&](size_t c, size_t bg, size_t en) {
+            uint64_t* h = hist.data() + c * NB;
             for (size_t i = bg; i < en; i++) dst[h[(src[i].g >> shift) & (NB - 1)]++] = src[i];
         });
         std::swap(src, dst);
@@ -244,17 +252,14 @@ inline RunArr induce_level_t(RunArr& bwt, const Level32& L, size_t n_threads) {
         cum_h.alloc(n_tuples + 1);
         cum_hb.alloc(n_tuples + 1);
         const size_t Tp = (T <= 1 || n_tuples < 4096) ? 1 : T;
-        const size_t per = (n_tuples + Tp - 1) / Tp;
         std::vector<uint64_t> ph(Tp + 1, 0), pb(Tp + 1, 0);
-        parallel_chunks(Tp, n_tuples, [&](size_t, size_t b, size_t e) {
+        parallel_chunks(Tp, n_tuples, [&](size_t c, size_t b, size_t e) {
             uint64_t sh = 0, sb = 0;
             for (size_t k = b; k < e; k++) { sh += hocc[k].f; sb += hocc[k].l == FROM_BWT32 ? hocc[k].f : 0; }
-            const size_t c = Tp == 1 ? 0 : b / per;
             ph[c + 1] = sh; pb[c + 1] = sb;
         });
         for (size_t t = 0; t < Tp; t++) { ph[t + 1] += ph[t]; pb[t + 1] += pb[t]; }
-        parallel_chunks(Tp, n_tuples, [&](size_t, size_t b, size_t e) {
-            const size_t c = Tp == 1 ? 0 : b / per;
+        parallel_chunks(Tp, n_tuples, [&](size_t c, size_t b, size_t e) {
             uint64_t sh = ph[c], sb = pb[c];
             for (size_t k = b; k < e; k++) {
                 cum_h[k] = sh; cum_hb[k] = sb;

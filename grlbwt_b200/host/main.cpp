@@ -7,6 +7,7 @@
 #include <filesystem>
 #include <iostream>
 #include <string>
+#include <vector>
 
 #include "grl_bwt.hpp"
 
@@ -17,7 +18,8 @@ struct arguments {
     float hbuff_frac = 0.15f;
     bool ver = false;
     uint8_t alph_bytes = 1;
-    int device = 0;
+    std::vector<int> devices{0};   // one rank per entry
+    int comm_kind = 0;
     std::string version = "v1.0.1 alpha (B200 parse phase)";
 };
 
@@ -34,7 +36,9 @@ static void usage(const char* prog) {
               << "  -f,--hbuff             Hashing step will use at most INPUT_SIZE*f bytes. O means no limit (def. 0.5)\n"
               << "  -b,--run-len-bytes     Max. number of bytes to encode the run lengths in the recursive BWTs (def. 1)\n"
               << "  -T,--tmp               Temporary folder (def. /tmp/grl.bwt.xxxx)\n"
-              << "  -g,--gpu               CUDA device that runs the parse phase (def. 0)\n"
+              << "  -g,--gpu               CUDA device(s) that run the parse phase: one rank per entry of a comma list (def. 0)\n"
+              << "  --gpus                 Number of GPUs: ranks on devices 0..N-1 (shards of whole strings, NCCL exchange)\n"
+              << "  --comm                 Exchange between the ranks: auto (def.), nccl, local (in-process peer copies)\n"
               << "  -v,--version           Print the software version and exit\n";
 }
 
@@ -70,7 +74,27 @@ static bool parse_args(int argc, char** argv, arguments& a) {
             } else if (s == "-T" || s == "--tmp") {
                 a.tmp_dir = value(s);
                 if (!std::filesystem::is_directory(a.tmp_dir)) bad("--tmp: Directory does not exist: " + a.tmp_dir, 105);
-            } else if (s == "-g" || s == "--gpu") a.device = std::stoi(value(s));
+            } else if (s == "-g" || s == "--gpu") {
+                const std::string v = value(s);
+                a.devices.clear();
+                size_t p0 = 0;
+                while (p0 <= v.size()) {
+                    const size_t p1 = v.find(',', p0);
+                    a.devices.push_back(std::stoi(v.substr(p0, p1 == std::string::npos ? std::string::npos : p1 - p0)));
+                    if (p1 == std::string::npos) break;
+                    p0 = p1 + 1;
+                }
+                if (a.devices.empty() || a.devices.size() > 31) bad("--gpu: between 1 and 31 devices", 105);
+            } else if (s == "--gpus") {
+                const int n = std::stoi(value(s));
+                if (n < 1 || n > 31) bad("--gpus: Value " + std::to_string(n) + " not in range 1 to 31", 105);
+                a.devices.clear();
+                for (int d = 0; d < n; d++) a.devices.push_back(d);
+            } else if (s == "--comm") {
+                const std::string v = value(s);
+                if (v == "auto") a.comm_kind = 0; else if (v == "local") a.comm_kind = 1; else if (v == "nccl") a.comm_kind = 2;
+                else bad("--comm: " + v + " is not one of auto, nccl, local", 105);
+            }
             else if (!s.empty() && s[0] == '-' && s.size() > 1) bad("The following argument was not expected: " + s, 109);
             else {
                 if (have_text) bad("The following argument was not expected: " + s, 109);
@@ -94,7 +118,7 @@ static void run_int(std::string input_collection, arguments& args) {
     tmp_workspace tmp_ws(args.tmp_dir, true, "grl.bwt");
     std::cout << "Temporary folder: " << tmp_ws.folder() << std::endl;
     std::cout << "BWT type:         BCR exact" << std::endl;
-    grl_bwt_algo<sym_type, false>(input_collection, args.output_file, tmp_ws, args.n_threads, args.hbuff_frac, args.b_f_r, args.device);
+    grl_bwt_algo<sym_type, false>(input_collection, args.output_file, tmp_ws, args.n_threads, args.hbuff_frac, args.b_f_r, args.devices, args.comm_kind);
 }
 
 int main(int argc, char** argv) {

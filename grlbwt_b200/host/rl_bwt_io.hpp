@@ -26,6 +26,8 @@ struct RunList {
     }
 };
 
+static_assert(__BYTE_ORDER__ == __ORDER_LITTLE_ENDIAN__, "the .rl_bwt records are packed with little-endian stores");
+
 template <class SymT>
 inline void write_rl_bwt(const std::string& path, const SymT* sym, const uint64_t* len, uint64_t n_runs, uint64_t sb, uint64_t fb) {
     FILE* f = fopen(path.c_str(), "wb");
@@ -57,7 +59,8 @@ inline void read_rl_bwt(const std::string& path, RunList& out, uint64_t& sb, uin
     if (sb == 0 || sb > 8 || fb == 0 || fb > 8) { fclose(f); throw std::runtime_error("bad header in " + path); }
     unsigned char rec[16];
     out.sym.clear(); out.len.clear();
-    while (fread(rec, 1, sb + fb, f) == sb + fb) {
+    size_t got;
+    while ((got = fread(rec, 1, sb + fb, f)) == sb + fb) {
         uint64_t s = 0, l = 0;
         memcpy(&s, rec, sb);
         memcpy(&l, rec + sb, fb);
@@ -65,6 +68,7 @@ inline void read_rl_bwt(const std::string& path, RunList& out, uint64_t& sb, uin
         out.len.push_back(l);
     }
     fclose(f);
+    if (got != 0) throw std::runtime_error("truncated record at the end of " + path);  // the file must be 16 + r * (sb + fb) bytes
 }
 
 }  // namespace grlbwt

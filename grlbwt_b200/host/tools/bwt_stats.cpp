@@ -2,7 +2,7 @@
 #include <iostream>
 #include "rl_bwt_tools.hpp"
 
-int main(int argc, char** argv) {
+static int run(int argc, char** argv) {
     if (argc != 2) {
         std::cout << "usage: ./bwt_stats file.rlbwt" << std::endl;
         return 0;
@@ -28,3 +28,4 @@ int main(int argc, char** argv) {
               << "Runs shorter than 2^16:  " << (r ? 100.0 * double(lt65536) / double(r) : 0.0) << " %" << std::endl;
     return 0;
 }
+GRL_TOOL_MAIN(run)

@@ -4,6 +4,8 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <exception>
+#include <iostream>
 #include <map>
 #include <string>
 #include <vector>
@@ -26,11 +28,25 @@ struct RlBwt {
         start.resize(r + 1);
         before.resize(r);
         std::map<uint64_t, uint64_t> cnt;
-        for (size_t i = 0; i < r; i++) {
-            start[i] = n;
-            before[i] = cnt[runs.sym[i]];
-            cnt[runs.sym[i]] += runs.len[i];
-            n += runs.len[i];
+        uint64_t max_sym = 0;
+        for (size_t i = 0; i < r; i++) max_sym = std::max(max_sym, runs.sym[i]);
+        if (max_sym < (1ull << 26)) {  // dense counters: one array access per run instead of a tree walk (billions of runs at full size)
+            std::vector<uint64_t> dense(max_sym + 1, 0);
+            for (size_t i = 0; i < r; i++) {
+                start[i] = n;
+                before[i] = dense[runs.sym[i]];
+                dense[runs.sym[i]] += runs.len[i];
+                n += runs.len[i];
+            }
+            for (uint64_t c = 0; c <= max_sym; c++)
+                if (dense[c]) cnt[c] = dense[c];
+        } else {
+            for (size_t i = 0; i < r; i++) {
+                start[i] = n;
+                before[i] = cnt[runs.sym[i]];
+                cnt[runs.sym[i]] += runs.len[i];
+                n += runs.len[i];
+            }
         }
         start[r] = n;
         uint64_t acc = 0;
@@ -50,3 +66,10 @@ inline void put_cell(std::vector<unsigned char>& out, uint64_t v, int width) {
 }
 
 }  // namespace grlbwt
+
+// a malformed input (bad header, truncated record) ends the tool with a message and status 1, not an abort
+#define GRL_TOOL_MAIN(fn)                                             \
+    int main(int argc, char** argv) {                                 \
+        try { return fn(argc, argv); }                                \
+        catch (const std::exception& e) { std::cerr << "Error: " << e.what() << std::endl; return 1; } \
+    }

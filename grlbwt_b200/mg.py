@@ -1,0 +1,130 @@
+"""Multi-GPU plumbing for tests and bench.py: ctypes handles of the exchange layer (include/grlgpu.h, grlgpu_comm) and a
+few helpers. The rounds, the exchanges and the per-rank host threads all live in the C/C++ libraries
+(grlbwt_b200/csrc/mg2.cuh, comm.hpp, host/gpu_par_phase.hpp); nothing here computes.
+
+Two ways to run N ranks:
+  * one process per GPU (bench.py under torchrun): `nccl_comm_from_torch` -- rank 0 makes the NCCL id, torch.distributed
+    broadcasts its 128 bytes, every rank builds its communicator inside libgrlgpu.so;
+  * one process, N host threads (the grlbwt CLI with --gpus N, `build_bwt_mg` here): NCCL when every rank has its own GPU,
+    else in-process peer copies (several ranks may share one GPU: the N > 1 path on a 1-GPU box).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from .api import BwtResult, GrlGpuError, _ptr, lib_gpu, lib_host
+
+COMM_AUTO, COMM_LOCAL, COMM_NCCL = 0, 1, 2
+
+
+class Comm:
+    """one rank's end of the exchange layer"""
+
+    def __init__(self, handle, group=None):
+        self.handle, self._group = handle, group
+
+    def info(self):
+        L = lib_gpu()
+        b, nb, ns = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        kind = C.create_string_buffer(128)
+        L.grlgpu_comm_info(self.handle, C.byref(b), C.byref(nb), C.byref(ns), kind, 128)
+        return {"bytes_sent": int(b.value), "bulk_collectives": int(nb.value), "small_collectives": int(ns.value), "kind": kind.value.decode()}
+
+    def close(self):
+        if self.handle:
+            lib_gpu().grlgpu_comm_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
+def nccl_unique_id() -> np.ndarray:
+    buf = np.zeros(128, np.uint8)
+    rc = lib_gpu().grlgpu_nccl_unique_id(_ptr(buf))
+    if rc != 0:
+        raise GrlGpuError(rc, "NCCL is not available")
+    return buf
+
+
+def nccl_comm(id128: np.ndarray, rank: int, world: int, device: int) -> Comm:
+    h = C.c_void_p()
+    id128 = np.ascontiguousarray(id128, np.uint8)
+    rc = lib_gpu().grlgpu_comm_create_nccl(C.byref(h), _ptr(id128), rank, world, device)
+    if rc != 0:
+        raise GrlGpuError(rc, "ncclCommInitRank failed")
+    return Comm(h)
+
+
+def nccl_comm_from_torch(dist, rank: int, world: int, device_index: int, torch) -> Comm:
+    """one process per GPU: the id travels through torch.distributed (any backend), the communicator lives in libgrlgpu.so"""
+    dev = torch.device("cuda", device_index) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        t.copy_(torch.from_numpy(nccl_unique_id()))
+    dist.broadcast(t, src=0)
+    return nccl_comm(t.cpu().numpy(), rank, world, device_index)
+
+
+def shard_bounds(text: np.ndarray, n_ranks: int):
+    """Contiguous ranges of WHOLE strings balanced by symbol count (same rule as host/gpu_par_phase.hpp: boundary r is the end
+    of the first string that ends at or after cell r*n/G). -> list of (begin, end) cell offsets, possibly fewer than n_ranks."""
+    n, sep = int(text.size), text[-1]
+    b = [0]
+    for r in range(1, n_ranks):
+        pos = max(r * n // n_ranks, b[-1])
+        hit = np.flatnonzero(text[pos:] == sep)
+        if hit.size == 0:
+            break
+        end = pos + int(hit[0]) + 1
+        if end >= n:
+            break
+        if end > b[-1]:
+            b.append(end)
+    b.append(n)
+    return [(b[i], b[i + 1]) for i in range(len(b) - 1)]
+
+
+def build_bwt_mg(text: np.ndarray, devices, n_threads: int = 1, comm: int = COMM_AUTO, verbose: bool = False):
+    """Whole construction over len(devices) ranks inside ONE process (host threads): -> (syms, lens, sb, fb, info).
+    info["digests"]: per round [tot_phrases, pre-BWT runs, parse length, distinct phrases, dictionary symbols, 4 checksums]."""
+    L = lib_host()
+    text = np.ascontiguousarray(text)
+    dv = np.asarray(devices, np.int32)
+    res = BwtResult()
+    rc = L.grlbwt_build_mg(_ptr(text), text.size, text.dtype.itemsize, _ptr(dv), dv.size, n_threads, comm, int(verbose), C.byref(res))
+    if rc != 0:
+        raise GrlGpuError(rc, L.grlbwt_last_error().decode())
+    try:
+        syms = np.ctypeslib.as_array(res.syms, shape=(res.n_runs,)).copy()
+        lens = np.ctypeslib.as_array(res.lens, shape=(res.n_runs,)).copy()
+        info = {k: getattr(res, k) for k in ("n_rounds", "h2d_ms", "par_phase_ms", "ind_phase_ms", "device_ms", "algorithmic_bytes")}
+        info["digests"] = last_digests()
+        info["exchange_bytes"] = int(L.grlbwt_last_exchange_bytes())
+        info["comm"] = L.grlbwt_last_comm().decode()
+        return syms, lens, int(res.sb), int(res.fb), info
+    finally:
+        L.grlbwt_free_result(C.byref(res))
+
+
+def last_digests():
+    L = lib_host()
+    n = int(L.grlbwt_last_digests(None, 0))
+    out = np.zeros((max(n, 1), 9), np.uint64)
+    L.grlbwt_last_digests(_ptr(out), n)
+    return [[int(x) for x in row] for row in out[:n]]
+
+
+def check_against_oracle(text: np.ndarray, n_ranks: int, device: int = 0):
+    """N in-process ranks on one device vs the oracle: per-round scalars and the final run-length BWT (sanitize driver, tests)"""
+    from oracle import oracle as O
+    o = O.Oracle(text)
+    R = o.par_phase()
+    syms, lens, sb, fb, info = build_bwt_mg(text, [device] * n_ranks, n_threads=2, comm=COMM_LOCAL)
+    osyms, olens, osb, ofb = o.ind_phase()
+    assert info["n_rounds"] == R, (info["n_rounds"], R)
+    for lv, d in enumerate(info["digests"]):
+        assert d[0] == o.scalar(lv, O.TOT_PHRASES) and d[2] == o.scalar(lv, O.PARSE_LEN), (lv, d)
+        assert d[3] == o.scalar(lv, O.D) and d[4] == o.scalar(lv, O.SUM_LEN), (lv, d)
+    assert (sb, fb) == (osb, ofb) and np.array_equal(syms, osyms) and np.array_equal(lens, olens)
+    o.close()
+    return info

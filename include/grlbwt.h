@@ -28,6 +28,17 @@ typedef struct {
 /* BWT of a collection held in host memory; status codes of grlgpu.h (or -100 for host-side errors) */
 int grlbwt_build(const void* text, uint64_t n_syms, int sym_bytes, int device, int n_threads, int verbose, grlbwt_result_t* out);
 void grlbwt_free_result(grlbwt_result_t* r);
+/* the same over several GPUs: one rank (host thread) per entry of `devices`, shards of whole strings, partitioned global
+ * dictionary (include/grlgpu.h, multi-GPU rounds). A device may be listed more than once (ranks then share it: this is how
+ * the N > 1 path runs on a 1-GPU box). comm_kind: 0 = NCCL when every rank has its own GPU, else in-process peer copies;
+ * 1 = in-process; 2 = NCCL. The bytes of the result do not depend on the number of ranks. */
+int grlbwt_build_mg(const void* text, uint64_t n_syms, int sym_bytes, const int* devices, int n_ranks, int n_threads, int comm_kind, int verbose,
+                    grlbwt_result_t* out);
+/* per-round digests of the calling thread's last build (9 values per round: tot_phrases, pre-BWT runs, parse length, distinct
+ * phrases, dictionary symbols, and the four sums of grlgpu_level_checksum added over the ranks); returns the number of rounds */
+uint64_t grlbwt_last_digests(uint64_t* out, uint64_t cap_rounds);
+uint64_t grlbwt_last_exchange_bytes(void);   /* bulk bytes exchanged between the ranks during the last build */
+const char* grlbwt_last_comm(void);          /* exchange backend of the last build */
 
 /* same as the CLI: TEXT file -> .rl_bwt file (main.cpp:98-154 + grl_bwt.hpp:23-79) */
 int grlbwt_build_file(const char* input_file, const char* output_file, int sym_bytes, int device, int n_threads, int verbose);
@@ -40,6 +51,10 @@ const char* grlbwt_last_error(void);
 int grlbwt_selftest_induce(int n_levels, const uint64_t* alphabet, const uint64_t* tot, const uint64_t* const* rule_l, const uint64_t* const* rule_r,
                            const uint8_t* const* has_hocc, const uint64_t* n_pre, const uint64_t* const* pre_sym, const uint64_t* const* pre_len,
                            const uint64_t* final_parse, uint64_t n_strings, int n_threads /* 0 = sequential 64-bit path */, grlbwt_result_t* out);
+
+/* self test of the multi-GPU sharding rule alone (no device): contiguous ranges of whole strings balanced by symbol count;
+ * bounds_out receives n_shards + 1 cell offsets (n_shards <= n_ranks: fewer when the collection has fewer strings) */
+int grlbwt_selftest_shard_bounds(const void* text, uint64_t n_syms, int sym_bytes, int n_ranks, uint64_t* bounds_out, int* n_shards);
 
 /* self test of the .rl_bwt writer alone (no device; format of include/bwt_io.h:377-382,448-490): runs given as u64
  * symbols / lengths; narrow != 0 routes through the 32-bit-symbol instantiation the multi-threaded host uses */

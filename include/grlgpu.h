@@ -34,7 +34,6 @@ enum grlgpu_status {
 #define GRLGPU_FLAG_FORCE_UNCACHED 8ull /* tests: dedup every phrase with the thread-per-phrase kernel (no cached tiles) */
 #define GRLGPU_FLAG_SMALL_PILOT 16ull /* tests: one pilot tile, so small inputs exercise pilot + remainder */
 #define GRLGPU_FLAG_FORCE_DOUBLING 32ull /* tests: refine suffix groups by prefix doubling even when key extension would do */
-#define GRLGPU_FLAG_FORCE_DIST_RANK 64ull /* tests: distribute the dictionary ranking over the ranks even for tiny dictionaries */
 #define GRLGPU_FLAG_KEEP_DICT 4ull /* tests: keep the last round's dictionary for grlgpu_fetch_dictionary */
 
 /* = str_collection (external/cdt/include/utils.h:20-28) as filled by collection_stats (utils.cpp:100-189) */
@@ -85,6 +84,16 @@ int grlgpu_set_text(grlgpu_ctx* ctx, const void* text, uint64_t n_syms, int sym_
 /* same, text already resident in DEVICE memory (16-byte aligned); borrowed, not copied, never written */
 int grlgpu_set_text_device(grlgpu_ctx* ctx, const void* dev_text, uint64_t n_syms, int sym_bytes);
 
+/* Streaming ingest of the round-1 input (what i_file_stream's 8 MB windows do for the reference,
+ * external/cdt/include/file_streams.hpp:93-105): begin allocates the device text and two pinned staging buffers of
+ * stage_bytes (0: 64 MB); stage hands out the next free buffer (*cap bytes of it may be filled, e.g. by read() from the input
+ * file); commit enqueues its copy to the device on the copy stream and returns at once, so the caller fills the other
+ * buffer meanwhile; end waits for the last copy. The bytes must be committed in text order. */
+int grlgpu_text_begin(grlgpu_ctx* ctx, uint64_t n_syms, int sym_bytes, uint64_t stage_bytes);
+int grlgpu_text_stage(grlgpu_ctx* ctx, void** buf, uint64_t* cap);
+int grlgpu_text_commit(grlgpu_ctx* ctx, uint64_t bytes);
+int grlgpu_text_end(grlgpu_ctx* ctx);
+
 /* replaces: collection_stats<sym_type>() (utils.cpp:100-189); validates sep == min && last == sep */
 int grlgpu_stats(grlgpu_ctx* ctx, grlgpu_stats_t* out);
 
@@ -113,6 +122,23 @@ int grlgpu_fetch_level_async(grlgpu_ctx* ctx, void* rule_l, void* rule_r, uint8_
  * 4 bytes less per preliminary-BWT run over PCIe; replaces the same files as grlgpu_fetch_level. */
 int grlgpu_fetch_level32(grlgpu_ctx* ctx, void* rule_l, void* rule_r, uint8_t* has_hocc, void* pre_sym, uint32_t* pre_len32, int async);
 int grlgpu_fetch_wait(grlgpu_ctx* ctx);
+/* Hand-over of the last level (grlgpu_round) or level slice (grlgpu_mg_round) to host-side fetch threads: the device arrays
+ * are parked -- kept alive until grlgpu_fetch_wait -- and their DEVICE addresses returned; any host thread may copy them with
+ * grlgpu_copy_to_host (blocking, on a stream of its own) while the context's thread runs the next round. len_bytes: width of
+ * the run lengths handed out (4 only when n_in + parse_len < 2^32: GRLGPU_ERR_LIMIT otherwise). */
+typedef struct {
+    const void *rule_l, *rule_r, *has_hocc, *pre_sym, *pre_len;
+    uint64_t tot, n_pre;       /* elements of rule_l / rule_r / has_hocc and of pre_sym / pre_len */
+    uint32_t sym_bytes, len_bytes;
+    int device;
+} grlgpu_level_ptrs_t;
+int grlgpu_level_park(grlgpu_ctx* ctx, int len_bytes, grlgpu_level_ptrs_t* out);
+int grlgpu_copy_to_host(int device, void* dst, const void* dev_src, uint64_t bytes);
+/* digest of the last round's level artefacts, computed on the device before they are fetched: four sums mod 2^64
+ * {rules weighted by rank, hocc marks weighted by rank, sum of the preliminary-BWT run lengths, runs weighted by symbol}.
+ * The sums of the per-rank slices of a multi-GPU level add up to the single-GPU value, so bench.py can check that 1, 2,
+ * 4 and 8 ranks produced the same dict_lev_k / pre_bwt_lev_k (exact_par_phase.hpp:189-203, exact_par_phase.cpp:150-155). */
+int grlgpu_level_checksum(grlgpu_ctx* ctx, uint64_t* out4);
 
 /* current parse (output of the last round): parse_len cells of cell_bytes_out bytes, cells = rank<<1|rep.
  * replaces: file tmp_input (exact_par_phase.cpp:307-308); after the last round this is the final parse
@@ -127,59 +153,63 @@ int grlgpu_fetch_dictionary(grlgpu_ctx* ctx, uint64_t* syms, uint64_t* lens, uin
 const char* grlgpu_strerror(int status);
 const char* grlgpu_last_error(const grlgpu_ctx* ctx);
 
-/* ---- multi-GPU rounds ---------------------------------------------------------------------
- * One context per GPU, each holding a shard of WHOLE strings (the reference's own split,
- * include/parsing_strategies.h:208-214, so no phrase crosses a shard). The caller owns the exchange (NCCL
- * through torch.distributed in bench.py / grlbwt_b200/multigpu.py); the library does every device step
- * before, between and after. Per round, on every rank, in this order:
- *   grlgpu_mg_local      boundary scan + local dedup; per owner rank (content hash % n_ranks) how many distinct
- *                        local phrases / cells go there; local parse length (caller all-reduces termination)
- *   grlgpu_mg_pack       fill caller-allocated DEVICE send buffers, ordered by owner   -> all-to-all-v
- *   grlgpu_mg_merge      owner side: dedup what arrived, sum the counts                -> partition sizes
- *   grlgpu_mg_pack_part  fill DEVICE buffers with this rank's partition               -> all-gather-v
- *   grlgpu_mg_global     the gathered dictionary (identical on every rank, rank order) is ranked exactly as in
- *                        grlgpu_round; local phrases get their metasymbols; the shard is rewritten.
- * Level artefacts are identical on every rank (fetch them on one). Before the first round every rank calls
- * grlgpu_stats and then grlgpu_mg_set_alphabet with the maximum symbol over all ranks.
- * replaces: mt_parse_strat_t's thread fan-out + serial join_thread_phrases (parsing_strategies.h:244-386). */
-typedef struct {
-    uint64_t n_phrases;
-    uint64_t n_cells;
-} grlgpu_part_t;
-/* byte alphabets: the 256-bin symbol histogram behind grlgpu_stats (ranks sum theirs to get the global max_sym_freq) */
-int grlgpu_histogram(grlgpu_ctx* ctx, uint64_t* hist256);
-int grlgpu_mg_set_alphabet(grlgpu_ctx* ctx, uint64_t global_max_sym);
-int grlgpu_mg_local(grlgpu_ctx* ctx, int n_ranks, grlgpu_part_t* per_owner, uint64_t* parse_len_local);
-int grlgpu_mg_pack(grlgpu_ctx* ctx, uint32_t* d_lens, uint64_t* d_counts, void* d_cells);
-int grlgpu_mg_merge(grlgpu_ctx* ctx, const uint32_t* d_lens, const uint64_t* d_counts, const void* d_cells, uint64_t m, uint64_t n_cells,
-                    grlgpu_part_t* part);
-int grlgpu_mg_pack_part(grlgpu_ctx* ctx, uint32_t* d_lens, uint64_t* d_freqs, void* d_cells);
-int grlgpu_mg_global(grlgpu_ctx* ctx, const uint32_t* d_lens, const uint64_t* d_freqs, const void* d_cells, uint64_t d, uint64_t n_cells,
-                     int done_global, grlgpu_round_t* out);
+/* ---- multi-GPU rounds ----------------------------------------------------------------------
+ * One context per GPU = one rank, each holding a shard of WHOLE strings (the reference's own split,
+ * include/parsing_strategies.h:208-214, so no phrase crosses a shard). The library owns the whole round, exchanges
+ * included; the global dictionary is never replicated: phrases are partitioned by owner (content hash), their suffix
+ * entries by first-key range, the grammar rules by rank range (grlbwt_b200/csrc/mg2.cuh). All ranks make the same
+ * calls in the same order:
+ *     grlgpu_set_text[_device] (its shard)  ->  grlgpu_mg_stats  ->  grlgpu_mg_round until done
+ *     after every round: grlgpu_mg_slice_info + grlgpu_mg_fetch_slice (this rank's part of the level)
+ *     after the last: grlgpu_fetch_parse (one cell per local string; rank order = string order)
+ * replaces: mt_parse_strat_t's thread fan-out + serial join_thread_phrases (parsing_strategies.h:244-386) and shards
+ * suffix_induction / produce_pre_bwt / produce_grammar (exact_LMS_induction.h:94-158, exact_par_phase.cpp:14-242).
+ *
+ * Exchange backends (grlgpu_comm): NCCL -- one rank per process (bench.py under torchrun: rank 0 makes the id, the
+ * launcher broadcasts its 128 bytes) or per host thread (the grlbwt CLI with --gpus N); "local" -- ranks are host
+ * threads of one process that pull from each other's send buffers with peer copies (NVLink P2P between GPUs, plain
+ * device copies when several ranks share one GPU: how the N > 1 path is tested on a 1-GPU box). NCCL is resolved
+ * with dlopen at the first use; the library loads without it. */
+typedef struct grlgpu_comm grlgpu_comm;
+typedef struct grlgpu_local_group grlgpu_local_group;
+int grlgpu_nccl_unique_id(void* id128);
+int grlgpu_comm_create_nccl(grlgpu_comm** comm, const void* id128, int rank, int world, int device);
+int grlgpu_local_group_create(grlgpu_local_group** group, int world);
+int grlgpu_local_group_abort(grlgpu_local_group* group);   /* a rank failed: wake the ranks waiting for it (they return GRLGPU_ERR_STATE) */
+int grlgpu_local_group_destroy(grlgpu_local_group* group);
+int grlgpu_comm_create_local(grlgpu_comm** comm, grlgpu_local_group* group, int rank, int device);
+int grlgpu_comm_destroy(grlgpu_comm* comm);
+/* bytes this rank sent in bulk exchanges so far, bulk / small collectives issued, backend description */
+int grlgpu_comm_info(const grlgpu_comm* comm, uint64_t* bytes_sent, uint64_t* n_bulk, uint64_t* n_small, char* kind, int kind_cap);
+/* in-process ranks on different GPUs: let the listed devices read this context's memory pool directly (NVLink P2P) */
+int grlgpu_set_peers(grlgpu_ctx* ctx, const int* devices, int n_devices);
 
-/* Distributed ranking of the gathered dictionary (optional; replaces grlgpu_mg_global when info5[0] comes back 1).
- * Every rank sorts, refines and groups only the suffix entries whose first key falls in its range (splitters from
- * a regular sample, identical on every rank), so the dominant cost of unique-heavy rounds shrinks with the ranks:
- *   grlgpu_mg_rank_sort    -> info5 = {distributed?, ranked groups here, pre-BWT runs here, dictionary entries nE, symbol bytes}
- *                             (0 in info5[0]: nothing was done -- small or long-phrase dictionary -- call grlgpu_mg_global)
- *   caller: rank_base = exclusive prefix of the ranked-group counts over the ranks, tot = their sum; allocates
- *           zero-filled device arrays ph_meta[d] (u64), is_suffix_next[tot] (u8), erank1[nE] (u32)
- *   grlgpu_mg_rank_apply   writes this rank's share into them (hocc marks as rank + 1)   -> all-reduce(MAX) of the three
- *   grlgpu_mg_reply        owner side of the metasymbol return (optional): reply[k] = metasymbol of the k-th phrase this rank
- *                          RECEIVED in grlgpu_mg_merge; part_base = global index of this rank's first partition phrase
- *                          -> reverse all-to-all-v: every rank gets the metasymbols of the pack it sent, in pack order
- *   grlgpu_mg_rank_finish  rules of this rank's groups, metasymbols of the local phrases (from d_local_meta when the owners
- *                          returned them, else -- NULL -- by content lookup in a table of the whole dictionary), rewrite
- *   grlgpu_mg_level_slice  this rank's slice of the level artefacts into caller DEVICE buffers (rules / has_hocc: info5[1]
- *                          entries, positions [rank_base, rank_base + info5[1]); pre-BWT: info5[2] runs, to be
- *                          concatenated in rank order, merging equal symbols where two ranks meet) */
-int grlgpu_mg_rank_sort(grlgpu_ctx* ctx, const uint32_t* d_lens, const uint64_t* d_freqs, const void* d_cells, uint64_t d, uint64_t n_cells, int rank_id,
-                        int n_ranks, uint64_t* info5);
-int grlgpu_mg_rank_apply(grlgpu_ctx* ctx, uint64_t rank_base, uint64_t* d_ph_meta, uint8_t* d_is_suffix_next, uint32_t* d_erank1);
-int grlgpu_mg_reply(grlgpu_ctx* ctx, uint64_t part_base, const uint64_t* d_ph_meta, uint64_t* d_reply);
-int grlgpu_mg_rank_finish(grlgpu_ctx* ctx, uint64_t rank_base, uint64_t tot, uint64_t n_pre_runs, const uint64_t* d_ph_meta, const uint8_t* d_is_suffix_next,
-                          uint32_t* d_erank1, const uint64_t* d_local_meta, int done_global, grlgpu_round_t* out);
-int grlgpu_mg_level_slice(grlgpu_ctx* ctx, void* d_rule_l, void* d_rule_r, uint8_t* d_has_hocc, void* d_pre_sym, uint64_t* d_pre_len);
+/* byte alphabets: the 256-bin symbol histogram behind grlgpu_stats */
+int grlgpu_histogram(grlgpu_ctx* ctx, uint64_t* hist256);
+/* collection_stats (utils.cpp:100-189) over ALL shards; fixes the global alphabet and string count in the context.
+ * Fails with GRLGPU_ERR_ILL_FORMED on every rank if any shard is ill formed. */
+int grlgpu_mg_stats(grlgpu_ctx* ctx, grlgpu_comm* comm, grlgpu_stats_t* global_out);
+/* one parse round over all ranks (= grlgpu_round; the scalars of `out` describe the GLOBAL round, algorithmic_bytes and
+ * the times this rank's share). */
+int grlgpu_mg_round(grlgpu_ctx* ctx, grlgpu_comm* comm, grlgpu_round_t* out);
+
+/* this rank's part of the level produced by the last grlgpu_mg_round: rules / hocc marks of the ranks
+ * [rank_base, rank_base + tot_local) and the preliminary-BWT runs [pre_first, pre_first + n_pre_local) of the level
+ * (runs that continue across two ranks' ranges are already merged into the earlier rank's last run) */
+typedef struct {
+    uint64_t rank_base, tot_local;
+    uint64_t pre_first, n_pre_local;
+    uint64_t exchange_bytes;   /* bulk bytes this rank sent to its peers during the round */
+    uint64_t n_in_local, parse_len_local; /* cells of this rank's shard before / after the round (grlgpu_fetch_parse copies parse_len_local cells) */
+    uint32_t sym_bytes;        /* element width (4 or 8) of rule_l / rule_r / pre_sym */
+    uint32_t reserved;
+} grlgpu_slice_t;
+int grlgpu_mg_slice_info(grlgpu_ctx* ctx, grlgpu_slice_t* out);
+/* copies the slice into caller-owned HOST buffers (NULL skips an array); pre_len elements are len_bytes (4 or 8) wide.
+ * async != 0: copies run on the copy stream while the next round computes; complete them with grlgpu_fetch_wait. */
+int grlgpu_mg_fetch_slice(grlgpu_ctx* ctx, void* rule_l, void* rule_r, uint8_t* has_hocc, void* pre_sym, void* pre_len, int len_bytes, int async);
+/* grlgpu_level_checksum of the slice: the four sums of all ranks add up (mod 2^64) to the single-GPU level's */
+int grlgpu_mg_slice_checksum(grlgpu_ctx* ctx, uint64_t* out4);
 
 /* launch accounting: number of kernel launches issued by this context so far, and (after
  * grlgpu_profile_enable(ctx, 1)) per-kernel CUDA-event durations measured live on the launch stream.

@@ -17,7 +17,8 @@ def test_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
-    assert line["metric"].startswith("input MB/s to BCR BWT")
+    assert line["metric"].startswith("input MB/s through the parse phase of the BCR BWT construction")
+    assert line["config"]["workload"].startswith("C2: 50000000 reads") and "reads x 150 bp" in line["config"]["sample"]
 
 
 def test_reference_arm_other_ranks_exit_quietly():

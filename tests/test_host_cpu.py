@@ -54,6 +54,19 @@ def test_multithreaded_induction_config_shapes(golden, all_cases, name):
         assert hashlib.sha256(raw).hexdigest() == g["rl_bwt_sha256"], (name, threads)
 
 
+@pytest.mark.parametrize("name", ["rep_50x200k", "mixed_reads"])
+def test_induction_with_more_threads_than_chunks(golden, all_cases, name):
+    """thread counts far above what the small levels can feed: chunks past the end of an array are empty and must not
+    touch the per-chunk partial sums (levels with 4096..T^2 runs used to lose the last chunk's total)"""
+    o = O.Oracle(all_cases[name])
+    R = o.par_phase()
+    levels, fp, g = oracle_levels(o, R), o.array(R - 1, O.A_PARSE), golden[name]
+    for threads in (96, 128, 258):
+        syms, lens = G.selftest_induce(levels, fp, threads)
+        raw = O.rl_bwt_bytes(syms, lens, g["sb"], g["fb"])
+        assert hashlib.sha256(raw).hexdigest() == g["rl_bwt_sha256"], (name, threads)
+
+
 def declared_symbols(header):
     src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)

@@ -78,6 +78,22 @@ def test_bwt_check_accepts_reference_bwts_and_rejects_corrupted(all_cases, tmp_p
             assert r.returncode == 1 and "FAILED" in r.stdout, (name, r.stdout)
 
 
+def test_truncated_rl_bwt_is_rejected(tmp_path, all_cases):
+    """a file that does not hold a whole number of records is an error for every consumer, not a silently shorter BWT"""
+    arr = all_cases["dna_500"]
+    o = O.Oracle(arr)
+    o.par_phase()
+    syms, lens, sb, fb = o.ind_phase()
+    raw = O.rl_bwt_bytes(syms, lens, sb, fb)
+    rl, txt = tmp_path / "cut.rl_bwt", tmp_path / "t.bin"
+    arr.tofile(txt)
+    rl.write_bytes(raw[:-1])
+    for cmd in ([tool("reverse_bwt"), str(rl), str(tmp_path / "o")], [tool("grl2plain"), str(rl), str(tmp_path / "o")],
+                [tool("bwt_check"), str(txt), str(rl)], [tool("bwt_stats"), str(rl)], [tool("grlbwt2rle"), str(rl), str(tmp_path / "p")]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 1 and "truncated" in r.stderr, (cmd[0], r.returncode, r.stderr[-200:])
+
+
 def test_tools_usage_messages():
     for t in ("grl2plain", "grlbwt2rle", "reverse_bwt", "bwt_stats", "bwt_check"):
         r = subprocess.run([tool(t)], capture_output=True, text=True)
