@@ -249,9 +249,9 @@ __global__ void __launch_bounds__(256) ext_keys_kernel(const u32* __restrict__ a
         else if (pos == r + 1) code = term_code;
         key = (bits >= 64) ? code : ((key << bits) | code);
     }
-    keys[j] = key;
+    if (keys) keys[j] = key;
     nk[j] = key;
-    vals[j] = (u32)j;
+    if (vals) vals[j] = (u32)j;
     ev[j] = e;
     gflag[j] = (head_bits[i >> 5] >> (i & 31)) & 1u;
 }
@@ -289,6 +289,83 @@ static __global__ void __launch_bounds__(256) ext_next_kernel(const u32* __restr
     const bool nh = i + 1 == nE || ((head_bits[(i + 1) >> 5] >> ((i + 1) & 31)) & 1u);
     aflag[q] = (!(hd && nh) && (u64)rem[ev[vals[q]]] + 1 >= dpt_next) ? 1u : 0u;
 }
+// ---- tile-local segmented sort of the active set. The members of an unresolved group are contiguous in the active list
+// (gflag marks the first of each group) and most groups are tiny, so instead of two device-wide radix sorts per depth
+// (by extension key, then stably by group) a CTA stages a window of the list in shared memory and the thread that owns a
+// group's first slot insertion-sorts the group in place (stable). Groups that straddle a window or exceed LS_MAXG members
+// are flagged and take the device-wide path (a fraction of a percent of the set).
+//   perm[q]  = active index of the element that belongs at slot q        flags[q] = 1 where a (sub)group starts at slot q
+constexpr int LS_THREADS = 256, LS_ITEMS = 8, LS_WIN = LS_THREADS * LS_ITEMS, LS_MAXG = 48;
+static __global__ void __launch_bounds__(LS_THREADS) ext_local_sort_kernel(const u64* __restrict__ nk, const u32* __restrict__ gflag, u64 nA, u32* __restrict__ perm,
+                                                                          u32* __restrict__ flags, u32* __restrict__ lflag) {
+    __shared__ u64 s_key[LS_WIN];
+    __shared__ unsigned short s_idx[LS_WIN];
+    __shared__ u8 s_head[LS_WIN + 1], s_left[LS_WIN];
+    __shared__ u32 s_first;
+    const u64 w0 = (u64)blockIdx.x * LS_WIN;
+    const u32 cnt = (u32)((nA - w0) < (u64)LS_WIN ? (nA - w0) : (u64)LS_WIN);
+    if (threadIdx.x == 0) { s_first = cnt; s_head[cnt] = (w0 + cnt < nA) ? (u8)gflag[w0 + cnt] : (u8)1; }
+    __syncthreads();
+    for (u32 s = threadIdx.x; s < cnt; s += LS_THREADS) {
+        s_key[s] = nk[w0 + s];
+        s_idx[s] = (unsigned short)s;
+        const u32 h = gflag[w0 + s];
+        s_head[s] = (u8)h;
+        s_left[s] = 0;
+        if (h) atomicMin(&s_first, s);
+    }
+    __syncthreads();
+    const u32 first = s_first;
+    for (u32 s = threadIdx.x; s < first; s += LS_THREADS) s_left[s] = 1;  // tail of a group that started in an earlier window
+    const u32 lo = threadIdx.x * LS_ITEMS, hi = lo + LS_ITEMS < cnt ? lo + LS_ITEMS : cnt;
+    for (u32 s = lo; s < hi; s++) {
+        if (!s_head[s]) continue;
+        u32 e = s + 1;
+        while (e < cnt && !s_head[e]) e++;
+        const bool complete = e < cnt || s_head[cnt];
+        if (!complete || e - s > (u32)LS_MAXG) {
+            for (u32 q = s; q < e; q++) s_left[q] = 1;
+            continue;
+        }
+        for (u32 q = s + 1; q < e; q++) {  // stable insertion sort of [s, e) by key
+            const u64 k = s_key[q];
+            const unsigned short ix = s_idx[q];
+            u32 r = q;
+            while (r > s && s_key[r - 1] > k) { s_key[r] = s_key[r - 1]; s_idx[r] = s_idx[r - 1]; r--; }
+            s_key[r] = k;
+            s_idx[r] = ix;
+        }
+    }
+    __syncthreads();
+    for (u32 s = threadIdx.x; s < cnt; s += LS_THREADS) {
+        const u32 left = s_left[s];
+        lflag[w0 + s] = left;
+        perm[w0 + s] = (u32)w0 + (left ? s : (u32)s_idx[s]);
+        flags[w0 + s] = left ? 0u : ((s_head[s] || s_key[s] != s_key[s - 1]) ? 1u : 0u);
+    }
+}
+// the flagged remainder as a list of its own (keys, group-start flags), and its results merged back
+static __global__ void __launch_bounds__(256) ext_left_gather_kernel(const u32* __restrict__ lflag, const u32* __restrict__ lexcl, const u64* __restrict__ nk,
+                                                                     const u32* __restrict__ gflag, u64 nA, u32* __restrict__ lpos, u64* __restrict__ lk,
+                                                                     u64* __restrict__ lnk, u32* __restrict__ lv, u32* __restrict__ lg) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nA || !lflag[j]) return;
+    const u32 k = lexcl[j];
+    lpos[k] = (u32)j;
+    lk[k] = nk[j];
+    lnk[k] = nk[j];
+    lv[k] = k;
+    lg[k] = gflag[j];
+}
+static __global__ void __launch_bounds__(256) ext_left_scatter_kernel(const u32* __restrict__ lpos, const u32* __restrict__ lvp, const u32* __restrict__ lf, u64 nL,
+                                                                      u32* __restrict__ perm, u32* __restrict__ flags) {
+    const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nL) return;
+    const u32 slot = lpos[k];
+    perm[slot] = lpos[lvp[k]];
+    flags[slot] = lf[k];
+}
+
 // dense variant of ginfo (indexed by group) and the per-entry finalisation done in sorted order: no per-entry rank needed
 static __global__ void __launch_bounds__(256) pack_ginfo_dense_kernel(const u32* __restrict__ gcnt, const u32* __restrict__ rflag, const u32* __restrict__ rrank, u64 G,
                                                                       u32* __restrict__ ginfo) {

@@ -160,6 +160,10 @@ static __global__ void adjacent_max_diff_kernel(const u64* __restrict__ ptrs, u6
     m = warp_max(m);
     if (lane_id() == 0 && m) atomicMax(out, m);
 }
+static __global__ void fill_u32_kernel(u32* __restrict__ p, u64 n, u32 v) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
 static __global__ void u32_to_u64_kernel(const u32* __restrict__ in, u64 n, u64* __restrict__ out) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i];
@@ -404,6 +408,43 @@ void stage_gather(Round& R, bool force_ext = false) {
                R.einfo.p, (const u32*)voff.p, c->alphabet + 1, R.sym_bits, R.K, R.spare, R.keys.p, R.vals.p);
 }
 
+// One refinement depth of the suffix order: the active elements (slot j: extension key nk[j], gflag[j] = first of its group)
+// are sorted by key inside their groups. -> perm[q] = active index of the element that belongs at slot q, flags[q] = 1 where
+// a new (sub)group starts. Tile-local segmented sort for the groups that fit a window; the flagged rest goes through two
+// device-wide radix sorts (by key, then stably by group), as every element did before.
+void refine_sort_groups(cudaStream_t st, const u64* nk, const u32* gflag, u64 nA, int key_bits, DevBuf<u32>& perm, DevBuf<u32>& flags) {
+    perm.alloc(nA, st);
+    flags.alloc(nA, st);
+    if (nA == 0) return;
+    const bool local = getenv("GRL_NO_LOCAL_SORT") == nullptr;
+    DevBuf<u32> lflag(nA, st), lexcl(nA, st), cnt(1, st);
+    u64 nLft = nA;
+    if (local) {
+        GRL_LAUNCH("ext_local_sort", nA * 24, ext_local_sort_kernel, (unsigned)div_up(nA, LS_WIN), LS_THREADS, 0, st, nk, gflag, nA, perm.p, flags.p, lflag.p);
+        exclusive_scan<u32, u32>(lflag.p, lexcl.p, nA, cnt.p, st);
+        nLft = d2h_scalar(cnt.p, st);
+    } else {
+        GRL_LAUNCH("fill_ones", nA * 4, fill_u32_kernel, grid_for(nA, 256), 256, 0, st, lflag.p, nA, 1u);
+        exclusive_scan<u32, u32>(lflag.p, lexcl.p, nA, cnt.p, st);
+    }
+    if (getenv("GRLGPU_TRACE")) fprintf(stderr, "[grlgpu]   refine sort: %llu active, %llu through the device-wide path\n", nA, nLft);
+    if (nLft == 0) return;
+    DevBuf<u32> lpos(nLft, st), lv(nLft, st), lv_alt(nLft, st), lg(nLft, st), gexcl(nLft, st), lf(nLft, st);
+    DevBuf<u64> lk(nLft, st), lk_alt(nLft, st), lnk(nLft, st);
+    GRL_LAUNCH("ext_left_gather", nA * 8 + nLft * 32, ext_left_gather_kernel, grid_for(nA, 256), 256, 0, st, lflag.p, lexcl.p, nk, gflag, nA, lpos.p, lk.p, lnk.p, lv.p, lg.p);
+    exclusive_scan<u32, u32>(lg.p, gexcl.p, nLft, cnt.p, st);
+    const u64 n_groups = d2h_scalar(cnt.p, st);
+    u64 *kp = lk.p, *ka = lk_alt.p;
+    u32 *vp = lv.p, *va = lv_alt.p;
+    radix_sort_pairs(&kp, &vp, &ka, &va, nLft, key_bits, st);  // by the extension key ...
+    GRL_LAUNCH("ext_gid", nLft * 12, ext_gid_kernel, grid_for(nLft, 256), 256, 0, st, lg.p, gexcl.p, nLft);
+    GRL_LAUNCH("ext_group_keys", nLft * 16, ext_group_keys_kernel, grid_for(nLft, 256), 256, 0, st, vp, gexcl.p, nLft, kp);
+    radix_sort_pairs(&kp, &vp, &ka, &va, nLft, std::max(1, bit_width64(n_groups)), st);  // ... then, stably, by group
+    GRL_LAUNCH("ext_heads", nLft * 24, ext_heads_kernel, grid_for(nLft, 256), 256, 0, st, vp, kp, lnk.p, nLft, lf.p);
+    GRL_LAUNCH("ext_left_scatter", nLft * 20, ext_left_scatter_kernel, grid_for(nLft, 256), 256, 0, st, lpos.p, vp, lf.p, nLft, perm.p, flags.p);
+    GRL_CUDA(cudaStreamSynchronize(st));  // the temporaries above go back to the pool
+}
+
 // ---------------- dictionary stage: suffix order, groups, ranks, pre-BWT, rules, metasymbols ----------------
 template <class SymT>
 void stage_dict(Round& R) {
@@ -450,20 +491,13 @@ void stage_dict(Round& R) {
             u64 dpt = (u64)K;  // codes already compared
             while (nA > 0) {
                 if (dpt > R.max_len + 1) throw Error(GRLGPU_ERR_STATE, "suffix refinement did not converge");
-                DevBuf<u64> ak(nA, st), ak_alt(nA, st), nk(nA, st);
-                DevBuf<u32> av(nA, st), av_alt(nA, st), ev(nA, st), gflag(nA, st), gexcl(nA, st), flags(nA, st), excl(nA, st), cnt(1, st);
-                u64 *akp = ak.p, *aka = ak_alt.p;
-                u32 *avp = av.p, *ava = av_alt.p;
-                GRL_LAUNCH("ext_keys", nA * 48, (ext_keys_kernel<SymT>), grid_for(nA, 256), 256, 0, st, apos.p, order_w, D, R.rem.p, head_bits.p, nA, dpt, A + 1, sym_bits, K, akp,
-                           avp, nk.p, ev.p, gflag.p);
-                exclusive_scan<u32, u32>(gflag.p, gexcl.p, nA, cnt.p, st);
-                const u64 n_groups = d2h_scalar(cnt.p, st);
-                if (getenv("GRLGPU_TRACE")) fprintf(stderr, "[grlgpu] round %d refine: depth %llu, active %llu in %llu groups (of %llu sorted)\n", c->round + 1, dpt, nA, n_groups, nS);
-                radix_sort_pairs(&akp, &avp, &aka, &ava, nA, std::min(64, sym_bits * K), st);  // by the extension key ...
-                GRL_LAUNCH("ext_gid", nA * 12, ext_gid_kernel, grid_for(nA, 256), 256, 0, st, gflag.p, gexcl.p, nA);
-                GRL_LAUNCH("ext_group_keys", nA * 16, ext_group_keys_kernel, grid_for(nA, 256), 256, 0, st, avp, gexcl.p, nA, akp);
-                radix_sort_pairs(&akp, &avp, &aka, &ava, nA, std::max(1, bit_width64(n_groups)), st);  // ... then, stably, by group
-                GRL_LAUNCH("ext_heads", nA * 24, ext_heads_kernel, grid_for(nA, 256), 256, 0, st, avp, akp, nk.p, nA, flags.p);
+                DevBuf<u64> nk(nA, st);
+                DevBuf<u32> ev(nA, st), gflag(nA, st), excl(nA, st), cnt(1, st), perm, flags;
+                GRL_LAUNCH("ext_keys", nA * 32, (ext_keys_kernel<SymT>), grid_for(nA, 256), 256, 0, st, apos.p, order_w, D, R.rem.p, head_bits.p, nA, dpt, A + 1, sym_bits, K,
+                           (u64*)nullptr, (u32*)nullptr, nk.p, ev.p, gflag.p);
+                if (getenv("GRLGPU_TRACE")) fprintf(stderr, "[grlgpu] round %d refine: depth %llu, active %llu (of %llu sorted)\n", c->round + 1, dpt, nA, nS);
+                refine_sort_groups(st, nk.p, gflag.p, nA, std::min(64, sym_bits * K), perm, flags);
+                const u32* avp = perm.p;
                 GRL_LAUNCH("ext_writeback", nA * 16, ext_writeback_kernel, grid_for(nA, 256), 256, 0, st, apos.p, avp, ev.p, flags.p, nA, order_w, head_bits.p);
                 dpt += (u64)K;
                 GRL_LAUNCH("ext_next", nA * 16, ext_next_kernel, grid_for(nA, 256), 256, 0, st, apos.p, avp, ev.p, head_bits.p, R.rem.p, nA, nS, dpt, flags.p);

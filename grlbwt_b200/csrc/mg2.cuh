@@ -141,9 +141,9 @@ static __global__ void __launch_bounds__(256) mg2_ext_scatter_kernel(const u32* 
     if (q >= nA) return;
     const u32 j = perm_j[q];
     const u64 k = resp[q];
-    keys[j] = k;
+    if (keys) keys[j] = k;
     nk[j] = k;
-    vals[j] = j;
+    if (vals) vals[j] = j;
     ev[j] = order[apos[j]];
 }
 // group aggregates over the sorted items of this range (produce_pre_bwt exact_par_phase.cpp:159-187); records in SoA form
@@ -480,18 +480,11 @@ void mg2_rank(grlgpu_ctx* c, Comm& cm, Mg2Part& P, Mg2Slices& S) {
         mg2_a2a<u64>(cm, serve_keys.p, serve_cnt, resp.p, req_cnt, st);
         GRL_CUDA(cudaStreamSynchronize(st));
         if (nA == 0) continue;
-        DevBuf<u64> ak(nA, st), ak_alt(nA, st), nk(nA, st);
-        DevBuf<u32> av(nA, st), av_alt(nA, st), ev(nA, st), gexcl(nA, st), flags(nA, st), excl(nA, st), cnt(1, st);
-        GRL_LAUNCH("mg_ext_scatter", nA * 40, mg2_ext_scatter_kernel, grid_for(nA, 256), 256, 0, st, perm_j.p, resp.p, apos.p, order.p, nA, ak.p, nk.p, av.p, ev.p);
-        u64 *akp = ak.p, *aka = ak_alt.p;
-        u32 *avp = av.p, *ava = av_alt.p;
-        exclusive_scan<u32, u32>(gflag.p, gexcl.p, nA, cnt.p, st);
-        const u64 n_groups = d2h_scalar(cnt.p, st);
-        radix_sort_pairs(&akp, &avp, &aka, &ava, nA, key_bits, st);  // by the extension key ...
-        GRL_LAUNCH("ext_gid", nA * 12, ext_gid_kernel, grid_for(nA, 256), 256, 0, st, gflag.p, gexcl.p, nA);
-        GRL_LAUNCH("ext_group_keys", nA * 16, ext_group_keys_kernel, grid_for(nA, 256), 256, 0, st, avp, gexcl.p, nA, akp);
-        radix_sort_pairs(&akp, &avp, &aka, &ava, nA, std::max(1, bit_width64(n_groups)), st);  // ... then, stably, by group
-        GRL_LAUNCH("ext_heads", nA * 24, ext_heads_kernel, grid_for(nA, 256), 256, 0, st, avp, akp, nk.p, nA, flags.p);
+        DevBuf<u64> nk(nA, st);
+        DevBuf<u32> ev(nA, st), excl(nA, st), cnt(1, st), perm, flags;
+        GRL_LAUNCH("mg_ext_scatter", nA * 40, mg2_ext_scatter_kernel, grid_for(nA, 256), 256, 0, st, perm_j.p, resp.p, apos.p, order.p, nA, (u64*)nullptr, nk.p, (u32*)nullptr, ev.p);
+        refine_sort_groups(st, nk.p, gflag.p, nA, key_bits, perm, flags);
+        const u32* avp = perm.p;
         GRL_LAUNCH("ext_writeback", nA * 16, ext_writeback_kernel, grid_for(nA, 256), 256, 0, st, apos.p, avp, ev.p, flags.p, nA, order.p, head_bits.p);
         GRL_LAUNCH("ext_next", nA * 16, ext_next_kernel, grid_for(nA, 256), 256, 0, st, apos.p, avp, ev.p, head_bits.p, r_rem.p, nA, nL, dpt + (u64)K, flags.p);
         exclusive_scan<u32, u32>(flags.p, excl.p, nA, cnt.p, st);
