@@ -506,6 +506,7 @@ def run_ours(args, rank, world, local_rank):
             bwt_total = {"value": round(sample.nbytes / 1e6 / (tot_ms / 1e3), 3), "unit": "MB/s", "n_gpus": world,
                          "sample": f"{sample.size // 151} reads x {READ_LEN} bp ({sample.nbytes / 1e6:.0f} MB)",
                          "h2d_ms": round(info["h2d_ms"], 1), "parse_phase_ms": round(info["par_phase_ms"], 1), "induction_ms": round(info["ind_phase_ms"], 1),
+                         "induction": "device (grlgpu_induce: levels never leave the GPU)" if info.get("induced_on_device") else "host threads",
                          "host_threads": thr, "bwt_runs": int(lens_.size), "exchange": info.get("comm"),
                          "what": "input MB/s to BCR BWT: host text -> run-length BCR BWT in host memory through the C++ host (grlbwt_build / grlbwt_build_mg: "
                                  "one host thread per GPU), file I/O excluded"}

@@ -42,7 +42,7 @@ class Slice(C.Structure):
 class BwtResult(C.Structure):
     _fields_ = [("n_runs", C.c_uint64), ("sb", C.c_uint64), ("fb", C.c_uint64), ("syms", C.POINTER(C.c_uint64)),
                 ("lens", C.POINTER(C.c_uint64)), ("n_rounds", C.c_uint64), ("h2d_ms", C.c_double), ("par_phase_ms", C.c_double),
-                ("ind_phase_ms", C.c_double), ("device_ms", C.c_double), ("algorithmic_bytes", C.c_uint64)]
+                ("ind_phase_ms", C.c_double), ("device_ms", C.c_double), ("algorithmic_bytes", C.c_uint64), ("induced_on_device", C.c_uint64)]
 
 
 _gpu = None
@@ -348,7 +348,7 @@ def build_bwt(text: np.ndarray, device: int = 0, n_threads: int = 1, verbose: bo
     try:
         syms = np.ctypeslib.as_array(res.syms, shape=(res.n_runs,)).copy()
         lens = np.ctypeslib.as_array(res.lens, shape=(res.n_runs,)).copy()
-        info = {k: getattr(res, k) for k in ("n_rounds", "h2d_ms", "par_phase_ms", "ind_phase_ms", "device_ms", "algorithmic_bytes")}
+        info = {k: getattr(res, k) for k in ("n_rounds", "h2d_ms", "par_phase_ms", "ind_phase_ms", "device_ms", "algorithmic_bytes", "induced_on_device")}
         return syms, lens, int(res.sb), int(res.fb), info
     finally:
         L.grlbwt_free_result(C.byref(res))

@@ -25,6 +25,18 @@ struct Mg2Slices {
     bool valid = false;
 };
 
+// device-side induction (induce.cuh): a level's BWT as maximal runs, and a level kept on the device for it
+struct IndBwt {
+    DevBuf<u32> sym, len;
+    u32 n_runs = 0, n_syms = 0;
+};
+
+struct IndLevel {  // a kept level (device): 32-bit symbols
+    u64 alphabet = 0, tot = 0, n_pre = 0;
+    DevBuf<u8> rule_l, rule_r, has_hocc, pre_sym;
+    DevBuf<u64> pre_len;
+};
+
 struct grlgpu_ctx {
     int device = 0;
     int n_sm = 148;
@@ -54,6 +66,7 @@ struct grlgpu_ctx {
 
     // artefacts of the last round (device)
     int lvl_sym_bytes = 4;
+    u64 lvl_alphabet = 0;
     u64 lvl_tot = 0, lvl_npre = 0, lvl_n_in = ~0ull;  // upper bound of the sum of the level's run lengths (all ones: unknown)
     DevBuf<u8> rule_l, rule_r, has_hocc, pre_sym;
     DevBuf<u64> pre_len;
@@ -72,6 +85,11 @@ struct grlgpu_ctx {
     u64 stage_cap = 0, ingest_off = 0, ingest_bytes = 0;
     int stage_cur = 0;
     bool ingesting = false;
+
+    // device-side induction: levels kept on the device (grlgpu_keep_level / grlgpu_level_adopt) and the resulting level-0 BWT
+    std::vector<IndLevel> kept;
+    IndBwt bwt_dev;
+    bool bwt_ready = false;
 
     // multi-GPU rounds (mg2.cuh): global string count, this rank's slices of the last level, bytes it sent in the last round
     u64 mg_n_strings = 0;
@@ -705,6 +723,7 @@ void finish_round(grlgpu_ctx* c, Round& R, u64 tot, u64 n_pre, u64 dict_d, u64 d
     c->n = R.p;
     c->w = w_out;
     c->first = false;
+    c->lvl_alphabet = c->alphabet;  // A of the round that produced the level (the induction needs it: dummies A+1 / A+2, rules from A+3)
     c->alphabet = tot;
     c->round++;
     c->done = out->done != 0;
@@ -741,6 +760,7 @@ void run_round_t(grlgpu_ctx* c, grlgpu_round_t* out) {
 }
 
 #include "mg2.cuh"
+#include "induce.cuh"
 
 void run_round(grlgpu_ctx* c, grlgpu_round_t* out) {
     if (c->first) {
@@ -1418,6 +1438,107 @@ int grlgpu_mg_slice_checksum(grlgpu_ctx* ctx, uint64_t* out4) {
         const Mg2Slices& S = ctx->mg_sl;
         level_checksum(ctx->st, S.sym_bytes, S.rule_l.p, S.rule_r.p, S.has_hocc.p, S.tot_local, S.rank_base, S.pre_sym.p + S.pre_drop * (u64)S.sym_bytes, S.pre_len.p + S.pre_drop,
                        S.n_pre_local, (u64*)out4);
+    });
+}
+
+// ---- induction phase on the device (induce.cuh) ----
+int grlgpu_keep_level(grlgpu_ctx* ctx) {
+    if (!ctx) return GRLGPU_ERR_ARG;
+    if (ctx->round == 0 || !ctx->rule_l.p) return GRLGPU_ERR_STATE;
+    if (ctx->lvl_sym_bytes != 4) return GRLGPU_ERR_LIMIT;
+    return guarded(ctx, [&] {
+        IndLevel L;
+        L.alphabet = ctx->lvl_alphabet; L.tot = ctx->lvl_tot; L.n_pre = ctx->lvl_npre;
+        L.rule_l = std::move(ctx->rule_l); L.rule_r = std::move(ctx->rule_r); L.has_hocc = std::move(ctx->has_hocc);
+        L.pre_sym = std::move(ctx->pre_sym); L.pre_len = std::move(ctx->pre_len);
+        ctx->kept.push_back(std::move(L));
+    });
+}
+int grlgpu_level_adopt(grlgpu_ctx* ctx, uint64_t alphabet, uint64_t tot, uint64_t n_pre, grlgpu_level_ptrs_t* out) {
+    if (!ctx || !out) return GRLGPU_ERR_ARG;
+    return guarded(ctx, [&] {
+        IndLevel L;
+        L.alphabet = alphabet; L.tot = tot; L.n_pre = n_pre;
+        L.rule_l.alloc(tot * 4, ctx->st); L.rule_r.alloc(tot * 4, ctx->st); L.has_hocc.alloc(tot, ctx->st);
+        L.pre_sym.alloc(n_pre * 4, ctx->st); L.pre_len.alloc(n_pre, ctx->st);
+        memset(out, 0, sizeof(*out));
+        out->rule_l = L.rule_l.p; out->rule_r = L.rule_r.p; out->has_hocc = L.has_hocc.p; out->pre_sym = L.pre_sym.p; out->pre_len = L.pre_len.p;
+        out->tot = tot; out->n_pre = n_pre; out->sym_bytes = 4; out->len_bytes = 8; out->device = ctx->device;
+        ctx->kept.push_back(std::move(L));
+        GRL_CUDA(cudaStreamSynchronize(ctx->st));
+    });
+}
+int grlgpu_copy_dev(int dst_device, void* dst, int src_device, const void* src, uint64_t bytes) {
+    if (bytes == 0) return GRLGPU_OK;
+    if (!dst || !src) return GRLGPU_ERR_ARG;
+    if (cudaSetDevice(dst_device) != cudaSuccess) return GRLGPU_ERR_CUDA;
+    const cudaError_t e = dst_device == src_device ? cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice) : cudaMemcpyPeer(dst, dst_device, src, src_device, bytes);
+    return e == cudaSuccess ? GRLGPU_OK : GRLGPU_ERR_CUDA;
+}
+int grlgpu_kept_levels(const grlgpu_ctx* ctx) { return ctx ? (int)ctx->kept.size() : 0; }
+int grlgpu_fetch_kept_level(grlgpu_ctx* ctx, int level, uint64_t* alphabet, uint64_t* tot, uint64_t* n_pre, void* rule_l, void* rule_r, uint8_t* has_hocc, void* pre_sym,
+                            uint64_t* pre_len) {
+    if (!ctx || level < 0 || (size_t)level >= ctx->kept.size()) return GRLGPU_ERR_ARG;
+    return guarded(ctx, [&] {
+        const IndLevel& L = ctx->kept[(size_t)level];
+        if (alphabet) *alphabet = L.alphabet;
+        if (tot) *tot = L.tot;
+        if (n_pre) *n_pre = L.n_pre;
+        if (rule_l) GRL_CUDA(cudaMemcpyAsync(rule_l, L.rule_l.p, L.tot * 4, cudaMemcpyDeviceToHost, ctx->st));
+        if (rule_r) GRL_CUDA(cudaMemcpyAsync(rule_r, L.rule_r.p, L.tot * 4, cudaMemcpyDeviceToHost, ctx->st));
+        if (has_hocc) GRL_CUDA(cudaMemcpyAsync(has_hocc, L.has_hocc.p, L.tot, cudaMemcpyDeviceToHost, ctx->st));
+        if (pre_sym) GRL_CUDA(cudaMemcpyAsync(pre_sym, L.pre_sym.p, L.n_pre * 4, cudaMemcpyDeviceToHost, ctx->st));
+        if (pre_len) GRL_CUDA(cudaMemcpyAsync(pre_len, L.pre_len.p, L.n_pre * 8, cudaMemcpyDeviceToHost, ctx->st));
+        GRL_CUDA(cudaStreamSynchronize(ctx->st));
+    });
+}
+int grlgpu_drop_kept(grlgpu_ctx* ctx) {
+    if (!ctx) return GRLGPU_ERR_ARG;
+    return guarded(ctx, [&] { ctx->kept.clear(); ctx->bwt_dev = IndBwt(); ctx->bwt_ready = false; });
+}
+int grlgpu_induce(grlgpu_ctx* ctx, const void* final_parse, uint64_t n_strings, int cell_bytes, uint64_t n_syms_total, uint64_t* n_runs) {
+    if (!ctx || !n_runs || !(cell_bytes == 1 || cell_bytes == 2 || cell_bytes == 4 || cell_bytes == 8)) return GRLGPU_ERR_ARG;
+    if (ctx->kept.empty()) return GRLGPU_ERR_STATE;
+    if (n_syms_total >= 0xfffffff0ull || n_strings >= 0xfffffff0ull) return GRLGPU_ERR_LIMIT;  // 32-bit offsets on the device
+    return guarded(ctx, [&] {
+        cudaStream_t st = ctx->st;
+        const bool trace = getenv("GRLGPU_TRACE") != nullptr;
+        ctx->bwt_ready = false;
+        const u32 n = (u32)n_strings;
+        IndBwt bwt;
+        {   // deepest level: the final parse in string order (host buffer, or this context's own current parse)
+            DevBuf<u8> fp;
+            const void* dparse = ctx->text;
+            if (final_parse) {
+                fp.alloc(n_strings * (u64)cell_bytes + 16, st);
+                GRL_CUDA(cudaMemcpyAsync(fp.p, final_parse, n_strings * (u64)cell_bytes, cudaMemcpyHostToDevice, st));
+                dparse = fp.p;
+            } else if (!ctx->done || ctx->n != n_strings || ctx->w != cell_bytes) throw Error(GRLGPU_ERR_STATE, "no final parse in the context");
+            DevBuf<u32> sym(n, st);
+            switch (cell_bytes) {
+                case 1: GRL_LAUNCH("ind_parse_syms", n * 5, (ind_parse_syms_kernel<u8>), grid_for(n, 256), 256, 0, st, (const u8*)dparse, n, sym.p); break;
+                case 2: GRL_LAUNCH("ind_parse_syms", n * 6, (ind_parse_syms_kernel<u16>), grid_for(n, 256), 256, 0, st, (const u16*)dparse, n, sym.p); break;
+                case 4: GRL_LAUNCH("ind_parse_syms", n * 8, (ind_parse_syms_kernel<u32>), grid_for(n, 256), 256, 0, st, (const u32*)dparse, n, sym.p); break;
+                default: GRL_LAUNCH("ind_parse_syms", n * 12, (ind_parse_syms_kernel<u64>), grid_for(n, 256), 256, 0, st, (const u64*)dparse, n, sym.p); break;
+            }
+            ind_maximal_runs(sym.p, nullptr, n, n, bwt, st);
+        }
+        // (the kept levels are only dropped once the whole induction has succeeded: after a failure the caller can still fetch them)
+        for (size_t lv = ctx->kept.size(); lv-- > 0;) ind_level_step(bwt, ctx->kept[lv], st, trace);
+        ctx->kept.clear();
+        if ((u64)bwt.n_syms != n_syms_total) throw Error(GRLGPU_ERR_STATE, "induction: the level-0 BWT does not have one symbol per input symbol");
+        *n_runs = bwt.n_runs;
+        ctx->bwt_dev = std::move(bwt);
+        ctx->bwt_ready = true;
+    });
+}
+int grlgpu_fetch_bwt(grlgpu_ctx* ctx, uint32_t* syms, uint32_t* lens) {
+    if (!ctx || !syms || !lens) return GRLGPU_ERR_ARG;
+    if (!ctx->bwt_ready) return GRLGPU_ERR_STATE;
+    return guarded(ctx, [&] {
+        GRL_CUDA(cudaMemcpyAsync(syms, ctx->bwt_dev.sym.p, (u64)ctx->bwt_dev.n_runs * 4, cudaMemcpyDeviceToHost, ctx->st));
+        GRL_CUDA(cudaMemcpyAsync(lens, ctx->bwt_dev.len.p, (u64)ctx->bwt_dev.n_runs * 4, cudaMemcpyDeviceToHost, ctx->st));
+        GRL_CUDA(cudaStreamSynchronize(ctx->st));
     });
 }
 

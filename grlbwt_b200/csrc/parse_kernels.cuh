@@ -513,12 +513,15 @@ __global__ void __launch_bounds__(FD_THREADS, FD_CTAS_PER_SM) dedup_cached_kerne
                 const u32 ci = (u32)(((k0 ^ (k1 * 0x9E3779B97F4A7C15ULL)) * 0xff51afd7ed558ccdULL) >> (64 - FD_CACHE_BITS));
                 for (int way = 0; way < 2; way++) {
                     const u32 c = ci ^ (u32)way;
-                    // the state word is the only location two threads of this phase touch without a barrier in between: every access
-                    // to it is an atomic (acquire: read-modify-write that changes nothing; release: fence, then exchange)
+                    // the cache words are the only locations two threads of this phase touch without a barrier in between (this is the
+                    // miss path): every access to them is an atomic -- the state word acquires (a read-modify-write that changes
+                    // nothing) and releases (fence, then exchange) the key and slot words written by the thread that claimed the way
                     const u32 stt = atomicOr(const_cast<u32*>(&c_state[c]), 0u);
-                    if (stt == 2u && c_k0[c] == k0 && c_k1[c] == k1) break;  // somebody cached it meanwhile
+                    if (stt == 2u && atomicOr(const_cast<u64*>(&c_k0[c]), 0ULL) == k0 && atomicOr(const_cast<u64*>(&c_k1[c]), 0ULL) == k1) break;  // cached meanwhile
                     if (stt == 0u && atomicCAS(const_cast<u32*>(&c_state[c]), 0u, 1u) == 0u) {
-                        c_k0[c] = k0; c_k1[c] = k1; c_slot[c] = slot;
+                        atomicExch(const_cast<u64*>(&c_k0[c]), k0);
+                        atomicExch(const_cast<u64*>(&c_k1[c]), k1);
+                        atomicExch(const_cast<u32*>(&c_slot[c]), slot);
                         __threadfence_block();
                         atomicExch(const_cast<u32*>(&c_state[c]), 2u);
                         break;

@@ -62,6 +62,10 @@ struct ParseResult {
     uint64_t exchange_bytes = 0;        // multi-GPU: bulk bytes sent between the ranks, all rounds, all ranks
     int n_ranks = 1;
     std::string comm_kind;
+    // induction on the device (include/grlgpu.h: grlgpu_keep_level / grlgpu_induce): the level-0 BWT, levels stay empty
+    bool induced_on_device = false;
+    double dev_ind_ms = 0;
+    RunArr bwt_dev;
 };
 
 // the input of the parse phase: a buffer in host memory or a byte range of a file
@@ -325,8 +329,42 @@ inline void widen_levels(ParseResult& res) {
     res.wide = true;
 }
 
+// the levels kept on the device -> level-0 BWT in res.bwt_dev; false (with the kept levels fetched into res.levels32) when the
+// device cannot do it (size limits, memory): the caller then induces on the host
+inline bool induce_on_device(const CtxHandle& ctx, ParseResult& res, const void* final_parse, uint64_t n_strings, int cell_bytes, bool verbose) {
+    const auto t0 = std::chrono::steady_clock::now();
+    uint64_t n_runs = 0;
+    const int rc = grlgpu_induce(ctx.p, final_parse, n_strings, cell_bytes, res.stats.n_syms, &n_runs);
+    if (rc == GRLGPU_OK) {
+        res.bwt_dev.n = n_runs;
+        res.bwt_dev.sym.alloc(n_runs);
+        res.bwt_dev.len32.alloc(n_runs);
+        ctx.check("grlgpu_fetch_bwt", grlgpu_fetch_bwt(ctx.p, res.bwt_dev.sym.data(), res.bwt_dev.len32.data()));
+        grlgpu_drop_kept(ctx.p);
+        res.induced_on_device = true;
+        res.dev_ind_ms = ms_since(t0);
+        return true;
+    }
+    if (rc != GRLGPU_ERR_LIMIT && rc != GRLGPU_ERR_NOMEM) ctx.check("grlgpu_induce", rc);
+    if (verbose) std::cout << "  (the device cannot hold the induction of this collection: " << grlgpu_last_error(ctx.p) << "; inducing on the host)" << std::endl;
+    const int n_kept = grlgpu_kept_levels(ctx.p);  // the levels the failed attempt had not consumed yet are still there: all of them, it fails before consuming
+    if (n_kept != (int)res.rounds.size()) throw GpuError(rc, std::string("grlgpu_induce: ") + grlgpu_strerror(rc) + " (" + grlgpu_last_error(ctx.p) + ")");
+    for (int lv = 0; lv < n_kept; lv++) {
+        Level32 L;
+        uint64_t A = 0, tot = 0, n_pre = 0;
+        ctx.check("grlgpu_fetch_kept_level", grlgpu_fetch_kept_level(ctx.p, lv, &A, &tot, &n_pre, nullptr, nullptr, nullptr, nullptr, nullptr));
+        L.alphabet = A; L.tot_phrases = tot;
+        L.rule_l.resize(tot); L.rule_r.resize(tot); L.has_hocc.resize(tot); L.pre_sym.resize(n_pre); L.pre_len.resize(n_pre);
+        ctx.check("grlgpu_fetch_kept_level", grlgpu_fetch_kept_level(ctx.p, lv, nullptr, nullptr, nullptr, L.rule_l.data(), L.rule_r.data(), L.has_hocc.data(), L.pre_sym.data(),
+                                                                    (uint64_t*)L.pre_len.data()));
+        res.levels32.push_back(std::move(L));
+    }
+    grlgpu_drop_kept(ctx.p);
+    return false;
+}
+
 // ---------------------------------------------------------------- one GPU
-inline ParseResult gpu_par_phase(const TextSource& src, int sym_bytes, int device, bool verbose, size_t fetch_threads = 4) {
+inline ParseResult gpu_par_phase(const TextSource& src, int sym_bytes, int device, bool verbose, bool dev_induction = false, size_t fetch_threads = 4) {
     ParseResult res;
     res.comm_kind = "single GPU";
     CtxHandle ctx(device, 0);
@@ -345,17 +383,39 @@ inline ParseResult gpu_par_phase(const TextSource& src, int sym_bytes, int devic
         dg.tot = r.tot_phrases; dg.n_pre = r.n_pre_runs; dg.parse_len = r.parse_len; dg.n_phrases = r.n_phrases; dg.dict_syms = r.dict_syms;
         ctx.check("grlgpu_level_checksum", grlgpu_level_checksum(ctx.p, dg.cs));
         res.digests.push_back(dg);
-        // the copies of the previous level ran while this round computed; release its device arrays, then hand this level over
-        pool.wait_all();
-        ctx.check("grlgpu_fetch_wait", grlgpu_fetch_wait(ctx.p));
-        const bool wide = res.wide || r.sym_bytes == 8;
-        sinks.emplace_back(new LevelSink());
-        sinks.back()->prepare(r, wide);
-        res.wide = wide;
-        queue_level(ctx, pool, *sinks.back(), 0, 0, tmp32, after);
+        if (dev_induction && r.sym_bytes == 4) {
+            ctx.check("grlgpu_keep_level", grlgpu_keep_level(ctx.p));  // stays on the device for grlgpu_induce
+        } else {
+            if (dev_induction) {  // a wide level: the whole induction goes to the host; move what was kept so far
+                dev_induction = false;
+                for (int lv = 0; lv < grlgpu_kept_levels(ctx.p); lv++) {
+                    uint64_t A = 0, tot = 0, n_pre = 0;
+                    ctx.check("grlgpu_fetch_kept_level", grlgpu_fetch_kept_level(ctx.p, lv, &A, &tot, &n_pre, nullptr, nullptr, nullptr, nullptr, nullptr));
+                    sinks.emplace_back(new LevelSink());
+                    Level32& L = sinks.back()->l32;
+                    L.alphabet = A; L.tot_phrases = tot;
+                    L.rule_l.resize(tot); L.rule_r.resize(tot); L.has_hocc.resize(tot); L.pre_sym.resize(n_pre); L.pre_len.resize(n_pre);
+                    ctx.check("grlgpu_fetch_kept_level", grlgpu_fetch_kept_level(ctx.p, lv, nullptr, nullptr, nullptr, L.rule_l.data(), L.rule_r.data(), L.has_hocc.data(),
+                                                                                L.pre_sym.data(), (uint64_t*)L.pre_len.data()));
+                }
+                grlgpu_drop_kept(ctx.p);
+            }
+            // the copies of the previous level ran while this round computed; release its device arrays, then hand this level over
+            pool.wait_all();
+            ctx.check("grlgpu_fetch_wait", grlgpu_fetch_wait(ctx.p));
+            const bool wide = res.wide || r.sym_bytes == 8;
+            sinks.emplace_back(new LevelSink());
+            sinks.back()->prepare(r, wide);
+            res.wide = wide;
+            queue_level(ctx, pool, *sinks.back(), 0, 0, tmp32, after);
+        }
         if (verbose) print_round(r);
         res.rounds.push_back(r);
         if (r.done) {
+            if (dev_induction) {
+                res.par_ms = ms_since(t0);
+                if (induce_on_device(ctx, res, nullptr, r.parse_len, (int)r.cell_bytes_out, verbose)) return res;
+            }
             std::vector<unsigned char> raw(r.parse_len * (uint64_t)r.cell_bytes_out);
             ctx.check("grlgpu_fetch_parse", grlgpu_fetch_parse(ctx.p, raw.data()));
             res.final_parse.resize(r.parse_len);
@@ -366,6 +426,10 @@ inline ParseResult gpu_par_phase(const TextSource& src, int sym_bytes, int devic
             }
             break;
         }
+    }
+    if (!res.levels32.empty()) {  // the device induction gave up at the end: its levels were fetched into levels32 already
+        res.par_ms = ms_since(t0);
+        return res;
     }
     pool.wait_all();
     ctx.check("grlgpu_fetch_wait", grlgpu_fetch_wait(ctx.p));
@@ -412,10 +476,11 @@ struct HostBarrier {
 enum CommKind { COMM_AUTO = 0, COMM_LOCAL = 1, COMM_NCCL = 2 };
 
 // devices: one entry per rank (a device may repeat: several ranks then share it, and the exchange is the in-process one)
-inline ParseResult gpu_par_phase_mg(const TextSource& src, int sym_bytes, const std::vector<int>& devices, int comm_kind, bool verbose, size_t fetch_threads = 2) {
+inline ParseResult gpu_par_phase_mg(const TextSource& src, int sym_bytes, const std::vector<int>& devices, int comm_kind, bool verbose, bool dev_induction = false,
+                                    size_t fetch_threads = 2) {
     const std::vector<uint64_t> bounds = shard_bounds(src, sym_bytes, (int)devices.size());
     const int G = (int)bounds.size() - 1;
-    if (G <= 1) return gpu_par_phase(src, sym_bytes, devices.at(0), verbose);
+    if (G <= 1) return gpu_par_phase(src, sym_bytes, devices.at(0), verbose, dev_induction);
     bool distinct = true;
     for (int a = 0; a < G; a++)
         for (int b = a + 1; b < G; b++) distinct = distinct && devices[(size_t)a] != devices[(size_t)b];
@@ -442,6 +507,10 @@ inline ParseResult gpu_par_phase_mg(const TextSource& src, int sym_bytes, const 
     std::vector<double> h2d((size_t)G, 0);
     const uint64_t w = (uint64_t)sym_bytes;
     const auto t_start = std::chrono::steady_clock::now();
+    // device induction: rank 0's context adopts every level (the ranks copy their slices into it over NVLink / on the device)
+    bool dev_ind = dev_induction;
+    grlgpu_level_ptrs_t adopt{};
+    double par_done_ms = 0;
 
     auto rank_main = [&](int me) {
         grlgpu_comm* comm = nullptr;
@@ -498,8 +567,41 @@ inline ParseResult gpu_par_phase_mg(const TextSource& src, int sym_bytes, const 
                     if (verbose) print_round(r);
                     res.rounds.push_back(r);
                 }
+                if (dev_ind && me == 0) {
+                    if (r.sym_bytes == 4) ctx.check("grlgpu_level_adopt", grlgpu_level_adopt(ctx.p, r.alphabet, r.tot_phrases, r.n_pre_runs, &adopt));
+                    else {  // a wide level: the induction goes to the host; what rank 0 adopted so far moves into host levels
+                        dev_ind = false;
+                        std::unique_ptr<LevelSink> cur = std::move(sinks.back());
+                        sinks.pop_back();
+                        for (int lv = 0; lv < grlgpu_kept_levels(ctx.p); lv++) {
+                            uint64_t A = 0, tot = 0, n_pre = 0;
+                            ctx.check("grlgpu_fetch_kept_level", grlgpu_fetch_kept_level(ctx.p, lv, &A, &tot, &n_pre, nullptr, nullptr, nullptr, nullptr, nullptr));
+                            sinks.emplace_back(new LevelSink());
+                            Level32& L = sinks.back()->l32;
+                            L.alphabet = A; L.tot_phrases = tot;
+                            L.rule_l.resize(tot); L.rule_r.resize(tot); L.has_hocc.resize(tot); L.pre_sym.resize(n_pre); L.pre_len.resize(n_pre);
+                            ctx.check("grlgpu_fetch_kept_level", grlgpu_fetch_kept_level(ctx.p, lv, nullptr, nullptr, nullptr, L.rule_l.data(), L.rule_r.data(),
+                                                                                        L.has_hocc.data(), L.pre_sym.data(), (uint64_t*)L.pre_len.data()));
+                        }
+                        grlgpu_drop_kept(ctx.p);
+                        sinks.push_back(std::move(cur));
+                    }
+                }
                 bar.wait();
-                queue_level(ctx, pool, *sinks.back(), sl.rank_base, sl.pre_first, tmp32, after);
+                if (dev_ind) {
+                    grlgpu_level_ptrs_t lp;
+                    ctx.check("grlgpu_level_park", grlgpu_level_park(ctx.p, 8, &lp));
+                    const int d0 = adopt.device;
+                    int rc = grlgpu_copy_dev(d0, (char*)adopt.rule_l + sl.rank_base * 4, lp.device, lp.rule_l, lp.tot * 4);
+                    if (rc == GRLGPU_OK) rc = grlgpu_copy_dev(d0, (char*)adopt.rule_r + sl.rank_base * 4, lp.device, lp.rule_r, lp.tot * 4);
+                    if (rc == GRLGPU_OK) rc = grlgpu_copy_dev(d0, (char*)adopt.has_hocc + sl.rank_base, lp.device, lp.has_hocc, lp.tot);
+                    if (rc == GRLGPU_OK) rc = grlgpu_copy_dev(d0, (char*)adopt.pre_sym + sl.pre_first * 4, lp.device, lp.pre_sym, lp.n_pre * 4);
+                    if (rc == GRLGPU_OK) rc = grlgpu_copy_dev(d0, (char*)adopt.pre_len + sl.pre_first * 8, lp.device, lp.pre_len, lp.n_pre * 8);
+                    if (rc != GRLGPU_OK) throw GpuError(rc, "copying a level slice to rank 0's device failed");
+                    ctx.check("grlgpu_fetch_wait", grlgpu_fetch_wait(ctx.p));
+                    bar.wait();  // the adopted level is complete before rank 0 adopts the next one
+                } else
+                    queue_level(ctx, pool, *sinks.back(), sl.rank_base, sl.pre_first, tmp32, after);
                 if (r.done) {
                     std::vector<unsigned char> raw(sl.parse_len_local * (uint64_t)r.cell_bytes_out + 8);
                     ctx.check("grlgpu_fetch_parse", grlgpu_fetch_parse(ctx.p, raw.data()));
@@ -518,6 +620,10 @@ inline ParseResult gpu_par_phase_mg(const TextSource& src, int sym_bytes, const 
             bar.wait();
             grlgpu_comm_destroy(comm);
             comm = nullptr;
+            if (me == 0) par_done_ms = ms_since(t_start);
+            if (dev_ind && me == 0) {  // every level sits in this context, the final parse of all ranks in res.final_parse (string order)
+                if (induce_on_device(ctx, res, res.final_parse.data(), res.final_parse.size(), 8, verbose)) sinks.clear();
+            }
         } catch (const GpuError& e) {
             errors[(size_t)me] = e.what();
             err_status[(size_t)me] = e.status;
@@ -544,15 +650,16 @@ inline ParseResult gpu_par_phase_mg(const TextSource& src, int sym_bytes, const 
             first_bad = r;
     if (first_bad >= 0) throw GpuError(err_status[(size_t)first_bad], "rank " + std::to_string(first_bad) + ": " + errors[(size_t)first_bad]);
     res.wide = false;
-    for (auto& s : sinks) {
-        if (!s->wide) res.levels32.push_back(std::move(s->l32));
-        else {
-            if (!res.wide) widen_levels(res);
-            res.levels.push_back(std::move(s->l64));
+    if (!res.induced_on_device && res.levels32.empty())
+        for (auto& s : sinks) {
+            if (!s->wide) res.levels32.push_back(std::move(s->l32));
+            else {
+                if (!res.wide) widen_levels(res);
+                res.levels.push_back(std::move(s->l64));
+            }
         }
-    }
     for (int r = 0; r < G; r++) { res.exchange_bytes += xbytes[(size_t)r]; res.h2d_ms = std::max(res.h2d_ms, h2d[(size_t)r]); }
-    res.par_ms = ms_since(t_start) - res.h2d_ms;
+    res.par_ms = par_done_ms - res.h2d_ms;
     return res;
 }
 

@@ -55,7 +55,8 @@ struct BwtResult {
     bool narrow = false;
     size_t n_runs() const { return narrow ? runs32.size() : runs.size(); }
     void write(const std::string& path) const {
-        if (narrow) write_rl_bwt(path, runs32.sym.data(), runs32.len.data(), runs32.size(), sb, fb);
+        if (narrow && !runs32.len32.empty()) write_rl_bwt(path, runs32.sym.data(), runs32.len32.data(), runs32.size(), sb, fb);
+        else if (narrow) write_rl_bwt(path, runs32.sym.data(), runs32.len.data(), runs32.size(), sb, fb);
         else write_rl_bwt(path, runs.sym.data(), runs.len.data(), runs.size(), sb, fb);
     }
     uint64_t sb = 0, fb = 0;
@@ -66,15 +67,26 @@ struct BwtResult {
 // devices: one entry per rank; one entry = the single-GPU path. comm_kind: CommKind of gpu_par_phase.hpp
 inline BwtResult build_bwt(const TextSource& src, int sym_bytes, const std::vector<int>& devices, int comm_kind, size_t n_threads, bool verbose) {
     BwtResult out;
-    out.parse = devices.size() > 1 ? gpu_par_phase_mg(src, sym_bytes, devices, comm_kind, verbose) : gpu_par_phase(src, sym_bytes, devices.empty() ? 0 : devices[0], verbose);
+    // the induction runs on the device when it can (fewer than 2^32 symbols, 32-bit level symbols, memory permitting): the levels
+    // then never leave the GPU and the parse phase hands back the level-0 BWT; GRLBWT_HOST_INDUCTION=1 forces the host code
+    const bool dev_ind = getenv("GRLBWT_HOST_INDUCTION") == nullptr && src.bytes / (uint64_t)sym_bytes < 0xfffffff0ull;
+    out.parse = devices.size() > 1 ? gpu_par_phase_mg(src, sym_bytes, devices, comm_kind, verbose, dev_ind)
+                                   : gpu_par_phase(src, sym_bytes, devices.empty() ? 0 : devices[0], verbose, dev_ind);
     auto t0 = std::chrono::steady_clock::now();
-    if (verbose) std::cout << "Inferring the BWT" << std::endl;
-    if (out.parse.wide) out.runs = ind_phase<uint64_t>(out.parse.levels, out.parse.final_parse.data(), out.parse.final_parse.size());
-    else {  // -t host threads drive the induction
-        out.runs32 = ind_phase_mt(out.parse.levels32, out.parse.final_parse.data(), out.parse.final_parse.size(), std::max<size_t>(1, n_threads));
+    if (out.parse.induced_on_device) {
+        if (verbose) std::cout << "Inferring the BWT (on the device): " << out.parse.dev_ind_ms << " ms" << std::endl;
+        out.runs32 = std::move(out.parse.bwt_dev);
         out.narrow = true;
+        out.ind_ms = out.parse.dev_ind_ms;
+    } else {
+        if (verbose) std::cout << "Inferring the BWT" << std::endl;
+        if (out.parse.wide) out.runs = ind_phase<uint64_t>(out.parse.levels, out.parse.final_parse.data(), out.parse.final_parse.size());
+        else {  // -t host threads drive the induction
+            out.runs32 = ind_phase_mt(out.parse.levels32, out.parse.final_parse.data(), out.parse.final_parse.size(), std::max<size_t>(1, n_threads));
+            out.narrow = true;
+        }
+        out.ind_ms = ms_since(t0);
     }
-    out.ind_ms = ms_since(t0);
     // header widths of the level-0 BWT (exact_ind_phase.cpp:274-276 with the level-0 dictionary: alphabet =
     // max_sym+1+3, prev_alphabet = 0, max_sym_freq from collection_stats)
     out.sb = int_ceil((uint64_t)sym_width(out.parse.stats.max_sym + 1 + 3), 8);

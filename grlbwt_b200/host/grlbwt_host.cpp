@@ -23,7 +23,8 @@ static int fill_result(grlbwt::BwtResult& r, grlbwt_result_t* out) {
     if (!out->syms || !out->lens) { free(out->syms); free(out->lens); out->syms = out->lens = nullptr; g_last_error = "out of host memory"; return -100; }
     if (r.narrow) {
         for (size_t k = 0; k < nr; k++) out->syms[k] = r.runs32.sym[k];
-        memcpy(out->lens, r.runs32.len.data(), nr * sizeof(uint64_t));
+        if (r.runs32.len32.empty()) memcpy(out->lens, r.runs32.len.data(), nr * sizeof(uint64_t));
+        else for (size_t k = 0; k < nr; k++) out->lens[k] = r.runs32.len32[k];
     } else {
         memcpy(out->syms, r.runs.sym.data(), nr * sizeof(uint64_t));
         memcpy(out->lens, r.runs.len.data(), nr * sizeof(uint64_t));
@@ -32,6 +33,7 @@ static int fill_result(grlbwt::BwtResult& r, grlbwt_result_t* out) {
     out->h2d_ms = r.parse.h2d_ms;
     out->par_phase_ms = r.parse.par_ms;
     out->ind_phase_ms = r.ind_ms;
+    out->induced_on_device = r.parse.induced_on_device ? 1 : 0;
     for (const auto& rd : r.parse.rounds) { out->device_ms += rd.device_ms; out->algorithmic_bytes += rd.algorithmic_bytes; }
     g_last_digests = r.parse.digests;
     g_last_exchange_bytes = r.parse.exchange_bytes;

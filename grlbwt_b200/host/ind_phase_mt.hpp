@@ -97,8 +97,10 @@ struct Runs32 {
 struct RunArr {
     RawBuf<uint32_t> sym;
     RawBuf<uint64_t> len;
+    RawBuf<uint32_t> len32;  // the level-0 BWT of the device induction comes with 32-bit run lengths (len stays empty then)
     size_t n = 0;
     size_t size() const { return n; }
+    uint64_t length(size_t i) const { return len32.empty() ? len[i] : (uint64_t)len32[i]; }
 };
 
 template <class F>

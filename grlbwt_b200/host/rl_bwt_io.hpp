@@ -28,8 +28,8 @@ struct RunList {
 
 static_assert(__BYTE_ORDER__ == __ORDER_LITTLE_ENDIAN__, "the .rl_bwt records are packed with little-endian stores");
 
-template <class SymT>
-inline void write_rl_bwt(const std::string& path, const SymT* sym, const uint64_t* len, uint64_t n_runs, uint64_t sb, uint64_t fb) {
+template <class SymT, class LenT>
+inline void write_rl_bwt(const std::string& path, const SymT* sym, const LenT* len, uint64_t n_runs, uint64_t sb, uint64_t fb) {
     FILE* f = fopen(path.c_str(), "wb");
     if (!f) throw std::runtime_error("cannot open " + path + " for writing");
     const size_t rec = sb + fb;
@@ -39,7 +39,7 @@ inline void write_rl_bwt(const std::string& path, const SymT* sym, const uint64_
     uint64_t hdr[2] = {sb, fb};
     bool ok = fwrite(hdr, 8, 2, f) == 2;
     for (uint64_t i = 0; i < n_runs && ok; i++) {
-        const uint64_t s64 = (uint64_t)sym[i], l64 = len[i];
+        const uint64_t s64 = (uint64_t)sym[i], l64 = (uint64_t)len[i];
         memcpy(p, &s64, 8);                       // little endian hosts only: the low sb bytes are the record's symbol ...
         memcpy(p + sb, &l64, 8);                  // ... overwritten from offset sb on by the low fb bytes of the length
         p += rec;

@@ -97,7 +97,7 @@ def build_bwt_mg(text: np.ndarray, devices, n_threads: int = 1, comm: int = COMM
     try:
         syms = np.ctypeslib.as_array(res.syms, shape=(res.n_runs,)).copy()
         lens = np.ctypeslib.as_array(res.lens, shape=(res.n_runs,)).copy()
-        info = {k: getattr(res, k) for k in ("n_rounds", "h2d_ms", "par_phase_ms", "ind_phase_ms", "device_ms", "algorithmic_bytes")}
+        info = {k: getattr(res, k) for k in ("n_rounds", "h2d_ms", "par_phase_ms", "ind_phase_ms", "device_ms", "algorithmic_bytes", "induced_on_device")}
         info["digests"] = last_digests()
         info["exchange_bytes"] = int(L.grlbwt_last_exchange_bytes())
         info["comm"] = L.grlbwt_last_comm().decode()

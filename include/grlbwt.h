@@ -23,6 +23,7 @@ typedef struct {
     double ind_phase_ms;      /* host induction */
     double device_ms;         /* sum of CUDA-event round times */
     uint64_t algorithmic_bytes; /* sum of B_r over the rounds */
+    uint64_t induced_on_device; /* 1: the induction phase ran on the GPU (ind_phase_ms is its time); 0: on the host threads */
 } grlbwt_result_t;
 
 /* BWT of a collection held in host memory; status codes of grlgpu.h (or -100 for host-side errors) */

@@ -134,6 +134,27 @@ typedef struct {
 } grlgpu_level_ptrs_t;
 int grlgpu_level_park(grlgpu_ctx* ctx, int len_bytes, grlgpu_level_ptrs_t* out);
 int grlgpu_copy_to_host(int device, void* dst, const void* dev_src, uint64_t bytes);
+/* ---- induction phase on the device (grlbwt_b200/csrc/induce.cuh) -----------------------------------------------------
+ * replaces, for collections of fewer than 2^32 symbols whose levels have 32-bit symbols, the host's level-by-level induction
+ * (exact_algo::ind_phase<b>, lib/exact_algo/exact_ind_phase.cpp:111-386,:603-697): the levels never leave the device.
+ *   grlgpu_keep_level     after a round, instead of fetching the level: keep its artefacts on the device
+ *   grlgpu_level_adopt    multi-GPU: an empty kept level of the given sizes on THIS context; the ranks copy their slices into the
+ *                         returned device arrays with grlgpu_copy_dev (rules at rank_base, runs at pre_first; pre_len is 64-bit)
+ *   grlgpu_induce         the whole induction, deepest level first; final_parse: host buffer of n_strings cells in string
+ *                         order, or NULL to use the context's own final parse. The kept levels are consumed.
+ *                         GRLGPU_ERR_LIMIT / GRLGPU_ERR_NOMEM: the caller falls back to the host induction after
+ *                         grlgpu_fetch_kept_level (the kept levels survive a failure).
+ *   grlgpu_fetch_bwt      the level-0 BWT as maximal runs: n_runs 32-bit symbols and 32-bit lengths */
+int grlgpu_keep_level(grlgpu_ctx* ctx);
+int grlgpu_level_adopt(grlgpu_ctx* ctx, uint64_t alphabet, uint64_t tot, uint64_t n_pre, grlgpu_level_ptrs_t* out);
+int grlgpu_copy_dev(int dst_device, void* dst, int src_device, const void* src, uint64_t bytes);
+int grlgpu_kept_levels(const grlgpu_ctx* ctx);
+int grlgpu_fetch_kept_level(grlgpu_ctx* ctx, int level, uint64_t* alphabet, uint64_t* tot, uint64_t* n_pre, void* rule_l, void* rule_r, uint8_t* has_hocc,
+                            void* pre_sym, uint64_t* pre_len);
+int grlgpu_drop_kept(grlgpu_ctx* ctx);
+int grlgpu_induce(grlgpu_ctx* ctx, const void* final_parse, uint64_t n_strings, int cell_bytes, uint64_t n_syms_total, uint64_t* n_runs);
+int grlgpu_fetch_bwt(grlgpu_ctx* ctx, uint32_t* syms, uint32_t* lens);
+
 /* digest of the last round's level artefacts, computed on the device before they are fetched: four sums mod 2^64
  * {rules weighted by rank, hocc marks weighted by rank, sum of the preliminary-BWT run lengths, runs weighted by symbol}.
  * The sums of the per-rank slices of a multi-GPU level add up to the single-GPU value, so bench.py can check that 1, 2,

@@ -177,6 +177,26 @@ def test_full_bwt_all_cases(golden, all_cases):
         assert info["n_rounds"] == len(g["rounds"]), name
 
 
+def test_host_and_device_induction_agree(golden, all_cases):
+    """the induction phase on the device (default below 2^32 symbols) and on the host threads (GRLBWT_HOST_INDUCTION=1, and
+    whenever a level needs 64-bit symbols) produce the reference's bytes"""
+    names = ("test_byte_alphabet", "test_2bytes_alphabet", "mutated_200x5k", "with_empty", "only_empty", "long_phrases", "u32_rand", "reads_100k", "rep_50x200k",
+             "u16_2M", "mixed_reads", "fuzz_5", "fuzz_77")
+    for name in names:
+        g = golden[name]
+        for host in (False, True):
+            if host:
+                os.environ["GRLBWT_HOST_INDUCTION"] = "1"
+            try:
+                syms, lens, sb, fb, info = G.build_bwt(all_cases[name], n_threads=4)
+            finally:
+                os.environ.pop("GRLBWT_HOST_INDUCTION", None)
+            assert bool(info["induced_on_device"]) == (not host), (name, host)
+            assert hashlib.sha256(O.rl_bwt_bytes(syms, lens, sb, fb)).hexdigest() == g["rl_bwt_sha256"], (name, host)
+    syms, lens, sb, fb, info = G.build_bwt(all_cases["u64_rand"])   # 64-bit symbols: the host induces
+    assert not info["induced_on_device"]
+
+
 def test_async_level_fetch_matches_sync(golden, all_cases):
     """levels fetched on the copy stream while later rounds run equal the synchronously fetched ones"""
     for name in ("mutated_200x5k", "u16_rand", "reads_2000x150"):
