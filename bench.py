@@ -229,8 +229,10 @@ def run_ours(args, rank, world, local_rank):
         raise RuntimeError("bench.py needs a CUDA device: the parse phase has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        host_group = dist.new_group(backend="gloo")   # host-side waits (an NCCL barrier would spin on the GPUs while rank 0 still uses them)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -316,7 +318,7 @@ def run_ours(args, rank, world, local_rank):
                     part = ctx.fetch_parse_local(plen_l).astype(np.uint64)
                     if world > 1:
                         parts = [None] * world if rank == 0 else None
-                        dist.gather_object(part, parts, dst=0)
+                        dist.gather_object(part, parts, dst=0, group=host_group)
                         part = np.concatenate(parts) if rank == 0 else None
                     digest.append(hashlib.sha256(part.tobytes()).hexdigest() if part is not None else None)
                 return d2h
@@ -490,7 +492,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- whole construction: device parse phase + multi-threaded host induction (C++ host, host text -> run-length BCR BWT) ----
     bwt_total = None
     if world > 1:
-        dist.barrier()   # every rank has released its device memory
+        dist.barrier(group=host_group)   # every rank has released its device memory
     if rank == 0 and not args.no_e2e and args.workload == "c2" and args.bwt_reads > 0:
         try:
             import gen
@@ -528,7 +530,7 @@ def run_ours(args, rank, world, local_rank):
                 "digest": dg, "bwt_total": bwt_total, "parse_rounds": parse_rounds, "kernels": kernels}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=host_group)
         dist.destroy_process_group()
 
 

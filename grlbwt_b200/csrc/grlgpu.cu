@@ -1077,7 +1077,7 @@ int grlgpu_text_begin(grlgpu_ctx* ctx, uint64_t n_syms, int sym_bytes, uint64_t 
     if (!ctx || n_syms == 0 || !(sym_bytes == 1 || sym_bytes == 2 || sym_bytes == 4 || sym_bytes == 8)) return GRLGPU_ERR_ARG;
     return guarded(ctx, [&] {
         ensure_copy_stream(ctx);
-        const u64 cap = std::max<u64>(1ull << 20, (stage_bytes ? stage_bytes : (64ull << 20)) / 4096 * 4096);
+        const u64 cap = std::max<u64>(1ull << 20, (stage_bytes ? stage_bytes : (16ull << 20)) / 4096 * 4096);
         if (cap != ctx->stage_cap) {
             for (int k = 0; k < 2; k++) {
                 if (ctx->stage_buf[k]) { GRL_CUDA(cudaFreeHost(ctx->stage_buf[k])); ctx->stage_buf[k] = nullptr; }
@@ -1475,6 +1475,7 @@ int grlgpu_copy_dev(int dst_device, void* dst, int src_device, const void* src, 
     const cudaError_t e = dst_device == src_device ? cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice) : cudaMemcpyPeer(dst, dst_device, src, src_device, bytes);
     return e == cudaSuccess ? GRLGPU_OK : GRLGPU_ERR_CUDA;
 }
+int grlgpu_device_of(const grlgpu_ctx* ctx) { return ctx ? ctx->device : -1; }
 int grlgpu_kept_levels(const grlgpu_ctx* ctx) { return ctx ? (int)ctx->kept.size() : 0; }
 int grlgpu_fetch_kept_level(grlgpu_ctx* ctx, int level, uint64_t* alphabet, uint64_t* tot, uint64_t* n_pre, void* rule_l, void* rule_r, uint8_t* has_hocc, void* pre_sym,
                             uint64_t* pre_len) {
@@ -1524,13 +1525,25 @@ int grlgpu_induce(grlgpu_ctx* ctx, const void* final_parse, uint64_t n_strings, 
             ind_maximal_runs(sym.p, nullptr, n, n, bwt, st);
         }
         // (the kept levels are only dropped once the whole induction has succeeded: after a failure the caller can still fetch them)
-        for (size_t lv = ctx->kept.size(); lv-- > 0;) ind_level_step(bwt, ctx->kept[lv], st, trace);
+        for (size_t lv = ctx->kept.size(); lv-- > 0;) {
+            Timer t(st);
+            t.start();
+            ind_level_step(bwt, ctx->kept[lv], st, trace);
+            t.stop();
+            if (trace) fprintf(stderr, "[grlgpu] induction: level %zu took %.2f ms\n", lv, t.ms());
+        }
         ctx->kept.clear();
         if ((u64)bwt.n_syms != n_syms_total) throw Error(GRLGPU_ERR_STATE, "induction: the level-0 BWT does not have one symbol per input symbol");
         *n_runs = bwt.n_runs;
         ctx->bwt_dev = std::move(bwt);
         ctx->bwt_ready = true;
     });
+}
+int grlgpu_bwt_ptrs(grlgpu_ctx* ctx, const uint32_t** d_syms, const uint32_t** d_lens, uint64_t* n_runs) {
+    if (!ctx || !d_syms || !d_lens || !n_runs) return GRLGPU_ERR_ARG;
+    if (!ctx->bwt_ready) return GRLGPU_ERR_STATE;
+    *d_syms = ctx->bwt_dev.sym.p; *d_lens = ctx->bwt_dev.len.p; *n_runs = ctx->bwt_dev.n_runs;
+    return GRLGPU_OK;
 }
 int grlgpu_fetch_bwt(grlgpu_ctx* ctx, uint32_t* syms, uint32_t* lens) {
     if (!ctx || !syms || !lens) return GRLGPU_ERR_ARG;

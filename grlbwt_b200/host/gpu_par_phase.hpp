@@ -146,6 +146,10 @@ struct CtxHandle {  // RAII around grlgpu_ctx
 inline double load_text(const CtxHandle& ctx, const TextSource& src, int sym_bytes) {
     const auto t0 = std::chrono::steady_clock::now();
     if (src.bytes == 0 || src.bytes % (uint64_t)sym_bytes) throw GpuError(GRLGPU_ERR_ILL_FORMED, "the input is empty or not a whole number of symbols");
+    if (src.mem) {  // already in host memory: one copy call (the driver stages pageable memory at ~10 GB/s; a caller with pinned memory gets DMA rate)
+        ctx.check("grlgpu_set_text", grlgpu_set_text(ctx.p, src.mem + src.offset, src.bytes / (uint64_t)sym_bytes, sym_bytes));
+        return ms_since(t0);
+    }
     ctx.check("grlgpu_text_begin", grlgpu_text_begin(ctx.p, src.bytes / (uint64_t)sym_bytes, sym_bytes, 0));
     int fd = -1;
     if (!src.mem) {
@@ -336,13 +340,24 @@ inline bool induce_on_device(const CtxHandle& ctx, ParseResult& res, const void*
     uint64_t n_runs = 0;
     const int rc = grlgpu_induce(ctx.p, final_parse, n_strings, cell_bytes, res.stats.n_syms, &n_runs);
     if (rc == GRLGPU_OK) {
+        const double compute_ms = ms_since(t0);
         res.bwt_dev.n = n_runs;
         res.bwt_dev.sym.alloc(n_runs);
         res.bwt_dev.len32.alloc(n_runs);
-        ctx.check("grlgpu_fetch_bwt", grlgpu_fetch_bwt(ctx.p, res.bwt_dev.sym.data(), res.bwt_dev.len32.data()));
+        {   // the runs come back through several copy threads (pageable destination: each thread stages its own pieces)
+            const uint32_t *ds = nullptr, *dl = nullptr;
+            uint64_t nr = 0;
+            ctx.check("grlgpu_bwt_ptrs", grlgpu_bwt_ptrs(ctx.p, &ds, &dl, &nr));
+            const int device = grlgpu_device_of(ctx.p);
+            FetchPool pool(6);
+            pool.enqueue(device, res.bwt_dev.sym.data(), ds, nr * 4);
+            pool.enqueue(device, res.bwt_dev.len32.data(), dl, nr * 4);
+            pool.wait_all();
+        }
         grlgpu_drop_kept(ctx.p);
         res.induced_on_device = true;
         res.dev_ind_ms = ms_since(t0);
+        if (verbose) std::cout << "  induction on the device: " << compute_ms << " ms, " << n_runs << " runs copied back in " << res.dev_ind_ms - compute_ms << " ms" << std::endl;
         return true;
     }
     if (rc != GRLGPU_ERR_LIMIT && rc != GRLGPU_ERR_NOMEM) ctx.check("grlgpu_induce", rc);

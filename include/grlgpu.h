@@ -86,7 +86,7 @@ int grlgpu_set_text_device(grlgpu_ctx* ctx, const void* dev_text, uint64_t n_sym
 
 /* Streaming ingest of the round-1 input (what i_file_stream's 8 MB windows do for the reference,
  * external/cdt/include/file_streams.hpp:93-105): begin allocates the device text and two pinned staging buffers of
- * stage_bytes (0: 64 MB); stage hands out the next free buffer (*cap bytes of it may be filled, e.g. by read() from the input
+ * stage_bytes (0: 16 MB); stage hands out the next free buffer (*cap bytes of it may be filled, e.g. by read() from the input
  * file); commit enqueues its copy to the device on the copy stream and returns at once, so the caller fills the other
  * buffer meanwhile; end waits for the last copy. The bytes must be committed in text order. */
 int grlgpu_text_begin(grlgpu_ctx* ctx, uint64_t n_syms, int sym_bytes, uint64_t stage_bytes);
@@ -149,11 +149,14 @@ int grlgpu_keep_level(grlgpu_ctx* ctx);
 int grlgpu_level_adopt(grlgpu_ctx* ctx, uint64_t alphabet, uint64_t tot, uint64_t n_pre, grlgpu_level_ptrs_t* out);
 int grlgpu_copy_dev(int dst_device, void* dst, int src_device, const void* src, uint64_t bytes);
 int grlgpu_kept_levels(const grlgpu_ctx* ctx);
+int grlgpu_device_of(const grlgpu_ctx* ctx);  /* CUDA device of the context */
 int grlgpu_fetch_kept_level(grlgpu_ctx* ctx, int level, uint64_t* alphabet, uint64_t* tot, uint64_t* n_pre, void* rule_l, void* rule_r, uint8_t* has_hocc,
                             void* pre_sym, uint64_t* pre_len);
 int grlgpu_drop_kept(grlgpu_ctx* ctx);
 int grlgpu_induce(grlgpu_ctx* ctx, const void* final_parse, uint64_t n_strings, int cell_bytes, uint64_t n_syms_total, uint64_t* n_runs);
 int grlgpu_fetch_bwt(grlgpu_ctx* ctx, uint32_t* syms, uint32_t* lens);
+/* the same arrays as DEVICE addresses (valid until grlgpu_drop_kept / the next grlgpu_induce), for parallel grlgpu_copy_to_host */
+int grlgpu_bwt_ptrs(grlgpu_ctx* ctx, const uint32_t** d_syms, const uint32_t** d_lens, uint64_t* n_runs);
 
 /* digest of the last round's level artefacts, computed on the device before they are fetched: four sums mod 2^64
  * {rules weighted by rank, hocc marks weighted by rank, sum of the preliminary-BWT run lengths, runs weighted by symbol}.
