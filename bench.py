@@ -497,21 +497,27 @@ def run_ours(args, rank, world, local_rank):
         try:
             import gen
             thr = os.cpu_count() or 1
-            sample = gen.dna_reads(min(args.reads, args.bwt_reads), READ_LEN, seed=42)
+            sample = torch.from_numpy(gen.dna_reads(min(args.reads, args.bwt_reads), READ_LEN, seed=42)).pin_memory().numpy()
             devs = list(range(world))
-            G.build_bwt(sample[: 151 * 1000], n_threads=thr)  # warm the host library
-            if world == 1:
-                _, lens_, _, _, info = G.build_bwt(sample, device=0, n_threads=thr)
-            else:
-                _, lens_, _, _, info = mg.build_bwt_mg(sample, devs, n_threads=thr, comm=mg.COMM_AUTO)
-            tot_ms = info["h2d_ms"] + info["par_phase_ms"] + info["ind_phase_ms"]
-            bwt_total = {"value": round(sample.nbytes / 1e6 / (tot_ms / 1e3), 3), "unit": "MB/s", "n_gpus": world,
-                         "sample": f"{sample.size // 151} reads x {READ_LEN} bp ({sample.nbytes / 1e6:.0f} MB)",
+            # caller-owned pinned landing zone for the run-length BWT (a run per symbol at most), reused from call to call
+            out_s = torch.empty(sample.size, dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
+            out_l = torch.empty(sample.size, dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
+            G.build_bwt_to(sample[: 151 * 1000], out_s, out_l, devices=devs, n_threads=thr)  # warm the libraries
+            best = None
+            for _ in range(2):
+                t0 = time.perf_counter()
+                n_runs, _, _, info = G.build_bwt_to(sample, out_s, out_l, devices=devs, n_threads=thr)
+                wall = (time.perf_counter() - t0) * 1e3
+                if best is None or wall < best[0]:
+                    best = (wall, n_runs, info)
+            wall, n_runs, info = best
+            bwt_total = {"value": round(sample.nbytes / 1e6 / (wall / 1e3), 3), "unit": "MB/s", "n_gpus": world,
+                         "sample": f"{sample.size // 151} reads x {READ_LEN} bp ({sample.nbytes / 1e6:.0f} MB)", "wall_ms": round(wall, 1),
                          "h2d_ms": round(info["h2d_ms"], 1), "parse_phase_ms": round(info["par_phase_ms"], 1), "induction_ms": round(info["ind_phase_ms"], 1),
                          "induction": "device (grlgpu_induce: levels never leave the GPU)" if info.get("induced_on_device") else "host threads",
-                         "host_threads": thr, "bwt_runs": int(lens_.size), "exchange": info.get("comm"),
-                         "what": "input MB/s to BCR BWT: host text -> run-length BCR BWT in host memory through the C++ host (grlbwt_build / grlbwt_build_mg: "
-                                 "one host thread per GPU), file I/O excluded"}
+                         "host_threads": thr, "bwt_runs": int(n_runs),
+                         "what": "input MB/s to BCR BWT: pinned host text -> run-length BCR BWT in pinned host memory through the C++ host (grlbwt_build_to: "
+                                 "one host thread per GPU, fresh device contexts every call), wall clock of the call, best of 2; file I/O excluded"}
         except Exception as e:
             bwt_total = {"value": None, "error": str(e)[:300]}
 

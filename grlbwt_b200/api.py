@@ -122,6 +122,7 @@ def lib_host():
         L.grlbwt_build_file.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.grlbwt_last_error.restype = C.c_char_p
         L.grlbwt_build_mg.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(BwtResult)]
+        L.grlbwt_build_to.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(BwtResult)]
         L.grlbwt_last_digests.argtypes = [C.c_void_p, C.c_uint64]
         L.grlbwt_last_digests.restype = C.c_uint64
         L.grlbwt_last_exchange_bytes.restype = C.c_uint64
@@ -352,6 +353,22 @@ def build_bwt(text: np.ndarray, device: int = 0, n_threads: int = 1, verbose: bo
         return syms, lens, int(res.sb), int(res.fb), info
     finally:
         L.grlbwt_free_result(C.byref(res))
+
+
+def build_bwt_to(text: np.ndarray, out_syms: np.ndarray, out_lens: np.ndarray, devices=(0,), n_threads: int = 1, comm: int = 0):
+    """Whole construction with the run-length BWT delivered into caller-owned uint32 arrays (e.g. views of pinned memory that is
+    reused from call to call). -> (n_runs, sb, fb, info)"""
+    L = lib_host()
+    text = np.ascontiguousarray(text)
+    assert out_syms.dtype == np.uint32 and out_lens.dtype == np.uint32 and out_syms.flags.c_contiguous and out_lens.flags.c_contiguous
+    dv = np.asarray(devices, np.int32)
+    res = BwtResult()
+    rc = L.grlbwt_build_to(_ptr(text), text.size, text.dtype.itemsize, _ptr(dv), dv.size, n_threads, comm, _ptr(out_syms), _ptr(out_lens),
+                           min(out_syms.size, out_lens.size), C.byref(res))
+    if rc != 0:
+        raise GrlGpuError(rc, L.grlbwt_last_error().decode())
+    info = {k: getattr(res, k) for k in ("n_rounds", "h2d_ms", "par_phase_ms", "ind_phase_ms", "device_ms", "algorithmic_bytes", "induced_on_device")}
+    return int(res.n_runs), int(res.sb), int(res.fb), info
 
 
 def build_bwt_file(inp: str, out: str, sym_bytes: int = 1, device: int = 0, n_threads: int = 1, verbose: bool = False):

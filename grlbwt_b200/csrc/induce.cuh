@@ -135,13 +135,16 @@ static __global__ void __launch_bounds__(256) ind_item_stream_len_kernel(const u
 }
 // D: stream-run starts: containing item, coincidence with an item start
 static __global__ void __launch_bounds__(256) ind_run_item_kernel(const u32* __restrict__ cum_s, u32 m, const u32* __restrict__ it_s, u32 n_items, u32* __restrict__ citem,
-                                                                 u32* __restrict__ ncflag) {
+                                                                 u32* __restrict__ ncflag, u32* rcnt) {
     const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m) return;
     const u32 x = cum_s[j];
     const u32 c = ind_upper_bound(it_s, n_items, x) - 1;  // last item whose stream offset is <= x: the stream item that holds x
     citem[j] = c;
     ncflag[j] = it_s[c] == x ? 0u : 1u;
+    // runs held by item c: their exclusive prefix over the items is, for every item t, the number of stream runs that start before
+    // t's stream offset (a run starts before it_s[t] exactly when its item comes before t) -- no search from the items' side
+    atomicAdd(&rcnt[c], 1u);
 }
 static __global__ void __launch_bounds__(256) ind_pieces_from_runs_kernel(const u32* __restrict__ cum_s, const u32* __restrict__ bsym2, u32 m, const u32* __restrict__ citem,
                                                                          const u32* __restrict__ ncflag, const u32* __restrict__ nc_before,
@@ -155,14 +158,14 @@ static __global__ void __launch_bounds__(256) ind_pieces_from_runs_kernel(const 
 }
 static __global__ void __launch_bounds__(256) ind_pieces_from_items_kernel(const u32* __restrict__ it_sym, const u32* __restrict__ it_s, const u32* __restrict__ it_o,
                                                                           u32 n_items, const u32* __restrict__ cum_s, const u32* __restrict__ bsym2, u32 m,
-                                                                          const u32* __restrict__ nc_before, u32* __restrict__ p_sym, u32* __restrict__ p_off) {
+                                                                          const u32* __restrict__ runs_before, const u32* __restrict__ nc_before,
+                                                                          u32* __restrict__ p_sym, u32* __restrict__ p_off) {
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_items) return;
-    const u32 s = it_s[t];
-    const u32 r = ind_lower_bound(cum_s, m, s);          // stream runs that start before the item's stream offset
+    const u32 r = runs_before[t];                        // stream runs that start before the item's stream offset
     const u32 q = t + nc_before[r];
     u32 sym = it_sym[t];
-    if (sym == IND_STREAM) sym = bsym2[ind_upper_bound(cum_s, m, s) - 1];  // the stream run that holds the slice's first symbol
+    if (sym == IND_STREAM) sym = bsym2[(r < m && cum_s[r] == it_s[t]) ? r : r - 1];  // the stream run that holds the slice's first symbol
     p_sym[q] = sym;
     p_off[q] = it_o[t];
 }
@@ -250,17 +253,19 @@ inline void ind_level_step(IndBwt& bwt, const IndLevel& L, cudaStream_t st, bool
     const u32 n_out = ind_scan_total(it_len.p, it_o.p, n_items, st);
     it_len.release();
     // ---- D: pieces ----
-    DevBuf<u32> cum_s((u64)m + 1, st), citem(m, st), ncflag(m, st), nc_before((u64)m + 1, st);
+    DevBuf<u32> cum_s((u64)m + 1, st), citem(m, st), ncflag(m, st), nc_before((u64)m + 1, st), runs_before((u64)n_items + 1, st);
     ind_scan_total(bwt.len.p, cum_s.p, m, st);
-    GRL_LAUNCH("ind_run_item", m * 40, ind_run_item_kernel, grid_for(m, 256), 256, 0, st, cum_s.p, m, it_s.p, n_items, citem.p, ncflag.p);
+    runs_before.zero();
+    GRL_LAUNCH("ind_run_item", m * 40, ind_run_item_kernel, grid_for(m, 256), 256, 0, st, cum_s.p, m, it_s.p, n_items, citem.p, ncflag.p, runs_before.p);
+    ind_scan_total(runs_before.p, runs_before.p, n_items, st);
     const u32 n_nc = ind_scan_total(ncflag.p, nc_before.p, m, st);
     const u32 n_pieces = n_items + n_nc;
     DevBuf<u32> p_sym(n_pieces, st), p_off(n_pieces, st);
     GRL_LAUNCH("ind_pieces_runs", m * 40, ind_pieces_from_runs_kernel, grid_for(m, 256), 256, 0, st, cum_s.p, bsym2.p, m, citem.p, ncflag.p, nc_before.p, it_s.p, it_o.p, p_sym.p, p_off.p);
-    GRL_LAUNCH("ind_pieces_items", n_items * 48, ind_pieces_from_items_kernel, grid_for(n_items, 256), 256, 0, st, it_sym.p, it_s.p, it_o.p, n_items, cum_s.p, bsym2.p, m, nc_before.p,
-               p_sym.p, p_off.p);
+    GRL_LAUNCH("ind_pieces_items", n_items * 40, ind_pieces_from_items_kernel, grid_for(n_items, 256), 256, 0, st, it_sym.p, it_s.p, it_o.p, n_items, cum_s.p, bsym2.p, m,
+               runs_before.p, nc_before.p, p_sym.p, p_off.p);
     GRL_CUDA(cudaStreamSynchronize(st));
-    it_sym.release(); it_s.release(); it_o.release(); cum_s.release(); citem.release(); ncflag.release(); nc_before.release(); bsym2.release();
+    it_sym.release(); it_s.release(); it_o.release(); cum_s.release(); citem.release(); ncflag.release(); nc_before.release(); bsym2.release(); runs_before.release();
     // ---- E: maximal runs ----
     IndBwt next;
     ind_maximal_runs(p_sym.p, p_off.p, n_pieces, n_out, next, st);

@@ -16,6 +16,7 @@
 #include <array>
 #include <chrono>
 #include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
@@ -64,8 +65,17 @@ struct ParseResult {
     std::string comm_kind;
     // induction on the device (include/grlgpu.h: grlgpu_keep_level / grlgpu_induce): the level-0 BWT, levels stay empty
     bool induced_on_device = false;
-    double dev_ind_ms = 0;
+    double dev_ind_ms = 0, dev_ind_compute_ms = 0;
     RunArr bwt_dev;
+    bool bwt_in_caller_buffers = false;  // the runs were written to the caller's OutputBuffers (bwt_dev holds only the count)
+};
+
+// caller-owned landing zone for the level-0 BWT of the device induction (32-bit symbols and lengths); pinned memory makes the
+// copy-back a plain DMA instead of a first-touch of fresh pages
+struct OutputBuffers {
+    uint32_t* sym = nullptr;
+    uint32_t* len = nullptr;
+    uint64_t cap = 0;  // runs each array can hold
 };
 
 // the input of the parse phase: a buffer in host memory or a byte range of a file
@@ -240,23 +250,25 @@ inline std::vector<uint64_t> shard_bounds(const TextSource& src, int sym_bytes, 
     return b;
 }
 
+// (stdio, not iostream: the library is also loaded into processes that carry another libstdc++, e.g. Python with torch)
 inline void print_stats(const grlgpu_stats_t& s) {
-    std::cout << "Stats: " << std::endl;
-    std::cout << "  Smallest symbol               : " << s.min_sym << std::endl;
-    std::cout << "  Greatest symbol               : " << s.max_sym << std::endl;
-    std::cout << "  Number of symbols in the file : " << s.n_syms << std::endl;
-    std::cout << "  Number of strings             : " << s.n_strings << std::endl;
-    std::cout << "Parsing the text:    " << std::endl;
+    printf("Stats: \n");
+    printf("  Smallest symbol               : %llu\n", (unsigned long long)s.min_sym);
+    printf("  Greatest symbol               : %llu\n", (unsigned long long)s.max_sym);
+    printf("  Number of symbols in the file : %llu\n", (unsigned long long)s.n_syms);
+    printf("  Number of strings             : %llu\n", (unsigned long long)s.n_strings);
+    printf("Parsing the text:    \n");
+    fflush(stdout);
 }
 inline void print_round(const grlgpu_round_t& r) {
-    std::cout << "  Parsing round " << r.round << std::endl;
-    std::cout << "    Stats:" << std::endl;
-    std::cout << "      Parsing phrases:                  " << r.n_phrases << std::endl;
-    std::cout << "      Number of symbols in the phrases: " << r.dict_syms << std::endl;
-    std::cout << "      Number of unsolved BWT blocks:    " << r.tot_phrases << std::endl;
-    std::cout << "      Parse size:                       " << r.parse_len << std::endl;
-    std::cout << "      Device time (ms):                 " << r.device_ms << " (text " << r.text_pass_ms << ", dictionary " << r.dict_ms << ", rewrite "
-              << r.rewrite_ms << ")" << std::endl;
+    printf("  Parsing round %llu\n", (unsigned long long)r.round);
+    printf("    Stats:\n");
+    printf("      Parsing phrases:                  %llu\n", (unsigned long long)r.n_phrases);
+    printf("      Number of symbols in the phrases: %llu\n", (unsigned long long)r.dict_syms);
+    printf("      Number of unsolved BWT blocks:    %llu\n", (unsigned long long)r.tot_phrases);
+    printf("      Parse size:                       %llu\n", (unsigned long long)r.parse_len);
+    printf("      Device time (ms):                 %g (text %g, dictionary %g, rewrite %g)\n", r.device_ms, r.text_pass_ms, r.dict_ms, r.rewrite_ms);
+    fflush(stdout);
 }
 
 // storage of one level on the host, shared by the ranks of a multi-GPU run (each fills its own part)
@@ -335,21 +347,26 @@ inline void widen_levels(ParseResult& res) {
 
 // the levels kept on the device -> level-0 BWT in res.bwt_dev; false (with the kept levels fetched into res.levels32) when the
 // device cannot do it (size limits, memory): the caller then induces on the host
-inline bool induce_on_device(const CtxHandle& ctx, ParseResult& res, const void* final_parse, uint64_t n_strings, int cell_bytes, bool verbose) {
+inline bool induce_on_device(const CtxHandle& ctx, ParseResult& res, const void* final_parse, uint64_t n_strings, int cell_bytes, bool verbose,
+                             const OutputBuffers* ob = nullptr) {
     const auto t0 = std::chrono::steady_clock::now();
     uint64_t n_runs = 0;
     const int rc = grlgpu_induce(ctx.p, final_parse, n_strings, cell_bytes, res.stats.n_syms, &n_runs);
     if (rc == GRLGPU_OK) {
         const double compute_ms = ms_since(t0);
         res.bwt_dev.n = n_runs;
-        res.bwt_dev.sym.alloc(n_runs);
-        res.bwt_dev.len32.alloc(n_runs);
-        {   // the runs come back through several copy threads (pageable destination: each thread stages its own pieces)
+        res.dev_ind_compute_ms = compute_ms;
+        if (ob && ob->sym && ob->len && ob->cap >= n_runs) {  // straight into the caller's (pinned) buffers
+            ctx.check("grlgpu_fetch_bwt", grlgpu_fetch_bwt(ctx.p, ob->sym, ob->len));
+            res.bwt_in_caller_buffers = true;
+        } else {   // fresh pageable arrays: several copy threads, each staging (and first-touching) its own pieces
+            res.bwt_dev.sym.alloc(n_runs);
+            res.bwt_dev.len32.alloc(n_runs);
             const uint32_t *ds = nullptr, *dl = nullptr;
             uint64_t nr = 0;
             ctx.check("grlgpu_bwt_ptrs", grlgpu_bwt_ptrs(ctx.p, &ds, &dl, &nr));
             const int device = grlgpu_device_of(ctx.p);
-            FetchPool pool(6);
+            FetchPool pool(8);
             pool.enqueue(device, res.bwt_dev.sym.data(), ds, nr * 4);
             pool.enqueue(device, res.bwt_dev.len32.data(), dl, nr * 4);
             pool.wait_all();
@@ -357,11 +374,11 @@ inline bool induce_on_device(const CtxHandle& ctx, ParseResult& res, const void*
         grlgpu_drop_kept(ctx.p);
         res.induced_on_device = true;
         res.dev_ind_ms = ms_since(t0);
-        if (verbose) std::cout << "  induction on the device: " << compute_ms << " ms, " << n_runs << " runs copied back in " << res.dev_ind_ms - compute_ms << " ms" << std::endl;
+        if (verbose) { printf("  induction on the device: %.1f ms, %llu runs copied back in %.1f ms\n", compute_ms, (unsigned long long)n_runs, res.dev_ind_ms - compute_ms); fflush(stdout); }
         return true;
     }
     if (rc != GRLGPU_ERR_LIMIT && rc != GRLGPU_ERR_NOMEM) ctx.check("grlgpu_induce", rc);
-    if (verbose) std::cout << "  (the device cannot hold the induction of this collection: " << grlgpu_last_error(ctx.p) << "; inducing on the host)" << std::endl;
+    if (verbose) { printf("  (the device cannot hold the induction of this collection: %s; inducing on the host)\n", grlgpu_last_error(ctx.p)); fflush(stdout); }
     const int n_kept = grlgpu_kept_levels(ctx.p);  // the levels the failed attempt had not consumed yet are still there: all of them, it fails before consuming
     if (n_kept != (int)res.rounds.size()) throw GpuError(rc, std::string("grlgpu_induce: ") + grlgpu_strerror(rc) + " (" + grlgpu_last_error(ctx.p) + ")");
     for (int lv = 0; lv < n_kept; lv++) {
@@ -379,7 +396,8 @@ inline bool induce_on_device(const CtxHandle& ctx, ParseResult& res, const void*
 }
 
 // ---------------------------------------------------------------- one GPU
-inline ParseResult gpu_par_phase(const TextSource& src, int sym_bytes, int device, bool verbose, bool dev_induction = false, size_t fetch_threads = 4) {
+inline ParseResult gpu_par_phase(const TextSource& src, int sym_bytes, int device, bool verbose, bool dev_induction = false, const OutputBuffers* ob = nullptr,
+                                 size_t fetch_threads = 4) {
     ParseResult res;
     res.comm_kind = "single GPU";
     CtxHandle ctx(device, 0);
@@ -429,7 +447,7 @@ inline ParseResult gpu_par_phase(const TextSource& src, int sym_bytes, int devic
         if (r.done) {
             if (dev_induction) {
                 res.par_ms = ms_since(t0);
-                if (induce_on_device(ctx, res, nullptr, r.parse_len, (int)r.cell_bytes_out, verbose)) return res;
+                if (induce_on_device(ctx, res, nullptr, r.parse_len, (int)r.cell_bytes_out, verbose, ob)) return res;
             }
             std::vector<unsigned char> raw(r.parse_len * (uint64_t)r.cell_bytes_out);
             ctx.check("grlgpu_fetch_parse", grlgpu_fetch_parse(ctx.p, raw.data()));
@@ -492,10 +510,10 @@ enum CommKind { COMM_AUTO = 0, COMM_LOCAL = 1, COMM_NCCL = 2 };
 
 // devices: one entry per rank (a device may repeat: several ranks then share it, and the exchange is the in-process one)
 inline ParseResult gpu_par_phase_mg(const TextSource& src, int sym_bytes, const std::vector<int>& devices, int comm_kind, bool verbose, bool dev_induction = false,
-                                    size_t fetch_threads = 2) {
+                                    const OutputBuffers* ob = nullptr, size_t fetch_threads = 2) {
     const std::vector<uint64_t> bounds = shard_bounds(src, sym_bytes, (int)devices.size());
     const int G = (int)bounds.size() - 1;
-    if (G <= 1) return gpu_par_phase(src, sym_bytes, devices.at(0), verbose, dev_induction);
+    if (G <= 1) return gpu_par_phase(src, sym_bytes, devices.at(0), verbose, dev_induction, ob);
     bool distinct = true;
     for (int a = 0; a < G; a++)
         for (int b = a + 1; b < G; b++) distinct = distinct && devices[(size_t)a] != devices[(size_t)b];
@@ -637,7 +655,7 @@ inline ParseResult gpu_par_phase_mg(const TextSource& src, int sym_bytes, const 
             comm = nullptr;
             if (me == 0) par_done_ms = ms_since(t_start);
             if (dev_ind && me == 0) {  // every level sits in this context, the final parse of all ranks in res.final_parse (string order)
-                if (induce_on_device(ctx, res, res.final_parse.data(), res.final_parse.size(), 8, verbose)) sinks.clear();
+                if (induce_on_device(ctx, res, res.final_parse.data(), res.final_parse.size(), 8, verbose, ob)) sinks.clear();
             }
         } catch (const GpuError& e) {
             errors[(size_t)me] = e.what();

@@ -65,21 +65,22 @@ struct BwtResult {
 };
 
 // devices: one entry per rank; one entry = the single-GPU path. comm_kind: CommKind of gpu_par_phase.hpp
-inline BwtResult build_bwt(const TextSource& src, int sym_bytes, const std::vector<int>& devices, int comm_kind, size_t n_threads, bool verbose) {
+inline BwtResult build_bwt(const TextSource& src, int sym_bytes, const std::vector<int>& devices, int comm_kind, size_t n_threads, bool verbose,
+                           const OutputBuffers* ob = nullptr) {
     BwtResult out;
     // the induction runs on the device when it can (fewer than 2^32 symbols, 32-bit level symbols, memory permitting): the levels
     // then never leave the GPU and the parse phase hands back the level-0 BWT; GRLBWT_HOST_INDUCTION=1 forces the host code
     const bool dev_ind = getenv("GRLBWT_HOST_INDUCTION") == nullptr && src.bytes / (uint64_t)sym_bytes < 0xfffffff0ull;
-    out.parse = devices.size() > 1 ? gpu_par_phase_mg(src, sym_bytes, devices, comm_kind, verbose, dev_ind)
-                                   : gpu_par_phase(src, sym_bytes, devices.empty() ? 0 : devices[0], verbose, dev_ind);
+    out.parse = devices.size() > 1 ? gpu_par_phase_mg(src, sym_bytes, devices, comm_kind, verbose, dev_ind, ob)
+                                   : gpu_par_phase(src, sym_bytes, devices.empty() ? 0 : devices[0], verbose, dev_ind, ob);
     auto t0 = std::chrono::steady_clock::now();
     if (out.parse.induced_on_device) {
-        if (verbose) std::cout << "Inferring the BWT (on the device): " << out.parse.dev_ind_ms << " ms" << std::endl;
+        if (verbose) { printf("Inferring the BWT (on the device): %.1f ms\n", out.parse.dev_ind_ms); fflush(stdout); }
         out.runs32 = std::move(out.parse.bwt_dev);
         out.narrow = true;
         out.ind_ms = out.parse.dev_ind_ms;
     } else {
-        if (verbose) std::cout << "Inferring the BWT" << std::endl;
+        if (verbose) { printf("Inferring the BWT\n"); fflush(stdout); }
         if (out.parse.wide) out.runs = ind_phase<uint64_t>(out.parse.levels, out.parse.final_parse.data(), out.parse.final_parse.size());
         else {  // -t host threads drive the induction
             out.runs32 = ind_phase_mt(out.parse.levels32, out.parse.final_parse.data(), out.parse.final_parse.size(), std::max<size_t>(1, n_threads));

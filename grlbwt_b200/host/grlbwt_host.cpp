@@ -79,6 +79,47 @@ int grlbwt_build_mg(const void* text, uint64_t n_syms, int sym_bytes, const int*
     }
 }
 
+// whole construction with the level-0 BWT delivered into caller-owned 32-bit arrays (see include/grlbwt.h)
+int grlbwt_build_to(const void* text, uint64_t n_syms, int sym_bytes, const int* devices, int n_ranks, int n_threads, int comm_kind, uint32_t* out_syms,
+                    uint32_t* out_lens, uint64_t cap_runs, grlbwt_result_t* out) {
+    if (!text || !out || n_syms == 0 || !devices || n_ranks < 1 || n_ranks > 31 || !out_syms || !out_lens) return GRLGPU_ERR_ARG;
+    if (!(sym_bytes == 1 || sym_bytes == 2 || sym_bytes == 4 || sym_bytes == 8)) return GRLGPU_ERR_ARG;
+    memset(out, 0, sizeof(*out));
+    try {
+        grlbwt::TextSource src;
+        src.mem = (const unsigned char*)text;
+        src.bytes = n_syms * (uint64_t)sym_bytes;
+        grlbwt::OutputBuffers ob;
+        ob.sym = out_syms; ob.len = out_lens; ob.cap = cap_runs;
+        grlbwt::BwtResult r = grlbwt::build_bwt(src, sym_bytes, std::vector<int>(devices, devices + n_ranks), comm_kind, (size_t)(n_threads > 0 ? n_threads : 1), false, &ob);
+        const size_t nr = r.n_runs();
+        out->n_runs = nr; out->sb = r.sb; out->fb = r.fb;
+        out->n_rounds = r.parse.rounds.size();
+        out->h2d_ms = r.parse.h2d_ms; out->par_phase_ms = r.parse.par_ms; out->ind_phase_ms = r.ind_ms;
+        out->induced_on_device = r.parse.induced_on_device ? 1 : 0;
+        for (const auto& rd : r.parse.rounds) { out->device_ms += rd.device_ms; out->algorithmic_bytes += rd.algorithmic_bytes; }
+        g_last_digests = r.parse.digests;
+        g_last_exchange_bytes = r.parse.exchange_bytes;
+        g_last_comm = r.parse.comm_kind;
+        if (!r.parse.bwt_in_caller_buffers) {  // host induction (or too many runs for the buffers): copy what fits the 32-bit arrays
+            if (nr > cap_runs) { g_last_error = "the output buffers are too small: " + std::to_string(nr) + " runs"; return GRLGPU_ERR_LIMIT; }
+            for (size_t k = 0; k < nr; k++) {
+                const uint64_t sy = r.narrow ? (uint64_t)r.runs32.sym[k] : r.runs.sym[k], ln = r.narrow ? r.runs32.length(k) : r.runs.len[k];
+                if (sy >> 32 || ln >> 32) { g_last_error = "the BWT does not fit 32-bit symbols and lengths"; return GRLGPU_ERR_LIMIT; }
+                out_syms[k] = (uint32_t)sy;
+                out_lens[k] = (uint32_t)ln;
+            }
+        }
+        return GRLGPU_OK;
+    } catch (const grlbwt::GpuError& e) {
+        g_last_error = e.what();
+        return e.status;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return -100;
+    }
+}
+
 uint64_t grlbwt_last_digests(uint64_t* out, uint64_t cap_rounds) {
     const uint64_t n = g_last_digests.size();
     for (uint64_t i = 0; i < n && i < cap_rounds && out; i++) {

@@ -35,6 +35,12 @@ void grlbwt_free_result(grlbwt_result_t* r);
  * 1 = in-process; 2 = NCCL. The bytes of the result do not depend on the number of ranks. */
 int grlbwt_build_mg(const void* text, uint64_t n_syms, int sym_bytes, const int* devices, int n_ranks, int n_threads, int comm_kind, int verbose,
                     grlbwt_result_t* out);
+/* the same construction with the level-0 BWT written into CALLER-OWNED arrays of cap_runs 32-bit symbols / 32-bit lengths
+ * (out->syms / out->lens stay NULL). With pinned buffers and the induction on the device the runs arrive by DMA, without a
+ * first touch of fresh host pages; a production caller reuses the buffers across collections. GRLGPU_ERR_LIMIT when the BWT
+ * has more than cap_runs runs or does not fit 32 bits. */
+int grlbwt_build_to(const void* text, uint64_t n_syms, int sym_bytes, const int* devices, int n_ranks, int n_threads, int comm_kind, uint32_t* out_syms,
+                    uint32_t* out_lens, uint64_t cap_runs, grlbwt_result_t* out);
 /* per-round digests of the calling thread's last build (9 values per round: tot_phrases, pre-BWT runs, parse length, distinct
  * phrases, dictionary symbols, and the four sums of grlgpu_level_checksum added over the ranks); returns the number of rounds */
 uint64_t grlbwt_last_digests(uint64_t* out, uint64_t cap_rounds);

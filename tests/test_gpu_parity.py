@@ -197,6 +197,24 @@ def test_host_and_device_induction_agree(golden, all_cases):
     assert not info["induced_on_device"]
 
 
+def test_build_into_caller_buffers(golden, all_cases):
+    """grlbwt_build_to: the run-length BWT lands in caller-owned 32-bit arrays (device induction: by DMA; host induction: copied)"""
+    for name in ("test_byte_alphabet", "reads_100k", "u16_2M"):
+        arr, g = all_cases[name], golden[name]
+        out_s, out_l = np.zeros(arr.size, np.uint32), np.zeros(arr.size, np.uint32)
+        for host in (False, True):
+            if host:
+                os.environ["GRLBWT_HOST_INDUCTION"] = "1"
+            try:
+                n_runs, sb, fb, info = G.build_bwt_to(arr, out_s, out_l, n_threads=4)
+            finally:
+                os.environ.pop("GRLBWT_HOST_INDUCTION", None)
+            raw = O.rl_bwt_bytes(out_s[:n_runs].astype(np.uint64), out_l[:n_runs].astype(np.uint64), sb, fb)
+            assert hashlib.sha256(raw).hexdigest() == g["rl_bwt_sha256"], (name, host)
+    with pytest.raises(G.GrlGpuError):
+        G.build_bwt_to(all_cases["reads_100k"], np.zeros(10, np.uint32), np.zeros(10, np.uint32))
+
+
 def test_async_level_fetch_matches_sync(golden, all_cases):
     """levels fetched on the copy stream while later rounds run equal the synchronously fetched ones"""
     for name in ("mutated_200x5k", "u16_rand", "reads_2000x150"):
