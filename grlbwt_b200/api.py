@@ -90,6 +90,7 @@ def lib_gpu():
         L.grlgpu_comm_create_local.argtypes = [C.POINTER(vp), vp, C.c_int, C.c_int]
         L.grlgpu_comm_destroy.argtypes = [vp]
         L.grlgpu_comm_info.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.c_char_p, C.c_int]
+        L.grlgpu_comm_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.grlgpu_set_peers.argtypes = [vp, vp, C.c_int]
         L.grlgpu_mg_stats.argtypes = [vp, vp, C.POINTER(Stats)]
         L.grlgpu_mg_round.argtypes = [vp, vp, C.POINTER(Round)]

@@ -11,6 +11,7 @@
 #include <dlfcn.h>
 #include <nccl.h>  // types and prototypes only; every call goes through the table resolved below
 
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <vector>
@@ -22,6 +23,7 @@ namespace grl {
 struct Comm {
     int rank = 0, world = 1, device = 0;
     u64 bytes_sent = 0, n_bulk = 0, n_small = 0;  // accounting for bench.py: bulk bytes this rank sent, collectives issued
+    double ms_bulk = 0, ms_small = 0;             // host wall time spent inside them (each call ends with the data in place)
     virtual ~Comm() {}
     virtual const char* kind() const = 0;
     // small host-side all-gather: all[p * bytes .. (p+1) * bytes) = rank p's `mine`. Blocking.
@@ -64,15 +66,18 @@ struct LocalComm : Comm {
     const char* kind() const override { return "in-process ranks, cudaMemcpyPeerAsync pulls"; }
     void all_gather_host(const void* mine, size_t bytes, void* all, cudaStream_t) override {
         n_small++;
+        const auto t0 = std::chrono::steady_clock::now();
         g->ptr[(size_t)rank] = mine;
         g->wait();
         for (int p = 0; p < world; p++) memcpy((char*)all + (size_t)p * bytes, g->ptr[(size_t)p], bytes);
         g->wait();
+        ms_small += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
     void all_to_all_v(const void* d_send, const u64* send_off, void* d_recv, const u64* recv_off, cudaStream_t st) override {
         n_bulk++;
         bytes_sent += send_off[world] - (send_off[rank + 1] - send_off[rank]);
         GRL_CUDA(cudaStreamSynchronize(st));  // my send buffer is complete
+        const auto t0 = std::chrono::steady_clock::now();
         g->ptr[(size_t)rank] = d_send;
         g->off[(size_t)rank] = send_off;
         g->dev[(size_t)rank] = device;
@@ -90,6 +95,7 @@ struct LocalComm : Comm {
         }
         GRL_CUDA(cudaStreamSynchronize(st));
         g->wait();  // every peer has pulled what it needed out of my send buffer
+        ms_bulk += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
 };
 
@@ -164,6 +170,7 @@ struct NcclComm : Comm {
     const char* kind() const override { return "NCCL grouped send/recv (all-to-all-v) + all-gather"; }
     void all_gather_host(const void* mine, size_t bytes, void* all, cudaStream_t st) override {
         n_small++;
+        const auto t0 = std::chrono::steady_clock::now();
         NcclApi& api = NcclApi::get();
         const size_t padded = (bytes + 15) / 16 * 16, need = padded * (size_t)(world + 1);
         if (need > stage_cap) {
@@ -176,13 +183,15 @@ struct NcclComm : Comm {
         GRL_CUDA(cudaMemcpyAsync(d_in, mine, bytes, cudaMemcpyHostToDevice, st));
         GRL_NCCL(api.AllGather(d_in, d_out, padded, ncclUint8, comm, st));
         std::vector<char> tmp(padded * (size_t)world);
-        GRL_CUDA(cudaMemcpyAsync(tmp.data(), d_out, tmp.size(), cudaMemcpyDeviceToHost, st));
-        GRL_CUDA(cudaStreamSynchronize(st));
+        d2h_mapped(tmp.data(), d_out, tmp.size(), st);  // through mapped pinned memory: a DMA readback would queue behind the level copies
         for (int p = 0; p < world; p++) memcpy((char*)all + (size_t)p * bytes, tmp.data() + (size_t)p * padded, bytes);
+        ms_small += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
     void all_to_all_v(const void* d_send, const u64* send_off, void* d_recv, const u64* recv_off, cudaStream_t st) override {
         n_bulk++;
         bytes_sent += send_off[world] - (send_off[rank + 1] - send_off[rank]);
+        GRL_CUDA(cudaStreamSynchronize(st));  // (for the accounting below: the clock starts when this rank's data is ready)
+        const auto t0 = std::chrono::steady_clock::now();
         NcclApi& api = NcclApi::get();
         const u64 self = send_off[rank + 1] - send_off[rank];
         if (self != recv_off[rank + 1] - recv_off[rank]) throw Error(-5, "all-to-all-v: send and receive sizes disagree");
@@ -195,6 +204,8 @@ struct NcclComm : Comm {
             if (rl) GRL_NCCL(api.Recv((char*)d_recv + recv_off[from], rl, ncclUint8, from, comm, st));
         }
         GRL_NCCL(api.GroupEnd());
+        GRL_CUDA(cudaStreamSynchronize(st));
+        ms_bulk += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
 };
 

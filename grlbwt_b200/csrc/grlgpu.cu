@@ -1307,6 +1307,12 @@ int grlgpu_comm_destroy(grlgpu_comm* comm) {
     delete comm;
     return GRLGPU_OK;
 }
+int grlgpu_comm_times(const grlgpu_comm* comm, double* ms_bulk, double* ms_small) {
+    if (!comm) return GRLGPU_ERR_ARG;
+    if (ms_bulk) *ms_bulk = comm->c->ms_bulk;
+    if (ms_small) *ms_small = comm->c->ms_small;
+    return GRLGPU_OK;
+}
 int grlgpu_comm_info(const grlgpu_comm* comm, uint64_t* bytes_sent, uint64_t* n_bulk, uint64_t* n_small, char* kind, int kind_cap) {
     if (!comm) return GRLGPU_ERR_ARG;
     if (bytes_sent) *bytes_sent = comm->c->bytes_sent;

@@ -316,8 +316,7 @@ inline std::vector<u64> mg2_partition(DevBuf<u32>& dest, DevBuf<u32>& idx, u64 n
     DevBuf<u64> first((u64)G + 1, st);
     GRL_LAUNCH("mg_bounds", 0, (mg2_bounds_kernel<u32>), 1, 32, 0, st, k1, n, (u32)G, first.p);
     std::vector<u64> hf((size_t)G + 1);
-    GRL_CUDA(cudaMemcpyAsync(hf.data(), first.p, ((size_t)G + 1) * 8, cudaMemcpyDeviceToHost, st));
-    GRL_CUDA(cudaStreamSynchronize(st));
+    d2h_mapped(hf.data(), first.p, ((size_t)G + 1) * 8, st);  // (not a copy-engine job: it would queue behind the asynchronous level copies)
     for (int g = 0; g < G; g++) cnt[(size_t)g] = hf[(size_t)g + 1] - hf[(size_t)g];
     if (v1 == idx.p) perm = std::move(idx); else perm = std::move(v2);
     return cnt;
@@ -373,8 +372,7 @@ void mg2_rank(grlgpu_ctx* c, Comm& cm, Mg2Part& P, Mg2Slices& S) {
             DevBuf<u64> sk(ns, st);
             DevBuf<u32> sv(ns, st);
             GRL_LAUNCH("key_sample", 0, key_sample_kernel, grid_for(ns, 256), 256, 0, st, PR.keys.p, nS, stride, ns, sk.p, sv.p);
-            GRL_CUDA(cudaMemcpyAsync(mine.data() + 1, sk.p, ns * 8, cudaMemcpyDeviceToHost, st));
-            GRL_CUDA(cudaStreamSynchronize(st));
+            d2h_mapped(mine.data() + 1, sk.p, ns * 8, st);
         }
         const std::vector<u64> all = mg2_gather(cm, mine, st);
         std::vector<u64> samp;
@@ -545,10 +543,9 @@ void mg2_rank(grlgpu_ctx* c, Comm& cm, Mg2Part& P, Mg2Slices& S) {
         mine[1] = n_pre_raw;
         if (n_pre_raw) {
             SymT fs, ls;
-            GRL_CUDA(cudaMemcpyAsync(&fs, (const SymT*)S.pre_sym.p, sizeof(SymT), cudaMemcpyDeviceToHost, st));
-            GRL_CUDA(cudaMemcpyAsync(&ls, (const SymT*)S.pre_sym.p + (n_pre_raw - 1), sizeof(SymT), cudaMemcpyDeviceToHost, st));
-            GRL_CUDA(cudaMemcpyAsync(&mine[3], S.pre_len.p, 8, cudaMemcpyDeviceToHost, st));
-            GRL_CUDA(cudaStreamSynchronize(st));
+            d2h_small(&fs, (const SymT*)S.pre_sym.p, sizeof(SymT), st);
+            d2h_small(&ls, (const SymT*)S.pre_sym.p + (n_pre_raw - 1), sizeof(SymT), st);
+            d2h_small(&mine[3], S.pre_len.p, 8, st);
             mine[2] = (u64)fs;
             mine[4] = (u64)ls;
         }
@@ -683,8 +680,7 @@ void mg2_round_t(grlgpu_ctx* c, Comm& cm, grlgpu_round_t* out) {
         DevBuf<u64> first((u64)G + 1, st);
         GRL_LAUNCH("mg_bounds", 0, (mg2_bounds_kernel<u64>), 1, 32, 0, st, kp, R.d, (u32)G, first.p);
         std::vector<u64> hf((size_t)G + 1), ho((size_t)G + 1);
-        GRL_CUDA(cudaMemcpyAsync(hf.data(), first.p, ((size_t)G + 1) * 8, cudaMemcpyDeviceToHost, st));
-        GRL_CUDA(cudaStreamSynchronize(st));
+        d2h_mapped(hf.data(), first.p, ((size_t)G + 1) * 8, st);
         for (int g = 0; g <= G; g++) ho[(size_t)g] = d2h_scalar(offs.p + hf[(size_t)g], st);
         for (int g = 0; g < G; g++) { s_phr[(size_t)g] = hf[(size_t)g + 1] - hf[(size_t)g]; s_cel[(size_t)g] = ho[(size_t)g + 1] - ho[(size_t)g]; }
         s_cells.alloc(ho[(size_t)G] * sizeof(CellT) + 16, st);

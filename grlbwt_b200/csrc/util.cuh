@@ -284,6 +284,27 @@ inline void d2h_small(void* host_dst, const void* dev_src, size_t bytes, cudaStr
 }
 
 
+// the same for readbacks of up to a few hundred KB (per-peer counts, key samples, gathered scalars of the multi-GPU rounds)
+static __global__ void copy_words_kernel(const u32* __restrict__ src, u32* __restrict__ dst, u64 n_words) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (u64)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+inline void d2h_mapped(void* host_dst, const void* dev_src, size_t bytes, cudaStream_t st) {
+    static thread_local u8* buf = nullptr;
+    static thread_local size_t cap = 0;
+    if (bytes == 0) return;
+    if (bytes % 4 || ((uintptr_t)dev_src & 3)) throw Error(GRLGPU_ERR_ARG, "d2h_mapped: unsupported size or alignment");
+    if (bytes > cap) {
+        if (buf) GRL_CUDA(cudaFreeHost(buf));
+        cap = std::max<size_t>(bytes, (size_t)1 << 20);
+        GRL_CUDA(cudaHostAlloc((void**)&buf, cap, cudaHostAllocMapped | cudaHostAllocPortable));
+    }
+    const u64 words = bytes / 4;
+    copy_words_kernel<<<(unsigned)std::min<u64>(64, (words + 255) / 256), 256, 0, st>>>((const u32*)dev_src, (u32*)buf, words);
+    GRL_CUDA(cudaGetLastError());
+    GRL_CUDA(cudaStreamSynchronize(st));
+    memcpy(host_dst, buf, bytes);
+}
+
 struct ProfScope {
     Profiler* p; cudaStream_t st; cudaEvent_t a{}, b{}; const char* name; u64 bytes;
     ProfScope(const char* nm, u64 by, cudaStream_t s) : p(g_prof), st(s), name(nm), bytes(by) {

@@ -550,8 +550,10 @@ inline ParseResult gpu_par_phase_mg(const TextSource& src, int sym_bytes, const 
         try {
             CtxHandle ctx(devices[(size_t)me], 0);
             ctx.check("grlgpu_set_peers", grlgpu_set_peers(ctx.p, devices.data(), G));
+            const auto t_c = std::chrono::steady_clock::now();
             int rc = use_nccl ? grlgpu_comm_create_nccl(&comm, nccl_id, me, G, devices[(size_t)me]) : grlgpu_comm_create_local(&comm, group, me, devices[(size_t)me]);
             if (rc != GRLGPU_OK) throw GpuError(rc, std::string("creating the exchange layer: ") + grlgpu_strerror(rc));
+            if (verbose && me == 0) { printf("  exchange layer ready in %.1f ms\n", ms_since(t_c)); fflush(stdout); }
             TextSource shard = src;
             shard.offset = src.offset + bounds[(size_t)me] * w;
             shard.bytes = (bounds[(size_t)me + 1] - bounds[(size_t)me]) * w;
@@ -597,7 +599,7 @@ inline ParseResult gpu_par_phase_mg(const TextSource& src, int sym_bytes, const 
                     res.wide = res.wide || r.sym_bytes == 8;
                     sinks.emplace_back(new LevelSink());
                     sinks.back()->prepare(r, res.wide);
-                    if (verbose) print_round(r);
+                    if (verbose) { print_round(r); printf("      Wall clock since start (ms):       %.1f\n", ms_since(t_start)); fflush(stdout); }
                     res.rounds.push_back(r);
                 }
                 if (dev_ind && me == 0) {

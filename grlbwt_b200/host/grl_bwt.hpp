@@ -138,7 +138,12 @@ void grl_bwt_algo(std::string& i_file, std::string& o_file, tmp_workspace& tmp_w
         throw;
     }
     std::string tmp_out = tmp_ws.get_file("bwt_lev_0");
+    const auto t_w = std::chrono::steady_clock::now();
     res.write(tmp_out);
+    printf("Timing (ms): text to device %.1f, parse phase %.1f (%d rank%s, %s), induction %.1f (%s), writing %zu runs %.1f\n", res.parse.h2d_ms, res.parse.par_ms,
+           res.parse.n_ranks, res.parse.n_ranks > 1 ? "s" : "", res.parse.comm_kind.c_str(), res.ind_ms, res.parse.induced_on_device ? "device" : "host", res.n_runs(),
+           grlbwt::ms_since(t_w));
+    fflush(stdout);
     std::error_code ec;
     std::filesystem::rename(tmp_out, o_file, ec);
     if (ec) {  // the reference fails across filesystems (grl_bwt.hpp:77); copy instead

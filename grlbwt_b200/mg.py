@@ -30,7 +30,10 @@ class Comm:
         b, nb, ns = C.c_uint64(), C.c_uint64(), C.c_uint64()
         kind = C.create_string_buffer(128)
         L.grlgpu_comm_info(self.handle, C.byref(b), C.byref(nb), C.byref(ns), kind, 128)
-        return {"bytes_sent": int(b.value), "bulk_collectives": int(nb.value), "small_collectives": int(ns.value), "kind": kind.value.decode()}
+        mb, ms = C.c_double(), C.c_double()
+        L.grlgpu_comm_times(self.handle, C.byref(mb), C.byref(ms))
+        return {"bytes_sent": int(b.value), "bulk_collectives": int(nb.value), "small_collectives": int(ns.value), "kind": kind.value.decode(),
+                "ms_in_bulk": round(mb.value, 1), "ms_in_small": round(ms.value, 1)}
 
     def close(self):
         if self.handle:

@@ -205,6 +205,9 @@ int grlgpu_comm_create_local(grlgpu_comm** comm, grlgpu_local_group* group, int 
 int grlgpu_comm_destroy(grlgpu_comm* comm);
 /* bytes this rank sent in bulk exchanges so far, bulk / small collectives issued, backend description */
 int grlgpu_comm_info(const grlgpu_comm* comm, uint64_t* bytes_sent, uint64_t* n_bulk, uint64_t* n_small, char* kind, int kind_cap);
+/* host wall time (ms) this rank has spent inside bulk exchanges (from "my data is ready" to "everything has arrived", so it
+ * includes waiting for slower peers) and inside the small gathers */
+int grlgpu_comm_times(const grlgpu_comm* comm, double* ms_bulk, double* ms_small);
 /* in-process ranks on different GPUs: let the listed devices read this context's memory pool directly (NVLink P2P) */
 int grlgpu_set_peers(grlgpu_ctx* ctx, const int* devices, int n_devices);
 
