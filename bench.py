@@ -37,7 +37,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=50_000_000, help="reads of the collection (C2: 50M x 150 bp = 7.55 GB)")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3"], help="c2: random reads (the metric's config); c3: repetitive genomes (BASELINE.json configs[2])")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"],
+                    help="c2: random reads (the metric's config); c3: repetitive genomes (BASELINE.json configs[2]); c5: 200M short + 10%% long reads, 33 GB (configs[4], needs 8 GPUs)")
+    ap.add_argument("--c5-blocks", type=int, default=302_114, help="c5: blocks of 662 reads x 150 bp + one 10 kbp read (302114 blocks = 200M short reads, 33.2 GB)")
     ap.add_argument("--copies", type=int, default=1000, help="c3: genome copies")
     ap.add_argument("--genome", type=int, default=4_000_000, help="c3: genome length")
     ap.add_argument("--sample-reads", type=int, default=1_000_000, help="reads of the bounded CPU-baseline / same-sample leg (151 MB)")
@@ -210,6 +212,31 @@ def make_genomes_on_device(torch, first_copy, n_copies, genome_len, seed, device
     return torch.cat(parts)
 
 
+C5_SHORT, C5_LONG, C5_CHUNK = 662, 10_000, 512   # a block = 662 short reads + one long read (10 % of the bases); generated 512 blocks at a time
+C5_BLOCK_BYTES = C5_SHORT * (READ_LEN + 1) + C5_LONG + 1
+
+
+def make_mixed_on_device(torch, first_chunk, n_chunks, total_blocks, seed, device):
+    """Chunks [first_chunk, first_chunk + n_chunks) of the C5 collection (shape of tests/gen.mixed_reads: short reads with a long
+    read interleaved deterministically after every 662 of them); chunk c covers blocks [512 c, 512 (c+1)) and comes from the
+    generator state seed * 1000003 + c, so every rank count sees the same global text"""
+    g = torch.Generator(device=device)
+    lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=device)
+    parts = []
+    for c in range(first_chunk, first_chunk + n_chunks):
+        nb = min(C5_CHUNK, total_blocks - c * C5_CHUNK)
+        g.manual_seed(seed * 1_000_003 + c)
+        blk = torch.empty((nb, C5_BLOCK_BYTES), dtype=torch.uint8, device=device)
+        short = blk[:, : C5_SHORT * (READ_LEN + 1)].view(nb, C5_SHORT, READ_LEN + 1)
+        short[:, :, :READ_LEN] = lut[torch.randint(0, 4, (C5_CHUNK, C5_SHORT, READ_LEN), generator=g, device=device, dtype=torch.int64)[:nb]]
+        short[:, :, READ_LEN] = 10
+        lng = blk[:, C5_SHORT * (READ_LEN + 1):]
+        lng[:, :C5_LONG] = lut[torch.randint(0, 4, (C5_CHUNK, C5_LONG), generator=g, device=device, dtype=torch.int64)[:nb]]
+        lng[:, C5_LONG] = 10
+        parts.append(blk.reshape(-1))
+    return torch.cat(parts)
+
+
 def split_range(total, world, rank):
     """contiguous ranges of whole strings, as even as possible (the reference's mt split, parsing_strategies.h:208-214)"""
     per, extra = divmod(total, world)
@@ -248,6 +275,15 @@ def run_ours(args, rank, world, local_rank):
         n_total = args.reads * (READ_LEN + 1)
         wl_desc = c2_workload_desc(args.reads)
         wl_key = f"c2_{args.reads}"
+    elif args.workload == "c5":
+        n_chunks_total = (args.c5_blocks + C5_CHUNK - 1) // C5_CHUNK
+        first_chunk, my_chunks = split_range(n_chunks_total, world, rank)
+        text = make_mixed_on_device(torch, first_chunk, my_chunks, args.c5_blocks, 5, dev)
+        n = text.numel()
+        n_total = args.c5_blocks * C5_BLOCK_BYTES
+        wl_desc = (f"C5: {args.c5_blocks * C5_SHORT} reads x {READ_LEN} bp + {args.c5_blocks} reads x {C5_LONG} bp (10 % of the bases), interleaved "
+                   f"({n_total / 1e9:.3f} GB), BASELINE.json configs[4]")
+        wl_key = f"c5_{args.c5_blocks}"
     else:
         first_copy, my_copies = split_range(args.copies, world, rank)
         text = make_genomes_on_device(torch, first_copy, my_copies, args.genome, 1000, dev)
@@ -264,6 +300,7 @@ def run_ours(args, rank, world, local_rank):
     ctx = G.GrlGpu(local_rank, 0, stream=stream.cuda_stream)
     comm = mg.nccl_comm_from_torch(dist, rank, world, local_rank, torch) if world > 1 else None
     arena = [None]
+    final_cells = [0]   # cells of this rank's final parse (one per local string)
     e2e_parts = {}
 
     def barrier():
@@ -309,6 +346,7 @@ def run_ours(args, rank, world, local_rank):
                 a_off = ctx.arena_end
                 d2h += tot_l * (2 * r.sym_bytes + 1) + pre_l * (r.sym_bytes + (4 if narrow else 8))
             if r.done:
+                final_cells[0] = plen_l
                 if fetch:
                     t_tail = time.perf_counter()
                     ctx.fetch_wait()
@@ -377,7 +415,7 @@ def run_ours(args, rank, world, local_rank):
             need = sum(r["tot_phrases"] * 9 + r["n_pre_runs"] * 12 + 256 for r in rounds_info)
         else:
             need = sum(int(t_ * 9 * 1.05) + int(p_ * 12 * 1.05) + 4096 for t_, p_ in slice_sizes)
-        need += (n // (READ_LEN + 1) + 1024) * 8 + (1 << 20)
+        need += (final_cells[0] + 1024) * 8 + (1 << 20)
         arena[0] = torch.empty(int(need), dtype=torch.uint8, pin_memory=True).numpy()
         d2h_bytes = [0]
 
@@ -493,8 +531,12 @@ def run_ours(args, rank, world, local_rank):
             expected = json.load(open(dpath)).get("sha256")
         elif world == 1 and args.write_digest:
             json.dump({"workload": wl_desc, "n_gpus": 1, "sha256": h, "per_round": digest[:-1], "final_parse_sha256": digest[-1]}, open(dpath, "w"), indent=1)
-        dg = {"sha256": h, "rounds": len(digest) - 1, "final_parse_sha256": digest[-1], "per_round_tot_phrases": [d[0] for d in digest[:-1]],
+        n_ins = [n_total] + [d_[2] for d_ in digest[:-2]]
+        covers = all(d_[7] == n_in_ for d_, n_in_ in zip(digest[:-1], n_ins))
+        dg = {"sha256": h, "rounds": len(digest) - 1, "pre_bwt_covers_every_level": covers, "final_parse_sha256": digest[-1], "per_round_tot_phrases": [d[0] for d in digest[:-1]],
               "expected_from_1_gpu": expected, "matches_1_gpu": (h == expected) if expected else None,
+              "invariant": "pre_bwt_covers_every_level: the run lengths of level r's preliminary BWT sum to the number of cells of round r's text (checked on the "
+                           "checksums, at full size, for every rank count)",
               "what": "sha256 over [tot_phrases, pre-BWT runs, parse length, distinct phrases, dictionary symbols, 4 checksums of rules/hocc/pre-BWT] of every "
                       "round + sha256 of the final parse in string order; the N-rank job parses slices of the same global text, so the value is the same for "
                       "1, 2, 4 and 8 GPUs (profiles/digest_*.json holds the 1-GPU value)"}

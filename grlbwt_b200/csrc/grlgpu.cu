@@ -643,7 +643,9 @@ void stage_dict(Round& R) {
     c->rule_r.alloc(tot * sizeof(SymT), st);
     c->has_hocc.alloc(tot, st);
     const u64 alph3 = A + 3, metasym_dummy = alph3 + tot + 1;  // exact_par_phase.cpp:19-20
-    GRL_LAUNCH("rules", 0, (rules_kernel<SymT>), grid_for(G, 256), 256, 0, st, gcnt.p, rflag.p, rrank.p, grep.p, G, D, R.rem.p, erank.p, isuf, alph3, metasym_dummy, (SymT*)c->rule_l.p, (SymT*)c->rule_r.p, c->has_hocc.p);
+    // model: 16 B of sequential group records + three random 32-byte sectors per ranked group (rem, hocc mark, symbols of the representative)
+    // + the rule written (2 symbols + 1 byte)
+    GRL_LAUNCH("rules", G * 16 + tot * (96 + 2 * sizeof(SymT) + 1), (rules_kernel<SymT>), grid_for(G, 256), 256, 0, st, gcnt.p, rflag.p, rrank.p, grep.p, G, D, R.rem.p, erank.p, isuf, alph3, metasym_dummy, (SymT*)c->rule_l.p, (SymT*)c->rule_r.p, c->has_hocc.p);
     c->lvl_tot = tot;
     c->lvl_npre = R.n_pre;
     // every valid dictionary entry contributes its phrase's frequency to exactly one run: the lengths of a level sum to at most
@@ -1476,10 +1478,16 @@ int grlgpu_level_adopt(grlgpu_ctx* ctx, uint64_t alphabet, uint64_t tot, uint64_
 }
 int grlgpu_copy_dev(int dst_device, void* dst, int src_device, const void* src, uint64_t bytes) {
     if (bytes == 0) return GRLGPU_OK;
-    if (!dst || !src) return GRLGPU_ERR_ARG;
+    if (!dst || !src || dst_device < 0 || dst_device >= 64) return GRLGPU_ERR_ARG;
+    // cudaMemcpyPeer / device-to-device cudaMemcpy return before the copy has finished: use a stream private to the calling
+    // thread and wait for it, so that the caller may release the source as soon as this returns
+    static thread_local cudaStream_t s[64] = {nullptr};
     if (cudaSetDevice(dst_device) != cudaSuccess) return GRLGPU_ERR_CUDA;
-    const cudaError_t e = dst_device == src_device ? cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice) : cudaMemcpyPeer(dst, dst_device, src, src_device, bytes);
-    return e == cudaSuccess ? GRLGPU_OK : GRLGPU_ERR_CUDA;
+    if (!s[dst_device] && cudaStreamCreateWithFlags(&s[dst_device], cudaStreamNonBlocking) != cudaSuccess) return GRLGPU_ERR_CUDA;
+    const cudaError_t e = dst_device == src_device ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s[dst_device])
+                                                   : cudaMemcpyPeerAsync(dst, dst_device, src, src_device, bytes, s[dst_device]);
+    if (e != cudaSuccess) return GRLGPU_ERR_CUDA;
+    return cudaStreamSynchronize(s[dst_device]) == cudaSuccess ? GRLGPU_OK : GRLGPU_ERR_CUDA;
 }
 int grlgpu_device_of(const grlgpu_ctx* ctx) { return ctx ? ctx->device : -1; }
 int grlgpu_kept_levels(const grlgpu_ctx* ctx) { return ctx ? (int)ctx->kept.size() : 0; }

@@ -247,16 +247,19 @@ __global__ void __launch_bounds__(256) mg2_rules_kernel(const u64* __restrict__ 
         o_r[k] = p_fin[phr_of[pos]] ? r_sym : l_sym;
     }
 }
-// owner of a rank = range it falls in (bases: G ascending rank offsets, bases[0] = 0)
-static __global__ void __launch_bounds__(256) mg2_rule_dest_kernel(const u64* __restrict__ u, u64 n, const u64* __restrict__ bases, int G, u32* __restrict__ dest,
-                                                                   u32* __restrict__ idx) {
-    const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const u64 r = u[k];
-    u32 g = 0;
-    for (int s = 1; s < G; s++) g += bases[s] <= r ? 1u : 0u;
-    dest[k] = g;
-    idx[k] = (u32)k;
+// the rules of this rank sorted by their (global) rank: first[g] = number of them below bases[g], g = 0..G (one thread per g):
+// the owner of a rank is the range it falls in, so the sorted list is already grouped by destination
+static __global__ void mg2_rule_bounds_kernel(const u64* __restrict__ sorted_u, u64 n, const u64* __restrict__ bases, int G, u64* __restrict__ first) {
+    const int g = threadIdx.x;
+    if (g > G) return;
+    if (g == G) { first[g] = n; return; }
+    const u64 b = bases[g];
+    u64 lo = 0, hi = n;
+    while (lo < hi) {
+        const u64 mid = (lo + hi) >> 1;
+        if (sorted_u[mid] < b) lo = mid + 1; else hi = mid;
+    }
+    first[g] = lo;
 }
 template <class SymT>
 __global__ void __launch_bounds__(256) mg2_rule_send_kernel(const u32* __restrict__ perm, u64 n, const u64* __restrict__ u, const SymT* __restrict__ l,
@@ -615,9 +618,27 @@ void mg2_rank(grlgpu_ctx* c, Comm& cm, Mg2Part& P, Mg2Slices& S) {
         rfl.release(); rex.release();
         DevBuf<u64> d_bases((u64)G + 1, st);
         GRL_CUDA(cudaMemcpyAsync(d_bases.p, bases.data(), ((size_t)G + 1) * 8, cudaMemcpyHostToDevice, st));
-        DevBuf<u32> dest(nR, st), idx(nR, st), perm;
-        if (nR) GRL_LAUNCH("mg_rule_dest", nR * 16, mg2_rule_dest_kernel, grid_for(nR, 256), 256, 0, st, ru.p, nR, d_bases.p, G, dest.p, idx.p);
-        rs_cnt = mg2_partition(dest, idx, nR, G, perm, st);
+        // the rules leave sorted by rank: every destination then receives G ascending streams and its scatter into the rank-ordered
+        // slice is nearly sequential (in entry order the ranks are random: one DRAM sector per rule and array)
+        DevBuf<u32> perm;
+        rs_cnt.assign((size_t)G, 0);
+        {
+            DevBuf<u64> sk(nR, st), sk_alt(nR, st), first((u64)G + 1, st);
+            DevBuf<u32> sv(nR, st), sv_alt(nR, st);
+            if (nR) {
+                GRL_CUDA(cudaMemcpyAsync(sk.p, ru.p, nR * 8, cudaMemcpyDeviceToDevice, st));
+                GRL_LAUNCH("mg_iota", nR * 4, mg2_iota_kernel, grid_for(nR, 256), 256, 0, st, sv.p, nR);
+            }
+            u64 *kp = sk.p, *ka = sk_alt.p;
+            u32 *vp = sv.p, *va = sv_alt.p;
+            radix_sort_pairs(&kp, &vp, &ka, &va, nR, std::max(1, bit_width64(S.tot)), st);
+            GRL_LAUNCH("mg_rule_bounds", 0, mg2_rule_bounds_kernel, 1, 32, 0, st, kp, nR, d_bases.p, G, first.p);
+            std::vector<u64> hf((size_t)G + 1);
+            d2h_mapped(hf.data(), first.p, ((size_t)G + 1) * 8, st);
+            for (int g = 0; g < G; g++) rs_cnt[(size_t)g] = hf[(size_t)g + 1] - hf[(size_t)g];
+            if (vp != sv.p) std::swap(sv, sv_alt);
+            perm = std::move(sv);
+        }
         DevBuf<u64> su(nR, st);
         DevBuf<u8> sl(nR * sizeof(SymT), st), sr(nR * sizeof(SymT), st), sh(nR, st);
         if (nR) GRL_LAUNCH("mg_rule_send", nR * 2 * (9 + 2 * sizeof(SymT)), (mg2_rule_send_kernel<SymT>), grid_for(nR, 256), 256, 0, st, perm.p, nR, ru.p, (const SymT*)rl.p,
