@@ -146,11 +146,15 @@ static __global__ void __launch_bounds__(256) mg2_ext_scatter_kernel(const u32* 
     if (vals) vals[j] = j;
     ev[j] = order[apos[j]];
 }
-// group aggregates over the sorted items of this range (produce_pre_bwt exact_par_phase.cpp:159-187); records in SoA form
+// the two record fields the group stage reads, side by side: ONE random 16-byte gather per entry instead of two
 template <class SymT>
-__global__ void __launch_bounds__(256) mg2_group_reduce_kernel(const u32* __restrict__ order, const u32* __restrict__ head_bits, const u32* __restrict__ head_pref,
-                                                               const SymT* __restrict__ r_left, const u64* __restrict__ r_y, u64 nL, u32* gcnt, u64* gacc, u64* gmin,
-                                                               u64* gmax) {
+__global__ void __launch_bounds__(256) mg2_zip_kernel(const SymT* __restrict__ r_left, const u64* __restrict__ r_y, u64 nL, ulonglong2* __restrict__ ei) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nL) ei[i] = make_ulonglong2((u64)r_left[i], r_y[i]);
+}
+// group aggregates over the sorted items of this range (produce_pre_bwt exact_par_phase.cpp:159-187)
+static __global__ void __launch_bounds__(256) mg2_group_reduce_kernel(const u32* __restrict__ order, const u32* __restrict__ head_bits, const u32* __restrict__ head_pref,
+                                                                     const ulonglong2* __restrict__ r_ei, u64 nL, u32* gcnt, u64* gacc, u64* gmin, u64* gmax) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     u32 g = 0xffffffffu, cnt = 0;
     u64 acc = 0, mn = ~0ULL, mx = 0;
@@ -161,11 +165,11 @@ __global__ void __launch_bounds__(256) mg2_group_reduce_kernel(const u32* __rest
         g = head_pref[i >> 5] + __popc(hw & (0xffffffffu >> (31 - (i & 31)))) - 1;
         hd = (hw >> (i & 31)) & 1u;
         nh = i + 1 == nL || ((head_bits[(i + 1) >> 5] >> ((i + 1) & 31)) & 1u);
-        const u64 y = ld_gather8(r_y + it);
-        const bool is_full = (y & EI_FULL) != 0;
+        const ulonglong2 ei = ld_gather16(r_ei + it);
+        const bool is_full = (ei.y & EI_FULL) != 0;
         cnt = 1u | (is_full ? 0x80000000u : 0u);
-        acc = y & EI_FREQ;
-        if (!is_full) { const u64 l = (u64)ld_gather(r_left + it); if (l) mn = mx = l; }
+        acc = ei.y & EI_FREQ;
+        if (!is_full && ei.x) mn = mx = ei.x;
     }
     const u32 m = __match_any_sync(0xffffffffu, g);
     const u32 first = __ffs(m) - 1, last = 31 - __clz(m);
@@ -511,8 +515,13 @@ void mg2_rank(grlgpu_ctx* c, Comm& cm, Mg2Part& P, Mg2Slices& S) {
     DevBuf<u32> gcnt(Gn, st), rflag(Gn, st), vflag(Gn, st), rrank(Gn, st), vidx(Gn, st);
     DevBuf<u64> gacc(Gn, st), gmin(Gn, st), gmax(Gn, st), psym(Gn, st);
     gcnt.zero(); gacc.zero(); gmax.zero(); gmin.fill_ff();
-    if (nL) GRL_LAUNCH("group_reduce", nL * 24 + Gn * 32, (mg2_group_reduce_kernel<SymT>), grid_for(nL, 256), 256, 0, st, order.p, head_bits.p, head_pref.p, r_left, r_y.p, nL, gcnt.p,
-                       gacc.p, gmin.p, gmax.p);
+    if (nL) {
+        DevBuf<ulonglong2> r_ei(nL, st);
+        GRL_LAUNCH("mg_zip", nL * (24 + sizeof(SymT)), (mg2_zip_kernel<SymT>), grid_for(nL, 256), 256, 0, st, r_left, r_y.p, nL, r_ei.p);
+        GRL_LAUNCH("group_reduce", nL * 24 + Gn * 32, mg2_group_reduce_kernel, grid_for(nL, 256), 256, 0, st, order.p, head_bits.p, head_pref.p, r_ei.p, nL, gcnt.p, gacc.p, gmin.p,
+                   gmax.p);
+        GRL_CUDA(cudaStreamSynchronize(st));
+    }
     r_y.release(); r_left_raw.release();
     const u64 bwt_dummy = A + 1, hocc_dummy = A + 2;  // exact_par_phase.hpp:113-115
     GRL_LAUNCH("group_finalize", 0, group_finalize_kernel, grid_for(Gn, 256), 256, 0, st, gcnt.p, gmin.p, gmax.p, Gn, bwt_dummy, hocc_dummy, rflag.p, vflag.p, psym.p);
