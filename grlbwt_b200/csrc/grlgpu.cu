@@ -1323,6 +1323,12 @@ int grlgpu_comm_info(const grlgpu_comm* comm, uint64_t* bytes_sent, uint64_t* n_
     if (kind && kind_cap > 0) snprintf(kind, (size_t)kind_cap, "%s", comm->c->kind());
     return GRLGPU_OK;
 }
+int grlgpu_can_peer(int device_a, int device_b) {
+    if (device_a == device_b) return 1;
+    int ab = 0, ba = 0;
+    if (cudaDeviceCanAccessPeer(&ab, device_a, device_b) != cudaSuccess || cudaDeviceCanAccessPeer(&ba, device_b, device_a) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return ab && ba;
+}
 int grlgpu_set_peers(grlgpu_ctx* ctx, const int* devices, int n_devices) {
     if (!ctx || (n_devices > 0 && !devices) || n_devices < 0) return GRLGPU_ERR_ARG;
     return guarded(ctx, [&] { ctx->pool.set_peers(std::vector<int>(devices, devices + n_devices)); });

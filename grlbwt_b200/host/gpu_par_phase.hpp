@@ -518,8 +518,13 @@ inline ParseResult gpu_par_phase_mg(const TextSource& src, int sym_bytes, const 
     for (int a = 0; a < G; a++)
         for (int b = a + 1; b < G; b++) distinct = distinct && devices[(size_t)a] != devices[(size_t)b];
     if (const char* e = getenv("GRLBWT_COMM")) comm_kind = !strcmp(e, "nccl") ? COMM_NCCL : !strcmp(e, "local") ? COMM_LOCAL : comm_kind;
+    // auto: in-process ranks whose GPUs can address each other exchange by peer copies (copy engines at NVLink rate, no communicator
+    // to set up: NCCL's costs ~1 s per process); NCCL when asked for, or when some pair of GPUs has no peer access
+    bool all_peers = true;
+    for (int a = 0; a < G; a++)
+        for (int b = a + 1; b < G; b++) all_peers = all_peers && grlgpu_can_peer(devices[(size_t)a], devices[(size_t)b]) != 0;
     unsigned char nccl_id[128];
-    bool use_nccl = comm_kind == COMM_NCCL || (comm_kind == COMM_AUTO && distinct);
+    bool use_nccl = comm_kind == COMM_NCCL || (comm_kind == COMM_AUTO && distinct && !all_peers);
     if (use_nccl && grlgpu_nccl_unique_id(nccl_id) != GRLGPU_OK) {
         if (comm_kind == COMM_NCCL) throw GpuError(GRLGPU_ERR_CUDA, "NCCL was requested but is not available");
         use_nccl = false;

@@ -37,8 +37,9 @@ static void usage(const char* prog) {
               << "  -b,--run-len-bytes     Max. number of bytes to encode the run lengths in the recursive BWTs (def. 1)\n"
               << "  -T,--tmp               Temporary folder (def. /tmp/grl.bwt.xxxx)\n"
               << "  -g,--gpu               CUDA device(s) that run the parse phase: one rank per entry of a comma list (def. 0)\n"
-              << "  --gpus                 Number of GPUs: ranks on devices 0..N-1 (shards of whole strings, NCCL exchange)\n"
-              << "  --comm                 Exchange between the ranks: auto (def.), nccl, local (in-process peer copies)\n"
+              << "  --gpus                 Number of GPUs: ranks on devices 0..N-1 (shards of whole strings, partitioned dictionary)\n"
+              << "  --comm                 Exchange between the ranks: nccl, local (in-process peer copies over NVLink), auto (def.: local when\n"
+              << "                         every pair of GPUs has peer access, else nccl)\n"
               << "  -v,--version           Print the software version and exit\n";
 }
 

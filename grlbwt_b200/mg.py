@@ -5,8 +5,8 @@ few helpers. The rounds, the exchanges and the per-rank host threads all live in
 Two ways to run N ranks:
   * one process per GPU (bench.py under torchrun): `nccl_comm_from_torch` -- rank 0 makes the NCCL id, torch.distributed
     broadcasts its 128 bytes, every rank builds its communicator inside libgrlgpu.so;
-  * one process, N host threads (the grlbwt CLI with --gpus N, `build_bwt_mg` here): NCCL when every rank has its own GPU,
-    else in-process peer copies (several ranks may share one GPU: the N > 1 path on a 1-GPU box).
+  * one process, N host threads (the grlbwt CLI with --gpus N, `build_bwt_mg` here): NCCL on request (COMM_NCCL), by default
+    in-process peer copies over NVLink (several ranks may also share one GPU: the N > 1 path on a 1-GPU box).
 """
 from __future__ import annotations
 

@@ -31,8 +31,8 @@ int grlbwt_build(const void* text, uint64_t n_syms, int sym_bytes, int device, i
 void grlbwt_free_result(grlbwt_result_t* r);
 /* the same over several GPUs: one rank (host thread) per entry of `devices`, shards of whole strings, partitioned global
  * dictionary (include/grlgpu.h, multi-GPU rounds). A device may be listed more than once (ranks then share it: this is how
- * the N > 1 path runs on a 1-GPU box). comm_kind: 0 = NCCL when every rank has its own GPU, else in-process peer copies;
- * 1 = in-process; 2 = NCCL. The bytes of the result do not depend on the number of ranks. */
+ * the N > 1 path runs on a 1-GPU box). comm_kind: 0 = in-process peer copies when every pair of GPUs has peer access (or ranks share a
+ * GPU), else NCCL; 1 = in-process peer copies; 2 = NCCL. The bytes of the result do not depend on the number of ranks. */
 int grlbwt_build_mg(const void* text, uint64_t n_syms, int sym_bytes, const int* devices, int n_ranks, int n_threads, int comm_kind, int verbose,
                     grlbwt_result_t* out);
 /* the same construction with the level-0 BWT written into CALLER-OWNED arrays of cap_runs 32-bit symbols / 32-bit lengths

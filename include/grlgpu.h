@@ -210,6 +210,7 @@ int grlgpu_comm_info(const grlgpu_comm* comm, uint64_t* bytes_sent, uint64_t* n_
 int grlgpu_comm_times(const grlgpu_comm* comm, double* ms_bulk, double* ms_small);
 /* in-process ranks on different GPUs: let the listed devices read this context's memory pool directly (NVLink P2P) */
 int grlgpu_set_peers(grlgpu_ctx* ctx, const int* devices, int n_devices);
+int grlgpu_can_peer(int device_a, int device_b);   /* 1 if the two devices can address each other's memory (NVLink / PCIe P2P) */
 
 /* byte alphabets: the 256-bin symbol histogram behind grlgpu_stats */
 int grlgpu_histogram(grlgpu_ctx* ctx, uint64_t* hist256);
