@@ -31,6 +31,16 @@ struct Comm {
     // device all-to-all-v in BYTES: send_off / recv_off are world + 1 prefix offsets (by destination / by source).
     // On return the received data is visible to work enqueued on `st` afterwards and d_send may be reused by it.
     virtual void all_to_all_v(const void* d_send, const u64* send_off, void* d_recv, const u64* recv_off, cudaStream_t st) = 0;
+    // several arrays that share the per-peer ELEMENT counts (a structure of arrays): one exchange instead of one per array
+    struct SoaPart { const void* send; void* recv; u64 elem_bytes; };
+    virtual void all_to_all_soa(const SoaPart* parts, int n_parts, const u64* send_cnt, const u64* recv_cnt, cudaStream_t st) {
+        std::vector<u64> so((size_t)world + 1), ro((size_t)world + 1);
+        for (int a = 0; a < n_parts; a++) {
+            so[0] = ro[0] = 0;
+            for (int p = 0; p < world; p++) { so[(size_t)p + 1] = so[(size_t)p] + send_cnt[p] * parts[a].elem_bytes; ro[(size_t)p + 1] = ro[(size_t)p] + recv_cnt[p] * parts[a].elem_bytes; }
+            all_to_all_v(parts[a].send, so.data(), parts[a].recv, ro.data(), st);
+        }
+    }
 };
 
 // ---------------------------------------------------------------- in-process ranks (host threads)
@@ -202,6 +212,35 @@ struct NcclComm : Comm {
             const u64 sl = send_off[to + 1] - send_off[to], rl = recv_off[from + 1] - recv_off[from];
             if (sl) GRL_NCCL(api.Send((const char*)d_send + send_off[to], sl, ncclUint8, to, comm, st));
             if (rl) GRL_NCCL(api.Recv((char*)d_recv + recv_off[from], rl, ncclUint8, from, comm, st));
+        }
+        GRL_NCCL(api.GroupEnd());
+        GRL_CUDA(cudaStreamSynchronize(st));
+        ms_bulk += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    // all arrays of the structure in ONE NCCL group: one rendezvous per peer instead of one per array
+    void all_to_all_soa(const SoaPart* parts, int n_parts, const u64* send_cnt, const u64* recv_cnt, cudaStream_t st) override {
+        n_bulk++;
+        GRL_CUDA(cudaStreamSynchronize(st));
+        const auto t0 = std::chrono::steady_clock::now();
+        NcclApi& api = NcclApi::get();
+        std::vector<u64> s_el((size_t)world + 1, 0), r_el((size_t)world + 1, 0);
+        for (int p = 0; p < world; p++) { s_el[(size_t)p + 1] = s_el[(size_t)p] + send_cnt[p]; r_el[(size_t)p + 1] = r_el[(size_t)p] + recv_cnt[p]; }
+        if (send_cnt[rank] != recv_cnt[rank]) throw Error(-5, "all-to-all-v: send and receive sizes disagree");
+        for (int a = 0; a < n_parts; a++) {
+            const u64 eb = parts[a].elem_bytes;
+            bytes_sent += (s_el[(size_t)world] - send_cnt[rank]) * eb;
+            if (send_cnt[rank])
+                GRL_CUDA(cudaMemcpyAsync((char*)parts[a].recv + r_el[(size_t)rank] * eb, (const char*)parts[a].send + s_el[(size_t)rank] * eb, send_cnt[rank] * eb,
+                                         cudaMemcpyDeviceToDevice, st));
+        }
+        GRL_NCCL(api.GroupStart());
+        for (int q = 1; q < world; q++) {
+            const int to = (rank + q) % world, from = (rank - q + world) % world;
+            for (int a = 0; a < n_parts; a++) {
+                const u64 eb = parts[a].elem_bytes;
+                if (send_cnt[to]) GRL_NCCL(api.Send((const char*)parts[a].send + s_el[(size_t)to] * eb, send_cnt[to] * eb, ncclUint8, to, comm, st));
+                if (recv_cnt[from]) GRL_NCCL(api.Recv((char*)parts[a].recv + r_el[(size_t)from] * eb, recv_cnt[from] * eb, ncclUint8, from, comm, st));
+            }
         }
         GRL_NCCL(api.GroupEnd());
         GRL_CUDA(cudaStreamSynchronize(st));

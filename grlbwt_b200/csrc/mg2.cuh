@@ -83,18 +83,20 @@ __global__ void mg2_bounds_kernel(const KeyT* __restrict__ keys, u64 m, u32 n_va
     first[g] = lo;
 }
 // the record of every valid entry, written in destination order (q-th record = valid entry perm[q])
-template <class SymT>
+// YT: the frequency word travels in 32 bits (frequency | full << 31) whenever the round's highest frequency is below 2^30
+template <class SymT, class YT>
 __global__ void __launch_bounds__(256) mg2_build_send_kernel(const u32* __restrict__ perm, u64 nS, const u64* __restrict__ keys, const u32* __restrict__ vals,
                                                              const SymT* __restrict__ D, const u32* __restrict__ rem, const u32* __restrict__ phr_of,
                                                              const u32* __restrict__ ph_off, const u64* __restrict__ ph_freq, u64* __restrict__ o_key,
-                                                             SymT* __restrict__ o_left, u64* __restrict__ o_y, u32* __restrict__ o_id, u32* __restrict__ o_rem) {
+                                                             SymT* __restrict__ o_left, YT* __restrict__ o_y, u32* __restrict__ o_id, u32* __restrict__ o_rem) {
     const u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nS) return;
     const u32 j = perm[q], e = vals[j], i = phr_of[e];
     const bool full = e == ph_off[i];
     o_key[q] = keys[j];
     o_left[q] = full ? (SymT)0 : (SymT)(D[e - 1] + 1);  // left symbol + 1; a whole phrase has none
-    o_y[q] = ph_freq[i] | EI_VALID | (full ? EI_FULL : 0ULL);
+    if constexpr (sizeof(YT) == 4) o_y[q] = (YT)((u32)ph_freq[i] | (full ? 0x80000000u : 0u));
+    else o_y[q] = (YT)(ph_freq[i] | EI_VALID | (full ? EI_FULL : 0ULL));
     o_id[q] = e;
     o_rem[q] = rem[e];
 }
@@ -147,10 +149,14 @@ static __global__ void __launch_bounds__(256) mg2_ext_scatter_kernel(const u32* 
     ev[j] = order[apos[j]];
 }
 // the two record fields the group stage reads, side by side: ONE random 16-byte gather per entry instead of two
-template <class SymT>
-__global__ void __launch_bounds__(256) mg2_zip_kernel(const SymT* __restrict__ r_left, const u64* __restrict__ r_y, u64 nL, ulonglong2* __restrict__ ei) {
+template <class SymT, class YT>
+__global__ void __launch_bounds__(256) mg2_zip_kernel(const SymT* __restrict__ r_left, const YT* __restrict__ r_y, u64 nL, ulonglong2* __restrict__ ei) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nL) ei[i] = make_ulonglong2((u64)r_left[i], r_y[i]);
+    if (i >= nL) return;
+    u64 y;
+    if constexpr (sizeof(YT) == 4) { const u32 v = (u32)r_y[i]; y = (u64)(v & 0x7fffffffu) | EI_VALID | ((v >> 31) ? EI_FULL : 0ULL); }
+    else y = (u64)r_y[i];
+    ei[i] = make_ulonglong2((u64)r_left[i], y);
 }
 // group aggregates over the sorted items of this range (produce_pre_bwt exact_par_phase.cpp:159-187)
 static __global__ void __launch_bounds__(256) mg2_group_reduce_kernel(const u32* __restrict__ order, const u32* __restrict__ head_bits, const u32* __restrict__ head_pref,
@@ -192,19 +198,21 @@ static __global__ void __launch_bounds__(256) mg2_group_reduce_kernel(const u32*
 }
 // code of every item, at the item's position in the receive buffer: 0 = its group is not ranked, else
 // ((global rank << 2) | hocc << 1 | representative) + 1   (phr_marks / new_phrases_ht, exact_par_phase.cpp:190-207)
-static __global__ void __launch_bounds__(256) mg2_codes_kernel(const u32* __restrict__ order, const u32* __restrict__ head_bits, const u32* __restrict__ head_pref,
-                                                               const u32* __restrict__ ginfo, u64 nL, u64 rank_base, u64* __restrict__ codes) {
+template <class CodeT>
+__global__ void __launch_bounds__(256) mg2_codes_kernel(const u32* __restrict__ order, const u32* __restrict__ head_bits, const u32* __restrict__ head_pref,
+                                                        const u32* __restrict__ ginfo, u64 nL, u64 rank_base, CodeT* __restrict__ codes) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nL) return;
     const u32 hw = head_bits[i >> 5];
     const u32 g = head_pref[i >> 5] + __popc(hw & (0xffffffffu >> (31 - (i & 31)))) - 1;
     const u32 gi = ginfo[g];
     const u64 rep = (hw >> (i & 31)) & 1u;
-    codes[order[i]] = (gi & 1u) ? ((((u64)(gi >> 2) + rank_base) << 2) | (u64)(gi & 2u) | rep) + 1ULL : 0ULL;
+    codes[order[i]] = (CodeT)((gi & 1u) ? ((((u64)(gi >> 2) + rank_base) << 2) | (u64)(gi & 2u) | rep) + 1ULL : 0ULL);
 }
-static __global__ void __launch_bounds__(256) mg2_codes_to_entries_kernel(const u32* __restrict__ sent_id, const u64* __restrict__ back, u64 nS, u64* __restrict__ ecode) {
+template <class CodeT>
+__global__ void __launch_bounds__(256) mg2_codes_to_entries_kernel(const u32* __restrict__ sent_id, const CodeT* __restrict__ back, u64 nS, u64* __restrict__ ecode) {
     const u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < nS) ecode[sent_id[q]] = back[q];
+    if (q < nS) ecode[sent_id[q]] = (u64)back[q];
 }
 // metasymbol of every phrase of the partition: rank of the group of its first entry (a whole phrase is always ranked)
 static __global__ void __launch_bounds__(256) mg2_meta_kernel(const u64* __restrict__ ecode, const u32* __restrict__ ph_off, const u64* __restrict__ ph_freq, u64 d,
@@ -265,22 +273,23 @@ static __global__ void mg2_rule_bounds_kernel(const u64* __restrict__ sorted_u, 
     }
     first[g] = lo;
 }
-template <class SymT>
+// UT: the rank travels in 32 bits whenever the round hands out fewer than 2^32 ranks
+template <class SymT, class UT>
 __global__ void __launch_bounds__(256) mg2_rule_send_kernel(const u32* __restrict__ perm, u64 n, const u64* __restrict__ u, const SymT* __restrict__ l,
-                                                            const SymT* __restrict__ r, const u8* __restrict__ h, u64* __restrict__ su, SymT* __restrict__ sl,
+                                                            const SymT* __restrict__ r, const u8* __restrict__ h, UT* __restrict__ su, SymT* __restrict__ sl,
                                                             SymT* __restrict__ sr, u8* __restrict__ sh) {
     const u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     const u32 k = perm[q];
-    su[q] = u[k]; sl[q] = l[k]; sr[q] = r[k]; sh[q] = h[k];
+    su[q] = (UT)u[k]; sl[q] = l[k]; sr[q] = r[k]; sh[q] = h[k];
 }
-template <class SymT>
-__global__ void __launch_bounds__(256) mg2_rule_scatter_kernel(const u64* __restrict__ u, const SymT* __restrict__ l, const SymT* __restrict__ r,
+template <class SymT, class UT>
+__global__ void __launch_bounds__(256) mg2_rule_scatter_kernel(const UT* __restrict__ u, const SymT* __restrict__ l, const SymT* __restrict__ r,
                                                                const u8* __restrict__ h, u64 m, u64 base, u64 tot_local, SymT* __restrict__ rule_l,
                                                                SymT* __restrict__ rule_r, u8* __restrict__ has_hocc, u32* err) {
     const u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= m) return;
-    const u64 k = u[q] - base;
+    const u64 k = (u64)u[q] - base;
     if (k >= tot_local) { atomicExch(err, 1u); return; }
     rule_l[k] = l[q]; rule_r[k] = r[q]; has_hocc[k] = h[q];
 }
@@ -308,6 +317,9 @@ inline std::vector<u64> mg2_exchange_counts(Comm& cm, const std::vector<u64>& se
     for (int p = 0; p < cm.world; p++) recv[(size_t)p] = all[(size_t)p * (size_t)cm.world + (size_t)cm.rank];
     return recv;
 }
+inline void mg2_a2a_soa(Comm& cm, const std::vector<Comm::SoaPart>& parts, const std::vector<u64>& send_counts, const std::vector<u64>& recv_counts, cudaStream_t st) {
+    cm.all_to_all_soa(parts.data(), (int)parts.size(), send_counts.data(), recv_counts.data(), st);
+}
 template <class T>
 inline void mg2_a2a(Comm& cm, const T* d_send, const std::vector<u64>& send_counts, T* d_recv, const std::vector<u64>& recv_counts, cudaStream_t st) {
     const std::vector<u64> so = mg2_offsets(send_counts, sizeof(T)), ro = mg2_offsets(recv_counts, sizeof(T));
@@ -334,7 +346,7 @@ struct Mg2Part {   // this rank's partition of the round's dictionary + what the
     DevBuf<u8> p_fin;
     DevBuf<u64> p_meta;
     int sym_bits = 0, K = 1, spare = 0;
-    u64 max_len_g = 0;
+    u64 max_len_g = 0, max_freq_g = 0;
     explicit Mg2Part(grlgpu_ctx* c) : PR(c) {}
 };
 
@@ -393,8 +405,10 @@ void mg2_rank(grlgpu_ctx* c, Comm& cm, Mg2Part& P, Mg2Slices& S) {
     // ---- R: records by key range -> E2 ----
     std::vector<u64> cnt_send, cnt_recv;
     DevBuf<u32> sent_id;   // entry id of the q-th record this rank sent (the codes come back in the same order)
-    DevBuf<u64> r_key, r_y;
-    DevBuf<u8> r_left_raw;
+    const bool narrow_y = P.max_freq_g < (1ull << 30);  // the records' frequency word fits 32 bits (frequency | full << 31)
+    const u64 y_bytes = narrow_y ? 4 : 8;
+    DevBuf<u64> r_key;
+    DevBuf<u8> r_left_raw, r_y_raw;
     DevBuf<u32> r_id, r_rem;
     u64 nL = 0;
     {
@@ -404,23 +418,24 @@ void mg2_rank(grlgpu_ctx* c, Comm& cm, Mg2Part& P, Mg2Slices& S) {
         GRL_LAUNCH("mg_key_dest", nS * 16, mg2_key_dest_kernel, grid_for(nS, 256), 256, 0, st, PR.keys.p, nS, d_split.p, (int)splitters.size(), dest.p, idx.p);
         cnt_send = mg2_partition(dest, idx, nS, G, perm, st);
         dest.release(); idx.release();
-        DevBuf<u64> s_key(nS, st), s_y(nS, st);
-        DevBuf<u8> s_left(nS * sizeof(SymT), st);
+        DevBuf<u64> s_key(nS, st);
+        DevBuf<u8> s_left(nS * sizeof(SymT), st), s_y(nS * y_bytes, st);
         DevBuf<u32> s_rem(nS, st);
         sent_id.alloc(nS, st);
-        GRL_LAUNCH("mg_build_send", nS * (48 + 2 * sizeof(SymT)), (mg2_build_send_kernel<SymT>), grid_for(nS, 256), 256, 0, st, perm.p, nS, PR.keys.p, PR.vals.p, D, PR.rem.p,
-                   PR.phr_of.p, PR.ph_off.p, PR.ph_freq.p, s_key.p, (SymT*)s_left.p, s_y.p, sent_id.p, s_rem.p);
+        if (narrow_y)
+            GRL_LAUNCH("mg_build_send", nS * (44 + 2 * sizeof(SymT)), (mg2_build_send_kernel<SymT, u32>), grid_for(nS, 256), 256, 0, st, perm.p, nS, PR.keys.p, PR.vals.p, D, PR.rem.p,
+                       PR.phr_of.p, PR.ph_off.p, PR.ph_freq.p, s_key.p, (SymT*)s_left.p, (u32*)s_y.p, sent_id.p, s_rem.p);
+        else
+            GRL_LAUNCH("mg_build_send", nS * (48 + 2 * sizeof(SymT)), (mg2_build_send_kernel<SymT, u64>), grid_for(nS, 256), 256, 0, st, perm.p, nS, PR.keys.p, PR.vals.p, D, PR.rem.p,
+                       PR.phr_of.p, PR.ph_off.p, PR.ph_freq.p, s_key.p, (SymT*)s_left.p, (u64*)s_y.p, sent_id.p, s_rem.p);
         perm.release();
         PR.keys.release(); PR.vals.release();
         cnt_recv = mg2_exchange_counts(cm, cnt_send, st);
         nL = mg2_sum(cnt_recv);
         if (nL >= 0xfffffff0ull) throw Error(GRLGPU_ERR_LIMIT, "more than 2^32 suffix entries in one rank's key range");
-        r_key.alloc(nL, st); r_y.alloc(nL, st); r_left_raw.alloc(nL * sizeof(SymT), st); r_id.alloc(nL, st); r_rem.alloc(nL, st);
-        mg2_a2a<u64>(cm, s_key.p, cnt_send, r_key.p, cnt_recv, st);
-        mg2_a2a<SymT>(cm, (const SymT*)s_left.p, cnt_send, (SymT*)r_left_raw.p, cnt_recv, st);
-        mg2_a2a<u64>(cm, s_y.p, cnt_send, r_y.p, cnt_recv, st);
-        mg2_a2a<u32>(cm, sent_id.p, cnt_send, r_id.p, cnt_recv, st);
-        mg2_a2a<u32>(cm, s_rem.p, cnt_send, r_rem.p, cnt_recv, st);
+        r_key.alloc(nL, st); r_y_raw.alloc(nL * y_bytes, st); r_left_raw.alloc(nL * sizeof(SymT), st); r_id.alloc(nL, st); r_rem.alloc(nL, st);
+        mg2_a2a_soa(cm, {{s_key.p, r_key.p, 8}, {s_left.p, r_left_raw.p, sizeof(SymT)}, {s_y.p, r_y_raw.p, y_bytes}, {sent_id.p, r_id.p, 4}, {s_rem.p, r_rem.p, 4}}, cnt_send, cnt_recv,
+                    st);
         GRL_CUDA(cudaStreamSynchronize(st));  // the send buffers go back to the pool at the end of this block
     }
     const SymT* r_left = (const SymT*)r_left_raw.p;
@@ -517,12 +532,13 @@ void mg2_rank(grlgpu_ctx* c, Comm& cm, Mg2Part& P, Mg2Slices& S) {
     gcnt.zero(); gacc.zero(); gmax.zero(); gmin.fill_ff();
     if (nL) {
         DevBuf<ulonglong2> r_ei(nL, st);
-        GRL_LAUNCH("mg_zip", nL * (24 + sizeof(SymT)), (mg2_zip_kernel<SymT>), grid_for(nL, 256), 256, 0, st, r_left, r_y.p, nL, r_ei.p);
+        if (narrow_y) GRL_LAUNCH("mg_zip", nL * (20 + sizeof(SymT)), (mg2_zip_kernel<SymT, u32>), grid_for(nL, 256), 256, 0, st, r_left, (const u32*)r_y_raw.p, nL, r_ei.p);
+        else GRL_LAUNCH("mg_zip", nL * (24 + sizeof(SymT)), (mg2_zip_kernel<SymT, u64>), grid_for(nL, 256), 256, 0, st, r_left, (const u64*)r_y_raw.p, nL, r_ei.p);
         GRL_LAUNCH("group_reduce", nL * 24 + Gn * 32, mg2_group_reduce_kernel, grid_for(nL, 256), 256, 0, st, order.p, head_bits.p, head_pref.p, r_ei.p, nL, gcnt.p, gacc.p, gmin.p,
                    gmax.p);
         GRL_CUDA(cudaStreamSynchronize(st));
     }
-    r_y.release(); r_left_raw.release();
+    r_y_raw.release(); r_left_raw.release();
     const u64 bwt_dummy = A + 1, hocc_dummy = A + 2;  // exact_par_phase.hpp:113-115
     GRL_LAUNCH("group_finalize", 0, group_finalize_kernel, grid_for(Gn, 256), 256, 0, st, gcnt.p, gmin.p, gmax.p, Gn, bwt_dummy, hocc_dummy, rflag.p, vflag.p, psym.p);
     DevBuf<u32> cnt2(2, st);
@@ -596,11 +612,19 @@ void mg2_rank(grlgpu_ctx* c, Comm& cm, Mg2Part& P, Mg2Slices& S) {
     {
         DevBuf<u32> ginfo(Gn, st);
         GRL_LAUNCH("pack_ginfo_dense", Gn * 16, pack_ginfo_dense_kernel, grid_for(Gn, 256), 256, 0, st, gcnt.p, rflag.p, rrank.p, Gn, ginfo.p);
-        DevBuf<u64> codes(nL, st), back(nS, st);
-        if (nL) GRL_LAUNCH("mg_codes", nL * 24, mg2_codes_kernel, grid_for(nL, 256), 256, 0, st, order.p, head_bits.p, head_pref.p, ginfo.p, nL, S.rank_base, codes.p);
-        mg2_a2a<u64>(cm, codes.p, cnt_recv, back.p, cnt_send, st);
+        const bool narrow_code = S.tot < (1ull << 29);  // ((rank << 2) | flags) + 1 fits 32 bits
+        const u64 cb = narrow_code ? 4 : 8;
+        DevBuf<u8> codes(nL * cb, st), back(nS * cb, st);
+        if (nL) {
+            if (narrow_code) GRL_LAUNCH("mg_codes", nL * 20, (mg2_codes_kernel<u32>), grid_for(nL, 256), 256, 0, st, order.p, head_bits.p, head_pref.p, ginfo.p, nL, S.rank_base, (u32*)codes.p);
+            else GRL_LAUNCH("mg_codes", nL * 24, (mg2_codes_kernel<u64>), grid_for(nL, 256), 256, 0, st, order.p, head_bits.p, head_pref.p, ginfo.p, nL, S.rank_base, (u64*)codes.p);
+        }
+        mg2_a2a_soa(cm, {{codes.p, back.p, cb}}, cnt_recv, cnt_send, st);
         ecode.zero();
-        if (nS) GRL_LAUNCH("mg_codes_to_entries", nS * 20, mg2_codes_to_entries_kernel, grid_for(nS, 256), 256, 0, st, sent_id.p, back.p, nS, ecode.p);
+        if (nS) {
+            if (narrow_code) GRL_LAUNCH("mg_codes_to_entries", nS * 16, (mg2_codes_to_entries_kernel<u32>), grid_for(nS, 256), 256, 0, st, sent_id.p, (const u32*)back.p, nS, ecode.p);
+            else GRL_LAUNCH("mg_codes_to_entries", nS * 20, (mg2_codes_to_entries_kernel<u64>), grid_for(nS, 256), 256, 0, st, sent_id.p, (const u64*)back.p, nS, ecode.p);
+        }
         GRL_CUDA(cudaStreamSynchronize(st));
     }
     order.release(); head_bits.release(); head_pref.release(); sent_id.release();
@@ -648,24 +672,33 @@ void mg2_rank(grlgpu_ctx* c, Comm& cm, Mg2Part& P, Mg2Slices& S) {
             if (vp != sv.p) std::swap(sv, sv_alt);
             perm = std::move(sv);
         }
-        DevBuf<u64> su(nR, st);
-        DevBuf<u8> sl(nR * sizeof(SymT), st), sr(nR * sizeof(SymT), st), sh(nR, st);
-        if (nR) GRL_LAUNCH("mg_rule_send", nR * 2 * (9 + 2 * sizeof(SymT)), (mg2_rule_send_kernel<SymT>), grid_for(nR, 256), 256, 0, st, perm.p, nR, ru.p, (const SymT*)rl.p,
-                           (const SymT*)rr.p, rh.p, su.p, (SymT*)sl.p, (SymT*)sr.p, sh.p);
+        const bool narrow_u = S.tot < (1ull << 32);
+        const u64 ub = narrow_u ? 4 : 8;
+        DevBuf<u8> su(nR * ub, st), sl(nR * sizeof(SymT), st), sr(nR * sizeof(SymT), st), sh(nR, st);
+        if (nR) {
+            if (narrow_u)
+                GRL_LAUNCH("mg_rule_send", nR * 2 * (9 + 2 * sizeof(SymT)), (mg2_rule_send_kernel<SymT, u32>), grid_for(nR, 256), 256, 0, st, perm.p, nR, ru.p, (const SymT*)rl.p,
+                           (const SymT*)rr.p, rh.p, (u32*)su.p, (SymT*)sl.p, (SymT*)sr.p, sh.p);
+            else
+                GRL_LAUNCH("mg_rule_send", nR * 2 * (9 + 2 * sizeof(SymT)), (mg2_rule_send_kernel<SymT, u64>), grid_for(nR, 256), 256, 0, st, perm.p, nR, ru.p, (const SymT*)rl.p,
+                           (const SymT*)rr.p, rh.p, (u64*)su.p, (SymT*)sl.p, (SymT*)sr.p, sh.p);
+        }
         rr_cnt = mg2_exchange_counts(cm, rs_cnt, st);
         const u64 mR = mg2_sum(rr_cnt);
         if (mR != tot_local) throw Error(GRLGPU_ERR_STATE, "multi-GPU round: " + std::to_string(mR) + " rules arrived for " + std::to_string(tot_local) + " ranks of this range");
-        DevBuf<u64> qu(mR, st);
-        DevBuf<u8> ql(mR * sizeof(SymT), st), qr(mR * sizeof(SymT), st), qh(mR, st);
-        mg2_a2a<u64>(cm, su.p, rs_cnt, qu.p, rr_cnt, st);
-        mg2_a2a<SymT>(cm, (const SymT*)sl.p, rs_cnt, (SymT*)ql.p, rr_cnt, st);
-        mg2_a2a<SymT>(cm, (const SymT*)sr.p, rs_cnt, (SymT*)qr.p, rr_cnt, st);
-        mg2_a2a<u8>(cm, sh.p, rs_cnt, qh.p, rr_cnt, st);
+        DevBuf<u8> qu(mR * ub, st), ql(mR * sizeof(SymT), st), qr(mR * sizeof(SymT), st), qh(mR, st);
+        mg2_a2a_soa(cm, {{su.p, qu.p, ub}, {sl.p, ql.p, sizeof(SymT)}, {sr.p, qr.p, sizeof(SymT)}, {sh.p, qh.p, 1}}, rs_cnt, rr_cnt, st);
         S.rule_l.alloc(tot_local * sizeof(SymT), st);
         S.rule_r.alloc(tot_local * sizeof(SymT), st);
         S.has_hocc.alloc(tot_local, st);
-        if (mR) GRL_LAUNCH("mg_rule_scatter", mR * 2 * (9 + 2 * sizeof(SymT)), (mg2_rule_scatter_kernel<SymT>), grid_for(mR, 256), 256, 0, st, qu.p, (const SymT*)ql.p, (const SymT*)qr.p,
-                           qh.p, mR, S.rank_base, tot_local, (SymT*)S.rule_l.p, (SymT*)S.rule_r.p, S.has_hocc.p, err.p);
+        if (mR) {
+            if (narrow_u)
+                GRL_LAUNCH("mg_rule_scatter", mR * 2 * (9 + 2 * sizeof(SymT)), (mg2_rule_scatter_kernel<SymT, u32>), grid_for(mR, 256), 256, 0, st, (const u32*)qu.p, (const SymT*)ql.p,
+                           (const SymT*)qr.p, qh.p, mR, S.rank_base, tot_local, (SymT*)S.rule_l.p, (SymT*)S.rule_r.p, S.has_hocc.p, err.p);
+            else
+                GRL_LAUNCH("mg_rule_scatter", mR * 2 * (9 + 2 * sizeof(SymT)), (mg2_rule_scatter_kernel<SymT, u64>), grid_for(mR, 256), 256, 0, st, (const u64*)qu.p, (const SymT*)ql.p,
+                           (const SymT*)qr.p, qh.p, mR, S.rank_base, tot_local, (SymT*)S.rule_l.p, (SymT*)S.rule_r.p, S.has_hocc.p, err.p);
+        }
         if (d2h_scalar(err.p, st)) throw Error(GRLGPU_ERR_STATE, "multi-GPU round: a phrase came back unranked or a rule left its rank range");
     }
     S.valid = true;
@@ -743,8 +776,7 @@ void mg2_round_t(grlgpu_ctx* c, Comm& cm, grlgpu_round_t* out) {
     DevBuf<u32> r_lens(m, st);
     DevBuf<u64> r_counts(m, st);
     DevBuf<u8> r_cells(ncr * sizeof(CellT) + 16, st);
-    mg2_a2a<u32>(cm, s_lens.p, s_phr, r_lens.p, r_phr, st);
-    mg2_a2a<u64>(cm, s_counts.p, s_phr, r_counts.p, r_phr, st);
+    mg2_a2a_soa(cm, {{s_lens.p, r_lens.p, 4}, {s_counts.p, r_counts.p, 8}}, s_phr, r_phr, st);
     mg2_a2a<CellT>(cm, (const CellT*)s_cells.p, s_cel, (CellT*)r_cells.p, r_cel, st);
     GRL_CUDA(cudaStreamSynchronize(st));
     s_lens.release(); s_counts.release(); s_cells.release();
@@ -802,6 +834,7 @@ void mg2_round_t(grlgpu_ctx* c, Comm& cm, grlgpu_round_t* out) {
             d_g += all[(size_t)p * 4];
             nE_g += all[(size_t)p * 4 + 1];
             maxf_g = std::max(maxf_g, all[(size_t)p * 4 + 2]);
+            P.max_freq_g = maxf_g;
             P.max_len_g = std::max(P.max_len_g, all[(size_t)p * 4 + 3]);
         }
     }
