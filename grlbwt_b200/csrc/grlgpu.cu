@@ -1331,7 +1331,16 @@ int grlgpu_can_peer(int device_a, int device_b) {
 }
 int grlgpu_set_peers(grlgpu_ctx* ctx, const int* devices, int n_devices) {
     if (!ctx || (n_devices > 0 && !devices) || n_devices < 0) return GRLGPU_ERR_ARG;
-    return guarded(ctx, [&] { ctx->pool.set_peers(std::vector<int>(devices, devices + n_devices)); });
+    return guarded(ctx, [&] {
+        // runtime peer copies (cudaMemcpyPeerAsync) are staged through host memory unless peer access is enabled between the two
+        // devices' contexts; with it they are direct NVLink DMA. Enabled once per pair and process ("already enabled" is fine).
+        for (int i = 0; i < n_devices; i++) {
+            if (devices[i] == ctx->device || !grlgpu_can_peer(ctx->device, devices[i])) continue;
+            const cudaError_t e = cudaDeviceEnablePeerAccess(devices[i], 0);
+            if (e != cudaSuccess) cudaGetLastError();  // cudaErrorPeerAccessAlreadyEnabled, or unsupported: the copies then take the staged path
+        }
+        ctx->pool.set_peers(std::vector<int>(devices, devices + n_devices));
+    });
 }
 
 int grlgpu_mg_stats(grlgpu_ctx* ctx, grlgpu_comm* comm, grlgpu_stats_t* out) {

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -66,6 +67,7 @@ struct DevicePool {
     std::map<u64, u64> free_ranges;       // offset -> length, inside [0, mapped)
     std::map<u64, u64> live;              // offset -> length
     u64 in_use = 0, peak = 0;
+    double grow_ms = 0;                   // host time spent mapping physical memory (GRLGPU_TRACE prints it when the pool is released)
     std::vector<int> peers;               // other devices that may read / write this pool directly (NVLink P2P, LocalComm pulls)
     static constexpr u64 ALIGN = 512;
 
@@ -110,6 +112,11 @@ struct DevicePool {
         prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
         prop.location.id = device;
         std::vector<CUmemAccessDesc> acc = access_descs();
+        const auto t_grow = std::chrono::steady_clock::now();
+        struct GrowClock {
+            double& ms; std::chrono::steady_clock::time_point t0;
+            ~GrowClock() { ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+        } gclk{grow_ms, t_grow};
         for (u64 done = 0; done < add; done += chunk) {
             CUmemGenericAllocationHandle h;
             if (p_create(&h, chunk, &prop, 0) != CUDA_SUCCESS)
@@ -182,6 +189,8 @@ struct DevicePool {
     }
     void release_all() {  // caller guarantees the device is idle
         if (!base) return;
+        if (getenv("GRLGPU_TRACE")) fprintf(stderr, "[grlgpu] device %d pool: %.1f GB mapped in %zu chunks (%zu peer device%s), %.1f ms spent mapping\n", device, mapped / 1e9,
+                                            handles.size(), peers.size(), peers.size() == 1 ? "" : "s", grow_ms);
         for (size_t i = 0; i < handles.size(); i++) { p_unmap(base + (u64)i * chunk, chunk); p_release(handles[i]); }
         p_addrfree(base, va_size);
         handles.clear(); free_ranges.clear(); live.clear();
