@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--bwt-reads", type=int, default=8_000_000, help="reads of the whole-construction leg (bwt_total); 0 skips it")
     ap.add_argument("--write-digest", action="store_true", help="1 GPU: store the output digest under profiles/ as the value every rank count must reproduce")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--comm", choices=["auto", "ipc", "nccl"], default="auto",
+                    help="exchange backend of the N > 1 ranks: CUDA IPC windows + shared-memory rendezvous (one box, NVLink), or NCCL send/recv")
     return ap.parse_args()
 
 
@@ -298,7 +300,7 @@ def run_ours(args, rank, world, local_rank):
     stream = torch.cuda.Stream(device=dev)   # the library issues every kernel (and NCCL call) on this stream, so torch events bracket it
     torch.cuda.set_stream(stream)
     ctx = G.GrlGpu(local_rank, 0, stream=stream.cuda_stream)
-    comm = mg.nccl_comm_from_torch(dist, rank, world, local_rank, torch) if world > 1 else None
+    comm = mg.comm_from_torch(dist, rank, world, local_rank, torch, kind=args.comm) if world > 1 else None
     arena = [None]
     final_cells = [0]   # cells of this rank's final parse (one per local string)
     e2e_parts = {}
@@ -582,7 +584,8 @@ def run_ours(args, rank, world, local_rank):
                            "generator": "torch CUDA RNG in fixed blocks of reads seeded per block: every rank count parses slices of the same global text",
                            "parallelism": "1 GPU" if world == 1 else
                            f"{world} ranks, contiguous ranges of whole reads; the round's dictionary is PARTITIONED, never replicated: phrases by owner (content hash), "
-                           f"suffix entries by first-key range, rules by rank range; all exchanges are NCCL grouped send/recv issued by libgrlgpu.so",
+                           f"suffix entries by first-key range, rules by rank range; all exchanges are issued by libgrlgpu.so "
+                           f"({exchange_per_step['backend'] if exchange_per_step else ''}; --comm nccl selects NCCL grouped send/recv)",
                            "exchange_per_step": exchange_per_step},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "same_sample": same_sample,
                 "digest": dg, "bwt_total": bwt_total, "parse_rounds": parse_rounds, "kernels": kernels}

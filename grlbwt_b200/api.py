@@ -84,6 +84,8 @@ def lib_gpu():
         L.grlgpu_histogram.argtypes = [vp, vp]
         L.grlgpu_nccl_unique_id.argtypes = [vp]
         L.grlgpu_comm_create_nccl.argtypes = [C.POINTER(vp), vp, C.c_int, C.c_int, C.c_int]
+        L.grlgpu_comm_create_ipc.argtypes = [C.POINTER(vp), C.c_char_p, C.c_int, C.c_int, C.c_int]
+        L.grlgpu_can_peer.argtypes = [C.c_int, C.c_int]
         L.grlgpu_local_group_create.argtypes = [C.POINTER(vp), C.c_int]
         L.grlgpu_local_group_abort.argtypes = [vp]
         L.grlgpu_local_group_destroy.argtypes = [vp]

@@ -870,6 +870,7 @@ inline void ensure_stats(grlgpu_ctx* ctx) {
     }
 }
 
+thread_local std::string t_last_error;  // errors of calls that have no context (communicator creation): grlgpu_last_error(NULL)
 template <class F>
 int guarded(grlgpu_ctx* c, F&& f) {
     struct CtxGuard {  // per-call binding of the context's launch accounting and memory pool
@@ -883,12 +884,12 @@ int guarded(grlgpu_ctx* c, F&& f) {
         f();
         return GRLGPU_OK;
     } catch (const Error& e) {
-        if (c) c->last_error = e.what();
+        if (c) c->last_error = e.what(); else t_last_error = e.what();
         cudaGetLastError();
         if (e.code == GRLGPU_ERR_CUDA && std::string(e.what()).find("out of memory") != std::string::npos) return GRLGPU_ERR_NOMEM;
         return e.code;
     } catch (const std::exception& e) {
-        if (c) c->last_error = e.what();
+        if (c) c->last_error = e.what(); else t_last_error = e.what();
         return GRLGPU_ERR_CUDA;
     }
 }
@@ -1283,6 +1284,15 @@ int grlgpu_comm_create_nccl(grlgpu_comm** comm, const void* id128, int rank, int
         *comm = h.release();
     });
 }
+int grlgpu_comm_create_ipc(grlgpu_comm** comm, const char* session, int rank, int world, int device) {
+    if (!comm || !session || session[0] != '/' || world < 1 || world > 31 || rank < 0 || rank >= world) return GRLGPU_ERR_ARG;
+    *comm = nullptr;
+    return guarded(nullptr, [&] {
+        std::unique_ptr<grlgpu_comm> h(new grlgpu_comm());
+        h->c.reset(new IpcComm(session, rank, world, device));
+        *comm = h.release();
+    });
+}
 int grlgpu_local_group_create(grlgpu_local_group** group, int world) {
     if (!group || world < 1 || world > 31) return GRLGPU_ERR_ARG;
     *group = new grlgpu_local_group(world);
@@ -1392,6 +1402,10 @@ int grlgpu_mg_round(grlgpu_ctx* ctx, grlgpu_comm* comm, grlgpu_round_t* out) {
     if (!ctx->text || ctx->done || !ctx->have_stats || !ctx->mg_n_strings) return GRLGPU_ERR_STATE;
     return guarded(ctx, [&] {
         Comm& cm = *comm->c;
+        struct AbortOnThrow {  // a rank that fails inside the round must not leave its peers waiting in an exchange
+            Comm& cm; bool armed = true;
+            ~AbortOnThrow() { if (armed) cm.abort_group(); }
+        } guard{cm};
         if (ctx->first) switch (ctx->w) {
             case 1: mg2_round_t<u8, true>(ctx, cm, out); break;
             case 2: mg2_round_t<u16, true>(ctx, cm, out); break;
@@ -1403,6 +1417,7 @@ int grlgpu_mg_round(grlgpu_ctx* ctx, grlgpu_comm* comm, grlgpu_round_t* out) {
             case 4: mg2_round_t<u32, false>(ctx, cm, out); break;
             default: mg2_round_t<u64, false>(ctx, cm, out); break;
         }
+        guard.armed = false;
     });
 }
 
@@ -1621,7 +1636,7 @@ const char* grlgpu_strerror(int status) {
     }
     return "unknown status";
 }
-const char* grlgpu_last_error(const grlgpu_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+const char* grlgpu_last_error(const grlgpu_ctx* ctx) { return ctx ? ctx->last_error.c_str() : t_last_error.c_str(); }
 
 // ---- self-test hooks ----
 int grlgpu_selftest_scan(const uint32_t* in, uint64_t n, uint64_t* out_exclusive, uint64_t* total) {

@@ -298,6 +298,23 @@ static __global__ void mg2_add_u64_kernel(u64* p, u64 v) {
 }
 
 // ---------------------------------------------------------------- host helpers
+// GRLGPU_TRACE: wall time of every stage of a multi-GPU round on this rank (a stream synchronisation per lap; off otherwise)
+struct Mg2StageClock {
+    bool on;
+    int rank, round;
+    cudaStream_t st;
+    std::chrono::steady_clock::time_point t0;
+    Mg2StageClock(int rank_, int round_, cudaStream_t st_) : on(getenv("GRLGPU_TRACE") != nullptr), rank(rank_), round(round_), st(st_) {
+        if (on) { cudaStreamSynchronize(st); t0 = std::chrono::steady_clock::now(); }
+    }
+    void lap(const char* what) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[grlgpu] rank %d round %d stage %-22s %8.2f ms\n", rank, round, what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 inline std::vector<u64> mg2_offsets(const std::vector<u64>& counts, u64 elem_bytes) {
     std::vector<u64> off(counts.size() + 1, 0);
     for (size_t i = 0; i < counts.size(); i++) off[i + 1] = off[i] + counts[i] * elem_bytes;
@@ -380,12 +397,15 @@ void mg2_rank(grlgpu_ctx* c, Comm& cm, Mg2Part& P, Mg2Slices& S) {
     const int sym_bits = P.sym_bits, K = P.K;
     const int key_bits = std::min(64, sym_bits * K), first_bits = std::min(64, sym_bits * K + P.spare);
     const bool trace = getenv("GRLGPU_TRACE") != nullptr;
+    Mg2StageClock clk(me, c->round + 1, st);
 
     // ---- S: splitters from an all-gathered regular sample of the first keys ----
     std::vector<u64> splitters;
     {
-        const u64 ns = std::min<u64>(nS, MG_NSAMP), stride = ns ? std::max<u64>(1, nS / ns) : 1;
-        std::vector<u64> mine(MG_NSAMP + 1, 0);
+        // ~16 K samples over all ranks put every splitter within about a percent of its quantile; more only lengthens the gather
+        const u64 ns_cap = std::min<u64>(MG_NSAMP, std::max<u64>(512, 16384 / (u64)G));
+        const u64 ns = std::min<u64>(nS, ns_cap), stride = ns ? std::max<u64>(1, nS / ns) : 1;
+        std::vector<u64> mine(ns_cap + 1, 0);
         mine[0] = ns;
         if (ns) {
             DevBuf<u64> sk(ns, st);
@@ -396,12 +416,13 @@ void mg2_rank(grlgpu_ctx* c, Comm& cm, Mg2Part& P, Mg2Slices& S) {
         const std::vector<u64> all = mg2_gather(cm, mine, st);
         std::vector<u64> samp;
         for (int p = 0; p < G; p++) {
-            const u64* row = all.data() + (size_t)p * (MG_NSAMP + 1);
+            const u64* row = all.data() + (size_t)p * (ns_cap + 1);
             samp.insert(samp.end(), row + 1, row + 1 + row[0]);
         }
         std::sort(samp.begin(), samp.end());
         for (int g = 1; g < G; g++) splitters.push_back(samp.empty() ? 0ULL : samp[(size_t)((u64)g * samp.size() / (u64)G)]);
     }
+    clk.lap("S splitters");
     // ---- R: records by key range -> E2 ----
     std::vector<u64> cnt_send, cnt_recv;
     DevBuf<u32> sent_id;   // entry id of the q-th record this rank sent (the codes come back in the same order)
@@ -430,6 +451,7 @@ void mg2_rank(grlgpu_ctx* c, Comm& cm, Mg2Part& P, Mg2Slices& S) {
                        PR.phr_of.p, PR.ph_off.p, PR.ph_freq.p, s_key.p, (SymT*)s_left.p, (u64*)s_y.p, sent_id.p, s_rem.p);
         perm.release();
         PR.keys.release(); PR.vals.release();
+        clk.lap("R build records");
         cnt_recv = mg2_exchange_counts(cm, cnt_send, st);
         nL = mg2_sum(cnt_recv);
         if (nL >= 0xfffffff0ull) throw Error(GRLGPU_ERR_LIMIT, "more than 2^32 suffix entries in one rank's key range");
@@ -438,6 +460,7 @@ void mg2_rank(grlgpu_ctx* c, Comm& cm, Mg2Part& P, Mg2Slices& S) {
                     st);
         GRL_CUDA(cudaStreamSynchronize(st));  // the send buffers go back to the pool at the end of this block
     }
+    clk.lap("E2 exchange");
     const SymT* r_left = (const SymT*)r_left_raw.p;
     DevBuf<u64> d_seg((u64)G + 1, st);
     {
@@ -472,6 +495,7 @@ void mg2_rank(grlgpu_ctx* c, Comm& cm, Mg2Part& P, Mg2Slices& S) {
         GRL_CUDA(cudaStreamSynchronize(st));
         r_key.release();
     }
+    clk.lap("O first-key sort");
     for (u64 dpt = (u64)K;; dpt += (u64)K) {
         // every rank takes part in every pass (it serves key requests even when its own range is resolved)
         u64 nA_max = 0;
@@ -517,6 +541,7 @@ void mg2_rank(grlgpu_ctx* c, Comm& cm, Mg2Part& P, Mg2Slices& S) {
     }
     apos.release();
     r_id.release(); r_rem.release();
+    clk.lap("O refinement");
 
     // ---- G: groups of my range, ranked / hocc, preliminary BWT of the range ----
     DevBuf<u32> head_pref(n_words, st);
@@ -607,6 +632,7 @@ void mg2_rank(grlgpu_ctx* c, Comm& cm, Mg2Part& P, Mg2Slices& S) {
     S.rank_base = bases[(size_t)me];
     S.tot_local = tot_local;
     S.tot = bases[(size_t)G];
+    clk.lap("G groups + pre-BWT");
     // ---- E3: one code per entry back to its owner ----
     DevBuf<u64> ecode(nE, st);
     {
@@ -629,6 +655,7 @@ void mg2_rank(grlgpu_ctx* c, Comm& cm, Mg2Part& P, Mg2Slices& S) {
     }
     order.release(); head_bits.release(); head_pref.release(); sent_id.release();
     gcnt.release(); rflag.release(); vflag.release(); rrank.release(); vidx.release(); gacc.release(); gmin.release(); gmax.release(); psym.release();
+    clk.lap("E3 codes back");
     // ---- U: metasymbols of my phrases, rules of the groups whose representative I own -> E4 by rank range ----
     P.p_meta.alloc(d, st);
     DevBuf<u32> err(1, st);
@@ -683,6 +710,7 @@ void mg2_rank(grlgpu_ctx* c, Comm& cm, Mg2Part& P, Mg2Slices& S) {
                 GRL_LAUNCH("mg_rule_send", nR * 2 * (9 + 2 * sizeof(SymT)), (mg2_rule_send_kernel<SymT, u64>), grid_for(nR, 256), 256, 0, st, perm.p, nR, ru.p, (const SymT*)rl.p,
                            (const SymT*)rr.p, rh.p, (u64*)su.p, (SymT*)sl.p, (SymT*)sr.p, sh.p);
         }
+        clk.lap("U rules by rank");
         rr_cnt = mg2_exchange_counts(cm, rs_cnt, st);
         const u64 mR = mg2_sum(rr_cnt);
         if (mR != tot_local) throw Error(GRLGPU_ERR_STATE, "multi-GPU round: " + std::to_string(mR) + " rules arrived for " + std::to_string(tot_local) + " ranks of this range");
@@ -701,6 +729,7 @@ void mg2_rank(grlgpu_ctx* c, Comm& cm, Mg2Part& P, Mg2Slices& S) {
         }
         if (d2h_scalar(err.p, st)) throw Error(GRLGPU_ERR_STATE, "multi-GPU round: a phrase came back unranked or a rule left its rank range");
     }
+    clk.lap("E4 rules exchange");
     S.valid = true;
 }
 
@@ -715,12 +744,14 @@ void mg2_round_t(grlgpu_ctx* c, Comm& cm, grlgpu_round_t* out) {
     const u64 sent0 = cm.bytes_sent;
     Round R(c);
     Timer t_all(st), t_text(st), t_dict(st);
+    Mg2StageClock clk(me, c->round + 1, st);
     t_all.start();
     t_text.start();
     // ---- L: this shard ----
     stage_flags<CellT, FIRST>(R);
     stage_dedup<CellT>(R);
     t_text.stop();
+    clk.lap("L text pass");
     t_dict.start();
     // owner of every local distinct phrase = content hash % G; pack by owner
     DevBuf<u32> perm;
@@ -751,6 +782,7 @@ void mg2_round_t(grlgpu_ctx* c, Comm& cm, grlgpu_round_t* out) {
                    R.d, s_lens.p, s_counts.p, (CellT*)s_cells.p);
         GRL_CUDA(cudaStreamSynchronize(st));
     }
+    clk.lap("pack by owner");
     // sizes: what every peer sends me, and the global parse length (termination: every string is one cell)
     std::vector<u64> r_phr((size_t)G), r_cel((size_t)G);
     bool done_global = false;
@@ -780,6 +812,7 @@ void mg2_round_t(grlgpu_ctx* c, Comm& cm, grlgpu_round_t* out) {
     mg2_a2a<CellT>(cm, (const CellT*)s_cells.p, s_cel, (CellT*)r_cells.p, r_cel, st);
     GRL_CUDA(cudaStreamSynchronize(st));
     s_lens.release(); s_counts.release(); s_cells.release();
+    clk.lap("E1 phrases to owners");
     // ---- M: owner-side dedup: my partition of the round's dictionary ----
     Mg2Part P(c);
     Round& PR = P.PR;
@@ -838,14 +871,16 @@ void mg2_round_t(grlgpu_ctx* c, Comm& cm, grlgpu_round_t* out) {
             P.max_len_g = std::max(P.max_len_g, all[(size_t)p * 4 + 3]);
         }
     }
+    clk.lap("M owner dedup");
     // ---- D .. E4: entries of my phrases, ranking by key range, rules by rank range ----
     const u64 A = c->alphabet;
     P.sym_bits = bit_width64(A + 1);
     P.K = std::max(1, 64 / P.sym_bits);
     P.spare = P.sym_bits * P.K < 64 ? 64 - P.sym_bits * P.K : 0;
     const bool wide = (A + nE_g + 8) >= (1ull << 32);  // rule values go up to A + 3 + tot + 1 with tot <= nE
-    if (wide) { mg2_gather<CellT, FIRST, u64>(c, P); mg2_rank<u64>(c, cm, P, S); }
-    else { mg2_gather<CellT, FIRST, u32>(c, P); mg2_rank<u32>(c, cm, P, S); }
+    if (wide) { mg2_gather<CellT, FIRST, u64>(c, P); clk.lap("D entries"); mg2_rank<u64>(c, cm, P, S); }
+    else { mg2_gather<CellT, FIRST, u32>(c, P); clk.lap("D entries"); mg2_rank<u32>(c, cm, P, S); }
+    clk.lap("(rank stages)");
     // ---- E5: metasymbols back to the ranks that saw the phrases, then the local rewrite ----
     {
         DevBuf<u64> reply(m, st), local_meta(R.d, st);
@@ -855,12 +890,14 @@ void mg2_round_t(grlgpu_ctx* c, Comm& cm, grlgpu_round_t* out) {
         GRL_CUDA(cudaStreamSynchronize(st));
     }
     t_dict.stop();
+    clk.lap("E5 metasymbols back");
     const u64 d_part = PR.d, nE_part = PR.nE;
     RoundTimes tm;
     tm.text = t_text.ms();
     tm.dict = t_dict.ms();
     c->lvl_sym_bytes = S.sym_bytes;
     finish_round(c, R, S.tot, S.n_pre_global, d_g, nE_g, maxf_g, tm, &t_all, out);
+    clk.lap("rewrite");
     out->done = done_global ? 1u : 0u;  // the phase ends when EVERY rank's strings are single cells
     c->done = done_global;
     out->n_strings = c->mg_n_strings;

@@ -3,14 +3,17 @@ few helpers. The rounds, the exchanges and the per-rank host threads all live in
 (grlbwt_b200/csrc/mg2.cuh, comm.hpp, host/gpu_par_phase.hpp); nothing here computes.
 
 Two ways to run N ranks:
-  * one process per GPU (bench.py under torchrun): `nccl_comm_from_torch` -- rank 0 makes the NCCL id, torch.distributed
-    broadcasts its 128 bytes, every rank builds its communicator inside libgrlgpu.so;
+  * one process per GPU (bench.py under torchrun): `comm_from_torch` -- on one box whose GPUs reach each other over NVLink the
+    ranks exchange through CUDA IPC windows and a shared-memory rendezvous (`ipc_comm`; rank 0 picks the segment's name and
+    torch.distributed broadcasts it); otherwise, or on request, NCCL (`nccl_comm_from_torch`: rank 0 makes the NCCL id,
+    torch.distributed broadcasts its 128 bytes). Either way the communicator lives inside libgrlgpu.so;
   * one process, N host threads (the grlbwt CLI with --gpus N, `build_bwt_mg` here): NCCL on request (COMM_NCCL), by default
     in-process peer copies over NVLink (several ranks may also share one GPU: the N > 1 path on a 1-GPU box).
 """
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -66,6 +69,44 @@ def nccl_comm_from_torch(dist, rank: int, world: int, device_index: int, torch) 
         t.copy_(torch.from_numpy(nccl_unique_id()))
     dist.broadcast(t, src=0)
     return nccl_comm(t.cpu().numpy(), rank, world, device_index)
+
+
+def ipc_comm(session: str, rank: int, world: int, device: int) -> Comm:
+    """one rank per process on one box: CUDA IPC windows + POSIX shared-memory rendezvous named `session` ("/name")"""
+    h = C.c_void_p()
+    L = lib_gpu()
+    rc = L.grlgpu_comm_create_ipc(C.byref(h), session.encode(), rank, world, device)
+    if rc != 0:
+        raise GrlGpuError(rc, "IPC communicator: " + L.grlgpu_last_error(None).decode())
+    return Comm(h)
+
+
+def can_peer_all(devices) -> bool:
+    L = lib_gpu()
+    return all(L.grlgpu_can_peer(int(a), int(b)) == 1 for a in devices for b in devices)
+
+
+def comm_from_torch(dist, rank: int, world: int, device_index: int, torch, kind: str = "auto") -> Comm:
+    """one process per GPU. kind: "ipc", "nccl" or "auto" (= ipc when every rank runs on this box and every pair of their GPUs
+    has peer access, else nccl; GRLBWT_COMM overrides). Every rank takes the same decision from the same facts."""
+    kind = os.environ.get("GRLBWT_COMM", kind)
+    if kind == "local":
+        kind = "ipc"
+    if kind == "auto":
+        one_box = int(os.environ.get("LOCAL_WORLD_SIZE", "0")) == world
+        kind = "ipc" if one_box and can_peer_all(range(world)) else "nccl"
+    if kind == "nccl":
+        return nccl_comm_from_torch(dist, rank, world, device_index, torch)
+    if kind != "ipc":
+        raise ValueError(f"unknown exchange backend {kind!r}")
+    dev = torch.device("cuda", device_index) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.zeros(64, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        name = f"/grlgpu-{os.getpid()}-{int.from_bytes(os.urandom(6), 'little'):x}".encode()
+        t[: len(name)] = torch.frombuffer(bytearray(name), dtype=torch.uint8).to(dev)
+    dist.broadcast(t, src=0)
+    session = bytes(t.cpu().numpy()).rstrip(b"\0").decode()
+    return ipc_comm(session, rank, world, device_index)
 
 
 def shard_bounds(text: np.ndarray, n_ranks: int):

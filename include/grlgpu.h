@@ -175,7 +175,7 @@ int grlgpu_fetch_str_ptrs(grlgpu_ctx* ctx, uint64_t* dst);
 int grlgpu_fetch_dictionary(grlgpu_ctx* ctx, uint64_t* syms, uint64_t* lens, uint64_t* freqs, uint64_t* metas);
 
 const char* grlgpu_strerror(int status);
-const char* grlgpu_last_error(const grlgpu_ctx* ctx);
+const char* grlgpu_last_error(const grlgpu_ctx* ctx);   /* ctx == NULL: the calling thread's last error of a call without a context */
 
 /* ---- multi-GPU rounds ----------------------------------------------------------------------
  * One context per GPU = one rank, each holding a shard of WHOLE strings (the reference's own split,
@@ -190,7 +190,10 @@ const char* grlgpu_last_error(const grlgpu_ctx* ctx);
  * suffix_induction / produce_pre_bwt / produce_grammar (exact_LMS_induction.h:94-158, exact_par_phase.cpp:14-242).
  *
  * Exchange backends (grlgpu_comm): NCCL -- one rank per process (bench.py under torchrun: rank 0 makes the id, the
- * launcher broadcasts its 128 bytes) or per host thread (the grlbwt CLI with --gpus N); "local" -- ranks are host
+ * launcher broadcasts its 128 bytes) or per host thread (the grlbwt CLI with --gpus N); "ipc" -- one rank per process
+ * on ONE box: every rank stages what it sends in a device window that its peers map through CUDA IPC and pull from
+ * with copy-engine DMA over NVLink, the rendezvous lives in a POSIX shared-memory segment named `session` ("/name",
+ * the same string on every rank, e.g. broadcast by the launcher; rank 0 creates and unlinks it); "local" -- ranks are host
  * threads of one process that pull from each other's send buffers with peer copies (NVLink P2P between GPUs, plain
  * device copies when several ranks share one GPU: how the N > 1 path is tested on a 1-GPU box). NCCL is resolved
  * with dlopen at the first use; the library loads without it. */
@@ -198,6 +201,7 @@ typedef struct grlgpu_comm grlgpu_comm;
 typedef struct grlgpu_local_group grlgpu_local_group;
 int grlgpu_nccl_unique_id(void* id128);
 int grlgpu_comm_create_nccl(grlgpu_comm** comm, const void* id128, int rank, int world, int device);
+int grlgpu_comm_create_ipc(grlgpu_comm** comm, const char* session, int rank, int world, int device);
 int grlgpu_local_group_create(grlgpu_local_group** group, int world);
 int grlgpu_local_group_abort(grlgpu_local_group* group);   /* a rank failed: wake the ranks waiting for it (they return GRLGPU_ERR_STATE) */
 int grlgpu_local_group_destroy(grlgpu_local_group* group);

@@ -112,9 +112,17 @@ import gen
 import grlbwt_b200 as G
 from grlbwt_b200 import mg
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-torch.cuda.set_device(lr)
-dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-comm = mg.nccl_comm_from_torch(dist, rank, world, lr, torch)
+kind = os.environ["GRL_COMM"]
+if kind == "ipc_shared":   # every rank on GPU 0 (the 1-GPU box): torch.distributed over gloo, exchanges through CUDA IPC
+    lr = 0
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo")
+    comm = mg.comm_from_torch(dist, rank, world, 0, torch, kind="ipc")
+else:
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    comm = mg.comm_from_torch(dist, rank, world, lr, torch, kind=kind)
+assert ("IPC" in comm.info()["kind"]) == kind.startswith("ipc"), comm.info()
 arr = {"reads": lambda: gen.dna_reads(100000, 150, seed=42), "rep": lambda: gen.repetitive_genomes(50, 200000, seed=7)}[os.environ["GRL_CASE"]]()
 lo, hi = mg.shard_bounds(arr, world)[rank]
 ctx = G.GrlGpu(lr)
@@ -123,7 +131,7 @@ ctx.mg_stats(comm)
 digests, cs_all = [], []
 while True:
     r = ctx.mg_round(comm)
-    cs = torch.tensor(np.array(ctx.mg_slice_checksum(), np.uint64).view(np.int64), device="cuda")
+    cs = torch.tensor(np.array(ctx.mg_slice_checksum(), np.uint64).view(np.int64), device="cuda" if dist.get_backend() == "nccl" else "cpu")
     dist.all_reduce(cs)
     digests.append([r.tot_phrases, r.n_pre_runs, r.parse_len, r.n_phrases, r.dict_syms] + [int(x) for x in cs.cpu().numpy().view(np.uint64)])
     sl = ctx.mg_slice_info()
@@ -140,9 +148,11 @@ dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("case", ["reads", "rep"])
-def test_mg_nccl_process_per_gpu(tmp_path, case):
-    """bench.py's arrangement: torchrun, one process per GPU, the NCCL id broadcast through torch.distributed"""
-    if n_gpus() < 2:
+@pytest.mark.parametrize("kind", ["nccl", "ipc", "ipc_shared"])
+def test_mg_process_per_gpu(tmp_path, case, kind):
+    """bench.py's arrangement: torchrun, one process per GPU; the NCCL id / the name of the IPC rendezvous segment is broadcast
+    through torch.distributed. "ipc_shared": three processes share GPU 0, so the IPC backend is also covered on a 1-GPU box."""
+    if kind != "ipc_shared" and n_gpus() < 2:
         pytest.skip("needs >= 2 GPUs")
     import gen
     import json
@@ -157,8 +167,8 @@ def test_mg_nccl_process_per_gpu(tmp_path, case):
                 break
     script = tmp_path / "w.py"
     script.write_text(NCCL_WORKER)
-    k = min(n_gpus(), 8)
-    env = dict(os.environ, GRL_ROOT=ROOT, GRL_CASE=case)
+    k = 3 if kind == "ipc_shared" else min(n_gpus(), 8)
+    env = dict(os.environ, GRL_ROOT=ROOT, GRL_CASE=case, GRL_COMM=kind, GRLGPU_IPC_TIMEOUT_S="120")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(k), "--master-addr", "127.0.0.1", "--master-port", "29741",
                         str(script)], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
