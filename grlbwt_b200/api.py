@@ -126,6 +126,8 @@ def lib_host():
         L.grlbwt_last_error.restype = C.c_char_p
         L.grlbwt_build_mg.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(BwtResult)]
         L.grlbwt_build_to.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(BwtResult)]
+        L.grlbwt_build_packed.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64),
+                                          C.POINTER(BwtResult)]
         L.grlbwt_last_digests.argtypes = [C.c_void_p, C.c_uint64]
         L.grlbwt_last_digests.restype = C.c_uint64
         L.grlbwt_last_exchange_bytes.restype = C.c_uint64
@@ -372,6 +374,22 @@ def build_bwt_to(text: np.ndarray, out_syms: np.ndarray, out_lens: np.ndarray, d
         raise GrlGpuError(rc, L.grlbwt_last_error().decode())
     info = {k: getattr(res, k) for k in ("n_rounds", "h2d_ms", "par_phase_ms", "ind_phase_ms", "device_ms", "algorithmic_bytes", "induced_on_device")}
     return int(res.n_runs), int(res.sb), int(res.fb), info
+
+
+def build_bwt_packed(text: np.ndarray, out_image: np.ndarray, devices=(0,), n_threads: int = 1, comm: int = 0):
+    """Whole construction with the run-length BWT delivered as the image of the .rl_bwt file ([sb u64][fb u64] + records of sb + fb
+    bytes) in a caller-owned uint8 array; the records are packed on the device. -> (image_bytes, n_runs, sb, fb, info)"""
+    L = lib_host()
+    text = np.ascontiguousarray(text)
+    assert out_image.dtype == np.uint8 and out_image.flags.c_contiguous
+    dv = np.asarray(devices, np.int32)
+    res = BwtResult()
+    nb = C.c_uint64()
+    rc = L.grlbwt_build_packed(_ptr(text), text.size, text.dtype.itemsize, _ptr(dv), dv.size, n_threads, comm, _ptr(out_image), out_image.size, C.byref(nb), C.byref(res))
+    if rc != 0:
+        raise GrlGpuError(rc, L.grlbwt_last_error().decode())
+    info = {k: getattr(res, k) for k in ("n_rounds", "h2d_ms", "par_phase_ms", "ind_phase_ms", "device_ms", "algorithmic_bytes", "induced_on_device")}
+    return int(nb.value), int(res.n_runs), int(res.sb), int(res.fb), info
 
 
 def build_bwt_file(inp: str, out: str, sym_bytes: int = 1, device: int = 0, n_threads: int = 1, verbose: bool = False):

@@ -926,6 +926,14 @@ int grlgpu_create_on_stream(grlgpu_ctx** ctx, int device, uint64_t flags, void* 
     return GRLGPU_OK;
 }
 
+uint64_t grlgpu_trim(void) {
+    DevicePool tmp;
+    try {
+        DevicePool::resolve("cuMemUnmap", tmp.p_unmap); DevicePool::resolve("cuMemRelease", tmp.p_release); DevicePool::resolve("cuMemAddressFree", tmp.p_addrfree);
+    } catch (const Error&) { return 0; }
+    return tmp.trim_spares(-1);
+}
+
 int grlgpu_destroy(grlgpu_ctx* ctx) {
     if (!ctx) return GRLGPU_ERR_ARG;
     cudaSetDevice(ctx->device);
@@ -1596,6 +1604,50 @@ int grlgpu_fetch_bwt(grlgpu_ctx* ctx, uint32_t* syms, uint32_t* lens) {
         GRL_CUDA(cudaMemcpyAsync(syms, ctx->bwt_dev.sym.p, (u64)ctx->bwt_dev.n_runs * 4, cudaMemcpyDeviceToHost, ctx->st));
         GRL_CUDA(cudaMemcpyAsync(lens, ctx->bwt_dev.len.p, (u64)ctx->bwt_dev.n_runs * 4, cudaMemcpyDeviceToHost, ctx->st));
         GRL_CUDA(cudaStreamSynchronize(ctx->st));
+    });
+}
+
+int grlgpu_fetch_bwt_packed(grlgpu_ctx* ctx, int sb, int fb, void* out, uint64_t cap_bytes, uint64_t* n_bytes) {
+    if (!ctx || !out || sb < 1 || sb > 8 || fb < 1 || fb > 8) return GRLGPU_ERR_ARG;
+    if (!ctx->bwt_ready) return GRLGPU_ERR_STATE;
+    const u64 n = ctx->bwt_dev.n_runs, rec = (u64)(sb + fb), need = 16 + n * rec;
+    if (n_bytes) *n_bytes = need;
+    if (cap_bytes < need) return GRLGPU_ERR_ARG;
+    return guarded(ctx, [&] {
+        cudaStream_t st = ctx->st;
+        // [sb u64][fb u64][records]: the image of the .rl_bwt file. The records are packed piece by piece into two device buffers, so a
+        // piece travels to the host while the next one is being packed
+        const u64 hdr[2] = {(u64)sb, (u64)fb};
+        memcpy(out, hdr, 16);
+        if (n == 0) return;
+        if (!ctx->copy_st) {
+            GRL_CUDA(cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking));
+            GRL_CUDA(cudaEventCreateWithFlags(&ctx->copy_ev, cudaEventDisableTiming));
+        }
+        const u64 piece = std::min<u64>(n, (u64)IND_PACK_RUNS * 32768);  // 32 M runs
+        DevBuf<u8> buf0(piece * rec, st), buf1(piece * rec, st);
+        DevBuf<u32> err(1, st);
+        err.zero();
+        cudaEvent_t packed[2], copied[2];
+        for (int k = 0; k < 2; k++) { GRL_CUDA(cudaEventCreateWithFlags(&packed[k], cudaEventDisableTiming)); GRL_CUDA(cudaEventCreateWithFlags(&copied[k], cudaEventDisableTiming)); }
+        int k = 0;
+        bool used[2] = {false, false};
+        for (u64 first = 0; first < n; first += piece, k ^= 1) {
+            const u64 m = std::min(piece, n - first);
+            u8* d = k ? buf1.p : buf0.p;
+            if (used[k]) GRL_CUDA(cudaStreamWaitEvent(st, copied[k], 0));  // the copy that last read this buffer
+            GRL_LAUNCH("ind_pack_records", m * (8 + rec), ind_pack_records_kernel, (unsigned)div_up(m, IND_PACK_RUNS), 256, (size_t)IND_PACK_RUNS * rec, st, ctx->bwt_dev.sym.p,
+                       ctx->bwt_dev.len.p, first, m, sb, fb, d, err.p);
+            GRL_CUDA(cudaEventRecord(packed[k], st));
+            GRL_CUDA(cudaStreamWaitEvent(ctx->copy_st, packed[k], 0));
+            GRL_CUDA(cudaMemcpyAsync((u8*)out + 16 + first * rec, d, m * rec, cudaMemcpyDeviceToHost, ctx->copy_st));
+            GRL_CUDA(cudaEventRecord(copied[k], ctx->copy_st));
+            used[k] = true;
+        }
+        GRL_CUDA(cudaStreamSynchronize(ctx->copy_st));
+        GRL_CUDA(cudaStreamSynchronize(st));
+        for (int q = 0; q < 2; q++) { cudaEventDestroy(packed[q]); cudaEventDestroy(copied[q]); }
+        if (d2h_scalar(err.p, st)) throw Error(GRLGPU_ERR_STATE, "a symbol or a run length of the BWT does not fit the record widths");
     });
 }
 

@@ -171,12 +171,29 @@ static __global__ void __launch_bounds__(256) ind_pieces_from_items_kernel(const
 }
 
 // LSD radix sort of (u32 key, u32 value) pairs on key bits [0, n_bits)
-inline void radix_sort_pairs_u32(u32** keys, u32** vals, u32** keys_alt, u32** vals_alt, u64 n, int n_bits, cudaStream_t st) {
-    if (n <= 1 || n_bits <= 0) return;
-    const u64 tiles = div_up(n, RS_THREADS * 8);
-    DevBuf<u32> hist(256 * tiles, st);
-    DevBuf<u64> goff(256 * tiles, st);
-    for (int shift = 0; shift < n_bits; shift += 8) radix_pass<u32, 8>(keys, vals, keys_alt, vals_alt, n, shift, hist, goff, st);
+
+// the run-length BWT as .rl_bwt records (rl_bwt_io.hpp; the reference's bwt_buff_writer, external/cdt/include/bwt_io.h): sb symbol
+// bytes + fb length bytes per run, little endian. A CTA packs IND_PACK_RUNS runs into shared memory and stores them as 16-byte
+// vectors (IND_PACK_RUNS * rec is a multiple of 16, so every CTA starts on a 16-byte boundary of the record stream).
+constexpr int IND_PACK_RUNS = 1024;
+static __global__ void __launch_bounds__(256) ind_pack_records_kernel(const u32* __restrict__ sym, const u32* __restrict__ len, u64 first, u64 n, int sb, int fb,
+                                                                      unsigned char* __restrict__ out, u32* err) {
+    extern __shared__ __align__(16) unsigned char pk_smem[];
+    const int rec = sb + fb;
+    const u64 r0 = (u64)blockIdx.x * IND_PACK_RUNS;
+    const u32 here = (u32)((n - r0) < (u64)IND_PACK_RUNS ? (n - r0) : (u64)IND_PACK_RUNS);
+    for (u32 k = threadIdx.x; k < here; k += 256) {
+        const u64 s = sym[first + r0 + k], l = len[first + r0 + k];
+        if ((sb < 8 && (s >> (8 * sb))) || (fb < 8 && (l >> (8 * fb)))) atomicExch(err, 1u);
+        unsigned char* q = pk_smem + (size_t)k * rec;
+        for (int b = 0; b < sb; b++) q[b] = (unsigned char)(s >> (8 * b));
+        for (int b = 0; b < fb; b++) q[sb + b] = (unsigned char)(l >> (8 * b));
+    }
+    __syncthreads();
+    const u32 bytes = here * (u32)rec, nvec = bytes >> 4;
+    unsigned char* dst = out + r0 * (u64)rec;
+    for (u32 v = threadIdx.x; v < nvec; v += 256) reinterpret_cast<uint4*>(dst)[v] = reinterpret_cast<const uint4*>(pk_smem)[v];
+    for (u32 b = (nvec << 4) + threadIdx.x; b < bytes; b += 256) dst[b] = pk_smem[b];
 }
 
 inline u32 ind_scan_total(const u32* in, u32* out, u32 n, cudaStream_t st) {  // exclusive scan; out may have n + 1 entries (total stored at out[n])

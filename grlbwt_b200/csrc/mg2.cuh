@@ -85,13 +85,15 @@ __global__ void mg2_bounds_kernel(const KeyT* __restrict__ keys, u64 m, u32 n_va
 // the record of every valid entry, written in destination order (q-th record = valid entry perm[q])
 // YT: the frequency word travels in 32 bits (frequency | full << 31) whenever the round's highest frequency is below 2^30
 template <class SymT, class YT>
-__global__ void __launch_bounds__(256) mg2_build_send_kernel(const u32* __restrict__ perm, u64 nS, const u64* __restrict__ keys, const u32* __restrict__ vals,
+__global__ void __launch_bounds__(256) mg2_build_send_kernel(const u32* __restrict__ pos, u64 nS, const u64* __restrict__ keys, const u32* __restrict__ vals,
                                                              const SymT* __restrict__ D, const u32* __restrict__ rem, const u32* __restrict__ phr_of,
                                                              const u32* __restrict__ ph_off, const u64* __restrict__ ph_freq, u64* __restrict__ o_key,
                                                              SymT* __restrict__ o_left, YT* __restrict__ o_y, u32* __restrict__ o_id, u32* __restrict__ o_rem) {
-    const u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nS) return;
-    const u32 j = perm[q], e = vals[j], i = phr_of[e];
+    // source order: keys, entry ids and everything they index are read front to back; the writes form one ascending stream per
+    // destination (gathering through the partition's permutation instead re-reads every sector once per destination)
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nS) return;
+    const u32 q = pos[j], e = vals[j], i = phr_of[e];
     const bool full = e == ph_off[i];
     o_key[q] = keys[j];
     o_left[q] = full ? (SymT)0 : (SymT)(D[e - 1] + 1);  // left symbol + 1; a whole phrase has none
@@ -99,6 +101,11 @@ __global__ void __launch_bounds__(256) mg2_build_send_kernel(const u32* __restri
     else o_y[q] = (YT)(ph_freq[i] | EI_VALID | (full ? EI_FULL : 0ULL));
     o_id[q] = e;
     o_rem[q] = rem[e];
+}
+// pos[perm[q]] = q: where the partition put every source item
+static __global__ void __launch_bounds__(256) mg2_invert_perm_kernel(const u32* __restrict__ perm, u64 n, u32* __restrict__ pos) {
+    const u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n) pos[perm[q]] = (u32)q;
 }
 // ---- distributed key extension: the active items ask the owners of their entries for the next K codes ----
 // source rank of a received item = segment of the receive buffer it lies in (seg_off: G + 1 ascending offsets)
@@ -210,9 +217,10 @@ __global__ void __launch_bounds__(256) mg2_codes_kernel(const u32* __restrict__ 
     codes[order[i]] = (CodeT)((gi & 1u) ? ((((u64)(gi >> 2) + rank_base) << 2) | (u64)(gi & 2u) | rep) + 1ULL : 0ULL);
 }
 template <class CodeT>
-__global__ void __launch_bounds__(256) mg2_codes_to_entries_kernel(const u32* __restrict__ sent_id, const CodeT* __restrict__ back, u64 nS, u64* __restrict__ ecode) {
-    const u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < nS) ecode[sent_id[q]] = (u64)back[q];
+__global__ void __launch_bounds__(256) mg2_codes_to_entries_kernel(const u32* __restrict__ vals, const u32* __restrict__ pos, const CodeT* __restrict__ back, u64 nS,
+                                                                   u64* __restrict__ ecode) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;   // source order again: ascending entry ids, one ascending read stream per destination
+    if (j < nS) ecode[vals[j]] = (u64)back[pos[j]];
 }
 // metasymbol of every phrase of the partition: rank of the group of its first entry (a whole phrase is always ranked)
 static __global__ void __launch_bounds__(256) mg2_meta_kernel(const u64* __restrict__ ecode, const u32* __restrict__ ph_off, const u64* __restrict__ ph_freq, u64 d,
@@ -232,36 +240,46 @@ template <class SymT>
 __global__ void __launch_bounds__(256) mg2_rules_kernel(const u64* __restrict__ ecode, const SymT* __restrict__ D, const u32* __restrict__ rem,
                                                         const u32* __restrict__ phr_of, const u8* __restrict__ p_fin, const u32* __restrict__ flags,
                                                         const u32* __restrict__ excl, u64 nE, u64 alph3, u64 metasym_dummy, u64* __restrict__ o_u,
-                                                        SymT* __restrict__ o_l, SymT* __restrict__ o_r, u8* __restrict__ o_h) {
+                                                        SymT* __restrict__ o_l, SymT* __restrict__ o_r, u8* __restrict__ o_h, uint4* __restrict__ o_rec,
+                                                        u32* __restrict__ o_key32) {
     const u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nE || !flags[e]) return;
     const u32 k = excl[e];
     const u64 c = ecode[e] - 1;
-    o_u[k] = c >> 2;
-    o_h[k] = (u8)((c >> 1) & 1ULL);
+    SymT l, r;
     u64 pos = e;
     if (rem[pos] == 0) {  // :38-41 one-symbol suffix
-        o_l[k] = (SymT)metasym_dummy;
-        o_r[k] = D[pos];
-        return;
+        l = (SymT)metasym_dummy;
+        r = D[pos];
+    } else {
+        pos++;
+        u64 cc = ecode[pos];
+        bool hocc = cc && ((cc - 1) & 2ULL);
+        while (!hocc && rem[pos] != 0) { pos++; cc = ecode[pos]; hocc = cc && ((cc - 1) & 2ULL); }  // :43-44
+        const SymT l_sym = D[pos - 1];
+        if (hocc) {  // :49-80
+            l = l_sym;
+            r = (SymT)(alph3 + ((cc - 1) >> 2));
+        } else {  // :81-85: pos is the phrase's last symbol, which is_suffix iff the phrase ends a string
+            const SymT r_sym = D[pos];
+            l = (SymT)metasym_dummy;
+            r = p_fin[phr_of[pos]] ? r_sym : l_sym;
+        }
     }
-    pos++;
-    u64 cc = ecode[pos];
-    bool hocc = cc && ((cc - 1) & 2ULL);
-    while (!hocc && rem[pos] != 0) { pos++; cc = ecode[pos]; hocc = cc && ((cc - 1) & 2ULL); }  // :43-44
-    const SymT l_sym = D[pos - 1];
-    if (hocc) {  // :49-80
-        o_l[k] = l_sym;
-        o_r[k] = (SymT)(alph3 + ((cc - 1) >> 2));
-    } else {  // :81-85: pos is the phrase's last symbol, which is_suffix iff the phrase ends a string
-        const SymT r_sym = D[pos];
-        o_l[k] = (SymT)metasym_dummy;
-        o_r[k] = p_fin[phr_of[pos]] ? r_sym : l_sym;
+    if (o_rec) {  // 32-bit symbols and ranks: one 16-byte record per rule, so the gather that follows the sort costs one sector, not four
+        o_rec[k] = make_uint4((u32)(c >> 2), (u32)l, (u32)r, (u32)((c >> 1) & 1ULL));
+        o_key32[k] = (u32)(c >> 2);
+    } else {
+        o_u[k] = c >> 2;
+        o_h[k] = (u8)((c >> 1) & 1ULL);
+        o_l[k] = l;
+        o_r[k] = r;
     }
 }
 // the rules of this rank sorted by their (global) rank: first[g] = number of them below bases[g], g = 0..G (one thread per g):
 // the owner of a rank is the range it falls in, so the sorted list is already grouped by destination
-static __global__ void mg2_rule_bounds_kernel(const u64* __restrict__ sorted_u, u64 n, const u64* __restrict__ bases, int G, u64* __restrict__ first) {
+template <class KeyT>
+__global__ void mg2_rule_bounds_kernel(const KeyT* __restrict__ sorted_u, u64 n, const u64* __restrict__ bases, int G, u64* __restrict__ first) {
     const int g = threadIdx.x;
     if (g > G) return;
     if (g == G) { first[g] = n; return; }
@@ -269,7 +287,7 @@ static __global__ void mg2_rule_bounds_kernel(const u64* __restrict__ sorted_u, 
     u64 lo = 0, hi = n;
     while (lo < hi) {
         const u64 mid = (lo + hi) >> 1;
-        if (sorted_u[mid] < b) lo = mid + 1; else hi = mid;
+        if ((u64)sorted_u[mid] < b) lo = mid + 1; else hi = mid;
     }
     first[g] = lo;
 }
@@ -282,6 +300,13 @@ __global__ void __launch_bounds__(256) mg2_rule_send_kernel(const u32* __restric
     if (q >= n) return;
     const u32 k = perm[q];
     su[q] = (UT)u[k]; sl[q] = l[k]; sr[q] = r[k]; sh[q] = h[k];
+}
+static __global__ void __launch_bounds__(256) mg2_rule_send_rec_kernel(const u32* __restrict__ perm, u64 n, const uint4* __restrict__ rec, u32* __restrict__ su,
+                                                                       u32* __restrict__ sl, u32* __restrict__ sr, u8* __restrict__ sh) {
+    const u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const ulonglong2 v = ld_gather16(reinterpret_cast<const ulonglong2*>(rec) + perm[q]);
+    su[q] = (u32)v.x; sl[q] = (u32)(v.x >> 32); sr[q] = (u32)v.y; sh[q] = (u8)(v.y >> 32);
 }
 template <class SymT, class UT>
 __global__ void __launch_bounds__(256) mg2_rule_scatter_kernel(const UT* __restrict__ u, const SymT* __restrict__ l, const SymT* __restrict__ r,
@@ -425,7 +450,7 @@ void mg2_rank(grlgpu_ctx* c, Comm& cm, Mg2Part& P, Mg2Slices& S) {
     clk.lap("S splitters");
     // ---- R: records by key range -> E2 ----
     std::vector<u64> cnt_send, cnt_recv;
-    DevBuf<u32> sent_id;   // entry id of the q-th record this rank sent (the codes come back in the same order)
+    DevBuf<u32> pos;       // slot of the j-th local suffix entry in the send buffers (the codes come back in that order)
     const bool narrow_y = P.max_freq_g < (1ull << 30);  // the records' frequency word fits 32 bits (frequency | full << 31)
     const u64 y_bytes = narrow_y ? 4 : 8;
     DevBuf<u64> r_key;
@@ -439,24 +464,25 @@ void mg2_rank(grlgpu_ctx* c, Comm& cm, Mg2Part& P, Mg2Slices& S) {
         GRL_LAUNCH("mg_key_dest", nS * 16, mg2_key_dest_kernel, grid_for(nS, 256), 256, 0, st, PR.keys.p, nS, d_split.p, (int)splitters.size(), dest.p, idx.p);
         cnt_send = mg2_partition(dest, idx, nS, G, perm, st);
         dest.release(); idx.release();
+        pos.alloc(nS, st);
+        if (nS) GRL_LAUNCH("mg_invert_perm", nS * 8, mg2_invert_perm_kernel, grid_for(nS, 256), 256, 0, st, perm.p, nS, pos.p);
+        perm.release();
         DevBuf<u64> s_key(nS, st);
         DevBuf<u8> s_left(nS * sizeof(SymT), st), s_y(nS * y_bytes, st);
-        DevBuf<u32> s_rem(nS, st);
-        sent_id.alloc(nS, st);
+        DevBuf<u32> s_rem(nS, st), s_id(nS, st);
         if (narrow_y)
-            GRL_LAUNCH("mg_build_send", nS * (44 + 2 * sizeof(SymT)), (mg2_build_send_kernel<SymT, u32>), grid_for(nS, 256), 256, 0, st, perm.p, nS, PR.keys.p, PR.vals.p, D, PR.rem.p,
-                       PR.phr_of.p, PR.ph_off.p, PR.ph_freq.p, s_key.p, (SymT*)s_left.p, (u32*)s_y.p, sent_id.p, s_rem.p);
+            GRL_LAUNCH("mg_build_send", nS * (44 + 2 * sizeof(SymT)), (mg2_build_send_kernel<SymT, u32>), grid_for(nS, 256), 256, 0, st, pos.p, nS, PR.keys.p, PR.vals.p, D, PR.rem.p,
+                       PR.phr_of.p, PR.ph_off.p, PR.ph_freq.p, s_key.p, (SymT*)s_left.p, (u32*)s_y.p, s_id.p, s_rem.p);
         else
-            GRL_LAUNCH("mg_build_send", nS * (48 + 2 * sizeof(SymT)), (mg2_build_send_kernel<SymT, u64>), grid_for(nS, 256), 256, 0, st, perm.p, nS, PR.keys.p, PR.vals.p, D, PR.rem.p,
-                       PR.phr_of.p, PR.ph_off.p, PR.ph_freq.p, s_key.p, (SymT*)s_left.p, (u64*)s_y.p, sent_id.p, s_rem.p);
-        perm.release();
-        PR.keys.release(); PR.vals.release();
+            GRL_LAUNCH("mg_build_send", nS * (48 + 2 * sizeof(SymT)), (mg2_build_send_kernel<SymT, u64>), grid_for(nS, 256), 256, 0, st, pos.p, nS, PR.keys.p, PR.vals.p, D, PR.rem.p,
+                       PR.phr_of.p, PR.ph_off.p, PR.ph_freq.p, s_key.p, (SymT*)s_left.p, (u64*)s_y.p, s_id.p, s_rem.p);
+        PR.keys.release();  // PR.vals (entry id of every local suffix entry) stays until the codes are back
         clk.lap("R build records");
         cnt_recv = mg2_exchange_counts(cm, cnt_send, st);
         nL = mg2_sum(cnt_recv);
         if (nL >= 0xfffffff0ull) throw Error(GRLGPU_ERR_LIMIT, "more than 2^32 suffix entries in one rank's key range");
         r_key.alloc(nL, st); r_y_raw.alloc(nL * y_bytes, st); r_left_raw.alloc(nL * sizeof(SymT), st); r_id.alloc(nL, st); r_rem.alloc(nL, st);
-        mg2_a2a_soa(cm, {{s_key.p, r_key.p, 8}, {s_left.p, r_left_raw.p, sizeof(SymT)}, {s_y.p, r_y_raw.p, y_bytes}, {sent_id.p, r_id.p, 4}, {s_rem.p, r_rem.p, 4}}, cnt_send, cnt_recv,
+        mg2_a2a_soa(cm, {{s_key.p, r_key.p, 8}, {s_left.p, r_left_raw.p, sizeof(SymT)}, {s_y.p, r_y_raw.p, y_bytes}, {s_id.p, r_id.p, 4}, {s_rem.p, r_rem.p, 4}}, cnt_send, cnt_recv,
                     st);
         GRL_CUDA(cudaStreamSynchronize(st));  // the send buffers go back to the pool at the end of this block
     }
@@ -648,12 +674,12 @@ void mg2_rank(grlgpu_ctx* c, Comm& cm, Mg2Part& P, Mg2Slices& S) {
         mg2_a2a_soa(cm, {{codes.p, back.p, cb}}, cnt_recv, cnt_send, st);
         ecode.zero();
         if (nS) {
-            if (narrow_code) GRL_LAUNCH("mg_codes_to_entries", nS * 16, (mg2_codes_to_entries_kernel<u32>), grid_for(nS, 256), 256, 0, st, sent_id.p, (const u32*)back.p, nS, ecode.p);
-            else GRL_LAUNCH("mg_codes_to_entries", nS * 20, (mg2_codes_to_entries_kernel<u64>), grid_for(nS, 256), 256, 0, st, sent_id.p, (const u64*)back.p, nS, ecode.p);
+            if (narrow_code) GRL_LAUNCH("mg_codes_to_entries", nS * 20, (mg2_codes_to_entries_kernel<u32>), grid_for(nS, 256), 256, 0, st, PR.vals.p, pos.p, (const u32*)back.p, nS, ecode.p);
+            else GRL_LAUNCH("mg_codes_to_entries", nS * 24, (mg2_codes_to_entries_kernel<u64>), grid_for(nS, 256), 256, 0, st, PR.vals.p, pos.p, (const u64*)back.p, nS, ecode.p);
         }
         GRL_CUDA(cudaStreamSynchronize(st));
     }
-    order.release(); head_bits.release(); head_pref.release(); sent_id.release();
+    order.release(); head_bits.release(); head_pref.release(); pos.release(); PR.vals.release();
     gcnt.release(); rflag.release(); vflag.release(); rrank.release(); vidx.release(); gacc.release(); gmin.release(); gmax.release(); psym.release();
     clk.lap("E3 codes back");
     // ---- U: metasymbols of my phrases, rules of the groups whose representative I own -> E4 by rank range ----
@@ -671,10 +697,15 @@ void mg2_rank(grlgpu_ctx* c, Comm& cm, Mg2Part& P, Mg2Slices& S) {
     const u64 alph3 = A + 3, metasym_dummy = alph3 + S.tot + 1;  // exact_par_phase.cpp:19-20
     std::vector<u64> rs_cnt, rr_cnt;
     {
-        DevBuf<u64> ru(nR, st);
-        DevBuf<u8> rl(nR * sizeof(SymT), st), rr(nR * sizeof(SymT), st), rh(nR, st);
+        const bool narrow_u = S.tot < (1ull << 32);
+        const u64 ub = narrow_u ? 4 : 8;
+        const bool zip = narrow_u && sizeof(SymT) == 4;  // 32-bit symbols and ranks: the rules travel through the sort as 16-byte records
+        DevBuf<u64> ru(zip ? 0 : nR, st);
+        DevBuf<u8> rl(zip ? 0 : nR * sizeof(SymT), st), rr(zip ? 0 : nR * sizeof(SymT), st), rh(zip ? 0 : nR, st);
+        DevBuf<uint4> rec(zip ? nR : 0, st);
+        DevBuf<u32> k32(zip ? nR : 0, st);
         if (nE) GRL_LAUNCH("rules", nE * 12 + nR * 64, (mg2_rules_kernel<SymT>), grid_for(nE, 256), 256, 0, st, ecode.p, D, PR.rem.p, PR.phr_of.p, P.p_fin.p, rfl.p, rex.p, nE, alph3,
-                           metasym_dummy, ru.p, (SymT*)rl.p, (SymT*)rr.p, rh.p);
+                           metasym_dummy, ru.p, (SymT*)rl.p, (SymT*)rr.p, rh.p, zip ? rec.p : (uint4*)nullptr, k32.p);
         rfl.release(); rex.release();
         DevBuf<u64> d_bases((u64)G + 1, st);
         GRL_CUDA(cudaMemcpyAsync(d_bases.p, bases.data(), ((size_t)G + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -683,27 +714,37 @@ void mg2_rank(grlgpu_ctx* c, Comm& cm, Mg2Part& P, Mg2Slices& S) {
         DevBuf<u32> perm;
         rs_cnt.assign((size_t)G, 0);
         {
-            DevBuf<u64> sk(nR, st), sk_alt(nR, st), first((u64)G + 1, st);
+            DevBuf<u64> first((u64)G + 1, st);
             DevBuf<u32> sv(nR, st), sv_alt(nR, st);
-            if (nR) {
-                GRL_CUDA(cudaMemcpyAsync(sk.p, ru.p, nR * 8, cudaMemcpyDeviceToDevice, st));
-                GRL_LAUNCH("mg_iota", nR * 4, mg2_iota_kernel, grid_for(nR, 256), 256, 0, st, sv.p, nR);
-            }
-            u64 *kp = sk.p, *ka = sk_alt.p;
+            if (nR) GRL_LAUNCH("mg_iota", nR * 4, mg2_iota_kernel, grid_for(nR, 256), 256, 0, st, sv.p, nR);
             u32 *vp = sv.p, *va = sv_alt.p;
-            radix_sort_pairs(&kp, &vp, &ka, &va, nR, std::max(1, bit_width64(S.tot)), st);
-            GRL_LAUNCH("mg_rule_bounds", 0, mg2_rule_bounds_kernel, 1, 32, 0, st, kp, nR, d_bases.p, G, first.p);
+            const int rank_bits = std::max(1, bit_width64(S.tot));
+            if (zip) {
+                DevBuf<u32> k32_alt(nR, st);
+                u32 *kp = k32.p, *ka = k32_alt.p;
+                radix_sort_pairs_u32(&kp, &vp, &ka, &va, nR, rank_bits, st);
+                GRL_LAUNCH("mg_rule_bounds", 0, (mg2_rule_bounds_kernel<u32>), 1, 32, 0, st, kp, nR, d_bases.p, G, first.p);
+                GRL_CUDA(cudaStreamSynchronize(st));  // k32_alt goes back to the pool
+            } else {
+                DevBuf<u64> sk(nR, st), sk_alt(nR, st);
+                if (nR) GRL_CUDA(cudaMemcpyAsync(sk.p, ru.p, nR * 8, cudaMemcpyDeviceToDevice, st));
+                u64 *kp = sk.p, *ka = sk_alt.p;
+                radix_sort_pairs(&kp, &vp, &ka, &va, nR, rank_bits, st);
+                GRL_LAUNCH("mg_rule_bounds", 0, (mg2_rule_bounds_kernel<u64>), 1, 32, 0, st, kp, nR, d_bases.p, G, first.p);
+                GRL_CUDA(cudaStreamSynchronize(st));
+            }
             std::vector<u64> hf((size_t)G + 1);
             d2h_mapped(hf.data(), first.p, ((size_t)G + 1) * 8, st);
             for (int g = 0; g < G; g++) rs_cnt[(size_t)g] = hf[(size_t)g + 1] - hf[(size_t)g];
             if (vp != sv.p) std::swap(sv, sv_alt);
             perm = std::move(sv);
         }
-        const bool narrow_u = S.tot < (1ull << 32);
-        const u64 ub = narrow_u ? 4 : 8;
+        k32.release();
         DevBuf<u8> su(nR * ub, st), sl(nR * sizeof(SymT), st), sr(nR * sizeof(SymT), st), sh(nR, st);
         if (nR) {
-            if (narrow_u)
+            if (zip)
+                GRL_LAUNCH("mg_rule_send", nR * (4 + 32 + 13), mg2_rule_send_rec_kernel, grid_for(nR, 256), 256, 0, st, perm.p, nR, rec.p, (u32*)su.p, (u32*)sl.p, (u32*)sr.p, sh.p);
+            else if (narrow_u)
                 GRL_LAUNCH("mg_rule_send", nR * 2 * (9 + 2 * sizeof(SymT)), (mg2_rule_send_kernel<SymT, u32>), grid_for(nR, 256), 256, 0, st, perm.p, nR, ru.p, (const SymT*)rl.p,
                            (const SymT*)rr.p, rh.p, (u32*)su.p, (SymT*)sl.p, (SymT*)sr.p, sh.p);
             else

@@ -677,6 +677,14 @@ inline void radix_partition_u32(u32** keys, u32** vals, u32** keys_alt, u32** va
     DevBuf<u64> goff(256 * tiles, st);
     radix_pass<u32, 8>(keys, vals, keys_alt, vals_alt, n, shift, hist, goff, st);
 }
+// LSD sort of (u32 key, u32 value) pairs on the low n_bits of the key
+inline void radix_sort_pairs_u32(u32** keys, u32** vals, u32** keys_alt, u32** vals_alt, u64 n, int n_bits, cudaStream_t st) {
+    if (n <= 1 || n_bits <= 0) return;
+    const u64 tiles = div_up(n, RS_THREADS * 8);
+    DevBuf<u32> hist(256 * tiles, st);
+    DevBuf<u64> goff(256 * tiles, st);
+    for (int shift = 0; shift < n_bits; shift += 8) radix_pass<u32, 8>(keys, vals, keys_alt, vals_alt, n, shift, hist, goff, st);
+}
 inline int rs_items_setting() {
     static int v = 0;
     if (!v) { const char* e = getenv("GRL_RS_ITEMS"); v = e ? atoi(e) : 8; if (v != 4 && v != 8 && v != 12 && v != 16) v = 8; }  // 8 items/thread: 59 registers, 4 CTAs/SM (measured best on B200)

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <chrono>
 #include <map>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -79,12 +80,60 @@ struct DevicePool {
             throw Error(-3, std::string("driver entry point unavailable: ") + name);
         f = (F)q;
     }
+    // Mapped memory of destroyed contexts, kept per device for the next context of this process (mapping 80 GB costs 0.3-0.9 s, more
+    // than a whole parse phase): a context that is created later adopts it instead of mapping afresh. GRLGPU_POOL_CACHE=0 turns it
+    // off; grlgpu_trim() hands everything back; an allocation that would otherwise fail releases the device's cached mappings first.
+    struct Spare {
+        int device; CUdeviceptr base; u64 va_size, mapped, chunk;
+        std::vector<CUmemGenericAllocationHandle> handles;
+        std::vector<int> peers;
+    };
+    struct SpareCache {
+        std::mutex m;
+        std::vector<Spare> spares;
+    };
+    static SpareCache& cache() { static SpareCache* c = new SpareCache(); return *c; }  // leaked on purpose: no driver calls during static destruction
+    static bool cache_enabled() { static const bool v = [] { const char* e = getenv("GRLGPU_POOL_CACHE"); return !e || atoi(e) != 0; }(); return v; }
+    bool adopt_spare() {
+        SpareCache& c = cache();
+        std::lock_guard<std::mutex> lk(c.m);
+        for (size_t i = 0; i < c.spares.size(); i++) {
+            if (c.spares[i].device != device) continue;
+            Spare sp = std::move(c.spares[i]);
+            c.spares.erase(c.spares.begin() + (long)i);
+            base = sp.base; va_size = sp.va_size; mapped = sp.mapped; chunk = sp.chunk;
+            handles = std::move(sp.handles); peers = std::move(sp.peers);
+            free_ranges.clear(); live.clear();
+            if (mapped) free_ranges[0] = mapped;
+            in_use = 0; peak = 0;
+            return true;
+        }
+        return false;
+    }
+    void release_spare(Spare& sp) {
+        for (size_t i = 0; i < sp.handles.size(); i++) { p_unmap(sp.base + (u64)i * sp.chunk, sp.chunk); p_release(sp.handles[i]); }
+        p_addrfree(sp.base, sp.va_size);
+    }
+    // hand the cached mappings of `dev` (or of every device: dev < 0) back to the driver; returns the bytes released
+    u64 trim_spares(int dev) {
+        SpareCache& c = cache();
+        std::lock_guard<std::mutex> lk(c.m);
+        u64 freed = 0;
+        for (size_t i = 0; i < c.spares.size();) {
+            if (dev >= 0 && c.spares[i].device != dev) { i++; continue; }
+            freed += c.spares[i].mapped;
+            release_spare(c.spares[i]);
+            c.spares.erase(c.spares.begin() + (long)i);
+        }
+        return freed;
+    }
     void init(int dev) {
         if (base) return;
         device = dev;
         resolve("cuMemAddressReserve", p_reserve); resolve("cuMemCreate", p_create); resolve("cuMemMap", p_map);
         resolve("cuMemSetAccess", p_access); resolve("cuMemUnmap", p_unmap); resolve("cuMemRelease", p_release);
         resolve("cuMemAddressFree", p_addrfree); resolve("cuMemGetAllocationGranularity", p_gran);
+        if (cache_enabled() && adopt_spare()) return;
         CUmemAllocationProp prop = {};
         prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
         prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
@@ -119,7 +168,9 @@ struct DevicePool {
         } gclk{grow_ms, t_grow};
         for (u64 done = 0; done < add; done += chunk) {
             CUmemGenericAllocationHandle h;
-            if (p_create(&h, chunk, &prop, 0) != CUDA_SUCCESS)
+            CUresult cr = p_create(&h, chunk, &prop, 0);
+            if (cr != CUDA_SUCCESS && trim_spares(device)) cr = p_create(&h, chunk, &prop, 0);  // memory parked by earlier contexts of this process
+            if (cr != CUDA_SUCCESS)
                 throw Error(-4, "out of device memory: request of " + std::to_string(need_bytes) + " bytes with " + std::to_string(mapped) + " mapped");
             if (p_map(base + mapped, chunk, 0, h, 0) != CUDA_SUCCESS || p_access(base + mapped, chunk, acc.data(), acc.size()) != CUDA_SUCCESS) {
                 p_release(h);
@@ -196,7 +247,21 @@ struct DevicePool {
         handles.clear(); free_ranges.clear(); live.clear();
         base = 0; mapped = 0; in_use = 0;
     }
-    ~DevicePool() { release_all(); }
+    ~DevicePool() {
+        if (base && mapped && live.empty() && cache_enabled()) {  // park the mapping for the next context on this device
+            SpareCache& c = cache();
+            std::lock_guard<std::mutex> lk(c.m);
+            size_t same = 0;
+            for (const Spare& sp : c.spares) same += sp.device == device;
+            if (same < 8) {
+                if (getenv("GRLGPU_TRACE")) fprintf(stderr, "[grlgpu] device %d pool: %.1f GB kept mapped for the next context (%.1f ms spent mapping)\n", device, mapped / 1e9, grow_ms);
+                c.spares.push_back(Spare{device, base, va_size, mapped, chunk, std::move(handles), std::move(peers)});
+                base = 0; mapped = 0; handles.clear(); free_ranges.clear();
+                return;
+            }
+        }
+        release_all();
+    }
 };
 inline thread_local DevicePool* g_pool = nullptr;  // set by the C ABI guard for the calling context
 

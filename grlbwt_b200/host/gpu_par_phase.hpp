@@ -67,6 +67,7 @@ struct ParseResult {
     bool induced_on_device = false;
     double dev_ind_ms = 0, dev_ind_compute_ms = 0;
     RunArr bwt_dev;
+    uint64_t packed_bytes = 0;           // size of the .rl_bwt image written to OutputBuffers::packed
     bool bwt_in_caller_buffers = false;  // the runs were written to the caller's OutputBuffers (bwt_dev holds only the count)
 };
 
@@ -76,6 +77,9 @@ struct OutputBuffers {
     uint32_t* sym = nullptr;
     uint32_t* len = nullptr;
     uint64_t cap = 0;  // runs each array can hold
+    // alternatively: the image of the .rl_bwt file ([sb][fb] + records of sb + fb bytes), packed on the device
+    unsigned char* packed = nullptr;
+    uint64_t packed_cap = 0;  // bytes
 };
 
 // the input of the parse phase: a buffer in host memory or a byte range of a file
@@ -345,6 +349,13 @@ inline void widen_levels(ParseResult& res) {
     res.wide = true;
 }
 
+// header widths of the level-0 BWT (exact_ind_phase.cpp:274-276 with the level-0 dictionary: alphabet = max_sym+1+3,
+// prev_alphabet = 0, max_sym_freq from collection_stats)
+inline void header_widths(const grlgpu_stats_t& stats, uint64_t& sb, uint64_t& fb) {
+    sb = int_ceil((uint64_t)sym_width(stats.max_sym + 1 + 3), 8);
+    fb = int_ceil((uint64_t)sym_width(stats.max_sym_freq), 8);
+}
+
 // the levels kept on the device -> level-0 BWT in res.bwt_dev; false (with the kept levels fetched into res.levels32) when the
 // device cannot do it (size limits, memory): the caller then induces on the host
 inline bool induce_on_device(const CtxHandle& ctx, ParseResult& res, const void* final_parse, uint64_t n_strings, int cell_bytes, bool verbose,
@@ -356,7 +367,15 @@ inline bool induce_on_device(const CtxHandle& ctx, ParseResult& res, const void*
         const double compute_ms = ms_since(t0);
         res.bwt_dev.n = n_runs;
         res.dev_ind_compute_ms = compute_ms;
-        if (ob && ob->sym && ob->len && ob->cap >= n_runs) {  // straight into the caller's (pinned) buffers
+        if (ob && ob->packed) {  // .rl_bwt records packed on the device, straight into the caller's (pinned) buffer
+            uint64_t sb = 0, fb = 0, nb = 0;
+            header_widths(res.stats, sb, fb);
+            const int st = grlgpu_fetch_bwt_packed(ctx.p, (int)sb, (int)fb, ob->packed, ob->packed_cap, &nb);
+            if (st == GRLGPU_ERR_ARG && nb > ob->packed_cap) throw GpuError(GRLGPU_ERR_LIMIT, "the output buffer is too small: the .rl_bwt image has " + std::to_string(nb) + " bytes");
+            ctx.check("grlgpu_fetch_bwt_packed", st);
+            res.packed_bytes = nb;
+            res.bwt_in_caller_buffers = true;
+        } else if (ob && ob->sym && ob->len && ob->cap >= n_runs) {  // straight into the caller's (pinned) buffers
             ctx.check("grlgpu_fetch_bwt", grlgpu_fetch_bwt(ctx.p, ob->sym, ob->len));
             res.bwt_in_caller_buffers = true;
         } else {   // fresh pageable arrays: several copy threads, each staging (and first-touching) its own pieces

@@ -88,10 +88,7 @@ inline BwtResult build_bwt(const TextSource& src, int sym_bytes, const std::vect
         }
         out.ind_ms = ms_since(t0);
     }
-    // header widths of the level-0 BWT (exact_ind_phase.cpp:274-276 with the level-0 dictionary: alphabet =
-    // max_sym+1+3, prev_alphabet = 0, max_sym_freq from collection_stats)
-    out.sb = int_ceil((uint64_t)sym_width(out.parse.stats.max_sym + 1 + 3), 8);
-    out.fb = int_ceil((uint64_t)sym_width(out.parse.stats.max_sym_freq), 8);
+    header_widths(out.parse.stats, out.sb, out.fb);
     return out;
 }
 inline BwtResult build_bwt(const void* text, uint64_t n_syms, int sym_bytes, int device, size_t n_threads, bool verbose) {

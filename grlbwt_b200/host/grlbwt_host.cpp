@@ -120,6 +120,47 @@ int grlbwt_build_to(const void* text, uint64_t n_syms, int sym_bytes, const int*
     }
 }
 
+// whole construction with the level-0 BWT delivered as the image of the .rl_bwt file (see include/grlbwt.h)
+int grlbwt_build_packed(const void* text, uint64_t n_syms, int sym_bytes, const int* devices, int n_ranks, int n_threads, int comm_kind, void* out_image,
+                        uint64_t cap_bytes, uint64_t* image_bytes, grlbwt_result_t* out) {
+    if (!text || !out || n_syms == 0 || !devices || n_ranks < 1 || n_ranks > 31 || !out_image || cap_bytes < 16) return GRLGPU_ERR_ARG;
+    if (!(sym_bytes == 1 || sym_bytes == 2 || sym_bytes == 4 || sym_bytes == 8)) return GRLGPU_ERR_ARG;
+    memset(out, 0, sizeof(*out));
+    if (image_bytes) *image_bytes = 0;
+    try {
+        grlbwt::TextSource src;
+        src.mem = (const unsigned char*)text;
+        src.bytes = n_syms * (uint64_t)sym_bytes;
+        grlbwt::OutputBuffers ob;
+        ob.packed = (unsigned char*)out_image; ob.packed_cap = cap_bytes;
+        grlbwt::BwtResult r = grlbwt::build_bwt(src, sym_bytes, std::vector<int>(devices, devices + n_ranks), comm_kind, (size_t)(n_threads > 0 ? n_threads : 1), false, &ob);
+        const size_t nr = r.n_runs();
+        out->n_runs = nr; out->sb = r.sb; out->fb = r.fb;
+        out->n_rounds = r.parse.rounds.size();
+        out->h2d_ms = r.parse.h2d_ms; out->par_phase_ms = r.parse.par_ms; out->ind_phase_ms = r.ind_ms;
+        out->induced_on_device = r.parse.induced_on_device ? 1 : 0;
+        for (const auto& rd : r.parse.rounds) { out->device_ms += rd.device_ms; out->algorithmic_bytes += rd.algorithmic_bytes; }
+        g_last_digests = r.parse.digests;
+        g_last_exchange_bytes = r.parse.exchange_bytes;
+        g_last_comm = r.parse.comm_kind;
+        const uint64_t need = 16 + (uint64_t)nr * (r.sb + r.fb);
+        if (image_bytes) *image_bytes = need;
+        if (!r.parse.bwt_in_caller_buffers) {  // host induction: pack here
+            if (need > cap_bytes) { g_last_error = "the output buffer is too small: the .rl_bwt image has " + std::to_string(need) + " bytes"; return GRLGPU_ERR_LIMIT; }
+            if (r.narrow && !r.runs32.len32.empty()) grlbwt::pack_rl_bwt((unsigned char*)out_image, r.runs32.sym.data(), r.runs32.len32.data(), nr, r.sb, r.fb);
+            else if (r.narrow) grlbwt::pack_rl_bwt((unsigned char*)out_image, r.runs32.sym.data(), r.runs32.len.data(), nr, r.sb, r.fb);
+            else grlbwt::pack_rl_bwt((unsigned char*)out_image, r.runs.sym.data(), r.runs.len.data(), nr, r.sb, r.fb);
+        }
+        return GRLGPU_OK;
+    } catch (const grlbwt::GpuError& e) {
+        g_last_error = e.what();
+        return e.status;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return -100;
+    }
+}
+
 uint64_t grlbwt_last_digests(uint64_t* out, uint64_t cap_rounds) {
     const uint64_t n = g_last_digests.size();
     for (uint64_t i = 0; i < n && i < cap_rounds && out; i++) {

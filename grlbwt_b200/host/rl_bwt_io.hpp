@@ -28,6 +28,19 @@ struct RunList {
 
 static_assert(__BYTE_ORDER__ == __ORDER_LITTLE_ENDIAN__, "the .rl_bwt records are packed with little-endian stores");
 
+// the image of the file in memory: 16 + n_runs * (sb + fb) bytes at `dst` (same packing as write_rl_bwt below)
+template <class SymT, class LenT>
+inline void pack_rl_bwt(unsigned char* dst, const SymT* sym, const LenT* len, uint64_t n_runs, uint64_t sb, uint64_t fb) {
+    const uint64_t hdr[2] = {sb, fb};
+    memcpy(dst, hdr, 16);
+    unsigned char* p = dst + 16;
+    for (uint64_t i = 0; i < n_runs; i++, p += sb + fb) {
+        const uint64_t s64 = (uint64_t)sym[i], l64 = (uint64_t)len[i];
+        memcpy(p, &s64, sb);
+        memcpy(p + sb, &l64, fb);
+    }
+}
+
 template <class SymT, class LenT>
 inline void write_rl_bwt(const std::string& path, const SymT* sym, const LenT* len, uint64_t n_runs, uint64_t sb, uint64_t fb) {
     FILE* f = fopen(path.c_str(), "wb");

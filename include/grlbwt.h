@@ -41,6 +41,12 @@ int grlbwt_build_mg(const void* text, uint64_t n_syms, int sym_bytes, const int*
  * has more than cap_runs runs or does not fit 32 bits. */
 int grlbwt_build_to(const void* text, uint64_t n_syms, int sym_bytes, const int* devices, int n_ranks, int n_threads, int comm_kind, uint32_t* out_syms,
                     uint32_t* out_lens, uint64_t cap_runs, grlbwt_result_t* out);
+/* the same construction with the level-0 BWT delivered as the IMAGE OF THE .rl_bwt FILE the reference writes (main.cpp:146-152):
+ * [sb u64][fb u64] then n_runs records of sb symbol bytes + fb length bytes. With the induction on the device the records are packed
+ * there, so sb + fb bytes per run cross PCIe instead of 8; sha256(image) == sha256 of the reference's output file. *image_bytes =
+ * 16 + n_runs * (sb + fb); GRLGPU_ERR_LIMIT when cap_bytes is smaller. */
+int grlbwt_build_packed(const void* text, uint64_t n_syms, int sym_bytes, const int* devices, int n_ranks, int n_threads, int comm_kind, void* out_image,
+                        uint64_t cap_bytes, uint64_t* image_bytes, grlbwt_result_t* out);
 /* per-round digests of the calling thread's last build (9 values per round: tot_phrases, pre-BWT runs, parse length, distinct
  * phrases, dictionary symbols, and the four sums of grlgpu_level_checksum added over the ranks); returns the number of rounds */
 uint64_t grlbwt_last_digests(uint64_t* out, uint64_t cap_rounds);

@@ -155,6 +155,10 @@ int grlgpu_fetch_kept_level(grlgpu_ctx* ctx, int level, uint64_t* alphabet, uint
 int grlgpu_drop_kept(grlgpu_ctx* ctx);
 int grlgpu_induce(grlgpu_ctx* ctx, const void* final_parse, uint64_t n_strings, int cell_bytes, uint64_t n_syms_total, uint64_t* n_runs);
 int grlgpu_fetch_bwt(grlgpu_ctx* ctx, uint32_t* syms, uint32_t* lens);
+/* the level-0 BWT as the image of the reference's .rl_bwt file (main.cpp:146-152 -> bwt_buff_writer): [sb u64][fb u64] then n_runs
+ * records of sb symbol bytes + fb length bytes, little endian, packed on the device (16 + n_runs * (sb + fb) bytes travel instead of
+ * 8 bytes per run). *n_bytes = size of the image; GRLGPU_ERR_ARG if cap_bytes is smaller (nothing is copied). */
+int grlgpu_fetch_bwt_packed(grlgpu_ctx* ctx, int sb, int fb, void* out, uint64_t cap_bytes, uint64_t* n_bytes);
 /* the same arrays as DEVICE addresses (valid until grlgpu_drop_kept / the next grlgpu_induce), for parallel grlgpu_copy_to_host */
 int grlgpu_bwt_ptrs(grlgpu_ctx* ctx, const uint32_t** d_syms, const uint32_t** d_lens, uint64_t* n_runs);
 
@@ -173,6 +177,11 @@ int grlgpu_fetch_str_ptrs(grlgpu_ctx* ctx, uint64_t* dst);
 /* dictionary of the last round in insertion-independent form, for tests: phrases listed in the A.2
  * order; syms: dict_syms u64 values, lens/freqs/metas: n_phrases entries (NULL to skip) */
 int grlgpu_fetch_dictionary(grlgpu_ctx* ctx, uint64_t* syms, uint64_t* lens, uint64_t* freqs, uint64_t* metas);
+
+/* Device memory that destroyed contexts left mapped for the next context of this process (mapping tens of GB costs more than a parse
+ * phase; GRLGPU_POOL_CACHE=0 disables the cache) goes back to the driver; returns the bytes released. An allocation that would
+ * otherwise fail does this by itself. */
+uint64_t grlgpu_trim(void);
 
 const char* grlgpu_strerror(int status);
 const char* grlgpu_last_error(const grlgpu_ctx* ctx);   /* ctx == NULL: the calling thread's last error of a call without a context */

@@ -215,6 +215,27 @@ def test_build_into_caller_buffers(golden, all_cases):
         G.build_bwt_to(all_cases["reads_100k"], np.zeros(10, np.uint32), np.zeros(10, np.uint32))
 
 
+def test_build_packed_image(golden, all_cases):
+    """grlbwt_build_packed: the image of the .rl_bwt file in a caller-owned buffer (records packed on the device; host induction:
+    packed by the host), bit-identical to the reference's output file; several ranks give the same image"""
+    for name in ("test_byte_alphabet", "test_2bytes_alphabet", "reads_100k", "u16_2M", "mutated_200x5k", "with_empty", "only_empty", "u64_rand", "homopolymer"):
+        arr, g = all_cases[name], golden[name]
+        img = np.zeros(16 + arr.size * 16, np.uint8)
+        for host in (False, True):
+            if host:
+                os.environ["GRLBWT_HOST_INDUCTION"] = "1"
+            try:
+                nb, n_runs, sb, fb, info = G.build_bwt_packed(arr, img, n_threads=4)
+            finally:
+                os.environ.pop("GRLBWT_HOST_INDUCTION", None)
+            assert nb == 16 + n_runs * (sb + fb) and not (host and info["induced_on_device"]), (name, host, info)
+            assert hashlib.sha256(img[:nb].tobytes()).hexdigest() == g["rl_bwt_sha256"], (name, host)
+        nb2, _, _, _, _ = G.build_bwt_packed(arr, img, devices=[0, 0, 0], n_threads=4)
+        assert hashlib.sha256(img[:nb2].tobytes()).hexdigest() == g["rl_bwt_sha256"], (name, "3 ranks")
+    with pytest.raises(G.GrlGpuError):
+        G.build_bwt_packed(all_cases["reads_100k"], np.zeros(64, np.uint8))
+
+
 def test_async_level_fetch_matches_sync(golden, all_cases):
     """levels fetched on the copy stream while later rounds run equal the synchronously fetched ones"""
     for name in ("mutated_200x5k", "u16_rand", "reads_2000x150"):
