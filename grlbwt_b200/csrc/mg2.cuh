@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(256) mg2_codes_kernel(const u32* __restrict__ 
     const u32 g = head_pref[i >> 5] + __popc(hw & (0xffffffffu >> (31 - (i & 31)))) - 1;
     const u32 gi = ginfo[g];
     const u64 rep = (hw >> (i & 31)) & 1u;
-    codes[order[i]] = (CodeT)((gi & 1u) ? ((((u64)(gi >> 2) + rank_base) << 2) | (u64)(gi & 2u) | rep) + 1ULL : 0ULL);
+    if (gi & 1u) codes[order[i]] = (CodeT)(((((u64)(gi >> 2) + rank_base) << 2) | (u64)(gi & 2u) | rep) + 1ULL);  // (zero-initialised: unranked groups cost no scattered write)
 }
 template <class CodeT>
 __global__ void __launch_bounds__(256) mg2_codes_to_entries_kernel(const u32* __restrict__ vals, const u32* __restrict__ pos, const CodeT* __restrict__ back, u64 nS,
@@ -667,6 +667,7 @@ void mg2_rank(grlgpu_ctx* c, Comm& cm, Mg2Part& P, Mg2Slices& S) {
         const bool narrow_code = S.tot < (1ull << 29);  // ((rank << 2) | flags) + 1 fits 32 bits
         const u64 cb = narrow_code ? 4 : 8;
         DevBuf<u8> codes(nL * cb, st), back(nS * cb, st);
+        codes.zero();
         if (nL) {
             if (narrow_code) GRL_LAUNCH("mg_codes", nL * 20, (mg2_codes_kernel<u32>), grid_for(nL, 256), 256, 0, st, order.p, head_bits.p, head_pref.p, ginfo.p, nL, S.rank_base, (u32*)codes.p);
             else GRL_LAUNCH("mg_codes", nL * 24, (mg2_codes_kernel<u64>), grid_for(nL, 256), 256, 0, st, order.p, head_bits.p, head_pref.p, ginfo.p, nL, S.rank_base, (u64*)codes.p);
