@@ -130,16 +130,18 @@ def run_reference(args, rank):
 
 # ---------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+    """nvidia-smi polling the job's GPUs every 100 ms from ONE process (rank 0). It is started before the warm-up steps, so that its
+    start-up (NVML initialisation takes driver-wide locks) stays outside the timed region; only the rows between mark() and stop() count."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, indices):
+        self.rows, self.proc, self.indices, self.first = [], None, list(indices), 0
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", ",".join(str(i) for i in self.indices), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -148,6 +150,9 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.rows.append([x.strip() for x in ln.split(",")])
 
+    def mark(self):
+        self.first = len(self.rows)
+
     def stop(self):
         if self.proc:
             self.proc.terminate()
@@ -155,18 +160,19 @@ class ClockSampler:
                 self.proc.wait(timeout=5)
             except Exception:
                 self.proc.kill()
+        rows = self.rows[self.first:] or self.rows[-len(self.indices):]   # a region shorter than one polling period: the latest sample
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                sm.append(float(r[1])); mx.append(float(r[2]))
             except Exception:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "gpus": self.indices}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm), "gpus": self.indices}
 
 
 # ---------------------------------------------------------------- our arm
@@ -368,6 +374,9 @@ def run_ours(args, rank, world, local_rank):
         run_phase(False, collect, digest, slices)
 
     # ---- value: text resident in HBM ----
+    sampler = ClockSampler(range(world)) if rank == 0 else None   # one nvidia-smi for all the job's GPUs, started ahead of the timed region
+    if sampler is not None:
+        sampler.start()
     for _ in range(args.warmup):
         step_resident()
     rounds_info, digest, slice_sizes = [], [], []
@@ -377,9 +386,9 @@ def run_ours(args, rank, world, local_rank):
     prof = ctx.profile()
     ctx.profile_enable(False); ctx.profile_reset()
 
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    if sampler is not None:
+        sampler.mark()
     ci0 = comm.info() if comm is not None else None
     l0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -398,7 +407,7 @@ def run_ours(args, rank, world, local_rank):
                              "bulk_exchanges": (ci1["bulk_collectives"] - ci0["bulk_collectives"]) // args.steps,
                              "small_gathers": (ci1["small_collectives"] - ci0["small_collectives"]) // args.steps, "backend": ci1["kind"],
                              "note": "host wall time of rank 0 inside the exchanges, from 'my data is ready' to 'all of it has arrived' (includes waiting for peers)"}
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler is not None else None
     ms_total = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
