@@ -459,7 +459,7 @@ def run_ours(args, rank, world, local_rank):
                "what": "every rank copies its shard from pinned host memory to its GPU and copies its part of every level (rules, hocc marks, "
                        "preliminary BWT) and of the final parse back to pinned host memory; bytes are summed over the ranks",
                "timing": "host wall clock between stream synchronisations, max over ranks",
-               "last_step_parts_ms": {k: (v if isinstance(v, list) else round(v, 1)) for k, v in e2e_parts.items()}}
+               "last_step_parts_ms": {k: (list(v) if isinstance(v, list) else round(v, 1)) for k, v in e2e_parts.items()}}
         del host_text
 
     # ---- same sample as the reference arm / cpu_baseline (numpy generator, host buffers), 1 GPU only ----

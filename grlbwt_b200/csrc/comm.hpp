@@ -202,14 +202,28 @@ struct IpcComm : Comm {
             throw;
         }
         if (rank == 0) shm_unlink(name.c_str());  // everyone has it mapped: the name can go, the memory lives until the last unmap
+        // a first small window right away: a box where CUDA IPC does not work between these processes fails HERE, on every rank
+        // together, where the caller can still choose another backend
+        try {
+            regrow(16u << 20);
+        } catch (...) {
+            abort_group();
+            release();
+            throw;
+        }
+    }
+    void release() {
+        for (auto& p : peer_win) if (p) { cudaIpcCloseMemHandle(p); p = nullptr; }
+        if (window) { cudaFree(window); window = nullptr; }
+        for (auto& s : pull_st) if (s) { cudaStreamDestroy(s); s = nullptr; }
+        if (map) { munmap(map, map_bytes); map = nullptr; hdr = nullptr; }
+        cudaGetLastError();
     }
     ~IpcComm() override {
         // peers must have closed their mappings of my window before it is freed: one last (short, best-effort) barrier in between
         for (auto& p : peer_win) if (p) { cudaIpcCloseMemHandle(p); p = nullptr; }
         if (hdr && !hdr->failed.load()) { timeout_s = std::min(timeout_s, 10.0); try { barrier(); } catch (...) {} }
-        if (window) cudaFree(window);
-        for (auto& s : pull_st) if (s) cudaStreamDestroy(s);
-        if (map) munmap(map, map_bytes);
+        release();
     }
     const char* kind() const override { return "CUDA IPC windows pulled by copy-engine DMA over NVLink + shared-memory rendezvous"; }
     void fail(const std::string& why) {
@@ -280,6 +294,14 @@ struct IpcComm : Comm {
     }
     void all_to_all_soa(const SoaPart* parts, int n_parts, const u64* send_cnt, const u64* recv_cnt, cudaStream_t st) override {
         if (n_parts > MAX_PARTS) { Comm::all_to_all_soa(parts, n_parts, send_cnt, recv_cnt, st); return; }
+        try {
+            exchange(parts, n_parts, send_cnt, recv_cnt, st);
+        } catch (...) {
+            abort_group();  // (a CUDA error on this rank must not leave the peers in a barrier)
+            throw;
+        }
+    }
+    void exchange(const SoaPart* parts, int n_parts, const u64* send_cnt, const u64* recv_cnt, cudaStream_t st) {
         n_bulk++;
         std::vector<u64> s_el((size_t)world + 1, 0), r_el((size_t)world + 1, 0);
         for (int p = 0; p < world; p++) { s_el[(size_t)p + 1] = s_el[(size_t)p] + send_cnt[p]; r_el[(size_t)p + 1] = r_el[(size_t)p] + recv_cnt[p]; }

@@ -92,21 +92,49 @@ def comm_from_torch(dist, rank: int, world: int, device_index: int, torch, kind:
     kind = os.environ.get("GRLBWT_COMM", kind)
     if kind == "local":
         kind = "ipc"
-    if kind == "auto":
+    if kind not in ("auto", "ipc", "nccl"):
+        raise ValueError(f"unknown exchange backend {kind!r}")
+    auto = kind == "auto"
+    if auto:
         one_box = int(os.environ.get("LOCAL_WORLD_SIZE", "0")) == world
         kind = "ipc" if one_box and can_peer_all(range(world)) else "nccl"
     if kind == "nccl":
         return nccl_comm_from_torch(dist, rank, world, device_index, torch)
-    if kind != "ipc":
-        raise ValueError(f"unknown exchange backend {kind!r}")
     dev = torch.device("cuda", device_index) if dist.get_backend() == "nccl" else torch.device("cpu")
     t = torch.zeros(64, dtype=torch.uint8, device=dev)
-    if rank == 0:
+    if rank == 0 and _shm_usable():   # (an all-zero name tells every rank that rank 0 cannot create the segment)
         name = f"/grlgpu-{os.getpid()}-{int.from_bytes(os.urandom(6), 'little'):x}".encode()
         t[: len(name)] = torch.frombuffer(bytearray(name), dtype=torch.uint8).to(dev)
     dist.broadcast(t, src=0)
     session = bytes(t.cpu().numpy()).rstrip(b"\0").decode()
-    return ipc_comm(session, rank, world, device_index)
+    comm, err = None, None
+    if session:
+        try:
+            comm = ipc_comm(session, rank, world, device_index)
+        except GrlGpuError as e:   # CUDA IPC or the segment is not usable here: the constructor fails on every rank together
+            err = e
+    else:
+        err = GrlGpuError(-5, "POSIX shared memory is not usable on this box")
+    ok = torch.tensor([1 if comm is not None else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) == 1:
+        return comm
+    if comm is not None:
+        comm.close()
+    if not auto:
+        raise err if err is not None else GrlGpuError(-5, "the IPC backend failed on another rank")
+    return nccl_comm_from_torch(dist, rank, world, device_index, torch)
+
+
+def _shm_usable() -> bool:
+    try:
+        path = f"/dev/shm/grlgpu-probe-{os.getpid()}"
+        fd = os.open(path, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+        os.close(fd)
+        os.unlink(path)
+        return True
+    except OSError:
+        return False
 
 
 def shard_bounds(text: np.ndarray, n_ranks: int):
