@@ -20,4 +20,9 @@ sanitize:
 	compute-sanitizer --tool synccheck --error-exitcode 9 --log-file $(SAN_OUT)/sanitize_synccheck.log $(PY) tests/sanitize_driver.py $(SAN_ARGS)
 	tail -n 3 $(SAN_OUT)/sanitize_memcheck.log $(SAN_OUT)/sanitize_racecheck.log $(SAN_OUT)/sanitize_synccheck.log
 
-.PHONY: all test-cpu test-gpu sanitize
+# memcheck over the multi-rank rounds and the packed output only (seconds; profiles/r02_sanitize_memcheck_quick_final.log)
+sanitize-quick:
+	mkdir -p $(SAN_OUT)
+	GRLGPU_NO_POOL=1 compute-sanitizer --tool memcheck --error-exitcode 9 --log-file $(SAN_OUT)/sanitize_memcheck_quick.log $(PY) tests/sanitize_driver.py --quick
+
+.PHONY: all test-cpu test-gpu sanitize sanitize-quick

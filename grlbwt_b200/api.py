@@ -108,6 +108,7 @@ def lib_gpu():
         L.grlgpu_selftest_scan.argtypes = [vp, u64, vp, vp]
         L.grlgpu_selftest_sort.argtypes = [vp, vp, u64, C.c_int]
         L.grlgpu_selftest_compact.argtypes = [vp, vp, u64, vp, vp]
+        L.grlgpu_selftest_ipc_rendezvous.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int]
         _gpu = L
     return _gpu
 

@@ -153,11 +153,12 @@ struct IpcComm : Comm {
     cudaStream_t pull_st[N_PULL_STREAMS] = {};
     double timeout_s = 300.0;
 
-    IpcComm(const char* session, int r, int w, int dev_) : name(session), peer_win((size_t)w, nullptr) {
+    bool use_cuda = true;  // false: the rendezvous only (barriers + small gathers), no device windows -- the CPU self-test of the segment code
+    IpcComm(const char* session, int r, int w, int dev_, bool with_cuda = true) : name(session), peer_win((size_t)w, nullptr), use_cuda(with_cuda) {
         rank = r; world = w; device = dev_;
         if (w > MAX_RANKS) throw Error(-2, "at most 32 ranks");
         if (const char* e = getenv("GRLGPU_IPC_TIMEOUT_S")) timeout_s = std::max(1.0, atof(e));
-        GRL_CUDA(cudaSetDevice(device));
+        if (use_cuda) GRL_CUDA(cudaSetDevice(device));
         map_bytes = shm_bytes(w);
         const auto t0 = std::chrono::steady_clock::now();
         auto waited = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
@@ -194,7 +195,8 @@ struct IpcComm : Comm {
             }
             if (hdr->world != (u32)world) throw Error(-2, "ranks disagree on the world size");
         }
-        for (auto& s : pull_st) GRL_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        if (use_cuda)
+            for (auto& s : pull_st) GRL_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
         try {
             barrier();
         } catch (...) {
@@ -204,6 +206,7 @@ struct IpcComm : Comm {
         if (rank == 0) shm_unlink(name.c_str());  // everyone has it mapped: the name can go, the memory lives until the last unmap
         // a first small window right away: a box where CUDA IPC does not work between these processes fails HERE, on every rank
         // together, where the caller can still choose another backend
+        if (!use_cuda) return;
         try {
             regrow(16u << 20);
         } catch (...) {
@@ -217,7 +220,7 @@ struct IpcComm : Comm {
         if (window) { cudaFree(window); window = nullptr; }
         for (auto& s : pull_st) if (s) { cudaStreamDestroy(s); s = nullptr; }
         if (map) { munmap(map, map_bytes); map = nullptr; hdr = nullptr; }
-        cudaGetLastError();
+        if (use_cuda) cudaGetLastError();
     }
     ~IpcComm() override {
         // peers must have closed their mappings of my window before it is freed: one last (short, best-effort) barrier in between
@@ -302,6 +305,7 @@ struct IpcComm : Comm {
         }
     }
     void exchange(const SoaPart* parts, int n_parts, const u64* send_cnt, const u64* recv_cnt, cudaStream_t st) {
+        if (!use_cuda) throw Error(-1, "this communicator was created without device windows");
         n_bulk++;
         std::vector<u64> s_el((size_t)world + 1, 0), r_el((size_t)world + 1, 0);
         for (int p = 0; p < world; p++) { s_el[(size_t)p + 1] = s_el[(size_t)p] + send_cnt[p]; r_el[(size_t)p + 1] = r_el[(size_t)p] + recv_cnt[p]; }

@@ -1301,6 +1301,24 @@ int grlgpu_comm_create_ipc(grlgpu_comm** comm, const char* session, int rank, in
         *comm = h.release();
     });
 }
+// CPU self-test of the shared-memory rendezvous (no GPU involved): `rounds` barriers and small all-gathers of payloads of varying size
+// between `world` processes; returns GRLGPU_OK when every gathered byte is what its rank wrote
+int grlgpu_selftest_ipc_rendezvous(const char* session, int rank, int world, int rounds) {
+    if (!session || session[0] != '/' || world < 1 || world > 31 || rank < 0 || rank >= world || rounds < 1) return GRLGPU_ERR_ARG;
+    return guarded(nullptr, [&] {
+        IpcComm cm(session, rank, world, 0, /*with_cuda=*/false);
+        for (int r = 0; r < rounds; r++) {
+            const size_t n = (size_t)1 + ((size_t)r * 7919u) % 100000u;  // up to ~800 KB per rank: several 64 KB pieces
+            std::vector<u64> mine(n), all(n * (size_t)world);
+            for (size_t i = 0; i < n; i++) mine[i] = ((u64)rank << 48) ^ ((u64)r << 24) ^ (u64)i;
+            cm.all_gather_host(mine.data(), n * sizeof(u64), all.data(), nullptr);
+            for (int p = 0; p < world; p++)
+                for (size_t i = 0; i < n; i++)
+                    if (all[(size_t)p * n + i] != (((u64)p << 48) ^ ((u64)r << 24) ^ (u64)i)) { cm.abort_group(); throw Error(GRLGPU_ERR_STATE, "rendezvous self-test: wrong byte gathered"); }
+            cm.barrier();
+        }
+    });
+}
 int grlgpu_local_group_create(grlgpu_local_group** group, int world) {
     if (!group || world < 1 || world > 31) return GRLGPU_ERR_ARG;
     *group = new grlgpu_local_group(world);

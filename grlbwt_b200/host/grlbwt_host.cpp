@@ -216,6 +216,21 @@ int grlbwt_selftest_write(const char* path, const uint64_t* syms, const uint64_t
     }
 }
 
+// the in-memory packer grlbwt_build_packed uses when the induction ran on the host (CPU-only self test)
+int grlbwt_selftest_pack(void* out_image, uint64_t cap_bytes, const uint64_t* syms, const uint64_t* lens, uint64_t n_runs, uint64_t sb, uint64_t fb, int narrow) {
+    try {
+        if (!out_image || sb == 0 || sb > 8 || fb == 0 || fb > 8 || cap_bytes < 16 + n_runs * (sb + fb)) throw std::runtime_error("bad arguments");
+        if (narrow) {
+            std::vector<uint32_t> s32(syms, syms + n_runs), l32(lens, lens + n_runs);
+            grlbwt::pack_rl_bwt((unsigned char*)out_image, s32.data(), l32.data(), n_runs, sb, fb);
+        } else grlbwt::pack_rl_bwt((unsigned char*)out_image, syms, lens, n_runs, sb, fb);
+        return 0;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return -100;
+    }
+}
+
 const char* grlbwt_last_error(void) { return g_last_error.c_str(); }
 
 // the shard boundaries a multi-GPU run would use (CPU-only self test of gpu_par_phase.hpp: shard_bounds)

@@ -72,6 +72,9 @@ int grlbwt_selftest_shard_bounds(const void* text, uint64_t n_syms, int sym_byte
 /* self test of the .rl_bwt writer alone (no device; format of include/bwt_io.h:377-382,448-490): runs given as u64
  * symbols / lengths; narrow != 0 routes through the 32-bit-symbol instantiation the multi-threaded host uses */
 int grlbwt_selftest_write(const char* path, const uint64_t* syms, const uint64_t* lens, uint64_t n_runs, uint64_t sb, uint64_t fb, int narrow);
+/* the same records packed into memory ([sb][fb] + records: the image grlbwt_build_packed returns); narrow != 0 packs from 32-bit
+ * symbols and lengths */
+int grlbwt_selftest_pack(void* out_image, uint64_t cap_bytes, const uint64_t* syms, const uint64_t* lens, uint64_t n_runs, uint64_t sb, uint64_t fb, int narrow);
 
 #ifdef __cplusplus
 }

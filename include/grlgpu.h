@@ -264,6 +264,9 @@ int grlgpu_profile_entry(grlgpu_ctx* ctx, int index, char* name, int name_cap, u
 int grlgpu_selftest_scan(const uint32_t* in, uint64_t n, uint64_t* out_exclusive, uint64_t* total);
 int grlgpu_selftest_sort(uint64_t* keys, uint32_t* vals, uint64_t n, int n_bits);
 int grlgpu_selftest_compact(const uint32_t* bits, const uint32_t* prev_bits, uint64_t n_bits, uint64_t* out, uint64_t* count);
+/* the shared-memory rendezvous of the "ipc" backend WITHOUT its device windows (runs on a box without a GPU): `rounds` barriers and small
+ * all-gathers of varying size between `world` processes that all pass the same `session`; GRLGPU_OK when every byte arrived intact */
+int grlgpu_selftest_ipc_rendezvous(const char* session, int rank, int world, int rounds);
 
 #ifdef __cplusplus
 }

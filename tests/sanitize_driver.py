@@ -37,6 +37,25 @@ def main():
              "u32_small_sigma", "u64_rand", "long_phrases", "reads_300x150", "empty_runs"]
     variants = [0, G.FLAG_SMALL_TABLE | G.FLAG_FORCE_SLOW_SCAN, G.FLAG_FORCE_UNCACHED, G.FLAG_SMALL_PILOT, G.FLAG_FORCE_DOUBLING]
     n = 0
+    if "--quick" in sys.argv:  # only what the full runs in profiles/ predate: multi-rank rounds (records in source order, rule records) + the packed output
+        from grlbwt_b200 import mg
+        for name in ("dna_500", "u16_small_sigma"):
+            mg.check_against_oracle(cases[name], n_ranks=3)
+            n += 1
+        for name in ("dna_500", "u16_small_sigma", "reads_300x150", "with_empty"):
+            arr = cases[name]
+            o = O.Oracle(arr)
+            o.par_phase()
+            osyms, olens, osb, ofb = o.ind_phase()
+            img = np.zeros(16 + arr.size * 16, np.uint8)
+            for devs in ([0], [0, 0]):
+                nb, n_runs, sb, fb, info = G.build_bwt_packed(arr, img, devices=devs, n_threads=2)
+                assert (sb, fb) == (osb, ofb) and n_runs == osyms.size, (name, devs, info)
+                assert img[:nb].tobytes() == O.rl_bwt_bytes(osyms, olens, osb, ofb), (name, devs)
+                n += 1
+            o.close()
+        print(f"sanitize driver ok (quick): {n} runs")
+        return
     for name in names:
         for fl in variants:
             run_case(name, cases[name], fl)

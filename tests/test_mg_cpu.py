@@ -97,3 +97,44 @@ def test_gloo_world_size_2_plumbing(tmp_path):
                         str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, (r.stdout + r.stderr)[-1500:]
     assert r.stdout.count("WORKER_OK") == 2
+
+
+RENDEZVOUS_WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["GRL_ROOT"])
+from grlbwt_b200.api import lib_gpu
+L = lib_gpu()
+rc = L.grlgpu_selftest_ipc_rendezvous(os.environ["GRL_SESSION"].encode(), int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]))
+if rc != 0:
+    print("ERR", rc, L.grlgpu_last_error(None).decode())
+sys.exit(0 if rc == 0 else 3)
+'''
+
+
+def _run_rendezvous(tmp_path, world, rounds, session, extra_env=None, skip_rank=None, timeout=120):
+    script = tmp_path / "rv.py"
+    script.write_text(RENDEZVOUS_WORKER)
+    env = dict(os.environ, GRL_ROOT=ROOT, GRL_SESSION=session, **(extra_env or {}))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), str(world), str(rounds)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(world) if r != skip_rank]
+    return [(p.wait(timeout=timeout), p.stdout.read()) for p in procs]
+
+
+def test_ipc_rendezvous_between_processes(tmp_path):
+    """the "ipc" exchange backend's shared-memory segment (barriers + small all-gathers in 64 KB pieces) between 5 processes, no GPU"""
+    session = f"/grlgpu-test-{os.getpid()}-a"
+    res = _run_rendezvous(tmp_path, 5, 40, session)
+    assert all(rc == 0 for rc, _ in res), res
+    assert not os.path.exists("/dev/shm" + session)   # rank 0 unlinks the name once everyone is attached
+
+
+def test_ipc_rendezvous_times_out_when_a_rank_is_missing(tmp_path):
+    """a rank that never arrives: the others give up after GRLGPU_IPC_TIMEOUT_S instead of hanging, and report it"""
+    session = f"/grlgpu-test-{os.getpid()}-b"
+    res = _run_rendezvous(tmp_path, 3, 4, session, extra_env={"GRLGPU_IPC_TIMEOUT_S": "2"}, skip_rank=2)
+    assert all(rc == 3 for rc, _ in res), res
+    assert any("timed out" in out or "aborted" in out for _, out in res), res
+    try:
+        os.unlink("/dev/shm" + session)   # rank 0 could not unlink it: not everyone attached
+    except OSError:
+        pass

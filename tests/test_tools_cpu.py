@@ -116,3 +116,14 @@ def test_rl_bwt_writer_matches_the_format(tmp_path, sb, fb):
             rc = L.grlbwt_selftest_write(str(path).encode(), syms.ctypes.data, lens.ctypes.data, n, sb, fb, narrow)
             assert rc == 0
             assert path.read_bytes() == O.rl_bwt_bytes(syms, lens, sb, fb), (n, narrow)
+    # the in-memory packer of grlbwt_build_packed (host induction) produces the same image
+    L.grlbwt_selftest_pack.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int]
+    for n in (0, 1, 100003):
+        syms = rng.integers(0, 1 << min(8 * sb, 32), size=n, dtype=np.uint64)
+        lens = rng.integers(1, 1 << min(8 * fb, 32), size=n, dtype=np.uint64)
+        img = np.full(16 + n * (sb + fb) + 8, 0xAB, np.uint8)
+        for narrow in (0, 1):
+            assert L.grlbwt_selftest_pack(img.ctypes.data, img.size - 8, syms.ctypes.data, lens.ctypes.data, n, sb, fb, narrow) == 0
+            assert img[:-8].tobytes() == O.rl_bwt_bytes(syms, lens, sb, fb), (n, narrow)
+            assert (img[-8:] == 0xAB).all()   # nothing written past the image
+        assert L.grlbwt_selftest_pack(img.ctypes.data, 15, syms.ctypes.data, lens.ctypes.data, n, sb, fb, 0) != 0
