@@ -1,5 +1,6 @@
-"""CPU suite: the .rl_bwt consumer tools (grl2plain, grlbwt2rle, reverse_bwt, bwt_stats) -- SURVEY.md 8(f)-4.
-Round trip text -> BWT (oracle) -> .rl_bwt -> reverse_bwt == text."""
+"""CPU suite: the .rl_bwt consumer tools (grl2plain, grlbwt2rle, reverse_bwt, bwt_stats, split_runs) -- SURVEY.md 8(f)-4.
+Round trip text -> BWT (oracle) -> .rl_bwt -> reverse_bwt == text; parity with the reference's own scripts where they build
+without SDSL (oracle/_ref/*_ref, compiled from /root/reference/scripts by oracle/Makefile)."""
 import os
 import subprocess
 
@@ -89,13 +90,14 @@ def test_truncated_rl_bwt_is_rejected(tmp_path, all_cases):
     arr.tofile(txt)
     rl.write_bytes(raw[:-1])
     for cmd in ([tool("reverse_bwt"), str(rl), str(tmp_path / "o")], [tool("grl2plain"), str(rl), str(tmp_path / "o")],
-                [tool("bwt_check"), str(txt), str(rl)], [tool("bwt_stats"), str(rl)], [tool("grlbwt2rle"), str(rl), str(tmp_path / "p")]):
+                [tool("bwt_check"), str(txt), str(rl)], [tool("bwt_stats"), str(rl)], [tool("grlbwt2rle"), str(rl), str(tmp_path / "p")],
+                [tool("split_runs"), str(rl), "4", "100", str(tmp_path / "s")]):
         r = subprocess.run(cmd, capture_output=True, text=True)
         assert r.returncode == 1 and "truncated" in r.stderr, (cmd[0], r.returncode, r.stderr[-200:])
 
 
 def test_tools_usage_messages():
-    for t in ("grl2plain", "grlbwt2rle", "reverse_bwt", "bwt_stats", "bwt_check"):
+    for t in ("grl2plain", "grlbwt2rle", "reverse_bwt", "bwt_stats", "bwt_check", "split_runs"):
         r = subprocess.run([tool(t)], capture_output=True, text=True)
         assert r.returncode == 0 and "usage:" in r.stdout
 
@@ -127,3 +129,84 @@ def test_rl_bwt_writer_matches_the_format(tmp_path, sb, fb):
             assert img[:-8].tobytes() == O.rl_bwt_bytes(syms, lens, sb, fb), (n, narrow)
             assert (img[-8:] == 0xAB).all()   # nothing written past the image
         assert L.grlbwt_selftest_pack(img.ctypes.data, 15, syms.ctypes.data, lens.ctypes.data, n, sb, fb, 0) != 0
+
+
+# ---------------------------------------------------------------- parity with the reference's scripts
+REF_DIR = os.path.join(G.ROOT if hasattr(G, "ROOT") else os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+
+
+def ref_tool(name):
+    path = os.path.join(REF_DIR, name + "_ref")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not built (needs /root/reference at build time)")
+    return path
+
+
+def _bwt_file(all_cases, tmp_path, name):
+    arr = all_cases[name]
+    o = O.Oracle(arr)
+    o.par_phase()
+    syms, lens, sb, fb = o.ind_phase()
+    o.close()
+    rl = tmp_path / f"{name}.rl_bwt"
+    rl.write_bytes(O.rl_bwt_bytes(syms, lens, sb, fb))
+    return rl, syms, lens, sb, fb
+
+
+def _records(raw):
+    sb, fb = int.from_bytes(raw[:8], "little"), int.from_bytes(raw[8:16], "little")
+    rec = np.frombuffer(raw[16:], np.uint8).reshape(-1, sb + fb)
+    sym = sum(rec[:, i].astype(np.uint64) << np.uint64(8 * i) for i in range(sb))
+    ln = sum(rec[:, sb + i].astype(np.uint64) << np.uint64(8 * i) for i in range(fb))
+    return sb, fb, np.asarray(sym, np.uint64), np.asarray(ln, np.uint64)
+
+
+@pytest.mark.parametrize("name", ["rep_50x200k", "mixed_reads", "homopolymers_multi", "test_byte_alphabet"])
+def test_tools_match_the_reference_scripts(all_cases, tmp_path, name):
+    """grl2plain and grlbwt2rle: the same bytes as scripts/grl2plain.cpp / grlbwt2rle.cpp; bwt_stats: the same report"""
+    rl, syms, lens, sb, fb = _bwt_file(all_cases, tmp_path, name)
+    for ours, theirs, outs in (("grl2plain", "grl2plain", ["{}"]), ("grlbwt2rle", "grlbwt2rle", ["{}.syms", "{}.len"])):
+        a, b = tmp_path / ("ref_" + ours), tmp_path / ("our_" + ours)
+        r1 = subprocess.run([ref_tool(theirs), str(rl), str(a)], capture_output=True, text=True)
+        r2 = subprocess.run([tool(ours), str(rl), str(b)], capture_output=True, text=True)
+        assert r1.returncode == 0 and r2.returncode == 0, (r1.stderr, r2.stderr)
+        for o_ in outs:
+            assert open(o_.format(a), "rb").read() == open(o_.format(b), "rb").read(), (ours, o_)
+    if len(syms) >= 20:   # (the reference reads one past its sorted lengths when there are fewer than 10 runs)
+        r1 = subprocess.run([ref_tool("bwt_stats"), str(rl)], capture_output=True, text=True)
+        r2 = subprocess.run([tool("bwt_stats"), str(rl)], capture_output=True, text=True)
+        want = r1.stdout.splitlines()
+        assert r2.stdout.splitlines()[: len(want)] == want
+
+
+@pytest.mark.parametrize("name", ["rep_50x200k", "homopolymers_multi", "mixed_reads"])
+def test_split_runs(all_cases, tmp_path, name):
+    """split_runs: no run longer than 2^bits - 1, no run across a multiple of n, the same BWT; the reference's output minus the
+    zero-length records it emits when a run ends exactly on a block boundary is the same byte stream"""
+    rl, syms, lens, sb, fb = _bwt_file(all_cases, tmp_path, name)
+    n_syms = int(lens.sum())
+    for bits, n in ((3, 1000), (2, 64), (8, 4096), (5, 999983), (12, 0), (4, n_syms + 1)):
+        out = tmp_path / f"s_{bits}_{n}"
+        r = subprocess.run([tool("split_runs"), str(rl), str(bits), str(n), str(out)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        osb, ofb, s2, l2 = _records(out.read_bytes())
+        assert (osb, ofb) == (sb, (bits + 7) // 8)
+        assert l2.min() >= 1 and l2.max() <= (1 << bits) - 1
+        assert np.array_equal(np.repeat(s2, l2.astype(np.int64)), np.repeat(syms, lens.astype(np.int64)))
+        ends = np.cumsum(l2)
+        starts = ends - l2
+        if n:
+            assert ((starts // np.uint64(n)) == ((ends - np.uint64(1)) // np.uint64(n))).all()   # no run crosses a block boundary
+            per_block = np.bincount((starts // np.uint64(n)).astype(np.int64))
+            dist = np.loadtxt(str(out) + ".dist", skiprows=1, ndmin=2)
+            assert dist[:, 1].sum() == per_block.size == -(-n_syms // n)
+            assert np.array_equal(np.bincount(per_block, minlength=dist.shape[0])[: dist.shape[0]], dist[:, 1].astype(np.int64))
+        if n and n >= 64:   # the reference: asserts (or worse) on tiny blocks and on n = 0
+            ref_out = tmp_path / f"r_{bits}_{n}"
+            rr = subprocess.run([ref_tool("split_runs"), str(rl), str(bits), str(n), str(ref_out)], capture_output=True, text=True)
+            if rr.returncode == 0 and ref_out.exists():
+                rsb, rfb, s3, l3 = _records(ref_out.read_bytes())
+                keep = l3 > 0
+                assert (rsb, rfb) == (osb, ofb) and np.array_equal(s3[keep], s2) and np.array_equal(l3[keep], l2), (bits, n)
+                if keep.all():   # no zero-length records: the distribution files agree too
+                    assert open(str(ref_out) + ".dist").read() == open(str(out) + ".dist").read(), (bits, n)
