@@ -190,10 +190,10 @@ struct IpcComm : Comm {
             hdr->magic.store(MAGIC, std::memory_order_release);
         } else {
             while (hdr->magic.load(std::memory_order_acquire) != MAGIC) {
-                if (waited() > timeout_s) throw Error(-5, "the rendezvous segment was never initialised");
+                if (waited() > timeout_s) { release(); throw Error(-5, "the rendezvous segment was never initialised"); }
                 usleep(200);
             }
-            if (hdr->world != (u32)world) throw Error(-2, "ranks disagree on the world size");
+            if (hdr->world != (u32)world) { release(); throw Error(-2, "ranks disagree on the world size"); }
         }
         if (use_cuda)
             for (auto& s : pull_st) GRL_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
@@ -201,6 +201,7 @@ struct IpcComm : Comm {
             barrier();
         } catch (...) {
             if (rank == 0) shm_unlink(name.c_str());
+            release();
             throw;
         }
         if (rank == 0) shm_unlink(name.c_str());  // everyone has it mapped: the name can go, the memory lives until the last unmap
