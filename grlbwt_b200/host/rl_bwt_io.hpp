@@ -34,7 +34,13 @@ inline void pack_rl_bwt(unsigned char* dst, const SymT* sym, const LenT* len, ui
     const uint64_t hdr[2] = {sb, fb};
     memcpy(dst, hdr, 16);
     unsigned char* p = dst + 16;
-    for (uint64_t i = 0; i < n_runs; i++, p += sb + fb) {
+    const uint64_t rec = sb + fb, tail = n_runs < 4 ? n_runs : 4;  // the two 8-byte stores of a record reach 8 - fb <= 7 bytes (< 4 records) past its end
+    for (uint64_t i = 0; i + tail < n_runs; i++, p += rec) {
+        const uint64_t s64 = (uint64_t)sym[i], l64 = (uint64_t)len[i];
+        memcpy(p, &s64, 8);
+        memcpy(p + sb, &l64, 8);
+    }
+    for (uint64_t i = n_runs - tail; i < n_runs; i++, p += rec) {  // the last records byte-exact: nothing is written past the image
         const uint64_t s64 = (uint64_t)sym[i], l64 = (uint64_t)len[i];
         memcpy(p, &s64, sb);
         memcpy(p + sb, &l64, fb);
