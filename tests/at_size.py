@@ -169,6 +169,8 @@ def main():
             entry["cli_rc"] = r.returncode
             entry["MBps_file_to_file"] = round(entry["bytes"] / 1e6 / dt, 1)
             entry["cli_tail"] = (r.stdout + r.stderr)[-1500:]
+            timing = [ln for ln in r.stdout.splitlines() if ln.startswith("Timing (ms):")]
+            entry["cli_timing"] = timing[-1] if timing else None   # text to device / parse phase / induction / writing, as the tool reports them
             if r.returncode == 0:
                 entry["rl_bwt_bytes"] = os.path.getsize(out)
                 with open(out, "rb") as f:
