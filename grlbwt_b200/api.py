@@ -393,6 +393,28 @@ def build_bwt_packed(text: np.ndarray, out_image: np.ndarray, devices=(0,), n_th
     return int(nb.value), int(res.n_runs), int(res.sb), int(res.fb), info
 
 
+def parse_rl_bwt(image) -> tuple:
+    """The .rl_bwt format (reference include/bwt_io.h:377-382,448-490) as numpy arrays: `image` is a file path or the bytes /
+    uint8 array of a file image (what build_bwt_packed fills). -> (syms uint64[r], lens uint64[r], sb, fb). Host-side helper."""
+    raw = np.fromfile(image, np.uint8) if isinstance(image, (str, os.PathLike)) else np.frombuffer(image, np.uint8)
+    if raw.size < 16:
+        raise ValueError("truncated header")
+    sb, fb = (int(x) for x in raw[:16].view(np.uint64))
+    if not (1 <= sb <= 8 and 1 <= fb <= 8):
+        raise ValueError(f"bad header widths sb={sb} fb={fb}")
+    body = raw[16:]
+    if body.size % (sb + fb):
+        raise ValueError("truncated record at the end of the image")
+    rec = body.reshape(-1, sb + fb)
+    syms = np.zeros(rec.shape[0], np.uint64)
+    lens = np.zeros(rec.shape[0], np.uint64)
+    for i in range(sb):
+        syms |= rec[:, i].astype(np.uint64) << np.uint64(8 * i)
+    for i in range(fb):
+        lens |= rec[:, sb + i].astype(np.uint64) << np.uint64(8 * i)
+    return syms, lens, sb, fb
+
+
 def build_bwt_file(inp: str, out: str, sym_bytes: int = 1, device: int = 0, n_threads: int = 1, verbose: bool = False):
     L = lib_host()
     rc = L.grlbwt_build_file(inp.encode(), out.encode(), sym_bytes, device, n_threads, int(verbose))

@@ -210,3 +210,23 @@ def test_split_runs(all_cases, tmp_path, name):
                 assert (rsb, rfb) == (osb, ofb) and np.array_equal(s3[keep], s2) and np.array_equal(l3[keep], l2), (bits, n)
                 if keep.all():   # no zero-length records: the distribution files agree too
                     assert open(str(ref_out) + ".dist").read() == open(str(out) + ".dist").read(), (bits, n)
+
+
+def test_parse_rl_bwt_helper(tmp_path):
+    """grlbwt_b200.parse_rl_bwt: file path, bytes and uint8 images; malformed images are errors"""
+    rng = np.random.default_rng(3)
+    for sb, fb in ((1, 1), (1, 4), (3, 4), (8, 8)):
+        syms = rng.integers(0, 1 << min(8 * sb, 63), size=1000, dtype=np.uint64)
+        lens = rng.integers(1, 1 << min(8 * fb, 63), size=1000, dtype=np.uint64)
+        raw = O.rl_bwt_bytes(syms, lens, sb, fb)
+        path = tmp_path / "p.rl_bwt"
+        path.write_bytes(raw)
+        for src in (str(path), raw, np.frombuffer(raw, np.uint8)):
+            s2, l2, sb2, fb2 = G.parse_rl_bwt(src)
+            assert (sb2, fb2) == (sb, fb) and np.array_equal(s2, syms) and np.array_equal(l2, lens)
+        with pytest.raises(ValueError):
+            G.parse_rl_bwt(raw[:-1])
+    with pytest.raises(ValueError):
+        G.parse_rl_bwt(b"\0" * 8)
+    with pytest.raises(ValueError):
+        G.parse_rl_bwt((9).to_bytes(8, "little") + (1).to_bytes(8, "little"))
